@@ -1,0 +1,223 @@
+"""Host-side mirror of the reference's only entry point, `run_markov_chain`
+(code/launcher.cpp:6-14), plus a step-wise `Chain` handle used by tests and bench.
+
+Same argument names, defaults and meaning as the Rcpp export; the returned dict has
+the eight fields of the reference's R list (code/launcher.cpp:57-63):
+total_cls, c_i, centers, sigmas, loglikelihood, final_ass, time, accepted.
+Errors of the reference (Rcpp::stop from validate_state, bad probabilities) surface
+as SmgError with the same message text.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as lb
+
+
+def _colmajor(data):
+    """R NumericMatrix layout: column-major float64 n x p."""
+    a = np.asarray(data, dtype=np.float64)
+    if a.ndim != 2:
+        raise ValueError("data must be an n x p matrix")
+    return np.asfortranarray(a)
+
+
+def run_markov_chain(data, attrisize, gamma, v, w, verbose=0, m=5, iterations=1000, L=1, c_i=None, burnin=5000, t=10,
+                     r=10, neal8=False, split_merge=True, n8_step_size=1, sam_step_size=1, thinning=1, seed=None,
+                     device=0):
+    lib = lb.load()
+    X = _colmajor(data)
+    n, p = X.shape
+    attr = lb.as_i32(attrisize)
+    vv, ww = lb.as_f64(v), lb.as_f64(w)
+    if attr.shape != (p,) or vv.shape != (p,) or ww.shape != (p,):
+        raise ValueError("attrisize, v and w must have length ncol(data)")
+    ci = None if c_i is None else lb.as_i32(c_i)
+    if ci is not None and ci.shape != (n,):
+        raise ValueError("c_i must have length nrow(data)")
+    if seed is None:
+        seed = int(np.random.SeedSequence().generate_state(2, dtype=np.uint32).astype(np.uint64) @ np.array(
+            [1, 1 << 32], dtype=np.uint64))
+    res = lb.SmgResults()
+    rc = lib.smg_run_markov_chain(X.ctypes.data_as(lb.c_dbl_p), n, p, lb.iptr(attr), float(gamma), lb.dptr(vv), lb.dptr(ww),
+                                  int(verbose), int(m), int(iterations), int(L), lb.iptr(ci), int(burnin), int(t),
+                                  int(r), int(bool(neal8)), int(bool(split_merge)), int(n8_step_size), int(sam_step_size),
+                                  int(thinning), C.c_ulonglong(int(seed) & (2**64 - 1)), int(device), C.byref(res))
+    lb.check(rc)
+    try:
+        it = res.iterations
+        total = np.ctypeslib.as_array(res.total_cls, shape=(max(it, 1),))[:it].copy()
+        c_all = np.ctypeslib.as_array(res.c_i, shape=(max(it, 1), n))[:it].copy()
+        off = np.ctypeslib.as_array(res.phi_offset, shape=(it + 1,)).copy()
+        nphi = int(off[-1])
+        cen = np.ctypeslib.as_array(res.centers, shape=(max(nphi, 1), p))[:nphi].copy()
+        sig = np.ctypeslib.as_array(res.sigmas, shape=(max(nphi, 1), p))[:nphi].copy()
+        out = {
+            "total_cls": [int(k) for k in total],
+            "c_i": [c_all[i] for i in range(it)],
+            "centers": [[cen[q] for q in range(off[i], off[i + 1])] for i in range(it)],
+            "sigmas": [[sig[q] for q in range(off[i], off[i + 1])] for i in range(it)],
+            "loglikelihood": np.ctypeslib.as_array(res.loglikelihood, shape=(max(it, 1),))[:it].copy(),
+            "final_ass": np.ctypeslib.as_array(res.final_ass, shape=(n,)).copy(),
+            "time": int(res.time),
+            "accepted": np.ctypeslib.as_array(res.accepted, shape=(max(it, 1),))[:it].copy(),
+            "seconds": float(res.seconds),
+        }
+    finally:
+        lib.smg_free_results(C.byref(res))
+    return out
+
+
+class Chain:
+    """One chain resident on one GPU (smg_create / smg_step / smg_snapshot / smg_destroy)."""
+
+    def __init__(self, data, attrisize, gamma, v, w, m=5, L=1, c_i=None, t=10, r=10, neal8=True, split_merge=True,
+                 n8_step_size=1, sam_step_size=1, thinning=1, seed=1, max_clusters=0, pool_size=0, device=0,
+                 compact_init=False, data_u8=False):
+        self.lib = lb.load()
+        self._attr = lb.as_i32(attrisize)
+        self._v, self._w = lb.as_f64(v), lb.as_f64(w)
+        if data_u8:
+            X = np.ascontiguousarray(data, dtype=np.uint8)
+        else:
+            X = _colmajor(data)
+        self.n, self.p = X.shape
+        self.m = int(m)
+        self.t, self.r = int(t), int(r)
+        cfg = lb.SmgConfig(self.n, self.p, lb.iptr(self._attr), float(gamma), lb.dptr(self._v), lb.dptr(self._w), int(m),
+                          int(L), int(t), int(r), int(bool(neal8)), int(bool(split_merge)), int(n8_step_size),
+                          int(sam_step_size), int(thinning), int(seed) & (2**64 - 1), int(max_clusters), int(pool_size),
+                          int(device), int(bool(compact_init)))
+        ci = None if c_i is None else lb.as_i32(c_i)
+        h = C.c_void_p()
+        if data_u8:
+            rc = self.lib.smg_create_u8(C.byref(cfg), X.ctypes.data_as(C.POINTER(C.c_ubyte)), lb.iptr(ci), C.byref(h))
+        else:
+            rc = self.lib.smg_create(C.byref(cfg), X.ctypes.data_as(lb.c_dbl_p), lb.iptr(ci), C.byref(h))
+        lb.check(rc)
+        self.h = h
+        self.kcap = 256
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, n_iters=1):
+        lb.check(self.lib.smg_step(self.h, int(n_iters)))
+
+    def snapshot(self, with_phi=True):
+        K = C.c_int()
+        ll = C.c_double()
+        acc = C.c_int()
+        c = np.empty(self.n, dtype=np.int32)
+        cen = np.empty((self.kcap, self.p)) if with_phi else None
+        sig = np.empty((self.kcap, self.p)) if with_phi else None
+        lb.check(self.lib.smg_snapshot(self.h, C.byref(K), lb.iptr(c), lb.dptr(cen), lb.dptr(sig), self.kcap, C.byref(ll),
+                                      C.byref(acc)))
+        k = K.value
+        return {"K": k, "c_i": c, "centers": None if cen is None else cen[:k].copy(),
+                "sigmas": None if sig is None else sig[:k].copy(), "loglikelihood": ll.value, "accepted": acc.value}
+
+    def stats(self):
+        out = np.zeros(8, dtype=np.uint64)
+        lb.check(self.lib.smg_get_stats(self.h, out.ctypes.data_as(lb.c_ull_p)))
+        keys = ["scan_rounds", "scan_events", "births", "deaths", "sweeps", "launches", "sm_proposals", "sm_accepted"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def timings(self):
+        out = np.zeros(8)
+        lb.check(self.lib.smg_get_timings(self.h, lb.dptr(out)))
+        keys = ["ll_block_ms", "aux_ll_ms", "scan_ms", "update_phi_ms", "split_merge_ms", "pool_ms", "loglik_ms", "total_ms"]
+        return dict(zip(keys, (float(x) for x in out)))
+
+    # ---- parity hooks ---------------------------------------------------------------------
+    def set_state(self, K, c_i, centers, sigmas):
+        c = lb.as_i32(c_i)
+        ce, sg = lb.as_f64(centers), lb.as_f64(sigmas)
+        lb.check(self.lib.smg_debug_set_state(self.h, int(K), lb.iptr(c), lb.dptr(ce), lb.dptr(sg)))
+
+    def set_pool(self, pool_center, pool_sigma):
+        pc, ps = lb.as_f64(pool_center), lb.as_f64(pool_sigma)
+        lb.check(self.lib.smg_debug_set_pool(self.h, pc.shape[0], lb.dptr(pc), lb.dptr(ps)))
+
+    def get_pool(self, first, count):
+        pc = np.empty((count, self.p))
+        ps = np.empty((count, self.p))
+        lb.check(self.lib.smg_debug_get_pool(self.h, int(first), int(count), lb.dptr(pc), lb.dptr(ps)))
+        return pc, ps
+
+    def ll_block(self, K):
+        LL = np.empty((self.n, K))
+        mm = np.empty((self.n, K), dtype=np.int32)
+        lb.check(self.lib.smg_debug_ll_block(self.h, lb.dptr(LL), lb.iptr(mm)))
+        return LL, mm
+
+    def neal8_scan(self, tape=None):
+        t = None if tape is None else lb.as_f64(tape)
+        if t is not None and t.size != self.n * (self.m + 1):
+            raise ValueError("tape must hold n*(m+1) uniforms")
+        lb.check(self.lib.smg_debug_neal8_scan(self.h, lb.dptr(t)))
+
+    def histogram(self, K):
+        mm = C.c_int()
+        lb.check(self.lib.smg_debug_histogram(self.h, None, None, C.byref(mm)))
+        H = np.empty((K, self.p, mm.value), dtype=np.int32)
+        cnt = np.empty(K, dtype=np.int32)
+        lb.check(self.lib.smg_debug_histogram(self.h, lb.iptr(H), lb.iptr(cnt), C.byref(mm)))
+        return H, cnt
+
+    def update_phi(self, u_center=None, u_sigma=None):
+        uc, us = lb.as_f64(u_center), lb.as_f64(u_sigma)
+        lb.check(self.lib.smg_debug_update_phi(self.h, lb.dptr(uc), lb.dptr(us)))
+
+    def loglik(self):
+        out = C.c_double()
+        lb.check(self.lib.smg_debug_loglik(self.h, C.byref(out)))
+        return out.value
+
+    def split_merge(self, tape=None):
+        """tape: dict with any of u_pair,u_prior_c,u_prior_s,u_launch,u_rg,u_rg_c,u_rg_s,u_mg_c,u_mg_s,u_accept."""
+        T = lb.SmgSmTape()
+        keep = []
+        if tape:
+            for k, a in tape.items():
+                arr = lb.as_f64(a)
+                keep.append(arr)
+                setattr(T, k, lb.dptr(arr))
+        info = np.zeros(8, dtype=np.int32)
+        S = np.zeros(self.n, dtype=np.int32)
+        zl = np.zeros(self.n, dtype=np.int32)
+        zs = np.zeros(self.n, dtype=np.int32)
+        phi = np.zeros((6, 2, self.p))
+        terms = np.zeros(24)
+        lb.check(self.lib.smg_debug_split_merge(self.h, C.byref(T) if tape else None, lb.iptr(info), lb.iptr(S), lb.iptr(zl),
+                                               lb.iptr(zs), lb.dptr(phi), lb.dptr(terms)))
+        nS = int(info[2])
+        return {"i1": int(info[0]), "i2": int(info[1]), "nS": nS, "is_split": int(info[3]), "accepted": int(info[4]),
+                "nA": int(info[5]), "nB": int(info[6]), "K": int(info[7]), "S": S[:nS].copy(), "z_launch": zl[:nS].copy(),
+                "z_star": zs[:nS].copy(), "phi": phi, "terms": terms}
+
+
+def hig_inv_u(omega, v, w, m):
+    lib = lb.load()
+    om, vv, ww, mm = (np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), np.shape(omega)))
+                      for x in (omega, v, w, m))
+    out = np.empty(om.shape)
+    lb.check(lib.smg_debug_hig_inv_u(om.size, lb.dptr(om), lb.dptr(vv), lb.dptr(ww), lb.dptr(mm), lb.dptr(out)))
+    return out
+
+
+def logdensity_hig(sigma, v, w, m):
+    lib = lb.load()
+    sg, vv, ww, mm = (np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), np.shape(sigma)))
+                      for x in (sigma, v, w, m))
+    out = np.empty(sg.shape)
+    lb.check(lib.smg_debug_logdensity_hig(sg.size, lb.dptr(sg), lb.dptr(vv), lb.dptr(ww), lb.dptr(mm), lb.dptr(out)))
+    return out

@@ -1,0 +1,929 @@
+// smg_chain.cu -- host driver of one chain + the extern "C" layer declared in include/smgibbs.h.
+// Mirrors code/launcher.cpp:7-174 (state initialisation, aux pool, iteration loop, snapshots);
+// all arithmetic happens in the kernels of smg_kernels.cuh / smg_sm.cuh.  There is no CPU path.
+#include "smg_chain.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+
+#include "smg_sm.cuh"
+
+namespace smg {
+thread_local std::string g_last_error;
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <typename T>
+static int dalloc(T** ptr, size_t count) {
+  SMG_CUDA(cudaMalloc((void**)ptr, std::max<size_t>(count, 1) * sizeof(T)));
+  return 0;
+}
+
+static int status_to_error(int st) {
+  if (st == 0) return SMG_OK;
+  if (st & ST_BAD_PROB) return fail(SMG_ERR_PROB, "Probabilities must be finite and non-negative! (allocation draw)");
+  if (st & ST_VALIDATE) return fail(SMG_ERR_STATE, "State validation failed: inconsistent cluster count");
+  if (st & ST_WALKER) return fail(SMG_ERR_CAPACITY, "allocation draw hit Rcpp's Walker-alias regime (nc > 200), not supported");
+  if (st & ST_TOO_MANY_ENTRIES) return fail(SMG_ERR_CAPACITY, "K + m exceeds 256 entries per allocation draw");
+  if (st & ST_LL_COLS) return fail(SMG_ERR_CAPACITY, "number of clusters exceeds max_clusters");
+  if (st & ST_SLOTS_EXHAUSTED) return fail(SMG_ERR_CAPACITY, "more than 1024 cluster slots used in one pass");
+  return fail(SMG_ERR_STATE, "device status " + std::to_string(st));
+}
+
+// ------------------------------------------------------------------------------------------
+static int chain_alloc(smg_chain* ch) {
+  const int n = ch->n, pp = ch->pp, NST = ch->NST;
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
+  for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
+  if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
+  if (dalloc(&ch->attr, pp) || dalloc(&ch->v, pp) || dalloc(&ch->w, pp)) return SMG_ERR_CUDA;
+  for (int b = 0; b < 2; b++) {
+    if (dalloc(&ch->cen[b], (size_t)NST * pp) || dalloc(&ch->sig[b], (size_t)NST * pp) ||
+        dalloc(&ch->isg[b], (size_t)NST * pp) || dalloc(&ch->sden[b], NST))
+      return SMG_ERR_CUDA;
+    SMG_CUDA(cudaMemset(ch->cen[b], 0, (size_t)NST * pp));
+    SMG_CUDA(cudaMemset(ch->sig[b], 0, (size_t)NST * pp * 8));
+    SMG_CUDA(cudaMemset(ch->isg[b], 0, (size_t)NST * pp * 8));
+    SMG_CUDA(cudaMemset(ch->sden[b], 0, (size_t)NST * 8));
+  }
+  if (dalloc(&ch->den, (size_t)NST * pp)) return SMG_ERR_CUDA;
+  if (dalloc(&ch->c, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
+      dalloc(&ch->slot2label, NST))
+    return SMG_ERR_CUDA;
+  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) ||
+      dalloc(&ch->aux_e, (size_t)n * ch->m_aux))
+    return SMG_ERR_CUDA;
+  const size_t P = (size_t)ch->pool_size;
+  if (dalloc(&ch->pcen, P * pp) || dalloc(&ch->psig, P * pp) || dalloc(&ch->pisg, P * pp) || dalloc(&ch->pden, P * pp) ||
+      dalloc(&ch->psden, P))
+    return SMG_ERR_CUDA;
+  if (dalloc(&ch->H, (size_t)ch->Kcap * pp * ch->mmax)) return SMG_ERR_CUDA;
+  ch->loglik_blocks = std::min(1184, std::max(1, cdiv(n, 8)));
+  if (dalloc(&ch->partial, ch->loglik_blocks) || dalloc(&ch->loglik_d, 1)) return SMG_ERR_CUDA;
+  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8)) return SMG_ERR_CUDA;
+  SMG_CUDA(cudaMemset(ch->status, 0, 4));
+  SMG_CUDA(cudaMemset(ch->accepted_d, 0, 4));
+  SMG_CUDA(cudaMemset(ch->stats_d, 0, 64));
+  if (dalloc(&ch->tape_d, (size_t)n * (ch->m_aux + 1))) return SMG_ERR_CUDA;
+  if (dalloc(&ch->uc_d, (size_t)NST * ch->p) || dalloc(&ch->us_d, (size_t)NST * ch->p)) return SMG_ERR_CUDA;
+  return sm_alloc(ch);
+}
+
+static void chain_free(smg_chain* ch) {
+  if (!ch) return;
+  cudaSetDevice(ch->device);
+  if (ch->st) cudaStreamSynchronize(ch->st);
+  sm_free(ch);
+  void* ptrs[] = {ch->X,      ch->attr,   ch->v,         ch->w,          ch->cen[0], ch->cen[1], ch->sig[0], ch->sig[1],
+                  ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
+                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
+                  ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
+                  ch->stats_d, ch->tape_d, ch->uc_d,     ch->us_d};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  for (int q = 0; q < 8; q++)
+    if (ch->ev[q]) cudaEventDestroy(ch->ev[q]);
+  if (ch->st) cudaStreamDestroy(ch->st);
+  delete ch;
+}
+
+// ------------------------------------------------------------------------------------------
+// phases
+// ------------------------------------------------------------------------------------------
+static int launch_ll_block(smg_chain* ch) {
+  dim3 grid(cdiv(ch->n, LLB_ROWS), cdiv(ch->Kcap, LLB_SLOTS));
+  hamming_ll_block_kernel<<<grid, 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], ch->isg[ch->cur],
+                                                    ch->sden[ch->cur], ch->K, ch->LL, ch->ldl);
+  ch->h_launches++;
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_aux_ll(smg_chain* ch, const double* tape) {
+  long long warps = (long long)ch->n * ch->m_aux;
+  aux_ll_kernel<<<cdiv(warps * 32, 256), 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->m_aux, ch->pcen, ch->pisg, ch->psden,
+                                                           ch->pool_size, tape, ch->m_aux + 1, mk_key(ch, SUB_SCAN),
+                                                           ch->LLaux, ch->aux_e);
+  ch->h_launches++;
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// one Neal-8 pass: launcher.cpp:95-99
+static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
+  if (!ch->pool_valid) return fail(SMG_ERR_STATE, "auxiliary pool not initialised");
+  if (timed) cudaEventRecord(ch->ev[0], ch->st);
+  if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+  if (timed) cudaEventRecord(ch->ev[1], ch->st);
+  if (launch_aux_ll(ch, tape)) return SMG_ERR_CUDA;
+  if (timed) cudaEventRecord(ch->ev[2], ch->st);
+  ScanArgs A;
+  A.n = ch->n;
+  A.pp = ch->pp;
+  A.m_aux = ch->m_aux;
+  A.ldl = ch->ldl;
+  A.K0cap = ch->Kcap;
+  A.X = ch->X;
+  A.LL = ch->LL;
+  A.LLaux = ch->LLaux;
+  A.aux_e = ch->aux_e;
+  A.u_alloc = tape ? tape + ch->m_aux : nullptr;
+  A.u_stride = ch->m_aux + 1;
+  A.key = mk_key(ch, SUB_SCAN);
+  A.c = ch->c;
+  A.cen = ch->cen[ch->cur];
+  A.sig = ch->sig[ch->cur];
+  A.isg = ch->isg[ch->cur];
+  A.sden = ch->sden[ch->cur];
+  A.pool_cen = ch->pcen;
+  A.pool_sig = ch->psig;
+  A.pool_isg = ch->pisg;
+  A.pool_sden = ch->psden;
+  A.Kptr = ch->K;
+  A.counts = ch->counts;
+  A.slot2label = ch->slot2label;
+  A.NS = ch->NS;
+  A.log_gamma_m = std::log(ch->gamma / ch->m_aux);
+  A.status = ch->status;
+  A.stats = ch->stats_d;
+  neal8_scan_kernel<<<1, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);
+  SMG_CUDA(cudaGetLastError());
+  // back to canonical form: labels in c, parameters in label order in the other buffer
+  const int nx = ch->cur ^ 1;
+  scan_finalize_labels_kernel<<<cdiv(ch->n, 256), 256, 0, ch->st>>>(ch->c, ch->n, ch->slot2label);
+  scan_finalize_params_kernel<<<ch->NS, 128, 0, ch->st>>>(ch->slot2label, ch->NS, ch->pp, ch->cen[ch->cur],
+                                                         ch->sig[ch->cur], ch->isg[ch->cur], ch->sden[ch->cur],
+                                                         ch->counts, ch->cen[nx], ch->sig[nx], ch->isg[nx],
+                                                         ch->sden[nx], ch->counts_slot);
+  SMG_CUDA(cudaGetLastError());
+  std::swap(ch->counts, ch->counts_slot);
+  ch->cur = nx;
+  ch->h_launches += 3;
+  if (timed) cudaEventRecord(ch->ev[3], ch->st);
+  return 0;
+}
+
+// K3: histogram + counts of the canonical state
+static int launch_histogram(smg_chain* ch) {
+  SMG_CUDA(cudaMemsetAsync(ch->H, 0, (size_t)ch->Kcap * ch->pp * ch->mmax * sizeof(int), ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->counts, 0, (size_t)ch->NST * sizeof(int), ch->st));
+  long long threads = (long long)ch->n * (ch->pp / 16);
+  cluster_histogram_kernel<<<cdiv(threads, 256), 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->c, ch->mmax, ch->H,
+                                                                  ch->counts);
+  ch->h_launches++;
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// update_phi on every cluster (common_functions.cpp:511-591)
+static int update_phi_all(smg_chain* ch, uint32_t sub, const double* uc, const double* us) {
+  if (launch_histogram(ch)) return SMG_ERR_CUDA;
+  PhiArgs A;
+  A.pp = ch->pp;
+  A.p = ch->p;
+  A.mmax = ch->mmax;
+  A.attr = ch->attr;
+  A.v = ch->v;
+  A.w = ch->w;
+  A.H = ch->H;
+  A.counts = ch->counts;
+  A.jobs = nullptr;
+  A.njobs_ptr = ch->K;
+  A.njobs = 0;
+  A.cen_src = ch->cen[ch->cur];
+  A.sig_src = ch->sig[ch->cur];
+  A.cen = ch->cen[ch->cur];
+  A.sig = ch->sig[ch->cur];
+  A.isg = ch->isg[ch->cur];
+  A.den = ch->den;
+  A.u_center = uc;
+  A.u_sigma = us;
+  A.u_stride = ch->p;
+  A.key = mk_key(ch, sub);
+  A.prior = 0;
+  A.enable = nullptr;
+  A.status = ch->status;
+  dim3 grid(cdiv(ch->pp, 128), ch->Kcap);
+  phi_draw_kernel<<<grid, 128, 0, ch->st>>>(A);
+  phi_sden_kernel<<<ch->Kcap, 256, 0, ch->st>>>(nullptr, ch->K, 0, ch->pp, ch->den, ch->sden[ch->cur], nullptr);
+  ch->h_launches += 2;
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// prior draws for clusters [0, K): sample_centers + sample_sigmas (launcher.cpp:46-48)
+static int prior_phi_all(smg_chain* ch, int K) {
+  PhiArgs A;
+  A.pp = ch->pp;
+  A.p = ch->p;
+  A.mmax = ch->mmax;
+  A.attr = ch->attr;
+  A.v = ch->v;
+  A.w = ch->w;
+  A.H = ch->H;
+  A.counts = ch->counts;
+  A.jobs = nullptr;
+  A.njobs_ptr = ch->K;
+  A.njobs = 0;
+  A.cen_src = ch->cen[ch->cur];
+  A.sig_src = ch->sig[ch->cur];
+  A.cen = ch->cen[ch->cur];
+  A.sig = ch->sig[ch->cur];
+  A.isg = ch->isg[ch->cur];
+  A.den = ch->den;
+  A.u_center = nullptr;
+  A.u_sigma = nullptr;
+  A.u_stride = ch->p;
+  A.key = mk_key(ch, SUB_INIT_PHI);
+  A.prior = 1;
+  A.enable = nullptr;
+  A.status = ch->status;
+  dim3 grid(cdiv(ch->pp, 128), std::max(K, 1));
+  phi_draw_kernel<<<grid, 128, 0, ch->st>>>(A);
+  phi_sden_kernel<<<std::max(K, 1), 256, 0, ch->st>>>(nullptr, ch->K, 0, ch->pp, ch->den, ch->sden[ch->cur], nullptr);
+  ch->h_launches += 2;
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int launch_loglik(smg_chain* ch) {
+  loglik_partial_kernel<<<ch->loglik_blocks, 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->c, ch->cen[ch->cur],
+                                                              ch->isg[ch->cur], ch->sden[ch->cur], ch->partial);
+  reduce_final_kernel<<<1, 256, 0, ch->st>>>(ch->partial, ch->loglik_blocks, ch->loglik_d);
+  ch->h_launches += 2;
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// aux pool (launcher.cpp:67-77, re-drawn at iter % 1000 == 0, :123-129)
+static int draw_pool(smg_chain* ch) {
+  long long total = ch->pool_size * ch->pp;
+  RngKey key = mk_key(ch, SUB_POOL);
+  pool_draw_kernel<<<cdiv(total, 128), 128, 0, ch->st>>>(ch->pool_size, ch->pp, ch->p, ch->attr, ch->v, ch->w, key, ch->pcen,
+                                                        ch->psig, ch->pisg, ch->pden);
+  pool_sden_kernel<<<cdiv(ch->pool_size * 32, 256), 256, 0, ch->st>>>(ch->pool_size, ch->pp, ch->pden, ch->psden);
+  ch->h_launches += 2;
+  SMG_CUDA(cudaGetLastError());
+  ch->pool_valid = true;
+  return 0;
+}
+
+// one iteration of launcher.cpp:85-154 (without the snapshot)
+static int sweep(smg_chain* ch, bool timed) {
+  SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, sizeof(int), ch->st));
+  if (timed) cudaEventRecord(ch->ev[0], ch->st);
+  if (ch->neal8 && ch->iter % ch->n8_step == 0) {
+    int rc = neal8_pass(ch, nullptr, timed);
+    if (rc) return rc;
+    rc = update_phi_all(ch, SUB_PHI_AFTER_SCAN, nullptr, nullptr);
+    if (rc) return rc;
+  } else if (timed) {
+    for (int q = 1; q <= 3; q++) cudaEventRecord(ch->ev[q], ch->st);
+  }
+  if (timed) cudaEventRecord(ch->ev[4], ch->st);
+  if (ch->split_merge && ch->iter % ch->sam_step == 0) {
+    int rc = sm_step(ch, nullptr);
+    if (rc) return rc;
+    ch->h_sm_props++;
+  }
+  if (timed) cudaEventRecord(ch->ev[5], ch->st);
+  if (ch->iter % 1000 == 0) {
+    int rc = draw_pool(ch);
+    if (rc) return rc;
+  }
+  if (timed) cudaEventRecord(ch->ev[6], ch->st);
+  int rc = launch_loglik(ch);
+  if (rc) return rc;
+  if (timed) cudaEventRecord(ch->ev[7], ch->st);
+  ch->iter++;
+  ch->h_sweeps++;
+  return 0;
+}
+
+static int sync_status(smg_chain* ch) {
+  int st = 0, K = 0, acc = 0;
+  double ll = 0;
+  SMG_CUDA(cudaMemcpyAsync(&st, ch->status, 4, cudaMemcpyDeviceToHost, ch->st));
+  SMG_CUDA(cudaMemcpyAsync(&K, ch->K, 4, cudaMemcpyDeviceToHost, ch->st));
+  SMG_CUDA(cudaMemcpyAsync(&acc, ch->accepted_d, 4, cudaMemcpyDeviceToHost, ch->st));
+  SMG_CUDA(cudaMemcpyAsync(&ll, ch->loglik_d, 8, cudaMemcpyDeviceToHost, ch->st));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  ch->h_K = K;
+  ch->h_accepted = acc;
+  ch->h_loglik = ll;
+  if (st) {
+    cudaMemsetAsync(ch->status, 0, 4, ch->st);
+    return status_to_error(st);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// creation
+// ------------------------------------------------------------------------------------------
+static int validate_cfg(const smg_config* cfg) {
+  if (!cfg || cfg->n < 2 || cfg->p < 1) return fail(SMG_ERR_ARG, "need n >= 2 observations and p >= 1 attributes");
+  if (!cfg->attrisize || !cfg->v || !cfg->w) return fail(SMG_ERR_ARG, "attrisize, v and w are required");
+  if (!(cfg->gamma > 0)) return fail(SMG_ERR_ARG, "gamma must be positive");
+  if (cfg->m_aux < 1 || cfg->m_aux > 32) return fail(SMG_ERR_ARG, "m (auxiliary components) must be in 1..32");
+  for (int j = 0; j < cfg->p; j++) {
+    if (cfg->attrisize[j] < 2 || cfg->attrisize[j] > SMG_MAX_LEVELS)
+      return fail(SMG_ERR_ARG, "attrisize[j] must be in 2..64 (attribute " + std::to_string(j) + ")");
+    if (!(cfg->v[j] > 1.0))
+      return fail(SMG_ERR_ARG, "v[j] must be > 1 (the HIG sampler uses the Beta(w+1, v-1) form; attribute " +
+                                   std::to_string(j) + ")");
+    if (!(cfg->w[j] >= 0.0)) return fail(SMG_ERR_ARG, "w[j] must be >= 0");
+  }
+  if (cfg->thinning < 1 || cfg->n8_step_size < 1 || cfg->sam_step_size < 1)
+    return fail(SMG_ERR_ARG, "thinning, n8_step_size and sam_step_size must be >= 1");
+  if (cfg->t < 0 || cfg->r < 0) return fail(SMG_ERR_ARG, "t and r must be >= 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SMG_ERR_ARG, "bad device ordinal");
+  return 0;
+}
+
+static int create_common(const smg_config* cfg, smg_chain** out) {
+  int rc = validate_cfg(cfg);
+  if (rc) return rc;
+  smg_chain* ch = new smg_chain();
+  ch->n = cfg->n;
+  ch->p = cfg->p;
+  ch->pp = (cfg->p + 15) / 16 * 16;
+  ch->m_aux = cfg->m_aux;
+  ch->L = std::max(cfg->L, 1);
+  ch->t = cfg->t;
+  ch->r = cfg->r;
+  ch->neal8 = cfg->neal8;
+  ch->split_merge = cfg->split_merge;
+  ch->n8_step = cfg->n8_step_size;
+  ch->sam_step = cfg->sam_step_size;
+  ch->thinning = cfg->thinning;
+  ch->gamma = cfg->gamma;
+  ch->seed = cfg->seed;
+  ch->device = cfg->device;
+  ch->Kcap = cfg->max_clusters > 0 ? cfg->max_clusters : 192;
+  ch->Kcap = std::min(ch->Kcap, SMG_MAX_ENTRIES - ch->m_aux);
+  ch->Kcap = std::max(ch->Kcap, 8);
+  ch->ldl = (ch->Kcap + 3) / 4 * 4;
+  ch->NS = SMG_MAX_SLOTS;
+  ch->NST = SMG_MAX_SLOTS + SM_NSLOTS;
+  ch->pool_size = cfg->pool_size > 0 ? cfg->pool_size : (long long)cfg->n * cfg->m_aux * cfg->thinning;
+  ch->h_attr.assign(cfg->attrisize, cfg->attrisize + cfg->p);
+  ch->h_v.assign(cfg->v, cfg->v + cfg->p);
+  ch->h_w.assign(cfg->w, cfg->w + cfg->p);
+  ch->mmax = *std::max_element(ch->h_attr.begin(), ch->h_attr.end());
+  if (ch->L > ch->Kcap) {
+    delete ch;
+    return fail(SMG_ERR_CAPACITY, "L exceeds max_clusters");
+  }
+  rc = chain_alloc(ch);
+  if (rc) {
+    chain_free(ch);
+    return rc;
+  }
+  std::vector<int> a(ch->pp, 2);
+  std::vector<double> v(ch->pp, 2.0), w(ch->pp, 1.0);
+  std::copy(ch->h_attr.begin(), ch->h_attr.end(), a.begin());
+  std::copy(ch->h_v.begin(), ch->h_v.end(), v.begin());
+  std::copy(ch->h_w.begin(), ch->h_w.end(), w.begin());
+  if (cudaMemcpy(ch->attr, a.data(), ch->pp * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ch->v, v.data(), ch->pp * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(ch->w, w.data(), ch->pp * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+    chain_free(ch);
+    return fail(SMG_ERR_CUDA, "upload of hyper-parameters failed");
+  }
+  *out = ch;
+  return 0;
+}
+
+// initial allocation + prior phi + update_phi + pool (launcher.cpp:31-77)
+static int init_state(smg_chain* ch, const int* c_init, int compact_init) {
+  std::vector<int> c(ch->n);
+  if (c_init) {
+    int mn = *std::min_element(c_init, c_init + ch->n);
+    for (int i = 0; i < ch->n; i++) c[i] = c_init[i] - mn;
+  } else {
+    init_assign_kernel<<<cdiv(ch->n, 256), 256, 0, ch->st>>>(ch->n, ch->L, nullptr, mk_key(ch, SUB_INIT), ch->c);
+    ch->h_launches++;
+    SMG_CUDA(cudaMemcpyAsync(c.data(), ch->c, (size_t)ch->n * 4, cudaMemcpyDeviceToHost, ch->st));
+    SMG_CUDA(cudaStreamSynchronize(ch->st));
+  }
+  int mx = *std::max_element(c.begin(), c.end());
+  if (mx >= ch->Kcap) return fail(SMG_ERR_CAPACITY, "initial labels exceed max_clusters");
+  std::vector<int> cnt(mx + 1, 0);
+  for (int x : c) cnt[x]++;
+  int nuniq = 0;
+  for (int x : cnt) nuniq += (x > 0);
+  int K = c_init ? nuniq : ch->L;  // launcher.cpp:38 / :28
+  if (nuniq != mx + 1 || nuniq != K) {
+    if (!compact_init)
+      // the reference runs into validate_state (common_functions.cpp:155-161) at the first move
+      return fail(SMG_ERR_STATE, "State validation failed: inconsistent cluster count from initial assignment "
+                                 "(a label in 0..K-1 is empty; pass contiguous labels or set compact_init)");
+    std::vector<int> remap(mx + 1, -1);
+    int nx = 0;
+    for (int l = 0; l <= mx; l++)
+      if (cnt[l] > 0) remap[l] = nx++;
+    for (int& x : c) x = remap[x];
+    K = nx;
+  }
+  std::vector<int> counts(ch->NST, 0);
+  for (int x : c) counts[x]++;
+  SMG_CUDA(cudaMemcpyAsync(ch->c, c.data(), (size_t)ch->n * 4, cudaMemcpyHostToDevice, ch->st));
+  SMG_CUDA(cudaMemcpyAsync(ch->counts, counts.data(), (size_t)ch->NST * 4, cudaMemcpyHostToDevice, ch->st));
+  SMG_CUDA(cudaMemcpyAsync(ch->K, &K, 4, cudaMemcpyHostToDevice, ch->st));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  ch->h_K = K;
+  int rc = prior_phi_all(ch, K);
+  if (rc) return rc;
+  rc = update_phi_all(ch, SUB_INIT_PHI + 1, nullptr, nullptr);
+  if (rc) return rc;
+  rc = draw_pool(ch);
+  if (rc) return rc;
+  return sync_status(ch);
+}
+
+static int upload_colmajor(smg_chain* ch, const double* data) {
+  double* tmp = nullptr;
+  int* bad = nullptr;
+  SMG_CUDA(cudaMalloc(&tmp, (size_t)ch->n * ch->p * 8));
+  SMG_CUDA(cudaMalloc(&bad, 4));
+  SMG_CUDA(cudaMemsetAsync(bad, 0, 4, ch->st));
+  SMG_CUDA(cudaMemcpyAsync(tmp, data, (size_t)ch->n * ch->p * 8, cudaMemcpyHostToDevice, ch->st));
+  long long total = (long long)ch->n * ch->pp;
+  ingest_colmajor_kernel<<<cdiv(total, 256), 256, 0, ch->st>>>(tmp, ch->n, ch->p, ch->pp, ch->attr, ch->X, bad);
+  ch->h_launches++;
+  int hbad = 0;
+  SMG_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ch->st));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  cudaFree(tmp);
+  cudaFree(bad);
+  if (hbad) return fail(SMG_ERR_ARG, std::to_string(hbad) + " data entries are not integer codes in 1..attrisize[j]");
+  return 0;
+}
+
+static int upload_u8(smg_chain* ch, const unsigned char* data) {
+  std::vector<uint8_t> buf((size_t)ch->n * ch->pp, 0);
+  for (int i = 0; i < ch->n; i++)
+    for (int j = 0; j < ch->p; j++) {
+      unsigned char x = data[(size_t)i * ch->p + j];
+      if (x < 1 || x > ch->h_attr[j]) return fail(SMG_ERR_ARG, "data entries must be codes in 1..attrisize[j]");
+      buf[(size_t)i * ch->pp + j] = x;
+    }
+  SMG_CUDA(cudaMemcpy(ch->X, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+}  // namespace smg
+
+using namespace smg;
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+extern "C" {
+
+const char* smg_last_error(void) { return g_last_error.c_str(); }
+
+int smg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+static int create_impl(const smg_config* cfg, const double* dcol, const unsigned char* du8, const int* c_init,
+                       smg_chain** out) {
+  if (!out) return fail(SMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (!dcol && !du8) return fail(SMG_ERR_ARG, "data is NULL");
+  smg_chain* ch = nullptr;
+  int rc = create_common(cfg, &ch);
+  if (rc) return rc;
+  rc = dcol ? upload_colmajor(ch, dcol) : upload_u8(ch, du8);
+  if (!rc) rc = init_state(ch, c_init, cfg->compact_init);
+  if (rc) {
+    std::string keep = g_last_error;
+    chain_free(ch);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = ch;
+  return 0;
+}
+
+int smg_create(const smg_config* cfg, const double* data_colmajor, const int* c_init, smg_chain** out) {
+  return create_impl(cfg, data_colmajor, nullptr, c_init, out);
+}
+int smg_create_u8(const smg_config* cfg, const unsigned char* data_rowmajor, const int* c_init, smg_chain** out) {
+  return create_impl(cfg, nullptr, data_rowmajor, c_init, out);
+}
+
+void smg_destroy(smg_chain* ch) { chain_free(ch); }
+
+int smg_step(smg_chain* ch, int n_iters) {
+  if (!ch) return fail(SMG_ERR_ARG, "chain is NULL");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  for (int it = 0; it < n_iters; it++) {
+    int rc = sweep(ch, it == n_iters - 1);
+    if (rc) return rc;
+  }
+  int rc = sync_status(ch);
+  if (n_iters > 0) {
+    const int a[7] = {0, 1, 2, 3, 4, 5, 6}, b[7] = {1, 2, 3, 4, 5, 6, 7};
+    float ms;
+    // [0] ll block, [1] aux, [2] scan(+finalize), [3] update_phi, [4] split-merge, [5] pool, [6] loglik ; [7] total
+    for (int q = 0; q < 7; q++) {
+      ms = 0;
+      cudaEventElapsedTime(&ms, ch->ev[a[q]], ch->ev[b[q]]);
+      ch->h_timings[q] = ms;
+    }
+    ms = 0;
+    cudaEventElapsedTime(&ms, ch->ev[0], ch->ev[7]);
+    ch->h_timings[7] = ms;
+  }
+  if (ch->h_accepted) ch->h_sm_acc++;
+  return rc;
+}
+
+int smg_snapshot(smg_chain* ch, int* K, int* c_i, double* centers, double* sigmas, int cap_clusters, double* loglik,
+                 int* accepted) {
+  if (!ch) return fail(SMG_ERR_ARG, "chain is NULL");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  const int Kh = ch->h_K;
+  if (K) *K = Kh;
+  if (loglik) *loglik = ch->h_loglik;
+  if (accepted) *accepted = ch->h_accepted;
+  if (c_i) SMG_CUDA(cudaMemcpy(c_i, ch->c, (size_t)ch->n * 4, cudaMemcpyDeviceToHost));
+  if (centers || sigmas) {
+    if (Kh > cap_clusters) return fail(SMG_ERR_CAPACITY, "snapshot buffers hold fewer clusters than K");
+    std::vector<uint8_t> hc((size_t)Kh * ch->pp);
+    std::vector<double> hs((size_t)Kh * ch->pp);
+    SMG_CUDA(cudaMemcpy(hc.data(), ch->cen[ch->cur], hc.size(), cudaMemcpyDeviceToHost));
+    SMG_CUDA(cudaMemcpy(hs.data(), ch->sig[ch->cur], hs.size() * 8, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < Kh; k++)
+      for (int j = 0; j < ch->p; j++) {
+        if (centers) centers[(size_t)k * ch->p + j] = (double)hc[(size_t)k * ch->pp + j];
+        if (sigmas) sigmas[(size_t)k * ch->p + j] = hs[(size_t)k * ch->pp + j];
+      }
+  }
+  return 0;
+}
+
+int smg_get_stats(smg_chain* ch, unsigned long long* out8) {
+  if (!ch || !out8) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  unsigned long long d[8];
+  SMG_CUDA(cudaMemcpy(d, ch->stats_d, 64, cudaMemcpyDeviceToHost));
+  out8[0] = d[0];
+  out8[1] = d[1];
+  out8[2] = d[2];
+  out8[3] = d[3];
+  out8[4] = ch->h_sweeps;
+  out8[5] = ch->h_launches;
+  out8[6] = ch->h_sm_props;
+  out8[7] = d[7];
+  return 0;
+}
+
+int smg_get_timings(smg_chain* ch, double* out8) {
+  if (!ch || !out8) return fail(SMG_ERR_ARG, "NULL argument");
+  for (int q = 0; q < 8; q++) out8[q] = ch->h_timings[q];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// whole run: code/launcher.cpp:7-174
+// ------------------------------------------------------------------------------------------
+void smg_free_results(smg_results* r) {
+  if (!r) return;
+  free(r->total_cls);
+  free(r->c_i);
+  free(r->phi_offset);
+  free(r->centers);
+  free(r->sigmas);
+  free(r->loglikelihood);
+  free(r->final_ass);
+  free(r->accepted);
+  memset(r, 0, sizeof(*r));
+}
+
+int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize, double gamma, const double* v,
+                         const double* w, int verbose, int m, int iterations, int L, const int* c_i, int burnin, int t,
+                         int r, int neal8, int split_merge, int n8_step_size, int sam_step_size, int thinning,
+                         unsigned long long seed, int device, smg_results* out) {
+  if (!out) return fail(SMG_ERR_ARG, "out is NULL");
+  memset(out, 0, sizeof(*out));
+  if (iterations < 0 || burnin < 0) return fail(SMG_ERR_ARG, "iterations and burnin must be >= 0");
+  smg_config cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.n = n;
+  cfg.p = p;
+  cfg.attrisize = attrisize;
+  cfg.gamma = gamma;
+  cfg.v = v;
+  cfg.w = w;
+  cfg.m_aux = m;
+  cfg.L = L;
+  cfg.t = t;
+  cfg.r = r;
+  cfg.neal8 = neal8;
+  cfg.split_merge = split_merge;
+  cfg.n8_step_size = n8_step_size;
+  cfg.sam_step_size = sam_step_size;
+  cfg.thinning = thinning;
+  cfg.seed = seed;
+  cfg.device = device;
+  smg_chain* ch = nullptr;
+  int rc = smg_create(&cfg, data, c_i, &ch);
+  if (rc) return rc;
+  out->iterations = iterations;
+  out->n = n;
+  out->p = p;
+  out->total_cls = (int*)calloc(std::max(iterations, 1), sizeof(int));
+  out->c_i = (int*)calloc((size_t)std::max(iterations, 1) * n, sizeof(int));
+  out->phi_offset = (long long*)calloc(iterations + 1, sizeof(long long));
+  out->loglikelihood = (double*)calloc(std::max(iterations, 1), sizeof(double));
+  out->final_ass = (int*)calloc(n, sizeof(int));
+  out->accepted = (int*)calloc(std::max(iterations, 1), sizeof(int));
+  std::vector<double> cen, sg;
+  std::vector<double> kc((size_t)ch->Kcap * p), ks((size_t)ch->Kcap * p);
+  auto t0 = std::chrono::steady_clock::now();
+  const long long total = (long long)(iterations + burnin) * thinning;
+  for (long long iter = 0; iter < total && !rc; ++iter) {
+    rc = smg_step(ch, 1);
+    if (rc) break;
+    if (verbose != 0) fprintf(stderr, "[DEBUG] - Iteration %lld of %d\n", iter, iterations + burnin);
+    if (iter >= (long long)thinning * burnin && iter % thinning == 0) {
+      const long long slot = iter / thinning - burnin;
+      int K = 0;
+      rc = smg_snapshot(ch, &K, out->c_i + (size_t)slot * n, kc.data(), ks.data(), ch->Kcap, &out->loglikelihood[slot],
+                        &out->accepted[slot]);
+      if (rc) break;
+      out->total_cls[slot] = K;
+      out->phi_offset[slot + 1] = out->phi_offset[slot] + K;
+      cen.insert(cen.end(), kc.begin(), kc.begin() + (size_t)K * p);
+      sg.insert(sg.end(), ks.begin(), ks.begin() + (size_t)K * p);
+    }
+  }
+  if (!rc) rc = smg_snapshot(ch, nullptr, out->final_ass, nullptr, nullptr, 0, nullptr, nullptr);
+  auto t1 = std::chrono::steady_clock::now();
+  out->seconds = std::chrono::duration<double>(t1 - t0).count();
+  out->time = (long long)std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count();
+  if (!rc) {
+    out->centers = (double*)malloc(std::max<size_t>(cen.size(), 1) * 8);
+    out->sigmas = (double*)malloc(std::max<size_t>(sg.size(), 1) * 8);
+    std::copy(cen.begin(), cen.end(), out->centers);
+    std::copy(sg.begin(), sg.end(), out->sigmas);
+  }
+  std::string keep = g_last_error;
+  smg_destroy(ch);
+  if (rc) {
+    smg_free_results(out);
+    g_last_error = keep;
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// parity hooks
+// ------------------------------------------------------------------------------------------
+int smg_debug_set_state(smg_chain* ch, int K, const int* c_i, const double* centers, const double* sigmas) {
+  if (!ch || !c_i || !centers || !sigmas) return fail(SMG_ERR_ARG, "NULL argument");
+  if (K < 1 || K > ch->Kcap) return fail(SMG_ERR_CAPACITY, "K out of range");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  std::vector<uint8_t> hc((size_t)K * ch->pp, 0);
+  std::vector<double> hs((size_t)K * ch->pp, 1.0);
+  for (int k = 0; k < K; k++)
+    for (int j = 0; j < ch->p; j++) {
+      hc[(size_t)k * ch->pp + j] = (uint8_t)centers[(size_t)k * ch->p + j];
+      hs[(size_t)k * ch->pp + j] = sigmas[(size_t)k * ch->p + j];
+    }
+  std::vector<int> counts(ch->NST, 0);
+  for (int i = 0; i < ch->n; i++) {
+    if (c_i[i] < 0 || c_i[i] >= K) return fail(SMG_ERR_ARG, "label out of range");
+    counts[c_i[i]]++;
+  }
+  SMG_CUDA(cudaMemcpy(ch->cen[ch->cur], hc.data(), hc.size(), cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(ch->sig[ch->cur], hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(ch->c, c_i, (size_t)ch->n * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(ch->counts, counts.data(), counts.size() * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(ch->K, &K, 4, cudaMemcpyHostToDevice));
+  derive_terms_kernel<<<K, 256, 0, ch->st>>>(K, ch->pp, ch->p, ch->attr, ch->sig[ch->cur], ch->isg[ch->cur], ch->den,
+                                             ch->sden[ch->cur]);
+  ch->h_launches++;
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  ch->h_K = K;
+  return 0;
+}
+
+int smg_debug_set_pool(smg_chain* ch, long long pool_size, const double* pool_center, const double* pool_sigma) {
+  if (!ch || !pool_center || !pool_sigma) return fail(SMG_ERR_ARG, "NULL argument");
+  if (pool_size < 1 || pool_size > ch->pool_size) return fail(SMG_ERR_ARG, "pool_size exceeds the allocated pool");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  std::vector<uint8_t> hc((size_t)pool_size * ch->pp, 0);
+  std::vector<double> hs((size_t)pool_size * ch->pp, 1.0);
+  for (long long e = 0; e < pool_size; e++)
+    for (int j = 0; j < ch->p; j++) {
+      hc[(size_t)e * ch->pp + j] = (uint8_t)pool_center[(size_t)e * ch->p + j];
+      hs[(size_t)e * ch->pp + j] = pool_sigma[(size_t)e * ch->p + j];
+    }
+  SMG_CUDA(cudaMemcpy(ch->pcen, hc.data(), hc.size(), cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(ch->psig, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
+  // derive 1/sigma, den and their per-entry sums, in chunks of 65535 entries (grid.x limit is larger, keep simple)
+  for (long long e0 = 0; e0 < pool_size; e0 += 1 << 20) {
+    int cnt = (int)std::min<long long>(1 << 20, pool_size - e0);
+    derive_terms_kernel<<<cnt, 256, 0, ch->st>>>(cnt, ch->pp, ch->p, ch->attr, ch->psig + (size_t)e0 * ch->pp,
+                                                 ch->pisg + (size_t)e0 * ch->pp, ch->pden + (size_t)e0 * ch->pp,
+                                                 ch->psden + e0);
+    ch->h_launches++;
+  }
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  ch->pool_size = pool_size;  // shrink the logical pool to what was injected
+  ch->pool_valid = true;
+  return 0;
+}
+
+int smg_debug_get_pool(smg_chain* ch, long long first, long long count, double* pool_center, double* pool_sigma) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  if (first < 0 || first + count > ch->pool_size) return fail(SMG_ERR_ARG, "pool range out of bounds");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  std::vector<uint8_t> hc((size_t)count * ch->pp);
+  std::vector<double> hs((size_t)count * ch->pp);
+  SMG_CUDA(cudaMemcpy(hc.data(), ch->pcen + (size_t)first * ch->pp, hc.size(), cudaMemcpyDeviceToHost));
+  SMG_CUDA(cudaMemcpy(hs.data(), ch->psig + (size_t)first * ch->pp, hs.size() * 8, cudaMemcpyDeviceToHost));
+  for (long long e = 0; e < count; e++)
+    for (int j = 0; j < ch->p; j++) {
+      if (pool_center) pool_center[(size_t)e * ch->p + j] = hc[(size_t)e * ch->pp + j];
+      if (pool_sigma) pool_sigma[(size_t)e * ch->p + j] = hs[(size_t)e * ch->pp + j];
+    }
+  return 0;
+}
+
+int smg_debug_ll_block(smg_chain* ch, double* LL, int* mism) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  const int K = ch->h_K;
+  if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  if (LL) {
+    std::vector<double> h((size_t)ch->n * ch->ldl);
+    SMG_CUDA(cudaMemcpy(h.data(), ch->LL, h.size() * 8, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < ch->n; i++)
+      for (int k = 0; k < K; k++) LL[(size_t)i * K + k] = h[(size_t)i * ch->ldl + k];
+  }
+  if (mism) {
+    int* d = nullptr;
+    SMG_CUDA(cudaMalloc(&d, (size_t)ch->n * K * 4));
+    long long warps = (long long)ch->n * K;
+    mismatch_count_kernel<<<cdiv(warps * 32, 256), 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], K, d);
+    ch->h_launches++;
+    SMG_CUDA(cudaGetLastError());
+    SMG_CUDA(cudaStreamSynchronize(ch->st));
+    SMG_CUDA(cudaMemcpy(mism, d, (size_t)ch->n * K * 4, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+  }
+  return 0;
+}
+
+int smg_debug_neal8_scan(smg_chain* ch, const double* tape) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  const double* td = nullptr;
+  if (tape) {
+    SMG_CUDA(cudaMemcpy(ch->tape_d, tape, (size_t)ch->n * (ch->m_aux + 1) * 8, cudaMemcpyHostToDevice));
+    td = ch->tape_d;
+  }
+  int rc = neal8_pass(ch, td, true);
+  if (rc) return rc;
+  rc = sync_status(ch);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ch->ev[0], ch->ev[1]);
+  ch->h_timings[0] = ms;
+  cudaEventElapsedTime(&ms, ch->ev[1], ch->ev[2]);
+  ch->h_timings[1] = ms;
+  cudaEventElapsedTime(&ms, ch->ev[2], ch->ev[3]);
+  ch->h_timings[2] = ms;
+  return rc;
+}
+
+int smg_debug_histogram(smg_chain* ch, int* H, int* counts, int* mmax_out) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  if (launch_histogram(ch)) return SMG_ERR_CUDA;
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  const int K = ch->h_K;
+  if (mmax_out) *mmax_out = ch->mmax;
+  if (H) {
+    std::vector<int> h((size_t)K * ch->pp * ch->mmax);
+    SMG_CUDA(cudaMemcpy(h.data(), ch->H, h.size() * 4, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < K; k++)
+      for (int j = 0; j < ch->p; j++)
+        for (int a = 0; a < ch->mmax; a++)
+          H[((size_t)k * ch->p + j) * ch->mmax + a] = h[((size_t)k * ch->pp + j) * ch->mmax + a];
+  }
+  if (counts) SMG_CUDA(cudaMemcpy(counts, ch->counts, (size_t)K * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int smg_debug_update_phi(smg_chain* ch, const double* u_center, const double* u_sigma) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  const int K = ch->h_K;
+  const double *uc = nullptr, *us = nullptr;
+  if (u_center) {
+    SMG_CUDA(cudaMemcpy(ch->uc_d, u_center, (size_t)K * ch->p * 8, cudaMemcpyHostToDevice));
+    uc = ch->uc_d;
+  }
+  if (u_sigma) {
+    SMG_CUDA(cudaMemcpy(ch->us_d, u_sigma, (size_t)K * ch->p * 8, cudaMemcpyHostToDevice));
+    us = ch->us_d;
+  }
+  rc = update_phi_all(ch, SUB_PHI_AFTER_SCAN, uc, us);
+  if (rc) return rc;
+  return sync_status(ch);
+}
+
+int smg_debug_loglik(smg_chain* ch, double* out) {
+  if (!ch || !out) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  if (launch_loglik(ch)) return SMG_ERR_CUDA;
+  int rc = sync_status(ch);
+  *out = ch->h_loglik;
+  return rc;
+}
+
+__global__ void dbg_hig_inv_kernel(int n, const double* om, const double* v, const double* w, const double* m,
+                                   double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = hig_inv_u_d(om[i], v[i], w[i], m[i]);
+}
+__global__ void dbg_loghig_kernel(int n, const double* s, const double* v, const double* w, const double* m,
+                                  double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = logdensity_hig_d(s[i], v[i], w[i], m[i]);
+}
+
+static int dbg_map4(int count, const double* a, const double* b, const double* c, const double* d, double* out, int which) {
+  if (count <= 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  double* buf = nullptr;
+  SMG_CUDA(cudaMalloc(&buf, (size_t)count * 5 * 8));
+  const double* src[4] = {a, b, c, d};
+  for (int q = 0; q < 4; q++) SMG_CUDA(cudaMemcpy(buf + (size_t)q * count, src[q], (size_t)count * 8, cudaMemcpyHostToDevice));
+  if (which == 0)
+    dbg_hig_inv_kernel<<<cdiv(count, 64), 64>>>(count, buf, buf + count, buf + 2 * (size_t)count, buf + 3 * (size_t)count,
+                                                buf + 4 * (size_t)count);
+  else
+    dbg_loghig_kernel<<<cdiv(count, 64), 64>>>(count, buf, buf + count, buf + 2 * (size_t)count, buf + 3 * (size_t)count,
+                                               buf + 4 * (size_t)count);
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaDeviceSynchronize());
+  SMG_CUDA(cudaMemcpy(out, buf + 4 * (size_t)count, (size_t)count * 8, cudaMemcpyDeviceToHost));
+  cudaFree(buf);
+  return 0;
+}
+
+int smg_debug_hig_inv_u(int count, const double* omega, const double* v, const double* w, const double* m, double* u_out) {
+  return dbg_map4(count, omega, v, w, m, u_out, 0);
+}
+int smg_debug_logdensity_hig(int count, const double* sigma, const double* v, const double* w, const double* m,
+                             double* out) {
+  return dbg_map4(count, sigma, v, w, m, out, 1);
+}
+
+int smg_debug_split_merge(smg_chain* ch, const smg_sm_tape* tape, int* info, int* S, int* z_launch, int* z_star,
+                          double* phi_out, double* terms) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, sizeof(int), ch->st));
+  rc = sm_step(ch, tape);
+  if (rc) return rc;
+  rc = sync_status(ch);
+  if (rc) return rc;
+  return sm_readback(ch, info, S, z_launch, z_star, phi_out, terms);
+}
+
+}  // extern "C"

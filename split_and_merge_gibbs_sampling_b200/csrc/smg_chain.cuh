@@ -1,0 +1,106 @@
+// smg_chain.cuh -- host-side state of one chain (the internal_state + aux_data of
+// code/common_functions.hpp:32-72, resident in HBM) and small helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smgibbs.h"
+#include "smg_kernels.cuh"
+
+namespace smg {
+
+extern thread_local std::string g_last_error;
+inline int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define SMG_CUDA(call)                                                                                       \
+  do {                                                                                                       \
+    cudaError_t _e = (call);                                                                                 \
+    if (_e != cudaSuccess)                                                                                   \
+      return smg::fail(SMG_ERR_CUDA, std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + __FILE__ + \
+                                         ":" + std::to_string(__LINE__));                                    \
+  } while (0)
+
+// Philox sub-stream ids inside one iteration
+enum SubPhase : uint32_t {
+  SUB_SCAN = 0,
+  SUB_PHI_AFTER_SCAN = 1,
+  SUB_SM_SELECT = 2,
+  SUB_SM_PRIOR = 3,       // prior draws of the launch states
+  SUB_SM_LAUNCH = 4,      // random launch allocation
+  SUB_SM_RG = 8,          // + scan index q  (restricted scans and their update_phi)
+  SUB_SM_MERGE = 64,      // + update index
+  SUB_SM_ACCEPT = 120,
+  SUB_POOL = 121,
+  SUB_INIT = 122,
+  SUB_INIT_PHI = 123
+};
+
+// extra parameter slots (beyond the SMG_MAX_SLOTS scan slots) used by the split-merge step
+enum SmSlot : int { SM_SL_A = 0, SM_SL_B, SM_ML_M, SM_ST_A, SM_ST_B, SM_ST_M, SM_TMP0, SM_TMP1, SM_NSLOTS };
+
+struct SmWork;  // split-merge workspace (smg_sm.cuh)
+
+}  // namespace smg
+
+struct smg_chain {
+  // ---- configuration (host copies)
+  int n = 0, p = 0, pp = 0, mmax = 0, m_aux = 0, L = 1, t = 10, r = 10;
+  int neal8 = 0, split_merge = 1, n8_step = 1, sam_step = 1, thinning = 1;
+  double gamma = 1.0;
+  unsigned long long seed = 0;
+  int Kcap = 192, NS = SMG_MAX_SLOTS, NST = SMG_MAX_SLOTS + smg::SM_NSLOTS, ldl = 192;
+  long long pool_size = 0;
+  int device = 0;
+  std::vector<int> h_attr;
+  std::vector<double> h_v, h_w;
+  // ---- device buffers
+  cudaStream_t st = nullptr;
+  uint8_t* X = nullptr;
+  int* attr = nullptr;
+  double *v = nullptr, *w = nullptr;
+  uint8_t* cen[2] = {nullptr, nullptr};
+  double *sig[2] = {nullptr, nullptr}, *isg[2] = {nullptr, nullptr}, *sden[2] = {nullptr, nullptr};
+  double* den = nullptr;
+  int cur = 0;
+  int *c = nullptr, *K = nullptr, *counts = nullptr, *counts_slot = nullptr, *slot2label = nullptr;
+  double *LL = nullptr, *LLaux = nullptr;
+  int* aux_e = nullptr;
+  uint8_t* pcen = nullptr;
+  double *psig = nullptr, *pisg = nullptr, *pden = nullptr, *psden = nullptr;
+  bool pool_valid = false;
+  int* H = nullptr;
+  double *partial = nullptr, *loglik_d = nullptr;
+  int* status = nullptr;
+  int* accepted_d = nullptr;
+  unsigned long long* stats_d = nullptr;
+  double* tape_d = nullptr;      // [n][m_aux+1] injected scan uniforms
+  double *uc_d = nullptr, *us_d = nullptr;  // injected phi uniforms [NST][p]
+  smg::SmWork* sm = nullptr;
+  // ---- host-side run state
+  long long iter = 0;
+  int h_K = 0, h_accepted = 0;
+  double h_loglik = 0.0;
+  unsigned long long h_launches = 0, h_sweeps = 0, h_sm_props = 0, h_sm_acc = 0;
+  cudaEvent_t ev[8] = {};
+  double h_timings[8] = {};
+  int loglik_blocks = 0;
+};
+
+namespace smg {
+inline RngKey mk_key(const smg_chain* ch, uint32_t sub) {
+  RngKey k;
+  k.k0 = (uint32_t)ch->seed;
+  k.k1 = (uint32_t)(ch->seed >> 32);
+  k.sweep = (uint32_t)ch->iter;
+  k.sub = sub;
+  return k;
+}
+}  // namespace smg

@@ -1,0 +1,303 @@
+// smg_device.cuh -- device-side building blocks shared by every kernel of the
+// B200 (sm_100a) Gibbs + split-merge sampler: counter-based uniforms, warp
+// reductions, the log-incomplete-beta function, the HIG inverse-CDF sampler and
+// the Rcpp-compatible categorical draw.
+//
+// Reference behaviour being reproduced (file:line in Filippo-Galli/Split_and_merge_Gibbs_sampling):
+//   dhamming                  code/common_functions.cpp:355-377
+//   norm_const2 / HIG density code/hyperg.cpp:11-48, code/split_merge.cpp:6-18
+//   rhig (sigma sampler)      code/hyperg.cpp:346-378  (+ bisec_hyper2 :221-287, lF_conK2 :183-217)
+//   Rcpp::sample with probs   call sites neal8.cpp:102, common_functions.cpp:195, split_merge.cpp:215
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace smg {
+
+#define SMG_FULL 0xffffffffu
+
+// ----------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator.  One call yields 4 x 32 bits addressed
+// by (seed, sweep, site, a, b): any thread can produce the uniform of any draw
+// site without a sequential stream (SURVEY Appendix A lists the sites).
+// ----------------------------------------------------------------------------
+enum Site : uint32_t {
+  U_POOL_IDX = 1,   // neal8.cpp:66        (a = observation, b = aux slot)
+  U_ALLOC = 2,      // neal8.cpp:102       (a = observation)
+  U_CENTER = 3,     // common_functions.cpp:195/199 (a = job, b = attribute)
+  U_SIGMA = 4,      // hyperg.cpp:373      (a = job, b = attribute)
+  U_SM_PAIR = 5,    // split_merge.cpp:275 (a = 0/1)
+  U_SM_LAUNCH = 6,  // split_merge.cpp:346 (a = position in S)
+  U_SM_RGIBBS = 7,  // split_merge.cpp:215 (a = position in S, b = scan index)
+  U_SM_ACCEPT = 8,  // split_merge.cpp:591
+  U_POOL_CENTER = 9,
+  U_POOL_SIGMA = 10,
+  U_INIT_ASSIGN = 11  // common_functions.cpp:180
+};
+
+struct RngKey {
+  uint32_t k0, k1;   // seed
+  uint32_t sweep;    // iteration index
+  uint32_t sub;      // sub-phase inside the iteration (which update_phi call, ...)
+};
+
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                                        uint32_t k1, uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0, hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0;
+    c1 = n1;
+    c2 = n2;
+    c3 = n3;
+    k0 += W0;
+    k1 += W1;
+  }
+  out[0] = c0;
+  out[1] = c1;
+  out[2] = c2;
+  out[3] = c3;
+}
+
+// uniform strictly inside (0,1) with 53 random bits, like R's unif_rand() contract
+__host__ __device__ __forceinline__ double u01_from_bits(uint32_t hi, uint32_t lo) {
+  uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+  return ((double)x + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+__host__ __device__ __forceinline__ double philox_u01(const RngKey& k, uint32_t site, uint32_t a, uint32_t b) {
+  uint32_t o[4];
+  philox4x32_10(a, b, site | (k.sub << 8), k.sweep, k.k0, k.k1, o);
+  return u01_from_bits(o[0], o[1]);
+}
+
+// injected uniform (parity tests / tape replay) or the Philox one
+__device__ __forceinline__ double get_u(const double* inj, size_t idx, const RngKey& k, uint32_t site, uint32_t a,
+                                        uint32_t b) {
+  return inj ? inj[idx] : philox_u01(k, site, a, b);
+}
+
+// ----------------------------------------------------------------------------
+// warp helpers
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(SMG_FULL, v, src); }
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(SMG_FULL, v, m); }
+
+// deterministic butterfly sum: every lane ends with the same value
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SMG_FULL, v); }
+
+// order-preserving map double -> uint64 (no NaNs expected)
+__device__ __forceinline__ uint64_t sort_key(double v) {
+  uint64_t b = (uint64_t)__double_as_longlong(v);
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_to_double(uint64_t k) {
+  uint64_t b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+// exact warp max of doubles with two REDUX ops (hi word, then lo word among the hi-maxima)
+__device__ __forceinline__ uint64_t warp_max_key(uint64_t key) {
+  uint32_t hi = (uint32_t)(key >> 32), lo = (uint32_t)key;
+  uint32_t mhi = __reduce_max_sync(SMG_FULL, hi);
+  uint32_t mlo = __reduce_max_sync(SMG_FULL, hi == mhi ? lo : 0u);
+  return ((uint64_t)mhi << 32) | mlo;
+}
+
+// ----------------------------------------------------------------------------
+// per-attribute Hamming terms (common_functions.cpp:368-376):
+//   dhamming = -[x != c]/s - log(1 + (m-1)/exp(1/s))
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double hamming_den(double s, int m) { return log(1.0 + ((double)m - 1.0) / exp(1.0 / s)); }
+
+// ----------------------------------------------------------------------------
+// log I_x(a,b): modified-Lentz continued fraction, evaluated on the smaller tail.
+// Returns both log I_x(a,b) (lower) and log(1 - I_x(a,b)) (upper).
+// `lb` = lbeta(a,b) supplied by the caller (computed once per draw).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ double lbeta_d(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+
+__device__ inline double betacf_d(double a, double b, double x) {
+  const double EPS = 1e-16, FPMIN = 1e-300;
+  double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < FPMIN) d = FPMIN;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 100000; m++) {
+    double m2 = 2.0 * m, dm = (double)m;
+    double aa = dm * (b - dm) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c;
+    if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + dm) * (qab + dm) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < FPMIN) d = FPMIN;
+    c = 1.0 + aa / c;
+    if (fabs(c) < FPMIN) c = FPMIN;
+    d = 1.0 / d;
+    double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < EPS) break;
+  }
+  return h;
+}
+
+__device__ inline void log_ibeta_pair(double x, double a, double b, double lb, double* lower, double* upper) {
+  if (x <= 0.0) {
+    *lower = -CUDART_INF;
+    *upper = 0.0;
+    return;
+  }
+  if (x >= 1.0) {
+    *lower = 0.0;
+    *upper = -CUDART_INF;
+    return;
+  }
+  double lbt = a * log(x) + b * log1p(-x) - lb;
+  if (x < (a + 1.0) / (a + b + 2.0)) {
+    double lo = lbt + log(betacf_d(a, b, x)) - log(a);
+    *lower = lo;
+    *upper = log1p(-exp(lo));
+  } else {
+    double up = lbt + log(betacf_d(b, a, 1.0 - x)) - log(b);
+    *upper = up;
+    *lower = log1p(-exp(up));
+  }
+}
+
+// norm_const2(d=w, c=v, m) through the overflow-free identity (needs v > 1):
+//   (w+1) log(m-1) - lbeta(w+1, v-1) - log I_{(m-1)/m}(w+1, v-1)
+// The reference evaluates log(d+1)+(d+c)log m - log 2F1(d+c,1;d+2;(m-1)/m) with GSL, which
+// overflows for clusters of ~10^3 members; both forms agree to <1e-14 rel
+// where the reference is finite (tests/test_oracle_known_answers.py).
+__device__ inline double norm_const2_d(double w, double v, double m) {
+  double a = w + 1.0, b = v - 1.0, lb = lbeta_d(a, b), lo, up;
+  log_ibeta_pair((m - 1.0) / m, a, b, lb, &lo, &up);
+  return a * log(m - 1.0) - lb - lo;
+}
+
+// logdensity_hig (split_merge.cpp:6-18)
+__device__ inline double logdensity_hig_d(double s, double v, double w, double m) {
+  double K = norm_const2_d(w, v, m);
+  return K - (v + w) * log(1.0 + exp(-1.0 / s) * (m - 1.0)) - (w + 1.0) / s - 2.0 * log(s);
+}
+
+// HIG(v,w,m) draw by inversion of the CDF in u = exp(-1/sigma):
+//   CDF(u) = I_x(w+1, v-1) / I_{(m-1)/m}(w+1, v-1),  x = u(m-1)/(1+u(m-1))
+// which is exactly what the reference's bisection branch solves (hyperg.cpp:221-287 with
+// lF_conK2 :183-217) and the law its Beta-rejection branch samples (hyperg.cpp:359-368).
+// Safeguarded Newton on the log of the smaller tail; returns u (sigma = -1/log u).
+__device__ inline double hig_inv_u_d(double Omega, double v, double w, double m) {
+  const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
+  const double lb = lbeta_d(a, b);
+  double ltot_lo, ltot_up;
+  log_ibeta_pair(xmax, a, b, lb, &ltot_lo, &ltot_up);
+  // target lower-tail probability P = Omega * I_tot ; upper Q = 1 - P = tail_tot + I_tot (1 - Omega)
+  const double lP = log(Omega) + ltot_lo;
+  const double Q = exp(ltot_up) + exp(ltot_lo) * (1.0 - Omega);
+  const bool use_lower = lP < -0.6931471805599453;  // P < 1/2
+  const double target = use_lower ? lP : log(Q);
+  double lo = 0.0, hi = xmax;
+  double x = a / (a + b);
+  if (!(x < xmax)) x = 0.5 * xmax;
+  if (!(x > 0.0)) x = 0.5 * xmax;
+  for (int it = 0; it < 200; it++) {
+    double l_lo, l_up;
+    log_ibeta_pair(x, a, b, lb, &l_lo, &l_up);
+    // g is increasing in x for the lower tail, decreasing for the upper tail
+    double g = (use_lower ? l_lo : l_up) - target;
+    bool below = use_lower ? (g < 0.0) : (g > 0.0);  // root lies to the right of x
+    if (below)
+      lo = x;
+    else
+      hi = x;
+    double lpdf = (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lb;
+    // d/dx log tail = +-pdf/tail
+    double dg = exp(lpdf - (use_lower ? l_lo : l_up));
+    if (!use_lower) dg = -dg;
+    double xn = x - g / dg;
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    double dx = fabs(xn - x);
+    x = xn;
+    if (dx <= 4e-16 * x || hi - lo <= 4e-16 * hi) break;
+  }
+  return x / ((m - 1.0) * (1.0 - x));
+}
+
+// ----------------------------------------------------------------------------
+// R's revsort (src/main/sort.c): heapsort into DESCENDING order carrying an index
+// array; the tie permutation is part of the contract for centre draws.
+// Small per-thread arrays (n <= SMG_MAX_LEVELS).
+// ----------------------------------------------------------------------------
+#define SMG_MAX_LEVELS 64
+
+__device__ inline void revsort_d(double* a0, int* ib0, int n) {
+  if (n <= 1) return;
+  double* a = a0 - 1;
+  int* ib = ib0 - 1;
+  int l = (n >> 1) + 1, ir = n, i, j, ii;
+  double ra;
+  for (;;) {
+    if (l > 1) {
+      l = l - 1;
+      ra = a[l];
+      ii = ib[l];
+    } else {
+      ra = a[ir];
+      ii = ib[ir];
+      a[ir] = a[1];
+      ib[ir] = ib[1];
+      if (--ir == 1) {
+        a[1] = ra;
+        ib[1] = ii;
+        return;
+      }
+    }
+    i = l;
+    j = l << 1;
+    while (j <= ir) {
+      if (j < ir && a[j] > a[j + 1]) ++j;
+      if (ra > a[j]) {
+        a[i] = a[j];
+        ib[i] = ib[j];
+        j += (i = j);
+      } else
+        j = ir + 1;
+    }
+    a[i] = ra;
+    ib[i] = ii;
+  }
+}
+
+// Rcpp::sample(x, 1, true, probs) for a short probability vector held by one thread
+// (centre draws, common_functions.cpp:195): normalise, revsort descending, cumulate,
+// first j < n-1 with u <= cum_j else n-1.  Returns the 0-based position. p[] is clobbered.
+__device__ inline int sample_probs_small(double* p, int n, double u) {
+  int perm[SMG_MAX_LEVELS];
+  double sum = 0.0;
+  for (int i = 0; i < n; i++) sum += p[i];
+  for (int i = 0; i < n; i++) {
+    p[i] /= sum;
+    perm[i] = i + 1;
+  }
+  revsort_d(p, perm, n);
+  for (int i = 1; i < n; i++) p[i] += p[i - 1];
+  int j;
+  for (j = 0; j < n - 1; j++)
+    if (u <= p[j]) break;
+  return perm[j] - 1;
+}
+
+}  // namespace smg

@@ -1,0 +1,915 @@
+// smg_kernels.cuh -- sm_100a kernels of the Neal-8 sweep and the centre/sigma update.
+//
+//   K1  hamming_ll_block_kernel   neal8.cpp:40-56   (existing-cluster columns, all observations)
+//       aux_ll_kernel             neal8.cpp:65-69,79-92 (auxiliary components from the pool)
+//   K2  neal8_scan_kernel         launcher.cpp:95-99 -> neal8.cpp:10-160 (one resident CTA)
+//       scan_finalize_*           label compaction after the pass
+//   K3  cluster_histogram_kernel  common_functions.cpp:480-493,572-579
+//   K4  phi_draw_kernel           common_functions.cpp:495-505,560,582-589 -> hyperg.cpp:346-378
+//       loglik_kernel             common_functions.cpp:379-401
+//
+// Data layout in HBM (all row-major, p padded to pp = multiple of 16):
+//   X      uint8  [n][pp]     category codes 1..m_j (0 in the padding)
+//   cen    uint8  [NS][pp]    cluster centres by slot (0 in the padding)
+//   sig    fp64   [NS][pp]    sigma
+//   isg    fp64   [NS][pp]    1/sigma (0 in the padding)
+//   sden   fp64   [NS]        sum_j log(1+(m_j-1)/exp(1/sigma_j))
+//   LL     fp64   [n][ldl]    LL[i][slot] = -sum_j [x_ij != c_j]*isg_j - sden
+#pragma once
+#include "smg_device.cuh"
+
+namespace smg {
+
+#define SMG_MAX_SLOTS 1024    // slot (column) capacity of the scan's shared-memory tables
+#define SMG_MAX_ENTRIES 256   // K + m_aux handled per allocation draw
+#define SMG_EPL (SMG_MAX_ENTRIES / 32)
+#define SMG_SCAN_WARPS 32
+
+enum StatusBits : int {
+  ST_OK = 0,
+  ST_SLOTS_EXHAUSTED = 1,    // more cluster births in one pass than free slots
+  ST_TOO_MANY_ENTRIES = 2,   // K + m_aux > SMG_MAX_ENTRIES
+  ST_WALKER = 4,             // Rcpp would have switched to Walker alias sampling (nc > 200)
+  ST_LL_COLS = 8,            // K exceeds the LL matrix column capacity
+  ST_BAD_PROB = 16,          // non-finite probability (Rcpp::sample would stop())
+  ST_VALIDATE = 32           // validate_state failure (common_functions.cpp:146-172)
+};
+
+// =============================================================================
+// K1: Hamming log-likelihood block.  Tile = 128 rows x 32 slots per CTA of 256 threads;
+// a warp owns 4 slots, a lane owns 4 rows (lane, lane+32, lane+64, lane+96); 16 fp64
+// accumulators per thread.  X and the per-slot tables are staged through shared memory in
+// j-tiles of 64 attributes: x words are read conflict-free (row stride 17 words), the centre
+// and 1/sigma words are warp-wide broadcasts.
+// Algorithmic bytes per row: pp (X) + 8*K (LL write); op count: K*p compare-adds.
+// =============================================================================
+#define LLB_ROWS 128
+#define LLB_SLOTS 32
+#define LLB_JT 64
+#define LLB_XS (LLB_JT / 4 + 1)  // padded row stride in words
+
+__global__ void __launch_bounds__(256) hamming_ll_block_kernel(const uint8_t* __restrict__ X, int n, int pp,
+                                                               const uint8_t* __restrict__ cen,
+                                                               const double* __restrict__ isg,
+                                                               const double* __restrict__ sden,
+                                                               const int* __restrict__ Kptr, double* __restrict__ LL,
+                                                               int ldl) {
+  const int K = *Kptr;
+  const int slot0 = blockIdx.y * LLB_SLOTS;
+  if (slot0 >= K) return;
+  const int row0 = blockIdx.x * LLB_ROWS;
+  __shared__ uint32_t sx[LLB_ROWS * LLB_XS];
+  __shared__ uint32_t sc[LLB_SLOTS * (LLB_JT / 4)];
+  __shared__ __align__(16) double sw[LLB_SLOTS * LLB_JT];
+  const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;  // wg: slot group (4 slots)
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
+
+  for (int j0 = 0; j0 < pp; j0 += LLB_JT) {
+    const int jt = min(LLB_JT, pp - j0);  // multiple of 16
+    // stage X tile: 128 rows x jt bytes, 16-byte chunks
+    for (int ch = tid; ch < LLB_ROWS * (LLB_JT / 16); ch += 256) {
+      int r = ch / (LLB_JT / 16), q = ch % (LLB_JT / 16);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row0 + r < n && q * 16 < jt) v = *reinterpret_cast<const uint4*>(X + (size_t)(row0 + r) * pp + j0 + q * 16);
+      uint32_t* d = &sx[r * LLB_XS + q * 4];
+      d[0] = v.x;
+      d[1] = v.y;
+      d[2] = v.z;
+      d[3] = v.w;
+    }
+    // stage centre tile
+    for (int ch = tid; ch < LLB_SLOTS * (LLB_JT / 16); ch += 256) {
+      int s = ch / (LLB_JT / 16), q = ch % (LLB_JT / 16);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (slot0 + s < K && q * 16 < jt) v = *reinterpret_cast<const uint4*>(cen + (size_t)(slot0 + s) * pp + j0 + q * 16);
+      *reinterpret_cast<uint4*>(&sc[s * (LLB_JT / 4) + q * 4]) = v;
+    }
+    // stage 1/sigma tile
+    for (int ch = tid; ch < LLB_SLOTS * (LLB_JT / 2); ch += 256) {
+      int s = ch / (LLB_JT / 2), q = ch % (LLB_JT / 2);
+      double2 v = make_double2(0.0, 0.0);
+      if (slot0 + s < K && q * 2 < jt) v = *reinterpret_cast<const double2*>(isg + (size_t)(slot0 + s) * pp + j0 + q * 2);
+      *reinterpret_cast<double2*>(&sw[s * LLB_JT + q * 2]) = v;
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int jw = 0; jw < LLB_JT / 4; jw++) {
+      uint32_t xw[4], cw[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) xw[r] = sx[(lane + 32 * r) * LLB_XS + jw];
+#pragma unroll
+      for (int c = 0; c < 4; c++) cw[c] = sc[(wg * 4 + c) * (LLB_JT / 4) + jw];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const double2 w01 = *reinterpret_cast<const double2*>(&sw[(wg * 4 + c) * LLB_JT + jw * 4]);
+        const double2 w23 = *reinterpret_cast<const double2*>(&sw[(wg * 4 + c) * LLB_JT + jw * 4 + 2]);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          uint32_t mm = __vcmpne4(xw[r], cw[c]);  // 0xff per mismatching byte
+          if (mm & 0x000000ffu) acc[r][c] += w01.x;
+          if (mm & 0x0000ff00u) acc[r][c] += w01.y;
+          if (mm & 0x00ff0000u) acc[r][c] += w23.x;
+          if (mm & 0xff000000u) acc[r][c] += w23.y;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // epilogue: each thread writes 4 consecutive doubles (one 32-byte sector) per row
+  double sd[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) sd[c] = (slot0 + wg * 4 + c < K) ? sden[slot0 + wg * 4 + c] : 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int row = row0 + lane + 32 * r;
+    if (row >= n) continue;
+    double* o = LL + (size_t)row * ldl + slot0 + wg * 4;
+    if (slot0 + wg * 4 + 3 < K && (ldl & 3) == 0) {
+      double4 v = make_double4(-acc[r][0] - sd[0], -acc[r][1] - sd[1], -acc[r][2] - sd[2], -acc[r][3] - sd[3]);
+      *reinterpret_cast<double4*>(o) = v;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (slot0 + wg * 4 + c < K) o[c] = -acc[r][c] - sd[c];
+    }
+  }
+}
+
+// One warp evaluates sum_j [x_j != c_j] * isg_j for one (row, parameter vector) pair.
+// Lanes take 8 attributes per 256-attribute chunk; butterfly reduction => every lane
+// returns the same value, and the value for a given (row, vector) is identical no matter
+// which kernel calls this (used for aux columns, columns born during a pass, member subsets).
+// (no __restrict__: the scan kernel reads parameter vectors it wrote earlier in the same launch,
+// so these loads must stay on the coherent path)
+__device__ __forceinline__ double warp_mismatch_dot(const uint8_t* xrow, const uint8_t* crow, const double* wrow, int pp,
+                                                    int lane) {
+  double acc = 0.0;
+  for (int j0 = lane * 8; j0 < pp; j0 += 256) {
+    uint2 xv = *reinterpret_cast<const uint2*>(xrow + j0);
+    uint2 cv = *reinterpret_cast<const uint2*>(crow + j0);
+    uint32_t m0 = __vcmpne4(xv.x, cv.x), m1 = __vcmpne4(xv.y, cv.y);
+    if (m0 | m1) {
+      const double2* w = reinterpret_cast<const double2*>(wrow + j0);
+      double2 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+      if (m0 & 0x000000ffu) acc += w0.x;
+      if (m0 & 0x0000ff00u) acc += w0.y;
+      if (m0 & 0x00ff0000u) acc += w1.x;
+      if (m0 & 0xff000000u) acc += w1.y;
+      if (m1 & 0x000000ffu) acc += w2.x;
+      if (m1 & 0x0000ff00u) acc += w2.y;
+      if (m1 & 0x00ff0000u) acc += w3.x;
+      if (m1 & 0xff000000u) acc += w3.y;
+    }
+  }
+  return warp_sum(acc);
+}
+
+// integer mismatch count (parity checks: bit-exact against the oracle)
+__global__ void mismatch_count_kernel(const uint8_t* __restrict__ X, int n, int pp, const uint8_t* __restrict__ cen,
+                                      int K, int* __restrict__ out) {
+  int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n * K) return;
+  int i = w / K, k = w % K;
+  int acc = 0;
+  for (int j0 = lane * 4; j0 < pp; j0 += 128) {
+    uint32_t xv = *reinterpret_cast<const uint32_t*>(X + (size_t)i * pp + j0);
+    uint32_t cv = *reinterpret_cast<const uint32_t*>(cen + (size_t)k * pp + j0);
+    acc += __popc(__vcmpne4(xv, cv)) >> 3;
+  }
+  acc = warp_sum_i(acc);
+  if (lane == 0) out[w] = acc;
+}
+
+// Auxiliary-component columns: for every observation i and aux slot a, draw the pool entry
+// (neal8.cpp:66: sample(pool_size,1)-1 = (int)(P*u+1)-1) and evaluate its log-likelihood.
+__global__ void __launch_bounds__(256) aux_ll_kernel(const uint8_t* __restrict__ X, int n, int pp, int m_aux,
+                                                     const uint8_t* __restrict__ pool_cen,
+                                                     const double* __restrict__ pool_isg,
+                                                     const double* __restrict__ pool_sden, long long pool_size,
+                                                     const double* __restrict__ tape, int tape_stride, RngKey key,
+                                                     double* __restrict__ LLaux, int* __restrict__ aux_e) {
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)n * m_aux) return;
+  const int i = (int)(w / m_aux), a = (int)(w % m_aux);
+  double u = get_u(tape, (size_t)i * tape_stride + a, key, U_POOL_IDX, (uint32_t)i, (uint32_t)a);
+  long long e = (long long)((double)pool_size * u + 1.0) - 1;
+  if (e >= pool_size) e = pool_size - 1;
+  double dot = warp_mismatch_dot(X + (size_t)i * pp, pool_cen + (size_t)e * pp, pool_isg + (size_t)e * pp, pp, lane);
+  if (lane == 0) {
+    LLaux[w] = -dot - pool_sden[e];
+    aux_e[w] = (int)e;
+  }
+}
+
+// =============================================================================
+// K2: Neal-8 allocation scan.  ONE resident CTA (32 warps).  The pass is sequential in
+// the observation index, but an observation whose draw re-selects its current cluster
+// changes nothing, so the CTA evaluates 32 consecutive observations per round against the
+// same state (one warp each), finds the first one whose draw changes the state ("event"),
+// applies it and restarts right after it.  Results are identical to the one-at-a-time scan.
+//
+// State kept in shared memory: member counts and their logs by slot, label<->slot maps.
+// Existing columns come from the precomputed LL block; a column born during the pass
+// (case 3/4) is evaluated on the fly from its parameter vector.
+// =============================================================================
+struct ScanArgs {
+  int n, pp, m_aux, ldl, K0cap;   // K0cap: number of valid LL columns (= K at pass start)
+  const uint8_t* X;
+  const double* LL;
+  const double* LLaux;
+  const int* aux_e;
+  const double* u_alloc;  // injected allocation uniforms (tape + m_aux, stride), or null
+  int u_stride;
+  RngKey key;
+  int* c;        // in: labels (== slots at pass start); out: slots (finalize maps back)
+  uint8_t* cen;  // slot-indexed parameter arrays
+  double* sig;
+  double* isg;
+  double* sden;
+  const uint8_t* pool_cen;
+  const double* pool_sig;
+  const double* pool_isg;
+  const double* pool_sden;
+  int* Kptr;      // in/out
+  int* counts;    // in: by label; out: by slot
+  int* slot2label;  // out [NS]
+  int NS;
+  double log_gamma_m;  // log(gamma/m)  (neal8.cpp:78)
+  int* status;
+  unsigned long long* stats;  // [0] rounds, [1] events, [2] births, [3] deaths
+};
+
+#define EVT_NONE (-1)
+
+__global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(ScanArgs A) {
+  __shared__ int s_cnt[SMG_MAX_SLOTS];
+  __shared__ double s_logc[SMG_MAX_SLOTS];
+  __shared__ double s_logcm1[SMG_MAX_SLOTS];
+  __shared__ int s_l2s[SMG_MAX_SLOTS];
+  __shared__ int s_s2l[SMG_MAX_SLOTS];
+  __shared__ int s_evt[SMG_SCAN_WARPS];
+  __shared__ int s_K, s_i0, s_next, s_err;
+  __shared__ unsigned long long s_stats[4];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = A.n, pp = A.pp, m = A.m_aux;
+  const int K0 = *A.Kptr;
+
+  for (int s = tid; s < SMG_MAX_SLOTS; s += blockDim.x) {
+    int cnt = (s < K0) ? A.counts[s] : 0;
+    s_cnt[s] = cnt;
+    s_logc[s] = cnt > 0 ? log((double)cnt) : -CUDART_INF;
+    s_logcm1[s] = cnt > 1 ? log((double)(cnt - 1)) : -CUDART_INF;
+    s_l2s[s] = s;
+    s_s2l[s] = (s < K0) ? s : -1;
+  }
+  if (tid == 0) {
+    s_K = K0;
+    s_i0 = 0;
+    s_next = K0;
+    s_err = 0;
+    s_stats[0] = s_stats[1] = s_stats[2] = s_stats[3] = 0;
+    if (K0 + m > SMG_MAX_ENTRIES) s_err |= ST_TOO_MANY_ENTRIES;
+    if (K0 > A.K0cap) s_err |= ST_LL_COLS;
+  }
+  __syncthreads();
+  if (s_err) {
+    if (tid == 0) atomicOr(A.status, s_err);
+    return;
+  }
+
+  for (;;) {
+    const int i0 = s_i0;
+    if (i0 >= n) break;
+    const int i = i0 + warp;
+    const int K = s_K;
+    const int ne = K + m;
+    int code = EVT_NONE;
+    if (i < n && ne <= SMG_MAX_ENTRIES) {
+      const int old_slot = A.c[i];
+      const bool singleton = (s_cnt[old_slot] == 1);
+      const uint8_t* xrow = A.X + (size_t)i * pp;
+      double lg[SMG_EPL];
+      double ll_own = 0.0;
+      // ---- existing clusters (neal8.cpp:40-56)
+#pragma unroll
+      for (int q = 0; q < SMG_EPL; q++) {
+        lg[q] = -CUDART_INF;
+        if (q * 32 >= K) continue;
+        const int e = q * 32 + lane;
+        int slot = (e < K) ? s_l2s[e] : -1;
+        double ll = 0.0;
+        if (slot >= 0 && slot < K0) ll = A.LL[(size_t)i * A.ldl + slot];
+        // columns born during this pass: evaluate on the fly, one at a time, whole warp
+        unsigned dyn = __ballot_sync(SMG_FULL, slot >= K0);
+        while (dyn) {
+          int src = __ffs(dyn) - 1;
+          dyn &= dyn - 1;
+          int ds = __shfl_sync(SMG_FULL, slot, src);
+          double dot = warp_mismatch_dot(xrow, A.cen + (size_t)ds * pp, A.isg + (size_t)ds * pp, pp, lane);
+          if (lane == src) ll = -dot - A.sden[ds];
+        }
+        if (slot >= 0) {
+          const bool own = (slot == old_slot);
+          const int cx = s_cnt[slot] - (own ? 1 : 0);
+          if (own) ll_own = ll;
+          lg[q] = (cx > 0) ? ((own ? s_logcm1[slot] : s_logc[slot]) + ll) : -CUDART_INF;
+        }
+      }
+      if (singleton) {  // own parameters become aux slot 0 (neal8.cpp:72-75)
+        unsigned who = __ballot_sync(SMG_FULL, ll_own != 0.0);
+        // ll_own is set by exactly one lane; LL is strictly negative so != 0 identifies it
+        int src = who ? (__ffs(who) - 1) : 0;
+        ll_own = shfl_d(ll_own, src);
+      }
+      // ---- auxiliary components (neal8.cpp:78-92)
+#pragma unroll
+      for (int q = 0; q < SMG_EPL; q++) {
+        const int e = q * 32 + lane;
+        if (e >= K && e < ne) {
+          const int a = e - K;
+          double ll = (singleton && a == 0) ? ll_own : A.LLaux[(size_t)i * m + a];
+          lg[q] = A.log_gamma_m + ll;
+        }
+      }
+      // ---- max, exp, sum  (neal8.cpp:95-96)
+      uint64_t mykey = 0;
+      int myarg = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < SMG_EPL; q++) {
+        if (q * 32 >= ne) continue;
+        const int e = q * 32 + lane;
+        if (e < ne) {
+          uint64_t k = sort_key(lg[q]);
+          if (k > mykey) {
+            mykey = k;
+            myarg = e;
+          }
+        }
+      }
+      const uint64_t maxkey = warp_max_key(mykey);
+      const double M = key_to_double(maxkey);
+      // smallest index attaining the max
+      const int argmax = (int)__reduce_min_sync(SMG_FULL, (unsigned)((mykey == maxkey) ? myarg : 0x7fffffff));
+      double pe[SMG_EPL];
+      double lsum = 0.0;
+      bool need_exp = false;
+#pragma unroll
+      for (int q = 0; q < SMG_EPL; q++) {
+        pe[q] = 0.0;
+        if (q * 32 >= ne) continue;
+        const int e = q * 32 + lane;
+        if (e < ne) {
+          double d = lg[q] - M;
+          if (d == 0.0)
+            pe[q] = 1.0;
+          else if (d > -746.0)
+            need_exp = true;
+        }
+      }
+      if (__any_sync(SMG_FULL, need_exp)) {
+#pragma unroll
+        for (int q = 0; q < SMG_EPL; q++) {
+          if (q * 32 >= ne) continue;
+          const int e = q * 32 + lane;
+          if (e < ne) {
+            double d = lg[q] - M;
+            if (d != 0.0 && d > -746.0) pe[q] = exp(d);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < SMG_EPL; q++) lsum += pe[q];
+      const double S = warp_sum(lsum);
+      const double u = get_u(A.u_alloc, (size_t)i * A.u_stride, A.key, U_ALLOC, (uint32_t)i, 0u);
+      const double T = u * S;  // compare against the cumulative sums of the unnormalised weights
+      int new_e;
+      if (!(M > -CUDART_INF) || !(S == S)) {
+        new_e = -2;  // all -Inf or NaN: Rcpp::sample would stop()
+      } else if (T <= 1.0) {
+        new_e = argmax;  // first entry of the descending order already covers u
+      } else {
+        // Rcpp::sample semantics: walk the probabilities in DESCENDING order and return the
+        // first entry whose cumulative sum reaches u.  before(y,x): y precedes x in that order.
+        double G[SMG_EPL];
+#pragma unroll
+        for (int q = 0; q < SMG_EPL; q++) G[q] = 0.0;
+#pragma unroll
+        for (int qy = 0; qy < SMG_EPL; qy++) {
+          if (qy * 32 >= ne) continue;
+          unsigned sig = __ballot_sync(SMG_FULL, pe[qy] > 0.0);
+          while (sig) {
+            int src = __ffs(sig) - 1;
+            sig &= sig - 1;
+            double py = shfl_d(pe[qy], src);
+            int ey = qy * 32 + src;
+#pragma unroll
+            for (int q = 0; q < SMG_EPL; q++) {
+              int ex = q * 32 + lane;
+              if (py > pe[q] || (py == pe[q] && ey < ex)) G[q] += py;
+            }
+          }
+        }
+        // candidate = entry with u*S <= G + p, largest p first (smallest index among ties)
+        uint64_t bestk = 0;
+        int beste = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < SMG_EPL; q++) {
+          int ex = q * 32 + lane;
+          if (ex < ne && pe[q] > 0.0 && T <= G[q] + pe[q]) {
+            uint64_t k = sort_key(pe[q]);
+            if (k > bestk || (k == bestk && ex < beste)) {
+              bestk = k;
+              beste = ex;
+            }
+          }
+        }
+        uint64_t wk = warp_max_key(bestk);
+        if (wk == 0) {
+          // fall-through of the reference loop: last entry of the descending order
+          // (smallest probability, largest index among ties)
+          uint64_t mink = ~0ull;
+          int mine = -1;
+#pragma unroll
+          for (int q = 0; q < SMG_EPL; q++) {
+            int ex = q * 32 + lane;
+            if (ex < ne) {
+              uint64_t k = sort_key(pe[q]);
+              if (k < mink || (k == mink && ex > mine)) {
+                mink = k;
+                mine = ex;
+              }
+            }
+          }
+          uint64_t wmin = ~warp_max_key(~mink);
+          new_e = (int)__reduce_max_sync(SMG_FULL, (unsigned)((mink == wmin) ? mine : 0));
+        } else {
+          new_e = (int)__reduce_min_sync(SMG_FULL, (unsigned)((bestk == wk) ? beste : 0x7fffffff));
+        }
+      }
+      // ---- does the draw change the state?
+      if (new_e == -2) {
+        code = -2;
+      } else if (new_e < K) {
+        int ns = s_l2s[new_e];
+        code = (ns != old_slot) ? new_e : EVT_NONE;
+      } else {
+        code = (singleton && new_e == K) ? EVT_NONE : new_e;  // singleton re-drawing its own phi: no-op
+      }
+    } else if (i < n) {
+      code = -3;
+    }
+    if (lane == 0) s_evt[warp] = code;
+    __syncthreads();
+    // ---- first event of the round, in observation order
+    int ev = s_evt[lane];
+    unsigned evm = __ballot_sync(SMG_FULL, ev != EVT_NONE);
+    if (evm == 0) {
+      if (tid == 0) {
+        s_i0 = i0 + SMG_SCAN_WARPS;
+        s_stats[0]++;
+      }
+      __syncthreads();
+      continue;
+    }
+    const int first = __ffs(evm) - 1;
+    const int new_e = __shfl_sync(SMG_FULL, ev, first);
+    const int ie = i0 + first;
+    if (new_e < 0) {  // error: stop the pass
+      if (tid == 0) atomicOr(A.status, new_e == -2 ? ST_BAD_PROB : ST_TOO_MANY_ENTRIES);
+      break;
+    }
+    const int old_slot = A.c[ie];
+    const bool singleton = (s_cnt[old_slot] == 1);
+    const int Kc = s_K;
+    int new_slot;
+    if (new_e < Kc) {
+      new_slot = s_l2s[new_e];
+    } else {
+      new_slot = s_next;  // birth (case 3) or parameter replacement (case 4)
+      if (new_slot >= A.NS || new_slot >= SMG_MAX_SLOTS) {
+        if (tid == 0) atomicOr(A.status, ST_SLOTS_EXHAUSTED);
+        break;
+      }
+      // copy the auxiliary component's parameters into the new slot
+      const int a = new_e - Kc;
+      const long long e = A.aux_e[(size_t)ie * m + a];
+      for (int j = tid; j < pp; j += blockDim.x) {
+        A.cen[(size_t)new_slot * pp + j] = A.pool_cen[(size_t)e * pp + j];
+        A.sig[(size_t)new_slot * pp + j] = A.pool_sig[(size_t)e * pp + j];
+        A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
+      }
+      if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
+    }
+    __syncthreads();  // everyone has read the pre-event state
+    if (tid == 0) {
+      s_stats[0]++;
+      s_stats[1]++;
+      A.c[ie] = new_slot;
+      if (new_e < Kc) {
+        s_cnt[new_slot]++;
+        s_logcm1[new_slot] = s_logc[new_slot];
+        s_logc[new_slot] = log((double)s_cnt[new_slot]);
+        if (!singleton) {  // case 1 (neal8.cpp:107-112)
+          int c0 = --s_cnt[old_slot];
+          s_logc[old_slot] = s_logcm1[old_slot];
+          s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+        } else {  // case 2 (neal8.cpp:115-137): last label moves into the hole
+          s_cnt[old_slot] = 0;
+          s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
+          int lab = s_s2l[old_slot];
+          int last_slot = s_l2s[Kc - 1];
+          s_l2s[lab] = last_slot;
+          s_s2l[last_slot] = lab;
+          s_s2l[old_slot] = -1;
+          if (lab == Kc - 1) s_s2l[last_slot] = -1;  // the dying cluster was the last label
+          s_K = Kc - 1;
+          s_stats[3]++;
+        }
+      } else {
+        s_next = new_slot + 1;
+        s_cnt[new_slot] = 1;
+        s_logc[new_slot] = 0.0;
+        s_logcm1[new_slot] = -CUDART_INF;
+        if (!singleton) {  // case 3 (neal8.cpp:140-150)
+          int c0 = --s_cnt[old_slot];
+          s_logc[old_slot] = s_logcm1[old_slot];
+          s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+          s_l2s[Kc] = new_slot;
+          s_s2l[new_slot] = Kc;
+          s_K = Kc + 1;
+          s_stats[2]++;
+        } else {  // case 4 (neal8.cpp:153-159): same label, new parameters
+          int lab = s_s2l[old_slot];
+          s_cnt[old_slot] = 0;
+          s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
+          s_s2l[old_slot] = -1;
+          s_l2s[lab] = new_slot;
+          s_s2l[new_slot] = lab;
+        }
+      }
+      s_i0 = ie + 1;
+    }
+    __threadfence_block();
+    __syncthreads();
+  }
+  __syncthreads();
+  // publish: K, counts by slot, slot->label map
+  for (int s = tid; s < A.NS && s < SMG_MAX_SLOTS; s += blockDim.x) {
+    A.counts[s] = s_cnt[s];
+    A.slot2label[s] = s_s2l[s];
+  }
+  if (tid == 0) {
+    *A.Kptr = s_K;
+    if (A.stats)
+      for (int q = 0; q < 4; q++) A.stats[q] += s_stats[q];
+  }
+}
+
+// After the pass: c[i] <- label of its slot; parameters gathered into label order (dst buffers).
+__global__ void scan_finalize_labels_kernel(int* __restrict__ c, int n, const int* __restrict__ slot2label) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) c[i] = slot2label[c[i]];
+}
+__global__ void scan_finalize_params_kernel(const int* __restrict__ slot2label, int NS, int pp,
+                                            const uint8_t* __restrict__ cen_s, const double* __restrict__ sig_s,
+                                            const double* __restrict__ isg_s, const double* __restrict__ sden_s,
+                                            const int* __restrict__ cnt_s, uint8_t* __restrict__ cen_d,
+                                            double* __restrict__ sig_d, double* __restrict__ isg_d,
+                                            double* __restrict__ sden_d, int* __restrict__ cnt_d) {
+  int s = blockIdx.x;
+  if (s >= NS) return;
+  int lab = slot2label[s];
+  if (lab < 0) return;
+  for (int j = threadIdx.x; j < pp; j += blockDim.x) {
+    cen_d[(size_t)lab * pp + j] = cen_s[(size_t)s * pp + j];
+    sig_d[(size_t)lab * pp + j] = sig_s[(size_t)s * pp + j];
+    isg_d[(size_t)lab * pp + j] = isg_s[(size_t)s * pp + j];
+  }
+  if (threadIdx.x == 0) {
+    sden_d[lab] = sden_s[s];
+    cnt_d[lab] = cnt_s[s];
+  }
+}
+
+// =============================================================================
+// K3: category histogram H[k][j][a] = #{i : c_i = k, x_ij = a+1} and member counts.
+// One thread per (observation, 16-attribute chunk); integer atomics into L2.
+// =============================================================================
+__global__ void __launch_bounds__(256) cluster_histogram_kernel(const uint8_t* __restrict__ X, int n, int pp,
+                                                                const int* __restrict__ c, int mmax,
+                                                                int* __restrict__ H, int* __restrict__ counts) {
+  const int chunks = pp / 16;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * chunks) return;
+  const int i = (int)(t / chunks), q = (int)(t % chunks);
+  const int k = c[i];
+  if (q == 0) atomicAdd(&counts[k], 1);
+  uint4 v = *reinterpret_cast<const uint4*>(X + (size_t)i * pp + q * 16);
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  int* Hk = H + ((size_t)k * pp + q * 16) * mmax;
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
+    if (x) atomicAdd(&Hk[b * mmax + (x - 1)], 1);
+  }
+}
+
+// histogram of a member subset split in two groups by z (split-merge launch states):
+// rows = S[0..nS) with group z[s], plus the two anchors i1 (group 0) and i2 (group 1).
+__global__ void __launch_bounds__(256) subset_histogram_kernel(const uint8_t* __restrict__ X, int pp,
+                                                               const int* __restrict__ S,
+                                                               const int* __restrict__ nSptr,
+                                                               const int* __restrict__ z, const int* __restrict__ anchors,
+                                                               int mmax, int* __restrict__ H2, int* __restrict__ cnt2) {
+  const int chunks = pp / 16;
+  const int nS = *nSptr;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)(nS + 2) * chunks) return;
+  const int r = (int)(t / chunks), q = (int)(t % chunks);
+  int row, g;
+  if (r < nS) {
+    row = S[r];
+    g = z ? z[r] : 0;
+  } else {
+    row = anchors[r - nS];
+    g = z ? (r - nS) : 0;
+  }
+  if (q == 0) atomicAdd(&cnt2[g], 1);
+  uint4 v = *reinterpret_cast<const uint4*>(X + (size_t)row * pp + q * 16);
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  int* Hk = H2 + ((size_t)g * pp + q * 16) * mmax;
+#pragma unroll
+  for (int b = 0; b < 16; b++) {
+    int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
+    if (x) atomicAdd(&Hk[b * mmax + (x - 1)], 1);
+  }
+}
+
+// =============================================================================
+// K4: per-(cluster, attribute) centre and sigma draws (update_phi).
+// A "job" updates one cluster: histogram row `hist`, current sigma from slot `src`,
+// result written to slot `dst`.  jobs == nullptr => job k updates cluster k in place.
+//   centre ~ Rcpp::sample(1..m_j, probs = softmax(-(n_k - freq)/sigma_j))   (:495-505, :195)
+//   s = freq[centre];  sigma ~ HIG(v_j + s, w_j + n_k - s, m_j)             (:582-589)
+// Prior draws (sample_center_1_cluster / sample_sigma_1_cluster without data,
+// common_functions.cpp:199,232) use count = 0 with `prior = 1`.
+// =============================================================================
+struct PhiJob {
+  int hist, src, dst, cnt_idx;
+};
+
+struct PhiArgs {
+  int pp, p, mmax;
+  const int* attr;
+  const double* v;
+  const double* w;
+  const int* H;
+  const int* counts;
+  const PhiJob* jobs;  // device array or null
+  const int* njobs_ptr;  // device count (e.g. K) when jobs == null
+  int njobs;             // host count when jobs != null
+  const uint8_t* cen_src;
+  const double* sig_src;
+  uint8_t* cen;
+  double* sig;
+  double* isg;
+  double* den;   // [NS][pp] per-attribute log-normaliser (summed into sden by phi_sden_kernel)
+  const double* u_center;  // injected uniforms [job][p] (stride u_stride) or null
+  const double* u_sigma;
+  int u_stride;
+  RngKey key;
+  int prior;    // 1 => draw from the prior (no data)
+  const int* enable;  // optional device flag: skip the whole launch when *enable == 0
+  int* status;
+};
+
+__global__ void __launch_bounds__(128) phi_draw_kernel(PhiArgs A) {
+  if (A.enable && *A.enable == 0) return;
+  const int job = blockIdx.y;
+  const int nj = A.jobs ? A.njobs : *A.njobs_ptr;
+  if (job >= nj) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= A.pp) return;
+  PhiJob J;
+  if (A.jobs)
+    J = A.jobs[job];
+  else {
+    J.hist = J.src = J.dst = J.cnt_idx = job;
+  }
+  const size_t o = (size_t)J.dst * A.pp + j;
+  if (j >= A.p) {  // padding attributes
+    A.cen[o] = 0;
+    A.sig[o] = 1.0;
+    A.isg[o] = 0.0;
+    A.den[o] = 0.0;
+    return;
+  }
+  const int m = A.attr[j];
+  const int nk = A.prior ? 0 : A.counts[J.cnt_idx];
+  if (!A.prior && nk == 0) return;  // empty cluster: untouched (common_functions.cpp:547)
+  int center;
+  double s_match = 0.0;
+  const double uc = get_u(A.u_center, (size_t)job * A.u_stride + j, A.key, U_CENTER, (uint32_t)job, (uint32_t)j);
+  if (A.prior) {
+    center = (int)((double)m * uc + 1.0);  // sample(m_j, 1): (int)(m*u + 1)
+    if (center > m) center = m;
+  } else {
+    const double sg = A.sig_src[(size_t)J.src * A.pp + j];
+    const int* h = A.H + ((size_t)J.hist * A.pp + j) * A.mmax;
+    double pt[SMG_MAX_LEVELS];
+    double mx = -CUDART_INF;
+    for (int a = 0; a < m; a++) {
+      pt[a] = -((double)nk - (double)h[a]) / sg;
+      mx = pt[a] > mx ? pt[a] : mx;
+    }
+    double sum = 0.0;
+    for (int a = 0; a < m; a++) {
+      pt[a] = exp(pt[a] - mx);
+      sum += pt[a];
+    }
+    for (int a = 0; a < m; a++) pt[a] = pt[a] / sum;
+    center = 1 + sample_probs_small(pt, m, uc);
+    s_match = (double)h[center - 1];
+  }
+  const double vv = A.v[j] + s_match;
+  const double ww = A.w[j] + (double)nk - s_match;
+  const double us = get_u(A.u_sigma, (size_t)job * A.u_stride + j, A.key, U_SIGMA, (uint32_t)job, (uint32_t)j);
+  const double uu = hig_inv_u_d(us, vv, ww, (double)m);
+  const double sigma = -1.0 / log(uu);
+  A.cen[o] = (uint8_t)center;
+  A.sig[o] = sigma;
+  A.isg[o] = 1.0 / sigma;
+  A.den[o] = hamming_den(sigma, m);
+}
+
+// sden[slot] = sum_j den[slot][j] in a fixed order (one CTA per job, tree in shared memory)
+__global__ void __launch_bounds__(256) phi_sden_kernel(const PhiJob* jobs, const int* njobs_ptr, int njobs, int pp,
+                                                       const double* __restrict__ den, double* __restrict__ sden,
+                                                       const int* enable) {
+  if (enable && *enable == 0) return;
+  const int job = blockIdx.x;
+  const int nj = jobs ? njobs : *njobs_ptr;
+  if (job >= nj) return;
+  const int dst = jobs ? jobs[job].dst : job;
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < pp; j += 256) acc += den[(size_t)dst * pp + j];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sden[dst] = sh[0];
+}
+
+// derive isg / den / sden from (cen, sig) for slots [0, nslots): used after host uploads
+__global__ void __launch_bounds__(256) derive_terms_kernel(int nslots, int pp, int p, const int* __restrict__ attr,
+                                                           const double* __restrict__ sig, double* __restrict__ isg,
+                                                           double* __restrict__ den, double* __restrict__ sden) {
+  const int s = blockIdx.x;
+  if (s >= nslots) return;
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int j = threadIdx.x; j < pp; j += 256) {
+    size_t o = (size_t)s * pp + j;
+    double d = 0.0, w = 0.0;
+    if (j < p) {
+      double sg = sig[o];
+      w = 1.0 / sg;
+      d = hamming_den(sg, attr[j]);
+    }
+    isg[o] = w;
+    if (den) den[o] = d;
+    acc += d;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) sden[s] = sh[0];
+}
+
+// =============================================================================
+// full-data log-likelihood (common_functions.cpp:379-401): one warp per observation,
+// per-CTA partials, then a fixed-order final reduction => run-to-run deterministic.
+// =============================================================================
+__global__ void __launch_bounds__(256) loglik_partial_kernel(const uint8_t* __restrict__ X, int n, int pp,
+                                                             const int* __restrict__ c,
+                                                             const uint8_t* __restrict__ cen,
+                                                             const double* __restrict__ isg,
+                                                             const double* __restrict__ sden,
+                                                             double* __restrict__ partial) {
+  __shared__ double sh[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double acc = 0.0;
+  for (int i = blockIdx.x * 8 + warp; i < n; i += gridDim.x * 8) {
+    int k = c[i];
+    double dot = warp_mismatch_dot(X + (size_t)i * pp, cen + (size_t)k * pp, isg + (size_t)k * pp, pp, lane);
+    acc += -dot - sden[k];
+  }
+  if (lane == 0) sh[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int q = 0; q < 8; q++) t += sh[q];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) reduce_final_kernel(const double* __restrict__ partial, int np,
+                                                           double* __restrict__ out) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int q = threadIdx.x; q < np; q += 256) acc += partial[q];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = sh[0];
+}
+
+// =============================================================================
+// data ingest / pool
+// =============================================================================
+// fp64 column-major R matrix -> uint8 row-major padded; flags non-integer / out-of-range codes
+__global__ void ingest_colmajor_kernel(const double* __restrict__ Xd, int n, int p, int pp,
+                                       const int* __restrict__ attr, uint8_t* __restrict__ X, int* __restrict__ bad) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * pp) return;
+  int i = (int)(t / pp), j = (int)(t % pp);
+  uint8_t o = 0;
+  if (j < p) {
+    double v = Xd[(size_t)i + (size_t)n * j];
+    int iv = (int)v;
+    if ((double)iv != v || iv < 1 || iv > attr[j] || iv > 255)
+      atomicAdd(bad, 1);
+    else
+      o = (uint8_t)iv;
+  }
+  X[t] = o;
+}
+
+// prior pool entries (launcher.cpp:67-77,123-129): centre ~ U{1..m_j}, sigma ~ HIG(v_j,w_j,m_j)
+__global__ void __launch_bounds__(128) pool_draw_kernel(long long pool_size, int pp, int p, const int* __restrict__ attr,
+                                                        const double* __restrict__ v, const double* __restrict__ w,
+                                                        RngKey key, uint8_t* __restrict__ pcen,
+                                                        double* __restrict__ psig, double* __restrict__ pisg,
+                                                        double* __restrict__ pden) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= pool_size * pp) return;
+  long long e = t / pp;
+  int j = (int)(t % pp);
+  if (j >= p) {
+    pcen[t] = 0;
+    psig[t] = 1.0;
+    pisg[t] = 0.0;
+    pden[t] = 0.0;
+    return;
+  }
+  const int m = attr[j];
+  // 64-bit entry index split over the two counter words
+  uint32_t o[4];
+  philox4x32_10((uint32_t)e, (uint32_t)(e >> 32) | ((uint32_t)j << 8), U_POOL_CENTER | (key.sub << 8), key.sweep, key.k0,
+                key.k1, o);
+  double uc = u01_from_bits(o[0], o[1]), us = u01_from_bits(o[2], o[3]);
+  int center = (int)((double)m * uc + 1.0);
+  if (center > m) center = m;
+  double uu = hig_inv_u_d(us, v[j], w[j], (double)m);
+  double sigma = -1.0 / log(uu);
+  pcen[t] = (uint8_t)center;
+  psig[t] = sigma;
+  pisg[t] = 1.0 / sigma;
+  pden[t] = hamming_den(sigma, m);
+}
+// per-entry sum of den (one warp per entry, fixed order)
+__global__ void pool_sden_kernel(long long pool_size, int pp, const double* __restrict__ pden,
+                                 double* __restrict__ psden) {
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= pool_size) return;
+  double acc = 0.0;
+  for (int j = lane; j < pp; j += 32) acc += pden[(size_t)w * pp + j];
+  acc = warp_sum(acc);
+  if (lane == 0) psden[w] = acc;
+}
+
+// initial labels: sample(L, n, replace) - 1 (common_functions.cpp:174-183)
+__global__ void init_assign_kernel(int n, int L, const double* __restrict__ u_inj, RngKey key, int* __restrict__ c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double u = get_u(u_inj, i, key, U_INIT_ASSIGN, (uint32_t)i, 0u);
+  int l = (int)((double)L * u + 1.0) - 1;
+  c[i] = l >= L ? L - 1 : l;
+}
+
+}  // namespace smg

@@ -1,0 +1,93 @@
+"""End-to-end: the run_markov_chain mirror (code/launcher.cpp:7-174) on the zoo data and on a synthetic
+mixture; posterior summaries agree with the oracle within Monte-Carlo error; argument errors surface."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from helpers import Problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _zoo():
+    from split_and_merge_gibbs_sampling_b200.synth import zoo_dataset
+    return zoo_dataset(os.path.join(os.path.dirname(__file__), "golden", "zoo.data"))
+
+
+def test_run_markov_chain_result_shape_matches_reference_list():
+    from split_and_merge_gibbs_sampling_b200 import run_markov_chain
+    X, attr, v, w, g, gt = _zoo()
+    res = run_markov_chain(X, attr, g, v, w, m=3, iterations=20, L=5, burnin=10, t=3, r=3, neal8=True, split_merge=True,
+                           seed=7)
+    assert set(res) >= {"total_cls", "c_i", "centers", "sigmas", "loglikelihood", "final_ass", "time", "accepted"}
+    assert len(res["total_cls"]) == 20 and len(res["c_i"]) == 20 and res["loglikelihood"].shape == (20,)
+    for it in range(20):
+        K = res["total_cls"][it]
+        assert len(res["centers"][it]) == K and len(res["sigmas"][it]) == K
+        c = res["c_i"][it]
+        assert c.min() == 0 and c.max() == K - 1 and len(np.unique(c)) == K  # validate_state invariant
+        for k in range(K):
+            assert np.all(res["centers"][it][k] >= 1) and np.all(res["centers"][it][k] <= attr)
+            assert np.all(res["sigmas"][it][k] > 0)
+    # log-likelihood of the snapshot is reproducible by the oracle from the same state (1e-12 rel)
+    d = orc.OracleData(X, attr, g, v, w)
+    it = 19
+    ll = orc.loglik(d, res["c_i"][it], np.array(res["centers"][it]), np.array(res["sigmas"][it]))
+    assert abs(ll - res["loglikelihood"][it]) <= 1e-12 * abs(ll)
+    assert np.array_equal(res["final_ass"], res["c_i"][-1])
+
+
+def test_zoo_posterior_matches_oracle_within_mc_error():
+    from sklearn.metrics import adjusted_rand_score
+    from split_and_merge_gibbs_sampling_b200 import run_markov_chain
+    X, attr, v, w, g, gt = _zoo()
+    d = orc.OracleData(X, attr, g, v, w)
+    k_gpu, k_cpu, ari_gpu, ari_cpu, ll_gpu, ll_cpu = [], [], [], [], [], []
+    for seed in range(1, 6):
+        res = run_markov_chain(X, attr, g, v, w, m=3, iterations=300, L=10, burnin=300, t=10, r=10, neal8=True,
+                               split_merge=True, seed=seed, c_i=np.arange(101) % 10)
+        k_gpu.append(np.mean(res["total_cls"]))
+        ari_gpu.append(adjusted_rand_score(gt, res["final_ass"]))
+        ll_gpu.append(np.mean(res["loglikelihood"]))
+        r = orc.run_chain(d, 3, 300, 10, np.arange(101) % 10, 300, 10, 10, True, True, seed=seed)
+        k_cpu.append(np.mean(r["total_cls"]))
+        ari_cpu.append(adjusted_rand_score(gt, r["final_ass"]))
+        ll_cpu.append(np.mean(r["loglikelihood"]))
+    # means over 5 seeds agree within 3 standard errors (plus a small floor)
+    def close(a, b, floor):
+        se = np.sqrt(np.var(a, ddof=1) / len(a) + np.var(b, ddof=1) / len(b))
+        return abs(np.mean(a) - np.mean(b)) <= 3 * se + floor
+    assert close(k_gpu, k_cpu, 0.5), (k_gpu, k_cpu)
+    assert close(ll_gpu, ll_cpu, 8.0), (ll_gpu, ll_cpu)
+    assert np.mean(ari_gpu) > 0.6 and np.mean(ari_cpu) > 0.6
+
+
+def test_synthetic_mixture_recovers_truth():
+    from sklearn.metrics import adjusted_rand_score
+    from split_and_merge_gibbs_sampling_b200 import Chain
+    pb = Problem(5000, 64, 4, 10, seed=3)
+    ch = Chain(pb.X.astype(np.float64), pb.attr, 1.0, pb.v, pb.w, m=3, L=10, neal8=True, split_merge=True, seed=5,
+               compact_init=True)
+    ch.step(30)
+    s = ch.snapshot()
+    assert adjusted_rand_score(pb.labels, s["c_i"]) > 0.95
+    assert 8 <= s["K"] <= 14
+    st = ch.stats()
+    assert st["sweeps"] == 30 and st["launches"] > 0
+    ch.close()
+
+
+def test_argument_errors():
+    from split_and_merge_gibbs_sampling_b200 import Chain, SmgError
+    X = np.array([[1, 2], [2, 1], [1, 1], [2, 2]], dtype=np.float64)
+    with pytest.raises(SmgError, match="codes"):
+        Chain(np.array([[1, 3], [2, 1], [1, 1], [2, 2]], dtype=np.float64), [2, 2], 1.0, [6, 6], [0.25, 0.25])
+    with pytest.raises(SmgError, match="v\\[j\\] must be > 1"):
+        Chain(X, [2, 2], 1.0, [0.5, 6], [0.25, 0.25])
+    with pytest.raises(SmgError, match="State validation failed"):
+        Chain(X, [2, 2], 1.0, [6, 6], [0.25, 0.25], c_i=[0, 0, 2, 2])
+    ch = Chain(X, [2, 2], 1.0, [6, 6], [0.25, 0.25], c_i=[5, 5, 6, 6])  # any base, shifted by min (launcher.cpp:34-37)
+    assert ch.snapshot()["K"] == 2
+    ch.close()

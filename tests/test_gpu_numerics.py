@@ -1,0 +1,70 @@
+"""Device special functions against the golden values and the oracle (fp64, tolerances stated)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "known_answers.json")))
+
+
+def test_hig_inverse_cdf_golden():
+    from split_and_merge_gibbs_sampling_b200 import hig_inv_u
+    g = G["hig_inv_u"]
+    u = hig_inv_u([r["omega"] for r in g], [r["v"] for r in g], [r["w"] for r in g], [float(r["m"]) for r in g])
+    ref = np.array([r["u"] for r in g])
+    assert np.max(np.abs(u - ref)) < 1e-13
+
+
+def test_hig_inverse_cdf_vs_reference_bisection():
+    # hyperg.cpp:221-287 stops at a bracket of 1e-9: the device root must lie within that width
+    from split_and_merge_gibbs_sampling_b200 import hig_inv_u
+    rng = np.random.default_rng(3)
+    L = orc.lib()
+    cases = [(6, 0.25, 2), (6, 0.25, 5), (3, 0.5, 6), (8, 18.25, 2), (40, 25.25, 4), (206, 120.25, 5), (1.5, 0.25, 3)]
+    for (v, w, m) in cases:
+        om = rng.random(64)
+        om[:4] = [1e-6, 1e-3, 0.999, 0.5]
+        got = hig_inv_u(om, v, w, float(m))
+        ref = np.empty_like(om)
+        o = orc.opts(stable_hig=1, sigma_inverse_cdf=1)
+        assert L.orc_rhig_u_from_omega(v, w, m, om.size, orc.P(om), C.byref(o), orc.P(ref)) == 0
+        assert np.max(np.abs(got - ref)) <= 1e-9
+        o2 = orc.opts(stable_hig=1, sigma_inverse_cdf=1, bisect_tol=0.0)
+        assert L.orc_rhig_u_from_omega(v, w, m, om.size, orc.P(om), C.byref(o2), orc.P(ref)) == 0
+        assert np.max(np.abs(got - ref) / np.maximum(ref, 1e-300)) <= 1e-10
+
+
+def test_hig_large_cluster_parameters():
+    from split_and_merge_gibbs_sampling_b200 import hig_inv_u
+    L = orc.lib()
+    rng = np.random.default_rng(5)
+    for (v, w, m) in [(1306, 700.25, 5), (6506, 3500.25, 5), (65006, 35000.25, 5), (30006, 20000.25, 2)]:
+        om = rng.random(16)
+        got = hig_inv_u(om, v, w, float(m))
+        ref = np.empty_like(om)
+        o2 = orc.opts(stable_hig=1, sigma_inverse_cdf=1, bisect_tol=0.0)
+        assert L.orc_rhig_u_from_omega(v, w, m, om.size, orc.P(om), C.byref(o2), orc.P(ref)) == 0
+        assert np.all(np.isfinite(got))
+        assert np.max(np.abs(got - ref) / ref) <= 1e-9
+
+
+def test_logdensity_hig_golden_and_oracle():
+    from split_and_merge_gibbs_sampling_b200 import logdensity_hig
+    g = G["logdensity_hig"]
+    got = logdensity_hig([r["s"] for r in g], [r["v"] for r in g], [r["w"] for r in g], [float(r["m"]) for r in g])
+    ref = np.array([r["val"] for r in g])
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 1e-12
+    rng = np.random.default_rng(9)
+    L = orc.lib()
+    s = rng.uniform(0.1, 3.0, 200)
+    v = rng.uniform(1.5, 3000, 200)
+    w = rng.uniform(0.0, 2000, 200)
+    m = rng.integers(2, 7, 200).astype(np.float64)
+    got = logdensity_hig(s, v, w, m)
+    ref = np.array([L.orc_logdensity_hig(a, b, c, d, 1, None) for a, b, c, d in zip(s, v, w, m)])
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 1e-12

@@ -1,0 +1,165 @@
+"""Parity of the Neal-8 sweep kernels with the CPU oracle on the same seeded inputs.
+Integer outputs (mismatch counts, histograms, allocations under an injected uniform tape, centres)
+are bit-exact; log-likelihoods agree to 1e-12 relative (fp64); sigma draws agree with the reference's
+bisection to its own bracket width (1e-9 in u)."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from helpers import Problem, oracle_state_full, rel_err
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # n, p, m, K_true  (ragged p, n not a multiple of the tile, K across tile edges)
+    (257, 13, 3, 2),
+    (1000, 64, 4, 10),
+    (515, 100, 5, 33),
+    (300, 257, 2, 5),
+]
+
+
+@pytest.mark.parametrize("n,p,m,k", SHAPES)
+def test_ll_block_matches_oracle(n, p, m, k):
+    pb = Problem(n, p, m, k, seed=n + p)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    ch = pb.chain()
+    ch.set_state(K, c, cen, sig)
+    LL, mm = ch.ll_block(K)
+    LLo, mmo = orc.ll_block(pb.od, cen, sig)
+    assert np.array_equal(mm, mmo)  # integer mismatch counts: bit-exact
+    assert np.max(rel_err(LL, LLo)) < 1e-12
+    assert abs(ch.loglik() - orc.loglik(pb.od, c, cen, sig)) <= 1e-12 * abs(orc.loglik(pb.od, c, cen, sig))
+    ch.close()
+
+
+def test_ll_block_mixed_attribute_sizes():
+    rng = np.random.default_rng(2)
+    attr = rng.integers(2, 7, 40)
+    from split_and_merge_gibbs_sampling_b200.synth import ham_mix_gen
+    pb = Problem(400, 40, 3, 4, seed=3)
+    X, lab, cent, at = ham_mix_gen(400, 40, attr, 4, seed=3)
+    pb.X, pb.labels, pb.cent, pb.attr = X, lab, cent, at
+    pb.od = orc.OracleData(X, at, pb.gamma, pb.v, pb.w)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    ch = pb.chain()
+    ch.set_state(K, c, cen, sig)
+    LL, mm = ch.ll_block(K)
+    LLo, mmo = orc.ll_block(pb.od, cen, sig)
+    assert np.array_equal(mm, mmo)
+    assert np.max(rel_err(LL, LLo)) < 1e-12
+    ch.close()
+
+
+def _scan_case(pb, mode, seed, m_aux=3, pool=97, L=None, iters=1):
+    K, c, cen, sig = oracle_state_full(pb, mode=mode, seed=seed, L=L, iters=iters, m_aux=m_aux)
+    pc, ps = orc.draw_pool(pb.od, pool, seed + 1, o=orc.opts(stable_hig=1))
+    rng = np.random.default_rng(seed)
+    tape = (rng.integers(0, 2**53, size=pb.n * (m_aux + 1)).astype(np.float64) + 0.5) / 2.0**53
+    ref = orc.neal8_scan(pb.od, m_aux, c, cen, sig, pc, ps, tape, o=orc.opts(counted=1))
+    ch = pb.chain(m=m_aux)
+    ch.set_state(K, c, cen, sig)
+    ch.set_pool(pc, ps)
+    ch.neal8_scan(tape)
+    got = ch.snapshot()
+    st = ch.stats()
+    ch.close()
+    return ref, got, st
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_scan_quiet_regime_bit_exact(seed):
+    pb = Problem(3000, 64, 4, 10, seed=seed)
+    ref, got, st = _scan_case(pb, "truth", seed)
+    if ref["exact_pos_ties"] == 0:
+        assert got["K"] == ref["K"]
+        assert np.array_equal(got["c_i"], ref["c"])
+        assert np.array_equal(got["centers"], ref["center"])
+        assert np.array_equal(got["sigmas"], ref["sigma"])
+
+
+@pytest.mark.parametrize("seed", [4, 5, 6])
+def test_scan_burn_in_regime_bit_exact(seed):
+    # random labels + diffuse data: many moves, births, deaths and singleton replacements (cases 1-4)
+    pb = Problem(1500, 24, 3, 6, seed=seed, s=1.5)
+    ref, got, st = _scan_case(pb, "random", seed, L=12, iters=1)
+    assert st["scan_events"] > 100
+    if ref["exact_pos_ties"] == 0:
+        assert got["K"] == ref["K"]
+        assert np.array_equal(got["c_i"], ref["c"])
+        assert np.array_equal(got["centers"], ref["center"])
+        assert np.array_equal(got["sigmas"], ref["sigma"])
+
+
+def test_scan_with_many_singletons():
+    # every observation starts in its own cluster (zoo_simulator.R L=101 analogue): cases 2 and 4 dominate
+    pb = Problem(120, 16, 3, 3, seed=7, s=0.8)
+    n = pb.n
+    c0 = np.arange(n, dtype=np.int32)
+    pc, ps = orc.draw_pool(pb.od, 200, 3, o=orc.opts(stable_hig=1))
+    cen, sig = pc[:n].copy(), ps[:n].copy()
+    rng = np.random.default_rng(11)
+    tape = (rng.integers(0, 2**53, size=n * 4).astype(np.float64) + 0.5) / 2.0**53
+    ref = orc.neal8_scan(pb.od, 3, c0, cen, sig, pc, ps, tape, o=orc.opts(counted=0), kcap=256)
+    ch = pb.chain(m=3, c_i=c0, max_clusters=200)
+    ch.set_state(n, c0, cen, sig)
+    ch.set_pool(pc, ps)
+    ch.neal8_scan(tape)
+    got = ch.snapshot()
+    ch.close()
+    if ref["exact_pos_ties"] == 0:
+        assert got["K"] == ref["K"]
+        assert np.array_equal(got["c_i"], ref["c"])
+        assert np.array_equal(got["sigmas"], ref["sigma"])
+
+
+def test_histogram_and_update_phi_match_oracle():
+    pb = Problem(2000, 37, 5, 7, seed=21)
+    K, c, cen, sig = oracle_state_full(pb, mode="random", seed=21, L=9, iters=2)
+    ch = pb.chain()
+    ch.set_state(K, c, cen, sig)
+    H, cnt = ch.histogram(K)
+    Ho, cnto = orc.histogram(pb.od, K, c, H.shape[2])
+    assert np.array_equal(H, Ho) and np.array_equal(cnt, cnto)  # integer: bit-exact
+    rng = np.random.default_rng(5)
+    uc = rng.random((K, pb.p))
+    us = rng.random((K, pb.p))
+    # oracle consumes, per cluster in label order, p centre uniforms then p sigma uniforms
+    tape = np.concatenate([np.concatenate([uc[k], us[k]]) for k in range(K)])
+    ref = orc.update_phi(pb.od, c, cen, sig, tape, o=orc.opts(stable_hig=1, sigma_inverse_cdf=1))
+    assert ref["consumed"] == tape.size
+    ch.update_phi(uc, us)
+    got = ch.snapshot()
+    assert np.array_equal(got["centers"], ref["center"])  # Rcpp::sample incl. revsort tie order: bit-exact
+    u_got, u_ref = np.exp(-1.0 / got["sigmas"]), np.exp(-1.0 / ref["sigma"])
+    assert np.max(np.abs(u_got - u_ref)) <= 1e-9  # reference bisection bracket (hyperg.cpp:263)
+    ref2 = orc.update_phi(pb.od, c, cen, sig, tape, o=orc.opts(stable_hig=1, sigma_inverse_cdf=1, bisect_tol=0.0))
+    assert np.max(rel_err(got["sigmas"], ref2["sigma"])) < 1e-9
+    ch.close()
+
+
+def test_update_phi_tie_heavy_centres():
+    # small clusters with 6-level attributes: most levels are unseen => equal probabilities => the
+    # revsort tie permutation decides the draw
+    pb = Problem(60, 20, 6, 12, seed=4, s=2.0)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    sig = sig * 4.0  # flatter conditionals: ties carry real mass
+    ch = pb.chain()
+    ch.set_state(K, c, cen, sig)
+    rng = np.random.default_rng(8)
+    uc, us = rng.random((K, pb.p)), rng.random((K, pb.p))
+    tape = np.concatenate([np.concatenate([uc[k], us[k]]) for k in range(K)])
+    ref = orc.update_phi(pb.od, c, cen, sig, tape, o=orc.opts(stable_hig=1, sigma_inverse_cdf=1))
+    ch.update_phi(uc, us)
+    got = ch.snapshot()
+    assert np.array_equal(got["centers"], ref["center"])
+    ch.close()
+
+
+def test_full_size_parity_config_c2():
+    # BASELINE.json config 2: n=1e4, p=64, m=4, K_true=10, injected uniform stream, bit-exact allocations
+    for seed in (1, 2, 3):
+        pb = Problem(10000, 64, 4, 10, seed=seed)
+        ref, got, st = _scan_case(pb, "truth", seed, pool=997)
+        if ref["exact_pos_ties"] == 0:
+            assert got["K"] == ref["K"]
+            assert np.array_equal(got["c_i"], ref["c"])
