@@ -67,4 +67,6 @@ def test_logdensity_hig_golden_and_oracle():
     m = rng.integers(2, 7, 200).astype(np.float64)
     got = logdensity_hig(s, v, w, m)
     ref = np.array([L.orc_logdensity_hig(a, b, c, d, 1, None) for a, b, c, d in zip(s, v, w, m)])
-    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) < 1e-12
+    # the density is a difference of lgamma-sized addends ((v+w) log(v+w)): 1e-12 relative to the largest addend
+    scale = np.maximum(np.maximum(1.0, np.abs(ref)), (v + w) * np.log(v + w))
+    assert np.max(np.abs(got - ref) / scale) < 1e-12
