@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs + split-merge sweeps/sec on synthetic Hamming-mixture data.
+
+One "step" = one iteration of code/launcher.cpp:85-154 on one chain: Neal-8 allocation pass over all n
+observations + update_phi + one split-merge proposal (t=r=10) + full log-likelihood.
+Workload (BASELINE.json metric config): n=1e5, p=256, 5 categories, K_true=50, m_aux=3, gamma=1,
+v=6, w=0.25, one chain per GPU (chains are independent => weak scaling, no data-path collective).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo (CUDA, sm_100a)
+  python bench.py --impl reference ...                   # the CPU oracle restating the reference,
+                                                         # all host threads (one chain per thread)
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "gibbs_split_merge_sweeps_per_sec"
+UNIT = "sweeps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--p", type=int, default=256)
+    ap.add_argument("--cats", type=int, default=5)
+    ap.add_argument("--k-true", type=int, default=50)
+    ap.add_argument("--m-aux", type=int, default=3)
+    ap.add_argument("--t", type=int, default=10)
+    ap.add_argument("--r", type=int, default=10)
+    ap.add_argument("--burn", type=int, default=3, help="untimed sweeps from the random start before warm-up")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-obs", type=int, default=600, help="observations of one pass timed by the faithful CPU baseline")
+    ap.add_argument("--seed", type=int, default=1)
+    return ap.parse_args()
+
+
+def workload(a, seed):
+    from split_and_merge_gibbs_sampling_b200.synth import ham_mix_gen
+    X, labels, cent, attr = ham_mix_gen(a.n, a.p, a.cats, a.k_true, s=0.5, seed=seed)
+    v = np.full(a.p, 6.0)
+    w = np.full(a.p, 0.25)
+    return X, labels, cent, attr, v, w, 1.0
+
+
+def config_dict(a):
+    return {"workload": f"synthetic Hamming mixture n={a.n} p={a.p} categories={a.cats} K_true={a.k_true} s=0.5",
+            "m_aux": a.m_aux, "t": a.t, "r": a.r, "gamma": 1.0, "v": 6.0, "w": 0.25,
+            "init": f"L={a.k_true} random labels, {a.burn} untimed sweeps before warm-up",
+            "chains_per_gpu": 1, "parallelism": "independent chains, one per GPU",
+            "cache": "inputs larger than L2: X 25.6 MB + LL block 154 MB + aux pool 1.3 GB are streamed every sweep"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = os.path.join(ROOT, "gpurun_out", f"clocks_rank{index}.csv")
+
+    def start(self):
+        os.makedirs(os.path.dirname(self.path), exist_ok=True)
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for ln in open(self.path):
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(a, X, labels, cent, attr, v, w, gamma, n_chains, cores_label):
+    """Times the oracle (CPU restatement of the reference) on a bounded sample of the same workload:
+    the Neal-8 pass over the first `cpu_obs` observations at the full n (cost per observation does not
+    depend on the index), then one full update_phi, one split-merge proposal and the log-likelihood."""
+    import oracle_lib as orc
+    od = orc.OracleData(X, attr, gamma, v, w)
+    K = int(labels.max() + 1)
+    cen = cent.astype(np.float64)
+    sig = np.full((K, a.p), 0.5)
+    pc, ps = orc.draw_pool(od, 512, 7, o=orc.opts(stable_hig=1))
+    out = {}
+    for name, counted, nobs in (("faithful", 0, a.cpu_obs), ("counted", 1, min(a.n, 20000))):
+        o = orc.opts(counted=counted, stable_hig=1, validate=1)
+        t = orc.time_sweep(od, a.m_aux, a.t, a.r, labels, cen, sig, pc, ps, nobs, True, n_chains, 11, o=o)
+        sweep_s = t["scan_s"] * (a.n / t["n_obs"]) + t["update_phi_s"] + t["split_merge_s"] + t["loglik_s"]
+        out[name] = {"sweep_s": sweep_s, "sweeps_per_s": n_chains / sweep_s, "parts": t}
+    f = out["faithful"]
+    return {"value": f["sweeps_per_s"], "unit": UNIT, "cores": n_chains, "kind": "port",
+            "sample": (f"faithful oracle (same O(n^2 K) asymptotics as the reference): Neal-8 pass over the first "
+                       f"{f['parts']['n_obs']} of {a.n} observations scaled to n, + full update_phi + one split-merge "
+                       f"(t=r={a.t}) + log-likelihood; {cores_label}; norm_const2 in the overflow-free form because the "
+                       f"reference's GSL 2F1 throws at this cluster size"),
+            "sweep_seconds": f["sweep_s"],
+            "counted_variant": {"value": out["counted"]["sweeps_per_s"], "sweep_seconds": out["counted"]["sweep_s"],
+                                "note": "identical outputs, O(n(K+m)p): counts kept incrementally, sigma terms cached"}}
+
+
+def run_reference(a):
+    """--impl reference: the CPU oracle (the reference cannot be built here: no R/Rcpp/GSL), one chain per
+    host thread on all cores, same config / metric / unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    X, labels, cent, attr, v, w, gamma = workload(a, a.seed)
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    vals = []
+    cb = None
+    reps = max(1, min(a.steps, 2))
+    for _ in range(reps):
+        cb = cpu_baseline(a, X, labels, cent, attr, v, w, gamma, cores, f"{cores} independent chains on {cores} host threads")
+        vals.append(cb["value"])
+    val = float(np.mean(vals))
+    line = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1000.0 * cores / val, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(a), "impl": "reference",
+            "cpu_baseline": dict(cb, value=val),
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.time() - t0,
+            "note": "aggregate over one chain per host thread; each timed step is a bounded sample (see cpu_baseline.sample)"}
+    print(json.dumps(line))
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    from split_and_merge_gibbs_sampling_b200 import Chain, run_markov_chain
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    X, labels, cent, attr, v, w, gamma = workload(a, a.seed + rank)
+    ch = Chain(X, attr, gamma, v, w, m=a.m_aux, L=a.k_true, t=a.t, r=a.r, neal8=True, split_merge=True, seed=a.seed + rank,
+               device=local, compact_init=True, data_u8=True)
+    ch.step(a.burn)  # leave the random start (untimed)
+    for _ in range(a.warmup):
+        ch.step(1)
+    st0 = ch.stats()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    phase = np.zeros(8)
+    dev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        ch.step(1)  # one launch sequence + one status read-back per sweep
+        dev_ms += ch.last_step_ms()  # CUDA events on the chain's stream around the sweep
+        tm = ch.timings()
+        phase += np.array([tm[k] for k in ("ll_block_ms", "aux_ll_ms", "scan_ms", "update_phi_ms", "split_merge_ms",
+                                           "pool_ms", "loglik_ms", "total_ms")])
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    st1 = ch.stats()
+    snap = ch.snapshot(with_phi=False)
+    K_now = snap["K"]
+    # max over ranks of the device time (and of the wall time, reported beside it)
+    tt = torch.tensor([dev_ms, wall * 1000.0], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(tt[0]), float(tt[1])
+    value = world * a.steps / (dev_ms_max / 1000.0)
+    phase /= a.steps
+    # ---- roofline of the likelihood-block kernel (K1), timed live with CUDA events on its stream
+    pp = (a.p + 15) // 16 * 16
+    alg_bytes = a.n * pp + 8.0 * a.n * K_now
+    peak, peak_src = measured_peaks()
+    ach = alg_bytes / (phase[0] / 1000.0) / 1e9 if phase[0] > 0 else 0.0
+    fp64_ops = float(a.n) * K_now * a.p
+    roofline = {"kernel": "hamming_ll_block_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": float(phase[0]),
+                "note": ("fp64 select-add bound, not HBM bound: n*K*p = %.3g predicated DADDs per launch = %.1f "
+                         "GDADD/s (B200 fp64 pipe ~ 64 lanes/clk/SM)" % (fp64_ops, fp64_ops / (phase[0] / 1e3) / 1e9
+                                                                         if phase[0] > 0 else 0.0))}
+    scan = {"ns_per_observation": 1e6 * phase[2] / a.n, "rounds_per_sweep": (st1["scan_rounds"] - st0["scan_rounds"]) / a.steps,
+            "events_per_sweep": (st1["scan_events"] - st0["scan_events"]) / a.steps, "avg_ms": float(phase[2])}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": dev_ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config_dict(a), "clocks": clocks,
+            "gpu_launches": int(st1["launches"] - st0["launches"]),
+            "wall_ms_per_step": wall_ms_max / a.steps,
+            "phase_ms": dict(zip(["ll_block", "aux_ll", "scan", "update_phi", "split_merge", "pool", "loglik", "total"],
+                                 [float(x) for x in phase])),
+            "roofline": roofline, "scan": scan, "K": int(K_now),
+            "sm_accept_rate": (st1["sm_accepted"] - st0["sm_accepted"]) / max(1, st1["sm_proposals"] - st0["sm_proposals"])}
+    ch.close()
+    # ---- end to end through the public entry point (run_markov_chain mirror, host buffers in/out):
+    # upload of the fp64 column-major matrix, state + pool initialisation, W+K sweeps, and a device->host
+    # snapshot (c_i, centres, sigmas, log-lik, accepted) for every kept iteration -- all inside the timed region.
+    Xd = np.asfortranarray(X.astype(np.float64))
+    barrier()
+    t0 = time.perf_counter()
+    res = run_markov_chain(Xd, attr, gamma, v, w, m=a.m_aux, iterations=a.steps, L=a.k_true, c_i=labels,
+                           burnin=a.warmup, t=a.t, r=a.r, neal8=True, split_merge=True, seed=a.seed + rank, device=local)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    nsw = a.steps + a.warmup
+    kbar = float(np.mean(res["total_cls"])) if len(res["total_cls"]) else 0.0
+    line["e2e"] = {"value": world * nsw / e2e_s, "unit": UNIT,
+                   "h2d_bytes_per_step": int(Xd.nbytes / nsw),
+                   "d2h_bytes_per_step": int((4 * a.n + kbar * pp * 9 + 16) * a.steps / nsw),
+                   "seconds": e2e_s, "sweeps": nsw,
+                   "note": ("whole run_markov_chain call from host buffers: data upload (amortised over the sweeps), "
+                            "initialisation incl. the n*m aux pool, W+K sweeps, per-kept-iteration snapshots")}
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(a, X, labels, cent, attr, v, w, gamma, 1, "1 chain on 1 host core")
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

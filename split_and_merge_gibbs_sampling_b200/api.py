@@ -112,6 +112,11 @@ class Chain:
     def step(self, n_iters=1):
         lb.check(self.lib.smg_step(self.h, int(n_iters)))
 
+    def last_step_ms(self):
+        ms = C.c_double()
+        lb.check(self.lib.smg_last_step_ms(self.h, C.byref(ms)))
+        return ms.value
+
     def snapshot(self, with_phi=True):
         K = C.c_int()
         ll = C.c_double()

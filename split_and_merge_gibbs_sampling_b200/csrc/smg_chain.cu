@@ -38,6 +38,7 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
+  for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
   if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
   if (dalloc(&ch->attr, pp) || dalloc(&ch->v, pp) || dalloc(&ch->w, pp)) return SMG_ERR_CUDA;
   for (int b = 0; b < 2; b++) {
@@ -86,6 +87,8 @@ static void chain_free(smg_chain* ch) {
     if (q) cudaFree(q);
   for (int q = 0; q < 8; q++)
     if (ch->ev[q]) cudaEventDestroy(ch->ev[q]);
+  for (int q = 0; q < 2; q++)
+    if (ch->ev_call[q]) cudaEventDestroy(ch->ev_call[q]);
   if (ch->st) cudaStreamDestroy(ch->st);
   delete ch;
 }
@@ -153,6 +156,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   SMG_CUDA(cudaGetLastError());
   // back to canonical form: labels in c, parameters in label order in the other buffer
   const int nx = ch->cur ^ 1;
+  SMG_CUDA(cudaMemsetAsync(ch->counts_slot, 0, (size_t)ch->NST * sizeof(int), ch->st));
   scan_finalize_labels_kernel<<<cdiv(ch->n, 256), 256, 0, ch->st>>>(ch->c, ch->n, ch->slot2label);
   scan_finalize_params_kernel<<<ch->NS, 128, 0, ch->st>>>(ch->slot2label, ch->NS, ch->pp, ch->cen[ch->cur],
                                                          ch->sig[ch->cur], ch->isg[ch->cur], ch->sden[ch->cur],
@@ -528,11 +532,18 @@ void smg_destroy(smg_chain* ch) { chain_free(ch); }
 int smg_step(smg_chain* ch, int n_iters) {
   if (!ch) return fail(SMG_ERR_ARG, "chain is NULL");
   SMG_CUDA(cudaSetDevice(ch->device));
+  cudaEventRecord(ch->ev_call[0], ch->st);
   for (int it = 0; it < n_iters; it++) {
     int rc = sweep(ch, it == n_iters - 1);
     if (rc) return rc;
   }
+  cudaEventRecord(ch->ev_call[1], ch->st);
   int rc = sync_status(ch);
+  {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ch->ev_call[0], ch->ev_call[1]);
+    ch->h_step_ms = ms;
+  }
   if (n_iters > 0) {
     const int a[7] = {0, 1, 2, 3, 4, 5, 6}, b[7] = {1, 2, 3, 4, 5, 6, 7};
     float ms;
@@ -590,6 +601,12 @@ int smg_get_stats(smg_chain* ch, unsigned long long* out8) {
   out8[5] = ch->h_launches;
   out8[6] = ch->h_sm_props;
   out8[7] = d[7];
+  return 0;
+}
+
+int smg_last_step_ms(smg_chain* ch, double* ms) {
+  if (!ch || !ms) return fail(SMG_ERR_ARG, "NULL argument");
+  *ms = ch->h_step_ms;
   return 0;
 }
 

@@ -90,6 +90,8 @@ struct smg_chain {
   double h_loglik = 0.0;
   unsigned long long h_launches = 0, h_sweeps = 0, h_sm_props = 0, h_sm_acc = 0;
   cudaEvent_t ev[8] = {};
+  cudaEvent_t ev_call[2] = {};
+  double h_step_ms = 0.0;
   double h_timings[8] = {};
   int loglik_blocks = 0;
 };
