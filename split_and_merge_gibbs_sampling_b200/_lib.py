@@ -23,7 +23,7 @@ class SmgConfig(C.Structure):
         ("n", C.c_int), ("p", C.c_int), ("attrisize", c_int_p), ("gamma", C.c_double), ("v", c_dbl_p), ("w", c_dbl_p),
         ("m_aux", C.c_int), ("L", C.c_int), ("t", C.c_int), ("r", C.c_int), ("neal8", C.c_int), ("split_merge", C.c_int),
         ("n8_step_size", C.c_int), ("sam_step_size", C.c_int), ("thinning", C.c_int), ("seed", C.c_ulonglong),
-        ("max_clusters", C.c_int), ("pool_size", C.c_longlong), ("device", C.c_int), ("compact_init", C.c_int),
+        ("max_clusters", C.c_int), ("pool_size", C.c_longlong), ("device", C.c_int), ("compact_init", C.c_int), ("exact_sigma_inverse", C.c_int),
     ]
 
 
@@ -44,7 +44,7 @@ EXPORTS = [
     "smg_last_error", "smg_device_count", "smg_run_markov_chain", "smg_free_results", "smg_create", "smg_create_u8",
     "smg_step", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
-    "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig",
+    "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
     "smg_debug_split_merge",
 ]
 
@@ -95,6 +95,7 @@ def load():
     lib.smg_debug_loglik.argtypes = [C.c_void_p, c_dbl_p]
     lib.smg_debug_hig_inv_u.argtypes = [C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]
     lib.smg_debug_logdensity_hig.argtypes = [C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]
+    lib.smg_debug_rhig_u.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_ulonglong, c_dbl_p]
     lib.smg_debug_split_merge.argtypes = [C.c_void_p, C.POINTER(SmgSmTape), c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p,
                                           c_dbl_p]
     _lib = lib

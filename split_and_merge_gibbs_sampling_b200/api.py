@@ -73,7 +73,7 @@ class Chain:
 
     def __init__(self, data, attrisize, gamma, v, w, m=5, L=1, c_i=None, t=10, r=10, neal8=True, split_merge=True,
                  n8_step_size=1, sam_step_size=1, thinning=1, seed=1, max_clusters=0, pool_size=0, device=0,
-                 compact_init=False, data_u8=False):
+                 compact_init=False, data_u8=False, exact_sigma_inverse=False):
         self.lib = lb.load()
         self._attr = lb.as_i32(attrisize)
         self._v, self._w = lb.as_f64(v), lb.as_f64(w)
@@ -87,7 +87,7 @@ class Chain:
         cfg = lb.SmgConfig(self.n, self.p, lb.iptr(self._attr), float(gamma), lb.dptr(self._v), lb.dptr(self._w), int(m),
                           int(L), int(t), int(r), int(bool(neal8)), int(bool(split_merge)), int(n8_step_size),
                           int(sam_step_size), int(thinning), int(seed) & (2**64 - 1), int(max_clusters), int(pool_size),
-                          int(device), int(bool(compact_init)))
+                          int(device), int(bool(compact_init)), int(bool(exact_sigma_inverse)))
         ci = None if c_i is None else lb.as_i32(c_i)
         h = C.c_void_p()
         if data_u8:
@@ -225,4 +225,12 @@ def logdensity_hig(sigma, v, w, m):
                       for x in (sigma, v, w, m))
     out = np.empty(sg.shape)
     lb.check(lib.smg_debug_logdensity_hig(sg.size, lb.dptr(sg), lb.dptr(vv), lb.dptr(ww), lb.dptr(mm), lb.dptr(out)))
+    return out
+
+
+def rhig_u(count, v, w, m, seed=1):
+    """`count` draws of u = exp(-1/sigma), sigma ~ HIG(v,w,m), from the device's production sampler."""
+    lib = lb.load()
+    out = np.empty(int(count))
+    lb.check(lib.smg_debug_rhig_u(int(count), float(v), float(w), float(m), int(seed), lb.dptr(out)))
     return out

@@ -208,6 +208,7 @@ static int update_phi_all(smg_chain* ch, uint32_t sub, const double* uc, const d
   A.u_stride = ch->p;
   A.key = mk_key(ch, sub);
   A.prior = 0;
+  A.sigma_exact = ch->sigma_exact;
   A.enable = nullptr;
   A.status = ch->status;
   dim3 grid(cdiv(ch->pp, 128), ch->Kcap);
@@ -243,6 +244,7 @@ static int prior_phi_all(smg_chain* ch, int K) {
   A.u_stride = ch->p;
   A.key = mk_key(ch, SUB_INIT_PHI);
   A.prior = 1;
+  A.sigma_exact = ch->sigma_exact;
   A.enable = nullptr;
   A.status = ch->status;
   dim3 grid(cdiv(ch->pp, 128), std::max(K, 1));
@@ -266,7 +268,7 @@ static int launch_loglik(smg_chain* ch) {
 static int draw_pool(smg_chain* ch) {
   long long total = ch->pool_size * ch->pp;
   RngKey key = mk_key(ch, SUB_POOL);
-  pool_draw_kernel<<<cdiv(total, 128), 128, 0, ch->st>>>(ch->pool_size, ch->pp, ch->p, ch->attr, ch->v, ch->w, key, ch->pcen,
+  pool_draw_kernel<<<cdiv(total, 128), 128, 0, ch->st>>>(ch->pool_size, ch->pp, ch->p, ch->attr, ch->v, ch->w, key, ch->sigma_exact, ch->pcen,
                                                         ch->psig, ch->pisg, ch->pden);
   pool_sden_kernel<<<cdiv(ch->pool_size * 32, 256), 256, 0, ch->st>>>(ch->pool_size, ch->pp, ch->pden, ch->psden);
   ch->h_launches += 2;
@@ -370,6 +372,7 @@ static int create_common(const smg_config* cfg, smg_chain** out) {
   ch->gamma = cfg->gamma;
   ch->seed = cfg->seed;
   ch->device = cfg->device;
+  ch->sigma_exact = cfg->exact_sigma_inverse;
   ch->Kcap = cfg->max_clusters > 0 ? cfg->max_clusters : 192;
   ch->Kcap = std::min(ch->Kcap, SMG_MAX_ENTRIES - ch->m_aux);
   ch->Kcap = std::max(ch->Kcap, 8);
@@ -899,6 +902,13 @@ __global__ void dbg_loghig_kernel(int n, const double* s, const double* v, const
   if (i < n) out[i] = logdensity_hig_d(s[i], v[i], w[i], m[i]);
 }
 
+__global__ void dbg_rhig_kernel(int n, double v, double w, double m, RngKey key, double* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  SubStream rs(key, U_SIGMA, (uint32_t)i, 0u);
+  out[i] = hig_draw_u_d(rs, v, w, m);
+}
+
 static int dbg_map4(int count, const double* a, const double* b, const double* c, const double* d, double* out, int which) {
   if (count <= 0) return 0;
   int ndev = 0;
@@ -927,6 +937,26 @@ int smg_debug_hig_inv_u(int count, const double* omega, const double* v, const d
 int smg_debug_logdensity_hig(int count, const double* sigma, const double* v, const double* w, const double* m,
                              double* out) {
   return dbg_map4(count, sigma, v, w, m, out, 1);
+}
+
+int smg_debug_rhig_u(int count, double v, double w, double m, unsigned long long seed, double* u_out) {
+  if (count <= 0) return 0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  double* buf = nullptr;
+  SMG_CUDA(cudaMalloc(&buf, (size_t)count * 8));
+  RngKey key;
+  key.k0 = (uint32_t)seed;
+  key.k1 = (uint32_t)(seed >> 32);
+  key.sweep = 0;
+  key.sub = 0;
+  dbg_rhig_kernel<<<cdiv(count, 128), 128>>>(count, v, w, m, key, buf);
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaDeviceSynchronize());
+  SMG_CUDA(cudaMemcpy(u_out, buf, (size_t)count * 8, cudaMemcpyDeviceToHost));
+  cudaFree(buf);
+  return 0;
 }
 
 int smg_debug_split_merge(smg_chain* ch, const smg_sm_tape* tape, int* info, int* S, int* z_launch, int* z_star,

@@ -53,7 +53,7 @@ struct SmWork;  // split-merge workspace (smg_sm.cuh)
 struct smg_chain {
   // ---- configuration (host copies)
   int n = 0, p = 0, pp = 0, mmax = 0, m_aux = 0, L = 1, t = 10, r = 10;
-  int neal8 = 0, split_merge = 1, n8_step = 1, sam_step = 1, thinning = 1;
+  int neal8 = 0, split_merge = 1, n8_step = 1, sam_step = 1, thinning = 1, sigma_exact = 0;
   double gamma = 1.0;
   unsigned long long seed = 0;
   int Kcap = 192, NS = SMG_MAX_SLOTS, NST = SMG_MAX_SLOTS + smg::SM_NSLOTS, ldl = 192;

@@ -126,7 +126,7 @@ __device__ __forceinline__ double hamming_den(double s, int m) { return log(1.0 
 __device__ __forceinline__ double lbeta_d(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
 
 __device__ inline double betacf_d(double a, double b, double x) {
-  const double EPS = 1e-16, FPMIN = 1e-300;
+  const double EPS = 3e-16, FPMIN = 1e-300;
   double qab = a + b, qap = a + 1.0, qam = a - 1.0;
   double c = 1.0, d = 1.0 - qab * x / qap;
   if (fabs(d) < FPMIN) d = FPMIN;
@@ -210,9 +210,17 @@ __device__ inline double hig_inv_u_d(double Omega, double v, double w, double m)
   const bool use_lower = lP < -0.6931471805599453;  // P < 1/2
   const double target = use_lower ? lP : log(Q);
   double lo = 0.0, hi = xmax;
-  double x = a / (a + b);
-  if (!(x < xmax)) x = 0.5 * xmax;
-  if (!(x > 0.0)) x = 0.5 * xmax;
+  // start from the normal approximation of the Beta quantile (exact enough for the large shapes of big
+  // clusters; Newton on the log-tail repairs it for the small shapes of the prior)
+  const double mean = a / (a + b);
+  double x = mean;
+  if (a > 2.0 && b > 2.0) {
+    const double sd = sqrt(mean * (1.0 - mean) / (a + b + 1.0));
+    const double z = use_lower ? normcdfinv(exp(lP)) : -normcdfinv(Q);
+    x = mean + sd * z;
+  }
+  if (!(x < xmax)) x = (mean < xmax) ? 0.5 * (mean + xmax) : 0.5 * xmax;
+  if (!(x > 0.0)) x = 0.5 * fmin(mean, xmax);
   for (int it = 0; it < 200; it++) {
     double l_lo, l_up;
     log_ibeta_pair(x, a, b, lb, &l_lo, &l_up);
@@ -224,16 +232,81 @@ __device__ inline double hig_inv_u_d(double Omega, double v, double w, double m)
     else
       hi = x;
     double lpdf = (a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lb;
-    // d/dx log tail = +-pdf/tail
-    double dg = exp(lpdf - (use_lower ? l_lo : l_up));
+    double dg = exp(lpdf - (use_lower ? l_lo : l_up));  // d/dx log tail = +-pdf/tail
     if (!use_lower) dg = -dg;
     double xn = x - g / dg;
-    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-    double dx = fabs(xn - x);
+    const bool newton_ok = (xn > lo && xn < hi);
+    if (!newton_ok) xn = 0.5 * (lo + hi);
+    const double dx = fabs(xn - x);
     x = xn;
-    if (dx <= 4e-16 * x || hi - lo <= 4e-16 * hi) break;
+    // a Newton step below 1e-8 relative leaves an error of order 1e-16 (quadratic convergence)
+    if (newton_ok && dx <= 1e-8 * x) break;
+    if (hi - lo <= 4e-16 * hi) break;
   }
   return x / ((m - 1.0) * (1.0 - x));
+}
+
+// ----------------------------------------------------------------------------
+// Counter-based uniform sub-stream of one draw site (variable consumption, reproducible):
+// Philox counter = (a, b | ctr << 20, site | sub << 8, sweep).
+// ----------------------------------------------------------------------------
+struct SubStream {
+  RngKey key;
+  uint32_t site, a, b, ctr;
+  double spare;
+  bool has_spare;
+  __device__ __forceinline__ SubStream(const RngKey& k, uint32_t site_, uint32_t a_, uint32_t b_)
+      : key(k), site(site_), a(a_), b(b_), ctr(0), spare(0.0), has_spare(false) {}
+  __device__ __forceinline__ double next() {
+    if (has_spare) {
+      has_spare = false;
+      return spare;
+    }
+    uint32_t o[4];
+    philox4x32_10(a, b | (ctr << 20), site | (key.sub << 8), key.sweep, key.k0, key.k1, o);
+    ctr++;
+    spare = u01_from_bits(o[2], o[3]);
+    has_spare = true;
+    return u01_from_bits(o[0], o[1]);
+  }
+};
+
+// Gamma(shape, 1) by Marsaglia & Tsang (2000); shape < 1 through Gamma(shape+1) * U^(1/shape)
+__device__ inline double gamma_draw_d(SubStream& rs, double shape) {
+  double boost = 1.0;
+  if (shape < 1.0) {
+    boost = pow(rs.next(), 1.0 / shape);
+    shape += 1.0;
+  }
+  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  for (int it = 0; it < 64; it++) {
+    const double x = normcdfinv(rs.next());
+    double vv = 1.0 + c * x;
+    if (vv <= 0.0) continue;
+    vv = vv * vv * vv;
+    const double u = rs.next();
+    const double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * vv;
+    if (log(u) < 0.5 * x2 + d * (1.0 - vv + log(vv))) return boost * d * vv;
+  }
+  return boost * d;  // not reached in practice (acceptance > 95% per round)
+}
+
+// sigma ~ HIG(v,w,m), returned as u = exp(-1/sigma).  Same law as hyperg.cpp:346-378:
+// x ~ Beta(w+1, v-1) conditioned on x <= (m-1)/m, u = x/((m-1)(1-x))  (the reference's own Beta branch,
+// hyperg.cpp:359-368); after 8 rejected proposals (the truncation keeps little mass) one exact
+// inverse-CDF draw (the reference's bisection branch) finishes -- the mixture is still the exact law.
+__device__ inline double hig_draw_u_d(SubStream& rs, double v, double w, double m) {
+  const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    const double ga = gamma_draw_d(rs, a), gb = gamma_draw_d(rs, b);
+    const double x = ga / (ga + gb);
+    if (x > 0.0 && x <= xmax) {
+      const double u = x / ((m - 1.0) * (1.0 - x));
+      if (u > 0.0 && u < 1.0) return u;
+    }
+  }
+  return hig_inv_u_d(rs.next(), v, w, m);
 }
 
 // ----------------------------------------------------------------------------

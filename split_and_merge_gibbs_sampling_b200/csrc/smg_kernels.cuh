@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) aux_ll_kernel(const uint8_t* __restrict__
 struct ScanArgs {
   int n, pp, m_aux, ldl, K0cap;   // K0cap: number of valid LL columns (= K at pass start)
   const uint8_t* X;
-  const double* LL;
+  double* LL;     // [n][ldl]; columns >= K0 are filled in windows for clusters born during the pass
   const double* LLaux;
   const int* aux_e;
   const double* u_alloc;  // injected allocation uniforms (tape + m_aux, stride), or null
@@ -245,6 +245,47 @@ struct ScanArgs {
 };
 
 #define EVT_NONE (-1)
+#define SCAN_FILL_W0 128      // first window (rows) materialised for a newly born column
+#define SCAN_FILL_WMAX 32768  // windows double up to this many rows
+
+// All 32 warps of the scan CTA materialise LL[r0..r1)[slot] for a column born during the pass.
+// Four rows per warp are in flight at a time; the value of each entry is the one warp_mismatch_dot
+// would return (same per-lane order, same butterfly).
+__device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, int r0, int r1, int warp, int lane) {
+  const int pp = A.pp;
+  const uint8_t* crow = A.cen + (size_t)slot * pp;
+  const double* wrow = A.isg + (size_t)slot * pp;
+  const double sd = A.sden[slot];
+  for (int row = r0 + warp * 4; row < r1; row += SMG_SCAN_WARPS * 4) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int j0 = lane * 8; j0 < pp; j0 += 256) {
+      const uint2 cv = *reinterpret_cast<const uint2*>(crow + j0);
+      uint2 xv[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        xv[r] = (row + r < r1) ? *reinterpret_cast<const uint2*>(A.X + (size_t)(row + r) * pp + j0) : cv;
+      const double2* w = reinterpret_cast<const double2*>(wrow + j0);
+      const double2 w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const uint32_t m0 = __vcmpne4(xv[r].x, cv.x), m1 = __vcmpne4(xv[r].y, cv.y);
+        if (m0 & 0x000000ffu) acc[r] += w0.x;
+        if (m0 & 0x0000ff00u) acc[r] += w0.y;
+        if (m0 & 0x00ff0000u) acc[r] += w1.x;
+        if (m0 & 0xff000000u) acc[r] += w1.y;
+        if (m1 & 0x000000ffu) acc[r] += w2.x;
+        if (m1 & 0x0000ff00u) acc[r] += w2.y;
+        if (m1 & 0x00ff0000u) acc[r] += w3.x;
+        if (m1 & 0xff000000u) acc[r] += w3.y;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const double dot = warp_sum(acc[r]);
+      if (lane == 0 && row + r < r1) A.LL[(size_t)(row + r) * A.ldl + slot] = -dot - sd;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(ScanArgs A) {
   __shared__ int s_cnt[SMG_MAX_SLOTS];
@@ -253,7 +294,9 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
   __shared__ int s_l2s[SMG_MAX_SLOTS];
   __shared__ int s_s2l[SMG_MAX_SLOTS];
   __shared__ int s_evt[SMG_SCAN_WARPS];
-  __shared__ int s_K, s_i0, s_next, s_err;
+  __shared__ int s_fill[SMG_MAX_SLOTS];   // rows [.., s_fill) of a born column are materialised
+  __shared__ int s_fillw[SMG_MAX_SLOTS];  // next window size
+  __shared__ int s_K, s_i0, s_next, s_err, s_minfill;
   __shared__ unsigned long long s_stats[4];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -267,12 +310,15 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     s_logcm1[s] = cnt > 1 ? log((double)(cnt - 1)) : -CUDART_INF;
     s_l2s[s] = s;
     s_s2l[s] = (s < K0) ? s : -1;
+    s_fill[s] = n;
+    s_fillw[s] = SCAN_FILL_W0;
   }
   if (tid == 0) {
     s_K = K0;
     s_i0 = 0;
     s_next = K0;
     s_err = 0;
+    s_minfill = n;
     s_stats[0] = s_stats[1] = s_stats[2] = s_stats[3] = 0;
     if (K0 + m > SMG_MAX_ENTRIES) s_err |= ST_TOO_MANY_ENTRIES;
     if (K0 > A.K0cap) s_err |= ST_LL_COLS;
@@ -286,6 +332,33 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
   for (;;) {
     const int i0 = s_i0;
     if (i0 >= n) break;
+    if (s_minfill < n && i0 + SMG_SCAN_WARPS > s_minfill) {
+      // some born column is materialised only up to s_minfill: extend every lagging window
+      const int Kx = s_K;
+      for (int e = 0; e < Kx; e++) {
+        const int slot = s_l2s[e];
+        if (slot < K0 || slot >= A.ldl) continue;
+        const int f0 = s_fill[slot];
+        if (f0 >= n || f0 >= i0 + 2 * SMG_SCAN_WARPS) continue;
+        const int f1 = min(n, f0 + s_fillw[slot]);
+        scan_fill_column(A, slot, f0, f1, warp, lane);
+        __syncthreads();
+        if (tid == 0) {
+          s_fill[slot] = f1;
+          s_fillw[slot] = min(SCAN_FILL_WMAX, s_fillw[slot] * 2);
+        }
+        __syncthreads();
+      }
+      if (tid == 0) {
+        int mf = n;
+        for (int e = 0; e < Kx; e++) {
+          const int slot = s_l2s[e];
+          if (slot >= K0 && slot < A.ldl) mf = min(mf, s_fill[slot]);
+        }
+        s_minfill = mf;
+      }
+      __syncthreads();
+    }
     const int i = i0 + warp;
     const int K = s_K;
     const int ne = K + m;
@@ -304,9 +377,9 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         const int e = q * 32 + lane;
         int slot = (e < K) ? s_l2s[e] : -1;
         double ll = 0.0;
-        if (slot >= 0 && slot < K0) ll = A.LL[(size_t)i * A.ldl + slot];
-        // columns born during this pass: evaluate on the fly, one at a time, whole warp
-        unsigned dyn = __ballot_sync(SMG_FULL, slot >= K0);
+        if (slot >= 0 && slot < A.ldl) ll = A.LL[(size_t)i * A.ldl + slot];
+        // born columns beyond the LL matrix width: evaluate on the fly, one at a time, whole warp
+        unsigned dyn = __ballot_sync(SMG_FULL, slot >= A.ldl);
         while (dyn) {
           int src = __ffs(dyn) - 1;
           dyn &= dyn - 1;
@@ -505,6 +578,10 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
       }
       if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
+      if (new_slot < A.ldl) {
+        __syncthreads();  // the new parameter vector is visible to the whole CTA
+        scan_fill_column(A, new_slot, ie + 1, min(n, ie + 1 + SCAN_FILL_W0), warp, lane);
+      }
     }
     __syncthreads();  // everyone has read the pre-event state
     if (tid == 0) {
@@ -533,6 +610,11 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         }
       } else {
         s_next = new_slot + 1;
+        if (new_slot < A.ldl) {
+          s_fill[new_slot] = min(n, ie + 1 + SCAN_FILL_W0);
+          s_fillw[new_slot] = 2 * SCAN_FILL_W0;
+          s_minfill = min(s_minfill, s_fill[new_slot]);
+        }
         s_cnt[new_slot] = 1;
         s_logc[new_slot] = 0.0;
         s_logcm1[new_slot] = -CUDART_INF;
@@ -566,6 +648,7 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
   }
   if (tid == 0) {
     *A.Kptr = s_K;
+    if (s_K > A.K0cap) atomicOr(A.status, ST_LL_COLS);
     if (A.stats)
       for (int q = 0; q < 4; q++) A.stats[q] += s_stats[q];
   }
@@ -685,6 +768,7 @@ struct PhiArgs {
   int u_stride;
   RngKey key;
   int prior;    // 1 => draw from the prior (no data)
+  int sigma_exact;  // 1 => always the one-uniform inverse-CDF sigma draw (also used whenever u_sigma is injected)
   const int* enable;  // optional device flag: skip the whole launch when *enable == 0
   int* status;
 };
@@ -739,8 +823,14 @@ __global__ void __launch_bounds__(128) phi_draw_kernel(PhiArgs A) {
   }
   const double vv = A.v[j] + s_match;
   const double ww = A.w[j] + (double)nk - s_match;
-  const double us = get_u(A.u_sigma, (size_t)job * A.u_stride + j, A.key, U_SIGMA, (uint32_t)job, (uint32_t)j);
-  const double uu = hig_inv_u_d(us, vv, ww, (double)m);
+  double uu;
+  if (A.u_sigma || A.sigma_exact) {
+    const double us = get_u(A.u_sigma, (size_t)job * A.u_stride + j, A.key, U_SIGMA, (uint32_t)job, (uint32_t)j);
+    uu = hig_inv_u_d(us, vv, ww, (double)m);
+  } else {
+    SubStream rs(A.key, U_SIGMA, (uint32_t)job, (uint32_t)j);
+    uu = hig_draw_u_d(rs, vv, ww, (double)m);
+  }
   const double sigma = -1.0 / log(uu);
   A.cen[o] = (uint8_t)center;
   A.sig[o] = sigma;
@@ -862,7 +952,7 @@ __global__ void ingest_colmajor_kernel(const double* __restrict__ Xd, int n, int
 // prior pool entries (launcher.cpp:67-77,123-129): centre ~ U{1..m_j}, sigma ~ HIG(v_j,w_j,m_j)
 __global__ void __launch_bounds__(128) pool_draw_kernel(long long pool_size, int pp, int p, const int* __restrict__ attr,
                                                         const double* __restrict__ v, const double* __restrict__ w,
-                                                        RngKey key, uint8_t* __restrict__ pcen,
+                                                        RngKey key, int sigma_exact, uint8_t* __restrict__ pcen,
                                                         double* __restrict__ psig, double* __restrict__ pisg,
                                                         double* __restrict__ pden) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -884,7 +974,15 @@ __global__ void __launch_bounds__(128) pool_draw_kernel(long long pool_size, int
   double uc = u01_from_bits(o[0], o[1]), us = u01_from_bits(o[2], o[3]);
   int center = (int)((double)m * uc + 1.0);
   if (center > m) center = m;
-  double uu = hig_inv_u_d(us, v[j], w[j], (double)m);
+  double uu;
+  if (sigma_exact) {
+    uu = hig_inv_u_d(us, v[j], w[j], (double)m);
+  } else {
+    RngKey k2 = key;
+    k2.sweep = key.sweep ^ ((uint32_t)(e >> 32) << 20);  // entries beyond 2^32 (never at the shapes in scope)
+    SubStream rs(k2, U_POOL_SIGMA, (uint32_t)e, (uint32_t)j);
+    uu = hig_draw_u_d(rs, v[j], w[j], (double)m);
+  }
   double sigma = -1.0 / log(uu);
   pcen[t] = (uint8_t)center;
   psig[t] = sigma;

@@ -33,6 +33,7 @@ struct SmWork {
   int* anchors = nullptr;  // alias of info->i1,i2 (two ints)
   int *H = nullptr, *cnt = nullptr;
   double* LL2 = nullptr;      // [n][2]
+  double *rg_dl = nullptr, *rg_lgt = nullptr, *LT = nullptr;  // [n], [n], [n+3]
   double* rowvals = nullptr;  // [4][n+2]
   double* partial = nullptr;  // [4][RB]
   double* terms = nullptr;    // [24]
@@ -156,14 +157,36 @@ __global__ void __launch_bounds__(256) sm_ll2_kernel(const uint8_t* __restrict__
   if (lane == 0) LL2[w] = -dot - sden[slot];
 }
 
-// Restricted Gibbs allocation scan over S (split_merge.cpp:186-216).  One warp; 32 consecutive
-// members are evaluated against the same pair of counts, the first member whose draw flips its
-// side is applied and the evaluation restarts after it -- identical to the sequential scan.
-// Two-way Rcpp::sample: probabilities sorted descending by revsort (on a tie the second entry
-// comes first), pick the first if u <= p_first, else the second.
-__global__ void __launch_bounds__(32) sm_rgibbs_kernel(const SmInfo* info, const double* __restrict__ LL2,
-                                                       const double* u_inj, RngKey key, int* __restrict__ z,
-                                                       const int* enable, int enable_val) {
+// log table LT[k] = log(k), k = 0..n+2 (member counts of the restricted scans)
+__global__ void sm_logtable_kernel(int len, double* __restrict__ LT) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < len) LT[k] = k > 0 ? log((double)k) : -CUDART_INF;
+}
+
+// Restricted Gibbs allocation scan over S (split_merge.cpp:186-216), in two phases.
+//
+// The two-way Rcpp::sample (split_merge.cpp:215) walks the two probabilities in descending order
+// (revsort; on a tie the SECOND entry comes first) and takes the first when u <= p_first.  With
+// D = (log n_1 + LL_1) - (log n_2 + LL_2) the larger probability is 1/(1+exp(-|D|)), so the member goes
+// to the larger side iff |D| >= logit(u), to the other side otherwise.  logit(u) and LL_1 - LL_2 do not
+// depend on the running counts, so phase 1 evaluates them for every member in parallel, and the
+// sequential phase 2 only needs a table look-up of log(count) and two comparisons per member.
+// Phase 2 runs on one warp: 32 consecutive members are decided against the same counts, the first one
+// that changes side is applied, and the evaluation restarts after it (same result as one at a time).
+__global__ void __launch_bounds__(256) sm_rg_prepare_kernel(const SmInfo* info, const double* __restrict__ LL2,
+                                                            const double* u_inj, RngKey key, double* __restrict__ dl,
+                                                            double* __restrict__ lgt, const int* enable, int enable_val) {
+  if (enable && *enable != enable_val) return;
+  int pos = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pos >= info->nS) return;
+  const double u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
+  dl[pos] = LL2[2 * (size_t)pos] - LL2[2 * (size_t)pos + 1];
+  lgt[pos] = log(u / (1.0 - u));
+}
+
+__global__ void __launch_bounds__(32) sm_rgibbs_kernel(const SmInfo* info, const double* __restrict__ dl,
+                                                       const double* __restrict__ lgt, const double* __restrict__ LT,
+                                                       int* __restrict__ z, const int* enable, int enable_val) {
   if (enable && *enable != enable_val) return;
   const int nS = info->nS, lane = threadIdx.x;
   // side counts including the anchors i_1 (side 0) and i_2 (side 1)
@@ -174,36 +197,24 @@ __global__ void __launch_bounds__(32) sm_rgibbs_kernel(const SmInfo* info, const
   for (int base = 0; base < nS; base += 32) {
     const int pos = base + lane;
     const bool valid = pos < nS;
-    double l0 = 0, l1 = 0, u = 0.5;
+    double d0 = 0.0, lg = 0.0;
     int zz = 0;
     if (valid) {
-      l0 = LL2[2 * (size_t)pos];
-      l1 = LL2[2 * (size_t)pos + 1];
-      u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
+      d0 = dl[pos];
+      lg = lgt[pos];
       zz = z[pos];
     }
     int start = 0;
     while (start < 32) {
+      // log-count difference seen by a member currently on side 0 / side 1 (itself excluded)
+      const double dA = LT[nA - 1] - LT[nB], dB = LT[nA] - LT[nB - 1];
       int newz = zz;
       if (valid && lane >= start) {
-        double a0 = log((double)(nA - (zz == 0))) + l0;
-        double a1 = log((double)(nB - (zz == 1))) + l1;
-        double mx = a0 > a1 ? a0 : a1;
-        double p0 = exp(a0 - mx), p1 = exp(a1 - mx);
-        double sm = 0.0;
-        sm += p0;
-        sm += p1;
-        p0 = p0 / sm;
-        p1 = p1 / sm;
-        double s2 = 0.0;  // Rcpp Normalize()
-        s2 += p0;
-        s2 += p1;
-        p0 /= s2;
-        p1 /= s2;
-        if (p0 > p1)
-          newz = (u <= p0) ? 0 : 1;
+        const double D = (zz == 0 ? dA : dB) + d0;
+        if (D > 0.0)
+          newz = (D >= lg) ? 0 : 1;
         else
-          newz = (u <= p1) ? 1 : 0;
+          newz = (-D >= lg) ? 1 : 0;
       }
       unsigned ch = __ballot_sync(SMG_FULL, valid && lane >= start && newz != zz);
       if (!ch) break;
@@ -523,6 +534,11 @@ static int sm_alloc(smg_chain* ch) {
   SMG_CUDA(cudaMalloc(&W->H, (size_t)SH_N * ch->pp * ch->mmax * 4));
   SMG_CUDA(cudaMalloc(&W->cnt, SH_N * 4 + 4));
   SMG_CUDA(cudaMalloc(&W->LL2, (size_t)n * 2 * 8));
+  SMG_CUDA(cudaMalloc(&W->rg_dl, (size_t)n * 8));
+  SMG_CUDA(cudaMalloc(&W->rg_lgt, (size_t)n * 8));
+  SMG_CUDA(cudaMalloc(&W->LT, (size_t)(n + 3) * 8));
+  sm_logtable_kernel<<<(n + 3 + 255) / 256, 256, 0, ch->st>>>(n + 3, W->LT);
+  SMG_CUDA(cudaGetLastError());
   SMG_CUDA(cudaMalloc(&W->rowvals, (size_t)4 * (n + 2) * 8));
   SMG_CUDA(cudaMalloc(&W->partial, (size_t)4 * SM_RB * 8));
   SMG_CUDA(cudaMalloc(&W->terms, 24 * 8));
@@ -546,7 +562,7 @@ static void sm_free(smg_chain* ch) {
   SmWork* W = ch->sm;
   if (!W) return;
   void* ptrs[] = {W->S,      W->zL,     W->zStar,    W->zState,   W->info,   W->plan, W->H,      W->cnt,
-                  W->LL2,    W->rowvals, W->partial, W->terms,    W->jobs,   W->u_pair, W->u_prior_c, W->u_prior_s,
+                  W->LL2,    W->rg_dl, W->rg_lgt, W->LT, W->rowvals, W->partial, W->terms,    W->jobs,   W->u_pair, W->u_prior_c, W->u_prior_s,
                   W->u_launch, W->u_rg, W->u_rg_c,   W->u_rg_s,   W->u_mg_c, W->u_mg_s, W->u_accept};
   for (void* q : ptrs)
     if (q) cudaFree(q);
@@ -611,6 +627,7 @@ static int sm_phi(smg_chain* ch, int j0, int nj, int prior, uint32_t sub, const 
   A.u_stride = ch->p;
   A.key = mk_key(ch, sub);
   A.prior = prior;
+  A.sigma_exact = ch->sigma_exact;
   A.enable = enable;
   A.status = ch->status;
   dim3 grid(sm_cdiv(ch->pp, 128), nj);
@@ -645,8 +662,10 @@ static int sm_restricted_scan(smg_chain* ch, int* z, int slotA, int slotB, int h
   sm_ll2_kernel<<<sm_cdiv(2ll * ch->n * 32, 256), 256, 0, ch->st>>>(ch->X, ch->pp, W->S, W->info, ch->cen[cur],
                                                                   ch->isg[cur], ch->sden[cur], slotA, slotB, W->LL2,
                                                                   enable, 1);
-  sm_rgibbs_kernel<<<1, 32, 0, ch->st>>>(W->info, W->LL2, u_rg, mk_key(ch, SUB_SM_RG + q), z, enable, 1);
-  ch->h_launches += 2;
+  sm_rg_prepare_kernel<<<sm_cdiv(ch->n, 256), 256, 0, ch->st>>>(W->info, W->LL2, u_rg, mk_key(ch, SUB_SM_RG + q), W->rg_dl,
+                                                               W->rg_lgt, enable, 1);
+  sm_rgibbs_kernel<<<1, 32, 0, ch->st>>>(W->info, W->rg_dl, W->rg_lgt, W->LT, z, enable, 1);
+  ch->h_launches += 3;
   SMG_CUDA(cudaGetLastError());
   if (sm_hist(ch, z, h0)) return SMG_ERR_CUDA;
   return sm_phi(ch, j0, 2, 0, SUB_SM_RG + q, uc, us, enable);

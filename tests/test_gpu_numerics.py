@@ -70,3 +70,23 @@ def test_logdensity_hig_golden_and_oracle():
     # the density is a difference of lgamma-sized addends ((v+w) log(v+w)): 1e-12 relative to the largest addend
     scale = np.maximum(np.maximum(1.0, np.abs(ref)), (v + w) * np.log(v + w))
     assert np.max(np.abs(got - ref) / scale) < 1e-12
+
+
+def test_production_sigma_sampler_has_the_hig_law():
+    """The Beta-rejection sampler (hyperg.cpp:359-368 branch) is checked in distribution:
+    KS against the exact CDF in u-space, I_x(w+1,v-1)/I_xmax(w+1,v-1), x = u(m-1)/(1+u(m-1))."""
+    from scipy import special, stats
+    from split_and_merge_gibbs_sampling_b200 import rhig_u
+    cases = [(6, 0.25, 2), (6, 0.25, 5), (3, 0.5, 6), (1.5, 0.25, 3), (8, 18.25, 2), (10, 40.25, 2), (1306, 700.25, 5),
+             (40, 25.25, 4)]
+    for (v, w, m) in cases:
+        u = rhig_u(20000, v, w, m, seed=3)
+        assert np.all((u > 0) & (u < 1))
+        a, b, xmax = w + 1.0, v - 1.0, (m - 1.0) / m
+
+        def cdf(uu):
+            x = uu * (m - 1) / (1 + uu * (m - 1))
+            return special.betainc(a, b, x) / special.betainc(a, b, xmax)
+        assert stats.kstest(u, cdf).pvalue > 1e-3, (v, w, m)
+    # draws of different seeds / sites are different streams
+    assert not np.array_equal(rhig_u(100, 6, 0.25, 2, seed=1), rhig_u(100, 6, 0.25, 2, seed=2))
