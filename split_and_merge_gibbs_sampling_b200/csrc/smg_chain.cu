@@ -39,6 +39,7 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
+  SMG_CUDA(cudaFuncSetAttribute(neal8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES));
   if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
   if (dalloc(&ch->attr, pp) || dalloc(&ch->v, pp) || dalloc(&ch->w, pp)) return SMG_ERR_CUDA;
   for (int b = 0; b < 2; b++) {
@@ -152,7 +153,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.log_gamma_m = std::log(ch->gamma / ch->m_aux);
   A.status = ch->status;
   A.stats = ch->stats_d;
-  neal8_scan_kernel<<<1, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);
+  neal8_scan_kernel<<<1, SMG_SCAN_WARPS * 32, SCAN_SMEM_BYTES, ch->st>>>(A);
   SMG_CUDA(cudaGetLastError());
   // back to canonical form: labels in c, parameters in label order in the other buffer
   const int nx = ch->cur ^ 1;

@@ -287,6 +287,24 @@ __device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, in
   }
 }
 
+// ---- asynchronous copies global -> shared (LDGSTS); one commit group per prefetched round
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+#define SCAN_WB_STRIDE (SMG_MAX_ENTRIES + 2)  // doubles per warp buffer: entries + one slot for c[i]
+#define SCAN_SMEM_BYTES (2 * SMG_SCAN_WARPS * SCAN_WB_STRIDE * 8)
+
 __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(ScanArgs A) {
   __shared__ int s_cnt[SMG_MAX_SLOTS];
   __shared__ double s_logc[SMG_MAX_SLOTS];
@@ -298,6 +316,9 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
   __shared__ int s_fillw[SMG_MAX_SLOTS];  // next window size
   __shared__ int s_K, s_i0, s_next, s_err, s_minfill;
   __shared__ unsigned long long s_stats[4];
+  // per-warp double buffer: the likelihood entries (and c[i]) of the observation a warp evaluates in the
+  // current round, and of the one it will evaluate in the next round if the current one has no event
+  extern __shared__ __align__(16) double s_wb[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = A.n, pp = A.pp, m = A.m_aux;
@@ -329,17 +350,39 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     return;
   }
 
+  // issue the asynchronous loads of observation i (this warp's) into buffer `b`:
+  // entry e < K : LL[i][slot of label e] ; K <= e < K+m : LLaux[i][e-K] ; last slot: c[i]
+  auto prefetch = [&](int b, int i) {
+    double* wb = s_wb + ((size_t)b * SMG_SCAN_WARPS + warp) * SCAN_WB_STRIDE;
+    if (i < n) {
+      const int K = s_K, ne = K + m;
+      for (int e = lane; e < ne && e < SMG_MAX_ENTRIES; e += 32) {
+        if (e < K) {
+          const int slot = s_l2s[e];
+          if (slot < A.ldl) cp_async8(&wb[e], &A.LL[(size_t)i * A.ldl + slot]);
+        } else {
+          cp_async8(&wb[e], &A.LLaux[(size_t)i * m + (e - K)]);
+        }
+      }
+      if (lane == 0) cp_async4(&wb[SMG_MAX_ENTRIES], &A.c[i]);
+    }
+    cp_async_commit();
+  };
+
+  int cb = 0;  // buffer holding (or receiving) the current round
+  prefetch(cb, warp);
+
   for (;;) {
     const int i0 = s_i0;
     if (i0 >= n) break;
-    if (s_minfill < n && i0 + SMG_SCAN_WARPS > s_minfill) {
-      // some born column is materialised only up to s_minfill: extend every lagging window
+    // ---- keep the windows of born columns ahead of everything this round reads or prefetches
+    if (s_minfill < n && i0 + 2 * SMG_SCAN_WARPS > s_minfill) {
       const int Kx = s_K;
       for (int e = 0; e < Kx; e++) {
         const int slot = s_l2s[e];
         if (slot < K0 || slot >= A.ldl) continue;
         const int f0 = s_fill[slot];
-        if (f0 >= n || f0 >= i0 + 2 * SMG_SCAN_WARPS) continue;
+        if (f0 >= n || f0 >= i0 + 4 * SMG_SCAN_WARPS) continue;
         const int f1 = min(n, f0 + s_fillw[slot]);
         scan_fill_column(A, slot, f0, f1, warp, lane);
         __syncthreads();
@@ -362,9 +405,14 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     const int i = i0 + warp;
     const int K = s_K;
     const int ne = K + m;
+    // next round's loads (valid if this round has no event), then wait for this round's
+    prefetch(cb ^ 1, i + SMG_SCAN_WARPS);
+    cp_async_wait<1>();
+    __syncwarp();
+    double* wb = s_wb + ((size_t)cb * SMG_SCAN_WARPS + warp) * SCAN_WB_STRIDE;
     int code = EVT_NONE;
     if (i < n && ne <= SMG_MAX_ENTRIES) {
-      const int old_slot = A.c[i];
+      const int old_slot = *reinterpret_cast<const int*>(&wb[SMG_MAX_ENTRIES]);
       const bool singleton = (s_cnt[old_slot] == 1);
       const uint8_t* xrow = A.X + (size_t)i * pp;
       double lg[SMG_EPL];
@@ -377,7 +425,7 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         const int e = q * 32 + lane;
         int slot = (e < K) ? s_l2s[e] : -1;
         double ll = 0.0;
-        if (slot >= 0 && slot < A.ldl) ll = A.LL[(size_t)i * A.ldl + slot];
+        if (slot >= 0 && slot < A.ldl) ll = wb[e];
         // born columns beyond the LL matrix width: evaluate on the fly, one at a time, whole warp
         unsigned dyn = __ballot_sync(SMG_FULL, slot >= A.ldl);
         while (dyn) {
@@ -406,7 +454,7 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         const int e = q * 32 + lane;
         if (e >= K && e < ne) {
           const int a = e - K;
-          double ll = (singleton && a == 0) ? ll_own : A.LLaux[(size_t)i * m + a];
+          double ll = (singleton && a == 0) ? ll_own : wb[e];
           lg[q] = A.log_gamma_m + ll;
         }
       }
@@ -547,6 +595,7 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         s_i0 = i0 + SMG_SCAN_WARPS;
         s_stats[0]++;
       }
+      cb ^= 1;  // the prefetched round becomes the current one
       __syncthreads();
       continue;
     }
@@ -583,7 +632,8 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
         scan_fill_column(A, new_slot, ie + 1, min(n, ie + 1 + SCAN_FILL_W0), warp, lane);
       }
     }
-    __syncthreads();  // everyone has read the pre-event state
+    cp_async_wait<0>();  // drain the speculative prefetch before its buffer is reused
+    __syncthreads();     // everyone has read the pre-event state
     if (tid == 0) {
       s_stats[0]++;
       s_stats[1]++;
@@ -639,7 +689,11 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     }
     __threadfence_block();
     __syncthreads();
+    // restart right after the event with fresh loads under the new state
+    cb ^= 1;
+    prefetch(cb, ie + 1 + warp);
   }
+  cp_async_wait<0>();
   __syncthreads();
   // publish: K, counts by slot, slot->label map
   for (int s = tid; s < A.NS && s < SMG_MAX_SLOTS; s += blockDim.x) {
