@@ -39,7 +39,6 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
-  SMG_CUDA(cudaFuncSetAttribute(neal8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES));
   if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
   if (dalloc(&ch->attr, pp) || dalloc(&ch->v, pp) || dalloc(&ch->w, pp)) return SMG_ERR_CUDA;
   for (int b = 0; b < 2; b++) {
@@ -55,7 +54,7 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->c, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
       dalloc(&ch->slot2label, NST))
     return SMG_ERR_CUDA;
-  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) ||
+  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n) ||
       dalloc(&ch->aux_e, (size_t)n * ch->m_aux))
     return SMG_ERR_CUDA;
   const size_t P = (size_t)ch->pool_size;
@@ -81,7 +80,7 @@ static void chain_free(smg_chain* ch) {
   sm_free(ch);
   void* ptrs[] = {ch->X,      ch->attr,   ch->v,         ch->w,          ch->cen[0], ch->cen[1], ch->sig[0], ch->sig[1],
                   ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
-                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
+                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->mrg, ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
                   ch->stats_d, ch->tape_d, ch->uc_d,     ch->us_d};
   for (void* q : ptrs)
@@ -133,6 +132,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.X = ch->X;
   A.LL = ch->LL;
   A.LLaux = ch->LLaux;
+  A.mrg = ch->mrg;
   A.aux_e = ch->aux_e;
   A.u_alloc = tape ? tape + ch->m_aux : nullptr;
   A.u_stride = ch->m_aux + 1;
@@ -153,7 +153,9 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.log_gamma_m = std::log(ch->gamma / ch->m_aux);
   A.status = ch->status;
   A.stats = ch->stats_d;
-  neal8_scan_kernel<<<1, SMG_SCAN_WARPS * 32, SCAN_SMEM_BYTES, ch->st>>>(A);
+  scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, ch->LLaux,
+                                                                          ch->c, ch->counts, A.log_gamma_m, ch->mrg);
+  neal8_scan_kernel<<<1, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);
   SMG_CUDA(cudaGetLastError());
   // back to canonical form: labels in c, parameters in label order in the other buffer
   const int nx = ch->cur ^ 1;
@@ -166,7 +168,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   SMG_CUDA(cudaGetLastError());
   std::swap(ch->counts, ch->counts_slot);
   ch->cur = nx;
-  ch->h_launches += 3;
+  ch->h_launches += 4;
   if (timed) cudaEventRecord(ch->ev[3], ch->st);
   return 0;
 }

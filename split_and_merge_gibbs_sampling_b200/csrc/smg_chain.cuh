@@ -71,7 +71,7 @@ struct smg_chain {
   double* den = nullptr;
   int cur = 0;
   int *c = nullptr, *K = nullptr, *counts = nullptr, *counts_slot = nullptr, *slot2label = nullptr;
-  double *LL = nullptr, *LLaux = nullptr;
+  double *LL = nullptr, *LLaux = nullptr, *mrg = nullptr;
   int* aux_e = nullptr;
   uint8_t* pcen = nullptr;
   double *psig = nullptr, *pisg = nullptr, *pden = nullptr, *psden = nullptr;

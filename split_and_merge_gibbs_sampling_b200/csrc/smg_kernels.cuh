@@ -220,8 +220,9 @@ __global__ void __launch_bounds__(256) aux_ll_kernel(const uint8_t* __restrict__
 struct ScanArgs {
   int n, pp, m_aux, ldl, K0cap;   // K0cap: number of valid LL columns (= K at pass start)
   const uint8_t* X;
-  double* LL;     // [n][ldl]; columns >= K0 are filled in windows for clusters born during the pass
+  double* LL;     // [n][ldl]; columns >= K0 are filled chunk by chunk for clusters born during the pass
   const double* LLaux;
+  const double* mrg;  // [n] dominance margins under the start-of-pass counts (scan_margin_kernel)
   const int* aux_e;
   const double* u_alloc;  // injected allocation uniforms (tape + m_aux, stride), or null
   int u_stride;
@@ -245,8 +246,6 @@ struct ScanArgs {
 };
 
 #define EVT_NONE (-1)
-#define SCAN_FILL_W0 128      // first window (rows) materialised for a newly born column
-#define SCAN_FILL_WMAX 32768  // windows double up to this many rows
 
 // All 32 warps of the scan CTA materialise LL[r0..r1)[slot] for a column born during the pass.
 // Four rows per warp are in flight at a time; the value of each entry is the one warp_mismatch_dot
@@ -287,59 +286,109 @@ __device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, in
   }
 }
 
-// ---- asynchronous copies global -> shared (LDGSTS); one commit group per prefetched round
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+// ---------------------------------------------------------------------------------------------
+// Dominance margins.  Under the counts at the start of the pass, observation i keeps its cluster
+// `own` with certainty when
+//     mrg[i] = (log(n_own - 1) + LL[i][own]) - max(others: log n_k + LL[i][k],  aux: log(gamma/m) + LLaux[i][a])
+// exceeds SCAN_DOMINANCE nats: every other entry then carries less than e^-44 of the own mass, the
+// normalised own probability rounds to exactly 1.0 in fp64 (256 * e^-44 < 2^-54) and Rcpp::sample returns
+// it for every u (neal8.cpp:95-102).  The scan keeps the test valid while counts drift (see below).
+// One warp per observation, all SMs; reads the LL block once (8*(K+m) B per row), writes 8 B per row.
+// ---------------------------------------------------------------------------------------------
+#define SCAN_DOMINANCE 44.0
+#define SCAN_SLACK 1e-6  // covers the rounding of the drift arithmetic
+
+__global__ void __launch_bounds__(256) scan_margin_kernel(int n, const int* __restrict__ Kptr, int ldl, int m_aux,
+                                                          const double* __restrict__ LL,
+                                                          const double* __restrict__ LLaux, const int* __restrict__ c,
+                                                          const int* __restrict__ counts, double log_gamma_m,
+                                                          double* __restrict__ mrg) {
+  __shared__ double s_lc[SMG_MAX_ENTRIES], s_lcm1[SMG_MAX_ENTRIES];
+  const int K = min(*Kptr, SMG_MAX_ENTRIES);
+  for (int s = threadIdx.x; s < K; s += blockDim.x) {
+    const int cnt = counts[s];
+    s_lc[s] = cnt > 0 ? log((double)cnt) : -CUDART_INF;
+    s_lcm1[s] = cnt > 1 ? log((double)(cnt - 1)) : -CUDART_INF;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+    const int own = c[i];
+    const double* row = LL + (size_t)i * ldl;
+    double a_own = -CUDART_INF, best = -CUDART_INF;
+    for (int e = lane; e < K; e += 32) {
+      const double ll = row[e];
+      if (e == own)
+        a_own = s_lcm1[e] + ll;
+      else
+        best = fmax(best, s_lc[e] + ll);
+    }
+    for (int a = lane; a < m_aux; a += 32) best = fmax(best, log_gamma_m + LLaux[(size_t)i * m_aux + a]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a_own = fmax(a_own, shfl_xor_d(a_own, o));
+      best = fmax(best, shfl_xor_d(best, o));
+    }
+    if (lane == 0) mrg[i] = (a_own > -CUDART_INF) ? a_own - best : -CUDART_INF;
+  }
 }
 
-#define SCAN_WB_STRIDE (SMG_MAX_ENTRIES + 2)  // doubles per warp buffer: entries + one slot for c[i]
-#define SCAN_SMEM_BYTES (2 * SMG_SCAN_WARPS * SCAN_WB_STRIDE * 8)
+#define SCAN_CHUNK (SMG_SCAN_WARPS * 32)  // observations screened per step: one per thread
 
+// =============================================================================
+// K2: the scan proper (one resident CTA of 32 warps).
+//
+// Chunks of 1024 consecutive observations.  (1) Screen: each thread tests its observation's margin
+// against the drift of the counts since the start of the pass,
+//     mrg[i] - dminus[own] - Dplus > SCAN_DOMINANCE,    dminus[k] = log(n0_k - 1) - log(n_k - 1),
+//                                                        Dplus >= max_k (log n_k - log n0_k),
+// and against every cluster born during the pass (whose columns are materialised chunk by chunk).
+// Observations that pass are certain non-events.  (2) The others ("undecided") are evaluated exactly,
+// 32 per round (one warp each) against the same state: Rcpp::sample's descending-order inverse CDF.
+// The first one whose draw changes the state (an event) is applied, the rest of the chunk is screened
+// again, and evaluation restarts right after it -- the result is the one-at-a-time scan's.
+// =============================================================================
 __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(ScanArgs A) {
   __shared__ int s_cnt[SMG_MAX_SLOTS];
   __shared__ double s_logc[SMG_MAX_SLOTS];
   __shared__ double s_logcm1[SMG_MAX_SLOTS];
   __shared__ int s_l2s[SMG_MAX_SLOTS];
   __shared__ int s_s2l[SMG_MAX_SLOTS];
+  __shared__ double s_lc0[SMG_MAX_ENTRIES];    // log n0_k of the clusters present at the start
+  __shared__ double s_lcm1_0[SMG_MAX_ENTRIES]; // log (n0_k - 1)
+  __shared__ double s_dminus[SMG_MAX_ENTRIES];
+  __shared__ double s_Dplus;
   __shared__ int s_evt[SMG_SCAN_WARPS];
-  __shared__ int s_fill[SMG_MAX_SLOTS];   // rows [.., s_fill) of a born column are materialised
-  __shared__ int s_fillw[SMG_MAX_SLOTS];  // next window size
-  __shared__ int s_K, s_i0, s_next, s_err, s_minfill;
+  __shared__ int s_row[SMG_SCAN_WARPS];
+  __shared__ unsigned s_und[SMG_SCAN_WARPS];  // undecided rows of the current chunk (bit per row)
+  __shared__ int s_K, s_next, s_err;
   __shared__ unsigned long long s_stats[4];
-  // per-warp double buffer: the likelihood entries (and c[i]) of the observation a warp evaluates in the
-  // current round, and of the one it will evaluate in the next round if the current one has no event
-  extern __shared__ __align__(16) double s_wb[];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = A.n, pp = A.pp, m = A.m_aux;
   const int K0 = *A.Kptr;
 
   for (int s = tid; s < SMG_MAX_SLOTS; s += blockDim.x) {
-    int cnt = (s < K0) ? A.counts[s] : 0;
+    const int cnt = (s < K0) ? A.counts[s] : 0;
+    const double lc = cnt > 0 ? log((double)cnt) : -CUDART_INF;
+    const double lcm1 = cnt > 1 ? log((double)(cnt - 1)) : -CUDART_INF;
     s_cnt[s] = cnt;
-    s_logc[s] = cnt > 0 ? log((double)cnt) : -CUDART_INF;
-    s_logcm1[s] = cnt > 1 ? log((double)(cnt - 1)) : -CUDART_INF;
+    s_logc[s] = lc;
+    s_logcm1[s] = lcm1;
     s_l2s[s] = s;
     s_s2l[s] = (s < K0) ? s : -1;
-    s_fill[s] = n;
-    s_fillw[s] = SCAN_FILL_W0;
+    if (s < SMG_MAX_ENTRIES) {
+      s_lc0[s] = lc;
+      s_lcm1_0[s] = lcm1;
+      s_dminus[s] = (cnt > 1) ? 0.0 : CUDART_INF;
+    }
   }
   if (tid == 0) {
     s_K = K0;
-    s_i0 = 0;
     s_next = K0;
     s_err = 0;
-    s_minfill = n;
+    s_Dplus = 0.0;
     s_stats[0] = s_stats[1] = s_stats[2] = s_stats[3] = 0;
     if (K0 + m > SMG_MAX_ENTRIES) s_err |= ST_TOO_MANY_ENTRIES;
     if (K0 > A.K0cap) s_err |= ST_LL_COLS;
@@ -350,351 +399,387 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     return;
   }
 
-  // issue the asynchronous loads of observation i (this warp's) into buffer `b`:
-  // entry e < K : LL[i][slot of label e] ; K <= e < K+m : LLaux[i][e-K] ; last slot: c[i]
-  auto prefetch = [&](int b, int i) {
-    double* wb = s_wb + ((size_t)b * SMG_SCAN_WARPS + warp) * SCAN_WB_STRIDE;
-    if (i < n) {
-      const int K = s_K, ne = K + m;
-      for (int e = lane; e < ne && e < SMG_MAX_ENTRIES; e += 32) {
-        if (e < K) {
-          const int slot = s_l2s[e];
-          if (slot < A.ldl) cp_async8(&wb[e], &A.LL[(size_t)i * A.ldl + slot]);
-        } else {
-          cp_async8(&wb[e], &A.LLaux[(size_t)i * m + (e - K)]);
-        }
-      }
-      if (lane == 0) cp_async4(&wb[SMG_MAX_ENTRIES], &A.c[i]);
+  bool abort_pass = false;
+  // this thread's observation of the NEXT chunk (loaded one chunk ahead)
+  int nx_own = 0;
+  double nx_mg = 0.0;
+  if (tid < n) {
+    nx_own = A.c[tid];
+    nx_mg = A.mrg[tid];
+  }
+
+  for (int i0 = 0; i0 < n && !abort_pass; i0 += SCAN_CHUNK) {
+    const int nrows = min(SCAN_CHUNK, n - i0);
+    const int my_own = nx_own;
+    const double my_mg = nx_mg;
+    if (i0 + SCAN_CHUNK + tid < n) {
+      nx_own = A.c[i0 + SCAN_CHUNK + tid];
+      nx_mg = A.mrg[i0 + SCAN_CHUNK + tid];
     }
-    cp_async_commit();
-  };
-
-  int cb = 0;  // buffer holding (or receiving) the current round
-  prefetch(cb, warp);
-
-  for (;;) {
-    const int i0 = s_i0;
-    if (i0 >= n) break;
-    // ---- keep the windows of born columns ahead of everything this round reads or prefetches
-    if (s_minfill < n && i0 + 2 * SMG_SCAN_WARPS > s_minfill) {
+    // ---- columns of the clusters born during this pass: materialise this chunk's rows
+    if (s_next > K0) {
       const int Kx = s_K;
       for (int e = 0; e < Kx; e++) {
         const int slot = s_l2s[e];
-        if (slot < K0 || slot >= A.ldl) continue;
-        const int f0 = s_fill[slot];
-        if (f0 >= n || f0 >= i0 + 4 * SMG_SCAN_WARPS) continue;
-        const int f1 = min(n, f0 + s_fillw[slot]);
-        scan_fill_column(A, slot, f0, f1, warp, lane);
-        __syncthreads();
-        if (tid == 0) {
-          s_fill[slot] = f1;
-          s_fillw[slot] = min(SCAN_FILL_WMAX, s_fillw[slot] * 2);
-        }
-        __syncthreads();
-      }
-      if (tid == 0) {
-        int mf = n;
-        for (int e = 0; e < Kx; e++) {
-          const int slot = s_l2s[e];
-          if (slot >= K0 && slot < A.ldl) mf = min(mf, s_fill[slot]);
-        }
-        s_minfill = mf;
+        if (slot >= K0 && slot < A.ldl) scan_fill_column(A, slot, i0, i0 + nrows, warp, lane);
       }
       __syncthreads();
     }
-    const int i = i0 + warp;
-    const int K = s_K;
-    const int ne = K + m;
-    // next round's loads (valid if this round has no event), then wait for this round's
-    prefetch(cb ^ 1, i + SMG_SCAN_WARPS);
-    cp_async_wait<1>();
-    __syncwarp();
-    double* wb = s_wb + ((size_t)cb * SMG_SCAN_WARPS + warp) * SCAN_WB_STRIDE;
-    int code = EVT_NONE;
-    if (i < n && ne <= SMG_MAX_ENTRIES) {
-      const int old_slot = *reinterpret_cast<const int*>(&wb[SMG_MAX_ENTRIES]);
-      const bool singleton = (s_cnt[old_slot] == 1);
-      const uint8_t* xrow = A.X + (size_t)i * pp;
-      double lg[SMG_EPL];
-      double ll_own = 0.0;
-      // ---- existing clusters (neal8.cpp:40-56)
-#pragma unroll
-      for (int q = 0; q < SMG_EPL; q++) {
-        lg[q] = -CUDART_INF;
-        if (q * 32 >= K) continue;
-        const int e = q * 32 + lane;
-        int slot = (e < K) ? s_l2s[e] : -1;
-        double ll = 0.0;
-        if (slot >= 0 && slot < A.ldl) ll = wb[e];
-        // born columns beyond the LL matrix width: evaluate on the fly, one at a time, whole warp
-        unsigned dyn = __ballot_sync(SMG_FULL, slot >= A.ldl);
-        while (dyn) {
-          int src = __ffs(dyn) - 1;
-          dyn &= dyn - 1;
-          int ds = __shfl_sync(SMG_FULL, slot, src);
-          double dot = warp_mismatch_dot(xrow, A.cen + (size_t)ds * pp, A.isg + (size_t)ds * pp, pp, lane);
-          if (lane == src) ll = -dot - A.sden[ds];
-        }
-        if (slot >= 0) {
-          const bool own = (slot == old_slot);
-          const int cx = s_cnt[slot] - (own ? 1 : 0);
-          if (own) ll_own = ll;
-          lg[q] = (cx > 0) ? ((own ? s_logcm1[slot] : s_logc[slot]) + ll) : -CUDART_INF;
-        }
-      }
-      if (singleton) {  // own parameters become aux slot 0 (neal8.cpp:72-75)
-        unsigned who = __ballot_sync(SMG_FULL, ll_own != 0.0);
-        // ll_own is set by exactly one lane; LL is strictly negative so != 0 identifies it
-        int src = who ? (__ffs(who) - 1) : 0;
-        ll_own = shfl_d(ll_own, src);
-      }
-      // ---- auxiliary components (neal8.cpp:78-92)
-#pragma unroll
-      for (int q = 0; q < SMG_EPL; q++) {
-        const int e = q * 32 + lane;
-        if (e >= K && e < ne) {
-          const int a = e - K;
-          double ll = (singleton && a == 0) ? ll_own : wb[e];
-          lg[q] = A.log_gamma_m + ll;
-        }
-      }
-      // ---- max, exp, sum  (neal8.cpp:95-96)
-      uint64_t mykey = 0;
-      int myarg = 0x7fffffff;
-#pragma unroll
-      for (int q = 0; q < SMG_EPL; q++) {
-        if (q * 32 >= ne) continue;
-        const int e = q * 32 + lane;
-        if (e < ne) {
-          uint64_t k = sort_key(lg[q]);
-          if (k > mykey) {
-            mykey = k;
-            myarg = e;
+
+    int start = 0;          // rows [0, start) of the chunk are final
+    bool screened = false;  // s_und valid for the current state
+    while (start < nrows) {
+      // ================= screen: one thread per row =================
+      if (!screened) {
+        bool und = false;
+        if (tid >= start && tid < nrows) {
+          const double Dp = s_Dplus;
+          // own slot is always a start-of-pass cluster for a row the scan has not reached yet
+          und = !(my_mg - s_dminus[my_own] - Dp > SCAN_DOMINANCE + SCAN_SLACK);
+          if (!und && s_next > K0) {
+            const int i = i0 + tid;
+            const double thr = s_logcm1[my_own] + A.LL[(size_t)i * A.ldl + my_own] - (SCAN_DOMINANCE + SCAN_SLACK);
+            const int K = s_K;
+            for (int e = 0; e < K; e++) {
+              const int slot = s_l2s[e];
+              if (slot < K0) continue;
+              if (slot >= A.ldl || !(s_logc[slot] + __ldcg(&A.LL[(size_t)i * A.ldl + slot]) < thr)) {
+                und = true;
+                break;
+              }
+            }
           }
         }
-      }
-      const uint64_t maxkey = warp_max_key(mykey);
-      const double M = key_to_double(maxkey);
-      // smallest index attaining the max
-      const int argmax = (int)__reduce_min_sync(SMG_FULL, (unsigned)((mykey == maxkey) ? myarg : 0x7fffffff));
-      double pe[SMG_EPL];
-      double lsum = 0.0;
-      bool need_exp = false;
-#pragma unroll
-      for (int q = 0; q < SMG_EPL; q++) {
-        pe[q] = 0.0;
-        if (q * 32 >= ne) continue;
-        const int e = q * 32 + lane;
-        if (e < ne) {
-          double d = lg[q] - M;
-          if (d == 0.0)
-            pe[q] = 1.0;
-          else if (d > -746.0)
-            need_exp = true;
+        const unsigned b = __ballot_sync(SMG_FULL, und);
+        if (lane == 0) s_und[warp] = b;
+        screened = true;
+        if (__syncthreads_count(und) == 0) {  // every remaining row of the chunk is a certain non-event
+          if (tid == 0) s_stats[0]++;
+          break;
         }
       }
-      if (__any_sync(SMG_FULL, need_exp)) {
+      // ================= batch: the next 32 undecided rows, one warp each =================
+      int myrow = -1, lastrow = -1;
+      {
+        int seen = 0;
+        for (int wd = start >> 5; wd < (nrows + 31) >> 5; wd++) {
+          unsigned b = s_und[wd];
+          if (wd == (start >> 5)) b &= ~0u << (start & 31);
+          const int cb = __popc(b);
+          if (myrow < 0 && seen + cb > warp) {
+            unsigned bb = b;
+            for (int q = seen; q < warp; q++) bb &= bb - 1;
+            myrow = wd * 32 + __ffs(bb) - 1;
+          }
+          if (seen + cb >= SMG_SCAN_WARPS) {  // the batch ends inside this word
+            unsigned bb = b;
+            for (int q = seen; q < SMG_SCAN_WARPS - 1; q++) bb &= bb - 1;
+            lastrow = wd * 32 + __ffs(bb) - 1;
+            seen = SMG_SCAN_WARPS;
+            break;
+          }
+          seen += cb;
+        }
+        if (seen == 0) {  // nothing left to decide in this chunk
+          if (tid == 0) s_stats[0]++;
+          break;
+        }
+        if (seen < SMG_SCAN_WARPS) lastrow = nrows - 1;  // every remaining undecided row is in this batch
+      }
+      const int K = s_K;
+      const int ne = K + m;
+      int code = EVT_NONE;
+      if (myrow >= 0 && ne > SMG_MAX_ENTRIES) code = -3;
+      if (myrow >= 0 && ne <= SMG_MAX_ENTRIES) {
+        const int i = i0 + myrow;
+        const double* rowp = A.LL + (size_t)i * A.ldl;
+        const double* auxp = A.LLaux + (size_t)i * m;
+        const int old_slot = A.c[i];
+        const bool singleton = (s_cnt[old_slot] == 1);
+        const uint8_t* xrow = A.X + (size_t)i * pp;
+        double lg[SMG_EPL];
+        double ll_own = 0.0;
+        // ---- existing clusters (neal8.cpp:40-56)
+#pragma unroll
+        for (int q = 0; q < SMG_EPL; q++) {
+          lg[q] = -CUDART_INF;
+          if (q * 32 >= K) continue;
+          const int e = q * 32 + lane;
+          int slot = (e < K) ? s_l2s[e] : -1;
+          double ll = 0.0;
+          if (slot >= 0 && slot < A.ldl) ll = __ldcg(&rowp[slot]);
+          // born columns beyond the LL matrix width: evaluate on the fly, one at a time, whole warp
+          unsigned dyn = __ballot_sync(SMG_FULL, slot >= A.ldl);
+          while (dyn) {
+            int src = __ffs(dyn) - 1;
+            dyn &= dyn - 1;
+            int ds = __shfl_sync(SMG_FULL, slot, src);
+            double dot = warp_mismatch_dot(xrow, A.cen + (size_t)ds * pp, A.isg + (size_t)ds * pp, pp, lane);
+            if (lane == src) ll = -dot - A.sden[ds];
+          }
+          if (slot >= 0) {
+            const bool own = (slot == old_slot);
+            const int cx = s_cnt[slot] - (own ? 1 : 0);
+            if (own) ll_own = ll;
+            lg[q] = (cx > 0) ? ((own ? s_logcm1[slot] : s_logc[slot]) + ll) : -CUDART_INF;
+          }
+        }
+        if (singleton) {  // own parameters become aux slot 0 (neal8.cpp:72-75)
+          unsigned who = __ballot_sync(SMG_FULL, ll_own != 0.0);
+          // ll_own is set by exactly one lane; LL is strictly negative so != 0 identifies it
+          int src = who ? (__ffs(who) - 1) : 0;
+          ll_own = shfl_d(ll_own, src);
+        }
+        // ---- auxiliary components (neal8.cpp:78-92)
+#pragma unroll
+        for (int q = 0; q < SMG_EPL; q++) {
+          const int e = q * 32 + lane;
+          if (e >= K && e < ne) {
+            const int a = e - K;
+            double ll = (singleton && a == 0) ? ll_own : auxp[a];
+            lg[q] = A.log_gamma_m + ll;
+          }
+        }
+        // ---- max, exp, sum  (neal8.cpp:95-96)
+        uint64_t mykey = 0;
+        int myarg = 0x7fffffff;
 #pragma unroll
         for (int q = 0; q < SMG_EPL; q++) {
           if (q * 32 >= ne) continue;
           const int e = q * 32 + lane;
           if (e < ne) {
-            double d = lg[q] - M;
-            if (d != 0.0 && d > -746.0) pe[q] = exp(d);
-          }
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < SMG_EPL; q++) lsum += pe[q];
-      const double S = warp_sum(lsum);
-      const double u = get_u(A.u_alloc, (size_t)i * A.u_stride, A.key, U_ALLOC, (uint32_t)i, 0u);
-      const double T = u * S;  // compare against the cumulative sums of the unnormalised weights
-      int new_e;
-      if (!(M > -CUDART_INF) || !(S == S)) {
-        new_e = -2;  // all -Inf or NaN: Rcpp::sample would stop()
-      } else if (T <= 1.0) {
-        new_e = argmax;  // first entry of the descending order already covers u
-      } else {
-        // Rcpp::sample semantics: walk the probabilities in DESCENDING order and return the
-        // first entry whose cumulative sum reaches u.  before(y,x): y precedes x in that order.
-        double G[SMG_EPL];
-#pragma unroll
-        for (int q = 0; q < SMG_EPL; q++) G[q] = 0.0;
-#pragma unroll
-        for (int qy = 0; qy < SMG_EPL; qy++) {
-          if (qy * 32 >= ne) continue;
-          unsigned sig = __ballot_sync(SMG_FULL, pe[qy] > 0.0);
-          while (sig) {
-            int src = __ffs(sig) - 1;
-            sig &= sig - 1;
-            double py = shfl_d(pe[qy], src);
-            int ey = qy * 32 + src;
-#pragma unroll
-            for (int q = 0; q < SMG_EPL; q++) {
-              int ex = q * 32 + lane;
-              if (py > pe[q] || (py == pe[q] && ey < ex)) G[q] += py;
+            uint64_t k = sort_key(lg[q]);
+            if (k > mykey) {
+              mykey = k;
+              myarg = e;
             }
           }
         }
-        // candidate = entry with u*S <= G + p, largest p first (smallest index among ties)
-        uint64_t bestk = 0;
-        int beste = 0x7fffffff;
+        const uint64_t maxkey = warp_max_key(mykey);
+        const double M = key_to_double(maxkey);
+        // smallest index attaining the max
+        const int argmax = (int)__reduce_min_sync(SMG_FULL, (unsigned)((mykey == maxkey) ? myarg : 0x7fffffff));
+        double pe[SMG_EPL];
+        double lsum = 0.0;
+        bool need_exp = false;
 #pragma unroll
         for (int q = 0; q < SMG_EPL; q++) {
-          int ex = q * 32 + lane;
-          if (ex < ne && pe[q] > 0.0 && T <= G[q] + pe[q]) {
-            uint64_t k = sort_key(pe[q]);
-            if (k > bestk || (k == bestk && ex < beste)) {
-              bestk = k;
-              beste = ex;
+          pe[q] = 0.0;
+          if (q * 32 >= ne) continue;
+          const int e = q * 32 + lane;
+          if (e < ne) {
+            double d = lg[q] - M;
+            if (d == 0.0)
+              pe[q] = 1.0;
+            else if (d >= -SCAN_DOMINANCE)
+              need_exp = true;
+          }
+        }
+        if (__any_sync(SMG_FULL, need_exp)) {
+#pragma unroll
+          for (int q = 0; q < SMG_EPL; q++) {
+            if (q * 32 >= ne) continue;
+            const int e = q * 32 + lane;
+            if (e < ne) {
+              double d = lg[q] - M;
+              if (d != 0.0 && d >= -SCAN_DOMINANCE) pe[q] = exp(d);
             }
           }
         }
-        uint64_t wk = warp_max_key(bestk);
-        if (wk == 0) {
-          // fall-through of the reference loop: last entry of the descending order
-          // (smallest probability, largest index among ties)
-          uint64_t mink = ~0ull;
-          int mine = -1;
 #pragma unroll
-          for (int q = 0; q < SMG_EPL; q++) {
-            int ex = q * 32 + lane;
-            if (ex < ne) {
-              uint64_t k = sort_key(pe[q]);
-              if (k < mink || (k == mink && ex > mine)) {
-                mink = k;
-                mine = ex;
+        for (int q = 0; q < SMG_EPL; q++) lsum += pe[q];
+        const double S = warp_sum(lsum);
+        const double u = get_u(A.u_alloc, (size_t)i * A.u_stride, A.key, U_ALLOC, (uint32_t)i, 0u);
+        const double T = u * S;  // compare against the cumulative sums of the unnormalised weights
+        int new_e;
+        if (!(M > -CUDART_INF) || !(S == S)) {
+          new_e = -2;  // all -Inf or NaN: Rcpp::sample would stop()
+        } else if (T <= 1.0) {
+          new_e = argmax;  // first entry of the descending order already covers u
+        } else {
+          // Rcpp::sample semantics: walk the probabilities in DESCENDING order and return the
+          // first entry whose cumulative sum reaches u.  before(y,x): y precedes x in that order.
+          double G[SMG_EPL];
+#pragma unroll
+          for (int q = 0; q < SMG_EPL; q++) G[q] = 0.0;
+#pragma unroll
+          for (int qy = 0; qy < SMG_EPL; qy++) {
+            if (qy * 32 >= ne) continue;
+            unsigned sig = __ballot_sync(SMG_FULL, pe[qy] > 0.0);
+            while (sig) {
+              int src = __ffs(sig) - 1;
+              sig &= sig - 1;
+              double py = shfl_d(pe[qy], src);
+              int ey = qy * 32 + src;
+#pragma unroll
+              for (int q = 0; q < SMG_EPL; q++) {
+                int ex = q * 32 + lane;
+                if (py > pe[q] || (py == pe[q] && ey < ex)) G[q] += py;
               }
             }
           }
-          uint64_t wmin = ~warp_max_key(~mink);
-          new_e = (int)__reduce_max_sync(SMG_FULL, (unsigned)((mink == wmin) ? mine : 0));
+          // candidate = entry with u*S <= G + p, largest p first (smallest index among ties)
+          uint64_t bestk = 0;
+          int beste = 0x7fffffff;
+#pragma unroll
+          for (int q = 0; q < SMG_EPL; q++) {
+            int ex = q * 32 + lane;
+            if (ex < ne && pe[q] > 0.0 && T <= G[q] + pe[q]) {
+              uint64_t k = sort_key(pe[q]);
+              if (k > bestk || (k == bestk && ex < beste)) {
+                bestk = k;
+                beste = ex;
+              }
+            }
+          }
+          uint64_t wk = warp_max_key(bestk);
+          if (wk == 0) {
+            // fall-through of the reference loop: last entry of the descending order
+            // (smallest probability, largest index among ties)
+            uint64_t mink = ~0ull;
+            int mine = -1;
+#pragma unroll
+            for (int q = 0; q < SMG_EPL; q++) {
+              int ex = q * 32 + lane;
+              if (ex < ne) {
+                uint64_t k = sort_key(pe[q]);
+                if (k < mink || (k == mink && ex > mine)) {
+                  mink = k;
+                  mine = ex;
+                }
+              }
+            }
+            uint64_t wmin = ~warp_max_key(~mink);
+            new_e = (int)__reduce_max_sync(SMG_FULL, (unsigned)((mink == wmin) ? mine : 0));
+          } else {
+            new_e = (int)__reduce_min_sync(SMG_FULL, (unsigned)((bestk == wk) ? beste : 0x7fffffff));
+          }
+        }
+        // ---- does the draw change the state?
+        if (new_e == -2) {
+          code = -2;
+        } else if (new_e < K) {
+          int ns = s_l2s[new_e];
+          code = (ns != old_slot) ? new_e : EVT_NONE;
         } else {
-          new_e = (int)__reduce_min_sync(SMG_FULL, (unsigned)((bestk == wk) ? beste : 0x7fffffff));
+          code = (singleton && new_e == K) ? EVT_NONE : new_e;  // singleton re-drawing its own phi: no-op
         }
       }
-      // ---- does the draw change the state?
-      if (new_e == -2) {
-        code = -2;
-      } else if (new_e < K) {
-        int ns = s_l2s[new_e];
-        code = (ns != old_slot) ? new_e : EVT_NONE;
-      } else {
-        code = (singleton && new_e == K) ? EVT_NONE : new_e;  // singleton re-drawing its own phi: no-op
+      if (lane == 0) {
+        s_evt[warp] = code;
+        s_row[warp] = myrow;
       }
-    } else if (i < n) {
-      code = -3;
-    }
-    if (lane == 0) s_evt[warp] = code;
-    __syncthreads();
-    // ---- first event of the round, in observation order
-    int ev = s_evt[lane];
-    unsigned evm = __ballot_sync(SMG_FULL, ev != EVT_NONE);
-    if (evm == 0) {
-      if (tid == 0) {
-        s_i0 = i0 + SMG_SCAN_WARPS;
-        s_stats[0]++;
-      }
-      cb ^= 1;  // the prefetched round becomes the current one
       __syncthreads();
-      continue;
-    }
-    const int first = __ffs(evm) - 1;
-    const int new_e = __shfl_sync(SMG_FULL, ev, first);
-    const int ie = i0 + first;
-    if (new_e < 0) {  // error: stop the pass
-      if (tid == 0) atomicOr(A.status, new_e == -2 ? ST_BAD_PROB : ST_TOO_MANY_ENTRIES);
-      break;
-    }
-    const int old_slot = A.c[ie];
-    const bool singleton = (s_cnt[old_slot] == 1);
-    const int Kc = s_K;
-    int new_slot;
-    if (new_e < Kc) {
-      new_slot = s_l2s[new_e];
-    } else {
-      new_slot = s_next;  // birth (case 3) or parameter replacement (case 4)
-      if (new_slot >= A.NS || new_slot >= SMG_MAX_SLOTS) {
-        if (tid == 0) atomicOr(A.status, ST_SLOTS_EXHAUSTED);
+      // ---- first event of the batch (warps hold ascending rows)
+      int ev = s_evt[lane];
+      unsigned evm = __ballot_sync(SMG_FULL, ev != EVT_NONE && s_row[lane] >= 0);
+      if (evm == 0) {
+        if (tid == 0) s_stats[0]++;
+        start = lastrow + 1;
+        __syncthreads();  // s_evt / s_row are rewritten by the next round
+        continue;
+      }
+      const int first = __ffs(evm) - 1;
+      const int new_e = __shfl_sync(SMG_FULL, ev, first);
+      const int erow = s_row[first];
+      const int ie = i0 + erow;
+      if (new_e < 0) {  // error: stop the pass
+        if (tid == 0) atomicOr(A.status, new_e == -2 ? ST_BAD_PROB : ST_TOO_MANY_ENTRIES);
+        abort_pass = true;
         break;
       }
-      // copy the auxiliary component's parameters into the new slot
-      const int a = new_e - Kc;
-      const long long e = A.aux_e[(size_t)ie * m + a];
-      for (int j = tid; j < pp; j += blockDim.x) {
-        A.cen[(size_t)new_slot * pp + j] = A.pool_cen[(size_t)e * pp + j];
-        A.sig[(size_t)new_slot * pp + j] = A.pool_sig[(size_t)e * pp + j];
-        A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
-      }
-      if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
-      if (new_slot < A.ldl) {
-        __syncthreads();  // the new parameter vector is visible to the whole CTA
-        scan_fill_column(A, new_slot, ie + 1, min(n, ie + 1 + SCAN_FILL_W0), warp, lane);
-      }
-    }
-    cp_async_wait<0>();  // drain the speculative prefetch before its buffer is reused
-    __syncthreads();     // everyone has read the pre-event state
-    if (tid == 0) {
-      s_stats[0]++;
-      s_stats[1]++;
-      A.c[ie] = new_slot;
+      const int old_slot = A.c[ie];
+      const bool singleton = (s_cnt[old_slot] == 1);
+      const int Kc = s_K;
+      int new_slot;
       if (new_e < Kc) {
-        s_cnt[new_slot]++;
-        s_logcm1[new_slot] = s_logc[new_slot];
-        s_logc[new_slot] = log((double)s_cnt[new_slot]);
-        if (!singleton) {  // case 1 (neal8.cpp:107-112)
-          int c0 = --s_cnt[old_slot];
-          s_logc[old_slot] = s_logcm1[old_slot];
-          s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
-        } else {  // case 2 (neal8.cpp:115-137): last label moves into the hole
-          s_cnt[old_slot] = 0;
-          s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
-          int lab = s_s2l[old_slot];
-          int last_slot = s_l2s[Kc - 1];
-          s_l2s[lab] = last_slot;
-          s_s2l[last_slot] = lab;
-          s_s2l[old_slot] = -1;
-          if (lab == Kc - 1) s_s2l[last_slot] = -1;  // the dying cluster was the last label
-          s_K = Kc - 1;
-          s_stats[3]++;
-        }
+        new_slot = s_l2s[new_e];
       } else {
-        s_next = new_slot + 1;
-        if (new_slot < A.ldl) {
-          s_fill[new_slot] = min(n, ie + 1 + SCAN_FILL_W0);
-          s_fillw[new_slot] = 2 * SCAN_FILL_W0;
-          s_minfill = min(s_minfill, s_fill[new_slot]);
+        new_slot = s_next;  // birth (case 3) or parameter replacement (case 4)
+        if (new_slot >= A.NS || new_slot >= SMG_MAX_SLOTS) {
+          if (tid == 0) atomicOr(A.status, ST_SLOTS_EXHAUSTED);
+          abort_pass = true;
+          break;
         }
-        s_cnt[new_slot] = 1;
-        s_logc[new_slot] = 0.0;
-        s_logcm1[new_slot] = -CUDART_INF;
-        if (!singleton) {  // case 3 (neal8.cpp:140-150)
-          int c0 = --s_cnt[old_slot];
-          s_logc[old_slot] = s_logcm1[old_slot];
-          s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
-          s_l2s[Kc] = new_slot;
-          s_s2l[new_slot] = Kc;
-          s_K = Kc + 1;
-          s_stats[2]++;
-        } else {  // case 4 (neal8.cpp:153-159): same label, new parameters
-          int lab = s_s2l[old_slot];
-          s_cnt[old_slot] = 0;
-          s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
-          s_s2l[old_slot] = -1;
-          s_l2s[lab] = new_slot;
-          s_s2l[new_slot] = lab;
+        // copy the auxiliary component's parameters into the new slot
+        const int a = new_e - Kc;
+        const long long e = A.aux_e[(size_t)ie * m + a];
+        for (int j = tid; j < pp; j += blockDim.x) {
+          A.cen[(size_t)new_slot * pp + j] = A.pool_cen[(size_t)e * pp + j];
+          A.sig[(size_t)new_slot * pp + j] = A.pool_sig[(size_t)e * pp + j];
+          A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
+        }
+        if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
+        if (new_slot < A.ldl) {
+          __syncthreads();  // the new parameter vector is visible to the whole CTA
+          // materialise the new column for the rest of this chunk; later chunks do it at their start
+          scan_fill_column(A, new_slot, ie + 1, i0 + nrows, warp, lane);
         }
       }
-      s_i0 = ie + 1;
+      __syncthreads();  // everyone has read the pre-event state
+      if (tid == 0) {
+        s_stats[0]++;
+        s_stats[1]++;
+        A.c[ie] = new_slot;
+        // drift bookkeeping of a start-of-pass cluster whose count just changed
+        auto drift = [&](int s) {
+          if (s >= K0) return;
+          s_dminus[s] = (s_cnt[s] > 1) ? (s_lcm1_0[s] - s_logcm1[s]) : CUDART_INF;
+          const double dp = s_logc[s] - s_lc0[s];
+          if (dp > s_Dplus) s_Dplus = dp;  // monotone upper bound
+        };
+        if (new_e < Kc) {
+          s_cnt[new_slot]++;
+          s_logcm1[new_slot] = s_logc[new_slot];
+          s_logc[new_slot] = log((double)s_cnt[new_slot]);
+          drift(new_slot);
+          if (!singleton) {  // case 1 (neal8.cpp:107-112)
+            int c0 = --s_cnt[old_slot];
+            s_logc[old_slot] = s_logcm1[old_slot];
+            s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+            drift(old_slot);
+          } else {  // case 2 (neal8.cpp:115-137): last label moves into the hole
+            s_cnt[old_slot] = 0;
+            s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
+            int lab = s_s2l[old_slot];
+            int last_slot = s_l2s[Kc - 1];
+            s_l2s[lab] = last_slot;
+            s_s2l[last_slot] = lab;
+            s_s2l[old_slot] = -1;
+            if (lab == Kc - 1) s_s2l[last_slot] = -1;  // the dying cluster was the last label
+            s_K = Kc - 1;
+            s_stats[3]++;
+          }
+        } else {
+          s_next = new_slot + 1;
+          s_cnt[new_slot] = 1;
+          s_logc[new_slot] = 0.0;
+          s_logcm1[new_slot] = -CUDART_INF;
+          if (!singleton) {  // case 3 (neal8.cpp:140-150)
+            int c0 = --s_cnt[old_slot];
+            s_logc[old_slot] = s_logcm1[old_slot];
+            s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+            drift(old_slot);
+            s_l2s[Kc] = new_slot;
+            s_s2l[new_slot] = Kc;
+            s_K = Kc + 1;
+            s_stats[2]++;
+          } else {  // case 4 (neal8.cpp:153-159): same label, new parameters
+            int lab = s_s2l[old_slot];
+            s_cnt[old_slot] = 0;
+            s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
+            s_s2l[old_slot] = -1;
+            s_l2s[lab] = new_slot;
+            s_s2l[new_slot] = lab;
+          }
+        }
+      }
+      start = erow + 1;
+      screened = false;  // the state changed: the remaining rows are screened again
+      __syncthreads();
     }
-    __threadfence_block();
     __syncthreads();
-    // restart right after the event with fresh loads under the new state
-    cb ^= 1;
-    prefetch(cb, ie + 1 + warp);
   }
-  cp_async_wait<0>();
-  __syncthreads();
   // publish: K, counts by slot, slot->label map
   for (int s = tid; s < A.NS && s < SMG_MAX_SLOTS; s += blockDim.x) {
     A.counts[s] = s_cnt[s];
