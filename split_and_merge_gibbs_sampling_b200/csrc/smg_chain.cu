@@ -185,10 +185,10 @@ static int launch_histogram(smg_chain* ch) {
   return 0;
 }
 
-// update_phi on every cluster (common_functions.cpp:511-591)
-static int update_phi_all(smg_chain* ch, uint32_t sub, const double* uc, const double* us) {
-  if (launch_histogram(ch)) return SMG_ERR_CUDA;
+// common fields of a phi_update_kernel launch on the canonical parameter buffers
+PhiArgs phi_args_base(smg_chain* ch, uint32_t sub) {
   PhiArgs A;
+  memset(&A, 0, sizeof(A));
   A.pp = ch->pp;
   A.p = ch->p;
   A.mmax = ch->mmax;
@@ -197,63 +197,40 @@ static int update_phi_all(smg_chain* ch, uint32_t sub, const double* uc, const d
   A.w = ch->w;
   A.H = ch->H;
   A.counts = ch->counts;
-  A.jobs = nullptr;
-  A.njobs_ptr = ch->K;
   A.njobs = 0;
+  A.njobs_ptr = ch->K;
   A.cen_src = ch->cen[ch->cur];
   A.sig_src = ch->sig[ch->cur];
   A.cen = ch->cen[ch->cur];
   A.sig = ch->sig[ch->cur];
   A.isg = ch->isg[ch->cur];
-  A.den = ch->den;
-  A.u_center = uc;
-  A.u_sigma = us;
+  A.sden = ch->sden[ch->cur];
   A.u_stride = ch->p;
   A.key = mk_key(ch, sub);
-  A.prior = 0;
   A.sigma_exact = ch->sigma_exact;
-  A.enable = nullptr;
   A.status = ch->status;
-  dim3 grid(cdiv(ch->pp, 128), ch->Kcap);
-  phi_draw_kernel<<<grid, 128, 0, ch->st>>>(A);
-  phi_sden_kernel<<<ch->Kcap, 256, 0, ch->st>>>(nullptr, ch->K, 0, ch->pp, ch->den, ch->sden[ch->cur], nullptr);
-  ch->h_launches += 2;
+  return A;
+}
+
+// update_phi on every cluster (common_functions.cpp:511-591)
+static int update_phi_all(smg_chain* ch, uint32_t sub, const double* uc, const double* us) {
+  if (launch_histogram(ch)) return SMG_ERR_CUDA;
+  PhiArgs A = phi_args_base(ch, sub);
+  A.u_center = uc;
+  A.u_sigma = us;
+  A.prior = 0;
+  phi_update_kernel<<<ch->Kcap, 256, 0, ch->st>>>(A);
+  ch->h_launches += 1;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
 
 // prior draws for clusters [0, K): sample_centers + sample_sigmas (launcher.cpp:46-48)
 static int prior_phi_all(smg_chain* ch, int K) {
-  PhiArgs A;
-  A.pp = ch->pp;
-  A.p = ch->p;
-  A.mmax = ch->mmax;
-  A.attr = ch->attr;
-  A.v = ch->v;
-  A.w = ch->w;
-  A.H = ch->H;
-  A.counts = ch->counts;
-  A.jobs = nullptr;
-  A.njobs_ptr = ch->K;
-  A.njobs = 0;
-  A.cen_src = ch->cen[ch->cur];
-  A.sig_src = ch->sig[ch->cur];
-  A.cen = ch->cen[ch->cur];
-  A.sig = ch->sig[ch->cur];
-  A.isg = ch->isg[ch->cur];
-  A.den = ch->den;
-  A.u_center = nullptr;
-  A.u_sigma = nullptr;
-  A.u_stride = ch->p;
-  A.key = mk_key(ch, SUB_INIT_PHI);
+  PhiArgs A = phi_args_base(ch, SUB_INIT_PHI);
   A.prior = 1;
-  A.sigma_exact = ch->sigma_exact;
-  A.enable = nullptr;
-  A.status = ch->status;
-  dim3 grid(cdiv(ch->pp, 128), std::max(K, 1));
-  phi_draw_kernel<<<grid, 128, 0, ch->st>>>(A);
-  phi_sden_kernel<<<std::max(K, 1), 256, 0, ch->st>>>(nullptr, ch->K, 0, ch->pp, ch->den, ch->sden[ch->cur], nullptr);
-  ch->h_launches += 2;
+  phi_update_kernel<<<std::max(K, 1), 256, 0, ch->st>>>(A);
+  ch->h_launches += 1;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }

@@ -97,6 +97,7 @@ struct smg_chain {
 };
 
 namespace smg {
+PhiArgs phi_args_base(smg_chain* ch, uint32_t sub);
 inline RngKey mk_key(const smg_chain* ch, uint32_t sub) {
   RngKey k;
   k.k0 = (uint32_t)ch->seed;

@@ -848,7 +848,9 @@ __global__ void __launch_bounds__(256) subset_histogram_kernel(const uint8_t* __
                                                                const int* __restrict__ S,
                                                                const int* __restrict__ nSptr,
                                                                const int* __restrict__ z, const int* __restrict__ anchors,
-                                                               int mmax, int* __restrict__ H2, int* __restrict__ cnt2) {
+                                                               int mmax, int* __restrict__ H2, int* __restrict__ cnt2,
+                                                               const int* enable, int enable_val) {
+  if (enable && *enable != enable_val) return;
   const int chunks = pp / 16;
   const int nS = *nSptr;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -873,6 +875,60 @@ __global__ void __launch_bounds__(256) subset_histogram_kernel(const uint8_t* __
   }
 }
 
+// Same, with the two histograms privatised in shared memory (2*pp*mmax ints) and a fixed grid that strides
+// over the member rows: one flush of integer atomics per CTA instead of one atomic per (row, attribute).
+// Counts are not touched when cnt2 == null (the restricted-scan decision kernel already knows them).
+__global__ void __launch_bounds__(256) subset_histogram_smem_kernel(const uint8_t* __restrict__ X, int pp,
+                                                                    const int* __restrict__ S,
+                                                                    const int* __restrict__ nSptr,
+                                                                    const int* __restrict__ z,
+                                                                    const int* __restrict__ anchors, int mmax,
+                                                                    int* __restrict__ H2, int* __restrict__ cnt2,
+                                                                    const int* enable, int enable_val) {
+  if (enable && *enable != enable_val) return;
+  extern __shared__ int s_h[];  // [2][pp][mmax]
+  const int len = pp * mmax;
+  const int ng = z ? 2 : 1;
+  for (int q = threadIdx.x; q < ng * len; q += blockDim.x) s_h[q] = 0;
+  __syncthreads();
+  const int chunks = pp / 16;
+  const int nS = *nSptr;
+  const long long total = (long long)(nS + 2) * chunks;
+  int c0 = 0, c1 = 0;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / chunks), q = (int)(t % chunks);
+    int row, g;
+    if (r < nS) {
+      row = S[r];
+      g = z ? z[r] : 0;
+    } else {
+      row = anchors[r - nS];
+      g = z ? (r - nS) : 0;
+    }
+    if (q == 0) {
+      c0 += (g == 0);
+      c1 += (g == 1);
+    }
+    const uint4 v = *reinterpret_cast<const uint4*>(X + (size_t)row * pp + q * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    int* Hk = s_h + (size_t)g * len + (size_t)q * 16 * mmax;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
+      if (x) atomicAdd(&Hk[b * mmax + (x - 1)], 1);
+    }
+  }
+  if (cnt2) {
+    if (c0) atomicAdd(&cnt2[0], c0);
+    if (c1) atomicAdd(&cnt2[1], c1);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < ng * len; q += blockDim.x) {
+    const int hv = s_h[q];
+    if (hv) atomicAdd(&H2[q], hv);
+  }
+}
+
 // =============================================================================
 // K4: per-(cluster, attribute) centre and sigma draws (update_phi).
 // A "job" updates one cluster: histogram row `hist`, current sigma from slot `src`,
@@ -884,7 +940,14 @@ __global__ void __launch_bounds__(256) subset_histogram_kernel(const uint8_t* __
 // =============================================================================
 struct PhiJob {
   int hist, src, dst, cnt_idx;
+  uint32_t sub;      // Philox sub-phase of this job's draws
+  int prior;         // 1 => draw from the prior (no data)
+  int enable_mode;   // 0: always; 1: only when *enable != 0; 2: only when *enable == 0
+  const double* uc;  // injected uniforms [p] of this job (centre / sigma) or null
+  const double* us;
 };
+
+#define PHI_MAX_INLINE_JOBS 4
 
 struct PhiArgs {
   int pp, p, mmax;
@@ -893,109 +956,107 @@ struct PhiArgs {
   const double* w;
   const int* H;
   const int* counts;
-  const PhiJob* jobs;  // device array or null
-  const int* njobs_ptr;  // device count (e.g. K) when jobs == null
-  int njobs;             // host count when jobs != null
+  // mode A (njobs > 0): the jobs listed here.  mode B (njobs == 0): job k updates cluster k in place for
+  // k < *njobs_ptr, with u_center / u_sigma [job][p] (stride u_stride) and the fields `sub`, `prior` below.
+  PhiJob jobs[PHI_MAX_INLINE_JOBS];
+  int njobs;
+  const int* njobs_ptr;
   const uint8_t* cen_src;
   const double* sig_src;
   uint8_t* cen;
   double* sig;
   double* isg;
-  double* den;   // [NS][pp] per-attribute log-normaliser (summed into sden by phi_sden_kernel)
-  const double* u_center;  // injected uniforms [job][p] (stride u_stride) or null
+  double* sden;
+  const double* u_center;
   const double* u_sigma;
   int u_stride;
   RngKey key;
-  int prior;    // 1 => draw from the prior (no data)
-  int sigma_exact;  // 1 => always the one-uniform inverse-CDF sigma draw (also used whenever u_sigma is injected)
-  const int* enable;  // optional device flag: skip the whole launch when *enable == 0
+  int prior;
+  int sigma_exact;  // 1 => always the one-uniform inverse-CDF sigma draw (also used whenever sigma uniforms are injected)
+  const int* enable;  // device flag consulted by jobs with enable_mode != 0
   int* status;
 };
 
-__global__ void __launch_bounds__(128) phi_draw_kernel(PhiArgs A) {
-  if (A.enable && *A.enable == 0) return;
-  const int job = blockIdx.y;
-  const int nj = A.jobs ? A.njobs : *A.njobs_ptr;
-  if (job >= nj) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= A.pp) return;
-  PhiJob J;
-  if (A.jobs)
-    J = A.jobs[job];
-  else {
-    J.hist = J.src = J.dst = J.cnt_idx = job;
-  }
-  const size_t o = (size_t)J.dst * A.pp + j;
-  if (j >= A.p) {  // padding attributes
-    A.cen[o] = 0;
-    A.sig[o] = 1.0;
-    A.isg[o] = 0.0;
-    A.den[o] = 0.0;
-    return;
-  }
-  const int m = A.attr[j];
-  const int nk = A.prior ? 0 : A.counts[J.cnt_idx];
-  if (!A.prior && nk == 0) return;  // empty cluster: untouched (common_functions.cpp:547)
-  int center;
-  double s_match = 0.0;
-  const double uc = get_u(A.u_center, (size_t)job * A.u_stride + j, A.key, U_CENTER, (uint32_t)job, (uint32_t)j);
-  if (A.prior) {
-    center = (int)((double)m * uc + 1.0);  // sample(m_j, 1): (int)(m*u + 1)
-    if (center > m) center = m;
-  } else {
-    const double sg = A.sig_src[(size_t)J.src * A.pp + j];
-    const int* h = A.H + ((size_t)J.hist * A.pp + j) * A.mmax;
-    double pt[SMG_MAX_LEVELS];
-    double mx = -CUDART_INF;
-    for (int a = 0; a < m; a++) {
-      pt[a] = -((double)nk - (double)h[a]) / sg;
-      mx = pt[a] > mx ? pt[a] : mx;
-    }
-    double sum = 0.0;
-    for (int a = 0; a < m; a++) {
-      pt[a] = exp(pt[a] - mx);
-      sum += pt[a];
-    }
-    for (int a = 0; a < m; a++) pt[a] = pt[a] / sum;
-    center = 1 + sample_probs_small(pt, m, uc);
-    s_match = (double)h[center - 1];
-  }
-  const double vv = A.v[j] + s_match;
-  const double ww = A.w[j] + (double)nk - s_match;
-  double uu;
-  if (A.u_sigma || A.sigma_exact) {
-    const double us = get_u(A.u_sigma, (size_t)job * A.u_stride + j, A.key, U_SIGMA, (uint32_t)job, (uint32_t)j);
-    uu = hig_inv_u_d(us, vv, ww, (double)m);
-  } else {
-    SubStream rs(A.key, U_SIGMA, (uint32_t)job, (uint32_t)j);
-    uu = hig_draw_u_d(rs, vv, ww, (double)m);
-  }
-  const double sigma = -1.0 / log(uu);
-  A.cen[o] = (uint8_t)center;
-  A.sig[o] = sigma;
-  A.isg[o] = 1.0 / sigma;
-  A.den[o] = hamming_den(sigma, m);
-}
-
-// sden[slot] = sum_j den[slot][j] in a fixed order (one CTA per job, tree in shared memory)
-__global__ void __launch_bounds__(256) phi_sden_kernel(const PhiJob* jobs, const int* njobs_ptr, int njobs, int pp,
-                                                       const double* __restrict__ den, double* __restrict__ sden,
-                                                       const int* enable) {
-  if (enable && *enable == 0) return;
+// One CTA per job; thread j draws attribute j (and j+256, ...), then the CTA sums the per-attribute
+// log-normalisers in a fixed order into sden[dst].
+__global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
   const int job = blockIdx.x;
-  const int nj = jobs ? njobs : *njobs_ptr;
-  if (job >= nj) return;
-  const int dst = jobs ? jobs[job].dst : job;
+  PhiJob J;
+  if (A.njobs > 0) {
+    if (job >= A.njobs) return;
+    J = A.jobs[job];
+    if (J.enable_mode == 1 && *A.enable == 0) return;
+    if (J.enable_mode == 2 && *A.enable != 0) return;
+  } else {
+    if (job >= *A.njobs_ptr) return;
+    J.hist = J.src = J.dst = J.cnt_idx = job;
+    J.sub = A.key.sub;
+    J.prior = A.prior;
+    J.uc = A.u_center ? A.u_center + (size_t)job * A.u_stride : nullptr;
+    J.us = A.u_sigma ? A.u_sigma + (size_t)job * A.u_stride : nullptr;
+  }
+  RngKey key = A.key;
+  key.sub = J.sub;
+  const int nk = J.prior ? 0 : A.counts[J.cnt_idx];
+  if (!J.prior && nk == 0) return;  // empty cluster: untouched (common_functions.cpp:547)
   __shared__ double sh[256];
   double acc = 0.0;
-  for (int j = threadIdx.x; j < pp; j += 256) acc += den[(size_t)dst * pp + j];
+  for (int j = threadIdx.x; j < A.pp; j += 256) {
+    const size_t o = (size_t)J.dst * A.pp + j;
+    if (j >= A.p) {  // padding attributes
+      A.cen[o] = 0;
+      A.sig[o] = 1.0;
+      A.isg[o] = 0.0;
+      continue;
+    }
+    const int m = A.attr[j];
+    int center;
+    double s_match = 0.0;
+    const double uc = get_u(J.uc, (size_t)j, key, U_CENTER, (uint32_t)job, (uint32_t)j);
+    if (J.prior) {
+      center = (int)((double)m * uc + 1.0);  // sample(m_j, 1): (int)(m*u + 1)
+      if (center > m) center = m;
+    } else {
+      const double sg = A.sig_src[(size_t)J.src * A.pp + j];
+      const int* h = A.H + ((size_t)J.hist * A.pp + j) * A.mmax;
+      double pt[SMG_MAX_LEVELS];
+      double mx = -CUDART_INF;
+      for (int a = 0; a < m; a++) {
+        pt[a] = -((double)nk - (double)h[a]) / sg;
+        mx = pt[a] > mx ? pt[a] : mx;
+      }
+      double sum = 0.0;
+      for (int a = 0; a < m; a++) {
+        pt[a] = exp(pt[a] - mx);
+        sum += pt[a];
+      }
+      for (int a = 0; a < m; a++) pt[a] = pt[a] / sum;
+      center = 1 + sample_probs_small(pt, m, uc);
+      s_match = (double)h[center - 1];
+    }
+    const double vv = A.v[j] + s_match;
+    const double ww = A.w[j] + (double)nk - s_match;
+    double uu;
+    if (J.us || A.sigma_exact) {
+      const double us = get_u(J.us, (size_t)j, key, U_SIGMA, (uint32_t)job, (uint32_t)j);
+      uu = hig_inv_u_d(us, vv, ww, (double)m);
+    } else {
+      SubStream rs(key, U_SIGMA, (uint32_t)job, (uint32_t)j);
+      uu = hig_draw_u_d(rs, vv, ww, (double)m);
+    }
+    const double sigma = -1.0 / log(uu);
+    A.cen[o] = (uint8_t)center;
+    A.sig[o] = sigma;
+    A.isg[o] = 1.0 / sigma;
+    acc += hamming_den(sigma, m);
+  }
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) sden[dst] = sh[0];
+  if (threadIdx.x == 0) A.sden[J.dst] = sh[0];
 }
 
 // derive isg / den / sden from (cen, sig) for slots [0, nslots): used after host uploads

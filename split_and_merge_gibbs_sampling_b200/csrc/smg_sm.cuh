@@ -32,12 +32,11 @@ struct SmWork {
   SmPlan* plan = nullptr;
   int* anchors = nullptr;  // alias of info->i1,i2 (two ints)
   int *H = nullptr, *cnt = nullptr;
-  double* LL2 = nullptr;      // [n][2]
-  double *rg_dl = nullptr, *rg_lgt = nullptr, *LT = nullptr;  // [n], [n], [n+3]
+  double *rg_dl = nullptr, *rg_lgt = nullptr;  // [n] LL_A - LL_B and logit(u) of the restricted scan in flight
   double* rowvals = nullptr;  // [4][n+2]
   double* partial = nullptr;  // [4][RB]
   double* terms = nullptr;    // [24]
-  PhiJob* jobs = nullptr;     // [9]
+  size_t hist_smem = 0;       // dynamic shared memory of subset_histogram_smem_kernel (0: does not fit)
   // injected uniforms (device copies, allocated on first use)
   double *u_pair = nullptr, *u_prior_c = nullptr, *u_prior_s = nullptr, *u_launch = nullptr, *u_rg = nullptr;
   double *u_rg_c = nullptr, *u_rg_s = nullptr, *u_mg_c = nullptr, *u_mg_s = nullptr, *u_accept = nullptr;
@@ -54,8 +53,8 @@ __global__ void __launch_bounds__(1024) sm_select_kernel(int n, const int* __res
                                                          const double* u_pair, RngKey key, int NS, int* __restrict__ S,
                                                          int* __restrict__ zState, SmInfo* info, SmPlan* plan,
                                                          int* __restrict__ cnt, double* terms) {
-  __shared__ int s_i1, s_i2, s_cA, s_cB, s_base, s_tot;
-  __shared__ int s_woff[32];
+  __shared__ int s_i1, s_i2, s_cA, s_cB, s_tot;
+  __shared__ int s_wcnt[32], s_woff[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     double u0 = get_u(u_pair, 0, key, U_SM_PAIR, 0u, 0u), u1 = get_u(u_pair, 1, key, U_SM_PAIR, 1u, 0u);
@@ -68,40 +67,47 @@ __global__ void __launch_bounds__(1024) sm_select_kernel(int n, const int* __res
     s_i2 = i2;
     s_cA = c[i1];
     s_cB = c[i2];
-    s_base = 0;
   }
   for (int q = tid; q < 24; q += blockDim.x) terms[q] = 0.0;
   __syncthreads();
   const int i1 = s_i1, i2 = s_i2, cA = s_cA, cB = s_cB;
-  for (int t0 = 0; t0 < n; t0 += 1024) {
-    int i = t0 + tid;
-    int ci = (i < n) ? c[i] : -1;
-    bool in = (i < n) && i != i1 && i != i2 && (ci == cA || ci == cB);
-    unsigned b = __ballot_sync(SMG_FULL, in);
-    if (lane == 0) s_woff[warp] = __popc(b);
-    __syncthreads();
-    if (warp == 0) {
-      int v = s_woff[lane], x = v;
+  // ordered compaction: warp w owns the contiguous rows [lo, hi); count, scan the 32 totals, write
+  const int seg = ((n + 31) / 32 + 31) & ~31;
+  const int lo = min(n, warp * seg), hi = min(n, lo + seg);
+  int mine = 0;
+  for (int i = lo + lane; i < hi; i += 32) {
+    const int ci = c[i];
+    mine += (i != i1 && i != i2 && (ci == cA || ci == cB));
+  }
+  mine = warp_sum_i(mine);
+  if (lane == 0) s_wcnt[warp] = mine;
+  __syncthreads();
+  if (warp == 0) {
+    int v = s_wcnt[lane], x = v;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        int y = __shfl_up_sync(SMG_FULL, x, o);
-        if (lane >= o) x += y;
-      }
-      s_woff[lane] = x - v;  // exclusive
-      if (lane == 31) s_tot = x;
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(SMG_FULL, x, o);
+      if (lane >= o) x += y;
     }
-    __syncthreads();
+    s_woff[lane] = x - v;  // exclusive
+    if (lane == 31) s_tot = x;
+  }
+  __syncthreads();
+  int off = s_woff[warp];
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane;
+    const int ci = (i < hi) ? c[i] : -1;
+    const bool in = (i < hi) && i != i1 && i != i2 && (ci == cA || ci == cB);
+    const unsigned b = __ballot_sync(SMG_FULL, in);
     if (in) {
-      int pos = s_base + s_woff[warp] + __popc(b & ((1u << lane) - 1));
+      const int pos = off + __popc(b & ((1u << lane) - 1));
       S[pos] = i;
       zState[pos] = (ci == cA) ? 0 : 1;
     }
-    __syncthreads();
-    if (tid == 0) s_base += s_tot;
-    __syncthreads();
+    off += __popc(b);
   }
   if (tid == 0) {
-    const int nS = s_base, same = (cA == cB), K = *Kptr;
+    const int nS = s_tot, same = (cA == cB), K = *Kptr;
     info->i1 = i1;
     info->i2 = i2;
     info->nS = nS;
@@ -141,107 +147,174 @@ __global__ void sm_launch_alloc_kernel(const SmInfo* info, const double* u_inj, 
   zL[pos] = z > 1 ? 1 : z;
 }
 
-// LL2[pos][g] = log-likelihood of member S[pos] under parameter slot (slotA, slotB)
-__global__ void __launch_bounds__(256) sm_ll2_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
-                                                     const SmInfo* info, const uint8_t* cen, const double* isg,
-                                                     const double* sden, int slotA, int slotB,
-                                                     double* __restrict__ LL2, const int* enable, int enable_val) {
-  if (enable && *enable != enable_val) return;
-  const int nS = info->nS;
-  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= 2ll * nS) return;
-  const int pos = (int)(w >> 1), g = (int)(w & 1);
-  const int slot = g ? slotB : slotA;
-  double dot = warp_mismatch_dot(X + (size_t)S[pos] * pp, cen + (size_t)slot * pp, isg + (size_t)slot * pp, pp, lane);
-  if (lane == 0) LL2[w] = -dot - sden[slot];
-}
-
-// log table LT[k] = log(k), k = 0..n+2 (member counts of the restricted scans)
-__global__ void sm_logtable_kernel(int len, double* __restrict__ LT) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < len) LT[k] = k > 0 ? log((double)k) : -CUDART_INF;
-}
-
-// Restricted Gibbs allocation scan over S (split_merge.cpp:186-216), in two phases.
+// Restricted Gibbs allocation scan over S (split_merge.cpp:186-216), in two kernels.
 //
 // The two-way Rcpp::sample (split_merge.cpp:215) walks the two probabilities in descending order
 // (revsort; on a tie the SECOND entry comes first) and takes the first when u <= p_first.  With
 // D = (log n_1 + LL_1) - (log n_2 + LL_2) the larger probability is 1/(1+exp(-|D|)), so the member goes
-// to the larger side iff |D| >= logit(u), to the other side otherwise.  logit(u) and LL_1 - LL_2 do not
-// depend on the running counts, so phase 1 evaluates them for every member in parallel, and the
-// sequential phase 2 only needs a table look-up of log(count) and two comparisons per member.
-// Phase 2 runs on one warp: 32 consecutive members are decided against the same counts, the first one
-// that changes side is applied, and the evaluation restarts after it (same result as one at a time).
-__global__ void __launch_bounds__(256) sm_rg_prepare_kernel(const SmInfo* info, const double* __restrict__ LL2,
-                                                            const double* u_inj, RngKey key, double* __restrict__ dl,
-                                                            double* __restrict__ lgt, const int* enable, int enable_val) {
+// to the larger side iff |D| >= logit(u), to the other side otherwise.  logit(u) and d0 = LL_1 - LL_2 do
+// not depend on the running counts: sm_ll2prep_kernel evaluates them for every member in parallel
+// (one warp per member, all SMs).
+__global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
+                                                         const SmInfo* info, const uint8_t* cen, const double* isg,
+                                                         const double* sden, int slotA, int slotB, const double* u_inj,
+                                                         RngKey key, double* __restrict__ dl, double* __restrict__ lgt,
+                                                         const int* enable, int enable_val) {
   if (enable && *enable != enable_val) return;
-  int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos >= info->nS) return;
-  const double u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
-  dl[pos] = LL2[2 * (size_t)pos] - LL2[2 * (size_t)pos + 1];
-  lgt[pos] = log(u / (1.0 - u));
+  const int nS = info->nS;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const uint8_t *cA = cen + (size_t)slotA * pp, *cB = cen + (size_t)slotB * pp;
+  const double *wA = isg + (size_t)slotA * pp, *wB = isg + (size_t)slotB * pp;
+  const double sdA = sden[slotA], sdB = sden[slotB];
+  for (int pos = blockIdx.x * wpb + (threadIdx.x >> 5); pos < nS; pos += gridDim.x * wpb) {
+    const uint8_t* x = X + (size_t)S[pos] * pp;
+    const double llA = -warp_mismatch_dot(x, cA, wA, pp, lane) - sdA;
+    const double llB = -warp_mismatch_dot(x, cB, wB, pp, lane) - sdB;
+    if (lane == 0) {
+      const double u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
+      dl[pos] = llA - llB;
+      lgt[pos] = log(u / (1.0 - u));
+    }
+  }
 }
 
-__global__ void __launch_bounds__(32) sm_rgibbs_kernel(const SmInfo* info, const double* __restrict__ dl,
-                                                       const double* __restrict__ lgt, const double* __restrict__ LT,
-                                                       int* __restrict__ z, const int* enable, int enable_val) {
+// The sequential part, one CTA.  The log-count term of D lies in [-log(nS+1), log(nS+1)] whatever the
+// running counts are, so a member with |d0| > log(nS+1) + |logit(u)| lands on the side of sign(d0) no
+// matter what happened before it ("robust").  Per chunk of 1024 members: robust members are decided in
+// parallel, a block prefix sum gives the count contribution of the robust members before every
+// position, and only the non-robust members are walked in order by one warp (32 at a time against the
+// same counts; the first one that changes side is applied and evaluation restarts after it).  Same
+// result as the one-at-a-time scan.  Also zeroes the histograms the next kernel fills and publishes
+// the side counts (anchors included).
+#define SM_DECIDE_T 1024
+__global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* info, const double* __restrict__ dl,
+                                                                 const double* __restrict__ lgt, int* __restrict__ z,
+                                                                 int* __restrict__ Hzero, int hlen, int* __restrict__ cnt2,
+                                                                 const int* enable, int enable_val) {
   if (enable && *enable != enable_val) return;
-  const int nS = info->nS, lane = threadIdx.x;
-  // side counts including the anchors i_1 (side 0) and i_2 (side 1)
-  int c1 = 0;
-  for (int pos = lane; pos < nS; pos += 32) c1 += z[pos];
-  c1 = warp_sum_i(c1);
-  int nA = 1 + (nS - c1), nB = 1 + c1;
-  for (int base = 0; base < nS; base += 32) {
-    const int pos = base + lane;
+  __shared__ double s_d0[SM_DECIDE_T], s_lg[SM_DECIDE_T];
+  __shared__ int s_z[SM_DECIDE_T], s_pre[SM_DECIDE_T], s_list[SM_DECIDE_T];
+  __shared__ int s_wsum[32], s_wnr[32];
+  __shared__ int s_nB, s_nnr, s_cdelta;
+  const int nS = info->nS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int q = tid; q < hlen; q += SM_DECIDE_T) Hzero[q] = 0;
+  {  // side-1 count on entry (anchor i_2 included)
+    int c1 = 0;
+    for (int pos = tid; pos < nS; pos += SM_DECIDE_T) c1 += z[pos];
+    c1 = warp_sum_i(c1);
+    if (lane == 0) s_wsum[warp] = c1;
+    __syncthreads();
+    if (warp == 0) {
+      int t = warp_sum_i(s_wsum[lane]);
+      if (lane == 0) s_nB = 1 + t;
+    }
+    __syncthreads();
+  }
+  const double Lmax = log((double)(nS + 1));
+  for (int base = 0; base < nS; base += SM_DECIDE_T) {
+    const int pos = base + tid;
     const bool valid = pos < nS;
-    double d0 = 0.0, lg = 0.0;
-    int zz = 0;
-    if (valid) {
-      d0 = dl[pos];
-      lg = lgt[pos];
-      zz = z[pos];
+    const double d0 = valid ? dl[pos] : 0.0, lg = valid ? lgt[pos] : 0.0;
+    const int zz = valid ? z[pos] : 0;
+    const bool robust = valid && (fabs(d0) > Lmax + fabs(lg) + 1e-9);
+    const bool nonrob = valid && !robust;
+    const int newz = robust ? (d0 > 0.0 ? 0 : 1) : zz;
+    const int delta = newz - zz;
+    int incl = delta;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(SMG_FULL, incl, o);
+      if (lane >= o) incl += y;
     }
-    int start = 0;
-    while (start < 32) {
-      // log-count difference seen by a member currently on side 0 / side 1 (itself excluded)
-      const double dA = LT[nA - 1] - LT[nB], dB = LT[nA] - LT[nB - 1];
-      int newz = zz;
-      if (valid && lane >= start) {
-        const double D = (zz == 0 ? dA : dB) + d0;
-        if (D > 0.0)
-          newz = (D >= lg) ? 0 : 1;
-        else
-          newz = (-D >= lg) ? 1 : 0;
+    const unsigned nb = __ballot_sync(SMG_FULL, nonrob);
+    if (lane == 31) s_wsum[warp] = incl;
+    if (lane == 0) s_wnr[warp] = __popc(nb);
+    __syncthreads();
+    if (warp == 0) {
+      int a = s_wsum[lane], b = s_wnr[lane], xa = a, xb = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int ya = __shfl_up_sync(SMG_FULL, xa, o), yb = __shfl_up_sync(SMG_FULL, xb, o);
+        if (lane >= o) {
+          xa += ya;
+          xb += yb;
+        }
       }
-      unsigned ch = __ballot_sync(SMG_FULL, valid && lane >= start && newz != zz);
-      if (!ch) break;
-      const int f = __ffs(ch) - 1;
-      const int zo = __shfl_sync(SMG_FULL, zz, f), zn = __shfl_sync(SMG_FULL, newz, f);
-      if (lane == f) zz = newz;
-      nA += (zn == 0) - (zo == 0);
-      nB += (zn == 1) - (zo == 1);
-      start = f + 1;
+      s_wsum[lane] = xa - a;
+      s_wnr[lane] = xb - b;
+      if (lane == 31) {
+        s_cdelta = xa;
+        s_nnr = xb;
+      }
     }
-    if (valid) z[pos] = zz;
+    __syncthreads();
+    s_pre[tid] = s_wsum[warp] + incl - delta;  // side-1 change of the robust members before this position
+    s_d0[tid] = d0;
+    s_lg[tid] = lg;
+    s_z[tid] = newz;
+    if (nonrob) s_list[s_wnr[warp] + __popc(nb & ((1u << lane) - 1))] = tid;
+    __syncthreads();
+    if (warp == 0) {
+      const int nnr = s_nnr, nB0 = s_nB;
+      int extra = 0;  // side-1 change of the non-robust members decided so far
+      for (int b0 = 0; b0 < nnr; b0 += 32) {
+        const int q = b0 + lane;
+        const bool v = q < nnr;
+        const int t = v ? s_list[q] : 0;
+        const double md0 = s_d0[t], mlg = s_lg[t];
+        const int pre = s_pre[t];
+        int mz = s_z[t];
+        int start = 0;
+        while (start < 32) {
+          int nz = mz;
+          if (v && lane >= start) {
+            const int nBq = nB0 + pre + extra, nAq = nS + 2 - nBq;
+            const double dc = (mz == 0) ? log((double)(nAq - 1)) - log((double)nBq)
+                                        : log((double)nAq) - log((double)(nBq - 1));
+            const double D = dc + md0;
+            if (D > 0.0)
+              nz = (D >= mlg) ? 0 : 1;
+            else
+              nz = (-D >= mlg) ? 1 : 0;
+          }
+          const unsigned chg = __ballot_sync(SMG_FULL, v && lane >= start && nz != mz);
+          if (!chg) break;
+          const int f = __ffs(chg) - 1;
+          const int zo = __shfl_sync(SMG_FULL, mz, f), zn = __shfl_sync(SMG_FULL, nz, f);
+          if (lane == f) mz = nz;
+          extra += zn - zo;
+          start = f + 1;
+        }
+        if (v) s_z[t] = mz;
+      }
+      if (lane == 0) s_nB = nB0 + s_cdelta + extra;
+    }
+    __syncthreads();
+    if (valid) z[pos] = s_z[tid];
+    __syncthreads();
+  }
+  if (tid == 0 && cnt2) {
+    cnt2[0] = nS + 2 - s_nB;
+    cnt2[1] = s_nB;
   }
 }
 
-__global__ void sm_copy_z_kernel(const SmInfo* info, const int* __restrict__ src, int* __restrict__ dst) {
-  int pos = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pos < info->nS) dst[pos] = src[pos];
-}
-
-// copy a parameter slot (centre, sigma, 1/sigma, sum of log-normalisers)
-__global__ void sm_copy_slot_kernel(int pp, uint8_t* cen, double* sig, double* isg, double* sden, int src, int dst) {
-  for (int j = threadIdx.x; j < pp; j += blockDim.x) {
-    cen[(size_t)dst * pp + j] = cen[(size_t)src * pp + j];
-    sig[(size_t)dst * pp + j] = sig[(size_t)src * pp + j];
-    isg[(size_t)dst * pp + j] = isg[(size_t)src * pp + j];
+// proposal = copy of the split launch state (sides and the two parameter slots), split_merge.cpp:575-577
+__global__ void __launch_bounds__(256) sm_begin_proposal_kernel(const SmInfo* info, const int* __restrict__ zL,
+                                                                int* __restrict__ zStar, int pp, uint8_t* cen,
+                                                                double* sig, double* isg, double* sden, int srcA,
+                                                                int dstA, int srcB, int dstB) {
+  const int nS = info->nS;
+  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nS; pos += gridDim.x * blockDim.x) zStar[pos] = zL[pos];
+  if (blockIdx.x < 2) {
+    const int src = blockIdx.x ? srcB : srcA, dst = blockIdx.x ? dstB : dstA;
+    for (int j = threadIdx.x; j < pp; j += blockDim.x) {
+      cen[(size_t)dst * pp + j] = cen[(size_t)src * pp + j];
+      sig[(size_t)dst * pp + j] = sig[(size_t)src * pp + j];
+      isg[(size_t)dst * pp + j] = isg[(size_t)src * pp + j];
+    }
+    if (threadIdx.x == 0) sden[dst] = sden[src];
   }
-  if (threadIdx.x == 0) sden[dst] = sden[src];
 }
 
 // H[dst] = H[a] + H[b] ; cnt likewise
@@ -533,37 +606,29 @@ static int sm_alloc(smg_chain* ch) {
   SMG_CUDA(cudaMalloc(&W->plan, sizeof(SmPlan)));
   SMG_CUDA(cudaMalloc(&W->H, (size_t)SH_N * ch->pp * ch->mmax * 4));
   SMG_CUDA(cudaMalloc(&W->cnt, SH_N * 4 + 4));
-  SMG_CUDA(cudaMalloc(&W->LL2, (size_t)n * 2 * 8));
   SMG_CUDA(cudaMalloc(&W->rg_dl, (size_t)n * 8));
   SMG_CUDA(cudaMalloc(&W->rg_lgt, (size_t)n * 8));
-  SMG_CUDA(cudaMalloc(&W->LT, (size_t)(n + 3) * 8));
-  sm_logtable_kernel<<<(n + 3 + 255) / 256, 256, 0, ch->st>>>(n + 3, W->LT);
-  SMG_CUDA(cudaGetLastError());
   SMG_CUDA(cudaMalloc(&W->rowvals, (size_t)4 * (n + 2) * 8));
   SMG_CUDA(cudaMalloc(&W->partial, (size_t)4 * SM_RB * 8));
   SMG_CUDA(cudaMalloc(&W->terms, 24 * 8));
   SMG_CUDA(cudaMemset(W->terms, 0, 24 * 8));
-  SMG_CUDA(cudaMalloc(&W->jobs, 9 * sizeof(PhiJob)));
-  const int B = ch->NS;
-  PhiJob j[9] = {{0, 0, B + SM_SL_A, 0},
-                 {0, 0, B + SM_SL_B, 0},
-                 {0, 0, B + SM_ML_M, 0},
-                 {SH_L0, B + SM_SL_A, B + SM_SL_A, SH_L0},
-                 {SH_L1, B + SM_SL_B, B + SM_SL_B, SH_L1},
-                 {SH_M, B + SM_ML_M, B + SM_ML_M, SH_M},
-                 {SH_P0, B + SM_ST_A, B + SM_ST_A, SH_P0},
-                 {SH_P1, B + SM_ST_B, B + SM_ST_B, SH_P1},
-                 {SH_M, B + SM_ML_M, B + SM_ST_M, SH_M}};
-  SMG_CUDA(cudaMemcpy(W->jobs, j, sizeof(j), cudaMemcpyHostToDevice));
+  // the two side histograms are privatised in shared memory when they fit
+  W->hist_smem = (size_t)2 * ch->pp * ch->mmax * sizeof(int);
+  if (W->hist_smem <= 160 * 1024) {
+    SMG_CUDA(cudaFuncSetAttribute(subset_histogram_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)W->hist_smem));
+  } else {
+    W->hist_smem = 0;
+  }
   return 0;
 }
 
 static void sm_free(smg_chain* ch) {
   SmWork* W = ch->sm;
   if (!W) return;
-  void* ptrs[] = {W->S,      W->zL,     W->zStar,    W->zState,   W->info,   W->plan, W->H,      W->cnt,
-                  W->LL2,    W->rg_dl, W->rg_lgt, W->LT, W->rowvals, W->partial, W->terms,    W->jobs,   W->u_pair, W->u_prior_c, W->u_prior_s,
-                  W->u_launch, W->u_rg, W->u_rg_c,   W->u_rg_s,   W->u_mg_c, W->u_mg_s, W->u_accept};
+  void* ptrs[] = {W->S,       W->zL,      W->zStar, W->zState, W->info,    W->plan,    W->H,      W->cnt,
+                  W->rg_dl,   W->rg_lgt,  W->rowvals, W->partial, W->terms, W->u_pair,  W->u_prior_c, W->u_prior_s,
+                  W->u_launch, W->u_rg,   W->u_rg_c, W->u_rg_s, W->u_mg_c,  W->u_mg_s,  W->u_accept};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   delete W;
@@ -599,76 +664,85 @@ static int sm_inject(smg_chain* ch, const smg_sm_tape* t) {
   return 0;
 }
 
-// phi_draw + sden on `nj` consecutive jobs starting at jobs[j0]
-static int sm_phi(smg_chain* ch, int j0, int nj, int prior, uint32_t sub, const double* uc, const double* us,
-                  const int* enable) {
+// the nine parameter-update jobs of a proposal (hist, current sigma slot, destination slot, count index)
+enum SmJob : int { J_PRI_A = 0, J_PRI_B, J_PRI_M, J_L0, J_L1, J_MG, J_P0, J_P1, J_MSTAR, J_N };
+
+static PhiJob sm_job(smg_chain* ch, int which, uint32_t sub, const double* uc, const double* us, int enable_mode) {
+  const int B = ch->NS;
+  static const int tab[J_N][4] = {{0, 0, SM_SL_A, 0},          {0, 0, SM_SL_B, 0},          {0, 0, SM_ML_M, 0},
+                                  {SH_L0, SM_SL_A, SM_SL_A, SH_L0}, {SH_L1, SM_SL_B, SM_SL_B, SH_L1},
+                                  {SH_M, SM_ML_M, SM_ML_M, SH_M},   {SH_P0, SM_ST_A, SM_ST_A, SH_P0},
+                                  {SH_P1, SM_ST_B, SM_ST_B, SH_P1}, {SH_M, SM_ML_M, SM_ST_M, SH_M}};
+  PhiJob J;
+  J.hist = tab[which][0];
+  J.src = B + tab[which][1];
+  J.dst = B + tab[which][2];
+  J.cnt_idx = tab[which][3];
+  J.sub = sub;
+  J.prior = which <= J_PRI_M;
+  J.enable_mode = enable_mode;
+  J.uc = uc;
+  J.us = us;
+  return J;
+}
+
+// one phi_update launch on up to PHI_MAX_INLINE_JOBS split-merge jobs (one CTA each)
+static int sm_phi(smg_chain* ch, const PhiJob* jobs, int nj) {
   SmWork* W = ch->sm;
-  const int cur = ch->cur;
-  PhiArgs A;
-  A.pp = ch->pp;
-  A.p = ch->p;
-  A.mmax = ch->mmax;
-  A.attr = ch->attr;
-  A.v = ch->v;
-  A.w = ch->w;
+  PhiArgs A = phi_args_base(ch, 0);
   A.H = W->H;
   A.counts = W->cnt;
-  A.jobs = W->jobs + j0;
-  A.njobs_ptr = nullptr;
   A.njobs = nj;
-  A.cen_src = ch->cen[cur];
-  A.sig_src = ch->sig[cur];
-  A.cen = ch->cen[cur];
-  A.sig = ch->sig[cur];
-  A.isg = ch->isg[cur];
-  A.den = ch->den;
-  A.u_center = uc;
-  A.u_sigma = us;
-  A.u_stride = ch->p;
-  A.key = mk_key(ch, sub);
-  A.prior = prior;
-  A.sigma_exact = ch->sigma_exact;
-  A.enable = enable;
-  A.status = ch->status;
-  dim3 grid(sm_cdiv(ch->pp, 128), nj);
-  phi_draw_kernel<<<grid, 128, 0, ch->st>>>(A);
-  phi_sden_kernel<<<nj, 256, 0, ch->st>>>(W->jobs + j0, nullptr, nj, ch->pp, ch->den, ch->sden[cur], enable);
-  ch->h_launches += 2;
+  A.njobs_ptr = nullptr;
+  for (int q = 0; q < nj; q++) A.jobs[q] = jobs[q];
+  A.enable = &W->info->same;
+  phi_update_kernel<<<nj, 256, 0, ch->st>>>(A);
+  ch->h_launches += 1;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
 
-// histogram of S u {i1,i2} split by z into H[h0], H[h0+1] (z == nullptr: everything into H[h0])
-static int sm_hist(smg_chain* ch, const int* z, int h0) {
+// histogram of S u {i1,i2} split by z into H[h0], H[h0+1] (z == nullptr: everything into H[h0]).
+// zeroed == true: the buffers were already cleared and the counts are known (restricted scans).
+static int sm_hist(smg_chain* ch, const int* z, int h0, bool zeroed, const int* enable) {
   SmWork* W = ch->sm;
   const size_t len = (size_t)ch->pp * ch->mmax;
   const int nh = z ? 2 : 1;
-  SMG_CUDA(cudaMemsetAsync(W->H + (size_t)h0 * len, 0, nh * len * 4, ch->st));
-  SMG_CUDA(cudaMemsetAsync(W->cnt + h0, 0, nh * 4, ch->st));
-  long long threads = (long long)(ch->n) * (ch->pp / 16);  // upper bound; the kernel trims to |S|+2
-  subset_histogram_kernel<<<sm_cdiv(threads, 256), 256, 0, ch->st>>>(ch->X, ch->pp, W->S, &W->info->nS, z,
-                                                                    &W->info->i1, ch->mmax, W->H + (size_t)h0 * len,
-                                                                    W->cnt + h0);
+  if (!zeroed) {
+    SMG_CUDA(cudaMemsetAsync(W->H + (size_t)h0 * len, 0, nh * len * 4, ch->st));
+    SMG_CUDA(cudaMemsetAsync(W->cnt + h0, 0, nh * 4, ch->st));
+  }
+  if (W->hist_smem) {
+    subset_histogram_smem_kernel<<<32, 256, W->hist_smem, ch->st>>>(ch->X, ch->pp, W->S, &W->info->nS, z, &W->info->i1,
+                                                                  ch->mmax, W->H + (size_t)h0 * len,
+                                                                  zeroed ? nullptr : W->cnt + h0, enable, 1);
+  } else {
+    if (zeroed)  // the global-atomic kernel recounts: clear what the decision kernel published
+      SMG_CUDA(cudaMemsetAsync(W->cnt + h0, 0, nh * 4, ch->st));
+    long long threads = (long long)(ch->n) * (ch->pp / 16);  // upper bound; the kernel trims to |S|+2
+    subset_histogram_kernel<<<sm_cdiv(threads, 256), 256, 0, ch->st>>>(ch->X, ch->pp, W->S, &W->info->nS, z,
+                                                                      &W->info->i1, ch->mmax, W->H + (size_t)h0 * len,
+                                                                      W->cnt + h0, enable, 1);
+  }
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
 
-// one restricted scan + update_phi of the two sides on (z, slots A/B, histograms h0/h0+1, jobs j0..j0+1)
-static int sm_restricted_scan(smg_chain* ch, int* z, int slotA, int slotB, int h0, int j0, int q, const double* u_rg,
-                              const double* uc, const double* us, const int* enable) {
+// allocation part of one restricted scan (split_merge.cpp:186-216) on sides z, parameter slots A/B;
+// leaves the side histograms in H[h0], H[h0+1] and the side counts in cnt[h0], cnt[h0+1]
+static int sm_restricted_alloc(smg_chain* ch, int* z, int slotA, int slotB, int h0, int q, const double* u_rg,
+                               const int* enable) {
   SmWork* W = ch->sm;
   const int cur = ch->cur;
-  sm_ll2_kernel<<<sm_cdiv(2ll * ch->n * 32, 256), 256, 0, ch->st>>>(ch->X, ch->pp, W->S, W->info, ch->cen[cur],
-                                                                  ch->isg[cur], ch->sden[cur], slotA, slotB, W->LL2,
-                                                                  enable, 1);
-  sm_rg_prepare_kernel<<<sm_cdiv(ch->n, 256), 256, 0, ch->st>>>(W->info, W->LL2, u_rg, mk_key(ch, SUB_SM_RG + q), W->rg_dl,
-                                                               W->rg_lgt, enable, 1);
-  sm_rgibbs_kernel<<<1, 32, 0, ch->st>>>(W->info, W->rg_dl, W->rg_lgt, W->LT, z, enable, 1);
-  ch->h_launches += 3;
+  const size_t len = (size_t)ch->pp * ch->mmax;
+  sm_ll2prep_kernel<<<296, 256, 0, ch->st>>>(ch->X, ch->pp, W->S, W->info, ch->cen[cur], ch->isg[cur], ch->sden[cur], slotA,
+                                            slotB, u_rg, mk_key(ch, SUB_SM_RG + q), W->rg_dl, W->rg_lgt, enable, 1);
+  sm_rdecide_kernel<<<1, SM_DECIDE_T, 0, ch->st>>>(W->info, W->rg_dl, W->rg_lgt, z, W->H + (size_t)h0 * len, (int)(2 * len),
+                                                   W->cnt + h0, enable, 1);
+  ch->h_launches += 2;
   SMG_CUDA(cudaGetLastError());
-  if (sm_hist(ch, z, h0)) return SMG_ERR_CUDA;
-  return sm_phi(ch, j0, 2, 0, SUB_SM_RG + q, uc, us, enable);
+  return sm_hist(ch, z, h0, true, enable);
 }
 
 // split_and_merge (split_merge.cpp:542-598)
@@ -691,58 +765,63 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     T.u_mg_s = tape->u_mg_s ? W->u_mg_s : nullptr;
     T.u_accept = tape->u_accept ? W->u_accept : nullptr;
   }
+  auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
   const size_t len = (size_t)pp * ch->mmax;
+  const int* same = &W->info->same;
   // ---- pair, S, plan
   sm_select_kernel<<<1, 1024, 0, ch->st>>>(n, ch->c, ch->K, T.u_pair, mk_key(ch, SUB_SM_SELECT), B, W->S, W->zState,
                                            W->info, W->plan, W->cnt, W->terms);
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
-  const int* same = &W->info->same;
-  // ---- prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380)
-  if (sm_phi(ch, 0, 3, 1, SUB_SM_PRIOR, T.u_prior_c, T.u_prior_s, nullptr)) return SMG_ERR_CUDA;
-  // ---- split launch: random sides then t restricted scans (split_merge.cpp:346-349)
-  sm_launch_alloc_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, T.u_launch, mk_key(ch, SUB_SM_LAUNCH), W->zL);
-  ch->h_launches++;
-  for (int q = 0; q < ch->t; q++) {
-    int rc = sm_restricted_scan(ch, W->zL, B + SM_SL_A, B + SM_SL_B, SH_L0, 3, q, T.u_rg ? T.u_rg + (size_t)q * n : nullptr,
-                                T.u_rg_c ? T.u_rg_c + (size_t)q * 2 * p : nullptr,
-                                T.u_rg_s ? T.u_rg_s + (size_t)q * 2 * p : nullptr, nullptr);
-    if (rc) return rc;
-  }
-  if (ch->t == 0 && sm_hist(ch, W->zL, SH_L0)) return SMG_ERR_CUDA;  // launch counts are still needed
-  // ---- histograms of the current-state sides and of the merged cluster
-  if (sm_hist(ch, W->zState, SH_S0)) return SMG_ERR_CUDA;
+  // ---- histograms of the current-state sides and of the merged cluster (fixed for the whole proposal)
+  if (sm_hist(ch, W->zState, SH_S0, false, nullptr)) return SMG_ERR_CUDA;
   sm_hist_add_kernel<<<sm_cdiv(len, 256), 256, 0, ch->st>>>((int)len, W->H, W->cnt, SH_S0, SH_S1, SH_M);
   ch->h_launches++;
-  // ---- merge launch: r parameter updates of the merged cluster (split_merge.cpp:386-387)
-  for (int q = 0; q < ch->r; q++) {
-    int rc = sm_phi(ch, 5, 1, 0, SUB_SM_MERGE + q, T.u_mg_c ? T.u_mg_c + (size_t)q * p : nullptr,
-                    T.u_mg_s ? T.u_mg_s + (size_t)q * p : nullptr, nullptr);
-    if (rc) return rc;
+  // ---- prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380)
+  {
+    PhiJob j[3];
+    for (int k = 0; k < 3; k++)
+      j[k] = sm_job(ch, J_PRI_A + k, SUB_SM_PRIOR, off(T.u_prior_c, (size_t)k * p), off(T.u_prior_s, (size_t)k * p), 0);
+    if (sm_phi(ch, j, 3)) return SMG_ERR_CUDA;
   }
+  // ---- split launch: random sides then t restricted scans (split_merge.cpp:346-349); the r parameter
+  //      updates of the merge launch (split_merge.cpp:386-387) are an independent chain on the fixed merged
+  //      histogram, so update q of it rides in the same launch as the update of scan q
+  sm_launch_alloc_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, T.u_launch, mk_key(ch, SUB_SM_LAUNCH), W->zL);
+  ch->h_launches++;
+  const int nsteps = ch->t > ch->r ? ch->t : ch->r;
+  for (int q = 0; q < nsteps; q++) {
+    PhiJob j[3];
+    int nj = 0;
+    if (q < ch->t) {
+      int rc = sm_restricted_alloc(ch, W->zL, B + SM_SL_A, B + SM_SL_B, SH_L0, q, off(T.u_rg, (size_t)q * n), nullptr);
+      if (rc) return rc;
+      for (int side = 0; side < 2; side++)
+        j[nj++] = sm_job(ch, J_L0 + side, SUB_SM_RG + q, off(T.u_rg_c, ((size_t)q * 2 + side) * p),
+                         off(T.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+    }
+    if (q < ch->r)
+      j[nj++] = sm_job(ch, J_MG, SUB_SM_MERGE + q, off(T.u_mg_c, (size_t)q * p), off(T.u_mg_s, (size_t)q * p), 0);
+    if (sm_phi(ch, j, nj)) return SMG_ERR_CUDA;
+  }
+  if (ch->t == 0 && sm_hist(ch, W->zL, SH_L0, false, nullptr)) return SMG_ERR_CUDA;  // launch counts are still needed
   // ---- proposal
   //   split (same == 1): star = split launch + one more restricted scan (split_merge.cpp:575-580)
-  sm_copy_z_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, W->zL, W->zStar);
-  sm_copy_slot_kernel<<<1, 256, 0, ch->st>>>(pp, ch->cen[cur], ch->sig[cur], ch->isg[cur], ch->sden[cur], B + SM_SL_A,
-                                             B + SM_ST_A);
-  sm_copy_slot_kernel<<<1, 256, 0, ch->st>>>(pp, ch->cen[cur], ch->sig[cur], ch->isg[cur], ch->sden[cur], B + SM_SL_B,
-                                             B + SM_ST_B);
-  ch->h_launches += 3;
+  //   merge (same == 0): star = merge launch + one more update_phi (split_merge.cpp:582-586); it is drawn in
+  //   both cases (it only fills the M* slot, the MH kernel ignores it for a split)
+  sm_begin_proposal_kernel<<<64, 256, 0, ch->st>>>(W->info, W->zL, W->zStar, pp, ch->cen[cur], ch->sig[cur], ch->isg[cur],
+                                                  ch->sden[cur], B + SM_SL_A, B + SM_ST_A, B + SM_SL_B, B + SM_ST_B);
+  ch->h_launches++;
   {
     const int q = ch->t;
-    int rc = sm_restricted_scan(ch, W->zStar, B + SM_ST_A, B + SM_ST_B, SH_P0, 6, q,
-                                T.u_rg ? T.u_rg + (size_t)q * n : nullptr,
-                                T.u_rg_c ? T.u_rg_c + (size_t)q * 2 * p : nullptr,
-                                T.u_rg_s ? T.u_rg_s + (size_t)q * 2 * p : nullptr, same);
+    int rc = sm_restricted_alloc(ch, W->zStar, B + SM_ST_A, B + SM_ST_B, SH_P0, q, off(T.u_rg, (size_t)q * n), same);
     if (rc) return rc;
-  }
-  //   merge (same == 0): star = merge launch + one more update_phi (split_merge.cpp:582-586).
-  //   The update is drawn in both cases (it only fills the M* slot); the MH kernel ignores it for a split.
-  {
-    const int q = ch->r;
-    int rc = sm_phi(ch, 8, 1, 0, SUB_SM_MERGE + q, T.u_mg_c ? T.u_mg_c + (size_t)q * p : nullptr,
-                    T.u_mg_s ? T.u_mg_s + (size_t)q * p : nullptr, nullptr);
-    if (rc) return rc;
+    PhiJob j[3];
+    for (int side = 0; side < 2; side++)
+      j[side] = sm_job(ch, J_P0 + side, SUB_SM_RG + q, off(T.u_rg_c, ((size_t)q * 2 + side) * p),
+                       off(T.u_rg_s, ((size_t)q * 2 + side) * p), 1);
+    j[2] = sm_job(ch, J_MSTAR, SUB_SM_MERGE + ch->r, off(T.u_mg_c, (size_t)ch->r * p), off(T.u_mg_s, (size_t)ch->r * p), 0);
+    if (sm_phi(ch, j, 3)) return SMG_ERR_CUDA;
   }
   // ---- MH terms
   sm_gsphi_prior_kernel<<<6, 256, 0, ch->st>>>(pp, p, ch->mmax, ch->attr, ch->v, ch->w, W->H, W->cnt, W->plan, ch->cen[cur],

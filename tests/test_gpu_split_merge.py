@@ -198,3 +198,17 @@ def test_split_merge_accepts_happen_and_match():
         if acc_split and acc_merge:
             break
     assert acc_split > 0 and acc_merge > 0
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_split_merge_large_member_set(seed):
+    # |S| spans several 1024-member chunks of the restricted-scan decision kernel; low-dimensional, noisy data
+    # keeps many members non-robust (count-dependent), so both the parallel and the ordered part are exercised
+    pb = Problem(3500 if seed % 2 == 0 else 7000, 12, 3, 2, seed=200 + seed, s=0.9)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    if seed % 2 == 0:  # everything in one cluster => a split proposal over n-2 members
+        c = np.zeros_like(c)
+        K, cen, sig = 1, cen[:1].copy(), sig[:1].copy()
+    ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=3, r=2)
+    assert ref["S"].size > 2048
+    check_case(pb, ref, got, after, labA, labB)
