@@ -39,6 +39,7 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
+  SMG_CUDA(cudaFuncSetAttribute(cluster_histogram_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
   if (dalloc(&ch->attr, pp) || dalloc(&ch->v, pp) || dalloc(&ch->w, pp)) return SMG_ERR_CUDA;
   for (int b = 0; b < 2; b++) {
@@ -64,7 +65,8 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->H, (size_t)ch->Kcap * pp * ch->mmax)) return SMG_ERR_CUDA;
   ch->loglik_blocks = std::min(1184, std::max(1, cdiv(n, 8)));
   if (dalloc(&ch->partial, ch->loglik_blocks) || dalloc(&ch->loglik_d, 1)) return SMG_ERR_CUDA;
-  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8)) return SMG_ERR_CUDA;
+  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4))
+    return SMG_ERR_CUDA;
   SMG_CUDA(cudaMemset(ch->status, 0, 4));
   SMG_CUDA(cudaMemset(ch->accepted_d, 0, 4));
   SMG_CUDA(cudaMemset(ch->stats_d, 0, 64));
@@ -82,7 +84,7 @@ static void chain_free(smg_chain* ch) {
                   ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
                   ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->mrg, ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
-                  ch->stats_d, ch->tape_d, ch->uc_d,     ch->us_d};
+                  ch->stats_d, ch->scan_job, ch->tape_d, ch->uc_d,     ch->us_d};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int q = 0; q < 8; q++)
@@ -153,9 +155,10 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.log_gamma_m = std::log(ch->gamma / ch->m_aux);
   A.status = ch->status;
   A.stats = ch->stats_d;
+  A.job = ch->scan_job;
   scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, ch->LLaux,
                                                                           ch->c, ch->counts, A.log_gamma_m, ch->mrg);
-  neal8_scan_kernel<<<1, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);
+  neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);  // one cluster
   SMG_CUDA(cudaGetLastError());
   // back to canonical form: labels in c, parameters in label order in the other buffer
   const int nx = ch->cur ^ 1;
@@ -177,9 +180,16 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
 static int launch_histogram(smg_chain* ch) {
   SMG_CUDA(cudaMemsetAsync(ch->H, 0, (size_t)ch->Kcap * ch->pp * ch->mmax * sizeof(int), ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->counts, 0, (size_t)ch->NST * sizeof(int), ch->st));
-  long long threads = (long long)ch->n * (ch->pp / 16);
-  cluster_histogram_kernel<<<cdiv(threads, 256), 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->c, ch->mmax, ch->H,
-                                                                  ch->counts);
+  const size_t smem = ((size_t)ch->Kcap * 16 * ch->mmax + ch->Kcap) * sizeof(int);
+  if (smem <= 72 * 1024) {  // three CTAs per SM
+    const int rg = std::max(1, std::min(32, cdiv(ch->n, 256 * 8)));
+    cluster_histogram_smem_kernel<<<dim3(ch->pp / 16, rg), 256, smem, ch->st>>>(ch->X, ch->n, ch->pp, ch->c, ch->mmax, ch->K,
+                                                                               ch->Kcap, ch->H, ch->counts);
+  } else {
+    long long threads = (long long)ch->n * (ch->pp / 16);
+    cluster_histogram_kernel<<<cdiv(threads, 256), 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->c, ch->mmax, ch->H,
+                                                                    ch->counts);
+  }
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;

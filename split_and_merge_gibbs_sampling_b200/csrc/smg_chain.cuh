@@ -81,6 +81,7 @@ struct smg_chain {
   int* status = nullptr;
   int* accepted_d = nullptr;
   unsigned long long* stats_d = nullptr;
+  int* scan_job = nullptr;       // mailbox of the scan cluster
   double* tape_d = nullptr;      // [n][m_aux+1] injected scan uniforms
   double *uc_d = nullptr, *us_d = nullptr;  // injected phi uniforms [NST][p]
   smg::SmWork* sm = nullptr;

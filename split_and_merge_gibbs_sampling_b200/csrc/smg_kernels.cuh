@@ -243,19 +243,21 @@ struct ScanArgs {
   double log_gamma_m;  // log(gamma/m)  (neal8.cpp:78)
   int* status;
   unsigned long long* stats;  // [0] rounds, [1] events, [2] births, [3] deaths
+  int* job;  // [4] mailbox of the scan cluster: {slot (-1: exit), first row, end row}
 };
 
 #define EVT_NONE (-1)
 
-// All 32 warps of the scan CTA materialise LL[r0..r1)[slot] for a column born during the pass.
-// Four rows per warp are in flight at a time; the value of each entry is the one warp_mismatch_dot
-// would return (same per-lane order, same butterfly).
-__device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, int r0, int r1, int warp, int lane) {
+// Materialise LL[r0..r1)[slot] for a column born during the pass.  The rows are dealt in blocks of 128
+// (4 per warp in flight) to the `nparts` CTAs of the scan cluster; `part` is this CTA's rank.  The value of
+// each entry is the one warp_mismatch_dot would return (same per-lane order, same butterfly).
+__device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, int r0, int r1, int warp, int lane, int part,
+                                                 int nparts) {
   const int pp = A.pp;
   const uint8_t* crow = A.cen + (size_t)slot * pp;
   const double* wrow = A.isg + (size_t)slot * pp;
   const double sd = A.sden[slot];
-  for (int row = r0 + warp * 4; row < r1; row += SMG_SCAN_WARPS * 4) {
+  for (int row = r0 + (part * SMG_SCAN_WARPS + warp) * 4; row < r1; row += nparts * SMG_SCAN_WARPS * 4) {
     double acc[4] = {0.0, 0.0, 0.0, 0.0};
     for (int j0 = lane * 8; j0 < pp; j0 += 256) {
       const uint2 cv = *reinterpret_cast<const uint2*>(crow + j0);
@@ -284,6 +286,17 @@ __device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, in
       if (lane == 0 && row + r < r1) A.LL[(size_t)(row + r) * A.ldl + slot] = -dot - sd;
     }
   }
+}
+
+// thread-block-cluster plumbing of the scan kernel (rank 0 scans, the other CTAs only fill born columns)
+#define SCAN_CLUSTER 8
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -348,8 +361,24 @@ __global__ void __launch_bounds__(256) scan_margin_kernel(int n, const int* __re
 // 32 per round (one warp each) against the same state: Rcpp::sample's descending-order inverse CDF.
 // The first one whose draw changes the state (an event) is applied, the rest of the chunk is screened
 // again, and evaluation restarts right after it -- the result is the one-at-a-time scan's.
+//
+// The kernel runs as ONE thread-block cluster of SCAN_CLUSTER CTAs.  Rank 0 does everything above.  When a
+// cluster is born (neal8.cpp:140-159) its likelihood column is needed for every later observation: rank 0
+// posts {slot, rows} in a mailbox and the whole cluster evaluates the column between two cluster barriers
+// (n*pp bytes of X spread over SCAN_CLUSTER SMs instead of one).  The other ranks sleep in the barrier.
 // =============================================================================
-__global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(ScanArgs A) {
+__global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_WARPS * 32, 1)
+    neal8_scan_kernel(ScanArgs A) {
+  if (cluster_cta_rank() != 0) {  // ---- column-fill helpers
+    const int lane_h = threadIdx.x & 31, warp_h = threadIdx.x >> 5;
+    for (;;) {
+      cluster_sync_all();  // the mailbox (and the new parameter vector) are published
+      const int slot = __ldcg(&A.job[0]), r0 = __ldcg(&A.job[1]), r1 = __ldcg(&A.job[2]);
+      if (slot < 0) return;
+      scan_fill_column(A, slot, r0, r1, warp_h, lane_h, (int)cluster_cta_rank(), SCAN_CLUSTER);
+      cluster_sync_all();  // the column is complete
+    }
+  }
   __shared__ int s_cnt[SMG_MAX_SLOTS];
   __shared__ double s_logc[SMG_MAX_SLOTS];
   __shared__ double s_logcm1[SMG_MAX_SLOTS];
@@ -394,12 +423,12 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     if (K0 > A.K0cap) s_err |= ST_LL_COLS;
   }
   __syncthreads();
+  bool abort_pass = false;
   if (s_err) {
     if (tid == 0) atomicOr(A.status, s_err);
-    return;
+    abort_pass = true;
   }
 
-  bool abort_pass = false;
   // this thread's observation of the NEXT chunk (loaded one chunk ahead)
   int nx_own = 0;
   double nx_mg = 0.0;
@@ -416,16 +445,6 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
       nx_own = A.c[i0 + SCAN_CHUNK + tid];
       nx_mg = A.mrg[i0 + SCAN_CHUNK + tid];
     }
-    // ---- columns of the clusters born during this pass: materialise this chunk's rows
-    if (s_next > K0) {
-      const int Kx = s_K;
-      for (int e = 0; e < Kx; e++) {
-        const int slot = s_l2s[e];
-        if (slot >= K0 && slot < A.ldl) scan_fill_column(A, slot, i0, i0 + nrows, warp, lane);
-      }
-      __syncthreads();
-    }
-
     int start = 0;          // rows [0, start) of the chunk are final
     bool screened = false;  // s_und valid for the current state
     while (start < nrows) {
@@ -710,10 +729,16 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
           A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
         }
         if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
-        if (new_slot < A.ldl) {
-          __syncthreads();  // the new parameter vector is visible to the whole CTA
-          // materialise the new column for the rest of this chunk; later chunks do it at their start
-          scan_fill_column(A, new_slot, ie + 1, i0 + nrows, warp, lane);
+        if (new_slot < A.ldl && ie + 1 < n) {
+          // materialise the new column for every later observation, on the whole cluster
+          if (tid == 0) {
+            A.job[0] = new_slot;
+            A.job[1] = ie + 1;
+            A.job[2] = n;
+          }
+          cluster_sync_all();  // mailbox + parameter vector visible to every CTA of the cluster
+          scan_fill_column(A, new_slot, ie + 1, n, warp, lane, 0, SCAN_CLUSTER);
+          cluster_sync_all();  // column complete (read below with ld.global.cg)
         }
       }
       __syncthreads();  // everyone has read the pre-event state
@@ -780,6 +805,9 @@ __global__ void __launch_bounds__(SMG_SCAN_WARPS * 32, 1) neal8_scan_kernel(Scan
     }
     __syncthreads();
   }
+  // release the helpers
+  if (tid == 0) A.job[0] = -1;
+  cluster_sync_all();
   // publish: K, counts by slot, slot->label map
   for (int s = tid; s < A.NS && s < SMG_MAX_SLOTS; s += blockDim.x) {
     A.counts[s] = s_cnt[s];
@@ -840,6 +868,48 @@ __global__ void __launch_bounds__(256) cluster_histogram_kernel(const uint8_t* _
     int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
     if (x) atomicAdd(&Hk[b * mmax + (x - 1)], 1);
   }
+}
+
+// Same result with the histogram privatised in shared memory: a CTA owns one 16-attribute slice of
+// the table ([K][16][mmax] ints) and a strided share of the rows, so the integer atomics stay on chip
+// and each (cluster, attribute, level) cell costs one global atomic per CTA instead of one per row.
+__global__ void __launch_bounds__(256) cluster_histogram_smem_kernel(const uint8_t* __restrict__ X, int n, int pp,
+                                                                     const int* __restrict__ c, int mmax,
+                                                                     const int* __restrict__ Kptr, int Kcap,
+                                                                     int* __restrict__ H, int* __restrict__ counts) {
+  extern __shared__ int s_h[];  // [K][16][mmax] then [Kcap] member counts
+  const int K = min(*Kptr, Kcap);
+  const int cells = K * 16 * mmax;
+  int* s_cnt = s_h + (size_t)Kcap * 16 * mmax;
+  const int slice = blockIdx.x;
+  for (int q = threadIdx.x; q < cells; q += blockDim.x) s_h[q] = 0;
+  for (int q = threadIdx.x; q < Kcap; q += blockDim.x) s_cnt[q] = 0;
+  __syncthreads();
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
+    const int k = c[i];
+    if (k >= K) continue;
+    const uint4 v = *reinterpret_cast<const uint4*>(X + (size_t)i * pp + slice * 16);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (slice == 0) atomicAdd(&s_cnt[k], 1);
+    int* Hk = s_h + (size_t)k * 16 * mmax;
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
+      if (x) atomicAdd(&Hk[b * mmax + (x - 1)], 1);
+    }
+  }
+  __syncthreads();
+  const int per = 16 * mmax;
+  for (int q = threadIdx.x; q < cells; q += blockDim.x) {
+    const int hv = s_h[q];
+    if (hv) {
+      const int k = q / per, rem = q - k * per;
+      atomicAdd(&H[((size_t)k * pp + slice * 16) * mmax + rem], hv);
+    }
+  }
+  if (slice == 0)
+    for (int q = threadIdx.x; q < K; q += blockDim.x)
+      if (s_cnt[q]) atomicAdd(&counts[q], s_cnt[q]);
 }
 
 // histogram of a member subset split in two groups by z (split-merge launch states):

@@ -178,9 +178,10 @@ __global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restri
   }
 }
 
-// The sequential part, one CTA.  The log-count term of D lies in [-log(nS+1), log(nS+1)] whatever the
-// running counts are, so a member with |d0| > log(nS+1) + |logit(u)| lands on the side of sign(d0) no
-// matter what happened before it ("robust").  Per chunk of 1024 members: robust members are decided in
+// The sequential part, one CTA.  Inside a chunk of 1024 members the running side counts can only move by
+// the chunk's own population, which bounds the log-count term of D; a member whose D clears |logit(u)|
+// over that whole interval lands on the side of sign(d0) no matter what happened before it ("robust").
+// Per chunk: robust members are decided in
 // parallel, a block prefix sum gives the count contribution of the robust members before every
 // position, and only the non-robust members are walked in order by one warp (32 at a time against the
 // same counts; the first one that changes side is applied and evaluation restarts after it).  Same
@@ -210,15 +211,24 @@ __global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* i
     }
     __syncthreads();
   }
-  const double Lmax = log((double)(nS + 1));
   for (int base = 0; base < nS; base += SM_DECIDE_T) {
     const int pos = base + tid;
     const bool valid = pos < nS;
     const double d0 = valid ? dl[pos] : 0.0, lg = valid ? lgt[pos] : 0.0;
     const int zz = valid ? z[pos] : 0;
-    const bool robust = valid && (fabs(d0) > Lmax + fabs(lg) + 1e-9);
+    // b = side-1 members other than the one being decided (anchor included) stays inside [blo, bhi] while
+    // this chunk is walked: at most the chunk's c1 side-1 members leave and its c0 side-0 members join.
+    // The log-count term log((nS+1-b)/b) of D is decreasing in b.
+    const int c1 = __syncthreads_count(valid && zz == 1);
+    const int c0 = min(SM_DECIDE_T, nS - base) - c1;
+    const int blo = s_nB - c1, bhi = s_nB + c0 - 1;
+    const double dc_max = log((double)(nS + 1 - blo)) - log((double)blo);
+    const double dc_min = log((double)(nS + 1 - bhi)) - log((double)bhi);
+    const bool robust0 = valid && (dc_min + d0 > fabs(lg) + 1e-9);   // D > |logit u| whatever the counts: side 0
+    const bool robust1 = valid && (dc_max + d0 < -fabs(lg) - 1e-9);  // D < -|logit u|: side 1
+    const bool robust = robust0 || robust1;
     const bool nonrob = valid && !robust;
-    const int newz = robust ? (d0 > 0.0 ? 0 : 1) : zz;
+    const int newz = robust0 ? 0 : (robust1 ? 1 : zz);
     const int delta = newz - zz;
     int incl = delta;
 #pragma unroll
