@@ -20,3 +20,5 @@ for it in range(nsw):
         tm["scan_ms"], tm["split_merge_ms"], tm["ll_block_ms"], tm["update_phi_ms"], tm["total_ms"]),
         {k: st[k] - prev[k] for k in ("scan_rounds", "scan_events", "births", "deaths")})
     prev = st
+    pr = ch.scan_profile()
+    print('    scan cycles:', {k: v for k, v in pr.items() if k != '_'})

@@ -45,7 +45,7 @@ EXPORTS = [
     "smg_step", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
     "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
-    "smg_debug_split_merge",
+    "smg_debug_split_merge", "smg_debug_scan_profile",
 ]
 
 _lib = None
@@ -85,6 +85,7 @@ def load():
     lib.smg_get_stats.argtypes = [C.c_void_p, c_ull_p]
     lib.smg_get_timings.argtypes = [C.c_void_p, c_dbl_p]
     lib.smg_last_step_ms.argtypes = [C.c_void_p, c_dbl_p]
+    lib.smg_debug_scan_profile.argtypes = [C.c_void_p, c_ull_p]
     lib.smg_debug_set_state.argtypes = [C.c_void_p, C.c_int, c_int_p, c_dbl_p, c_dbl_p]
     lib.smg_debug_set_pool.argtypes = [C.c_void_p, C.c_longlong, c_dbl_p, c_dbl_p]
     lib.smg_debug_get_pool.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, c_dbl_p, c_dbl_p]

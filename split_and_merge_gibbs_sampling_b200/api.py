@@ -136,6 +136,12 @@ class Chain:
         keys = ["scan_rounds", "scan_events", "births", "deaths", "sweeps", "launches", "sm_proposals", "sm_accepted"]
         return dict(zip(keys, (int(x) for x in out)))
 
+    def scan_profile(self):
+        out = np.zeros(8, dtype=np.uint64)
+        lb.check(self.lib.smg_debug_scan_profile(self.h, out.ctypes.data_as(lb.c_ull_p)))
+        keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "_"]
+        return dict(zip(keys, (int(x) for x in out)))
+
     def timings(self):
         out = np.zeros(8)
         lb.check(self.lib.smg_get_timings(self.h, lb.dptr(out)))

@@ -65,8 +65,9 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->H, (size_t)ch->Kcap * pp * ch->mmax)) return SMG_ERR_CUDA;
   ch->loglik_blocks = std::min(1184, std::max(1, cdiv(n, 8)));
   if (dalloc(&ch->partial, ch->loglik_blocks) || dalloc(&ch->loglik_d, 1)) return SMG_ERR_CUDA;
-  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4))
+  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4) || dalloc(&ch->scan_prof, 8))
     return SMG_ERR_CUDA;
+  SMG_CUDA(cudaMemset(ch->scan_prof, 0, 64));
   SMG_CUDA(cudaMemset(ch->status, 0, 4));
   SMG_CUDA(cudaMemset(ch->accepted_d, 0, 4));
   SMG_CUDA(cudaMemset(ch->stats_d, 0, 64));
@@ -84,7 +85,7 @@ static void chain_free(smg_chain* ch) {
                   ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
                   ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->mrg, ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
-                  ch->stats_d, ch->scan_job, ch->tape_d, ch->uc_d,     ch->us_d};
+                  ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d};
   for (void* q : ptrs)
     if (q) cudaFree(q);
   for (int q = 0; q < 8; q++)
@@ -156,6 +157,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.status = ch->status;
   A.stats = ch->stats_d;
   A.job = ch->scan_job;
+  A.prof = ch->scan_prof;
   scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, ch->LLaux,
                                                                           ch->c, ch->counts, A.log_gamma_m, ch->mrg);
   neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);  // one cluster
@@ -594,6 +596,15 @@ int smg_get_stats(smg_chain* ch, unsigned long long* out8) {
   out8[5] = ch->h_launches;
   out8[6] = ch->h_sm_props;
   out8[7] = d[7];
+  return 0;
+}
+
+int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
+  if (!ch || !out8) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  SMG_CUDA(cudaMemcpy(out8, ch->scan_prof, 64, cudaMemcpyDeviceToHost));
+  SMG_CUDA(cudaMemset(ch->scan_prof, 0, 64));
   return 0;
 }
 

@@ -82,6 +82,7 @@ struct smg_chain {
   int* accepted_d = nullptr;
   unsigned long long* stats_d = nullptr;
   int* scan_job = nullptr;       // mailbox of the scan cluster
+  unsigned long long* scan_prof = nullptr;  // cycle counters of the scanner's phases
   double* tape_d = nullptr;      // [n][m_aux+1] injected scan uniforms
   double *uc_d = nullptr, *us_d = nullptr;  // injected phi uniforms [NST][p]
   smg::SmWork* sm = nullptr;

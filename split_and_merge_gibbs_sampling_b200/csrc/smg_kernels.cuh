@@ -48,6 +48,14 @@ enum StatusBits : int {
 #define LLB_JT 64
 #define LLB_XS (LLB_JT / 4 + 1)  // padded row stride in words
 
+// acc += w when (mm & mask) != 0, as ONE predicated DADD (LOP3 with predicate output + @p DADD) instead of the
+// add + two 32-bit selects the compiler emits for the C form: the kernel is bound by the integer ALU pipe.
+__device__ __forceinline__ void pred_add(double& acc, uint32_t mm, uint32_t mask, double w) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.f64 %0, %0, %3;\n\t}"
+      : "+d"(acc)
+      : "r"(mm), "r"(mask), "d"(w));
+}
+
 __global__ void __launch_bounds__(256) hamming_ll_block_kernel(const uint8_t* __restrict__ X, int n, int pp,
                                                                const uint8_t* __restrict__ cen,
                                                                const double* __restrict__ isg,
@@ -109,11 +117,11 @@ __global__ void __launch_bounds__(256) hamming_ll_block_kernel(const uint8_t* __
         const double2 w23 = *reinterpret_cast<const double2*>(&sw[(wg * 4 + c) * LLB_JT + jw * 4 + 2]);
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-          uint32_t mm = __vcmpne4(xw[r], cw[c]);  // 0xff per mismatching byte
-          if (mm & 0x000000ffu) acc[r][c] += w01.x;
-          if (mm & 0x0000ff00u) acc[r][c] += w01.y;
-          if (mm & 0x00ff0000u) acc[r][c] += w23.x;
-          if (mm & 0xff000000u) acc[r][c] += w23.y;
+          const uint32_t mm = __vcmpne4(xw[r], cw[c]);  // 0xff per mismatching byte
+          pred_add(acc[r][c], mm, 0x000000ffu, w01.x);
+          pred_add(acc[r][c], mm, 0x0000ff00u, w01.y);
+          pred_add(acc[r][c], mm, 0x00ff0000u, w23.x);
+          pred_add(acc[r][c], mm, 0xff000000u, w23.y);
         }
       }
     }
@@ -244,6 +252,7 @@ struct ScanArgs {
   int* status;
   unsigned long long* stats;  // [0] rounds, [1] events, [2] births, [3] deaths
   int* job;  // [4] mailbox of the scan cluster: {slot (-1: exit), first row, end row}
+  unsigned long long* prof;  // [8] optional cycle counters of the scanner's phases (thread 0), or null
 };
 
 #define EVT_NONE (-1)
@@ -349,6 +358,237 @@ __global__ void __launch_bounds__(256) scan_margin_kernel(int n, const int* __re
 
 #define SCAN_CHUNK (SMG_SCAN_WARPS * 32)  // observations screened per step: one per thread
 
+// Shared-memory state of the scan CTA (counts, their logs, label <-> slot maps, drift of the counts).
+struct ScanState {
+  int cnt[SMG_MAX_SLOTS];
+  double logc[SMG_MAX_SLOTS];
+  double logcm1[SMG_MAX_SLOTS];
+  int l2s[SMG_MAX_SLOTS];
+  int s2l[SMG_MAX_SLOTS];
+  double lc0[SMG_MAX_ENTRIES];     // log n0_k of the clusters present at the start
+  double lcm1_0[SMG_MAX_ENTRIES];  // log (n0_k - 1)
+  double dminus[SMG_MAX_ENTRIES];
+  double Dplus;
+  int own[SCAN_CHUNK];  // start-of-pass slot of the chunk's undecided rows
+  int evt[SMG_SCAN_WARPS];
+  int row[SMG_SCAN_WARPS];
+  unsigned und[SMG_SCAN_WARPS];  // undecided rows of the current chunk (bit per row)
+  int K, next, err;
+  unsigned long long stats[4];
+};
+
+// likelihood of observation i under a cluster whose column is not materialised (slot >= ldl: more births in
+// one pass than spare LL columns) -- whole warp, rare
+__device__ __noinline__ double scan_dyn_ll(const ScanArgs& A, int i, int slot, int lane) {
+  const int pp = A.pp;
+  const double dot = warp_mismatch_dot(A.X + (size_t)i * pp, A.cen + (size_t)slot * pp, A.isg + (size_t)slot * pp, pp, lane);
+  return -dot - A.sden[slot];
+}
+
+// Exact allocation draw of observation i by one warp (neal8.cpp:40-102 + Rcpp::sample's descending-order
+// inverse CDF).  Entry e = q*32 + lane; NQ*32 >= K + m_aux.  Returns EVT_NONE when the draw leaves the
+// state unchanged, the selected entry (0..K+m-1) when it changes it, -2 when the weights are not finite.
+template <int NQ>
+__device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane) {
+  const int m = A.m_aux, ne = K + m;
+  const double* rowp = A.LL + (size_t)i * A.ldl;
+  const double* auxp = A.LLaux + (size_t)i * m;
+  // the allocation uniform does not depend on anything loaded below: its Philox rounds overlap the loads
+  const double u = get_u(A.u_alloc, (size_t)i * A.u_stride, A.key, U_ALLOC, (uint32_t)i, 0u);
+  int slot[NQ];
+  double ll[NQ];
+  bool anydyn = false;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int e = q * 32 + lane;
+    slot[q] = (e < K) ? S.l2s[e] : -1;
+    ll[q] = 0.0;
+    if (slot[q] >= 0 && slot[q] < A.ldl)
+      ll[q] = __ldcg(&rowp[slot[q]]);
+    else if (e >= K && e < ne)
+      ll[q] = auxp[e - K];
+    anydyn |= (slot[q] >= A.ldl);
+  }
+  if (__any_sync(SMG_FULL, anydyn)) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      unsigned dyn = __ballot_sync(SMG_FULL, slot[q] >= A.ldl);
+      while (dyn) {
+        const int src = __ffs(dyn) - 1;
+        dyn &= dyn - 1;
+        const double v = scan_dyn_ll(A, i, __shfl_sync(SMG_FULL, slot[q], src), lane);
+        if (lane == src) ll[q] = v;
+      }
+    }
+  }
+  const bool singleton = (S.cnt[old_slot] == 1);
+  // ---- log weights: existing clusters (neal8.cpp:40-56), auxiliary components (neal8.cpp:78-92)
+  double ll_own = 0.0;
+#pragma unroll
+  for (int q = 0; q < NQ; q++)
+    if (slot[q] == old_slot) ll_own = ll[q];
+  if (singleton) {  // own parameters become aux slot 0 (neal8.cpp:72-75)
+    // ll_own is set by exactly one lane; LL is strictly negative so != 0 identifies it
+    const unsigned who = __ballot_sync(SMG_FULL, ll_own != 0.0);
+    ll_own = shfl_d(ll_own, who ? (__ffs(who) - 1) : 0);
+  }
+  double lg[NQ];
+  uint64_t mykey = 0;
+  int myarg = 0x7fffffff;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int e = q * 32 + lane;
+    lg[q] = -CUDART_INF;
+    if (slot[q] >= 0) {
+      const bool own = (slot[q] == old_slot);
+      const int cx = S.cnt[slot[q]] - (own ? 1 : 0);
+      if (cx > 0) lg[q] = (own ? S.logcm1[slot[q]] : S.logc[slot[q]]) + ll[q];
+    } else if (e >= K && e < ne) {
+      lg[q] = A.log_gamma_m + ((singleton && e == K) ? ll_own : ll[q]);
+    }
+    if (e < ne) {
+      const uint64_t k = sort_key(lg[q]);
+      if (k > mykey) {
+        mykey = k;
+        myarg = e;
+      }
+    }
+  }
+  // ---- max, exp, sum  (neal8.cpp:95-96)
+  const uint64_t maxkey = warp_max_key(mykey);
+  const double M = key_to_double(maxkey);
+  const int argmax = (int)__reduce_min_sync(SMG_FULL, (unsigned)((mykey == maxkey) ? myarg : 0x7fffffff));  // smallest index
+  double pe[NQ];
+  double lsum = 0.0;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int e = q * 32 + lane;
+    pe[q] = 0.0;
+    if (e < ne) {
+      const double d = lg[q] - M;
+      if (d == 0.0)
+        pe[q] = 1.0;
+      else if (d >= -SCAN_DOMINANCE)
+        pe[q] = exp(d);
+    }
+    lsum += pe[q];
+  }
+  const double Ssum = warp_sum(lsum);
+  const double T = u * Ssum;  // compared against the cumulative sums of the unnormalised weights
+  int new_e;
+  if (!(M > -CUDART_INF) || !(Ssum == Ssum)) {
+    return -2;  // all -Inf or NaN: Rcpp::sample would stop()
+  } else if (T <= 1.0) {
+    new_e = argmax;  // first entry of the descending order already covers u
+  } else {
+    // Rcpp::sample semantics: walk the probabilities in DESCENDING order (smallest index first among
+    // ties) and return the first entry whose cumulative sum reaches u; the last entry if none does.
+    int mysig = 0;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) mysig += (pe[q] > 0.0);
+    const int nsig = warp_sum_i(mysig);
+    new_e = -1;
+    if (nsig <= 16) {
+      // few significant entries: extract the maxima one by one, accumulating in that order
+      unsigned rem = 0;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) rem |= (pe[q] > 0.0) ? (1u << q) : 0u;
+      double cum = 0.0;
+      for (int it = 0; it < nsig; it++) {
+        uint64_t ck = 0;
+        int ce = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const uint64_t k = (uint64_t)__double_as_longlong(pe[q]);  // positive doubles order like their bits
+          if (((rem >> q) & 1u) && k > ck) {
+            ck = k;
+            ce = q * 32 + lane;
+          }
+        }
+        const uint64_t wk = warp_max_key(ck);
+        const int we = (int)__reduce_min_sync(SMG_FULL, (unsigned)((ck == wk) ? ce : 0x7fffffff));
+        cum += __longlong_as_double((long long)wk);
+        if (T <= cum) {
+          new_e = we;
+          break;
+        }
+        if ((we & 31) == lane) rem &= ~(1u << (we >> 5));
+      }
+    } else {
+      // many significant entries (burn-in): cumulative sum of everything that precedes each entry
+      double G[NQ];
+#pragma unroll
+      for (int q = 0; q < NQ; q++) G[q] = 0.0;
+#pragma unroll
+      for (int qy = 0; qy < NQ; qy++) {
+        unsigned sig = __ballot_sync(SMG_FULL, pe[qy] > 0.0);
+        while (sig) {
+          const int src = __ffs(sig) - 1;
+          sig &= sig - 1;
+          const double py = shfl_d(pe[qy], src);
+          const int ey = qy * 32 + src;
+#pragma unroll
+          for (int q = 0; q < NQ; q++) {
+            const int ex = q * 32 + lane;
+            if (py > pe[q] || (py == pe[q] && ey < ex)) G[q] += py;
+          }
+        }
+      }
+      // candidate = entry with u*S <= G + p, largest p first (smallest index among ties)
+      uint64_t bestk = 0;
+      int beste = 0x7fffffff;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int ex = q * 32 + lane;
+        if (ex < ne && pe[q] > 0.0 && T <= G[q] + pe[q]) {
+          const uint64_t k = sort_key(pe[q]);
+          if (k > bestk || (k == bestk && ex < beste)) {
+            bestk = k;
+            beste = ex;
+          }
+        }
+      }
+      const uint64_t wk = warp_max_key(bestk);
+      if (wk != 0) new_e = (int)__reduce_min_sync(SMG_FULL, (unsigned)((bestk == wk) ? beste : 0x7fffffff));
+    }
+    if (new_e < 0) {
+      // fall-through of the reference loop: last entry of the descending order
+      // (smallest probability, largest index among ties)
+      uint64_t mink = ~0ull;
+      int mine = -1;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int ex = q * 32 + lane;
+        if (ex < ne) {
+          const uint64_t k = sort_key(pe[q]);
+          if (k < mink || (k == mink && ex > mine)) {
+            mink = k;
+            mine = ex;
+          }
+        }
+      }
+      const uint64_t wmin = ~warp_max_key(~mink);
+      new_e = (int)__reduce_max_sync(SMG_FULL, (unsigned)((mink == wmin) ? mine : 0));
+    }
+  }
+  // ---- does the draw change the state?
+  if (new_e < K) return (S.l2s[new_e] != old_slot) ? new_e : EVT_NONE;
+  return (singleton && new_e == K) ? EVT_NONE : new_e;  // singleton re-drawing its own phi: no-op
+}
+
+
+// loads of the NEXT chunk's slot and margin, issued here and now (volatile asm: the compiler may not sink them
+// to their first use one chunk later, which would expose the whole memory latency at every chunk)
+__device__ __forceinline__ void scan_prefetch_row(const int* cp, const double* mp, int& own, double& mg) {
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(own) : "l"(cp) : "memory");
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(mg) : "l"(mp) : "memory");
+}
+
+// more than 64 entries per draw: rare, kept out of line so that its registers do not weigh on the scan kernel
+__device__ __noinline__ int scan_eval_row_wide(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane) {
+  return scan_eval_row<SMG_EPL>(A, S, i, old_slot, K, lane);
+}
+
 // =============================================================================
 // K2: the scan proper (one resident CTA of 32 warps).
 //
@@ -379,20 +619,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       cluster_sync_all();  // the column is complete
     }
   }
-  __shared__ int s_cnt[SMG_MAX_SLOTS];
-  __shared__ double s_logc[SMG_MAX_SLOTS];
-  __shared__ double s_logcm1[SMG_MAX_SLOTS];
-  __shared__ int s_l2s[SMG_MAX_SLOTS];
-  __shared__ int s_s2l[SMG_MAX_SLOTS];
-  __shared__ double s_lc0[SMG_MAX_ENTRIES];    // log n0_k of the clusters present at the start
-  __shared__ double s_lcm1_0[SMG_MAX_ENTRIES]; // log (n0_k - 1)
-  __shared__ double s_dminus[SMG_MAX_ENTRIES];
-  __shared__ double s_Dplus;
-  __shared__ int s_evt[SMG_SCAN_WARPS];
-  __shared__ int s_row[SMG_SCAN_WARPS];
-  __shared__ unsigned s_und[SMG_SCAN_WARPS];  // undecided rows of the current chunk (bit per row)
-  __shared__ int s_K, s_next, s_err;
-  __shared__ unsigned long long s_stats[4];
+  __shared__ ScanState S;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = A.n, pp = A.pp, m = A.m_aux;
@@ -402,305 +629,155 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     const int cnt = (s < K0) ? A.counts[s] : 0;
     const double lc = cnt > 0 ? log((double)cnt) : -CUDART_INF;
     const double lcm1 = cnt > 1 ? log((double)(cnt - 1)) : -CUDART_INF;
-    s_cnt[s] = cnt;
-    s_logc[s] = lc;
-    s_logcm1[s] = lcm1;
-    s_l2s[s] = s;
-    s_s2l[s] = (s < K0) ? s : -1;
+    S.cnt[s] = cnt;
+    S.logc[s] = lc;
+    S.logcm1[s] = lcm1;
+    S.l2s[s] = s;
+    S.s2l[s] = (s < K0) ? s : -1;
     if (s < SMG_MAX_ENTRIES) {
-      s_lc0[s] = lc;
-      s_lcm1_0[s] = lcm1;
-      s_dminus[s] = (cnt > 1) ? 0.0 : CUDART_INF;
+      S.lc0[s] = lc;
+      S.lcm1_0[s] = lcm1;
+      S.dminus[s] = (cnt > 1) ? 0.0 : CUDART_INF;
     }
   }
   if (tid == 0) {
-    s_K = K0;
-    s_next = K0;
-    s_err = 0;
-    s_Dplus = 0.0;
-    s_stats[0] = s_stats[1] = s_stats[2] = s_stats[3] = 0;
-    if (K0 + m > SMG_MAX_ENTRIES) s_err |= ST_TOO_MANY_ENTRIES;
-    if (K0 > A.K0cap) s_err |= ST_LL_COLS;
+    S.K = K0;
+    S.next = K0;
+    S.err = 0;
+    S.Dplus = 0.0;
+    S.stats[0] = S.stats[1] = S.stats[2] = S.stats[3] = 0;
+    if (K0 + m > SMG_MAX_ENTRIES) S.err |= ST_TOO_MANY_ENTRIES;
+    if (K0 > A.K0cap) S.err |= ST_LL_COLS;
   }
   __syncthreads();
   bool abort_pass = false;
-  if (s_err) {
-    if (tid == 0) atomicOr(A.status, s_err);
+  int W = SMG_SCAN_WARPS;  // rows evaluated per round
+  // phase cycle counters of thread 0 (compile with -DSMG_SCAN_PROFILE): [0] chunk prologue, [1] screen,
+  // [2] batch pick, [3] evaluation, [4] event detection, [5] event application, [6] whole loop
+#ifdef SMG_SCAN_PROFILE
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tmark = clock64();
+  const long long tstart = tmark;
+#define SCAN_TICK(k)                 \
+  do {                               \
+    const long long _t = clock64();  \
+    pc[k] += _t - tmark;             \
+    tmark = _t;                      \
+  } while (0)
+#else
+#define SCAN_TICK(k)
+#endif
+  if (S.err) {
+    if (tid == 0) atomicOr(A.status, S.err);
     abort_pass = true;
   }
 
   // this thread's observation of the NEXT chunk (loaded one chunk ahead)
   int nx_own = 0;
   double nx_mg = 0.0;
-  if (tid < n) {
-    nx_own = A.c[tid];
-    nx_mg = A.mrg[tid];
-  }
+  if (tid < n) scan_prefetch_row(A.c + tid, A.mrg + tid, nx_own, nx_mg);
 
   for (int i0 = 0; i0 < n && !abort_pass; i0 += SCAN_CHUNK) {
     const int nrows = min(SCAN_CHUNK, n - i0);
     const int my_own = nx_own;
     const double my_mg = nx_mg;
-    if (i0 + SCAN_CHUNK + tid < n) {
-      nx_own = A.c[i0 + SCAN_CHUNK + tid];
-      nx_mg = A.mrg[i0 + SCAN_CHUNK + tid];
-    }
+    if (i0 + SCAN_CHUNK + tid < n) scan_prefetch_row(A.c + i0 + SCAN_CHUNK + tid, A.mrg + i0 + SCAN_CHUNK + tid, nx_own, nx_mg);
+    SCAN_TICK(0);
     int start = 0;          // rows [0, start) of the chunk are final
-    bool screened = false;  // s_und valid for the current state
-    while (start < nrows) {
+    bool screened = false;  // the undecided set below is valid for the current state
+    int total_und = 0, consumed = 0;  // undecided rows from `start` on / already evaluated without an event
+    for (;;) {
       // ================= screen: one thread per row =================
       if (!screened) {
         bool und = false;
         if (tid >= start && tid < nrows) {
-          const double Dp = s_Dplus;
+          const double Dp = S.Dplus;
           // own slot is always a start-of-pass cluster for a row the scan has not reached yet
-          und = !(my_mg - s_dminus[my_own] - Dp > SCAN_DOMINANCE + SCAN_SLACK);
-          if (!und && s_next > K0) {
+          und = !(my_mg - S.dminus[my_own] - Dp > SCAN_DOMINANCE + SCAN_SLACK);
+          if (!und && S.next > K0) {
             const int i = i0 + tid;
-            const double thr = s_logcm1[my_own] + A.LL[(size_t)i * A.ldl + my_own] - (SCAN_DOMINANCE + SCAN_SLACK);
-            const int K = s_K;
+            const double thr = S.logcm1[my_own] + A.LL[(size_t)i * A.ldl + my_own] - (SCAN_DOMINANCE + SCAN_SLACK);
+            const int K = S.K;
             for (int e = 0; e < K; e++) {
-              const int slot = s_l2s[e];
+              const int slot = S.l2s[e];
               if (slot < K0) continue;
-              if (slot >= A.ldl || !(s_logc[slot] + __ldcg(&A.LL[(size_t)i * A.ldl + slot]) < thr)) {
+              if (slot >= A.ldl || !(S.logc[slot] + __ldcg(&A.LL[(size_t)i * A.ldl + slot]) < thr)) {
                 und = true;
                 break;
               }
             }
           }
         }
+        if (und) S.own[tid] = my_own;
         const unsigned b = __ballot_sync(SMG_FULL, und);
-        if (lane == 0) s_und[warp] = b;
+        if (lane == 0) S.und[warp] = b;
         screened = true;
-        if (__syncthreads_count(und) == 0) {  // every remaining row of the chunk is a certain non-event
-          if (tid == 0) s_stats[0]++;
+        consumed = 0;
+        total_und = __syncthreads_count(und);
+        if (total_und == 0) {  // every remaining row of the chunk is a certain non-event
+          if (tid == 0) S.stats[0]++;
           break;
         }
       }
-      // ================= batch: the next 32 undecided rows, one warp each =================
-      int myrow = -1, lastrow = -1;
-      {
-        int seen = 0;
-        for (int wd = start >> 5; wd < (nrows + 31) >> 5; wd++) {
-          unsigned b = s_und[wd];
-          if (wd == (start >> 5)) b &= ~0u << (start & 31);
-          const int cb = __popc(b);
-          if (myrow < 0 && seen + cb > warp) {
-            unsigned bb = b;
-            for (int q = seen; q < warp; q++) bb &= bb - 1;
-            myrow = wd * 32 + __ffs(bb) - 1;
-          }
-          if (seen + cb >= SMG_SCAN_WARPS) {  // the batch ends inside this word
-            unsigned bb = b;
-            for (int q = seen; q < SMG_SCAN_WARPS - 1; q++) bb &= bb - 1;
-            lastrow = wd * 32 + __ffs(bb) - 1;
-            seen = SMG_SCAN_WARPS;
-            break;
-          }
-          seen += cb;
+      SCAN_TICK(1);
+      if (consumed >= total_und) break;
+      // ================= batch: the next `nb` undecided rows, one warp each =================
+      // (only the warps that evaluate a row run the selection; the others go straight to the barrier)
+      const int nb = min(W, total_und - consumed);
+      int myrow = -1;
+      if (warp < nb) {
+        // lane l: undecided bits of rows [32l, 32l+32) of the chunk, how many undecided rows lie in that word
+        // and how many precede it
+        const unsigned wbits = S.und[lane];
+        const int wpc = __popc(wbits);
+        int incl = wpc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(SMG_FULL, incl, o);
+          if (lane >= o) incl += y;
         }
-        if (seen == 0) {  // nothing left to decide in this chunk
-          if (tid == 0) s_stats[0]++;
-          break;
-        }
-        if (seen < SMG_SCAN_WARPS) lastrow = nrows - 1;  // every remaining undecided row is in this batch
+        const int wpref = incl - wpc;
+        const int t = consumed + warp;
+        const unsigned hit = __ballot_sync(SMG_FULL, t >= wpref && t < wpref + wpc);
+        const int src = __ffs(hit) - 1;  // exactly one word holds the t-th undecided row
+        unsigned bits = __shfl_sync(SMG_FULL, wbits, src);
+        const int off = t - __shfl_sync(SMG_FULL, wpref, src);
+        for (int q = 0; q < off; q++) bits &= bits - 1;  // drop the `off` lowest set bits
+        myrow = src * 32 + __ffs(bits) - 1;
       }
-      const int K = s_K;
+      SCAN_TICK(2);
+      const int K = S.K;
       const int ne = K + m;
       int code = EVT_NONE;
       if (myrow >= 0 && ne > SMG_MAX_ENTRIES) code = -3;
       if (myrow >= 0 && ne <= SMG_MAX_ENTRIES) {
         const int i = i0 + myrow;
-        const double* rowp = A.LL + (size_t)i * A.ldl;
-        const double* auxp = A.LLaux + (size_t)i * m;
-        const int old_slot = A.c[i];
-        const bool singleton = (s_cnt[old_slot] == 1);
-        const uint8_t* xrow = A.X + (size_t)i * pp;
-        double lg[SMG_EPL];
-        double ll_own = 0.0;
-        // ---- existing clusters (neal8.cpp:40-56)
-#pragma unroll
-        for (int q = 0; q < SMG_EPL; q++) {
-          lg[q] = -CUDART_INF;
-          if (q * 32 >= K) continue;
-          const int e = q * 32 + lane;
-          int slot = (e < K) ? s_l2s[e] : -1;
-          double ll = 0.0;
-          if (slot >= 0 && slot < A.ldl) ll = __ldcg(&rowp[slot]);
-          // born columns beyond the LL matrix width: evaluate on the fly, one at a time, whole warp
-          unsigned dyn = __ballot_sync(SMG_FULL, slot >= A.ldl);
-          while (dyn) {
-            int src = __ffs(dyn) - 1;
-            dyn &= dyn - 1;
-            int ds = __shfl_sync(SMG_FULL, slot, src);
-            double dot = warp_mismatch_dot(xrow, A.cen + (size_t)ds * pp, A.isg + (size_t)ds * pp, pp, lane);
-            if (lane == src) ll = -dot - A.sden[ds];
-          }
-          if (slot >= 0) {
-            const bool own = (slot == old_slot);
-            const int cx = s_cnt[slot] - (own ? 1 : 0);
-            if (own) ll_own = ll;
-            lg[q] = (cx > 0) ? ((own ? s_logcm1[slot] : s_logc[slot]) + ll) : -CUDART_INF;
-          }
-        }
-        if (singleton) {  // own parameters become aux slot 0 (neal8.cpp:72-75)
-          unsigned who = __ballot_sync(SMG_FULL, ll_own != 0.0);
-          // ll_own is set by exactly one lane; LL is strictly negative so != 0 identifies it
-          int src = who ? (__ffs(who) - 1) : 0;
-          ll_own = shfl_d(ll_own, src);
-        }
-        // ---- auxiliary components (neal8.cpp:78-92)
-#pragma unroll
-        for (int q = 0; q < SMG_EPL; q++) {
-          const int e = q * 32 + lane;
-          if (e >= K && e < ne) {
-            const int a = e - K;
-            double ll = (singleton && a == 0) ? ll_own : auxp[a];
-            lg[q] = A.log_gamma_m + ll;
-          }
-        }
-        // ---- max, exp, sum  (neal8.cpp:95-96)
-        uint64_t mykey = 0;
-        int myarg = 0x7fffffff;
-#pragma unroll
-        for (int q = 0; q < SMG_EPL; q++) {
-          if (q * 32 >= ne) continue;
-          const int e = q * 32 + lane;
-          if (e < ne) {
-            uint64_t k = sort_key(lg[q]);
-            if (k > mykey) {
-              mykey = k;
-              myarg = e;
-            }
-          }
-        }
-        const uint64_t maxkey = warp_max_key(mykey);
-        const double M = key_to_double(maxkey);
-        // smallest index attaining the max
-        const int argmax = (int)__reduce_min_sync(SMG_FULL, (unsigned)((mykey == maxkey) ? myarg : 0x7fffffff));
-        double pe[SMG_EPL];
-        double lsum = 0.0;
-        bool need_exp = false;
-#pragma unroll
-        for (int q = 0; q < SMG_EPL; q++) {
-          pe[q] = 0.0;
-          if (q * 32 >= ne) continue;
-          const int e = q * 32 + lane;
-          if (e < ne) {
-            double d = lg[q] - M;
-            if (d == 0.0)
-              pe[q] = 1.0;
-            else if (d >= -SCAN_DOMINANCE)
-              need_exp = true;
-          }
-        }
-        if (__any_sync(SMG_FULL, need_exp)) {
-#pragma unroll
-          for (int q = 0; q < SMG_EPL; q++) {
-            if (q * 32 >= ne) continue;
-            const int e = q * 32 + lane;
-            if (e < ne) {
-              double d = lg[q] - M;
-              if (d != 0.0 && d >= -SCAN_DOMINANCE) pe[q] = exp(d);
-            }
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < SMG_EPL; q++) lsum += pe[q];
-        const double S = warp_sum(lsum);
-        const double u = get_u(A.u_alloc, (size_t)i * A.u_stride, A.key, U_ALLOC, (uint32_t)i, 0u);
-        const double T = u * S;  // compare against the cumulative sums of the unnormalised weights
-        int new_e;
-        if (!(M > -CUDART_INF) || !(S == S)) {
-          new_e = -2;  // all -Inf or NaN: Rcpp::sample would stop()
-        } else if (T <= 1.0) {
-          new_e = argmax;  // first entry of the descending order already covers u
-        } else {
-          // Rcpp::sample semantics: walk the probabilities in DESCENDING order and return the
-          // first entry whose cumulative sum reaches u.  before(y,x): y precedes x in that order.
-          double G[SMG_EPL];
-#pragma unroll
-          for (int q = 0; q < SMG_EPL; q++) G[q] = 0.0;
-#pragma unroll
-          for (int qy = 0; qy < SMG_EPL; qy++) {
-            if (qy * 32 >= ne) continue;
-            unsigned sig = __ballot_sync(SMG_FULL, pe[qy] > 0.0);
-            while (sig) {
-              int src = __ffs(sig) - 1;
-              sig &= sig - 1;
-              double py = shfl_d(pe[qy], src);
-              int ey = qy * 32 + src;
-#pragma unroll
-              for (int q = 0; q < SMG_EPL; q++) {
-                int ex = q * 32 + lane;
-                if (py > pe[q] || (py == pe[q] && ey < ex)) G[q] += py;
-              }
-            }
-          }
-          // candidate = entry with u*S <= G + p, largest p first (smallest index among ties)
-          uint64_t bestk = 0;
-          int beste = 0x7fffffff;
-#pragma unroll
-          for (int q = 0; q < SMG_EPL; q++) {
-            int ex = q * 32 + lane;
-            if (ex < ne && pe[q] > 0.0 && T <= G[q] + pe[q]) {
-              uint64_t k = sort_key(pe[q]);
-              if (k > bestk || (k == bestk && ex < beste)) {
-                bestk = k;
-                beste = ex;
-              }
-            }
-          }
-          uint64_t wk = warp_max_key(bestk);
-          if (wk == 0) {
-            // fall-through of the reference loop: last entry of the descending order
-            // (smallest probability, largest index among ties)
-            uint64_t mink = ~0ull;
-            int mine = -1;
-#pragma unroll
-            for (int q = 0; q < SMG_EPL; q++) {
-              int ex = q * 32 + lane;
-              if (ex < ne) {
-                uint64_t k = sort_key(pe[q]);
-                if (k < mink || (k == mink && ex > mine)) {
-                  mink = k;
-                  mine = ex;
-                }
-              }
-            }
-            uint64_t wmin = ~warp_max_key(~mink);
-            new_e = (int)__reduce_max_sync(SMG_FULL, (unsigned)((mink == wmin) ? mine : 0));
-          } else {
-            new_e = (int)__reduce_min_sync(SMG_FULL, (unsigned)((bestk == wk) ? beste : 0x7fffffff));
-          }
-        }
-        // ---- does the draw change the state?
-        if (new_e == -2) {
-          code = -2;
-        } else if (new_e < K) {
-          int ns = s_l2s[new_e];
-          code = (ns != old_slot) ? new_e : EVT_NONE;
-        } else {
-          code = (singleton && new_e == K) ? EVT_NONE : new_e;  // singleton re-drawing its own phi: no-op
-        }
+        const int old_slot = S.own[myrow];
+        code = (ne <= 64) ? scan_eval_row<2>(A, S, i, old_slot, K, lane) : scan_eval_row_wide(A, S, i, old_slot, K, lane);
       }
       if (lane == 0) {
-        s_evt[warp] = code;
-        s_row[warp] = myrow;
+        S.evt[warp] = code;
+        S.row[warp] = myrow;
       }
+      SCAN_TICK(3);
       __syncthreads();
       // ---- first event of the batch (warps hold ascending rows)
-      int ev = s_evt[lane];
-      unsigned evm = __ballot_sync(SMG_FULL, ev != EVT_NONE && s_row[lane] >= 0);
+      int ev = S.evt[lane];
+      unsigned evm = __ballot_sync(SMG_FULL, ev != EVT_NONE && S.row[lane] >= 0);
       if (evm == 0) {
-        if (tid == 0) s_stats[0]++;
-        start = lastrow + 1;
-        __syncthreads();  // s_evt / s_row are rewritten by the next round
+        if (tid == 0) S.stats[0]++;
+        consumed += nb;
+        W = SMG_SCAN_WARPS;  // quiet: speculate over a full batch again
+        __syncthreads();     // S.evt / S.row are rewritten by the next round
+        SCAN_TICK(4);
         continue;
       }
+      SCAN_TICK(4);
       const int first = __ffs(evm) - 1;
+      // event-dense stretches (burn-in): evaluating 32 rows per round only burns issue slots
+      W = min(SMG_SCAN_WARPS, max(4, 2 * (first + 1)));
       const int new_e = __shfl_sync(SMG_FULL, ev, first);
-      const int erow = s_row[first];
+      const int erow = S.row[first];
       const int ie = i0 + erow;
       if (new_e < 0) {  // error: stop the pass
         if (tid == 0) atomicOr(A.status, new_e == -2 ? ST_BAD_PROB : ST_TOO_MANY_ENTRIES);
@@ -708,13 +785,13 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         break;
       }
       const int old_slot = A.c[ie];
-      const bool singleton = (s_cnt[old_slot] == 1);
-      const int Kc = s_K;
+      const bool singleton = (S.cnt[old_slot] == 1);
+      const int Kc = S.K;
       int new_slot;
       if (new_e < Kc) {
-        new_slot = s_l2s[new_e];
+        new_slot = S.l2s[new_e];
       } else {
-        new_slot = s_next;  // birth (case 3) or parameter replacement (case 4)
+        new_slot = S.next;  // birth (case 3) or parameter replacement (case 4)
         if (new_slot >= A.NS || new_slot >= SMG_MAX_SLOTS) {
           if (tid == 0) atomicOr(A.status, ST_SLOTS_EXHAUSTED);
           abort_pass = true;
@@ -743,81 +820,88 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       }
       __syncthreads();  // everyone has read the pre-event state
       if (tid == 0) {
-        s_stats[0]++;
-        s_stats[1]++;
+        S.stats[0]++;
+        S.stats[1]++;
         A.c[ie] = new_slot;
         // drift bookkeeping of a start-of-pass cluster whose count just changed
         auto drift = [&](int s) {
           if (s >= K0) return;
-          s_dminus[s] = (s_cnt[s] > 1) ? (s_lcm1_0[s] - s_logcm1[s]) : CUDART_INF;
-          const double dp = s_logc[s] - s_lc0[s];
-          if (dp > s_Dplus) s_Dplus = dp;  // monotone upper bound
+          S.dminus[s] = (S.cnt[s] > 1) ? (S.lcm1_0[s] - S.logcm1[s]) : CUDART_INF;
+          const double dp = S.logc[s] - S.lc0[s];
+          if (dp > S.Dplus) S.Dplus = dp;  // monotone upper bound
         };
         if (new_e < Kc) {
-          s_cnt[new_slot]++;
-          s_logcm1[new_slot] = s_logc[new_slot];
-          s_logc[new_slot] = log((double)s_cnt[new_slot]);
+          S.cnt[new_slot]++;
+          S.logcm1[new_slot] = S.logc[new_slot];
+          S.logc[new_slot] = log((double)S.cnt[new_slot]);
           drift(new_slot);
           if (!singleton) {  // case 1 (neal8.cpp:107-112)
-            int c0 = --s_cnt[old_slot];
-            s_logc[old_slot] = s_logcm1[old_slot];
-            s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+            int c0 = --S.cnt[old_slot];
+            S.logc[old_slot] = S.logcm1[old_slot];
+            S.logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
             drift(old_slot);
           } else {  // case 2 (neal8.cpp:115-137): last label moves into the hole
-            s_cnt[old_slot] = 0;
-            s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
-            int lab = s_s2l[old_slot];
-            int last_slot = s_l2s[Kc - 1];
-            s_l2s[lab] = last_slot;
-            s_s2l[last_slot] = lab;
-            s_s2l[old_slot] = -1;
-            if (lab == Kc - 1) s_s2l[last_slot] = -1;  // the dying cluster was the last label
-            s_K = Kc - 1;
-            s_stats[3]++;
+            S.cnt[old_slot] = 0;
+            S.logc[old_slot] = S.logcm1[old_slot] = -CUDART_INF;
+            int lab = S.s2l[old_slot];
+            int last_slot = S.l2s[Kc - 1];
+            S.l2s[lab] = last_slot;
+            S.s2l[last_slot] = lab;
+            S.s2l[old_slot] = -1;
+            if (lab == Kc - 1) S.s2l[last_slot] = -1;  // the dying cluster was the last label
+            S.K = Kc - 1;
+            S.stats[3]++;
           }
         } else {
-          s_next = new_slot + 1;
-          s_cnt[new_slot] = 1;
-          s_logc[new_slot] = 0.0;
-          s_logcm1[new_slot] = -CUDART_INF;
+          S.next = new_slot + 1;
+          S.cnt[new_slot] = 1;
+          S.logc[new_slot] = 0.0;
+          S.logcm1[new_slot] = -CUDART_INF;
           if (!singleton) {  // case 3 (neal8.cpp:140-150)
-            int c0 = --s_cnt[old_slot];
-            s_logc[old_slot] = s_logcm1[old_slot];
-            s_logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+            int c0 = --S.cnt[old_slot];
+            S.logc[old_slot] = S.logcm1[old_slot];
+            S.logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
             drift(old_slot);
-            s_l2s[Kc] = new_slot;
-            s_s2l[new_slot] = Kc;
-            s_K = Kc + 1;
-            s_stats[2]++;
+            S.l2s[Kc] = new_slot;
+            S.s2l[new_slot] = Kc;
+            S.K = Kc + 1;
+            S.stats[2]++;
           } else {  // case 4 (neal8.cpp:153-159): same label, new parameters
-            int lab = s_s2l[old_slot];
-            s_cnt[old_slot] = 0;
-            s_logc[old_slot] = s_logcm1[old_slot] = -CUDART_INF;
-            s_s2l[old_slot] = -1;
-            s_l2s[lab] = new_slot;
-            s_s2l[new_slot] = lab;
+            int lab = S.s2l[old_slot];
+            S.cnt[old_slot] = 0;
+            S.logc[old_slot] = S.logcm1[old_slot] = -CUDART_INF;
+            S.s2l[old_slot] = -1;
+            S.l2s[lab] = new_slot;
+            S.s2l[new_slot] = lab;
           }
         }
       }
       start = erow + 1;
       screened = false;  // the state changed: the remaining rows are screened again
       __syncthreads();
+      SCAN_TICK(5);
     }
     __syncthreads();
   }
+#ifdef SMG_SCAN_PROFILE
+  if (tid == 0 && A.prof) {
+    pc[6] = clock64() - tstart;
+    for (int q = 0; q < 8; q++) A.prof[q] += (unsigned long long)pc[q];
+  }
+#endif
   // release the helpers
   if (tid == 0) A.job[0] = -1;
   cluster_sync_all();
   // publish: K, counts by slot, slot->label map
   for (int s = tid; s < A.NS && s < SMG_MAX_SLOTS; s += blockDim.x) {
-    A.counts[s] = s_cnt[s];
-    A.slot2label[s] = s_s2l[s];
+    A.counts[s] = S.cnt[s];
+    A.slot2label[s] = S.s2l[s];
   }
   if (tid == 0) {
-    *A.Kptr = s_K;
-    if (s_K > A.K0cap) atomicOr(A.status, ST_LL_COLS);
+    *A.Kptr = S.K;
+    if (S.K > A.K0cap) atomicOr(A.status, ST_LL_COLS);
     if (A.stats)
-      for (int q = 0; q < 4; q++) A.stats[q] += s_stats[q];
+      for (int q = 0; q < 4; q++) A.stats[q] += S.stats[q];
   }
 }
 
