@@ -39,6 +39,7 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
+  SMG_CUDA(cudaFuncSetAttribute(hamming_ll_block_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LLT_SMEM_BYTES));
   SMG_CUDA(cudaFuncSetAttribute(cluster_histogram_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
   if (dalloc(&ch->attr, pp) || dalloc(&ch->v, pp) || dalloc(&ch->w, pp)) return SMG_ERR_CUDA;
@@ -101,8 +102,13 @@ static void chain_free(smg_chain* ch) {
 // ------------------------------------------------------------------------------------------
 static int launch_ll_block(smg_chain* ch) {
   dim3 grid(cdiv(ch->n, LLB_ROWS), cdiv(ch->Kcap, LLB_SLOTS));
-  hamming_ll_block_kernel<<<grid, 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], ch->isg[ch->cur],
-                                                    ch->sden[ch->cur], ch->K, ch->LL, ch->ldl);
+  if (ch->mmax <= 7)  // every code fits 3 bits: subset-sum table form
+    hamming_ll_block_t16_kernel<<<grid, 256, LLT_SMEM_BYTES, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur],
+                                                                      ch->isg[ch->cur], ch->sden[ch->cur], ch->K, ch->LL,
+                                                                      ch->ldl);
+  else
+    hamming_ll_block_kernel<<<grid, 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], ch->isg[ch->cur],
+                                                      ch->sden[ch->cur], ch->K, ch->LL, ch->ldl);
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;

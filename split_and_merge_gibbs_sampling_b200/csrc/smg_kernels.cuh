@@ -48,14 +48,6 @@ enum StatusBits : int {
 #define LLB_JT 64
 #define LLB_XS (LLB_JT / 4 + 1)  // padded row stride in words
 
-// acc += w when (mm & mask) != 0, as ONE predicated DADD (LOP3 with predicate output + @p DADD) instead of the
-// add + two 32-bit selects the compiler emits for the C form: the kernel is bound by the integer ALU pipe.
-__device__ __forceinline__ void pred_add(double& acc, uint32_t mm, uint32_t mask, double w) {
-  asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t@p add.f64 %0, %0, %3;\n\t}"
-      : "+d"(acc)
-      : "r"(mm), "r"(mask), "d"(w));
-}
-
 __global__ void __launch_bounds__(256) hamming_ll_block_kernel(const uint8_t* __restrict__ X, int n, int pp,
                                                                const uint8_t* __restrict__ cen,
                                                                const double* __restrict__ isg,
@@ -117,17 +109,155 @@ __global__ void __launch_bounds__(256) hamming_ll_block_kernel(const uint8_t* __
         const double2 w23 = *reinterpret_cast<const double2*>(&sw[(wg * 4 + c) * LLB_JT + jw * 4 + 2]);
 #pragma unroll
         for (int r = 0; r < 4; r++) {
-          const uint32_t mm = __vcmpne4(xw[r], cw[c]);  // 0xff per mismatching byte
-          pred_add(acc[r][c], mm, 0x000000ffu, w01.x);
-          pred_add(acc[r][c], mm, 0x0000ff00u, w01.y);
-          pred_add(acc[r][c], mm, 0x00ff0000u, w23.x);
-          pred_add(acc[r][c], mm, 0xff000000u, w23.y);
+          uint32_t mm = __vcmpne4(xw[r], cw[c]);  // 0xff per mismatching byte
+          if (mm & 0x000000ffu) acc[r][c] += w01.x;
+          if (mm & 0x0000ff00u) acc[r][c] += w01.y;
+          if (mm & 0x00ff0000u) acc[r][c] += w23.x;
+          if (mm & 0xff000000u) acc[r][c] += w23.y;
         }
       }
     }
     __syncthreads();
   }
   // epilogue: each thread writes 4 consecutive doubles (one 32-byte sector) per row
+  double sd[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) sd[c] = (slot0 + wg * 4 + c < K) ? sden[slot0 + wg * 4 + c] : 0.0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    int row = row0 + lane + 32 * r;
+    if (row >= n) continue;
+    double* o = LL + (size_t)row * ldl + slot0 + wg * 4;
+    if (slot0 + wg * 4 + 3 < K && (ldl & 3) == 0) {
+      double4 v = make_double4(-acc[r][0] - sd[0], -acc[r][1] - sd[1], -acc[r][2] - sd[2], -acc[r][3] - sd[3]);
+      *reinterpret_cast<double4*>(o) = v;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        if (slot0 + wg * 4 + c < K) o[c] = -acc[r][c] - sd[c];
+    }
+  }
+}
+
+// -----------------------------------------------------------------------------
+// K1, table form (attributes with at most 7 levels, i.e. every code fits 3 bits).
+// Same tile as above.  Four attributes (one 32-bit word of codes) are handled by ONE shared-memory look-up:
+// per (slot, word) the CTA keeps the 16 subset sums of the word's four 1/sigma values, and the 4-bit mismatch
+// pattern of (x word, centre word) indexes them.  Pattern -> address is three integer ops and a DP4A:
+//     t = x ^ c                      (per byte 0..7, zero iff the codes match)
+//     t = (t + 0x07070707) & 0x08080808     (per byte 8 iff mismatch)
+//     addr = dp4a(t, {1,2,4,8}, base)       (= base + 8 * pattern: byte offset of the fp64 subset sum)
+// so a (row, slot, word) costs 6 instructions and one DADD instead of 4 x (LOP3 + DADD + 2 FSEL): the C form
+// is bound by the integer ALU pipe (86% busy, fp64 pipe 22%: profiles/r01_ncu_summary.md), this one by the
+// shared-memory pipe.  16 look-up entries of one (slot, word) fill one 128-byte line: conflict-free.
+// -----------------------------------------------------------------------------
+// byte b of entry w is 8 when bit b of w is set: XOR-swizzle of the look-up lines (see the kernel)
+__constant__ uint32_t c_llt_swz[16] = {0x00000000u, 0x00000008u, 0x00000800u, 0x00000808u, 0x00080000u, 0x00080008u,
+                                       0x00080800u, 0x00080808u, 0x08000000u, 0x08000008u, 0x08000800u, 0x08000808u,
+                                       0x08080000u, 0x08080008u, 0x08080800u, 0x08080808u};
+#define LLT_TB_BYTES (LLB_SLOTS * (LLB_JT / 4) * 16 * 8)  // 64 KB of subset sums per attribute tile
+#define LLT_SMEM_BYTES (LLT_TB_BYTES + LLB_ROWS * LLB_XS * 4 + LLB_SLOTS * (LLB_JT / 4) * 4 + LLB_SLOTS * LLB_JT * 8)
+
+__global__ void __launch_bounds__(256, 2) hamming_ll_block_t16_kernel(const uint8_t* __restrict__ X, int n, int pp,
+                                                                      const uint8_t* __restrict__ cen,
+                                                                      const double* __restrict__ isg,
+                                                                      const double* __restrict__ sden,
+                                                                      const int* __restrict__ Kptr,
+                                                                      double* __restrict__ LL, int ldl) {
+  const int K = *Kptr;
+  const int slot0 = blockIdx.y * LLB_SLOTS;
+  if (slot0 >= K) return;
+  const int row0 = blockIdx.x * LLB_ROWS;
+  extern __shared__ __align__(128) unsigned char smem[];
+  double* tb = reinterpret_cast<double*>(smem);                                   // [32 slots][16 words][16]
+  uint32_t* sx = reinterpret_cast<uint32_t*>(smem + LLT_TB_BYTES);                // [128 rows][17]
+  uint32_t* sc = sx + LLB_ROWS * LLB_XS;                                          // [32 slots][16 words]
+  double* sw = reinterpret_cast<double*>(sc + LLB_SLOTS * (LLB_JT / 4));          // [32 slots][64]
+  const unsigned tb_base = (unsigned)__cvta_generic_to_shared(tb);
+  const int tid = threadIdx.x, lane = tid & 31, wg = tid >> 5;  // wg: slot group (4 slots)
+  double acc[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[r][c] = 0.0;
+
+  for (int j0 = 0; j0 < pp; j0 += LLB_JT) {
+    const int jt = min(LLB_JT, pp - j0);  // multiple of 16
+    for (int ch = tid; ch < LLB_ROWS * (LLB_JT / 16); ch += 256) {
+      int r = ch / (LLB_JT / 16), q = ch % (LLB_JT / 16);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (row0 + r < n && q * 16 < jt) v = *reinterpret_cast<const uint4*>(X + (size_t)(row0 + r) * pp + j0 + q * 16);
+      uint32_t* d = &sx[r * LLB_XS + q * 4];
+      d[0] = v.x;
+      d[1] = v.y;
+      d[2] = v.z;
+      d[3] = v.w;
+    }
+    for (int ch = tid; ch < LLB_SLOTS * (LLB_JT / 16); ch += 256) {
+      int s = ch / (LLB_JT / 16), q = ch % (LLB_JT / 16);
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (slot0 + s < K && q * 16 < jt) v = *reinterpret_cast<const uint4*>(cen + (size_t)(slot0 + s) * pp + j0 + q * 16);
+      *reinterpret_cast<uint4*>(&sc[s * (LLB_JT / 4) + q * 4]) = v;
+    }
+    for (int ch = tid; ch < LLB_SLOTS * (LLB_JT / 2); ch += 256) {
+      int s = ch / (LLB_JT / 2), q = ch % (LLB_JT / 2);
+      double2 v = make_double2(0.0, 0.0);
+      if (slot0 + s < K && q * 2 < jt) v = *reinterpret_cast<const double2*>(isg + (size_t)(slot0 + s) * pp + j0 + q * 2);
+      *reinterpret_cast<double2*>(&sw[s * LLB_JT + q * 2]) = v;
+    }
+    __syncthreads();
+    // subset sums: pair = (slot, word); bit b of the pattern <-> byte b of the word <-> attribute 4*word + b.
+    // Entry k of a pair lives at position k ^ word of its 128-byte line: the 32 lanes of a warp (32 consecutive
+    // pairs) then store to distinct banks, and the reader folds the XOR into its mask constant for free.
+    for (int pair = tid; pair < LLB_SLOTS * (LLB_JT / 4); pair += 256) {
+      const double2 w01 = *reinterpret_cast<const double2*>(&sw[pair * 4]);
+      const double2 w23 = *reinterpret_cast<const double2*>(&sw[pair * 4 + 2]);
+      const double s01 = w01.x + w01.y, s23 = w23.x + w23.y;
+      double* line = &tb[pair * 16];
+      const int sz = pair & 15;
+      line[0 ^ sz] = 0.0;
+      line[1 ^ sz] = w01.x;
+      line[2 ^ sz] = w01.y;
+      line[3 ^ sz] = s01;
+      line[4 ^ sz] = w23.x;
+      line[5 ^ sz] = w01.x + w23.x;
+      line[6 ^ sz] = w01.y + w23.x;
+      line[7 ^ sz] = s01 + w23.x;
+      line[8 ^ sz] = w23.y;
+      line[9 ^ sz] = w01.x + w23.y;
+      line[10 ^ sz] = w01.y + w23.y;
+      line[11 ^ sz] = s01 + w23.y;
+      line[12 ^ sz] = s23;
+      line[13 ^ sz] = w01.x + s23;
+      line[14 ^ sz] = w01.y + s23;
+      line[15 ^ sz] = s01 + s23;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jw = 0; jw < LLB_JT / 4; jw++) {
+      // byte b of the swizzle constant is 8 when bit b of the word index is set
+      const uint32_t swz = c_llt_swz[jw];  // from constant memory: stays a register operand of the LOP3 below
+      uint32_t xw[4], cw[4];
+#pragma unroll
+      for (int r = 0; r < 4; r++) xw[r] = sx[(lane + 32 * r) * LLB_XS + jw];
+#pragma unroll
+      for (int c = 0; c < 4; c++) cw[c] = sc[(wg * 4 + c) * (LLB_JT / 4) + jw];
+#pragma unroll
+      for (int c = 0; c < 4; c++) {
+        const unsigned base = tb_base + (unsigned)((((wg * 4 + c) * (LLB_JT / 4)) + jw) * 128);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          uint32_t t = (xw[r] ^ cw[c]) + 0x07070707u;
+          asm("lop3.b32 %0, %1, %2, 0x08080808, 0x28;" : "=r"(t) : "r"(t), "r"(swz));  // (t ^ swz) & 0x08080808
+          const unsigned addr = __dp4a(t, 0x08040201u, base);
+          double v;
+          asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+          acc[r][c] += v;
+        }
+      }
+    }
+    __syncthreads();
+  }
   double sd[4];
 #pragma unroll
   for (int c = 0; c < 4; c++) sd[c] = (slot0 + wg * 4 + c < K) ? sden[slot0 + wg * 4 + c] : 0.0;
