@@ -216,6 +216,67 @@ class Chain:
                 "z_star": zs[:nS].copy(), "phi": phi, "terms": terms}
 
 
+class Psm:
+    """Posterior similarity matrix accumulated on the tensor cores (smg_psm_*): int32 co-clustering counts.
+    `external` may be a torch int32 CUDA tensor of shape (n, n) that the caller owns (e.g. to all-reduce it over
+    GPUs with NCCL afterwards); otherwise the library owns the matrix."""
+
+    def __init__(self, n, device=0, capacity_sweeps=64, external=None):
+        self.lib = lb.load()
+        self.n = int(n)
+        self._keep = external
+        ptr = None
+        if external is not None:
+            if tuple(external.shape) != (self.n, self.n) or external.element_size() != 4 or not external.is_contiguous():
+                raise ValueError("external must be a contiguous int32 (n, n) CUDA tensor")
+            ptr = C.c_void_p(external.data_ptr())
+        h = C.c_void_p()
+        lb.check(self.lib.smg_psm_create(self.n, int(device), int(capacity_sweeps), ptr, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smg_psm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def push_chain(self, chain):
+        lb.check(self.lib.smg_psm_push_chain(self.h, chain.h))
+
+    def push(self, c_i):
+        c = lb.as_i32(c_i)
+        if c.shape != (self.n,):
+            raise ValueError("c_i must have length n")
+        lb.check(self.lib.smg_psm_push_host(self.h, lb.iptr(c)))
+
+    def flush(self):
+        lb.check(self.lib.smg_psm_flush(self.h))
+
+    def read(self, row0=0, nrows=None):
+        nrows = self.n - row0 if nrows is None else int(nrows)
+        out = np.empty((nrows, self.n), dtype=np.int32)
+        lb.check(self.lib.smg_psm_read(self.h, int(row0), nrows, lb.iptr(out)))
+        return out
+
+    def info(self):
+        sw = C.c_longlong()
+        ms = C.c_double()
+        nl = C.c_ulonglong()
+        lb.check(self.lib.smg_psm_info(self.h, C.byref(sw), C.byref(ms), C.byref(nl)))
+        return {"sweeps": sw.value, "last_flush_ms": ms.value, "launches": nl.value}
+
+    def reference(self):
+        """CUDA-core evaluation of the currently buffered sweeps (n x n), for cross-checks."""
+        out = np.empty((self.n, self.n), dtype=np.int32)
+        lb.check(self.lib.smg_debug_psm_reference(self.h, lb.iptr(out)))
+        return out
+
+
 def hig_inv_u(omega, v, w, m):
     lib = lb.load()
     om, vv, ww, mm = (np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), np.shape(omega)))

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 
+#include "smg_psm.cuh"
 #include "smg_sm.cuh"
 
 namespace smg {
@@ -487,6 +488,28 @@ static int upload_u8(smg_chain* ch, const unsigned char* data) {
 }  // namespace smg
 
 using namespace smg;
+
+struct smg_psm {
+  int n = 0, device = 0, cap = 0, count = 0, kmax = 0;
+  long long total = 0;
+  int* psm = nullptr;
+  bool owns = false;
+  uint8_t* labels = nullptr;
+  cudaStream_t st = nullptr;
+  unsigned long long launches = 0;
+  double last_ms = 0.0;
+  cudaEvent_t ev[2] = {};
+};
+
+template <int KP, int NST>
+static int psm_launch(smg_psm* P) {
+  const size_t smem = (size_t)NST * (PSM_M + PSM_N) * KP;
+  SMG_CUDA(cudaFuncSetAttribute(psm_accumulate_kernel<KP, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(cdiv(P->n, PSM_N), cdiv(P->n, PSM_M));
+  psm_accumulate_kernel<KP, NST><<<grid, PSM_THREADS, smem, P->st>>>(P->labels, P->n, P->count, P->psm);
+  SMG_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // ==========================================================================================
 // extern "C"
@@ -978,6 +1001,152 @@ int smg_debug_split_merge(smg_chain* ch, const smg_sm_tape* tape, int* info, int
   rc = sync_status(ch);
   if (rc) return rc;
   return sm_readback(ch, info, S, z_launch, z_star, phi_out, terms);
+}
+
+
+// ------------------------------------------------------------------------------------------
+// posterior similarity matrix (smg_psm.cuh)
+// ------------------------------------------------------------------------------------------
+int smg_psm_create(int n, int device, int capacity_sweeps, void* external_psm_int32, smg_psm** out) {
+  if (!out) return fail(SMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (n < 1 || capacity_sweeps < 1) return fail(SMG_ERR_ARG, "n and capacity_sweeps must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(SMG_ERR_ARG, "bad device ordinal");
+  SMG_CUDA(cudaSetDevice(device));
+  smg_psm* P = new smg_psm();
+  P->n = n;
+  P->device = device;
+  P->cap = capacity_sweeps;
+  if (external_psm_int32) {
+    P->psm = (int*)external_psm_int32;
+  } else {
+    if (cudaMalloc(&P->psm, (size_t)n * n * sizeof(int)) != cudaSuccess) {
+      delete P;
+      return fail(SMG_ERR_CUDA, "cudaMalloc of the n x n int32 matrix failed");
+    }
+    P->owns = true;
+    cudaMemset(P->psm, 0, (size_t)n * n * sizeof(int));
+  }
+  if (cudaMalloc(&P->labels, (size_t)capacity_sweeps * n) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&P->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&P->ev[0]) != cudaSuccess || cudaEventCreate(&P->ev[1]) != cudaSuccess) {
+    smg_psm_destroy(P);
+    return fail(SMG_ERR_CUDA, "allocation of the label buffer failed");
+  }
+  *out = P;
+  return 0;
+}
+
+void smg_psm_destroy(smg_psm* P) {
+  if (!P) return;
+  cudaSetDevice(P->device);
+  if (P->st) cudaStreamSynchronize(P->st);
+  if (P->owns && P->psm) cudaFree(P->psm);
+  if (P->labels) cudaFree(P->labels);
+  for (int q = 0; q < 2; q++)
+    if (P->ev[q]) cudaEventDestroy(P->ev[q]);
+  if (P->st) cudaStreamDestroy(P->st);
+  delete P;
+}
+
+int smg_psm_flush(smg_psm* P) {
+  if (!P) return fail(SMG_ERR_ARG, "psm is NULL");
+  SMG_CUDA(cudaSetDevice(P->device));
+  if (P->count == 0) return 0;
+  cudaEventRecord(P->ev[0], P->st);
+  int rc;
+  if (P->kmax <= 64)
+    rc = psm_launch<64, 4>(P);
+  else if (P->kmax <= 128)
+    rc = psm_launch<128, 3>(P);
+  else
+    rc = psm_launch<256, 2>(P);
+  if (rc) return rc;
+  cudaEventRecord(P->ev[1], P->st);
+  SMG_CUDA(cudaStreamSynchronize(P->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, P->ev[0], P->ev[1]);
+  P->last_ms = ms;
+  P->launches++;
+  P->total += P->count;
+  P->count = 0;
+  P->kmax = 0;
+  return 0;
+}
+
+int smg_psm_push_host(smg_psm* P, const int* c_i) {
+  if (!P || !c_i) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(P->device));
+  if (P->count == P->cap) {
+    int rc = smg_psm_flush(P);
+    if (rc) return rc;
+  }
+  std::vector<uint8_t> h(P->n);
+  int mx = 0;
+  for (int i = 0; i < P->n; i++) {
+    if (c_i[i] < 0 || c_i[i] > 255) return fail(SMG_ERR_ARG, "labels must lie in 0..255");
+    h[i] = (uint8_t)c_i[i];
+    mx = std::max(mx, c_i[i]);
+  }
+  SMG_CUDA(cudaMemcpyAsync(P->labels + (size_t)P->count * P->n, h.data(), P->n, cudaMemcpyHostToDevice, P->st));
+  SMG_CUDA(cudaStreamSynchronize(P->st));
+  P->kmax = std::max(P->kmax, mx + 1);
+  P->count++;
+  return 0;
+}
+
+int smg_psm_push_chain(smg_psm* P, smg_chain* ch) {
+  if (!P || !ch) return fail(SMG_ERR_ARG, "NULL argument");
+  if (ch->n != P->n || ch->device != P->device) return fail(SMG_ERR_ARG, "chain and matrix differ in n or device");
+  SMG_CUDA(cudaSetDevice(P->device));
+  if (P->count == P->cap) {
+    int rc = smg_psm_flush(P);
+    if (rc) return rc;
+  }
+  // the chain's allocation is final once its stream is idle (smg_step ends with a synchronisation)
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  psm_pack_labels_kernel<<<cdiv(P->n, 256), 256, 0, P->st>>>(ch->c, P->n, P->labels + (size_t)P->count * P->n);
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaStreamSynchronize(P->st));
+  P->kmax = std::max(P->kmax, ch->h_K);
+  P->count++;
+  return 0;
+}
+
+int smg_psm_read(smg_psm* P, int row0, int nrows, int* out) {
+  if (!P || !out) return fail(SMG_ERR_ARG, "NULL argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > P->n) return fail(SMG_ERR_ARG, "row range out of bounds");
+  int rc = smg_psm_flush(P);
+  if (rc) return rc;
+  SMG_CUDA(cudaMemcpy(out, P->psm + (size_t)row0 * P->n, (size_t)nrows * P->n * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int smg_psm_info(smg_psm* P, long long* sweeps, double* last_flush_ms, unsigned long long* launches) {
+  if (!P) return fail(SMG_ERR_ARG, "psm is NULL");
+  if (sweeps) *sweeps = P->total + P->count;
+  if (last_flush_ms) *last_flush_ms = P->last_ms;
+  if (launches) *launches = P->launches;
+  return 0;
+}
+
+// CUDA-core evaluation of the same buffered sweeps into `out_psm_host` (n x n, overwritten): device-side
+// cross-check of the tensor-core kernel; does not consume the buffer
+int smg_debug_psm_reference(smg_psm* P, int* out_psm_host) {
+  if (!P || !out_psm_host) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(P->device));
+  int* d = nullptr;
+  SMG_CUDA(cudaMalloc(&d, (size_t)P->n * P->n * sizeof(int)));
+  SMG_CUDA(cudaMemsetAsync(d, 0, (size_t)P->n * P->n * sizeof(int), P->st));
+  psm_reference_kernel<<<dim3(cdiv(P->n, 256), P->n), 256, 0, P->st>>>(P->labels, P->n, P->count, d);
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaStreamSynchronize(P->st));
+  SMG_CUDA(cudaMemcpy(out_psm_host, d, (size_t)P->n * P->n * sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return 0;
 }
 
 }  // extern "C"
