@@ -216,6 +216,14 @@ class Chain:
                 "z_star": zs[:nS].copy(), "phi": phi, "terms": terms}
 
 
+def step_many(chains, n_iters=1):
+    """n_iters iterations on every chain of the list, overlapped on the GPU (smg_step_many)."""
+    if not chains:
+        return
+    arr = (C.c_void_p * len(chains))(*[ch.h for ch in chains])
+    lb.check(lb.load().smg_step_many(arr, len(chains), int(n_iters)))
+
+
 class Psm:
     """Posterior similarity matrix accumulated on the tensor cores (smg_psm_*): int32 co-clustering counts.
     `external` may be a torch int32 CUDA tensor of shape (n, n) that the caller owns (e.g. to all-reduce it over

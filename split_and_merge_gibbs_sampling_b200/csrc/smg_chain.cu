@@ -553,8 +553,8 @@ int smg_create_u8(const smg_config* cfg, const unsigned char* data_rowmajor, con
 
 void smg_destroy(smg_chain* ch) { chain_free(ch); }
 
-int smg_step(smg_chain* ch, int n_iters) {
-  if (!ch) return fail(SMG_ERR_ARG, "chain is NULL");
+// launches n_iters iterations on the chain's stream without waiting for them
+static int step_launch(smg_chain* ch, int n_iters) {
   SMG_CUDA(cudaSetDevice(ch->device));
   cudaEventRecord(ch->ev_call[0], ch->st);
   for (int it = 0; it < n_iters; it++) {
@@ -562,6 +562,12 @@ int smg_step(smg_chain* ch, int n_iters) {
     if (rc) return rc;
   }
   cudaEventRecord(ch->ev_call[1], ch->st);
+  return 0;
+}
+
+// waits for the chain's stream, reads back status / K / log-likelihood / acceptance and the phase timings
+static int step_finish(smg_chain* ch, int n_iters) {
+  SMG_CUDA(cudaSetDevice(ch->device));
   int rc = sync_status(ch);
   {
     float ms = 0;
@@ -583,6 +589,47 @@ int smg_step(smg_chain* ch, int n_iters) {
   }
   if (ch->h_accepted) ch->h_sm_acc++;
   return rc;
+}
+
+int smg_step(smg_chain* ch, int n_iters) {
+  if (!ch) return fail(SMG_ERR_ARG, "chain is NULL");
+  int rc = step_launch(ch, n_iters);
+  if (rc) return rc;
+  return step_finish(ch, n_iters);
+}
+
+// n_iters iterations on each of `count` independent chains (possibly on different devices): the sweeps are
+// launched iteration by iteration round-robin over the chains' streams so that they overlap on the GPU, and the
+// host waits only once per chain at the end
+int smg_step_many(smg_chain** chains, int count, int n_iters) {
+  if (!chains || count < 0) return fail(SMG_ERR_ARG, "bad chain list");
+  for (int q = 0; q < count; q++)
+    if (!chains[q]) return fail(SMG_ERR_ARG, "chain is NULL");
+  for (int q = 0; q < count; q++) {
+    SMG_CUDA(cudaSetDevice(chains[q]->device));
+    cudaEventRecord(chains[q]->ev_call[0], chains[q]->st);
+  }
+  for (int it = 0; it < n_iters; it++)
+    for (int q = 0; q < count; q++) {
+      SMG_CUDA(cudaSetDevice(chains[q]->device));
+      int rc = sweep(chains[q], it == n_iters - 1);
+      if (rc) return rc;
+    }
+  for (int q = 0; q < count; q++) {
+    SMG_CUDA(cudaSetDevice(chains[q]->device));
+    cudaEventRecord(chains[q]->ev_call[1], chains[q]->st);
+  }
+  int first_err = 0;
+  std::string msg;
+  for (int q = 0; q < count; q++) {
+    int rc = step_finish(chains[q], n_iters);
+    if (rc && !first_err) {
+      first_err = rc;
+      msg = g_last_error;
+    }
+  }
+  if (first_err) g_last_error = msg;
+  return first_err;
 }
 
 int smg_snapshot(smg_chain* ch, int* K, int* c_i, double* centers, double* sigmas, int cap_clusters, double* loglik,
