@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <thread>
 
 #include "smg_psm.cuh"
 #include "smg_sm.cuh"
@@ -16,9 +17,10 @@ thread_local std::string g_last_error;
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+static thread_local cudaStream_t g_alloc_stream = nullptr;  // stream of the chain being allocated
 template <typename T>
 static int dalloc(T** ptr, size_t count) {
-  SMG_CUDA(cudaMalloc((void**)ptr, std::max<size_t>(count, 1) * sizeof(T)));
+  SMG_CUDA(dev_malloc(ptr, std::max<size_t>(count, 1) * sizeof(T), g_alloc_stream));
   return 0;
 }
 
@@ -37,7 +39,9 @@ static int status_to_error(int st) {
 static int chain_alloc(smg_chain* ch) {
   const int n = ch->n, pp = ch->pp, NST = ch->NST;
   SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(dev_pool_init(ch->device));
   SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
+  g_alloc_stream = ch->st;
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
   SMG_CUDA(cudaFuncSetAttribute(hamming_ll_block_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LLT_SMEM_BYTES));
@@ -48,10 +52,10 @@ static int chain_alloc(smg_chain* ch) {
     if (dalloc(&ch->cen[b], (size_t)NST * pp) || dalloc(&ch->sig[b], (size_t)NST * pp) ||
         dalloc(&ch->isg[b], (size_t)NST * pp) || dalloc(&ch->sden[b], NST))
       return SMG_ERR_CUDA;
-    SMG_CUDA(cudaMemset(ch->cen[b], 0, (size_t)NST * pp));
-    SMG_CUDA(cudaMemset(ch->sig[b], 0, (size_t)NST * pp * 8));
-    SMG_CUDA(cudaMemset(ch->isg[b], 0, (size_t)NST * pp * 8));
-    SMG_CUDA(cudaMemset(ch->sden[b], 0, (size_t)NST * 8));
+    SMG_CUDA(cudaMemsetAsync(ch->cen[b], 0, (size_t)NST * pp, ch->st));
+    SMG_CUDA(cudaMemsetAsync(ch->sig[b], 0, (size_t)NST * pp * 8, ch->st));
+    SMG_CUDA(cudaMemsetAsync(ch->isg[b], 0, (size_t)NST * pp * 8, ch->st));
+    SMG_CUDA(cudaMemsetAsync(ch->sden[b], 0, (size_t)NST * 8, ch->st));
   }
   if (dalloc(&ch->den, (size_t)NST * pp)) return SMG_ERR_CUDA;
   if (dalloc(&ch->c, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
@@ -69,13 +73,16 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->partial, ch->loglik_blocks) || dalloc(&ch->loglik_d, 1)) return SMG_ERR_CUDA;
   if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4) || dalloc(&ch->scan_prof, 8))
     return SMG_ERR_CUDA;
-  SMG_CUDA(cudaMemset(ch->scan_prof, 0, 64));
-  SMG_CUDA(cudaMemset(ch->status, 0, 4));
-  SMG_CUDA(cudaMemset(ch->accepted_d, 0, 4));
-  SMG_CUDA(cudaMemset(ch->stats_d, 0, 64));
+  SMG_CUDA(cudaMemsetAsync(ch->scan_prof, 0, 64, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->status, 0, 4, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, 4, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->stats_d, 0, 64, ch->st));
   if (dalloc(&ch->tape_d, (size_t)n * (ch->m_aux + 1))) return SMG_ERR_CUDA;
   if (dalloc(&ch->uc_d, (size_t)NST * ch->p) || dalloc(&ch->us_d, (size_t)NST * ch->p)) return SMG_ERR_CUDA;
-  return sm_alloc(ch);
+  int rc = sm_alloc(ch);
+  if (rc) return rc;
+  SMG_CUDA(cudaStreamSynchronize(ch->st));  // every buffer is now usable from any stream
+  return 0;
 }
 
 static void chain_free(smg_chain* ch) {
@@ -89,7 +96,8 @@ static void chain_free(smg_chain* ch) {
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
                   ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d};
   for (void* q : ptrs)
-    if (q) cudaFree(q);
+    if (q) cudaFreeAsync(q, ch->st);
+  if (ch->st) cudaStreamSynchronize(ch->st);
   for (int q = 0; q < 8; q++)
     if (ch->ev[q]) cudaEventDestroy(ch->ev[q]);
   for (int q = 0; q < 2; q++)
@@ -454,22 +462,66 @@ static int init_state(smg_chain* ch, const int* c_init, int compact_init) {
   return sync_status(ch);
 }
 
+// R's column-major fp64 matrix -> row-major padded u8 codes.  Small inputs are copied as they are and converted
+// (and validated) on the device; large ones are packed by host threads first, which moves 8x fewer bytes over
+// PCIe from pageable memory (205 MB -> 25.6 MB at the metric shape).
 static int upload_colmajor(smg_chain* ch, const double* data) {
-  double* tmp = nullptr;
-  int* bad = nullptr;
-  SMG_CUDA(cudaMalloc(&tmp, (size_t)ch->n * ch->p * 8));
-  SMG_CUDA(cudaMalloc(&bad, 4));
-  SMG_CUDA(cudaMemsetAsync(bad, 0, 4, ch->st));
-  SMG_CUDA(cudaMemcpyAsync(tmp, data, (size_t)ch->n * ch->p * 8, cudaMemcpyHostToDevice, ch->st));
-  long long total = (long long)ch->n * ch->pp;
-  ingest_colmajor_kernel<<<cdiv(total, 256), 256, 0, ch->st>>>(tmp, ch->n, ch->p, ch->pp, ch->attr, ch->X, bad);
-  ch->h_launches++;
-  int hbad = 0;
-  SMG_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ch->st));
-  SMG_CUDA(cudaStreamSynchronize(ch->st));
-  cudaFree(tmp);
-  cudaFree(bad);
+  const int n = ch->n, p = ch->p, pp = ch->pp;
+  if ((long long)n * p < (1ll << 20)) {
+    double* tmp = nullptr;
+    int* bad = nullptr;
+    SMG_CUDA(dev_malloc(&tmp, (size_t)n * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&bad, 4, ch->st));
+    SMG_CUDA(cudaMemsetAsync(bad, 0, 4, ch->st));
+    SMG_CUDA(cudaMemcpyAsync(tmp, data, (size_t)n * p * 8, cudaMemcpyHostToDevice, ch->st));
+    long long total = (long long)n * pp;
+    ingest_colmajor_kernel<<<cdiv(total, 256), 256, 0, ch->st>>>(tmp, n, p, pp, ch->attr, ch->X, bad);
+    ch->h_launches++;
+    int hbad = 0;
+    SMG_CUDA(cudaMemcpyAsync(&hbad, bad, 4, cudaMemcpyDeviceToHost, ch->st));
+    SMG_CUDA(cudaStreamSynchronize(ch->st));
+    cudaFreeAsync(tmp, ch->st);
+    cudaFreeAsync(bad, ch->st);
+    if (hbad) return fail(SMG_ERR_ARG, std::to_string(hbad) + " data entries are not integer codes in 1..attrisize[j]");
+    return 0;
+  }
+  std::vector<uint8_t> buf((size_t)n * pp);
+  const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::vector<long long> nbad(nthr, 0);
+  std::vector<std::thread> pool;
+  const int* attr = ch->h_attr.data();
+  for (int tix = 0; tix < nthr; tix++) {
+    pool.emplace_back([&, tix]() {
+      const int r0 = (int)((long long)n * tix / nthr), r1 = (int)((long long)n * (tix + 1) / nthr);
+      long long bad = 0;
+      for (int b0 = r0; b0 < r1; b0 += 64) {  // 64-row blocks: the destination block stays in cache
+        const int b1 = std::min(r1, b0 + 64);
+        for (int j = 0; j < p; j++) {
+          const double* col = data + (size_t)n * j;
+          const int mj = attr[j];
+          for (int i = b0; i < b1; i++) {
+            const double v = col[i];
+            const int iv = (int)v;
+            uint8_t o = 0;
+            if ((double)iv != v || iv < 1 || iv > mj || iv > 255)
+              bad++;
+            else
+              o = (uint8_t)iv;
+            buf[(size_t)i * pp + j] = o;
+          }
+        }
+        for (int i = b0; i < b1; i++)
+          for (int j = p; j < pp; j++) buf[(size_t)i * pp + j] = 0;
+      }
+      nbad[tix] = bad;
+    });
+  }
+  for (auto& t : pool) t.join();
+  long long hbad = 0;
+  for (long long b : nbad) hbad += b;
   if (hbad) return fail(SMG_ERR_ARG, std::to_string(hbad) + " data entries are not integer codes in 1..attrisize[j]");
+  SMG_CUDA(cudaMemcpyAsync(ch->X, buf.data(), buf.size(), cudaMemcpyHostToDevice, ch->st));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
   return 0;
 }
 
@@ -739,8 +791,10 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   cfg.seed = seed;
   cfg.device = device;
   smg_chain* ch = nullptr;
+  auto tc0 = std::chrono::steady_clock::now();
   int rc = smg_create(&cfg, data, c_i, &ch);
   if (rc) return rc;
+  const double create_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - tc0).count();
   out->iterations = iterations;
   out->n = n;
   out->p = p;
@@ -751,26 +805,91 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   out->final_ass = (int*)calloc(n, sizeof(int));
   out->accepted = (int*)calloc(std::max(iterations, 1), sizeof(int));
   std::vector<double> cen, sg;
-  std::vector<double> kc((size_t)ch->Kcap * p), ks((size_t)ch->Kcap * p);
+  // Snapshots (launcher.cpp:140-153) leave the device asynchronously: every kept iteration enqueues its copies
+  // into one of RING pinned slots behind the sweep on the chain's stream and the host only waits for a slot
+  // when it comes round again, so sweeps are launched back to back.
+  const int RING = 4;
+  const int pp = ch->pp, Kcap = ch->Kcap;
+  struct Slot {
+    int* hdr;  // K, status, accepted
+    double* ll;
+    int* c;
+    uint8_t* cen;
+    double* sig;
+    cudaEvent_t ev;
+    long long result_slot;
+  };
+  const size_t slot_bytes = 64 + (size_t)n * 4 + (((size_t)Kcap * pp + 63) & ~(size_t)63) + (size_t)Kcap * pp * 8;
+  uint8_t* pinned = nullptr;
+  if (cudaHostAlloc((void**)&pinned, slot_bytes * RING, cudaHostAllocDefault) != cudaSuccess) {
+    smg_destroy(ch);
+    smg_free_results(out);
+    return fail(SMG_ERR_CUDA, "cudaHostAlloc of the snapshot ring failed");
+  }
+  Slot ring[RING];
+  for (int q = 0; q < RING; q++) {
+    uint8_t* base = pinned + slot_bytes * q;
+    ring[q].hdr = (int*)base;
+    ring[q].ll = (double*)(base + 16);
+    ring[q].c = (int*)(base + 64);
+    ring[q].cen = base + 64 + (size_t)n * 4;
+    ring[q].sig = (double*)(ring[q].cen + (((size_t)Kcap * pp + 63) & ~(size_t)63));
+    ring[q].result_slot = -1;
+    cudaEventCreateWithFlags(&ring[q].ev, cudaEventDisableTiming);
+  }
+  auto consume = [&](Slot& S) -> int {
+    if (S.result_slot < 0) return 0;
+    if (cudaEventSynchronize(S.ev) != cudaSuccess) return fail(SMG_ERR_CUDA, "snapshot copy failed");
+    const long long slot = S.result_slot;
+    S.result_slot = -1;
+    if (S.hdr[1]) return status_to_error(S.hdr[1]);
+    const int K = S.hdr[0];
+    if (K > Kcap) return fail(SMG_ERR_CAPACITY, "number of clusters exceeds max_clusters");
+    out->total_cls[slot] = K;
+    out->accepted[slot] = S.hdr[2];
+    out->loglikelihood[slot] = *S.ll;
+    memcpy(out->c_i + (size_t)slot * n, S.c, (size_t)n * 4);
+    out->phi_offset[slot + 1] = out->phi_offset[slot] + K;
+    const size_t o0 = cen.size();
+    cen.resize(o0 + (size_t)K * p);
+    sg.resize(o0 + (size_t)K * p);
+    for (int k = 0; k < K; k++)
+      for (int j = 0; j < p; j++) {
+        cen[o0 + (size_t)k * p + j] = (double)S.cen[(size_t)k * pp + j];
+        sg[o0 + (size_t)k * p + j] = S.sig[(size_t)k * pp + j];
+      }
+    return 0;
+  };
   auto t0 = std::chrono::steady_clock::now();
   const long long total = (long long)(iterations + burnin) * thinning;
+  long long nkept = 0;
   for (long long iter = 0; iter < total && !rc; ++iter) {
-    rc = smg_step(ch, 1);
+    rc = sweep(ch, false);
     if (rc) break;
-    if (verbose != 0) fprintf(stderr, "[DEBUG] - Iteration %lld of %d\n", iter, iterations + burnin);
+    if (verbose == 1 || verbose == 2) fprintf(stderr, "[DEBUG] - Iteration %lld of %d\n", iter, iterations + burnin);
     if (iter >= (long long)thinning * burnin && iter % thinning == 0) {
-      const long long slot = iter / thinning - burnin;
-      int K = 0;
-      rc = smg_snapshot(ch, &K, out->c_i + (size_t)slot * n, kc.data(), ks.data(), ch->Kcap, &out->loglikelihood[slot],
-                        &out->accepted[slot]);
+      Slot& S = ring[nkept % RING];
+      rc = consume(S);  // results are appended in order: the slot's previous occupant is RING snapshots old
       if (rc) break;
-      out->total_cls[slot] = K;
-      out->phi_offset[slot + 1] = out->phi_offset[slot] + K;
-      cen.insert(cen.end(), kc.begin(), kc.begin() + (size_t)K * p);
-      sg.insert(sg.end(), ks.begin(), ks.begin() + (size_t)K * p);
+      const int cur = ch->cur;
+      cudaMemcpyAsync(&S.hdr[0], ch->K, 4, cudaMemcpyDeviceToHost, ch->st);
+      cudaMemcpyAsync(&S.hdr[1], ch->status, 4, cudaMemcpyDeviceToHost, ch->st);
+      cudaMemcpyAsync(&S.hdr[2], ch->accepted_d, 4, cudaMemcpyDeviceToHost, ch->st);
+      cudaMemcpyAsync(S.ll, ch->loglik_d, 8, cudaMemcpyDeviceToHost, ch->st);
+      cudaMemcpyAsync(S.c, ch->c, (size_t)n * 4, cudaMemcpyDeviceToHost, ch->st);
+      cudaMemcpyAsync(S.cen, ch->cen[cur], (size_t)Kcap * pp, cudaMemcpyDeviceToHost, ch->st);
+      cudaMemcpyAsync(S.sig, ch->sig[cur], (size_t)Kcap * pp * 8, cudaMemcpyDeviceToHost, ch->st);
+      if (cudaEventRecord(S.ev, ch->st) != cudaSuccess) {
+        rc = fail(SMG_ERR_CUDA, "cudaEventRecord failed");
+        break;
+      }
+      S.result_slot = iter / thinning - burnin;
+      nkept++;
     }
   }
-  if (!rc) rc = smg_snapshot(ch, nullptr, out->final_ass, nullptr, nullptr, 0, nullptr, nullptr);
+  // drain the ring in result order
+  for (long long q = std::max<long long>(0, nkept - RING); q < nkept && !rc; q++) rc = consume(ring[q % RING]);
+  if (!rc) rc = smg_snapshot(ch, nullptr, out->final_ass, nullptr, nullptr, 0, nullptr, nullptr);  // also checks the status
   auto t1 = std::chrono::steady_clock::now();
   out->seconds = std::chrono::duration<double>(t1 - t0).count();
   out->time = (long long)std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count();
@@ -780,8 +899,15 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
     std::copy(cen.begin(), cen.end(), out->centers);
     std::copy(sg.begin(), sg.end(), out->sigmas);
   }
+  cudaStreamSynchronize(ch->st);
+  for (int q = 0; q < RING; q++) cudaEventDestroy(ring[q].ev);
+  cudaFreeHost(pinned);
   std::string keep = g_last_error;
+  auto td0 = std::chrono::steady_clock::now();
   smg_destroy(ch);
+  if (verbose == 3)
+    fprintf(stderr, "[smgibbs] create %.4f s, loop %.4f s, destroy %.4f s\n", create_s, out->seconds,
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count());
   if (rc) {
     smg_free_results(out);
     g_last_error = keep;

@@ -28,6 +28,25 @@ inline int fail(int code, const std::string& msg) {
                                          ":" + std::to_string(__LINE__));                                    \
   } while (0)
 
+// Stream-ordered device memory from the device's default pool with an unbounded release threshold: chains
+// are created and destroyed per run_markov_chain call, and cudaMalloc / cudaFree of multi-GB buffers cost tens
+// of milliseconds each time; the pool hands the same memory back in microseconds.
+inline cudaError_t dev_pool_init(int device) {
+  static bool done[64] = {};
+  if (device < 0 || device >= 64 || done[device]) return cudaSuccess;
+  cudaMemPool_t pool;
+  cudaError_t e = cudaDeviceGetDefaultMemPool(&pool, device);
+  if (e != cudaSuccess) return e;
+  unsigned long long thr = ~0ull;
+  e = cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  done[device] = (e == cudaSuccess);
+  return e;
+}
+template <typename T>
+inline cudaError_t dev_malloc(T** ptr, size_t bytes, cudaStream_t st) {
+  return cudaMallocAsync((void**)ptr, bytes ? bytes : 1, st);
+}
+
 // Philox sub-stream ids inside one iteration
 enum SubPhase : uint32_t {
   SUB_SCAN = 0,

@@ -607,21 +607,21 @@ static int sm_alloc(smg_chain* ch) {
   SmWork* W = new SmWork();
   ch->sm = W;
   const int n = ch->n;
-  SMG_CUDA(cudaMalloc(&W->S, (size_t)n * 4));
-  SMG_CUDA(cudaMalloc(&W->zL, (size_t)n * 4));
-  SMG_CUDA(cudaMalloc(&W->zStar, (size_t)n * 4));
-  SMG_CUDA(cudaMalloc(&W->zState, (size_t)n * 4));
-  SMG_CUDA(cudaMalloc(&W->info, sizeof(SmInfo)));
-  SMG_CUDA(cudaMemset(W->info, 0, sizeof(SmInfo)));
-  SMG_CUDA(cudaMalloc(&W->plan, sizeof(SmPlan)));
-  SMG_CUDA(cudaMalloc(&W->H, (size_t)SH_N * ch->pp * ch->mmax * 4));
-  SMG_CUDA(cudaMalloc(&W->cnt, SH_N * 4 + 4));
-  SMG_CUDA(cudaMalloc(&W->rg_dl, (size_t)n * 8));
-  SMG_CUDA(cudaMalloc(&W->rg_lgt, (size_t)n * 8));
-  SMG_CUDA(cudaMalloc(&W->rowvals, (size_t)4 * (n + 2) * 8));
-  SMG_CUDA(cudaMalloc(&W->partial, (size_t)4 * SM_RB * 8));
-  SMG_CUDA(cudaMalloc(&W->terms, 24 * 8));
-  SMG_CUDA(cudaMemset(W->terms, 0, 24 * 8));
+  SMG_CUDA(dev_malloc(&W->S, (size_t)n * 4, ch->st));
+  SMG_CUDA(dev_malloc(&W->zL, (size_t)n * 4, ch->st));
+  SMG_CUDA(dev_malloc(&W->zStar, (size_t)n * 4, ch->st));
+  SMG_CUDA(dev_malloc(&W->zState, (size_t)n * 4, ch->st));
+  SMG_CUDA(dev_malloc(&W->info, sizeof(SmInfo), ch->st));
+  SMG_CUDA(cudaMemsetAsync(W->info, 0, sizeof(SmInfo), ch->st));
+  SMG_CUDA(dev_malloc(&W->plan, sizeof(SmPlan), ch->st));
+  SMG_CUDA(dev_malloc(&W->H, (size_t)SH_N * ch->pp * ch->mmax * 4, ch->st));
+  SMG_CUDA(dev_malloc(&W->cnt, SH_N * 4 + 4, ch->st));
+  SMG_CUDA(dev_malloc(&W->rg_dl, (size_t)n * 8, ch->st));
+  SMG_CUDA(dev_malloc(&W->rg_lgt, (size_t)n * 8, ch->st));
+  SMG_CUDA(dev_malloc(&W->rowvals, (size_t)4 * (n + 2) * 8, ch->st));
+  SMG_CUDA(dev_malloc(&W->partial, (size_t)4 * SM_RB * 8, ch->st));
+  SMG_CUDA(dev_malloc(&W->terms, 24 * 8, ch->st));
+  SMG_CUDA(cudaMemsetAsync(W->terms, 0, 24 * 8, ch->st));
   // the two side histograms are privatised in shared memory when they fit
   W->hist_smem = (size_t)2 * ch->pp * ch->mmax * sizeof(int);
   if (W->hist_smem <= 160 * 1024) {
@@ -640,7 +640,7 @@ static void sm_free(smg_chain* ch) {
                   W->rg_dl,   W->rg_lgt,  W->rowvals, W->partial, W->terms, W->u_pair,  W->u_prior_c, W->u_prior_s,
                   W->u_launch, W->u_rg,   W->u_rg_c, W->u_rg_s, W->u_mg_c,  W->u_mg_s,  W->u_accept};
   for (void* q : ptrs)
-    if (q) cudaFree(q);
+    if (q) cudaFreeAsync(q, ch->st);
   delete W;
   ch->sm = nullptr;
 }
@@ -649,16 +649,17 @@ static int sm_inject(smg_chain* ch, const smg_sm_tape* t) {
   SmWork* W = ch->sm;
   const int n = ch->n, p = ch->p, T1 = ch->t + 1, R1 = ch->r + 1;
   if (!W->inj_alloc) {
-    SMG_CUDA(cudaMalloc(&W->u_pair, 2 * 8));
-    SMG_CUDA(cudaMalloc(&W->u_prior_c, (size_t)3 * p * 8));
-    SMG_CUDA(cudaMalloc(&W->u_prior_s, (size_t)3 * p * 8));
-    SMG_CUDA(cudaMalloc(&W->u_launch, (size_t)n * 8));
-    SMG_CUDA(cudaMalloc(&W->u_rg, (size_t)T1 * n * 8));
-    SMG_CUDA(cudaMalloc(&W->u_rg_c, (size_t)T1 * 2 * p * 8));
-    SMG_CUDA(cudaMalloc(&W->u_rg_s, (size_t)T1 * 2 * p * 8));
-    SMG_CUDA(cudaMalloc(&W->u_mg_c, (size_t)R1 * p * 8));
-    SMG_CUDA(cudaMalloc(&W->u_mg_s, (size_t)R1 * p * 8));
-    SMG_CUDA(cudaMalloc(&W->u_accept, 8));
+    SMG_CUDA(dev_malloc(&W->u_pair, 2 * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_prior_c, (size_t)3 * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_prior_s, (size_t)3 * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_launch, (size_t)n * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_rg, (size_t)T1 * n * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_rg_c, (size_t)T1 * 2 * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_rg_s, (size_t)T1 * 2 * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_mg_c, (size_t)R1 * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_mg_s, (size_t)R1 * p * 8, ch->st));
+    SMG_CUDA(dev_malloc(&W->u_accept, 8, ch->st));
+    SMG_CUDA(cudaStreamSynchronize(ch->st));
     W->inj_alloc = true;
   }
   auto up = [&](double* d, const double* h, size_t cnt) -> int {

@@ -91,3 +91,33 @@ def test_argument_errors():
     ch = Chain(X, [2, 2], 1.0, [6, 6], [0.25, 0.25], c_i=[5, 5, 6, 6])  # any base, shifted by min (launcher.cpp:34-37)
     assert ch.snapshot()["K"] == 2
     ch.close()
+
+
+def test_run_markov_chain_equals_stepwise_chain_on_a_large_matrix():
+    """>= 2^20 entries: the fp64 matrix is packed by host threads (not by the device ingest kernel) and the
+    snapshots leave through the asynchronous pinned ring; every kept iteration must equal what the step-wise
+    handle (uint8 upload, synchronous snapshot) produces from the same seed."""
+    from split_and_merge_gibbs_sampling_b200 import run_markov_chain
+    pb = Problem(4200, 256, 5, 8, seed=21)
+    kw = dict(m=3, L=8, t=3, r=3, neal8=True, split_merge=True)
+    res = run_markov_chain(np.asfortranarray(pb.X.astype(np.float64)), pb.attr, pb.gamma, pb.v, pb.w, iterations=7,
+                           burnin=2, c_i=pb.labels, seed=33, thinning=2, **kw)
+    from split_and_merge_gibbs_sampling_b200 import Chain
+    ch = Chain(pb.X, pb.attr, pb.gamma, pb.v, pb.w, c_i=pb.labels, seed=33, thinning=2, data_u8=True, **kw)
+    ch.step(2 * 2)  # burn-in * thinning
+    for it in range(7):
+        ch.step(1)
+        s = ch.snapshot()
+        assert res["total_cls"][it] == s["K"]
+        assert np.array_equal(res["c_i"][it], s["c_i"])
+        assert res["loglikelihood"][it] == s["loglikelihood"]
+        assert np.array_equal(np.array(res["centers"][it]), s["centers"])
+        assert np.array_equal(np.array(res["sigmas"][it]), s["sigmas"])
+        assert res["accepted"][it] == s["accepted"]
+        ch.step(1)
+    ch.close()
+    bad = np.asfortranarray(pb.X.astype(np.float64))
+    bad[17, 3] = 9.0  # beyond attrisize
+    from split_and_merge_gibbs_sampling_b200 import SmgError
+    with pytest.raises(SmgError):
+        run_markov_chain(bad, pb.attr, pb.gamma, pb.v, pb.w, iterations=1, burnin=0, c_i=pb.labels, seed=1, **kw)
