@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <thread>
 
 #include "smg_psm.cuh"
@@ -541,6 +542,37 @@ static int upload_u8(smg_chain* ch, const unsigned char* data) {
 
 using namespace smg;
 
+// One cached page-locked staging buffer per process for the snapshot ring of smg_run_markov_chain:
+// cudaHostAlloc / cudaFreeHost cost milliseconds to >100 ms per call (measured), far more than the run
+// itself at small iteration counts.  A second concurrent caller simply allocates its own.
+static std::mutex g_pin_mu;
+static uint8_t* g_pin_buf = nullptr;
+static size_t g_pin_size = 0;
+static bool g_pin_busy = false;
+static int pinned_acquire(size_t bytes, uint8_t** out) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (!g_pin_busy) {
+    if (g_pin_size < bytes) {
+      if (g_pin_buf) cudaFreeHost(g_pin_buf);
+      g_pin_buf = nullptr;
+      g_pin_size = 0;
+      if (cudaHostAlloc((void**)&g_pin_buf, bytes, cudaHostAllocDefault) != cudaSuccess) return 1;
+      g_pin_size = bytes;
+    }
+    g_pin_busy = true;
+    *out = g_pin_buf;
+    return 0;
+  }
+  return cudaHostAlloc((void**)out, bytes, cudaHostAllocDefault) != cudaSuccess;
+}
+static void pinned_release(uint8_t* p) {
+  std::lock_guard<std::mutex> lk(g_pin_mu);
+  if (p == g_pin_buf)
+    g_pin_busy = false;
+  else if (p)
+    cudaFreeHost(p);
+}
+
 struct smg_psm {
   int n = 0, device = 0, cap = 0, count = 0, kmax = 0;
   long long total = 0;
@@ -821,11 +853,13 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   };
   const size_t slot_bytes = 64 + (size_t)n * 4 + (((size_t)Kcap * pp + 63) & ~(size_t)63) + (size_t)Kcap * pp * 8;
   uint8_t* pinned = nullptr;
-  if (cudaHostAlloc((void**)&pinned, slot_bytes * RING, cudaHostAllocDefault) != cudaSuccess) {
+  auto th0 = std::chrono::steady_clock::now();
+  if (pinned_acquire(slot_bytes * RING, &pinned)) {
     smg_destroy(ch);
     smg_free_results(out);
     return fail(SMG_ERR_CUDA, "cudaHostAlloc of the snapshot ring failed");
   }
+  const double pin_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - th0).count();
   Slot ring[RING];
   for (int q = 0; q < RING; q++) {
     uint8_t* base = pinned + slot_bytes * q;
@@ -901,13 +935,15 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   }
   cudaStreamSynchronize(ch->st);
   for (int q = 0; q < RING; q++) cudaEventDestroy(ring[q].ev);
-  cudaFreeHost(pinned);
+  auto tf0 = std::chrono::steady_clock::now();
+  pinned_release(pinned);
+  const double unpin_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();
   std::string keep = g_last_error;
   auto td0 = std::chrono::steady_clock::now();
   smg_destroy(ch);
   if (verbose == 3)
-    fprintf(stderr, "[smgibbs] create %.4f s, loop %.4f s, destroy %.4f s\n", create_s, out->seconds,
-            std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count());
+    fprintf(stderr, "[smgibbs] create %.4f s, pinned alloc %.4f s, loop %.4f s, pinned free %.4f s, destroy %.4f s\n", create_s,
+            pin_s, out->seconds, unpin_s, std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count());
   if (rc) {
     smg_free_results(out);
     g_last_error = keep;
