@@ -41,7 +41,16 @@ static int chain_alloc(smg_chain* ch) {
   const int n = ch->n, pp = ch->pp, NST = ch->NST;
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(dev_pool_init(ch->device));
-  SMG_CUDA(cudaStreamCreateWithFlags(&ch->st, cudaStreamNonBlocking));
+  {
+    // the chain's (latency-bound) stream outranks the side stream: the side stream's bandwidth-bound gather fills
+    // every SM and would otherwise hold back the small kernels it is meant to overlap
+    int prio_lo = 0, prio_hi = 0;
+    SMG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SMG_CUDA(cudaStreamCreateWithPriority(&ch->st, cudaStreamNonBlocking, prio_hi));
+    SMG_CUDA(cudaStreamCreateWithPriority(&ch->st_aux, cudaStreamNonBlocking, prio_lo));
+  }
+  SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_scan_done, cudaEventDisableTiming));
+  SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_aux_done, cudaEventDisableTiming));
   g_alloc_stream = ch->st;
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
@@ -72,9 +81,9 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->H, (size_t)ch->Kcap * pp * ch->mmax)) return SMG_ERR_CUDA;
   ch->loglik_blocks = std::min(1184, std::max(1, cdiv(n, 8)));
   if (dalloc(&ch->partial, ch->loglik_blocks) || dalloc(&ch->loglik_d, 1)) return SMG_ERR_CUDA;
-  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4) || dalloc(&ch->scan_prof, 8))
+  if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4) || dalloc(&ch->scan_prof, 16))
     return SMG_ERR_CUDA;
-  SMG_CUDA(cudaMemsetAsync(ch->scan_prof, 0, 64, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->scan_prof, 0, 128, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->status, 0, 4, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, 4, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->stats_d, 0, 64, ch->st));
@@ -89,6 +98,7 @@ static int chain_alloc(smg_chain* ch) {
 static void chain_free(smg_chain* ch) {
   if (!ch) return;
   cudaSetDevice(ch->device);
+  if (ch->st_aux) cudaStreamSynchronize(ch->st_aux);
   if (ch->st) cudaStreamSynchronize(ch->st);
   sm_free(ch);
   void* ptrs[] = {ch->X,      ch->attr,   ch->v,         ch->w,          ch->cen[0], ch->cen[1], ch->sig[0], ch->sig[1],
@@ -103,6 +113,9 @@ static void chain_free(smg_chain* ch) {
     if (ch->ev[q]) cudaEventDestroy(ch->ev[q]);
   for (int q = 0; q < 2; q++)
     if (ch->ev_call[q]) cudaEventDestroy(ch->ev_call[q]);
+  if (ch->ev_scan_done) cudaEventDestroy(ch->ev_scan_done);
+  if (ch->ev_aux_done) cudaEventDestroy(ch->ev_aux_done);
+  if (ch->st_aux) cudaStreamDestroy(ch->st_aux);
   if (ch->st) cudaStreamDestroy(ch->st);
   delete ch;
 }
@@ -124,11 +137,12 @@ static int launch_ll_block(smg_chain* ch) {
   return 0;
 }
 
-static int launch_aux_ll(smg_chain* ch, const double* tape) {
+static int launch_aux_ll(smg_chain* ch, const double* tape, cudaStream_t stream, long long iter) {
   long long warps = (long long)ch->n * ch->m_aux;
-  aux_ll_kernel<<<cdiv(warps * 32, 256), 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->m_aux, ch->pcen, ch->pisg, ch->psden,
-                                                           ch->pool_size, tape, ch->m_aux + 1, mk_key(ch, SUB_SCAN),
-                                                           ch->LLaux, ch->aux_e);
+  RngKey key = mk_key(ch, SUB_SCAN);
+  key.sweep = (uint32_t)iter;
+  aux_ll_kernel<<<cdiv(warps * 32, 256), 256, 0, stream>>>(ch->X, ch->n, ch->pp, ch->m_aux, ch->pcen, ch->pisg, ch->psden,
+                                                          ch->pool_size, tape, ch->m_aux + 1, key, ch->LLaux, ch->aux_e);
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;
@@ -140,7 +154,14 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   if (timed) cudaEventRecord(ch->ev[0], ch->st);
   if (launch_ll_block(ch)) return SMG_ERR_CUDA;
   if (timed) cudaEventRecord(ch->ev[1], ch->st);
-  if (launch_aux_ll(ch, tape)) return SMG_ERR_CUDA;
+  if (!tape && ch->aux_ready && ch->aux_iter == ch->iter) {
+    // the columns were evaluated on the side stream while the previous split-merge step was running
+    SMG_CUDA(cudaStreamWaitEvent(ch->st, ch->ev_aux_done, 0));
+  } else {
+    if (ch->aux_ready) SMG_CUDA(cudaStreamWaitEvent(ch->st, ch->ev_aux_done, 0));  // do not race a stale prefetch
+    if (launch_aux_ll(ch, tape, ch->st, ch->iter)) return SMG_ERR_CUDA;
+  }
+  ch->aux_ready = false;
   if (timed) cudaEventRecord(ch->ev[2], ch->st);
   ScanArgs A;
   A.n = ch->n;
@@ -190,7 +211,26 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   std::swap(ch->counts, ch->counts_slot);
   ch->cur = nx;
   ch->h_launches += 4;
+  SMG_CUDA(cudaEventRecord(ch->ev_scan_done, ch->st));
   if (timed) cudaEventRecord(ch->ev[3], ch->st);
+  return 0;
+}
+
+// The auxiliary-component columns depend on X, the pool and the Philox key only -- not on the state -- so the ones
+// of the next pass are evaluated on a side stream as soon as this pass has consumed the current ones: the HBM-bound
+// gather then overlaps the latency-bound update_phi + split-merge chain.  Not done when the pool is about to be
+// re-drawn (launcher.cpp:123-129).
+static int prefetch_next_aux(smg_chain* ch) {
+  const long long next_iter = ch->iter + ch->n8_step;
+  if (!ch->neal8 || ch->iter % 1000 == 0) return 0;
+  // an iteration in between that re-draws the pool would invalidate the columns
+  for (long long it = ch->iter + 1; it < next_iter; it++)
+    if (it % 1000 == 0) return 0;
+  SMG_CUDA(cudaStreamWaitEvent(ch->st_aux, ch->ev_scan_done, 0));
+  if (launch_aux_ll(ch, nullptr, ch->st_aux, next_iter)) return SMG_ERR_CUDA;
+  SMG_CUDA(cudaEventRecord(ch->ev_aux_done, ch->st_aux));
+  ch->aux_ready = true;
+  ch->aux_iter = next_iter;
   return 0;
 }
 
@@ -237,6 +277,7 @@ PhiArgs phi_args_base(smg_chain* ch, uint32_t sub) {
   A.key = mk_key(ch, sub);
   A.sigma_exact = ch->sigma_exact;
   A.status = ch->status;
+  A.prof = ch->scan_prof + 8;
   return A;
 }
 
@@ -291,6 +332,8 @@ static int sweep(smg_chain* ch, bool timed) {
   if (timed) cudaEventRecord(ch->ev[0], ch->st);
   if (ch->neal8 && ch->iter % ch->n8_step == 0) {
     int rc = neal8_pass(ch, nullptr, timed);
+    if (rc) return rc;
+    rc = prefetch_next_aux(ch);
     if (rc) return rc;
     rc = update_phi_all(ch, SUB_PHI_AFTER_SCAN, nullptr, nullptr);
     if (rc) return rc;
@@ -764,7 +807,10 @@ int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   SMG_CUDA(cudaMemcpy(out8, ch->scan_prof, 64, cudaMemcpyDeviceToHost));
-  SMG_CUDA(cudaMemset(ch->scan_prof, 0, 64));
+#ifdef SMG_PHI_PROFILE
+  SMG_CUDA(cudaMemcpy(out8, ch->scan_prof + 8, 32, cudaMemcpyDeviceToHost));  // phi_update counters instead
+#endif
+  SMG_CUDA(cudaMemset(ch->scan_prof, 0, 128));
   return 0;
 }
 
@@ -989,6 +1035,8 @@ int smg_debug_set_pool(smg_chain* ch, long long pool_size, const double* pool_ce
   if (!ch || !pool_center || !pool_sigma) return fail(SMG_ERR_ARG, "NULL argument");
   if (pool_size < 1 || pool_size > ch->pool_size) return fail(SMG_ERR_ARG, "pool_size exceeds the allocated pool");
   SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st_aux));  // a prefetched aux pass may still be reading the old pool
+  ch->aux_ready = false;
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   std::vector<uint8_t> hc((size_t)pool_size * ch->pp, 0);
   std::vector<double> hs((size_t)pool_size * ch->pp, 1.0);

@@ -125,7 +125,7 @@ __device__ __forceinline__ double hamming_den(double s, int m) { return log(1.0 
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ double lbeta_d(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
 
-__device__ inline double betacf_d(double a, double b, double x) {
+__device__ __noinline__ double betacf_d(double a, double b, double x) {
   const double EPS = 3e-16, FPMIN = 1e-300;
   double qab = a + b, qap = a + 1.0, qam = a - 1.0;
   double c = 1.0, d = 1.0 - qab * x / qap;
@@ -154,7 +154,7 @@ __device__ inline double betacf_d(double a, double b, double x) {
   return h;
 }
 
-__device__ inline void log_ibeta_pair(double x, double a, double b, double lb, double* lower, double* upper) {
+__device__ __noinline__ void log_ibeta_pair(double x, double a, double b, double lb, double* lower, double* upper) {
   if (x <= 0.0) {
     *lower = -CUDART_INF;
     *upper = 0.0;
@@ -182,7 +182,7 @@ __device__ inline void log_ibeta_pair(double x, double a, double b, double lb, d
 // The reference evaluates log(d+1)+(d+c)log m - log 2F1(d+c,1;d+2;(m-1)/m) with GSL, which
 // overflows for clusters of ~10^3 members; both forms agree to <1e-14 rel
 // where the reference is finite (tests/test_oracle_known_answers.py).
-__device__ inline double norm_const2_d(double w, double v, double m) {
+__device__ __noinline__ double norm_const2_d(double w, double v, double m) {
   double a = w + 1.0, b = v - 1.0, lb = lbeta_d(a, b), lo, up;
   log_ibeta_pair((m - 1.0) / m, a, b, lb, &lo, &up);
   return a * log(m - 1.0) - lb - lo;
@@ -199,7 +199,7 @@ __device__ inline double logdensity_hig_d(double s, double v, double w, double m
 // which is exactly what the reference's bisection branch solves (hyperg.cpp:221-287 with
 // lF_conK2 :183-217) and the law its Beta-rejection branch samples (hyperg.cpp:359-368).
 // Safeguarded Newton on the log of the smaller tail; returns u (sigma = -1/log u).
-__device__ inline double hig_inv_u_d(double Omega, double v, double w, double m) {
+__device__ __noinline__ double hig_inv_u_d(double Omega, double v, double w, double m) {
   const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
   const double lb = lbeta_d(a, b);
   double ltot_lo, ltot_up;
@@ -272,7 +272,7 @@ struct SubStream {
 };
 
 // Gamma(shape, 1) by Marsaglia & Tsang (2000); shape < 1 through Gamma(shape+1) * U^(1/shape)
-__device__ inline double gamma_draw_d(SubStream& rs, double shape) {
+__device__ __noinline__ double gamma_draw_d(SubStream& rs, double shape) {
   double boost = 1.0;
   if (shape < 1.0) {
     boost = pow(rs.next(), 1.0 / shape);

@@ -1259,6 +1259,7 @@ struct PhiArgs {
   int sigma_exact;  // 1 => always the one-uniform inverse-CDF sigma draw (also used whenever sigma uniforms are injected)
   const int* enable;  // device flag consulted by jobs with enable_mode != 0
   int* status;
+  unsigned long long* prof;  // optional cycle counters (SMG_PHI_PROFILE): [0] centre part, [1] sigma part, [2] tail, [3] calls
 };
 
 // One CTA per job; thread j draws attribute j (and j+256, ...), then the CTA sums the per-attribute
@@ -1285,6 +1286,9 @@ __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
   if (!J.prior && nk == 0) return;  // empty cluster: untouched (common_functions.cpp:547)
   __shared__ double sh[256];
   double acc = 0.0;
+#ifdef SMG_PHI_PROFILE
+  long long tp0 = clock64(), tp1 = tp0, tp2 = tp0;
+#endif
   for (int j = threadIdx.x; j < A.pp; j += 256) {
     const size_t o = (size_t)J.dst * A.pp + j;
     if (j >= A.p) {  // padding attributes
@@ -1321,6 +1325,9 @@ __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
     const double vv = A.v[j] + s_match;
     const double ww = A.w[j] + (double)nk - s_match;
     double uu;
+#ifdef SMG_PHI_PROFILE
+    tp1 = clock64();
+#endif
     if (J.us || A.sigma_exact) {
       const double us = get_u(J.us, (size_t)j, key, U_SIGMA, (uint32_t)job, (uint32_t)j);
       uu = hig_inv_u_d(us, vv, ww, (double)m);
@@ -1328,12 +1335,24 @@ __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
       SubStream rs(key, U_SIGMA, (uint32_t)job, (uint32_t)j);
       uu = hig_draw_u_d(rs, vv, ww, (double)m);
     }
+#ifdef SMG_PHI_PROFILE
+    tp2 = clock64();
+#endif
     const double sigma = -1.0 / log(uu);
     A.cen[o] = (uint8_t)center;
     A.sig[o] = sigma;
     A.isg[o] = 1.0 / sigma;
     acc += hamming_den(sigma, m);
   }
+#ifdef SMG_PHI_PROFILE
+  if (threadIdx.x == 0 && A.prof) {
+    const long long tp3 = clock64();
+    atomicAdd(&A.prof[0], (unsigned long long)(tp1 - tp0));
+    atomicAdd(&A.prof[1], (unsigned long long)(tp2 - tp1));
+    atomicAdd(&A.prof[2], (unsigned long long)(tp3 - tp2));
+    atomicAdd(&A.prof[3], 1ull);
+  }
+#endif
   sh[threadIdx.x] = acc;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
