@@ -54,6 +54,7 @@ static int chain_alloc(smg_chain* ch) {
   g_alloc_stream = ch->st;
   for (int q = 0; q < 8; q++) SMG_CUDA(cudaEventCreate(&ch->ev[q]));
   for (int q = 0; q < 2; q++) SMG_CUDA(cudaEventCreate(&ch->ev_call[q]));
+  SMG_CUDA(cudaFuncSetAttribute(neal8_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_PF_BYTES));
   SMG_CUDA(cudaFuncSetAttribute(hamming_ll_block_t16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LLT_SMEM_BYTES));
   SMG_CUDA(cudaFuncSetAttribute(cluster_histogram_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
   if (dalloc(&ch->X, (size_t)n * pp)) return SMG_ERR_CUDA;
@@ -197,7 +198,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.prof = ch->scan_prof;
   scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, ch->LLaux,
                                                                           ch->c, ch->counts, A.log_gamma_m, ch->mrg);
-  neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, 0, ch->st>>>(A);  // one cluster
+  neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, SCAN_PF_BYTES, ch->st>>>(A);  // one cluster
   SMG_CUDA(cudaGetLastError());
   // back to canonical form: labels in c, parameters in label order in the other buffer
   const int nx = ch->cur ^ 1;

@@ -707,11 +707,18 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 }
 
 
-// loads of the NEXT chunk's slot and margin, issued here and now (volatile asm: the compiler may not sink them
-// to their first use one chunk later, which would expose the whole memory latency at every chunk)
-__device__ __forceinline__ void scan_prefetch_row(const int* cp, const double* mp, int& own, double& mg) {
-  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(own) : "l"(cp) : "memory");
-  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(mg) : "l"(mp) : "memory");
+// Ring of SCAN_PF_DEPTH chunks of (slot, margin) pairs in shared memory, filled with cp.async (LDGSTS): every
+// thread copies the pair of "its" observation of a chunk SCAN_PF_DEPTH chunks ahead and later reads back only what
+// it copied itself, so cp.async.wait_group is the only synchronisation needed and a chunk with nothing to evaluate
+// costs a barrier, not a memory round trip.
+#define SCAN_PF_DEPTH 8
+#define SCAN_SUPER 4  // chunks screened together by the quiet-stretch fast path
+#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12)
+__device__ __forceinline__ void scan_cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void scan_cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
 // more than 64 entries per draw: rare, kept out of line so that its registers do not weigh on the scan kernel
@@ -802,16 +809,66 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     abort_pass = true;
   }
 
-  // this thread's observation of the NEXT chunk (loaded one chunk ahead)
-  int nx_own = 0;
-  double nx_mg = 0.0;
-  if (tid < n) scan_prefetch_row(A.c + tid, A.mrg + tid, nx_own, nx_mg);
+  // prefetch ring (see SCAN_PF_DEPTH): one cp.async group per chunk, committed even when empty
+  extern __shared__ __align__(16) unsigned char s_ring[];
+  double* ring_mg = reinterpret_cast<double*>(s_ring);                                    // [DEPTH][1024]
+  int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [DEPTH][1024]
+  auto issue_chunk = [&](int chunk) {
+    const long long i = (long long)chunk * SCAN_CHUNK + tid;
+    if (i < n) {
+      const int slot = chunk % SCAN_PF_DEPTH;
+      scan_cp_async8(&ring_mg[slot * SCAN_CHUNK + tid], A.mrg + i);
+      scan_cp_async4(&ring_own[slot * SCAN_CHUNK + tid], A.c + i);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+#pragma unroll
+  for (int q = 0; q < SCAN_PF_DEPTH; q++) issue_chunk(q);
 
-  for (int i0 = 0; i0 < n && !abort_pass; i0 += SCAN_CHUNK) {
+  // can observation i (slot `own`, margin `mg`) be anything but a certain non-event under the current state?
+  auto undecided = [&](int i, int own, double mg) -> bool {
+    // own slot is always a start-of-pass cluster for a row the scan has not reached yet
+    if (!(mg - S.dminus[own] - S.Dplus > SCAN_DOMINANCE + SCAN_SLACK)) return true;
+    if (S.next > K0) {  // clusters born during this pass: compare with their materialised columns
+      const double thr = S.logcm1[own] + A.LL[(size_t)i * A.ldl + own] - (SCAN_DOMINANCE + SCAN_SLACK);
+      const int K = S.K;
+      for (int e = 0; e < K; e++) {
+        const int slot = S.l2s[e];
+        if (slot < K0) continue;
+        if (slot >= A.ldl || !(S.logc[slot] + __ldcg(&A.LL[(size_t)i * A.ldl + slot]) < thr)) return true;
+      }
+    }
+    return false;
+  };
+
+  const int nfull = n / SCAN_CHUNK;  // chunks with SCAN_CHUNK rows
+  int quiet = SCAN_SUPER;            // consecutive chunks without a single undecided row (optimistic start)
+  for (int i0 = 0, chunk = 0; i0 < n && !abort_pass; i0 += SCAN_CHUNK, chunk++) {
+    // ---- quiet stretch: SCAN_SUPER chunks whose rows are all certain non-events cost one barrier together
+    //      (tried only after SCAN_SUPER quiet chunks in a row, so that busy data does not pay for failed attempts)
+    if ((chunk % SCAN_SUPER) == 0 && chunk + SCAN_SUPER <= nfull && quiet >= SCAN_SUPER) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_PF_DEPTH - SCAN_SUPER) : "memory");
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < SCAN_SUPER; q++) {
+        const int slot = (chunk + q) % SCAN_PF_DEPTH;
+        any |= undecided(i0 + q * SCAN_CHUNK + tid, ring_own[slot * SCAN_CHUNK + tid], ring_mg[slot * SCAN_CHUNK + tid]);
+      }
+      if (!__syncthreads_or(any)) {
+#pragma unroll
+        for (int q = 0; q < SCAN_SUPER; q++) issue_chunk(chunk + SCAN_PF_DEPTH + q);
+        if (tid == 0) S.stats[0] += SCAN_SUPER;
+        i0 += (SCAN_SUPER - 1) * SCAN_CHUNK;
+        chunk += SCAN_SUPER - 1;
+        continue;
+      }
+      quiet = 0;
+    }
     const int nrows = min(SCAN_CHUNK, n - i0);
-    const int my_own = nx_own;
-    const double my_mg = nx_mg;
-    if (i0 + SCAN_CHUNK + tid < n) scan_prefetch_row(A.c + i0 + SCAN_CHUNK + tid, A.mrg + i0 + SCAN_CHUNK + tid, nx_own, nx_mg);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_PF_DEPTH - 1) : "memory");  // this chunk's pair has landed
+    const int my_own = ring_own[(chunk % SCAN_PF_DEPTH) * SCAN_CHUNK + tid];
+    const double my_mg = ring_mg[(chunk % SCAN_PF_DEPTH) * SCAN_CHUNK + tid];
+    issue_chunk(chunk + SCAN_PF_DEPTH);  // refill the slot just read (same thread, same addresses)
     SCAN_TICK(0);
     int start = 0;          // rows [0, start) of the chunk are final
     bool screened = false;  // the undecided set below is valid for the current state
@@ -819,25 +876,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     for (;;) {
       // ================= screen: one thread per row =================
       if (!screened) {
-        bool und = false;
-        if (tid >= start && tid < nrows) {
-          const double Dp = S.Dplus;
-          // own slot is always a start-of-pass cluster for a row the scan has not reached yet
-          und = !(my_mg - S.dminus[my_own] - Dp > SCAN_DOMINANCE + SCAN_SLACK);
-          if (!und && S.next > K0) {
-            const int i = i0 + tid;
-            const double thr = S.logcm1[my_own] + A.LL[(size_t)i * A.ldl + my_own] - (SCAN_DOMINANCE + SCAN_SLACK);
-            const int K = S.K;
-            for (int e = 0; e < K; e++) {
-              const int slot = S.l2s[e];
-              if (slot < K0) continue;
-              if (slot >= A.ldl || !(S.logc[slot] + __ldcg(&A.LL[(size_t)i * A.ldl + slot]) < thr)) {
-                und = true;
-                break;
-              }
-            }
-          }
-        }
+        const bool und = (tid >= start && tid < nrows) && undecided(i0 + tid, my_own, my_mg);
         if (und) S.own[tid] = my_own;
         const unsigned b = __ballot_sync(SMG_FULL, und);
         if (lane == 0) S.und[warp] = b;
@@ -846,8 +885,10 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         total_und = __syncthreads_count(und);
         if (total_und == 0) {  // every remaining row of the chunk is a certain non-event
           if (tid == 0) S.stats[0]++;
+          quiet = (start == 0) ? quiet + 1 : 0;
           break;
         }
+        quiet = 0;
       }
       SCAN_TICK(1);
       if (consumed >= total_und) break;
@@ -1262,6 +1303,69 @@ struct PhiArgs {
   unsigned long long* prof;  // optional cycle counters (SMG_PHI_PROFILE): [0] centre part, [1] sigma part, [2] tail, [3] calls
 };
 
+// Centre draw of one attribute (compute_prob_centers + sample_center_1_cluster, common_functions.cpp:495-505,195):
+// probs = softmax(-(n_k - freq_a)/sigma), then Rcpp::sample(1..m, 1, true, probs).  Up to 8 levels everything stays in
+// registers, and when the largest probability is unique and already covers u -- the first step of Rcpp's
+// descending-order walk -- the sort is skipped; ties and the other draws take the general path, which
+// reproduces R's revsort permutation.  Returns the 1-based level.
+__device__ __forceinline__ int draw_center(const int* __restrict__ h, int nk, double sg, int m, double u) {
+  if (m <= 8) {
+    double p[8];
+    double mx = -CUDART_INF;
+#pragma unroll
+    for (int a = 0; a < 8; a++) {
+      p[a] = (a < m) ? -((double)nk - (double)h[a]) / sg : -CUDART_INF;
+      mx = p[a] > mx ? p[a] : mx;
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+      if (a < m) {
+        p[a] = exp(p[a] - mx);
+        sum += p[a];
+      }
+    double sum2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+      if (a < m) {
+        p[a] = p[a] / sum;
+        sum2 += p[a];
+      }
+    double qmax = -1.0;
+    int arg = 0, nmax = 0;
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+      if (a < m) {
+        const double q = p[a] / sum2;  // what Rcpp::sample compares against after its own normalisation
+        if (q > qmax) {
+          qmax = q;
+          arg = a;
+          nmax = 1;
+        } else if (q == qmax) {
+          nmax++;
+        }
+      }
+    if (nmax == 1 && u <= qmax) return arg + 1;
+    double pt[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) pt[a] = (a < m) ? p[a] : 0.0;
+    return 1 + sample_probs_small(pt, m, u);
+  }
+  double pt[SMG_MAX_LEVELS];
+  double mx = -CUDART_INF;
+  for (int a = 0; a < m; a++) {
+    pt[a] = -((double)nk - (double)h[a]) / sg;
+    mx = pt[a] > mx ? pt[a] : mx;
+  }
+  double sum = 0.0;
+  for (int a = 0; a < m; a++) {
+    pt[a] = exp(pt[a] - mx);
+    sum += pt[a];
+  }
+  for (int a = 0; a < m; a++) pt[a] = pt[a] / sum;
+  return 1 + sample_probs_small(pt, m, u);
+}
+
 // One CTA per job; thread j draws attribute j (and j+256, ...), then the CTA sums the per-attribute
 // log-normalisers in a fixed order into sden[dst].
 __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
@@ -1307,19 +1411,7 @@ __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
     } else {
       const double sg = A.sig_src[(size_t)J.src * A.pp + j];
       const int* h = A.H + ((size_t)J.hist * A.pp + j) * A.mmax;
-      double pt[SMG_MAX_LEVELS];
-      double mx = -CUDART_INF;
-      for (int a = 0; a < m; a++) {
-        pt[a] = -((double)nk - (double)h[a]) / sg;
-        mx = pt[a] > mx ? pt[a] : mx;
-      }
-      double sum = 0.0;
-      for (int a = 0; a < m; a++) {
-        pt[a] = exp(pt[a] - mx);
-        sum += pt[a];
-      }
-      for (int a = 0; a < m; a++) pt[a] = pt[a] / sum;
-      center = 1 + sample_probs_small(pt, m, uc);
+      center = draw_center(h, nk, sg, m, uc);
       s_match = (double)h[center - 1];
     }
     const double vv = A.v[j] + s_match;
