@@ -163,3 +163,76 @@ def test_full_size_parity_config_c2():
         if ref["exact_pos_ties"] == 0:
             assert got["K"] == ref["K"]
             assert np.array_equal(got["c_i"], ref["c"])
+
+
+def _assert_scan_equal(ref, got):
+    if ref["exact_pos_ties"] == 0:
+        assert got["K"] == ref["K"]
+        assert np.array_equal(got["c_i"], ref["c"])
+        assert np.array_equal(got["centers"], ref["center"])
+        assert np.array_equal(got["sigmas"], ref["sigma"])
+
+
+@pytest.mark.parametrize("seed", [31, 32])
+def test_scan_more_than_64_entries(seed):
+    # K + m_aux > 64: the 8-entries-per-lane evaluation path; diffuse data so that draws are real decisions
+    pb = Problem(2800, 32, 4, 70, seed=seed, s=1.1)
+    ref, got, st = _scan_case(pb, "truth", seed, pool=211)
+    assert ref["K"] + 3 > 64 and st["scan_events"] > 20
+    _assert_scan_equal(ref, got)
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_scan_and_update_phi_with_12_levels(seed):
+    # more than 7 levels: C-form likelihood kernel, global-atomic histogram, general centre draw
+    pb = Problem(1500, 40, 12, 6, seed=seed, s=1.0)
+    ref, got, st = _scan_case(pb, "random", seed, L=9, iters=1)
+    assert st["scan_events"] > 50
+    _assert_scan_equal(ref, got)
+    K, c, cen, sig = oracle_state_full(pb, mode="random", seed=seed, L=9, iters=2)
+    ch = pb.chain()
+    ch.set_state(K, c, cen, sig)
+    LL, mm = ch.ll_block(K)
+    LLo, mmo = orc.ll_block(pb.od, cen, sig)
+    assert np.array_equal(mm, mmo) and np.max(rel_err(LL, LLo)) < 1e-12
+    H, cnt = ch.histogram(K)
+    Ho, cnto = orc.histogram(pb.od, K, c, H.shape[2])
+    assert np.array_equal(H, Ho) and np.array_equal(cnt, cnto)
+    rng = np.random.default_rng(seed)
+    uc, us = rng.random((K, pb.p)), rng.random((K, pb.p))
+    tape = np.concatenate([np.concatenate([uc[k], us[k]]) for k in range(K)])
+    refp = orc.update_phi(pb.od, c, cen, sig, tape, o=orc.opts(stable_hig=1, sigma_inverse_cdf=1))
+    ch.update_phi(uc, us)
+    assert np.array_equal(ch.snapshot()["centers"], refp["center"])
+    ch.close()
+
+
+def test_scan_tiny_problem_one_aux():
+    pb = Problem(40, 8, 3, 2, seed=51, s=1.0)
+    ref, got, st = _scan_case(pb, "random", 51, m_aux=1, pool=17, L=3)
+    _assert_scan_equal(ref, got)
+
+
+def test_scan_births_beyond_the_materialised_columns():
+    # every observation its own cluster and only 4 spare LL columns (max_clusters = n + 4): the clusters opened by
+    # cases 3 and 4 soon get slots >= ldl, whose likelihoods are evaluated on the fly instead of being read
+    pb = Problem(100, 16, 3, 3, seed=61, s=0.8)
+    n = pb.n
+    c0 = np.arange(n, dtype=np.int32)
+    pc, ps = orc.draw_pool(pb.od, 150, 62, o=orc.opts(stable_hig=1))
+    cen, sig = pc[:n].copy(), ps[:n].copy()
+    rng = np.random.default_rng(61)
+    tape = (rng.integers(0, 2**53, size=n * 4).astype(np.float64) + 0.5) / 2.0**53
+    ref = orc.neal8_scan(pb.od, 3, c0, cen, sig, pc, ps, tape, o=orc.opts(counted=0), kcap=256)
+    ch = pb.chain(m=3, c_i=c0, max_clusters=n + 4)
+    ch.set_state(n, c0, cen, sig)
+    ch.set_pool(pc, ps)
+    ch.neal8_scan(tape)
+    got = ch.snapshot()
+    st = ch.stats()
+    ch.close()
+    assert st["scan_events"] > 30
+    if ref["exact_pos_ties"] == 0:
+        assert got["K"] == ref["K"]
+        assert np.array_equal(got["c_i"], ref["c"])
+        assert np.array_equal(got["sigmas"], ref["sigma"])
