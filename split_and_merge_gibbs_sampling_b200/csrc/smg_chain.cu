@@ -33,6 +33,7 @@ static int status_to_error(int st) {
   if (st & ST_TOO_MANY_ENTRIES) return fail(SMG_ERR_CAPACITY, "K + m exceeds 256 entries per allocation draw");
   if (st & ST_LL_COLS) return fail(SMG_ERR_CAPACITY, "number of clusters exceeds max_clusters");
   if (st & ST_SLOTS_EXHAUSTED) return fail(SMG_ERR_CAPACITY, "more than 1024 cluster slots used in one pass");
+  if (st & ST_GRID_TIMEOUT) return fail(SMG_ERR_CUDA, "grid barrier of the split-merge chain kernel timed out");
   return fail(SMG_ERR_STATE, "device status " + std::to_string(st));
 }
 
@@ -740,7 +741,9 @@ int smg_step_many(smg_chain** chains, int count, int n_iters) {
   for (int it = 0; it < n_iters; it++)
     for (int q = 0; q < count; q++) {
       SMG_CUDA(cudaSetDevice(chains[q]->device));
+      chains[q]->many = count > 1;
       int rc = sweep(chains[q], it == n_iters - 1);
+      chains[q]->many = false;
       if (rc) return rc;
     }
   for (int q = 0; q < count; q++) {
@@ -809,7 +812,7 @@ int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   SMG_CUDA(cudaMemcpy(out8, ch->scan_prof, 64, cudaMemcpyDeviceToHost));
 #ifdef SMG_PHI_PROFILE
-  SMG_CUDA(cudaMemcpy(out8, ch->scan_prof + 8, 32, cudaMemcpyDeviceToHost));  // phi_update counters instead
+  SMG_CUDA(cudaMemcpy(out8, ch->scan_prof + 8, 64, cudaMemcpyDeviceToHost));  // phi_update / chain counters instead
 #endif
   SMG_CUDA(cudaMemset(ch->scan_prof, 0, 128));
   return 0;

@@ -32,7 +32,8 @@ enum StatusBits : int {
   ST_WALKER = 4,             // Rcpp would have switched to Walker alias sampling (nc > 200)
   ST_LL_COLS = 8,            // K exceeds the LL matrix column capacity
   ST_BAD_PROB = 16,          // non-finite probability (Rcpp::sample would stop())
-  ST_VALIDATE = 32           // validate_state failure (common_functions.cpp:146-172)
+  ST_VALIDATE = 32,          // validate_state failure (common_functions.cpp:146-172)
+  ST_GRID_TIMEOUT = 64       // a grid barrier of the persistent split-merge kernel timed out
 };
 
 // =============================================================================
@@ -1203,24 +1204,18 @@ __global__ void __launch_bounds__(256) subset_histogram_kernel(const uint8_t* __
 // Same, with the two histograms privatised in shared memory (2*pp*mmax ints) and a fixed grid that strides
 // over the member rows: one flush of integer atomics per CTA instead of one atomic per (row, attribute).
 // Counts are not touched when cnt2 == null (the restricted-scan decision kernel already knows them).
-__global__ void __launch_bounds__(256) subset_histogram_smem_kernel(const uint8_t* __restrict__ X, int pp,
-                                                                    const int* __restrict__ S,
-                                                                    const int* __restrict__ nSptr,
-                                                                    const int* __restrict__ z,
-                                                                    const int* __restrict__ anchors, int mmax,
-                                                                    int* __restrict__ H2, int* __restrict__ cnt2,
-                                                                    const int* enable, int enable_val) {
-  if (enable && *enable != enable_val) return;
-  extern __shared__ int s_h[];  // [2][pp][mmax]
+__device__ __forceinline__ void subset_hist_body(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S, int nS,
+                                                 const int* __restrict__ z, const int* __restrict__ anchors, int mmax,
+                                                 int* __restrict__ H2, int* __restrict__ cnt2, int* s_h, int block,
+                                                 int nblocks) {
   const int len = pp * mmax;
   const int ng = z ? 2 : 1;
   for (int q = threadIdx.x; q < ng * len; q += blockDim.x) s_h[q] = 0;
   __syncthreads();
   const int chunks = pp / 16;
-  const int nS = *nSptr;
   const long long total = (long long)(nS + 2) * chunks;
   int c0 = 0, c1 = 0;
-  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+  for (long long t = (long long)block * blockDim.x + threadIdx.x; t < total; t += (long long)nblocks * blockDim.x) {
     const int r = (int)(t / chunks), q = (int)(t % chunks);
     int row, g;
     if (r < nS) {
@@ -1252,6 +1247,18 @@ __global__ void __launch_bounds__(256) subset_histogram_smem_kernel(const uint8_
     const int hv = s_h[q];
     if (hv) atomicAdd(&H2[q], hv);
   }
+}
+
+__global__ void __launch_bounds__(256) subset_histogram_smem_kernel(const uint8_t* __restrict__ X, int pp,
+                                                                    const int* __restrict__ S,
+                                                                    const int* __restrict__ nSptr,
+                                                                    const int* __restrict__ z,
+                                                                    const int* __restrict__ anchors, int mmax,
+                                                                    int* __restrict__ H2, int* __restrict__ cnt2,
+                                                                    const int* enable, int enable_val) {
+  if (enable && *enable != enable_val) return;
+  extern __shared__ int s_h[];  // [2][pp][mmax]
+  subset_hist_body(X, pp, S, *nSptr, z, anchors, mmax, H2, cnt2, s_h, blockIdx.x, gridDim.x);
 }
 
 // =============================================================================
@@ -1368,32 +1375,18 @@ __device__ __forceinline__ int draw_center(const int* __restrict__ h, int nk, do
 
 // One CTA per job; thread j draws attribute j (and j+256, ...), then the CTA sums the per-attribute
 // log-normalisers in a fixed order into sden[dst].
-__global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
-  const int job = blockIdx.x;
-  PhiJob J;
-  if (A.njobs > 0) {
-    if (job >= A.njobs) return;
-    J = A.jobs[job];
-    if (J.enable_mode == 1 && *A.enable == 0) return;
-    if (J.enable_mode == 2 && *A.enable != 0) return;
-  } else {
-    if (job >= *A.njobs_ptr) return;
-    J.hist = J.src = J.dst = J.cnt_idx = job;
-    J.sub = A.key.sub;
-    J.prior = A.prior;
-    J.uc = A.u_center ? A.u_center + (size_t)job * A.u_stride : nullptr;
-    J.us = A.u_sigma ? A.u_sigma + (size_t)job * A.u_stride : nullptr;
-  }
+// One parameter-update job executed by one CTA (any block size >= 256: the first 256 threads draw, everybody
+// takes part in the barriers of the final reduction).  `sh` = 256 doubles of shared memory.
+__device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, int job, double* sh) {
   RngKey key = A.key;
   key.sub = J.sub;
   const int nk = J.prior ? 0 : A.counts[J.cnt_idx];
   if (!J.prior && nk == 0) return;  // empty cluster: untouched (common_functions.cpp:547)
-  __shared__ double sh[256];
   double acc = 0.0;
 #ifdef SMG_PHI_PROFILE
   long long tp0 = clock64(), tp1 = tp0, tp2 = tp0;
 #endif
-  for (int j = threadIdx.x; j < A.pp; j += 256) {
+  for (int j = threadIdx.x; j < A.pp && threadIdx.x < 256; j += 256) {
     const size_t o = (size_t)J.dst * A.pp + j;
     if (j >= A.p) {  // padding attributes
       A.cen[o] = 0;
@@ -1445,13 +1438,35 @@ __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
     atomicAdd(&A.prof[3], 1ull);
   }
 #endif
-  sh[threadIdx.x] = acc;
+  if (threadIdx.x < 256) sh[threadIdx.x] = acc;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
   if (threadIdx.x == 0) A.sden[J.dst] = sh[0];
+}
+
+
+__global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
+  const int job = blockIdx.x;
+  PhiJob J;
+  if (A.njobs > 0) {
+    if (job >= A.njobs) return;
+    J = A.jobs[job];
+    if (J.enable_mode == 1 && *A.enable == 0) return;
+    if (J.enable_mode == 2 && *A.enable != 0) return;
+  } else {
+    if (job >= *A.njobs_ptr) return;
+    J.hist = J.src = J.dst = J.cnt_idx = job;
+    J.sub = A.key.sub;
+    J.prior = A.prior;
+    J.enable_mode = 0;
+    J.uc = A.u_center ? A.u_center + (size_t)job * A.u_stride : nullptr;
+    J.us = A.u_sigma ? A.u_sigma + (size_t)job * A.u_stride : nullptr;
+  }
+  __shared__ double sh[256];
+  phi_job_body(A, J, job, sh);
 }
 
 // derive isg / den / sden from (cen, sig) for slots [0, nslots): used after host uploads

@@ -37,6 +37,8 @@ struct SmWork {
   double* partial = nullptr;  // [4][RB]
   double* terms = nullptr;    // [24]
   size_t hist_smem = 0;       // dynamic shared memory of subset_histogram_smem_kernel (0: does not fit)
+  unsigned* chain_bar = nullptr;  // [2]: grid-barrier counter and error flag of sm_chain_kernel
+  bool persistent = false;        // restricted-scan chain as one cooperative kernel
   // injected uniforms (device copies, allocated on first use)
   double *u_pair = nullptr, *u_prior_c = nullptr, *u_prior_s = nullptr, *u_launch = nullptr, *u_rg = nullptr;
   double *u_rg_c = nullptr, *u_rg_s = nullptr, *u_mg_c = nullptr, *u_mg_s = nullptr, *u_accept = nullptr;
@@ -155,18 +157,15 @@ __global__ void sm_launch_alloc_kernel(const SmInfo* info, const double* u_inj, 
 // to the larger side iff |D| >= logit(u), to the other side otherwise.  logit(u) and d0 = LL_1 - LL_2 do
 // not depend on the running counts: sm_ll2prep_kernel evaluates them for every member in parallel
 // (one warp per member, all SMs).
-__global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
-                                                         const SmInfo* info, const uint8_t* cen, const double* isg,
-                                                         const double* sden, int slotA, int slotB, const double* u_inj,
-                                                         RngKey key, double* __restrict__ dl, double* __restrict__ lgt,
-                                                         const int* enable, int enable_val) {
-  if (enable && *enable != enable_val) return;
-  const int nS = info->nS;
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+__device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S, int nS,
+                                                const uint8_t* cen, const double* isg, const double* sden, int slotA,
+                                                int slotB, const double* u_inj, const RngKey& key, double* dl,
+                                                double* lgt, int gwarp, int nwarps) {
+  const int lane = threadIdx.x & 31;
   const uint8_t *cA = cen + (size_t)slotA * pp, *cB = cen + (size_t)slotB * pp;
   const double *wA = isg + (size_t)slotA * pp, *wB = isg + (size_t)slotB * pp;
   const double sdA = sden[slotA], sdB = sden[slotB];
-  for (int pos = blockIdx.x * wpb + (threadIdx.x >> 5); pos < nS; pos += gridDim.x * wpb) {
+  for (int pos = gwarp; pos < nS; pos += nwarps) {
     const uint8_t* x = X + (size_t)S[pos] * pp;
     const double llA = -warp_mismatch_dot(x, cA, wA, pp, lane) - sdA;
     const double llB = -warp_mismatch_dot(x, cB, wB, pp, lane) - sdB;
@@ -176,6 +175,17 @@ __global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restri
       lgt[pos] = log(u / (1.0 - u));
     }
   }
+}
+
+__global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
+                                                         const SmInfo* info, const uint8_t* cen, const double* isg,
+                                                         const double* sden, int slotA, int slotB, const double* u_inj,
+                                                         RngKey key, double* __restrict__ dl, double* __restrict__ lgt,
+                                                         const int* enable, int enable_val) {
+  if (enable && *enable != enable_val) return;
+  const int wpb = blockDim.x >> 5;
+  sm_ll2prep_body(X, pp, S, info->nS, cen, isg, sden, slotA, slotB, u_inj, key, dl, lgt,
+                  blockIdx.x * wpb + (threadIdx.x >> 5), gridDim.x * wpb);
 }
 
 // The sequential part, one CTA.  Inside a chunk of 1024 members the running side counts can only move by
@@ -188,30 +198,33 @@ __global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restri
 // result as the one-at-a-time scan.  Also zeroes the histograms the next kernel fills and publishes
 // the side counts (anchors included).
 #define SM_DECIDE_T 1024
-__global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* info, const double* __restrict__ dl,
-                                                                 const double* __restrict__ lgt, int* __restrict__ z,
-                                                                 int* __restrict__ Hzero, int hlen, int* __restrict__ cnt2,
-                                                                 const int* enable, int enable_val) {
-  if (enable && *enable != enable_val) return;
-  __shared__ double s_d0[SM_DECIDE_T], s_lg[SM_DECIDE_T];
-  __shared__ int s_z[SM_DECIDE_T], s_pre[SM_DECIDE_T], s_list[SM_DECIDE_T];
-  __shared__ int s_wsum[32], s_wnr[32];
-  __shared__ int s_nB, s_nnr, s_cdelta;
-  const int nS = info->nS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int q = tid; q < hlen; q += SM_DECIDE_T) Hzero[q] = 0;
+template <int T>
+struct RdecideSmem {
+  double d0[T], lg[T];
+  int z[T], pre[T], list[T];
+  int wsum[32], wnr[32];
+  int nB, nnr, cdelta;
+};
+
+// (no __restrict__ here: inside sm_chain_kernel these arrays are written by other CTAs earlier in the same launch)
+template <int T>
+__device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const double* lgt, int* z, int* Hzero, int hlen,
+                                                int* cnt2, RdecideSmem<T>& M) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int q = tid; q < hlen; q += T) Hzero[q] = 0;
   {  // side-1 count on entry (anchor i_2 included)
     int c1 = 0;
-    for (int pos = tid; pos < nS; pos += SM_DECIDE_T) c1 += z[pos];
+    for (int pos = tid; pos < nS; pos += T) c1 += z[pos];
     c1 = warp_sum_i(c1);
-    if (lane == 0) s_wsum[warp] = c1;
+    if (lane == 0) M.wsum[warp] = c1;
     __syncthreads();
     if (warp == 0) {
-      int t = warp_sum_i(s_wsum[lane]);
-      if (lane == 0) s_nB = 1 + t;
+      int t = warp_sum_i(lane < T / 32 ? M.wsum[lane] : 0);
+      if (lane == 0) M.nB = 1 + t;
     }
     __syncthreads();
   }
-  for (int base = 0; base < nS; base += SM_DECIDE_T) {
+  for (int base = 0; base < nS; base += T) {
     const int pos = base + tid;
     const bool valid = pos < nS;
     const double d0 = valid ? dl[pos] : 0.0, lg = valid ? lgt[pos] : 0.0;
@@ -220,8 +233,8 @@ __global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* i
     // this chunk is walked: at most the chunk's c1 side-1 members leave and its c0 side-0 members join.
     // The log-count term log((nS+1-b)/b) of D is decreasing in b.
     const int c1 = __syncthreads_count(valid && zz == 1);
-    const int c0 = min(SM_DECIDE_T, nS - base) - c1;
-    const int blo = s_nB - c1, bhi = s_nB + c0 - 1;
+    const int c0 = min(T, nS - base) - c1;
+    const int blo = M.nB - c1, bhi = M.nB + c0 - 1;
     const double dc_max = log((double)(nS + 1 - blo)) - log((double)blo);
     const double dc_min = log((double)(nS + 1 - bhi)) - log((double)bhi);
     const bool robust0 = valid && (dc_min + d0 > fabs(lg) + 1e-9);   // D > |logit u| whatever the counts: side 0
@@ -237,11 +250,11 @@ __global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* i
       if (lane >= o) incl += y;
     }
     const unsigned nb = __ballot_sync(SMG_FULL, nonrob);
-    if (lane == 31) s_wsum[warp] = incl;
-    if (lane == 0) s_wnr[warp] = __popc(nb);
+    if (lane == 31) M.wsum[warp] = incl;
+    if (lane == 0) M.wnr[warp] = __popc(nb);
     __syncthreads();
     if (warp == 0) {
-      int a = s_wsum[lane], b = s_wnr[lane], xa = a, xb = b;
+      int a = lane < T / 32 ? M.wsum[lane] : 0, b = lane < T / 32 ? M.wnr[lane] : 0, xa = a, xb = b;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         int ya = __shfl_up_sync(SMG_FULL, xa, o), yb = __shfl_up_sync(SMG_FULL, xb, o);
@@ -250,30 +263,30 @@ __global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* i
           xb += yb;
         }
       }
-      s_wsum[lane] = xa - a;
-      s_wnr[lane] = xb - b;
+      M.wsum[lane] = xa - a;
+      M.wnr[lane] = xb - b;
       if (lane == 31) {
-        s_cdelta = xa;
-        s_nnr = xb;
+        M.cdelta = xa;
+        M.nnr = xb;
       }
     }
     __syncthreads();
-    s_pre[tid] = s_wsum[warp] + incl - delta;  // side-1 change of the robust members before this position
-    s_d0[tid] = d0;
-    s_lg[tid] = lg;
-    s_z[tid] = newz;
-    if (nonrob) s_list[s_wnr[warp] + __popc(nb & ((1u << lane) - 1))] = tid;
+    M.pre[tid] = M.wsum[warp] + incl - delta;  // side-1 change of the robust members before this position
+    M.d0[tid] = d0;
+    M.lg[tid] = lg;
+    M.z[tid] = newz;
+    if (nonrob) M.list[M.wnr[warp] + __popc(nb & ((1u << lane) - 1))] = tid;
     __syncthreads();
     if (warp == 0) {
-      const int nnr = s_nnr, nB0 = s_nB;
+      const int nnr = M.nnr, nB0 = M.nB;
       int extra = 0;  // side-1 change of the non-robust members decided so far
       for (int b0 = 0; b0 < nnr; b0 += 32) {
         const int q = b0 + lane;
         const bool v = q < nnr;
-        const int t = v ? s_list[q] : 0;
-        const double md0 = s_d0[t], mlg = s_lg[t];
-        const int pre = s_pre[t];
-        int mz = s_z[t];
+        const int t = v ? M.list[q] : 0;
+        const double md0 = M.d0[t], mlg = M.lg[t];
+        const int pre = M.pre[t];
+        int mz = M.z[t];
         int start = 0;
         while (start < 32) {
           int nz = mz;
@@ -295,18 +308,28 @@ __global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* i
           extra += zn - zo;
           start = f + 1;
         }
-        if (v) s_z[t] = mz;
+        if (v) M.z[t] = mz;
       }
-      if (lane == 0) s_nB = nB0 + s_cdelta + extra;
+      if (lane == 0) M.nB = nB0 + M.cdelta + extra;
     }
     __syncthreads();
-    if (valid) z[pos] = s_z[tid];
+    if (valid) z[pos] = M.z[tid];
     __syncthreads();
   }
   if (tid == 0 && cnt2) {
-    cnt2[0] = nS + 2 - s_nB;
-    cnt2[1] = s_nB;
+    cnt2[0] = nS + 2 - M.nB;
+    cnt2[1] = M.nB;
   }
+}
+
+
+__global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* info, const double* __restrict__ dl,
+                                                                 const double* __restrict__ lgt, int* __restrict__ z,
+                                                                 int* __restrict__ Hzero, int hlen, int* __restrict__ cnt2,
+                                                                 const int* enable, int enable_val) {
+  if (enable && *enable != enable_val) return;
+  __shared__ RdecideSmem<SM_DECIDE_T> M;
+  sm_rdecide_body<SM_DECIDE_T>(info->nS, dl, lgt, z, Hzero, hlen, cnt2, M);
 }
 
 // proposal = copy of the split launch state (sides and the two parameter slots), split_merge.cpp:575-577
@@ -332,6 +355,176 @@ __global__ void sm_hist_add_kernel(int len, int* H, int* cnt, int a, int b, int 
   int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < len) H[(size_t)dst * len + q] = H[(size_t)a * len + q] + H[(size_t)b * len + q];
   if (q == 0) cnt[dst] = cnt[a] + cnt[b];
+}
+
+// ------------------------------------------------------------------------------------------
+// The restricted-scan chain as ONE persistent cooperative kernel.
+//
+// t launch scans + the proposal scan are 4 dependent phases each (likelihood differences -> ordered decision ->
+// side histograms -> parameter update): as separate launches every phase starts on cold SMs (ncu: 38% of the
+// parameter-update kernel's stall samples are instruction-fetch starvation) and pays a launch gap.  Here a small grid
+// of co-resident CTAs (cudaLaunchCooperativeKernel) walks the whole chain, phases separated by a grid barrier
+// (release add / acquire poll on one global counter).  Same device functions and the same Philox keys as the
+// multi-launch path: the two are interchangeable bit for bit (tests run both).  Measured at the metric config:
+// 0.73 ms per proposal against 0.85 ms as ~50 launches, with 120 CTAs (24 CTAs: 0.97 ms, the likelihood phase
+// starves).  A gang-scheduled 120-CTA grid does not share the GPU well, so chains that are stepped together
+// (smg_step_many) keep the multi-launch path.
+// ------------------------------------------------------------------------------------------
+enum SmJob : int { J_PRI_A = 0, J_PRI_B, J_PRI_M, J_L0, J_L1, J_MG, J_P0, J_P1, J_MSTAR, J_N };
+
+__host__ __device__ inline PhiJob sm_job_at(int B, int which, uint32_t sub, const double* uc, const double* us, int enable_mode) {
+  // (hist, current sigma slot, destination slot, count index) of J_PRI_A .. J_MSTAR
+  const int hist[J_N] = {0, 0, 0, SH_L0, SH_L1, SH_M, SH_P0, SH_P1, SH_M};
+  const int src[J_N] = {0, 0, 0, SM_SL_A, SM_SL_B, SM_ML_M, SM_ST_A, SM_ST_B, SM_ML_M};
+  const int dst[J_N] = {SM_SL_A, SM_SL_B, SM_ML_M, SM_SL_A, SM_SL_B, SM_ML_M, SM_ST_A, SM_ST_B, SM_ST_M};
+  const int cix[J_N] = {0, 0, 0, SH_L0, SH_L1, SH_M, SH_P0, SH_P1, SH_M};
+  PhiJob J;
+  J.hist = hist[which];
+  J.src = B + src[which];
+  J.dst = B + dst[which];
+  J.cnt_idx = cix[which];
+  J.sub = sub;
+  J.prior = which <= J_PRI_M;
+  J.enable_mode = enable_mode;
+  J.uc = uc;
+  J.us = us;
+  return J;
+}
+struct GridBar {
+  unsigned* counter;
+  unsigned target, nblocks;
+  int* err;
+  int* status;
+};
+__device__ __forceinline__ void grid_sync(GridBar& B) {
+  __syncthreads();
+  B.target += B.nblocks;
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(B.counter) : "memory");
+    unsigned seen = 0, spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(B.counter) : "memory");
+      if (seen >= B.target) break;
+      if (++spins > (1u << 22)) {  // a lost CTA must not hang the device: flag it and let everybody run out
+        atomicExch(B.err, 1);
+        if (B.status) atomicOr(B.status, ST_GRID_TIMEOUT);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+struct SmChainArgs {
+  int n, p, pp, mmax, t, r, NS;
+  const uint8_t* X;
+  const int* S;
+  const SmInfo* info;
+  uint8_t* cen;
+  double *sig, *isg, *sden;
+  int *H, *cnt, *zL, *zStar;
+  double *dl, *lgt;
+  PhiArgs phi;  // common fields of the parameter updates (jobs are filled on the device)
+  const double *u_rg, *u_rg_c, *u_rg_s, *u_mg_c, *u_mg_s;  // injected uniforms (bases) or null
+  RngKey key;
+  unsigned* bar;
+  int* err;
+};
+
+#define SM_CHAIN_CTAS 120
+#define SM_CHAIN_T 512  // 128 registers per thread: the parameter-update body does not spill
+
+__global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) {
+  extern __shared__ int s_hist[];
+  __shared__ RdecideSmem<SM_CHAIN_T> M;
+  __shared__ double sh[256];
+  GridBar B{A.bar, 0u, gridDim.x, A.err, A.phi.status};
+  const int nS = A.info->nS, same = A.info->same;
+  const int n = A.n, p = A.p, pp = A.pp, NSB = A.NS;
+  const int gwarp = blockIdx.x * (SM_CHAIN_T / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (SM_CHAIN_T / 32);
+  const size_t len = (size_t)pp * A.mmax;
+  auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
+
+  // allocation part of restricted scan q on sides z / slots (slotA, slotB) -> histograms h0, h0+1
+#ifdef SMG_PHI_PROFILE
+  long long tk = clock64();
+#define CHAIN_TICK(k)                                                                   \
+  do {                                                                                  \
+    const long long _t = clock64();                                                     \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.phi.prof) A.phi.prof[k] += (unsigned long long)(_t - tk); \
+    tk = _t;                                                                            \
+  } while (0)
+#else
+#define CHAIN_TICK(k)
+#endif
+  auto alloc_scan = [&](int* z, int slotA, int slotB, int h0, int q) {
+    RngKey k = A.key;
+    k.sub = SUB_SM_RG + q;
+    CHAIN_TICK(7);
+    sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, A.lgt, gwarp,
+                    nwarps);
+    grid_sync(B);
+    CHAIN_TICK(4);
+    if (blockIdx.x == 0) sm_rdecide_body<SM_CHAIN_T>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
+    grid_sync(B);
+    CHAIN_TICK(5);
+    subset_hist_body(A.X, pp, A.S, nS, z, &A.info->i1, A.mmax, A.H + (size_t)h0 * len, nullptr, s_hist, blockIdx.x,
+                     gridDim.x);
+    grid_sync(B);
+    CHAIN_TICK(6);
+  };
+  auto run_jobs = [&](const PhiJob* jobs, int nj) {
+    if ((int)blockIdx.x < nj) phi_job_body(A.phi, jobs[blockIdx.x], blockIdx.x, sh);
+    grid_sync(B);
+  };
+
+  const int nsteps = A.t > A.r ? A.t : A.r;
+  for (int q = 0; q < nsteps; q++) {
+    PhiJob j[3];
+    int nj = 0;
+    if (q < A.t) {
+      alloc_scan(A.zL, NSB + SM_SL_A, NSB + SM_SL_B, SH_L0, q);
+      for (int side = 0; side < 2; side++)
+        j[nj++] = sm_job_at(NSB, J_L0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+    }
+    if (q < A.r)
+      j[nj++] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + q, off(A.u_mg_c, (size_t)q * p), off(A.u_mg_s, (size_t)q * p), 0);
+    run_jobs(j, nj);
+    if (*(volatile int*)A.err) return;
+  }
+  // proposal = split launch state (sides + the two parameter slots) ...
+  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nS; pos += gridDim.x * blockDim.x) A.zStar[pos] = A.zL[pos];
+  if (blockIdx.x < 2) {
+    const int src = NSB + (blockIdx.x ? SM_SL_B : SM_SL_A), dst = NSB + (blockIdx.x ? SM_ST_B : SM_ST_A);
+    for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
+      A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
+      A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
+      A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
+    }
+    if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
+  }
+  grid_sync(B);
+  // ... + one more restricted scan for a split; the merged cluster's final update in both cases
+  {
+    const int q = A.t;
+    PhiJob j[3];
+    int nj = 0;
+    if (same) {
+      alloc_scan(A.zStar, NSB + SM_ST_A, NSB + SM_ST_B, SH_P0, q);
+      for (int side = 0; side < 2; side++)
+        j[nj++] = sm_job_at(NSB, J_P0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+    }
+    j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
+    // the job index enters the Philox counter: keep the merged cluster at index 2 as in the multi-launch path
+    if (!same) {
+      if (blockIdx.x == 2) phi_job_body(A.phi, j[0], 2, sh);
+      grid_sync(B);
+    } else {
+      run_jobs(j, nj);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -630,6 +823,17 @@ static int sm_alloc(smg_chain* ch) {
   } else {
     W->hist_smem = 0;
   }
+  SMG_CUDA(dev_malloc(&W->chain_bar, 2 * sizeof(unsigned), ch->st));
+  SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 2 * sizeof(unsigned), ch->st));
+  {
+    // the persistent chain kernel needs co-resident CTAs (cooperative launch) and the side histograms in shared memory
+    int coop = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ch->device);
+    const char* env = getenv("SMG_SM_PERSISTENT");
+    W->persistent = coop && W->hist_smem > 0 && W->hist_smem <= 64 * 1024 && !(env && env[0] == '0');
+    if (W->persistent)
+      SMG_CUDA(cudaFuncSetAttribute(sm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W->hist_smem));
+  }
   return 0;
 }
 
@@ -637,7 +841,7 @@ static void sm_free(smg_chain* ch) {
   SmWork* W = ch->sm;
   if (!W) return;
   void* ptrs[] = {W->S,       W->zL,      W->zStar, W->zState, W->info,    W->plan,    W->H,      W->cnt,
-                  W->rg_dl,   W->rg_lgt,  W->rowvals, W->partial, W->terms, W->u_pair,  W->u_prior_c, W->u_prior_s,
+                  W->rg_dl,   W->rg_lgt,  W->rowvals, W->partial, W->terms, W->chain_bar, W->u_pair,  W->u_prior_c, W->u_prior_s,
                   W->u_launch, W->u_rg,   W->u_rg_c, W->u_rg_s, W->u_mg_c,  W->u_mg_s,  W->u_accept};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ch->st);
@@ -675,26 +879,8 @@ static int sm_inject(smg_chain* ch, const smg_sm_tape* t) {
   return 0;
 }
 
-// the nine parameter-update jobs of a proposal (hist, current sigma slot, destination slot, count index)
-enum SmJob : int { J_PRI_A = 0, J_PRI_B, J_PRI_M, J_L0, J_L1, J_MG, J_P0, J_P1, J_MSTAR, J_N };
-
 static PhiJob sm_job(smg_chain* ch, int which, uint32_t sub, const double* uc, const double* us, int enable_mode) {
-  const int B = ch->NS;
-  static const int tab[J_N][4] = {{0, 0, SM_SL_A, 0},          {0, 0, SM_SL_B, 0},          {0, 0, SM_ML_M, 0},
-                                  {SH_L0, SM_SL_A, SM_SL_A, SH_L0}, {SH_L1, SM_SL_B, SM_SL_B, SH_L1},
-                                  {SH_M, SM_ML_M, SM_ML_M, SH_M},   {SH_P0, SM_ST_A, SM_ST_A, SH_P0},
-                                  {SH_P1, SM_ST_B, SM_ST_B, SH_P1}, {SH_M, SM_ML_M, SM_ST_M, SH_M}};
-  PhiJob J;
-  J.hist = tab[which][0];
-  J.src = B + tab[which][1];
-  J.dst = B + tab[which][2];
-  J.cnt_idx = tab[which][3];
-  J.sub = sub;
-  J.prior = which <= J_PRI_M;
-  J.enable_mode = enable_mode;
-  J.uc = uc;
-  J.us = us;
-  return J;
+  return sm_job_at(ch->NS, which, sub, uc, us, enable_mode);
 }
 
 // one phi_update launch on up to PHI_MAX_INLINE_JOBS split-merge jobs (one CTA each)
@@ -800,6 +986,50 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
   //      histogram, so update q of it rides in the same launch as the update of scan q
   sm_launch_alloc_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, T.u_launch, mk_key(ch, SUB_SM_LAUNCH), W->zL);
   ch->h_launches++;
+  if (W->persistent && ch->t > 0 && !ch->many) {
+    // ---- the t launch scans, the r merge-launch updates and the proposal as one cooperative kernel
+    SmChainArgs CA;
+    memset(&CA, 0, sizeof(CA));
+    CA.n = n;
+    CA.p = p;
+    CA.pp = pp;
+    CA.mmax = ch->mmax;
+    CA.t = ch->t;
+    CA.r = ch->r;
+    CA.NS = B;
+    CA.X = ch->X;
+    CA.S = W->S;
+    CA.info = W->info;
+    CA.cen = ch->cen[cur];
+    CA.sig = ch->sig[cur];
+    CA.isg = ch->isg[cur];
+    CA.sden = ch->sden[cur];
+    CA.H = W->H;
+    CA.cnt = W->cnt;
+    CA.zL = W->zL;
+    CA.zStar = W->zStar;
+    CA.dl = W->rg_dl;
+    CA.lgt = W->rg_lgt;
+    CA.phi = phi_args_base(ch, 0);
+    CA.phi.H = W->H;
+    CA.phi.counts = W->cnt;
+    CA.phi.njobs = 1;
+    CA.phi.njobs_ptr = nullptr;
+    CA.phi.enable = same;
+    CA.u_rg = T.u_rg;
+    CA.u_rg_c = T.u_rg_c;
+    CA.u_rg_s = T.u_rg_s;
+    CA.u_mg_c = T.u_mg_c;
+    CA.u_mg_s = T.u_mg_s;
+    CA.key = mk_key(ch, 0);
+    CA.bar = W->chain_bar;
+    CA.err = reinterpret_cast<int*>(W->chain_bar + 1);
+    SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 2 * sizeof(unsigned), ch->st));
+    void* kargs[] = {&CA};
+    SMG_CUDA(cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(SM_CHAIN_CTAS), dim3(SM_CHAIN_T), kargs, W->hist_smem,
+                                         ch->st));
+    ch->h_launches++;
+  } else {
   const int nsteps = ch->t > ch->r ? ch->t : ch->r;
   for (int q = 0; q < nsteps; q++) {
     PhiJob j[3];
@@ -833,6 +1063,7 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
                        off(T.u_rg_s, ((size_t)q * 2 + side) * p), 1);
     j[2] = sm_job(ch, J_MSTAR, SUB_SM_MERGE + ch->r, off(T.u_mg_c, (size_t)ch->r * p), off(T.u_mg_s, (size_t)ch->r * p), 0);
     if (sm_phi(ch, j, 3)) return SMG_ERR_CUDA;
+  }
   }
   // ---- MH terms
   sm_gsphi_prior_kernel<<<6, 256, 0, ch->st>>>(pp, p, ch->mmax, ch->attr, ch->v, ch->w, W->H, W->cnt, W->plan, ch->cen[cur],

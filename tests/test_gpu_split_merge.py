@@ -103,7 +103,10 @@ def build_gpu_tape(log, n, p, t, r, ref, c_before):
     return T, labA, labB
 
 
-def run_case(pb, state, seed, t=3, r=3):
+def run_case(pb, state, seed, t=3, r=3, persistent=True):
+    import os
+    # the restricted-scan chain runs either as one cooperative kernel or as a sequence of launches (same results)
+    os.environ["SMG_SM_PERSISTENT"] = "1" if persistent else "0"
     K, c, cen, sig = state
     rng = np.random.default_rng(seed)
     tape = (rng.integers(0, 2**53, size=50 + (t + 3) * pb.n + (2 * t + r + 12) * 2 * pb.p).astype(np.float64) + 0.5) / 2.0**53
@@ -156,8 +159,9 @@ def check_case(pb, ref, got, after, labA, labB):
     assert np.max(rel_err(after["sigmas"], ref["sigma"])) < 1e-9
 
 
+@pytest.mark.parametrize("persistent", [True, False])
 @pytest.mark.parametrize("seed", list(range(1, 13)))
-def test_split_merge_matches_oracle(seed):
+def test_split_merge_matches_oracle(seed, persistent):
     # over-merged state (K_true=6 collapsed to 3 labels) => splits get accepted; seeds hit both branches
     pb = Problem(600, 24, 4, 6, seed=100 + seed, s=0.6)
     K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
@@ -167,7 +171,7 @@ def test_split_merge_matches_oracle(seed):
         state = (K2, c2, cen2, sig2)
     else:
         state = (K, c, cen, sig)
-    ref, got, after, labA, labB = run_case(pb, state, seed)
+    ref, got, after, labA, labB = run_case(pb, state, seed, persistent=persistent)
     check_case(pb, ref, got, after, labA, labB)
 
 
@@ -200,8 +204,9 @@ def test_split_merge_accepts_happen_and_match():
     assert acc_split > 0 and acc_merge > 0
 
 
+@pytest.mark.parametrize("persistent", [True, False])
 @pytest.mark.parametrize("seed", [3, 4])
-def test_split_merge_large_member_set(seed):
+def test_split_merge_large_member_set(seed, persistent):
     # |S| spans several 1024-member chunks of the restricted-scan decision kernel; low-dimensional, noisy data
     # keeps many members non-robust (count-dependent), so both the parallel and the ordered part are exercised
     pb = Problem(3500 if seed % 2 == 0 else 7000, 12, 3, 2, seed=200 + seed, s=0.9)
@@ -209,6 +214,6 @@ def test_split_merge_large_member_set(seed):
     if seed % 2 == 0:  # everything in one cluster => a split proposal over n-2 members
         c = np.zeros_like(c)
         K, cen, sig = 1, cen[:1].copy(), sig[:1].copy()
-    ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=3, r=2)
+    ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=3, r=2, persistent=persistent)
     assert ref["S"].size > 2048
     check_case(pb, ref, got, after, labA, labB)
