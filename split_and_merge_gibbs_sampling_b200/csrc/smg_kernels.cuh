@@ -500,10 +500,9 @@ struct ScanState {
   double lcm1_0[SMG_MAX_ENTRIES];  // log (n0_k - 1)
   double dminus[SMG_MAX_ENTRIES];
   double Dplus;
-  int own[SCAN_CHUNK];  // start-of-pass slot of the chunk's undecided rows
   int evt[SMG_SCAN_WARPS];
   int row[SMG_SCAN_WARPS];
-  unsigned und[SMG_SCAN_WARPS];  // undecided rows of the current chunk (bit per row)
+  unsigned und[4 * SMG_SCAN_WARPS];  // undecided rows of the current block of 4096 observations (bit per row)
   int K, next, err;
   unsigned long long stats[4];
 };
@@ -713,7 +712,8 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 // it copied itself, so cp.async.wait_group is the only synchronisation needed and a chunk with nothing to evaluate
 // costs a barrier, not a memory round trip.
 #define SCAN_PF_DEPTH 8
-#define SCAN_SUPER 4  // chunks screened together by the quiet-stretch fast path
+#define SCAN_SUPER 4  // ring slots (chunks of 1024 observations) screened and evaluated together
+#define SCAN_BLOCK (SCAN_SUPER * SCAN_CHUNK)
 #define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12)
 __device__ __forceinline__ void scan_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -842,66 +842,67 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     return false;
   };
 
-  const int nfull = n / SCAN_CHUNK;  // chunks with SCAN_CHUNK rows
-  int quiet = SCAN_SUPER;            // consecutive chunks without a single undecided row (optimistic start)
-  for (int i0 = 0, chunk = 0; i0 < n && !abort_pass; i0 += SCAN_CHUNK, chunk++) {
-    // ---- quiet stretch: SCAN_SUPER chunks whose rows are all certain non-events cost one barrier together
-    //      (tried only after SCAN_SUPER quiet chunks in a row, so that busy data does not pay for failed attempts)
-    if ((chunk % SCAN_SUPER) == 0 && chunk + SCAN_SUPER <= nfull && quiet >= SCAN_SUPER) {
-      asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_PF_DEPTH - SCAN_SUPER) : "memory");
-      bool any = false;
-#pragma unroll
-      for (int q = 0; q < SCAN_SUPER; q++) {
-        const int slot = (chunk + q) % SCAN_PF_DEPTH;
-        any |= undecided(i0 + q * SCAN_CHUNK + tid, ring_own[slot * SCAN_CHUNK + tid], ring_mg[slot * SCAN_CHUNK + tid]);
-      }
-      if (!__syncthreads_or(any)) {
-#pragma unroll
-        for (int q = 0; q < SCAN_SUPER; q++) issue_chunk(chunk + SCAN_PF_DEPTH + q);
-        if (tid == 0) S.stats[0] += SCAN_SUPER;
-        i0 += (SCAN_SUPER - 1) * SCAN_CHUNK;
-        chunk += SCAN_SUPER - 1;
-        continue;
-      }
-      quiet = 0;
-    }
-    const int nrows = min(SCAN_CHUNK, n - i0);
-    asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_PF_DEPTH - 1) : "memory");  // this chunk's pair has landed
-    const int my_own = ring_own[(chunk % SCAN_PF_DEPTH) * SCAN_CHUNK + tid];
-    const double my_mg = ring_mg[(chunk % SCAN_PF_DEPTH) * SCAN_CHUNK + tid];
-    issue_chunk(chunk + SCAN_PF_DEPTH);  // refill the slot just read (same thread, same addresses)
+  // Blocks of SCAN_SUPER ring slots (SCAN_BLOCK = 4096 observations): thread t screens rows t, t+1024, ...; the
+  // undecided rows of the whole block are evaluated together, so a quiet block costs one barrier and a block with a
+  // handful of undecided rows one evaluation round instead of one per 1024 rows.
+  for (int i0 = 0, blk = 0; i0 < n && !abort_pass; i0 += SCAN_BLOCK, blk++) {
+    const int nrows = min(SCAN_BLOCK, n - i0);
+    asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_PF_DEPTH - SCAN_SUPER) : "memory");  // this block's slots have landed
+    const int slot0 = (blk * SCAN_SUPER) % SCAN_PF_DEPTH;
     SCAN_TICK(0);
-    int start = 0;          // rows [0, start) of the chunk are final
+    int start = 0;          // rows [0, start) of the block are final
     bool screened = false;  // the undecided set below is valid for the current state
     int total_und = 0, consumed = 0;  // undecided rows from `start` on / already evaluated without an event
+    int scr_rows = 0;                 // rows [start, scr_rows) are covered by the current screen
     for (;;) {
-      // ================= screen: one thread per row =================
+      // ================= screen: up to SCAN_SUPER rows per thread =================
+      // In quiet stretches the whole block is screened at once; while events are dense (W small: every event
+      // invalidates the screen) only the 1024-row slice that holds `start` is, the later ones when they are reached.
       if (!screened) {
-        const bool und = (tid >= start && tid < nrows) && undecided(i0 + tid, my_own, my_mg);
-        if (und) S.own[tid] = my_own;
-        const unsigned b = __ballot_sync(SMG_FULL, und);
-        if (lane == 0) S.und[warp] = b;
+        const int q0 = start / SCAN_CHUNK;
+        const int q1 = (W == SMG_SCAN_WARPS) ? SCAN_SUPER : min(SCAN_SUPER, q0 + 1);
+#pragma unroll
+        for (int q = 0; q < SCAN_SUPER; q++) {
+          const int r = q * SCAN_CHUNK + tid;
+          bool und = false;
+          if (q >= q0 && q < q1 && r >= start && r < nrows)
+            und = undecided(i0 + r, ring_own[(slot0 + q) * SCAN_CHUNK + tid], ring_mg[(slot0 + q) * SCAN_CHUNK + tid]);
+          const unsigned b = __ballot_sync(SMG_FULL, und);
+          if (lane == 0) S.und[q * SMG_SCAN_WARPS + warp] = b;  // word w covers rows [32w, 32w + 32) of the block
+        }
+        scr_rows = min(nrows, q1 * SCAN_CHUNK);
         screened = true;
         consumed = 0;
-        total_und = __syncthreads_count(und);
-        if (total_und == 0) {  // every remaining row of the chunk is a certain non-event
-          if (tid == 0) S.stats[0]++;
-          quiet = (start == 0) ? quiet + 1 : 0;
-          break;
-        }
-        quiet = 0;
+        __syncthreads();
+        int pc = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_SUPER; k++) pc += __popc(S.und[SCAN_SUPER * lane + k]);
+        total_und = warp_sum_i(pc);
       }
       SCAN_TICK(1);
-      if (consumed >= total_und) break;
+      if (consumed >= total_und) {  // every screened row from `start` on is final
+        if (scr_rows >= nrows) {
+          if (tid == 0) S.stats[0]++;
+          break;
+        }
+        start = scr_rows;  // go on with the next slice
+        screened = false;
+        __syncthreads();   // S.und is rewritten
+        continue;
+      }
       // ================= batch: the next `nb` undecided rows, one warp each =================
       // (only the warps that evaluate a row run the selection; the others go straight to the barrier)
       const int nb = min(W, total_und - consumed);
       int myrow = -1;
       if (warp < nb) {
-        // lane l: undecided bits of rows [32l, 32l+32) of the chunk, how many undecided rows lie in that word
-        // and how many precede it
-        const unsigned wbits = S.und[lane];
-        const int wpc = __popc(wbits);
+        // lane l owns words SCAN_SUPER*l .. SCAN_SUPER*l + SCAN_SUPER-1 of the undecided bit map
+        unsigned wb[SCAN_SUPER];
+        int wpc = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_SUPER; k++) {
+          wb[k] = S.und[SCAN_SUPER * lane + k];
+          wpc += __popc(wb[k]);
+        }
         int incl = wpc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -910,12 +911,23 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         }
         const int wpref = incl - wpc;
         const int t = consumed + warp;
-        const unsigned hit = __ballot_sync(SMG_FULL, t >= wpref && t < wpref + wpc);
-        const int src = __ffs(hit) - 1;  // exactly one word holds the t-th undecided row
-        unsigned bits = __shfl_sync(SMG_FULL, wbits, src);
-        const int off = t - __shfl_sync(SMG_FULL, wpref, src);
-        for (int q = 0; q < off; q++) bits &= bits - 1;  // drop the `off` lowest set bits
-        myrow = src * 32 + __ffs(bits) - 1;
+        // the lane whose words hold the t-th undecided row locates it; everybody reads the answer from that lane
+        int found = -1;
+        if (t >= wpref && t < wpref + wpc) {
+          int off = t - wpref;
+#pragma unroll
+          for (int k = 0; k < SCAN_SUPER; k++) {
+            const int c = __popc(wb[k]);
+            if (found < 0 && off < c) {
+              unsigned bits = wb[k];
+              for (int q = 0; q < off; q++) bits &= bits - 1;  // drop the `off` lowest set bits
+              found = (SCAN_SUPER * lane + k) * 32 + __ffs(bits) - 1;
+            }
+            off -= c;
+          }
+        }
+        const unsigned hit = __ballot_sync(SMG_FULL, found >= 0);
+        myrow = __shfl_sync(SMG_FULL, found, __ffs(hit) - 1);
       }
       SCAN_TICK(2);
       const int K = S.K;
@@ -924,7 +936,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       if (myrow >= 0 && ne > SMG_MAX_ENTRIES) code = -3;
       if (myrow >= 0 && ne <= SMG_MAX_ENTRIES) {
         const int i = i0 + myrow;
-        const int old_slot = S.own[myrow];
+        const int old_slot = ring_own[(slot0 + myrow / SCAN_CHUNK) * SCAN_CHUNK + (myrow % SCAN_CHUNK)];
         code = (ne <= 64) ? scan_eval_row<2>(A, S, i, old_slot, K, lane) : scan_eval_row_wide(A, S, i, old_slot, K, lane);
       }
       if (lane == 0) {
@@ -1053,7 +1065,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       __syncthreads();
       SCAN_TICK(5);
     }
-    __syncthreads();
+    __syncthreads();  // everybody is done with this block's ring slots
+#pragma unroll
+    for (int q = 0; q < SCAN_SUPER; q++) issue_chunk(blk * SCAN_SUPER + SCAN_PF_DEPTH + q);  // refill them, two blocks ahead
   }
 #ifdef SMG_SCAN_PROFILE
   if (tid == 0 && A.prof) {
