@@ -254,7 +254,8 @@ def main():
     aux_bytes = a.n * a.m_aux * (9.0 * pp + 8.0 + 12.0) + a.n * pp
     aux_ach = aux_bytes / (phase[1] / 1000.0) / 1e9 if phase[1] > 0 else 0.0
     other = {"aux_ll_kernel": {"bound": "hbm", "achieved": aux_ach, "peak": peak, "unit": "GB/s", "frac": aux_ach / peak,
-                               "algorithmic_bytes_per_launch": aux_bytes, "avg_launch_ms": float(phase[1])}}
+                               "algorithmic_bytes_per_launch": aux_bytes, "avg_launch_ms": float(phase[1]),
+                               "note": "runs on a low-priority side stream, overlapped with update_phi + split-merge of the same sweep"}}
     scan = {"ns_per_observation": 1e6 * phase[2] / a.n, "rounds_per_sweep": (st1["scan_rounds"] - st0["scan_rounds"]) / a.steps,
             "events_per_sweep": (st1["scan_events"] - st0["scan_events"]) / a.steps, "avg_ms": float(phase[2])}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

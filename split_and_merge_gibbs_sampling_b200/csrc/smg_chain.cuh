@@ -84,6 +84,8 @@ struct smg_chain {
   cudaStream_t st = nullptr;
   cudaStream_t st_aux = nullptr;  // side stream: auxiliary-component columns of the NEXT pass, behind the split-merge step
   cudaEvent_t ev_scan_done = nullptr, ev_aux_done = nullptr;
+  cudaEvent_t ev_aux_t0 = nullptr, ev_aux_t1 = nullptr;  // device time of the prefetched aux pass (side stream)
+  bool aux_timed = false;
   bool many = false;              // stepped together with other chains: keep every kernel small (no gang-scheduled grids)
   bool aux_ready = false;         // LLaux / aux_e already hold the columns of iteration aux_iter
   long long aux_iter = -1;

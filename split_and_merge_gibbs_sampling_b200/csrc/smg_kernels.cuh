@@ -429,7 +429,7 @@ __device__ __forceinline__ void scan_fill_column(const ScanArgs& A, int slot, in
 }
 
 // thread-block-cluster plumbing of the scan kernel (rank 0 scans, the other CTAs only fill born columns)
-#define SCAN_CLUSTER 8
+#define SCAN_CLUSTER 4
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
