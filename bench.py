@@ -319,7 +319,7 @@ def main():
     # ---- extra: posterior similarity matrix on the tensor cores at the C5 shape (n=2e4), rank 0 only
     if rank == 0 and not a.no_psm:
         from split_and_merge_gibbs_sampling_b200 import Psm
-        npsm, T = 20000, 128
+        npsm, T = 20000, 256
         rng = np.random.default_rng(3)
         lab = rng.integers(0, a.k_true, size=(T, npsm)).astype(np.int32)
         P = Psm(npsm, device=local, capacity_sweeps=T)

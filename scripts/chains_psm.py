@@ -50,7 +50,7 @@ def main():
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     out = mc.run_chains(a.n, a.chains, factory, a.burnin, a.iterations,
-                        psm_factory=(lambda t: Psm(a.n, device=local, capacity_sweeps=128, external=t)),
+                        psm_factory=(lambda t: Psm(a.n, device=local, capacity_sweeps=256, external=t)),
                         dist=dist if world > 1 else None, device=dev, step_many=step_many, psm_mode=a.psm_mode)
     torch.cuda.synchronize()
     secs = time.perf_counter() - t0

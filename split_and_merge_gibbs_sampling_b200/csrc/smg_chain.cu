@@ -642,7 +642,8 @@ static int psm_launch(smg_psm* P) {
   const size_t smem = (size_t)NST * (PSM_M + PSM_N) * KP;
   SMG_CUDA(cudaFuncSetAttribute(psm_accumulate_kernel<KP, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(P->n, PSM_N), cdiv(P->n, PSM_M));
-  psm_accumulate_kernel<KP, NST><<<grid, PSM_THREADS, smem, P->st>>>(P->labels, P->n, P->count, P->psm);
+  const char* mo = getenv("SMG_PSM_MMA_ONLY");
+  psm_accumulate_kernel<KP, NST><<<grid, PSM_THREADS, smem, P->st>>>(P->labels, P->n, P->count, P->psm, (mo && mo[0] == '1') ? 1 : 0);
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
