@@ -748,33 +748,57 @@ int smg_step_many(smg_chain** chains, int count, int n_iters) {
   if (!chains || count < 0) return fail(SMG_ERR_ARG, "bad chain list");
   for (int q = 0; q < count; q++)
     if (!chains[q]) return fail(SMG_ERR_ARG, "chain is NULL");
-  for (int q = 0; q < count; q++) {
-    SMG_CUDA(cudaSetDevice(chains[q]->device));
-    cudaEventRecord(chains[q]->ev_call[0], chains[q]->st);
-  }
-  for (int it = 0; it < n_iters; it++)
-    for (int q = 0; q < count; q++) {
-      SMG_CUDA(cudaSetDevice(chains[q]->device));
-      chains[q]->many = count > 1;
-      int rc = sweep(chains[q], it == n_iters - 1);
-      chains[q]->many = false;
-      if (rc) return rc;
+  // A sweep is ~75 kernel launches and with many chains the host launch rate, not the GPU, bounds the throughput:
+  // the chains are dealt to a few host threads, each launching its share iteration by iteration.
+  const char* env = getenv("SMG_STEP_THREADS");
+  int nthr = env ? atoi(env) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  nthr = std::max(1, std::min(nthr, count));
+  std::vector<int> rcs(nthr, 0);
+  std::vector<std::string> msgs(nthr);
+  auto worker = [&](int w) {
+    for (int q = w; q < count; q += nthr) {
+      if (cudaSetDevice(chains[q]->device) != cudaSuccess) {
+        rcs[w] = SMG_ERR_CUDA;
+        msgs[w] = "cudaSetDevice failed";
+        return;
+      }
+      cudaEventRecord(chains[q]->ev_call[0], chains[q]->st);
     }
-  for (int q = 0; q < count; q++) {
-    SMG_CUDA(cudaSetDevice(chains[q]->device));
-    cudaEventRecord(chains[q]->ev_call[1], chains[q]->st);
-  }
-  int first_err = 0;
-  std::string msg;
-  for (int q = 0; q < count; q++) {
-    int rc = step_finish(chains[q], n_iters);
-    if (rc && !first_err) {
-      first_err = rc;
-      msg = g_last_error;
+    for (int it = 0; it < n_iters; it++)
+      for (int q = w; q < count; q += nthr) {
+        cudaSetDevice(chains[q]->device);
+        chains[q]->many = count > 1;
+        int rc = sweep(chains[q], it == n_iters - 1);
+        chains[q]->many = false;
+        if (rc) {
+          rcs[w] = rc;
+          msgs[w] = g_last_error;
+          return;
+        }
+      }
+    for (int q = w; q < count; q += nthr) {
+      cudaSetDevice(chains[q]->device);
+      cudaEventRecord(chains[q]->ev_call[1], chains[q]->st);
+      int rc = step_finish(chains[q], n_iters);
+      if (rc && !rcs[w]) {
+        rcs[w] = rc;
+        msgs[w] = g_last_error;
+      }
     }
+  };
+  if (nthr == 1) {
+    worker(0);
+  } else {
+    std::vector<std::thread> pool;
+    for (int w = 0; w < nthr; w++) pool.emplace_back(worker, w);
+    for (auto& t : pool) t.join();
   }
-  if (first_err) g_last_error = msg;
-  return first_err;
+  for (int w = 0; w < nthr; w++)
+    if (rcs[w]) {
+      g_last_error = msgs[w];
+      return rcs[w];
+    }
+  return 0;
 }
 
 int smg_snapshot(smg_chain* ch, int* K, int* c_i, double* centers, double* sigmas, int cap_clusters, double* loglik,

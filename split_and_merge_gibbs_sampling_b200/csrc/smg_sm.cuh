@@ -368,7 +368,8 @@ __global__ void sm_hist_add_kernel(int len, int* H, int* cnt, int a, int b, int 
 // multi-launch path: the two are interchangeable bit for bit (tests run both).  Measured at the metric config:
 // 0.73 ms per proposal against 0.85 ms as ~50 launches, with 120 CTAs (24 CTAs: 0.97 ms, the likelihood phase
 // starves).  A gang-scheduled 120-CTA grid does not share the GPU well, so chains that are stepped together
-// (smg_step_many) keep the multi-launch path.
+// (smg_step_many) use a gang of 8 CTAs when they are small (n <= 30000: fewer launches per sweep) and the multi-launch
+// path otherwise.
 // ------------------------------------------------------------------------------------------
 enum SmJob : int { J_PRI_A = 0, J_PRI_B, J_PRI_M, J_L0, J_L1, J_MG, J_P0, J_P1, J_MSTAR, J_N };
 
@@ -986,7 +987,7 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
   //      histogram, so update q of it rides in the same launch as the update of scan q
   sm_launch_alloc_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, T.u_launch, mk_key(ch, SUB_SM_LAUNCH), W->zL);
   ch->h_launches++;
-  if (W->persistent && ch->t > 0 && !ch->many) {
+  if (W->persistent && ch->t > 0 && !(ch->many && n > 30000)) {
     // ---- the t launch scans, the r merge-launch updates and the proposal as one cooperative kernel
     SmChainArgs CA;
     memset(&CA, 0, sizeof(CA));
@@ -1026,8 +1027,10 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.err = reinterpret_cast<int*>(W->chain_bar + 1);
     SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 2 * sizeof(unsigned), ch->st));
     void* kargs[] = {&CA};
-    SMG_CUDA(cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(SM_CHAIN_CTAS), dim3(SM_CHAIN_T), kargs, W->hist_smem,
-                                         ch->st));
+    // grid: enough CTAs for the member-likelihood phase of a single chain; a small gang when several chains share the
+    // GPU (smg_step_many), where the number of launches per sweep matters more than the latency of one proposal
+    const int ctas = ch->many ? 8 : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
+    SMG_CUDA(cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(ctas), dim3(SM_CHAIN_T), kargs, W->hist_smem, ch->st));
     ch->h_launches++;
   } else {
   const int nsteps = ch->t > ch->r ? ch->t : ch->r;
