@@ -52,6 +52,8 @@ static int chain_alloc(smg_chain* ch) {
   }
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_scan_done, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_aux_done, cudaEventDisableTiming));
+  SMG_CUDA(cudaEventCreate(&ch->ev_k1[0]));
+  SMG_CUDA(cudaEventCreate(&ch->ev_k1[1]));
   SMG_CUDA(cudaEventCreate(&ch->ev_aux_t0));
   SMG_CUDA(cudaEventCreate(&ch->ev_aux_t1));
   g_alloc_stream = ch->st;
@@ -119,6 +121,8 @@ static void chain_free(smg_chain* ch) {
     if (ch->ev_call[q]) cudaEventDestroy(ch->ev_call[q]);
   if (ch->ev_scan_done) cudaEventDestroy(ch->ev_scan_done);
   if (ch->ev_aux_done) cudaEventDestroy(ch->ev_aux_done);
+  for (int q = 0; q < 2; q++)
+    if (ch->ev_k1[q]) cudaEventDestroy(ch->ev_k1[q]);
   if (ch->ev_aux_t0) cudaEventDestroy(ch->ev_aux_t0);
   if (ch->ev_aux_t1) cudaEventDestroy(ch->ev_aux_t1);
   if (ch->st_aux) cudaStreamDestroy(ch->st_aux);
@@ -130,6 +134,7 @@ static void chain_free(smg_chain* ch) {
 // phases
 // ------------------------------------------------------------------------------------------
 static int launch_ll_block(smg_chain* ch) {
+  cudaEventRecord(ch->ev_k1[0], ch->st);
   dim3 grid(cdiv(ch->n, LLB_ROWS), cdiv(ch->Kcap, LLB_SLOTS));
   if (ch->mmax <= 7)  // every code fits 3 bits: subset-sum table form
     hamming_ll_block_t16_kernel<<<grid, 256, LLT_SMEM_BYTES, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur],
@@ -138,6 +143,8 @@ static int launch_ll_block(smg_chain* ch) {
   else
     hamming_ll_block_kernel<<<grid, 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], ch->isg[ch->cur],
                                                       ch->sden[ch->cur], ch->K, ch->LL, ch->ldl);
+  cudaEventRecord(ch->ev_k1[1], ch->st);
+  ch->k1_timed = true;
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;
@@ -158,7 +165,11 @@ static int launch_aux_ll(smg_chain* ch, const double* tape, cudaStream_t stream,
 static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   if (!ch->pool_valid) return fail(SMG_ERR_STATE, "auxiliary pool not initialised");
   if (timed) cudaEventRecord(ch->ev[0], ch->st);
-  if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+  // the block of this pass was normally evaluated at the end of the previous iteration (see sweep())
+  if (tape || ch->ll_for_iter != ch->iter) {
+    if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+  }
+  ch->ll_for_iter = -1;  // the pass moves observations: the block no longer matches the state
   if (timed) cudaEventRecord(ch->ev[1], ch->st);
   if (!tape && ch->aux_ready && ch->aux_iter == ch->iter) {
     // the columns were evaluated on the side stream while the previous split-merge step was running
@@ -361,8 +372,20 @@ static int sweep(smg_chain* ch, bool timed) {
     if (rc) return rc;
   }
   if (timed) cudaEventRecord(ch->ev[6], ch->st);
-  int rc = launch_loglik(ch);
-  if (rc) return rc;
+  if (ch->neal8 && (ch->iter + 1) % ch->n8_step == 0) {
+    // The next iteration starts with a Neal-8 pass on exactly this state: evaluate its likelihood block now and read
+    // the full-data log-likelihood (common_functions.cpp:379-401) off it, sum_i LL[i][c_i], instead of a separate pass
+    // over X.
+    if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+    loglik_gather_kernel<<<ch->loglik_blocks, 256, 0, ch->st>>>(ch->LL, ch->ldl, ch->c, ch->n, ch->partial);
+    reduce_final_kernel<<<1, 256, 0, ch->st>>>(ch->partial, ch->loglik_blocks, ch->loglik_d);
+    ch->h_launches += 2;
+    SMG_CUDA(cudaGetLastError());
+    ch->ll_for_iter = ch->iter + 1;
+  } else {
+    int rc = launch_loglik(ch);
+    if (rc) return rc;
+  }
   if (timed) cudaEventRecord(ch->ev[7], ch->st);
   ch->iter++;
   ch->h_sweeps++;
@@ -723,6 +746,15 @@ static int step_finish(smg_chain* ch, int n_iters) {
     ms = 0;
     cudaEventElapsedTime(&ms, ch->ev[0], ch->ev[7]);
     ch->h_timings[7] = ms;
+    if (ch->k1_timed) {
+      // the likelihood block is launched either at the start of the pass or (normally) at the end of the previous
+      // iteration, inside the [6]-[7] interval: report it as phase [0] and take it out of the log-likelihood phase
+      ms = 0;
+      cudaEventElapsedTime(&ms, ch->ev_k1[0], ch->ev_k1[1]);
+      const bool in_tail = ch->ll_for_iter == ch->iter;
+      ch->h_timings[0] = ms;
+      if (in_tail) ch->h_timings[6] = std::max(0.0, ch->h_timings[6] - (double)ms);
+    }
     if (ch->aux_timed && cudaEventSynchronize(ch->ev_aux_t1) == cudaSuccess) {
       // the aux columns of the next pass ran on the side stream, overlapped with the split-merge step
       ms = 0;
@@ -1045,6 +1077,7 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
 int smg_debug_set_state(smg_chain* ch, int K, const int* c_i, const double* centers, const double* sigmas) {
   if (!ch || !c_i || !centers || !sigmas) return fail(SMG_ERR_ARG, "NULL argument");
   if (K < 1 || K > ch->Kcap) return fail(SMG_ERR_CAPACITY, "K out of range");
+  ch->ll_for_iter = -1;  // the state is about to change outside a sweep: the cached likelihood block is stale
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   std::vector<uint8_t> hc((size_t)K * ch->pp, 0);
@@ -1193,6 +1226,7 @@ int smg_debug_histogram(smg_chain* ch, int* H, int* counts, int* mmax_out) {
 
 int smg_debug_update_phi(smg_chain* ch, const double* u_center, const double* u_sigma) {
   if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  ch->ll_for_iter = -1;  // the state is about to change outside a sweep: the cached likelihood block is stale
   SMG_CUDA(cudaSetDevice(ch->device));
   int rc = sync_status(ch);
   if (rc) return rc;
@@ -1291,6 +1325,7 @@ int smg_debug_rhig_u(int count, double v, double w, double m, unsigned long long
 int smg_debug_split_merge(smg_chain* ch, const smg_sm_tape* tape, int* info, int* S, int* z_launch, int* z_star,
                           double* phi_out, double* terms) {
   if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  ch->ll_for_iter = -1;  // the state is about to change outside a sweep: the cached likelihood block is stale
   SMG_CUDA(cudaSetDevice(ch->device));
   int rc = sync_status(ch);
   if (rc) return rc;

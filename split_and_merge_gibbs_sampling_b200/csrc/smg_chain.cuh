@@ -86,6 +86,9 @@ struct smg_chain {
   cudaEvent_t ev_scan_done = nullptr, ev_aux_done = nullptr;
   cudaEvent_t ev_aux_t0 = nullptr, ev_aux_t1 = nullptr;  // device time of the prefetched aux pass (side stream)
   bool aux_timed = false;
+  long long ll_for_iter = -1;      // the LL block holds the columns of the state at the start of this iteration (-1: stale)
+  cudaEvent_t ev_k1[2] = {};      // device time of the likelihood-block kernel wherever in the sweep it was launched
+  bool k1_timed = false;
   bool many = false;              // stepped together with other chains: keep every kernel small (no gang-scheduled grids)
   bool aux_ready = false;         // LLaux / aux_e already hold the columns of iteration aux_iter
   long long aux_iter = -1;

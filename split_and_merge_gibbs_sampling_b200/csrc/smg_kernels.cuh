@@ -1538,6 +1538,21 @@ __global__ void __launch_bounds__(256) loglik_partial_kernel(const uint8_t* __re
     partial[blockIdx.x] = t;
   }
 }
+// the same sum read off a likelihood block that was evaluated for exactly this state: sum_i LL[i][c_i]
+// (the block of the next pass is computed right after the split-merge step, see sweep())
+__global__ void __launch_bounds__(256) loglik_gather_kernel(const double* __restrict__ LL, int ldl, const int* __restrict__ c,
+                                                            int n, double* __restrict__ partial) {
+  __shared__ double sh[256];
+  double acc = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) acc += LL[(size_t)i * ldl + c[i]];
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
 __global__ void __launch_bounds__(256) reduce_final_kernel(const double* __restrict__ partial, int np,
                                                            double* __restrict__ out) {
   __shared__ double sh[256];
