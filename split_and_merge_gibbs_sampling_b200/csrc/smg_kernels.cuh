@@ -504,6 +504,7 @@ struct ScanState {
   int row[SMG_SCAN_WARPS];
   unsigned und[4 * SMG_SCAN_WARPS];  // undecided rows of the current block of 4096 observations (bit per row)
   int K, next, err;
+  int serial_next;  // first row after a serial stretch of warp 0
   unsigned long long stats[4];
 };
 
@@ -712,6 +713,8 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 // it copied itself, so cp.async.wait_group is the only synchronisation needed and a chunk with nothing to evaluate
 // costs a barrier, not a memory round trip.
 #define SCAN_PF_DEPTH 8
+#define SCAN_DENSE_ENTER 6    // events in a row at the head of their batch before warp 0 goes serial
+#define SCAN_DENSE_LEAVE 48   // rows in a row without a move before it hands back to the block
 #define SCAN_SUPER 4  // ring slots (chunks of 1024 observations) screened and evaluated together
 #define SCAN_BLOCK (SCAN_SUPER * SCAN_CHUNK)
 #define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12)
@@ -725,6 +728,44 @@ __device__ __forceinline__ void scan_cp_async8(void* smem, const void* gmem) {
 // more than 64 entries per draw: rare, kept out of line so that its registers do not weigh on the scan kernel
 __device__ __noinline__ int scan_eval_row_wide(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane) {
   return scan_eval_row<SMG_EPL>(A, S, i, old_slot, K, lane);
+}
+
+// State update for a draw that moves observation `ie` from `old_slot` to the existing cluster of entry `new_e`
+// (cases 1 and 2 of neal8.cpp:107-137).  One thread; the caller orders it against the readers of the state.
+__device__ __forceinline__ void scan_apply_move(const ScanArgs& A, ScanState& S, int K0, int ie, int old_slot, int new_e) {
+  const int Kc = S.K;
+  const int new_slot = S.l2s[new_e];
+  const bool singleton = (S.cnt[old_slot] == 1);
+  S.stats[1]++;
+  A.c[ie] = new_slot;
+  // drift bookkeeping of a start-of-pass cluster whose count just changed
+  auto drift = [&](int s) {
+    if (s >= K0) return;
+    S.dminus[s] = (S.cnt[s] > 1) ? (S.lcm1_0[s] - S.logcm1[s]) : CUDART_INF;
+    const double dp = S.logc[s] - S.lc0[s];
+    if (dp > S.Dplus) S.Dplus = dp;  // monotone upper bound
+  };
+  S.cnt[new_slot]++;
+  S.logcm1[new_slot] = S.logc[new_slot];
+  S.logc[new_slot] = log((double)S.cnt[new_slot]);
+  drift(new_slot);
+  if (!singleton) {  // case 1 (neal8.cpp:107-112)
+    int c0 = --S.cnt[old_slot];
+    S.logc[old_slot] = S.logcm1[old_slot];
+    S.logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
+    drift(old_slot);
+  } else {  // case 2 (neal8.cpp:115-137): last label moves into the hole
+    S.cnt[old_slot] = 0;
+    S.logc[old_slot] = S.logcm1[old_slot] = -CUDART_INF;
+    int lab = S.s2l[old_slot];
+    int last_slot = S.l2s[Kc - 1];
+    S.l2s[lab] = last_slot;
+    S.s2l[last_slot] = lab;
+    S.s2l[old_slot] = -1;
+    if (lab == Kc - 1) S.s2l[last_slot] = -1;  // the dying cluster was the last label
+    S.K = Kc - 1;
+    S.stats[3]++;
+  }
 }
 
 // =============================================================================
@@ -790,6 +831,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   __syncthreads();
   bool abort_pass = false;
   int W = SMG_SCAN_WARPS;  // rows evaluated per round
+  int dense_run = 0;        // consecutive events found at the head of their batch
   // phase cycle counters of thread 0 (compile with -DSMG_SCAN_PROFILE): [0] chunk prologue, [1] screen,
   // [2] batch pick, [3] evaluation, [4] event detection, [5] event application, [6] whole loop
 #ifdef SMG_SCAN_PROFILE
@@ -855,6 +897,50 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     int total_und = 0, consumed = 0;  // undecided rows from `start` on / already evaluated without an event
     int scr_rows = 0;                 // rows [start, scr_rows) are covered by the current screen
     for (;;) {
+      // ================= serial stretch: one warp, no block barriers =================
+      // While nearly every observation moves (burn-in from a random start) speculation over a batch buys nothing
+      // and every event costs several block barriers.  After SCAN_DENSE_ENTER events in a row at the head of their
+      // batch, warp 0 walks the rows one at a time on its own -- evaluate, apply, next -- until a stretch of
+      // SCAN_DENSE_LEAVE rows without a move, the end of the block, or a draw the block must handle together
+      // (a new cluster: its column is filled by the whole cluster of CTAs; an error).
+      if (dense_run >= SCAN_DENSE_ENTER && S.K + m <= 64) {
+        __syncthreads();
+        if (warp == 0) {
+          int r = start, calm = 0;
+          while (r < nrows && calm < SCAN_DENSE_LEAVE) {
+            const int own = ring_own[(slot0 + r / SCAN_CHUNK) * SCAN_CHUNK + (r % SCAN_CHUNK)];
+            const double mg = ring_mg[(slot0 + r / SCAN_CHUNK) * SCAN_CHUNK + (r % SCAN_CHUNK)];
+            int code = EVT_NONE;
+            if (undecided(i0 + r, own, mg)) {
+              const int K = S.K;
+              if (K + m > 64) break;
+              code = scan_eval_row<2>(A, S, i0 + r, own, K, lane);
+              if (code != EVT_NONE && (code < 0 || code >= K)) break;  // left to the block: row r is evaluated again
+            }
+            if (code == EVT_NONE) {
+              calm++;
+            } else {
+              if (lane == 0) {
+                S.stats[0]++;
+                scan_apply_move(A, S, K0, i0 + r, own, code);
+              }
+              __syncwarp();
+              calm = 0;
+            }
+            r++;
+          }
+          if (lane == 0) S.serial_next = r;
+        }
+        __syncthreads();
+        start = S.serial_next;
+        dense_run = 0;
+        W = SMG_SCAN_WARPS;
+        screened = false;
+        if (start >= nrows) {
+          if (tid == 0) S.stats[0]++;
+          break;
+        }
+      }
       // ================= screen: up to SCAN_SUPER rows per thread =================
       // In quiet stretches the whole block is screened at once; while events are dense (W small: every event
       // invalidates the screen) only the 1024-row slice that holds `start` is, the later ones when they are reached.
@@ -951,6 +1037,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       if (evm == 0) {
         if (tid == 0) S.stats[0]++;
         consumed += nb;
+        dense_run = 0;
         W = SMG_SCAN_WARPS;  // quiet: speculate over a full batch again
         __syncthreads();     // S.evt / S.row are rewritten by the next round
         SCAN_TICK(4);
@@ -960,6 +1047,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       const int first = __ffs(evm) - 1;
       // event-dense stretches (burn-in): evaluating 32 rows per round only burns issue slots
       W = min(SMG_SCAN_WARPS, max(4, 2 * (first + 1)));
+      dense_run = (first == 0) ? dense_run + 1 : 0;
       const int new_e = __shfl_sync(SMG_FULL, ev, first);
       const int erow = S.row[first];
       const int ie = i0 + erow;
@@ -1005,38 +1093,17 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       __syncthreads();  // everyone has read the pre-event state
       if (tid == 0) {
         S.stats[0]++;
-        S.stats[1]++;
-        A.c[ie] = new_slot;
-        // drift bookkeeping of a start-of-pass cluster whose count just changed
-        auto drift = [&](int s) {
-          if (s >= K0) return;
-          S.dminus[s] = (S.cnt[s] > 1) ? (S.lcm1_0[s] - S.logcm1[s]) : CUDART_INF;
-          const double dp = S.logc[s] - S.lc0[s];
-          if (dp > S.Dplus) S.Dplus = dp;  // monotone upper bound
-        };
         if (new_e < Kc) {
-          S.cnt[new_slot]++;
-          S.logcm1[new_slot] = S.logc[new_slot];
-          S.logc[new_slot] = log((double)S.cnt[new_slot]);
-          drift(new_slot);
-          if (!singleton) {  // case 1 (neal8.cpp:107-112)
-            int c0 = --S.cnt[old_slot];
-            S.logc[old_slot] = S.logcm1[old_slot];
-            S.logcm1[old_slot] = c0 > 1 ? log((double)(c0 - 1)) : -CUDART_INF;
-            drift(old_slot);
-          } else {  // case 2 (neal8.cpp:115-137): last label moves into the hole
-            S.cnt[old_slot] = 0;
-            S.logc[old_slot] = S.logcm1[old_slot] = -CUDART_INF;
-            int lab = S.s2l[old_slot];
-            int last_slot = S.l2s[Kc - 1];
-            S.l2s[lab] = last_slot;
-            S.s2l[last_slot] = lab;
-            S.s2l[old_slot] = -1;
-            if (lab == Kc - 1) S.s2l[last_slot] = -1;  // the dying cluster was the last label
-            S.K = Kc - 1;
-            S.stats[3]++;
-          }
+          scan_apply_move(A, S, K0, ie, old_slot, new_e);
         } else {
+          S.stats[1]++;
+          A.c[ie] = new_slot;
+          auto drift = [&](int s) {
+            if (s >= K0) return;
+            S.dminus[s] = (S.cnt[s] > 1) ? (S.lcm1_0[s] - S.logcm1[s]) : CUDART_INF;
+            const double dp = S.logc[s] - S.lc0[s];
+            if (dp > S.Dplus) S.Dplus = dp;  // monotone upper bound
+          };
           S.next = new_slot + 1;
           S.cnt[new_slot] = 1;
           S.logc[new_slot] = 0.0;
