@@ -1,0 +1,51 @@
+"""Driver options of run_markov_chain (code/launcher.cpp:85-154): n8_step_size, sam_step_size, neal8 / split_merge
+switches, capacity errors.  In every mode the snapshot must satisfy the reference's validate_state invariant and its
+log-likelihood must be reproducible by the oracle from the snapshot itself (1e-12 relative)."""
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from helpers import Problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_snapshot(pb, s):
+    K, c = s["K"], s["c_i"]
+    assert c.min() == 0 and c.max() == K - 1 and len(np.unique(c)) == K
+    ll = orc.loglik(pb.od, c, s["centers"], s["sigmas"])
+    assert abs(ll - s["loglikelihood"]) <= 1e-12 * abs(ll)
+
+
+@pytest.mark.parametrize("kw", [dict(n8_step_size=2, sam_step_size=3), dict(n8_step_size=3, sam_step_size=1),
+                                dict(neal8=False, split_merge=True), dict(neal8=True, split_merge=False),
+                                dict(t=0, r=0), dict(t=4, r=1), dict(t=1, r=5)])
+def test_step_sizes_and_switches(kw):
+    pb = Problem(1800, 40, 4, 5, seed=71, s=0.9)
+    ch = pb.chain(L=7, c_i=None, compact_init=True, seed=72, **kw)
+    for _ in range(9):
+        ch.step(1)
+        _check_snapshot(pb, ch.snapshot())
+    ch.close()
+
+
+def test_step_many_iterations_equals_one_at_a_time():
+    pb = Problem(1500, 32, 4, 5, seed=73)
+    a = pb.chain(L=6, c_i=None, compact_init=True, seed=74, n8_step_size=2)
+    b = pb.chain(L=6, c_i=None, compact_init=True, seed=74, n8_step_size=2)
+    a.step(7)
+    for _ in range(7):
+        b.step(1)
+    sa, sb = a.snapshot(), b.snapshot()
+    assert sa["K"] == sb["K"] and np.array_equal(sa["c_i"], sb["c_i"]) and sa["loglikelihood"] == sb["loglikelihood"]
+    assert np.array_equal(sa["sigmas"], sb["sigmas"])
+    a.close()
+    b.close()
+
+
+def test_cluster_capacity_error_is_reported():
+    from split_and_merge_gibbs_sampling_b200 import SmgError
+    # every observation its own cluster, capacity far below n
+    pb = Problem(64, 8, 3, 3, seed=75, s=1.5)
+    with pytest.raises(SmgError):
+        pb.chain(c_i=np.arange(64, dtype=np.int32), max_clusters=16)
