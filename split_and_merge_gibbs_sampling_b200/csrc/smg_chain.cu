@@ -239,7 +239,8 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
 // re-drawn (launcher.cpp:123-129).
 static int prefetch_next_aux(smg_chain* ch) {
   const long long next_iter = ch->iter + ch->n8_step;
-  if (!ch->neal8 || ch->iter % 1000 == 0) return 0;
+  static const bool disabled = [] { const char* e = getenv("SMG_NO_AUX_PREFETCH"); return e && e[0] == '1'; }();
+  if (disabled || !ch->neal8 || ch->iter % 1000 == 0) return 0;
   // an iteration in between that re-draws the pool would invalidate the columns
   for (long long it = ch->iter + 1; it < next_iter; it++)
     if (it % 1000 == 0) return 0;

@@ -49,3 +49,21 @@ def test_cluster_capacity_error_is_reported():
     pb = Problem(64, 8, 3, 3, seed=75, s=1.5)
     with pytest.raises(SmgError):
         pb.chain(c_i=np.arange(64, dtype=np.int32), max_clusters=16)
+
+
+def test_long_run_crosses_the_pool_refresh():
+    """1100 iterations: the auxiliary pool is re-drawn at iteration 1000 (launcher.cpp:123-129).  The chain must stay
+    valid, and a second chain from the same seed stepped in different call sizes must agree bit for bit (the aux
+    columns of the next pass are prefetched on a side stream; the refresh must not race them)."""
+    pb = Problem(700, 24, 4, 4, seed=81, s=0.9)
+    a = pb.chain(L=5, c_i=None, compact_init=True, seed=82)
+    b = pb.chain(L=5, c_i=None, compact_init=True, seed=82)
+    a.step(1100)
+    for k in (999, 1, 1, 99):
+        b.step(k)
+    sa, sb = a.snapshot(), b.snapshot()
+    _check_snapshot(pb, sa)
+    assert sa["K"] == sb["K"] and np.array_equal(sa["c_i"], sb["c_i"]) and sa["loglikelihood"] == sb["loglikelihood"]
+    assert np.array_equal(sa["sigmas"], sb["sigmas"])
+    a.close()
+    b.close()
