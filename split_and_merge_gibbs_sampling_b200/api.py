@@ -112,6 +112,18 @@ class Chain:
     def step(self, n_iters=1):
         lb.check(self.lib.smg_step(self.h, int(n_iters)))
 
+    def checkpoint(self):
+        """State needed to continue this chain later: iteration counter + snapshot (see `resume`)."""
+        it = C.c_longlong()
+        lb.check(self.lib.smg_get_iteration(self.h, C.byref(it)))
+        s = self.snapshot()
+        return {"iteration": it.value, "K": s["K"], "c_i": s["c_i"], "centers": s["centers"], "sigmas": s["sigmas"]}
+
+    def resume(self, ckpt):
+        """Continue from `checkpoint()` of a chain created with the same data, configuration and seed."""
+        self.set_state(ckpt["K"], ckpt["c_i"], ckpt["centers"], ckpt["sigmas"])
+        lb.check(self.lib.smg_resume_at(self.h, int(ckpt["iteration"])))
+
     def last_step_ms(self):
         ms = C.c_double()
         lb.check(self.lib.smg_last_step_ms(self.h, C.byref(ms)))

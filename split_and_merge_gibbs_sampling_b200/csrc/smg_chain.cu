@@ -335,9 +335,10 @@ static int launch_loglik(smg_chain* ch) {
 }
 
 // aux pool (launcher.cpp:67-77, re-drawn at iter % 1000 == 0, :123-129)
-static int draw_pool(smg_chain* ch) {
+static int draw_pool(smg_chain* ch, long long epoch_iter = -1) {
   long long total = ch->pool_size * ch->pp;
   RngKey key = mk_key(ch, SUB_POOL);
+  if (epoch_iter >= 0) key.sweep = (uint32_t)epoch_iter;  // re-create the pool of an earlier refresh (resume)
   pool_draw_kernel<<<cdiv(total, 128), 128, 0, ch->st>>>(ch->pool_size, ch->pp, ch->p, ch->attr, ch->v, ch->w, key, ch->sigma_exact, ch->pcen,
                                                         ch->psig, ch->pisg, ch->pden);
   pool_sden_kernel<<<cdiv(ch->pool_size * 32, 256), 256, 0, ch->st>>>(ch->pool_size, ch->pp, ch->pden, ch->psden);
@@ -875,6 +876,29 @@ int smg_get_stats(smg_chain* ch, unsigned long long* out8) {
   out8[6] = ch->h_sm_props;
   out8[7] = d[7];
   return 0;
+}
+
+// Checkpoint / resume (the reference has none: SURVEY section 5).  A chain is a deterministic function of
+// (seed, iteration, allocation, parameters): smg_get_iteration + smg_snapshot save it; on a chain created with the same
+// data, configuration and seed, smg_debug_set_state followed by smg_resume_at continues bit for bit -- the auxiliary
+// pool is re-drawn from the Philox key of the refresh (launcher.cpp:123-129) that was current at `iteration`.
+int smg_get_iteration(smg_chain* ch, long long* iteration) {
+  if (!ch || !iteration) return fail(SMG_ERR_ARG, "NULL argument");
+  *iteration = ch->iter;
+  return 0;
+}
+int smg_resume_at(smg_chain* ch, long long iteration) {
+  if (!ch || iteration < 0) return fail(SMG_ERR_ARG, "bad argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st_aux));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  ch->iter = iteration;
+  ch->ll_for_iter = -1;
+  ch->aux_ready = false;
+  const long long epoch = ((iteration - 1) / 1000) * 1000;  // iteration r (r % 1000 == 0) re-draws the pool AFTER its pass
+  int rc = draw_pool(ch, epoch < 0 ? 0 : epoch);
+  if (rc) return rc;
+  return sync_status(ch);
 }
 
 int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {

@@ -67,3 +67,23 @@ def test_long_run_crosses_the_pool_refresh():
     assert np.array_equal(sa["sigmas"], sb["sigmas"])
     a.close()
     b.close()
+
+
+def test_checkpoint_resume_is_bit_exact():
+    """A chain resumed from (iteration, snapshot) on a fresh handle continues exactly like the uninterrupted one,
+    also across the pool refresh at iteration 1000 (the reference has no checkpointing)."""
+    pb = Problem(600, 24, 4, 4, seed=91, s=0.9)
+    kw = dict(L=5, c_i=None, compact_init=True, seed=92)
+    a = pb.chain(**kw)
+    a.step(997)
+    ck = a.checkpoint()
+    assert ck["iteration"] == 997
+    a.step(40)
+    b = pb.chain(**kw)
+    b.resume(ck)
+    b.step(40)
+    sa, sb = a.snapshot(), b.snapshot()
+    assert sa["K"] == sb["K"] and np.array_equal(sa["c_i"], sb["c_i"]) and sa["loglikelihood"] == sb["loglikelihood"]
+    assert np.array_equal(sa["centers"], sb["centers"]) and np.array_equal(sa["sigmas"], sb["sigmas"])
+    a.close()
+    b.close()
