@@ -42,7 +42,7 @@ class SmgSmTape(C.Structure):
 
 EXPORTS = [
     "smg_last_error", "smg_device_count", "smg_run_markov_chain", "smg_free_results", "smg_create", "smg_create_u8",
-    "smg_step", "smg_step_many", "smg_get_iteration", "smg_resume_at", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
+    "smg_step", "smg_step_many", "smg_get_iteration", "smg_resume_at", "smg_validate_state", "smg_synth_generate", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
     "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
     "smg_debug_split_merge", "smg_debug_scan_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
@@ -82,6 +82,9 @@ def load():
     lib.smg_step.argtypes = [C.c_void_p, C.c_int]
     lib.smg_step_many.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
     lib.smg_get_iteration.argtypes = [C.c_void_p, c_ll_p]
+    lib.smg_validate_state.argtypes = [C.c_void_p]
+    lib.smg_synth_generate.argtypes = [C.c_int, C.c_int, c_int_p, C.c_int, C.c_double, C.c_ulonglong, C.c_int,
+                                       C.POINTER(C.c_ubyte), c_int_p, C.POINTER(C.c_ubyte)]
     lib.smg_resume_at.argtypes = [C.c_void_p, C.c_longlong]
     lib.smg_snapshot.argtypes = [C.c_void_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, C.c_int, c_dbl_p, c_int_p]
     lib.smg_destroy.argtypes = [C.c_void_p]

@@ -112,6 +112,10 @@ class Chain:
     def step(self, n_iters=1):
         lb.check(self.lib.smg_step(self.h, int(n_iters)))
 
+    def validate_state(self):
+        """The reference's validate_state invariant on the device state; raises SmgError on failure."""
+        lb.check(self.lib.smg_validate_state(self.h))
+
     def checkpoint(self):
         """State needed to continue this chain later: iteration counter + snapshot (see `resume`)."""
         it = C.c_longlong()
@@ -226,6 +230,18 @@ class Chain:
         return {"i1": int(info[0]), "i2": int(info[1]), "nS": nS, "is_split": int(info[3]), "accepted": int(info[4]),
                 "nA": int(info[5]), "nB": int(info[6]), "K": int(info[7]), "S": S[:nS].copy(), "z_launch": zl[:nS].copy(),
                 "z_star": zs[:nS].copy(), "phi": phi, "terms": terms}
+
+
+def synth_generate(n, p, attrisize, k_true, s=0.5, seed=1, device=0):
+    """Synthetic Hamming-mixture data generated on the GPU (smg_synth_generate): X uint8 [n][p], labels, centres."""
+    lib = lb.load()
+    attr = lb.as_i32(np.full(p, attrisize) if np.isscalar(attrisize) else attrisize)
+    X = np.empty((n, p), dtype=np.uint8)
+    lab = np.empty(n, dtype=np.int32)
+    cen = np.empty((k_true, p), dtype=np.uint8)
+    lb.check(lib.smg_synth_generate(int(n), int(p), lb.iptr(attr), int(k_true), float(s), int(seed) & (2**64 - 1), int(device),
+                                    X.ctypes.data_as(C.POINTER(C.c_ubyte)), lb.iptr(lab), cen.ctypes.data_as(C.POINTER(C.c_ubyte))))
+    return X, lab, cen, attr
 
 
 def step_many(chains, n_iters=1):

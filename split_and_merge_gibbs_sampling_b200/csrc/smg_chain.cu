@@ -901,6 +901,74 @@ int smg_resume_at(smg_chain* ch, long long iteration) {
   return sync_status(ch);
 }
 
+// validate_state (common_functions.cpp:146-172) of the current state; the reference runs it after every move
+int smg_validate_state(smg_chain* ch) {
+  if (!ch) return fail(SMG_ERR_ARG, "chain is NULL");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int* tmp = nullptr;
+  SMG_CUDA(dev_malloc(&tmp, (size_t)ch->Kcap * sizeof(int), ch->st));
+  SMG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)ch->Kcap * sizeof(int), ch->st));
+  validate_recount_kernel<<<cdiv(ch->n, 256), 256, 0, ch->st>>>(ch->c, ch->n, ch->K, tmp, ch->status);
+  validate_compare_kernel<<<cdiv(ch->Kcap, 256), 256, 0, ch->st>>>(ch->K, ch->Kcap, tmp, ch->counts, ch->status);
+  ch->h_launches += 2;
+  SMG_CUDA(cudaGetLastError());
+  cudaFreeAsync(tmp, ch->st);
+  return sync_status(ch);
+}
+
+// synthetic Hamming-mixture data generated on `device` and copied back: X [n][p] codes 1..attrisize[j], labels [n]
+// (components as equal as possible, interleaved), centres [k_true][p]
+int smg_synth_generate(int n, int p, const int* attrisize, int k_true, double s, unsigned long long seed, int device,
+                       unsigned char* X_out, int* labels_out, unsigned char* centres_out) {
+  if (n < 1 || p < 1 || !attrisize || k_true < 1 || k_true > 255 || !(s > 0) || !X_out || !labels_out || !centres_out)
+    return fail(SMG_ERR_ARG, "bad argument");
+  for (int j = 0; j < p; j++)
+    if (attrisize[j] < 2 || attrisize[j] > SMG_MAX_LEVELS) return fail(SMG_ERR_ARG, "attrisize[j] must be in 2..64");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(SMG_ERR_ARG, "bad device ordinal");
+  SMG_CUDA(cudaSetDevice(device));
+  const int pp = (p + 15) / 16 * 16;
+  // labels and centres are tiny host-side draws from the same Philox generator
+  std::vector<int> lab(n);
+  std::vector<uint8_t> cen((size_t)k_true * pp, 0);
+  for (int i = 0; i < n; i++) lab[i] = i % k_true;
+  RngKey key;
+  key.k0 = (uint32_t)seed;
+  key.k1 = (uint32_t)(seed >> 32);
+  key.sweep = 0;
+  key.sub = 0;
+  for (int k = 0; k < k_true; k++)
+    for (int j = 0; j < p; j++) {
+      uint32_t r[4];
+      philox4x32_10((uint32_t)k, (uint32_t)j, 78u, 0u, key.k0, key.k1, r);
+      cen[(size_t)k * pp + j] = (uint8_t)(1 + r[0] % (uint32_t)attrisize[j]);
+    }
+  std::vector<int> attr(pp, 2);
+  std::copy(attrisize, attrisize + p, attr.begin());
+  int *d_attr = nullptr, *d_lab = nullptr;
+  uint8_t *d_cen = nullptr, *d_X = nullptr;
+  SMG_CUDA(cudaMalloc(&d_attr, (size_t)pp * 4));
+  SMG_CUDA(cudaMalloc(&d_lab, (size_t)n * 4));
+  SMG_CUDA(cudaMalloc(&d_cen, cen.size()));
+  SMG_CUDA(cudaMalloc(&d_X, (size_t)n * pp));
+  SMG_CUDA(cudaMemcpy(d_attr, attr.data(), (size_t)pp * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(d_lab, lab.data(), (size_t)n * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(d_cen, cen.data(), cen.size(), cudaMemcpyHostToDevice));
+  synth_generate_kernel<<<cdiv((long long)n * pp, 256), 256>>>(n, p, pp, d_attr, d_cen, d_lab, s, key, d_X);
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaMemcpy2D(X_out, p, d_X, pp, p, n, cudaMemcpyDeviceToHost));
+  cudaFree(d_attr);
+  cudaFree(d_lab);
+  cudaFree(d_cen);
+  cudaFree(d_X);
+  std::copy(lab.begin(), lab.end(), labels_out);
+  for (int k = 0; k < k_true; k++)
+    for (int j = 0; j < p; j++) centres_out[(size_t)k * p + j] = cen[(size_t)k * pp + j];
+  return 0;
+}
+
 int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
   if (!ch || !out8) return fail(SMG_ERR_ARG, "NULL argument");
   SMG_CUDA(cudaSetDevice(ch->device));

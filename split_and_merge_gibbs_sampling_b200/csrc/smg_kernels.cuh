@@ -1707,6 +1707,52 @@ __global__ void pool_sden_kernel(long long pool_size, int pp, const double* __re
   if (lane == 0) psden[w] = acc;
 }
 
+// validate_state (common_functions.cpp:146-172): #unique(c_i) == total_cls == number of parameter vectors, i.e.
+// every label lies in [0, K), every label in [0, K) is used, and the maintained member counts are the true ones.
+// Two kernels: recount (integer atomics into `tmp`, zeroed by the caller), then compare.
+__global__ void validate_recount_kernel(const int* __restrict__ c, int n, const int* __restrict__ Kptr, int* tmp, int* status) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int k = c[i];
+  if (k < 0 || k >= *Kptr)
+    atomicOr(status, ST_VALIDATE);
+  else
+    atomicAdd(&tmp[k], 1);
+}
+__global__ void validate_compare_kernel(const int* __restrict__ Kptr, int kcap, const int* __restrict__ tmp,
+                                        const int* __restrict__ counts, int* status) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kcap) return;
+  const int K = *Kptr;
+  if (K < 1 || K > kcap) atomicOr(status, ST_VALIDATE);
+  if (k < K ? (tmp[k] <= 0 || tmp[k] != counts[k]) : (tmp[k] != 0)) atomicOr(status, ST_VALIDATE);
+}
+
+// Synthetic Hamming-mixture data on the device (spec: code/old_code/data_generation.R:1-101, ham_mix_gen):
+// x_ij = c_kj with probability 1/(1+(m_j-1)exp(-1/s)), otherwise one of the other levels uniformly; k = label of i.
+__global__ void synth_generate_kernel(int n, int p, int pp, const int* __restrict__ attr, const uint8_t* __restrict__ cent,
+                                      const int* __restrict__ labels, double s, RngKey key, uint8_t* __restrict__ X) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * pp) return;
+  const int i = (int)(t / pp), j = (int)(t % pp);
+  uint8_t o = 0;
+  if (j < p) {
+    const int m = attr[j];
+    const int c = cent[(size_t)labels[i] * pp + j];
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)j, 77u, key.sweep, key.k0, key.k1, r);
+    const double u = u01_from_bits(r[0], r[1]);
+    const double pm = 1.0 / (1.0 + ((double)m - 1.0) * exp(-1.0 / s));
+    if (u < pm) {
+      o = (uint8_t)c;
+    } else {
+      const int shift = 1 + (int)(r[2] % (uint32_t)(m - 1));  // a uniformly chosen other level
+      o = (uint8_t)((c - 1 + shift) % m + 1);
+    }
+  }
+  X[t] = o;
+}
+
 // initial labels: sample(L, n, replace) - 1 (common_functions.cpp:174-183)
 __global__ void init_assign_kernel(int n, int L, const double* __restrict__ u_inj, RngKey key, int* __restrict__ c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

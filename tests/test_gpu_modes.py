@@ -87,3 +87,22 @@ def test_checkpoint_resume_is_bit_exact():
     assert np.array_equal(sa["centers"], sb["centers"]) and np.array_equal(sa["sigmas"], sb["sigmas"])
     a.close()
     b.close()
+
+
+def test_validate_state_and_device_generator():
+    from split_and_merge_gibbs_sampling_b200 import Chain, synth_generate
+    n, p, m, kt, s = 6000, 48, 5, 6, 0.5
+    X, lab, cen, attr = synth_generate(n, p, m, kt, s=s, seed=5)
+    assert X.min() >= 1 and X.max() <= m and np.array_equal(np.bincount(lab), np.full(kt, n // kt))
+    match = (X == cen[lab]).mean()
+    pm = 1.0 / (1.0 + (m - 1) * np.exp(-1.0 / s))
+    assert abs(match - pm) < 4 * np.sqrt(pm * (1 - pm) / (n * p))  # match rate of the spec (data_generation.R)
+    other = X[X != cen[lab]]
+    assert other.size > 0 and len(np.unique(other)) == m
+    ch = Chain(X, attr, 1.0, np.full(p, 6.0), np.full(p, 0.25), m=3, L=kt, seed=3, compact_init=True, data_u8=True)
+    for _ in range(6):
+        ch.step(1)
+        ch.validate_state()  # common_functions.cpp:146-172 on the device state
+    from sklearn.metrics import adjusted_rand_score
+    assert adjusted_rand_score(lab, ch.snapshot(with_phi=False)["c_i"]) > 0.95
+    ch.close()
