@@ -535,8 +535,10 @@ static int init_state(smg_chain* ch, const int* c_init, int compact_init) {
   if (rc) return rc;
   rc = update_phi_all(ch, SUB_INIT_PHI + 1, nullptr, nullptr);
   if (rc) return rc;
-  rc = draw_pool(ch);
-  if (rc) return rc;
+  if (!ch->pool_valid) {  // normally already drawn by create_impl, under the upload
+    rc = draw_pool(ch);
+    if (rc) return rc;
+  }
   return sync_status(ch);
 }
 
@@ -694,7 +696,10 @@ static int create_impl(const smg_config* cfg, const double* dcol, const unsigned
   smg_chain* ch = nullptr;
   int rc = create_common(cfg, &ch);
   if (rc) return rc;
-  rc = dcol ? upload_colmajor(ch, dcol) : upload_u8(ch, du8);
+  // the initial auxiliary pool (launcher.cpp:67-77) depends on the hyper-parameters only: draw it first so that the
+  // device works while the host packs and uploads the data
+  rc = draw_pool(ch);
+  if (!rc) rc = dcol ? upload_colmajor(ch, dcol) : upload_u8(ch, du8);
   if (!rc) rc = init_state(ch, c_init, cfg->compact_init);
   if (rc) {
     std::string keep = g_last_error;

@@ -1098,7 +1098,15 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     // grid: enough CTAs for the member-likelihood phase of a single chain; a small gang when several chains share the
     // GPU (smg_step_many), where the number of launches per sweep matters more than the latency of one proposal
     const int ctas = ch->many ? 8 : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
-    SMG_CUDA(cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(ctas), dim3(SM_CHAIN_T), kargs, W->chain_smem, ch->st));
+    const cudaError_t ce =
+        cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(ctas), dim3(SM_CHAIN_T), kargs, W->chain_smem, ch->st);
+    if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources) {
+      // the gang does not fit next to whatever else runs on this device: use the sequence of launches from now on
+      (void)cudaGetLastError();
+      W->persistent = false;
+      return sm_step(ch, tape);
+    }
+    SMG_CUDA(ce);
     ch->h_launches++;
   } else {
   const int nsteps = ch->t > ch->r ? ch->t : ch->r;
