@@ -542,6 +542,10 @@ static int init_state(smg_chain* ch, const int* c_init, int compact_init) {
   return sync_status(ch);
 }
 
+}  // namespace smg
+static int pinned_acquire(size_t bytes, uint8_t** out, int which);
+static void pinned_release(uint8_t* p);
+namespace smg {
 // R's column-major fp64 matrix -> row-major padded u8 codes.  Small inputs are copied as they are and converted
 // (and validated) on the device; large ones are packed by host threads first, which moves 8x fewer bytes over
 // PCIe from pageable memory (205 MB -> 25.6 MB at the metric shape).
@@ -565,7 +569,9 @@ static int upload_colmajor(smg_chain* ch, const double* data) {
     if (hbad) return fail(SMG_ERR_ARG, std::to_string(hbad) + " data entries are not integer codes in 1..attrisize[j]");
     return 0;
   }
-  std::vector<uint8_t> buf((size_t)n * pp);
+  // packed into a cached page-locked buffer: no page faults after the first call and a faster copy
+  uint8_t* buf = nullptr;
+  if (pinned_acquire((size_t)n * pp, &buf, 1)) return fail(SMG_ERR_CUDA, "cudaHostAlloc of the upload staging buffer failed");
   const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
   std::vector<long long> nbad(nthr, 0);
   std::vector<std::thread> pool;
@@ -599,9 +605,14 @@ static int upload_colmajor(smg_chain* ch, const double* data) {
   for (auto& t : pool) t.join();
   long long hbad = 0;
   for (long long b : nbad) hbad += b;
-  if (hbad) return fail(SMG_ERR_ARG, std::to_string(hbad) + " data entries are not integer codes in 1..attrisize[j]");
-  SMG_CUDA(cudaMemcpyAsync(ch->X, buf.data(), buf.size(), cudaMemcpyHostToDevice, ch->st));
-  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  if (hbad) {
+    pinned_release(buf);
+    return fail(SMG_ERR_ARG, std::to_string(hbad) + " data entries are not integer codes in 1..attrisize[j]");
+  }
+  cudaError_t ce = cudaMemcpyAsync(ch->X, buf, (size_t)n * pp, cudaMemcpyHostToDevice, ch->st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(ch->st);
+  pinned_release(buf);
+  SMG_CUDA(ce);
   return 0;
 }
 
@@ -625,31 +636,37 @@ using namespace smg;
 // cudaHostAlloc / cudaFreeHost cost milliseconds to >100 ms per call (measured), far more than the run
 // itself at small iteration counts.  A second concurrent caller simply allocates its own.
 static std::mutex g_pin_mu;
-static uint8_t* g_pin_buf = nullptr;
-static size_t g_pin_size = 0;
-static bool g_pin_busy = false;
-static int pinned_acquire(size_t bytes, uint8_t** out) {
+struct PinSlot {
+  uint8_t* buf = nullptr;
+  size_t size = 0;
+  bool busy = false;
+};
+static PinSlot g_pin[2];  // 0: snapshot ring of smg_run_markov_chain, 1: packed data of upload_colmajor
+static int pinned_acquire(size_t bytes, uint8_t** out, int which) {
   std::lock_guard<std::mutex> lk(g_pin_mu);
-  if (!g_pin_busy) {
-    if (g_pin_size < bytes) {
-      if (g_pin_buf) cudaFreeHost(g_pin_buf);
-      g_pin_buf = nullptr;
-      g_pin_size = 0;
-      if (cudaHostAlloc((void**)&g_pin_buf, bytes, cudaHostAllocDefault) != cudaSuccess) return 1;
-      g_pin_size = bytes;
+  PinSlot& P = g_pin[which];
+  if (!P.busy) {
+    if (P.size < bytes) {
+      if (P.buf) cudaFreeHost(P.buf);
+      P.buf = nullptr;
+      P.size = 0;
+      if (cudaHostAlloc((void**)&P.buf, bytes, cudaHostAllocDefault) != cudaSuccess) return 1;
+      P.size = bytes;
     }
-    g_pin_busy = true;
-    *out = g_pin_buf;
+    P.busy = true;
+    *out = P.buf;
     return 0;
   }
   return cudaHostAlloc((void**)out, bytes, cudaHostAllocDefault) != cudaSuccess;
 }
 static void pinned_release(uint8_t* p) {
   std::lock_guard<std::mutex> lk(g_pin_mu);
-  if (p == g_pin_buf)
-    g_pin_busy = false;
-  else if (p)
-    cudaFreeHost(p);
+  for (PinSlot& P : g_pin)
+    if (p == P.buf) {
+      P.busy = false;
+      return;
+    }
+  if (p) cudaFreeHost(p);
 }
 
 struct smg_psm {
@@ -1069,10 +1086,11 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
     cudaEvent_t ev;
     long long result_slot;
   };
-  const size_t slot_bytes = 64 + (size_t)n * 4 + (((size_t)Kcap * pp + 63) & ~(size_t)63) + (size_t)Kcap * pp * 8;
+  const size_t c_bytes = ((size_t)n * 4 + 63) & ~(size_t)63;  // every region of a slot starts 64-byte aligned
+  const size_t slot_bytes = 64 + c_bytes + (((size_t)Kcap * pp + 63) & ~(size_t)63) + (size_t)Kcap * pp * 8;
   uint8_t* pinned = nullptr;
   auto th0 = std::chrono::steady_clock::now();
-  if (pinned_acquire(slot_bytes * RING, &pinned)) {
+  if (pinned_acquire(slot_bytes * RING, &pinned, 0)) {
     smg_destroy(ch);
     smg_free_results(out);
     return fail(SMG_ERR_CUDA, "cudaHostAlloc of the snapshot ring failed");
@@ -1084,11 +1102,23 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
     ring[q].hdr = (int*)base;
     ring[q].ll = (double*)(base + 16);
     ring[q].c = (int*)(base + 64);
-    ring[q].cen = base + 64 + (size_t)n * 4;
+    ring[q].cen = base + 64 + c_bytes;
     ring[q].sig = (double*)(ring[q].cen + (((size_t)Kcap * pp + 63) & ~(size_t)63));
     ring[q].result_slot = -1;
     cudaEventCreateWithFlags(&ring[q].ev, cudaEventDisableTiming);
   }
+  const size_t cen_off = 64 + c_bytes, sig_off = cen_off + (((size_t)Kcap * pp + 63) & ~(size_t)63);
+  unsigned char* dstage = nullptr;  // device-side staging blocks, one per ring slot
+  cudaStream_t st_copy = nullptr;
+  cudaEvent_t ev_packed[RING];
+  if (dev_malloc(&dstage, slot_bytes * RING, ch->st) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking) != cudaSuccess) {
+    pinned_release(pinned);
+    smg_destroy(ch);
+    smg_free_results(out);
+    return fail(SMG_ERR_CUDA, "allocation of the snapshot staging failed");
+  }
+  for (int q = 0; q < RING; q++) cudaEventCreateWithFlags(&ev_packed[q], cudaEventDisableTiming);
   auto consume = [&](Slot& S) -> int {
     if (S.result_slot < 0) return 0;
     if (cudaEventSynchronize(S.ev) != cudaSuccess) return fail(SMG_ERR_CUDA, "snapshot copy failed");
@@ -1124,14 +1154,14 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
       rc = consume(S);  // results are appended in order: the slot's previous occupant is RING snapshots old
       if (rc) break;
       const int cur = ch->cur;
-      cudaMemcpyAsync(&S.hdr[0], ch->K, 4, cudaMemcpyDeviceToHost, ch->st);
-      cudaMemcpyAsync(&S.hdr[1], ch->status, 4, cudaMemcpyDeviceToHost, ch->st);
-      cudaMemcpyAsync(&S.hdr[2], ch->accepted_d, 4, cudaMemcpyDeviceToHost, ch->st);
-      cudaMemcpyAsync(S.ll, ch->loglik_d, 8, cudaMemcpyDeviceToHost, ch->st);
-      cudaMemcpyAsync(S.c, ch->c, (size_t)n * 4, cudaMemcpyDeviceToHost, ch->st);
-      cudaMemcpyAsync(S.cen, ch->cen[cur], (size_t)Kcap * pp, cudaMemcpyDeviceToHost, ch->st);
-      cudaMemcpyAsync(S.sig, ch->sig[cur], (size_t)Kcap * pp * 8, cudaMemcpyDeviceToHost, ch->st);
-      if (cudaEventRecord(S.ev, ch->st) != cudaSuccess) {
+      unsigned char* dslot = dstage + slot_bytes * (nkept % RING);
+      snapshot_pack_kernel<<<148, 256, 0, ch->st>>>(ch->K, ch->status, ch->accepted_d, ch->loglik_d, ch->c, n, ch->cen[cur],
+                                                    ch->sig[cur], Kcap * pp, cen_off, sig_off, dslot);
+      ch->h_launches++;
+      cudaEventRecord(ev_packed[nkept % RING], ch->st);
+      cudaStreamWaitEvent(st_copy, ev_packed[nkept % RING], 0);
+      cudaMemcpyAsync(pinned + slot_bytes * (nkept % RING), dslot, slot_bytes, cudaMemcpyDeviceToHost, st_copy);
+      if (cudaEventRecord(S.ev, st_copy) != cudaSuccess) {
         rc = fail(SMG_ERR_CUDA, "cudaEventRecord failed");
         break;
       }
@@ -1151,8 +1181,14 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
     std::copy(cen.begin(), cen.end(), out->centers);
     std::copy(sg.begin(), sg.end(), out->sigmas);
   }
+  cudaStreamSynchronize(st_copy);
   cudaStreamSynchronize(ch->st);
-  for (int q = 0; q < RING; q++) cudaEventDestroy(ring[q].ev);
+  for (int q = 0; q < RING; q++) {
+    cudaEventDestroy(ring[q].ev);
+    cudaEventDestroy(ev_packed[q]);
+  }
+  cudaStreamDestroy(st_copy);
+  cudaFreeAsync(dstage, ch->st);
   auto tf0 = std::chrono::steady_clock::now();
   pinned_release(pinned);
   const double unpin_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - tf0).count();

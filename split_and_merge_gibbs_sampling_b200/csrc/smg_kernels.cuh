@@ -1753,6 +1753,31 @@ __global__ void synth_generate_kernel(int n, int p, int pp, const int* __restric
   X[t] = o;
 }
 
+// Snapshot of one kept iteration (launcher.cpp:140-153) gathered into ONE contiguous staging block on the device, so
+// that it leaves with a single copy on a side stream while the next sweep already runs:
+// [0] K, status, accepted (ints) | [16] log-likelihood | [64] c_i[n] | centres [Kcap][pp] u8 | sigmas [Kcap][pp] f64
+__global__ void snapshot_pack_kernel(const int* __restrict__ Kptr, const int* __restrict__ status,
+                                     const int* __restrict__ accepted, const double* __restrict__ loglik,
+                                     const int* __restrict__ c, int n, const uint8_t* __restrict__ cen,
+                                     const double* __restrict__ sig, int rows_pp, size_t cen_off, size_t sig_off,
+                                     unsigned char* __restrict__ out) {
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  if (t0 == 0) {
+    int* h = reinterpret_cast<int*>(out);
+    h[0] = *Kptr;
+    h[1] = *status;
+    h[2] = *accepted;
+    *reinterpret_cast<double*>(out + 16) = *loglik;
+  }
+  int* oc = reinterpret_cast<int*>(out + 64);
+  for (size_t i = t0; i < (size_t)n; i += stride) oc[i] = c[i];
+  const uint32_t* cs = reinterpret_cast<const uint32_t*>(cen);
+  uint32_t* od = reinterpret_cast<uint32_t*>(out + cen_off);
+  for (size_t i = t0; i < (size_t)rows_pp / 4; i += stride) od[i] = cs[i];  // pp is a multiple of 16
+  double* os = reinterpret_cast<double*>(out + sig_off);
+  for (size_t i = t0; i < (size_t)rows_pp; i += stride) os[i] = sig[i];
+}
+
 // initial labels: sample(L, n, replace) - 1 (common_functions.cpp:174-183)
 __global__ void init_assign_kernel(int n, int L, const double* __restrict__ u_inj, RngKey key, int* __restrict__ c) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
