@@ -806,8 +806,11 @@ int smg_step_many(smg_chain** chains, int count, int n_iters) {
     if (!chains[q]) return fail(SMG_ERR_ARG, "chain is NULL");
   // A sweep is ~75 kernel launches and with many chains the host launch rate, not the GPU, bounds the throughput:
   // the chains are dealt to a few host threads, each launching its share iteration by iteration.
+  // (large chains keep the GPU busy from one launching thread; measured at n=1e5 more threads only add contention)
   const char* env = getenv("SMG_STEP_THREADS");
-  int nthr = env ? atoi(env) : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+  int nmax = 0;
+  for (int q = 0; q < count; q++) nmax = std::max(nmax, chains[q]->n);
+  int nthr = env ? atoi(env) : (nmax > 50000 ? 1 : (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
   nthr = std::max(1, std::min(nthr, count));
   std::vector<int> rcs(nthr, 0);
   std::vector<std::string> msgs(nthr);
