@@ -203,6 +203,17 @@ __global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restri
 // first scans after the random launch allocation (small likelihood differences) that leaves many more members to the
 // ordered walk: 2048-member chunks measured 0.84 ms per proposal against 0.72 ms with one member per thread.
 #define SM_DECIDE_R 1
+// ... so only the scans after the first two (sides settled, large likelihood differences) use wide chunks:
+#define SM_DECIDE_WIDE_CHUNK 2048
+#define SM_DECIDE_WIDE_FROM 2
+static int g_sm_wide_from = -1;
+static inline int sm_wide_from() {
+  if (g_sm_wide_from < 0) {
+    const char* e = getenv("SMG_SM_WIDE_FROM");
+    g_sm_wide_from = e ? atoi(e) : SM_DECIDE_WIDE_FROM;
+  }
+  return g_sm_wide_from;
+}
 template <int N>
 struct RdecideSmem {  // per-member scratch of one chunk (only the non-robust members are read back)
   double d0[N], lg[N];
@@ -385,11 +396,16 @@ __device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const 
 __global__ void __launch_bounds__(SM_DECIDE_T) sm_rdecide_kernel(const SmInfo* info, const double* __restrict__ dl,
                                                                  const double* __restrict__ lgt, int* __restrict__ z,
                                                                  int* __restrict__ Hzero, int hlen, int* __restrict__ cnt2,
-                                                                 const int* enable, int enable_val) {
+                                                                 const int* enable, int enable_val, int wide) {
   if (enable && *enable != enable_val) return;
   extern __shared__ __align__(16) unsigned char s_rd_raw[];
-  RdecideSmem<SM_DECIDE_T * SM_DECIDE_R>& M = *reinterpret_cast<RdecideSmem<SM_DECIDE_T * SM_DECIDE_R>*>(s_rd_raw);
-  sm_rdecide_body<SM_DECIDE_T, SM_DECIDE_R>(info->nS, dl, lgt, z, Hzero, hlen, cnt2, M);
+  if (wide) {
+    RdecideSmem<SM_DECIDE_WIDE_CHUNK>& M = *reinterpret_cast<RdecideSmem<SM_DECIDE_WIDE_CHUNK>*>(s_rd_raw);
+    sm_rdecide_body<SM_DECIDE_T, SM_DECIDE_WIDE_CHUNK / SM_DECIDE_T>(info->nS, dl, lgt, z, Hzero, hlen, cnt2, M);
+  } else {
+    RdecideSmem<SM_DECIDE_T * SM_DECIDE_R>& M = *reinterpret_cast<RdecideSmem<SM_DECIDE_T * SM_DECIDE_R>*>(s_rd_raw);
+    sm_rdecide_body<SM_DECIDE_T, SM_DECIDE_R>(info->nS, dl, lgt, z, Hzero, hlen, cnt2, M);
+  }
 }
 
 // proposal = copy of the split launch state (sides and the two parameter slots), split_merge.cpp:575-577
@@ -477,7 +493,7 @@ __device__ __forceinline__ void grid_sync(GridBar& B) {
 }
 
 struct SmChainArgs {
-  int n, p, pp, mmax, t, r, NS;
+  int n, p, pp, mmax, t, r, NS, wide_from;
   const uint8_t* X;
   const int* S;
   const SmInfo* info;
@@ -500,6 +516,7 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
   // (never live at the same time)
   extern __shared__ __align__(16) int s_hist[];
   RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>& M = *reinterpret_cast<RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>*>(s_hist);
+  RdecideSmem<SM_DECIDE_WIDE_CHUNK>& MW = *reinterpret_cast<RdecideSmem<SM_DECIDE_WIDE_CHUNK>*>(s_hist);
   __shared__ double sh[256];
   GridBar B{A.bar, 0u, gridDim.x, A.err, A.phi.status};
   const int nS = A.info->nS, same = A.info->same;
@@ -528,8 +545,13 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
                     nwarps);
     grid_sync(B);
     CHAIN_TICK(4);
-    if (blockIdx.x == 0)
-      sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_R>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
+    if (blockIdx.x == 0) {
+      if (q >= A.wide_from)
+        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_WIDE_CHUNK / SM_CHAIN_T>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len),
+                                                                       A.cnt + h0, MW);
+      else
+        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_R>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
+    }
     grid_sync(B);
     CHAIN_TICK(5);
     subset_hist_body(A.X, pp, A.S, nS, z, &A.info->i1, A.mmax, A.H + (size_t)h0 * len, nullptr, s_hist, blockIdx.x,
@@ -888,7 +910,7 @@ static int sm_alloc(smg_chain* ch) {
     W->hist_smem = 0;
   }
   SMG_CUDA(cudaFuncSetAttribute(sm_rdecide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)sizeof(RdecideSmem<SM_DECIDE_T * SM_DECIDE_R>)));
+                                (int)sizeof(RdecideSmem<SM_DECIDE_WIDE_CHUNK>)));
   SMG_CUDA(dev_malloc(&W->chain_bar, 2 * sizeof(unsigned), ch->st));
   SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 2 * sizeof(unsigned), ch->st));
   {
@@ -899,7 +921,7 @@ static int sm_alloc(smg_chain* ch) {
     W->persistent = coop && W->hist_smem > 0 && W->hist_smem <= 64 * 1024 && !(env && env[0] == '0');
     if (W->persistent)
     {
-      W->chain_smem = std::max(W->hist_smem, sizeof(RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>));
+      W->chain_smem = std::max(W->hist_smem, sizeof(RdecideSmem<SM_DECIDE_WIDE_CHUNK>));
       SMG_CUDA(cudaFuncSetAttribute(sm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W->chain_smem));
     }
   }
@@ -1004,8 +1026,9 @@ static int sm_restricted_alloc(smg_chain* ch, int* z, int slotA, int slotB, int 
   const size_t len = (size_t)ch->pp * ch->mmax;
   sm_ll2prep_kernel<<<296, 256, 0, ch->st>>>(ch->X, ch->pp, W->S, W->info, ch->cen[cur], ch->isg[cur], ch->sden[cur], slotA,
                                             slotB, u_rg, mk_key(ch, SUB_SM_RG + q), W->rg_dl, W->rg_lgt, enable, 1);
-  sm_rdecide_kernel<<<1, SM_DECIDE_T, sizeof(RdecideSmem<SM_DECIDE_T * SM_DECIDE_R>), ch->st>>>(W->info, W->rg_dl, W->rg_lgt, z, W->H + (size_t)h0 * len, (int)(2 * len),
-                                                   W->cnt + h0, enable, 1);
+  sm_rdecide_kernel<<<1, SM_DECIDE_T, sizeof(RdecideSmem<SM_DECIDE_WIDE_CHUNK>), ch->st>>>(
+      W->info, W->rg_dl, W->rg_lgt, z, W->H + (size_t)h0 * len, (int)(2 * len), W->cnt + h0, enable, 1,
+      q >= sm_wide_from() ? 1 : 0);
   ch->h_launches += 2;
   SMG_CUDA(cudaGetLastError());
   return sm_hist(ch, z, h0, true, enable);
@@ -1066,6 +1089,7 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.t = ch->t;
     CA.r = ch->r;
     CA.NS = B;
+    CA.wide_from = sm_wide_from();
     CA.X = ch->X;
     CA.S = W->S;
     CA.info = W->info;
