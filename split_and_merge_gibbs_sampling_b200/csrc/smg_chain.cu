@@ -73,7 +73,12 @@ static int chain_alloc(smg_chain* ch) {
     SMG_CUDA(cudaMemsetAsync(ch->isg[b], 0, (size_t)NST * pp * 8, ch->st));
     SMG_CUDA(cudaMemsetAsync(ch->sden[b], 0, (size_t)NST * 8, ch->st));
   }
-  if (dalloc(&ch->den, (size_t)NST * pp)) return SMG_ERR_CUDA;
+  if (dalloc(&ch->den, (size_t)NST * pp) || dalloc(&ch->phi_cnt, NST)) return SMG_ERR_CUDA;
+  SMG_CUDA(cudaMemsetAsync(ch->phi_cnt, 0, (size_t)NST * 4, ch->st));
+  {
+    const char* e = getenv("SMG_PHI_PARTS");
+    ch->phi_parts = phi_parts_for(pp, e ? atoi(e) : pp / 64);
+  }
   if (dalloc(&ch->c, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
       dalloc(&ch->slot2label, NST))
     return SMG_ERR_CUDA;
@@ -299,6 +304,9 @@ PhiArgs phi_args_base(smg_chain* ch, uint32_t sub) {
   A.sigma_exact = ch->sigma_exact;
   A.status = ch->status;
   A.prof = ch->scan_prof + 8;
+  A.nparts = 1;
+  A.den = ch->den;
+  A.part_cnt = ch->phi_cnt;
   return A;
 }
 
@@ -309,7 +317,8 @@ static int update_phi_all(smg_chain* ch, uint32_t sub, const double* uc, const d
   A.u_center = uc;
   A.u_sigma = us;
   A.prior = 0;
-  phi_update_kernel<<<ch->Kcap, 256, 0, ch->st>>>(A);
+  A.nparts = ch->phi_parts;
+  phi_update_kernel<<<ch->Kcap * A.nparts, 256, 0, ch->st>>>(A);
   ch->h_launches += 1;
   SMG_CUDA(cudaGetLastError());
   return 0;

@@ -98,6 +98,8 @@ struct smg_chain {
   uint8_t* cen[2] = {nullptr, nullptr};
   double *sig[2] = {nullptr, nullptr}, *isg[2] = {nullptr, nullptr}, *sden[2] = {nullptr, nullptr};
   double* den = nullptr;
+  int* phi_cnt = nullptr;  // finished parts per destination slot of a split parameter-update job
+  int phi_parts = 1;       // CTAs per job in phi_update_kernel
   int cur = 0;
   int *c = nullptr, *K = nullptr, *counts = nullptr, *counts_slot = nullptr, *slot2label = nullptr;
   double *LL = nullptr, *LLaux = nullptr, *mrg = nullptr;

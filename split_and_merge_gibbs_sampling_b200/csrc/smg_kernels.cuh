@@ -1362,8 +1362,19 @@ struct PhiJob {
 
 #define PHI_MAX_INLINE_JOBS 4
 
+// A job may be split over several CTAs ("parts" of consecutive attributes, a multiple of 32 each): the draws are a
+// long double-precision dependency chain per attribute, so spreading them over more SMs shortens the job.
+__host__ __device__ inline int phi_part_chunk(int pp, int nparts) { return (((pp + nparts - 1) / nparts) + 31) & ~31; }
+__host__ __device__ inline int phi_parts_for(int pp, int want) {
+  const int chunk = phi_part_chunk(pp, want < 1 ? 1 : want);
+  return (pp + chunk - 1) / chunk;
+}
+
 struct PhiArgs {
   int pp, p, mmax;
+  int nparts;     // CTAs per job
+  double* den;    // [slots][pp] per-attribute log-normalisers (scratch of the split jobs)
+  int* part_cnt;  // [slots] finished parts of the job writing that slot (self-resetting)
   const int* attr;
   const double* v;
   const double* w;
@@ -1458,21 +1469,23 @@ __device__ __forceinline__ int draw_center(const int* __restrict__ h, int nk, do
 // log-normalisers in a fixed order into sden[dst].
 // One parameter-update job executed by one CTA (any block size >= 256: the first 256 threads draw, everybody
 // takes part in the barriers of the final reduction).  `sh` = 256 doubles of shared memory.
-__device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, int job, double* sh) {
+__device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, int job, int part, int nparts, double* sh) {
   RngKey key = A.key;
   key.sub = J.sub;
   const int nk = J.prior ? 0 : A.counts[J.cnt_idx];
   if (!J.prior && nk == 0) return;  // empty cluster: untouched (common_functions.cpp:547)
-  double acc = 0.0;
+  const int chunk = phi_part_chunk(A.pp, nparts);
+  const int j1 = min(A.pp, (part + 1) * chunk);
 #ifdef SMG_PHI_PROFILE
   long long tp0 = clock64(), tp1 = tp0, tp2 = tp0;
 #endif
-  for (int j = threadIdx.x; j < A.pp && threadIdx.x < 256; j += 256) {
+  for (int j = part * chunk + threadIdx.x; j < j1; j += blockDim.x) {
     const size_t o = (size_t)J.dst * A.pp + j;
     if (j >= A.p) {  // padding attributes
       A.cen[o] = 0;
       A.sig[o] = 1.0;
       A.isg[o] = 0.0;
+      A.den[o] = 0.0;
       continue;
     }
     const int m = A.attr[j];
@@ -1508,7 +1521,7 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
     A.cen[o] = (uint8_t)center;
     A.sig[o] = sigma;
     A.isg[o] = 1.0 / sigma;
-    acc += hamming_den(sigma, m);
+    A.den[o] = hamming_den(sigma, m);
   }
 #ifdef SMG_PHI_PROFILE
   if (threadIdx.x == 0 && A.prof) {
@@ -1519,7 +1532,23 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
     atomicAdd(&A.prof[3], 1ull);
   }
 #endif
-  if (threadIdx.x < 256) sh[threadIdx.x] = acc;
+  // the CTA that finishes the job last sums the normalisers of all attributes, always in the same order
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = nparts > 1 ? atomicAdd(&A.part_cnt[J.dst], 1) + 1 : 1;
+    s_last = done == nparts;
+    if (s_last && nparts > 1) A.part_cnt[J.dst] = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double acc = 0.0;
+  if (threadIdx.x < 256) {
+    for (int j = threadIdx.x; j < A.p; j += 256) acc += __ldcg(&A.den[(size_t)J.dst * A.pp + j]);
+    sh[threadIdx.x] = acc;
+  }
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
@@ -1530,7 +1559,8 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
 
 
 __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
-  const int job = blockIdx.x;
+  // grid = jobs x A.nparts, parts of one job strided by the job count
+  const int njg = gridDim.x / A.nparts, job = blockIdx.x % njg, part = blockIdx.x / njg;
   PhiJob J;
   if (A.njobs > 0) {
     if (job >= A.njobs) return;
@@ -1547,7 +1577,7 @@ __global__ void __launch_bounds__(256) phi_update_kernel(PhiArgs A) {
     J.us = A.u_sigma ? A.u_sigma + (size_t)job * A.u_stride : nullptr;
   }
   __shared__ double sh[256];
-  phi_job_body(A, J, job, sh);
+  phi_job_body(A, J, job, part, A.nparts, sh);
 }
 
 // derive isg / den / sden from (cen, sig) for slots [0, nslots): used after host uploads

@@ -190,9 +190,9 @@ __global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restri
 }
 
 // The sequential part, one CTA.  Inside a chunk of 1024 members the running side counts can only move by
-// the chunk's own population, which bounds the log-count term of D; a member whose D clears |logit(u)|
-// over that whole interval lands on the side of sign(d0) no matter what happened before it ("robust").
-// Per chunk: robust members are decided in
+// the chunk's own population, which bounds the log-count term of D; a member whose D stays on one side of
+// every decision threshold over that whole interval lands on the same side no matter what happened before
+// it ("robust").  Per chunk: robust members are decided in
 // parallel, a block prefix sum gives the count contribution of the robust members before every
 // position, and only the non-robust members are walked in order by one warp (32 at a time against the
 // same counts; the first one that changes side is applied and evaluation restarts after it).  Same
@@ -214,6 +214,17 @@ static inline int sm_wide_from() {
   }
   return g_sm_wide_from;
 }
+// Interval of D = (log n_1 + LL_1) - (log n_2 + LL_2) a value falls in, for logit(u) = lg; even intervals decide side 1,
+// odd ones side 0 (the rule of the ordered walk below: the larger side iff |D| >= logit u, ties in D to side 1).
+__device__ __forceinline__ int sm_d_region(double D, double lg) {
+  if (lg <= 0.0) return D > 0.0 ? 3 : 0;
+  return D >= lg ? 3 : (D > 0.0 ? 2 : (D > -lg ? 1 : 0));
+}
+// log((nS+1-b)/b) in single precision (absolute error below 1e-5 for nS < 2^31); callers widen it by SM_DC_MARGIN
+#define SM_DC_MARGIN 1e-4
+__device__ __forceinline__ double sm_dc_bound(int nS, int b) {
+  return (double)(logf((float)(nS + 1 - b)) - logf((float)b));
+}
 template <int N>
 struct RdecideSmem {  // per-member scratch of one chunk (only the non-robust members are read back)
   double d0[N], lg[N];
@@ -229,6 +240,19 @@ __device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const 
                                                 int* cnt2, RdecideSmem<T * R>& M) {
   constexpr int N = T * R;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // this thread's members of the next two chunks (loads run two chunks ahead of the decisions)
+  double nx_d0[R], nx_lg[R], n2_d0[R], n2_lg[R];
+  int nx_z[R], n2_z[R];
+#pragma unroll
+  for (int k = 0; k < R; k++) {
+    const int pos = tid * R + k, pos2 = N + pos;
+    nx_d0[k] = pos < nS ? dl[pos] : 0.0;
+    nx_lg[k] = pos < nS ? lgt[pos] : 0.0;
+    nx_z[k] = pos < nS ? z[pos] : 0;
+    n2_d0[k] = pos2 < nS ? dl[pos2] : 0.0;
+    n2_lg[k] = pos2 < nS ? lgt[pos2] : 0.0;
+    n2_z[k] = pos2 < nS ? z[pos2] : 0;
+  }
   for (int q = tid; q < hlen; q += T) Hzero[q] = 0;
   {  // side-1 count on entry (anchor i_2 included)
     int c1 = 0;
@@ -243,16 +267,6 @@ __device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const 
     __syncthreads();
   }
   int nBcur = M.nB;  // side-1 count (anchor included) on entry to the current chunk, kept by every thread
-  // this thread's members of the NEXT chunk (loaded one chunk ahead)
-  double nx_d0[R], nx_lg[R];
-  int nx_z[R];
-#pragma unroll
-  for (int k = 0; k < R; k++) {
-    const int pos = tid * R + k;
-    nx_d0[k] = pos < nS ? dl[pos] : 0.0;
-    nx_lg[k] = pos < nS ? lgt[pos] : 0.0;
-    nx_z[k] = pos < nS ? z[pos] : 0;
-  }
   for (int base = 0; base < nS; base += N) {
     double d0[R], lg[R];
     int zz[R];
@@ -261,11 +275,14 @@ __device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const 
       d0[k] = nx_d0[k];
       lg[k] = nx_lg[k];
       zz[k] = nx_z[k];
-      const int pn = base + N + tid * R + k;
+      nx_d0[k] = n2_d0[k];
+      nx_lg[k] = n2_lg[k];
+      nx_z[k] = n2_z[k];
+      const int pn = base + 2 * N + tid * R + k;
       if (pn < nS) {
-        nx_d0[k] = dl[pn];
-        nx_lg[k] = lgt[pn];
-        nx_z[k] = z[pn];
+        n2_d0[k] = dl[pn];
+        n2_lg[k] = lgt[pn];
+        n2_z[k] = z[pn];
       }
     }
     // b = side-1 members other than the one being decided (anchor included) stays inside [blo, bhi] while this
@@ -273,18 +290,21 @@ __device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const 
     // The log-count term log((nS+1-b)/b) of D is decreasing in b.
     const int nv = min(N, nS - base);
     const int blo = nBcur - min(nv, nBcur - 1), bhi = nBcur + min(nv, nS + 1 - nBcur) - 1;
-    const double dc_max = log((double)(nS + 1 - blo)) - log((double)blo);
-    const double dc_min = log((double)(nS + 1 - bhi)) - log((double)bhi);
+    // (single-precision logs widened by a margin far above their error: these are bounds, and every thread needs them)
+    const double dc_max = sm_dc_bound(nS, blo) + SM_DC_MARGIN;
+    const double dc_min = sm_dc_bound(nS, bhi) - SM_DC_MARGIN;
     int newz[R], pre[R];
     unsigned nrmask = 0;  // bit k: member k of this thread needs the ordered walk
     int run = 0;          // side-1 change of this thread's robust members so far
 #pragma unroll
     for (int k = 0; k < R; k++) {
       const bool valid = base + tid * R + k < nS;
-      const bool robust0 = valid && (dc_min + d0[k] > fabs(lg[k]) + 1e-9);   // D > |logit u| whatever the counts: side 0
-      const bool robust1 = valid && (dc_max + d0[k] < -fabs(lg[k]) - 1e-9);  // D < -|logit u|: side 1
-      newz[k] = robust0 ? 0 : (robust1 ? 1 : zz[k]);
-      if (valid && !robust0 && !robust1) nrmask |= 1u << k;
+      // the decision is constant on each of the D-intervals cut by {-logit u, 0, logit u} (just {0} when u <= 1/2):
+      // a member whose whole D range falls inside one of them is decided whatever the counts are
+      const int rlo = sm_d_region(dc_min + d0[k], lg[k]), rhi = sm_d_region(dc_max + d0[k], lg[k]);
+      const bool robust = valid && rlo == rhi;
+      newz[k] = robust ? (~rlo & 1) : zz[k];
+      if (valid && !robust) nrmask |= 1u << k;
       pre[k] = run;
       run += newz[k] - zz[k];
     }
@@ -355,25 +375,42 @@ __device__ __forceinline__ void sm_rdecide_body(int nS, const double* dl, const 
         const double md0 = v ? M.d0[t] : 0.0, mlg = v ? M.lg[t] : 0.0;
         const int mpre = v ? M.pre[t] : 0;
         int mz = M.z[t];
+        // Lanes [start, f) are settled together: lane l sees at most l - start undecided members of this block
+        // before it, which bounds its count term as above; f is the first lane whose D range straddles a
+        // threshold.  That one is evaluated exactly (double-precision logs, one lane) against the settled counts.
         int start = 0;
-        while (start < 32) {
-          int nz = mz;
-          if (v && lane >= start) {
-            const int nBq = nB0 + mpre + extra, nAq = nS + 2 - nBq;
-            const double dc = (mz == 0) ? log((double)(nAq - 1)) - log((double)nBq)
-                                        : log((double)nAq) - log((double)(nBq - 1));
-            const double D = dc + md0;
-            if (D > 0.0)
-              nz = (D >= mlg) ? 0 : 1;
-            else
-              nz = (-D >= mlg) ? 1 : 0;
+        while (start < 32 && b0 + start < nnr) {
+          const bool act = v && lane >= start;
+          const int nBq = nB0 + mpre + extra, b = nBq - mz, dev = lane - start;
+          const int blo = max(1, b - dev), bhi = min(nS, b + dev);
+          const int rlo = sm_d_region(sm_dc_bound(nS, bhi) - SM_DC_MARGIN + md0, mlg),
+                    rhi = sm_d_region(sm_dc_bound(nS, blo) + SM_DC_MARGIN + md0, mlg);
+          const unsigned fr = __ballot_sync(SMG_FULL, act && rlo != rhi);
+          const int f = fr ? __ffs(fr) - 1 : 32;
+          int d = 0;
+          if (act && lane < f) {
+            const int nz = ~rlo & 1;
+            d = nz - mz;
+            mz = nz;
           }
-          const unsigned chg = __ballot_sync(SMG_FULL, v && lane >= start && nz != mz);
-          if (!chg) break;
-          const int f = __ffs(chg) - 1;
-          const int zo = __shfl_sync(SMG_FULL, mz, f), zn = __shfl_sync(SMG_FULL, nz, f);
-          if (lane == f) mz = nz;
-          extra += zn - zo;
+          extra += warp_sum_i(d);
+          if (f < 32) {
+            int df = 0;
+            if (lane == f) {
+              const int nBf = nB0 + mpre + extra, nAf = nS + 2 - nBf;
+              const double dc = (mz == 0) ? log((double)(nAf - 1)) - log((double)nBf)
+                                          : log((double)nAf) - log((double)(nBf - 1));
+              const double D = dc + md0;
+              int nz;
+              if (D > 0.0)
+                nz = (D >= mlg) ? 0 : 1;
+              else
+                nz = (-D >= mlg) ? 1 : 0;
+              df = nz - mz;
+              mz = nz;
+            }
+            extra += __shfl_sync(SMG_FULL, df, f);
+          }
           start = f + 1;
         }
         if (v) M.z[t] = mz;
@@ -560,7 +597,7 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     CHAIN_TICK(6);
   };
   auto run_jobs = [&](const PhiJob* jobs, int nj) {
-    if ((int)blockIdx.x < nj) phi_job_body(A.phi, jobs[blockIdx.x], blockIdx.x, sh);
+    if ((int)blockIdx.x < nj * A.phi.nparts) phi_job_body(A.phi, jobs[blockIdx.x % nj], blockIdx.x % nj, blockIdx.x / nj, A.phi.nparts, sh);
     grid_sync(B);
   };
 
@@ -605,7 +642,7 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
     // the job index enters the Philox counter: keep the merged cluster at index 2 as in the multi-launch path
     if (!same) {
-      if (blockIdx.x == 2) phi_job_body(A.phi, j[0], 2, sh);
+      if ((int)blockIdx.x < A.phi.nparts) phi_job_body(A.phi, j[0], 2, blockIdx.x, A.phi.nparts, sh);
       grid_sync(B);
     } else {
       run_jobs(j, nj);
@@ -984,7 +1021,8 @@ static int sm_phi(smg_chain* ch, const PhiJob* jobs, int nj) {
   A.njobs_ptr = nullptr;
   for (int q = 0; q < nj; q++) A.jobs[q] = jobs[q];
   A.enable = &W->info->same;
-  phi_update_kernel<<<nj, 256, 0, ch->st>>>(A);
+  A.nparts = ch->phi_parts;
+  phi_update_kernel<<<nj * A.nparts, 256, 0, ch->st>>>(A);
   ch->h_launches += 1;
   SMG_CUDA(cudaGetLastError());
   return 0;
@@ -1122,6 +1160,14 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     // grid: enough CTAs for the member-likelihood phase of a single chain; a small gang when several chains share the
     // GPU (smg_step_many), where the number of launches per sweep matters more than the latency of one proposal
     const int ctas = ch->many ? 8 : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
+    {  // up to 3 parameter-update jobs run side by side, each split over `nparts` CTAs
+      static int want = -1;
+      if (want < 0) {
+        const char* e = getenv("SMG_SM_PHI_PARTS");
+        want = e ? atoi(e) : 8;
+      }
+      CA.phi.nparts = phi_parts_for(ch->pp, std::max(1, std::min(want, ctas / 3)));
+    }
     const cudaError_t ce =
         cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(ctas), dim3(SM_CHAIN_T), kargs, W->chain_smem, ch->st);
     if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources) {
