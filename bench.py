@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--m-aux", type=int, default=3)
     ap.add_argument("--t", type=int, default=10)
     ap.add_argument("--r", type=int, default=10)
-    ap.add_argument("--burn", type=int, default=3, help="untimed sweeps from the random start before warm-up")
+    ap.add_argument("--burn", type=int, default=40, help="untimed sweeps from the random start before warm-up (the chain reaches K~50 in about 30)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--multi-chains", type=int, default=8, help="extra measurement: this many chains stepped together on one GPU (0: skip)")
     ap.add_argument("--no-psm", action="store_true", help="skip the tensor-core PSM measurement (n=2e4, C5 shape)")
@@ -65,7 +65,7 @@ def workload(a, seed):
 def config_dict(a):
     return {"workload": f"synthetic Hamming mixture n={a.n} p={a.p} categories={a.cats} K_true={a.k_true} s=0.5",
             "m_aux": a.m_aux, "t": a.t, "r": a.r, "gamma": 1.0, "v": 6.0, "w": 0.25,
-            "init": f"L={a.k_true} random labels, {a.burn} untimed sweeps before warm-up",
+            "init": f"L={a.k_true} random labels, {a.burn} untimed sweeps before warm-up (stationary chain, K~{a.k_true})",
             "chains_per_gpu": 1, "parallelism": "independent chains, one per GPU",
             "cache": "inputs larger than L2: X 25.6 MB + LL block 154 MB + aux pool 1.3 GB are streamed every sweep"}
 

@@ -77,9 +77,9 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaMemsetAsync(ch->phi_cnt, 0, (size_t)NST * 4, ch->st));
   {
     const char* e = getenv("SMG_PHI_PARTS");
-    ch->phi_parts = phi_parts_for(pp, e ? atoi(e) : pp / 64);
+    ch->phi_parts = phi_parts_for(pp, e ? atoi(e) : pp / 32);  // 32 attributes x PHI_G lanes = one pass of a 256-thread CTA
   }
-  if (dalloc(&ch->c, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
+  if (dalloc(&ch->c, n) || dalloc(&ch->c_hist, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
       dalloc(&ch->slot2label, NST))
     return SMG_ERR_CUDA;
   if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n) ||
@@ -262,8 +262,22 @@ static int prefetch_next_aux(smg_chain* ch) {
 
 // K3: histogram + counts of the canonical state
 static int launch_histogram(smg_chain* ch) {
-  SMG_CUDA(cudaMemsetAsync(ch->H, 0, (size_t)ch->Kcap * ch->pp * ch->mmax * sizeof(int), ch->st));
+  static const bool incremental = [] {
+    const char* e = getenv("SMG_NO_INCR_HIST");
+    return !(e && atoi(e) != 0);
+  }();
   SMG_CUDA(cudaMemsetAsync(ch->counts, 0, (size_t)ch->NST * sizeof(int), ch->st));
+  if (ch->hist_valid && incremental) {  // H matches c_hist: move only the rows whose label changed since
+    const int ctas = std::max(1, std::min(148 * 4, cdiv(ch->n, 256)));
+    cluster_histogram_update_kernel<<<ctas, 256, (size_t)ch->Kcap * sizeof(int), ch->st>>>(
+        ch->X, ch->n, ch->pp, ch->c, ch->c_hist, ch->mmax, ch->Kcap, ch->H, ch->counts);
+    ch->h_launches++;
+    SMG_CUDA(cudaGetLastError());
+    return 0;
+  }
+  SMG_CUDA(cudaMemsetAsync(ch->H, 0, (size_t)ch->Kcap * ch->pp * ch->mmax * sizeof(int), ch->st));
+  SMG_CUDA(cudaMemcpyAsync(ch->c_hist, ch->c, (size_t)ch->n * sizeof(int), cudaMemcpyDeviceToDevice, ch->st));
+  ch->hist_valid = true;
   const size_t smem = ((size_t)ch->Kcap * 16 * ch->mmax + ch->Kcap) * sizeof(int);
   if (smem <= 72 * 1024) {  // three CTAs per SM
     const int rg = std::max(1, std::min(32, cdiv(ch->n, 256 * 8)));
@@ -536,6 +550,7 @@ static int init_state(smg_chain* ch, const int* c_init, int compact_init) {
   std::vector<int> counts(ch->NST, 0);
   for (int x : c) counts[x]++;
   SMG_CUDA(cudaMemcpyAsync(ch->c, c.data(), (size_t)ch->n * 4, cudaMemcpyHostToDevice, ch->st));
+  ch->hist_valid = false;
   SMG_CUDA(cudaMemcpyAsync(ch->counts, counts.data(), (size_t)ch->NST * 4, cudaMemcpyHostToDevice, ch->st));
   SMG_CUDA(cudaMemcpyAsync(ch->K, &K, 4, cudaMemcpyHostToDevice, ch->st));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
@@ -1241,6 +1256,7 @@ int smg_debug_set_state(smg_chain* ch, int K, const int* c_i, const double* cent
   SMG_CUDA(cudaMemcpy(ch->cen[ch->cur], hc.data(), hc.size(), cudaMemcpyHostToDevice));
   SMG_CUDA(cudaMemcpy(ch->sig[ch->cur], hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
   SMG_CUDA(cudaMemcpy(ch->c, c_i, (size_t)ch->n * 4, cudaMemcpyHostToDevice));
+  ch->hist_valid = false;
   SMG_CUDA(cudaMemcpy(ch->counts, counts.data(), counts.size() * 4, cudaMemcpyHostToDevice));
   SMG_CUDA(cudaMemcpy(ch->K, &K, 4, cudaMemcpyHostToDevice));
   derive_terms_kernel<<<K, 256, 0, ch->st>>>(K, ch->pp, ch->p, ch->attr, ch->sig[ch->cur], ch->isg[ch->cur], ch->den,
@@ -1412,10 +1428,16 @@ __global__ void dbg_loghig_kernel(int n, const double* s, const double* v, const
 }
 
 __global__ void dbg_rhig_kernel(int n, double v, double w, double m, RngKey key, double* out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  SubStream rs(key, U_SIGMA, (uint32_t)i, 0u);
-  out[i] = hig_draw_u_d(rs, v, w, m);
+  // first half: the lane-group sampler of the parameter updates; second half: the one-thread sampler of the pool
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, half = n / 2;
+  const int i = t / PHI_G, g = t % PHI_G, lane = threadIdx.x & 31, gbase = lane & ~(PHI_G - 1);
+  if (i < half) {  // whole groups
+    const double u = hig_draw_u_grp(key, (uint32_t)i, 0u, v, w, m, g, ((1u << PHI_G) - 1u) << gbase, gbase);
+    if (g == 0) out[i] = u;
+  } else if (i < n && g == 0) {
+    SubStream rs(key, U_SIGMA, (uint32_t)i, 0u);
+    out[i] = hig_draw_u_d(rs, v, w, m);
+  }
 }
 
 static int dbg_map4(int count, const double* a, const double* b, const double* c, const double* d, double* out, int which) {
@@ -1460,7 +1482,7 @@ int smg_debug_rhig_u(int count, double v, double w, double m, unsigned long long
   key.k1 = (uint32_t)(seed >> 32);
   key.sweep = 0;
   key.sub = 0;
-  dbg_rhig_kernel<<<cdiv(count, 128), 128>>>(count, v, w, m, key, buf);
+  dbg_rhig_kernel<<<cdiv(count * PHI_G, 128), 128>>>(count, v, w, m, key, buf);
   SMG_CUDA(cudaGetLastError());
   SMG_CUDA(cudaDeviceSynchronize());
   SMG_CUDA(cudaMemcpy(u_out, buf, (size_t)count * 8, cudaMemcpyDeviceToHost));

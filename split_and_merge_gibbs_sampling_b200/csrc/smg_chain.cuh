@@ -98,6 +98,8 @@ struct smg_chain {
   uint8_t* cen[2] = {nullptr, nullptr};
   double *sig[2] = {nullptr, nullptr}, *isg[2] = {nullptr, nullptr}, *sden[2] = {nullptr, nullptr};
   double* den = nullptr;
+  int* c_hist = nullptr;    // labels the cluster histogram H was last brought up to date with
+  bool hist_valid = false;  // H matches c_hist (cleared whenever labels are uploaded from the host)
   int* phi_cnt = nullptr;  // finished parts per destination slot of a split parameter-update job
   int phi_parts = 1;       // CTAs per job in phi_update_kernel
   int cur = 0;

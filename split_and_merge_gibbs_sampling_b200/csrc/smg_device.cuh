@@ -33,7 +33,8 @@ enum Site : uint32_t {
   U_SM_ACCEPT = 8,  // split_merge.cpp:591
   U_POOL_CENTER = 9,
   U_POOL_SIGMA = 10,
-  U_INIT_ASSIGN = 11  // common_functions.cpp:180
+  U_INIT_ASSIGN = 11,  // common_functions.cpp:180
+  U_SIGMA_B = 12      // second gamma stream of the lane-pair sigma draw (a = job, b = attribute)
 };
 
 struct RngKey {
@@ -307,6 +308,37 @@ __device__ inline double hig_draw_u_d(SubStream& rs, double v, double w, double 
     }
   }
   return hig_inv_u_d(rs.next(), v, w, m);
+}
+
+// The same draw by a group of PHI_G consecutive lanes (all of them call this; `g` = lane index inside the group,
+// `gmask` its lane mask, `gbase` its first lane).  The two gamma variates of a proposal are independent, so lanes 0
+// and 1 draw them side by side from two sub-streams -- the dependency chain of a proposal is one gamma draw
+// instead of two.  Result valid on lane 0 of the group.
+#define PHI_G 8
+__device__ inline double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
+                                        unsigned gmask, int gbase) {
+  SubStream rs(key, g == 1 ? U_SIGMA_B : U_SIGMA, sa, sb);
+  const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
+  double res = 0.0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    double gm = 0.0;
+    if (g < 2) gm = gamma_draw_d(rs, g == 0 ? a : b);
+    const double gb = __shfl_sync(gmask, gm, gbase + 1);
+    int ok = 0;
+    if (g == 0) {
+      const double x = gm / (gm + gb);
+      if (x > 0.0 && x <= xmax) {
+        const double u = x / ((m - 1.0) * (1.0 - x));
+        if (u > 0.0 && u < 1.0) {
+          ok = 1;
+          res = u;
+        }
+      }
+    }
+    if (__shfl_sync(gmask, ok, gbase)) return res;
+  }
+  if (g == 0) res = hig_inv_u_d(rs.next(), v, w, m);
+  return res;
 }
 
 // ----------------------------------------------------------------------------

@@ -1249,6 +1249,50 @@ __global__ void __launch_bounds__(256) cluster_histogram_smem_kernel(const uint8
       if (s_cnt[q]) atomicAdd(&counts[q], s_cnt[q]);
 }
 
+// Incremental form: H already holds the histogram of the labels c_hist; only the rows whose label changed since
+// then are moved (subtracted from the old cluster, added to the new one), which at stationarity is a handful of
+// rows per sweep instead of all n.  Integer arithmetic, so the table equals a full rebuild.  One warp per 32
+// rows; a changed row is moved by the whole warp (8 attributes per lane and step).  Member counts are rebuilt
+// from c (privatised in shared memory) exactly as the full kernels do.
+__global__ void __launch_bounds__(256) cluster_histogram_update_kernel(const uint8_t* __restrict__ X, int n, int pp,
+                                                                       const int* __restrict__ c, int* __restrict__ c_hist,
+                                                                       int mmax, int Kcap, int* __restrict__ H,
+                                                                       int* __restrict__ counts) {
+  extern __shared__ int s_cnt[];  // [Kcap]
+  for (int q = threadIdx.x; q < Kcap; q += blockDim.x) s_cnt[q] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+  for (int base = gw * 32; base < n; base += nw * 32) {
+    const int i = base + lane;
+    const int k = i < n ? c[i] : -1, kp = i < n ? c_hist[i] : -1;
+    if (k >= 0 && k < Kcap) atomicAdd(&s_cnt[k], 1);
+    unsigned chg = __ballot_sync(SMG_FULL, k != kp);
+    if (k != kp) c_hist[i] = k;
+    while (chg) {
+      const int b = __ffs(chg) - 1;
+      chg &= chg - 1;
+      const int kn = __shfl_sync(SMG_FULL, k, b), ko = __shfl_sync(SMG_FULL, kp, b);
+      const uint8_t* x = X + (size_t)(base + b) * pp;
+      for (int off = lane * 8; off < pp; off += 256) {
+        const uint2 v = *reinterpret_cast<const uint2*>(x + off);
+        const uint32_t w[2] = {v.x, v.y};
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int lv = (w[q >> 2] >> ((q & 3) * 8)) & 0xff;
+          if (lv) {
+            if (ko >= 0 && ko < Kcap) atomicSub(&H[((size_t)ko * pp + off + q) * mmax + (lv - 1)], 1);
+            if (kn >= 0 && kn < Kcap) atomicAdd(&H[((size_t)kn * pp + off + q) * mmax + (lv - 1)], 1);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < Kcap; q += blockDim.x)
+    if (s_cnt[q]) atomicAdd(&counts[q], s_cnt[q]);
+}
+
 // histogram of a member subset split in two groups by z (split-merge launch states):
 // rows = S[0..nS) with group z[s], plus the two anchors i1 (group 0) and i2 (group 1).
 __global__ void __launch_bounds__(256) subset_histogram_kernel(const uint8_t* __restrict__ X, int pp,
@@ -1465,6 +1509,56 @@ __device__ __forceinline__ int draw_center(const int* __restrict__ h, int nk, do
   return 1 + sample_probs_small(pt, m, u);
 }
 
+// The m <= 8 case by a group of PHI_G lanes, lane g holding level g+1 (hg = its count): the divisions and
+// exponentials of the levels run side by side, the two normalising sums are accumulated in level order on every
+// lane (same roundings as the one-thread version above).  Returns the level on every lane; *s_match = its count.
+__device__ __forceinline__ int draw_center_grp(int hg, int nk, double sg, int m, double u, int g, unsigned gmask,
+                                               int gbase, double* s_match) {
+  const bool valid = g < m;
+  const double lp = valid ? -((double)nk - (double)hg) / sg : -CUDART_INF;
+  double mx = lp;
+#pragma unroll
+  for (int o = 1; o < PHI_G; o <<= 1) {
+    const double y = __shfl_xor_sync(gmask, mx, o);
+    mx = y > mx ? y : mx;
+  }
+  const double e = valid ? exp(lp - mx) : 0.0;
+  double sum = 0.0;
+#pragma unroll
+  for (int a = 0; a < PHI_G; a++) {
+    const double y = __shfl_sync(gmask, e, gbase + a);
+    if (a < m) sum += y;
+  }
+  const double pn = valid ? e / sum : 0.0;
+  double sum2 = 0.0;
+#pragma unroll
+  for (int a = 0; a < PHI_G; a++) {
+    const double y = __shfl_sync(gmask, pn, gbase + a);
+    if (a < m) sum2 += y;
+  }
+  const double q = valid ? pn / sum2 : -1.0;  // what Rcpp::sample compares against after its own normalisation
+  double qmax = q;
+#pragma unroll
+  for (int o = 1; o < PHI_G; o <<= 1) {
+    const double y = __shfl_xor_sync(gmask, qmax, o);
+    qmax = y > qmax ? y : qmax;
+  }
+  const unsigned top = __ballot_sync(gmask, valid && q == qmax) & gmask;
+  int center;
+  if (__popc(top) == 1 && u <= qmax) {
+    center = (__ffs(top) - 1 - gbase) + 1;
+  } else {  // ties and the other draws: R's descending-order walk on lane 0
+    double pt[PHI_G];
+#pragma unroll
+    for (int a = 0; a < PHI_G; a++) pt[a] = __shfl_sync(gmask, pn, gbase + a);
+    center = 0;
+    if (g == 0) center = 1 + sample_probs_small(pt, m, u);
+    center = __shfl_sync(gmask, center, gbase);
+  }
+  *s_match = (double)__shfl_sync(gmask, hg, gbase + center - 1);
+  return center;
+}
+
 // One CTA per job; thread j draws attribute j (and j+256, ...), then the CTA sums the per-attribute
 // log-normalisers in a fixed order into sden[dst].
 // One parameter-update job executed by one CTA (any block size >= 256: the first 256 threads draw, everybody
@@ -1479,13 +1573,20 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
 #ifdef SMG_PHI_PROFILE
   long long tp0 = clock64(), tp1 = tp0, tp2 = tp0;
 #endif
-  for (int j = part * chunk + threadIdx.x; j < j1; j += blockDim.x) {
+  // PHI_G lanes per attribute
+  const int g = threadIdx.x & (PHI_G - 1), lane = threadIdx.x & 31, gbase = lane & ~(PHI_G - 1);
+  const unsigned gmask = ((1u << PHI_G) - 1u) << gbase;
+  for (int jb = part * chunk; jb < j1; jb += blockDim.x / PHI_G) {
+    const int j = jb + (int)(threadIdx.x / PHI_G);
+    if (j >= j1) continue;  // whole groups drop out together
     const size_t o = (size_t)J.dst * A.pp + j;
     if (j >= A.p) {  // padding attributes
-      A.cen[o] = 0;
-      A.sig[o] = 1.0;
-      A.isg[o] = 0.0;
-      A.den[o] = 0.0;
+      if (g == 0) {
+        A.cen[o] = 0;
+        A.sig[o] = 1.0;
+        A.isg[o] = 0.0;
+        A.den[o] = 0.0;
+      }
       continue;
     }
     const int m = A.attr[j];
@@ -1498,30 +1599,42 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
     } else {
       const double sg = A.sig_src[(size_t)J.src * A.pp + j];
       const int* h = A.H + ((size_t)J.hist * A.pp + j) * A.mmax;
-      center = draw_center(h, nk, sg, m, uc);
-      s_match = (double)h[center - 1];
+      if (m <= PHI_G) {
+        center = draw_center_grp(g < m ? h[g] : 0, nk, sg, m, uc, g, gmask, gbase, &s_match);
+      } else {
+        center = 0;
+        if (g == 0) {
+          center = draw_center(h, nk, sg, m, uc);
+          s_match = (double)h[center - 1];
+        }
+        center = __shfl_sync(gmask, center, gbase);
+        s_match = __shfl_sync(gmask, s_match, gbase);
+      }
     }
     const double vv = A.v[j] + s_match;
     const double ww = A.w[j] + (double)nk - s_match;
-    double uu;
+    double uu = 0.5;
 #ifdef SMG_PHI_PROFILE
     tp1 = clock64();
 #endif
     if (J.us || A.sigma_exact) {
-      const double us = get_u(J.us, (size_t)j, key, U_SIGMA, (uint32_t)job, (uint32_t)j);
-      uu = hig_inv_u_d(us, vv, ww, (double)m);
+      if (g == 0) {
+        const double us = get_u(J.us, (size_t)j, key, U_SIGMA, (uint32_t)job, (uint32_t)j);
+        uu = hig_inv_u_d(us, vv, ww, (double)m);
+      }
     } else {
-      SubStream rs(key, U_SIGMA, (uint32_t)job, (uint32_t)j);
-      uu = hig_draw_u_d(rs, vv, ww, (double)m);
+      uu = hig_draw_u_grp(key, (uint32_t)job, (uint32_t)j, vv, ww, (double)m, g, gmask, gbase);
     }
 #ifdef SMG_PHI_PROFILE
     tp2 = clock64();
 #endif
-    const double sigma = -1.0 / log(uu);
-    A.cen[o] = (uint8_t)center;
-    A.sig[o] = sigma;
-    A.isg[o] = 1.0 / sigma;
-    A.den[o] = hamming_den(sigma, m);
+    if (g == 0) {
+      const double sigma = -1.0 / log(uu);
+      A.cen[o] = (uint8_t)center;
+      A.sig[o] = sigma;
+      A.isg[o] = 1.0 / sigma;
+      A.den[o] = hamming_den(sigma, m);
+    }
   }
 #ifdef SMG_PHI_PROFILE
   if (threadIdx.x == 0 && A.prof) {
