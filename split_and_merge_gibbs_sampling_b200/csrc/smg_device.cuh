@@ -185,7 +185,13 @@ __device__ __noinline__ void log_ibeta_pair(double x, double a, double b, double
 // where the reference is finite (tests/test_oracle_known_answers.py).
 __device__ __noinline__ double norm_const2_d(double w, double v, double m) {
   double a = w + 1.0, b = v - 1.0, lb = lbeta_d(a, b), lo, up;
-  log_ibeta_pair((m - 1.0) / m, a, b, lb, &lo, &up);
+  // With data the truncation point x = (m-1)/m lies far in the upper tail of Beta(a,b).  Chernoff on the gamma
+  // representation X = G_a/(G_a+G_b) gives P(X >= x) <= exp(-(a+b) KL(mu||x)), mu = a/(a+b) < x; once that is below
+  // e^-80 the log of the truncated mass is 0 to far below one ulp of the result and the continued fraction (tens of
+  // iterations for large shapes) is skipped.
+  const double x = (m - 1.0) / m, mu = a / (a + b);
+  if (x > mu && b > 0.0 && -(a * log(mu / x) + b * log((1.0 - mu) / (1.0 - x))) > 80.0) return a * log(m - 1.0) - lb;
+  log_ibeta_pair(x, a, b, lb, &lo, &up);
   return a * log(m - 1.0) - lb - lo;
 }
 

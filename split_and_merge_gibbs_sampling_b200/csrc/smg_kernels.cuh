@@ -1636,7 +1636,7 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
       A.den[o] = hamming_den(sigma, m);
     }
   }
-#ifdef SMG_PHI_PROFILE
+#if defined(SMG_PHI_PROFILE) && !defined(SMG_SM_HT_PROFILE)
   if (threadIdx.x == 0 && A.prof) {
     const long long tp3 = clock64();
     atomicAdd(&A.prof[0], (unsigned long long)(tp1 - tp0));

@@ -37,7 +37,9 @@ struct SmWork {
   double* partial = nullptr;  // [4][RB]
   double* terms = nullptr;    // [24]
   size_t hist_smem = 0;       // dynamic shared memory of subset_histogram_smem_kernel (0: does not fit)
-  unsigned* chain_bar = nullptr;  // [2]: grid-barrier counter and error flag of sm_chain_kernel
+  unsigned* chain_bar = nullptr;  // [4]: two grid-barrier counters (used in turn) and the error flag of sm_chain_kernel
+  int bar_flip = 0;
+  int* selcnt = nullptr;          // [grid] members found per CTA in the selection phase
   bool persistent = false;        // restricted-scan chain as one cooperative kernel
   size_t chain_smem = 0;          // its dynamic shared memory: max(side histograms, decision scratch)
   // injected uniforms (device copies, allocated on first use)
@@ -47,6 +49,51 @@ struct SmWork {
 };
 
 #define SM_RB 256  // partial-sum blocks of the row reductions
+
+// sample(indices, 2, replace=false) (split_merge.cpp:275): j1=(int)(n*u0); j2=(int)((n-1)*u1) over the swapped array
+__device__ __forceinline__ void sm_pick_pair(int n, const double* u_pair, const RngKey& key, int* i1, int* i2) {
+  const double u0 = get_u(u_pair, 0, key, U_SM_PAIR, 0u, 0u), u1 = get_u(u_pair, 1, key, U_SM_PAIR, 1u, 0u);
+  int j1 = (int)((double)n * u0);
+  if (j1 >= n) j1 = n - 1;
+  int j2 = (int)((double)(n - 1) * u1);
+  if (j2 >= n - 1) j2 = n - 2;
+  *i1 = j1;
+  *i2 = (j2 == j1) ? (n - 1) : j2;
+}
+// proposal descriptor + which slots / histograms feed each MH term
+__device__ __forceinline__ void sm_fill_info_plan(SmInfo* info, SmPlan* plan, int NS, int i1, int i2, int nS, int cA, int cB,
+                                                  int K) {
+  const int same = (cA == cB);
+  {
+    info->i1 = i1;
+    info->i2 = i2;
+    info->nS = nS;
+    info->same = same;
+    info->cA = cA;
+    info->cB = cB;
+    info->K = K;
+    SmPlan P;
+    const int B = NS;
+    if (same) {  // split_acc_prob (split_merge.cpp:438-487)
+      P.gs_hist[0] = SH_P0, P.gs_sigL[0] = B + SM_SL_A, P.gs_star[0] = B + SM_ST_A;
+      P.gs_hist[1] = SH_P1, P.gs_sigL[1] = B + SM_SL_B, P.gs_star[1] = B + SM_ST_B;
+      P.gs_hist[2] = SH_M, P.gs_sigL[2] = B + SM_ML_M, P.gs_star[2] = cA;
+      P.pri_slot[0] = B + SM_ST_A, P.pri_slot[1] = B + SM_ST_B, P.pri_slot[2] = cA;
+      P.lg_cnt[0] = SH_P0, P.lg_cnt[1] = SH_P1, P.lg_cnt[2] = SH_M;
+      P.slotA = B + SM_ST_A, P.slotB = B + SM_ST_B, P.slotAll = cA;
+      P.zsel = 0;
+    } else {  // merge_acc_prob (split_merge.cpp:489-540)
+      P.gs_hist[0] = SH_S0, P.gs_sigL[0] = B + SM_SL_A, P.gs_star[0] = cA;
+      P.gs_hist[1] = SH_S1, P.gs_sigL[1] = B + SM_SL_B, P.gs_star[1] = cB;
+      P.gs_hist[2] = SH_M, P.gs_sigL[2] = B + SM_ML_M, P.gs_star[2] = B + SM_ST_M;
+      P.pri_slot[0] = cA, P.pri_slot[1] = cB, P.pri_slot[2] = B + SM_ST_M;
+      P.lg_cnt[0] = SH_S0, P.lg_cnt[1] = SH_S1, P.lg_cnt[2] = SH_M;
+      P.slotA = cA, P.slotB = cB, P.slotAll = B + SM_ST_M;
+      P.zsel = 1;
+    }
+    *plan = P;
+  }
+}
 
 // ------------------------------------------------------------------------------------------
 // pair selection + S (split_merge.cpp:263-301).  One CTA; ordered stream compaction.
@@ -60,12 +107,8 @@ __global__ void __launch_bounds__(1024) sm_select_kernel(int n, const int* __res
   __shared__ int s_wcnt[32], s_woff[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
-    double u0 = get_u(u_pair, 0, key, U_SM_PAIR, 0u, 0u), u1 = get_u(u_pair, 1, key, U_SM_PAIR, 1u, 0u);
-    int j1 = (int)((double)n * u0);
-    if (j1 >= n) j1 = n - 1;
-    int j2 = (int)((double)(n - 1) * u1);
-    if (j2 >= n - 1) j2 = n - 2;
-    int i1 = j1, i2 = (j2 == j1) ? (n - 1) : j2;
+    int i1, i2;
+    sm_pick_pair(n, u_pair, key, &i1, &i2);
     s_i1 = i1;
     s_i2 = i2;
     s_cA = c[i1];
@@ -109,36 +152,7 @@ __global__ void __launch_bounds__(1024) sm_select_kernel(int n, const int* __res
     }
     off += __popc(b);
   }
-  if (tid == 0) {
-    const int nS = s_tot, same = (cA == cB), K = *Kptr;
-    info->i1 = i1;
-    info->i2 = i2;
-    info->nS = nS;
-    info->same = same;
-    info->cA = cA;
-    info->cB = cB;
-    info->K = K;
-    SmPlan P;
-    const int B = NS;
-    if (same) {  // split_acc_prob (split_merge.cpp:438-487)
-      P.gs_hist[0] = SH_P0, P.gs_sigL[0] = B + SM_SL_A, P.gs_star[0] = B + SM_ST_A;
-      P.gs_hist[1] = SH_P1, P.gs_sigL[1] = B + SM_SL_B, P.gs_star[1] = B + SM_ST_B;
-      P.gs_hist[2] = SH_M, P.gs_sigL[2] = B + SM_ML_M, P.gs_star[2] = cA;
-      P.pri_slot[0] = B + SM_ST_A, P.pri_slot[1] = B + SM_ST_B, P.pri_slot[2] = cA;
-      P.lg_cnt[0] = SH_P0, P.lg_cnt[1] = SH_P1, P.lg_cnt[2] = SH_M;
-      P.slotA = B + SM_ST_A, P.slotB = B + SM_ST_B, P.slotAll = cA;
-      P.zsel = 0;
-    } else {  // merge_acc_prob (split_merge.cpp:489-540)
-      P.gs_hist[0] = SH_S0, P.gs_sigL[0] = B + SM_SL_A, P.gs_star[0] = cA;
-      P.gs_hist[1] = SH_S1, P.gs_sigL[1] = B + SM_SL_B, P.gs_star[1] = cB;
-      P.gs_hist[2] = SH_M, P.gs_sigL[2] = B + SM_ML_M, P.gs_star[2] = B + SM_ST_M;
-      P.pri_slot[0] = cA, P.pri_slot[1] = cB, P.pri_slot[2] = B + SM_ST_M;
-      P.lg_cnt[0] = SH_S0, P.lg_cnt[1] = SH_S1, P.lg_cnt[2] = SH_M;
-      P.slotA = cA, P.slotB = cB, P.slotAll = B + SM_ST_M;
-      P.zsel = 1;
-    }
-    *plan = P;
-  }
+  if (tid == 0) sm_fill_info_plan(info, plan, NS, i1, i2, s_tot, cA, cB, *Kptr);
 }
 
 // random launch allocation (split_merge.cpp:346): sample({a,b}, |S|, replace) -> (int)(2u)
@@ -529,141 +543,19 @@ __device__ __forceinline__ void grid_sync(GridBar& B) {
   __syncthreads();
 }
 
-struct SmChainArgs {
-  int n, p, pp, mmax, t, r, NS, wide_from;
-  const uint8_t* X;
-  const int* S;
-  const SmInfo* info;
-  uint8_t* cen;
-  double *sig, *isg, *sden;
-  int *H, *cnt, *zL, *zStar;
-  double *dl, *lgt;
-  PhiArgs phi;  // common fields of the parameter updates (jobs are filled on the device)
-  const double *u_rg, *u_rg_c, *u_rg_s, *u_mg_c, *u_mg_s;  // injected uniforms (bases) or null
-  RngKey key;
-  unsigned* bar;
-  int* err;
-};
-
-#define SM_CHAIN_CTAS 120
-#define SM_CHAIN_T 512  // 128 registers per thread: the parameter-update body does not spill
-
-__global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) {
-  // dynamic shared memory: the side histograms of the histogram phase and the scratch of the decision phase
-  // (never live at the same time)
-  extern __shared__ __align__(16) int s_hist[];
-  RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>& M = *reinterpret_cast<RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>*>(s_hist);
-  RdecideSmem<SM_DECIDE_WIDE_CHUNK>& MW = *reinterpret_cast<RdecideSmem<SM_DECIDE_WIDE_CHUNK>*>(s_hist);
-  __shared__ double sh[256];
-  GridBar B{A.bar, 0u, gridDim.x, A.err, A.phi.status};
-  const int nS = A.info->nS, same = A.info->same;
-  const int n = A.n, p = A.p, pp = A.pp, NSB = A.NS;
-  const int gwarp = blockIdx.x * (SM_CHAIN_T / 32) + (threadIdx.x >> 5), nwarps = gridDim.x * (SM_CHAIN_T / 32);
-  const size_t len = (size_t)pp * A.mmax;
-  auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
-
-  // allocation part of restricted scan q on sides z / slots (slotA, slotB) -> histograms h0, h0+1
-#ifdef SMG_PHI_PROFILE
-  long long tk = clock64();
-#define CHAIN_TICK(k)                                                                   \
-  do {                                                                                  \
-    const long long _t = clock64();                                                     \
-    if (blockIdx.x == 0 && threadIdx.x == 0 && A.phi.prof) A.phi.prof[k] += (unsigned long long)(_t - tk); \
-    tk = _t;                                                                            \
-  } while (0)
-#else
-#define CHAIN_TICK(k)
-#endif
-  auto alloc_scan = [&](int* z, int slotA, int slotB, int h0, int q) {
-    RngKey k = A.key;
-    k.sub = SUB_SM_RG + q;
-    CHAIN_TICK(7);
-    sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, A.lgt, gwarp,
-                    nwarps);
-    grid_sync(B);
-    CHAIN_TICK(4);
-    if (blockIdx.x == 0) {
-      if (q >= A.wide_from)
-        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_WIDE_CHUNK / SM_CHAIN_T>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len),
-                                                                       A.cnt + h0, MW);
-      else
-        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_R>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
-    }
-    grid_sync(B);
-    CHAIN_TICK(5);
-    subset_hist_body(A.X, pp, A.S, nS, z, &A.info->i1, A.mmax, A.H + (size_t)h0 * len, nullptr, s_hist, blockIdx.x,
-                     gridDim.x);
-    grid_sync(B);
-    CHAIN_TICK(6);
-  };
-  auto run_jobs = [&](const PhiJob* jobs, int nj) {
-    if ((int)blockIdx.x < nj * A.phi.nparts) phi_job_body(A.phi, jobs[blockIdx.x % nj], blockIdx.x % nj, blockIdx.x / nj, A.phi.nparts, sh);
-    grid_sync(B);
-  };
-
-  const int nsteps = A.t > A.r ? A.t : A.r;
-  for (int q = 0; q < nsteps; q++) {
-    PhiJob j[3];
-    int nj = 0;
-    if (q < A.t) {
-      alloc_scan(A.zL, NSB + SM_SL_A, NSB + SM_SL_B, SH_L0, q);
-      for (int side = 0; side < 2; side++)
-        j[nj++] = sm_job_at(NSB, J_L0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
-                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
-    }
-    if (q < A.r)
-      j[nj++] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + q, off(A.u_mg_c, (size_t)q * p), off(A.u_mg_s, (size_t)q * p), 0);
-    run_jobs(j, nj);
-    if (*(volatile int*)A.err) return;
-  }
-  // proposal = split launch state (sides + the two parameter slots) ...
-  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nS; pos += gridDim.x * blockDim.x) A.zStar[pos] = A.zL[pos];
-  if (blockIdx.x < 2) {
-    const int src = NSB + (blockIdx.x ? SM_SL_B : SM_SL_A), dst = NSB + (blockIdx.x ? SM_ST_B : SM_ST_A);
-    for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
-      A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
-      A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
-      A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
-    }
-    if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
-  }
-  grid_sync(B);
-  // ... + one more restricted scan for a split; the merged cluster's final update in both cases
-  {
-    const int q = A.t;
-    PhiJob j[3];
-    int nj = 0;
-    if (same) {
-      alloc_scan(A.zStar, NSB + SM_ST_A, NSB + SM_ST_B, SH_P0, q);
-      for (int side = 0; side < 2; side++)
-        j[nj++] = sm_job_at(NSB, J_P0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
-                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
-    }
-    j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
-    // the job index enters the Philox counter: keep the merged cluster at index 2 as in the multi-launch path
-    if (!same) {
-      if ((int)blockIdx.x < A.phi.nparts) phi_job_body(A.phi, j[0], 2, blockIdx.x, A.phi.nparts, sh);
-      grid_sync(B);
-    } else {
-      run_jobs(j, nj);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // MH terms
 // ------------------------------------------------------------------------------------------
 // logprobgs_phi (split_merge.cpp:20-94): block b evaluates term b; also priors (:419-436) in blocks 3..5
-__global__ void __launch_bounds__(256) sm_gsphi_prior_kernel(int pp, int p, int mmax, const int* __restrict__ attr,
-                                                             const double* __restrict__ v, const double* __restrict__ w,
-                                                             const int* __restrict__ H, const int* __restrict__ cnt,
-                                                             const SmPlan* plan, const uint8_t* cen, const double* sig,
-                                                             double* terms) {
-  __shared__ double sh[256];
-  const int b = blockIdx.x;
+// (no __restrict__: inside sm_chain_kernel these arrays were written earlier in the same launch.)  Term b by the first
+// 256 threads of the calling CTA; all of its threads must call.
+__device__ __forceinline__ void sm_gsphi_prior_body(int b, int pp, int p, int mmax, const int* attr, const double* v,
+                                                    const double* w, const int* H, const int* cnt, const SmPlan* plan,
+                                                    const uint8_t* cen, const double* sig, double* terms, double* sh) {
   const int len = pp * mmax;
   double acc = 0.0;
-  if (b < 3) {
+  if (threadIdx.x >= 256) {
+  } else if (b < 3) {
     const int hist = plan->gs_hist[b], sL = plan->gs_sigL[b], st = plan->gs_star[b];
     const int nm = cnt[hist];
     for (int j = threadIdx.x; j < p; j += 256) {
@@ -695,7 +587,7 @@ __global__ void __launch_bounds__(256) sm_gsphi_prior_kernel(int pp, int p, int 
       acc += -log((double)m) + logdensity_hig_d(sig[(size_t)slot * pp + j], v[j], w[j], (double)m);
     }
   }
-  sh[threadIdx.x] = acc;
+  if (threadIdx.x < 256) sh[threadIdx.x] = acc;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
@@ -703,23 +595,28 @@ __global__ void __launch_bounds__(256) sm_gsphi_prior_kernel(int pp, int p, int 
   }
   // terms layout: [4..6] pri, [10..12] gs_phi
   if (threadIdx.x == 0) terms[b < 3 ? 10 + b : 4 + (b - 3)] = sh[0];
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) sm_gsphi_prior_kernel(int pp, int p, int mmax, const int* __restrict__ attr,
+                                                             const double* __restrict__ v, const double* __restrict__ w,
+                                                             const int* __restrict__ H, const int* __restrict__ cnt,
+                                                             const SmPlan* plan, const uint8_t* cen, const double* sig,
+                                                             double* terms) {
+  __shared__ double sh[256];
+  sm_gsphi_prior_body(blockIdx.x, pp, p, mmax, attr, v, w, H, cnt, plan, cen, sig, terms, sh);
 }
 
 // per-member likelihood values feeding loglikelihood_hamming (:393-417) and logprobgs_c_i (:96-161)
 // rowvals[0][r] = LL under its own side's parameters if side 0 else 0
 // rowvals[1][r] = same for side 1 ; rowvals[2][r] = LL under the merged/old parameters
 // rowvals[3][r] = log prob of the member's side under the launch counts (0 for the anchors)
-__global__ void __launch_bounds__(256) sm_rowterms_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
-                                                          const SmInfo* info, const SmPlan* plan,
-                                                          const int* __restrict__ zL, const int* __restrict__ zStar,
-                                                          const int* __restrict__ zState, const int* __restrict__ cnt,
-                                                          const uint8_t* cen, const double* isg, const double* sden,
-                                                          double* __restrict__ rowvals, int stride) {
+__device__ __forceinline__ void sm_rowterms_body(const uint8_t* __restrict__ X, int pp, const int* S, const SmInfo* info,
+                                                 const SmPlan* plan, const int* zL, const int* zStar, const int* zState,
+                                                 const int* cnt, const uint8_t* cen, const double* isg, const double* sden,
+                                                 double* rowvals, int stride, int gw, int nw) {
   const int nS = info->nS;
-  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (w >= nS + 2) return;
-  const int r = (int)w;
+  for (int r = gw; r < nS + 2; r += nw) {
   const int row = r < nS ? S[r] : (r == nS ? info->i1 : info->i2);
   const int* zs = plan->zsel ? zState : zStar;
   const int side = r < nS ? zs[r] : (r - nS);
@@ -746,43 +643,89 @@ __global__ void __launch_bounds__(256) sm_rowterms_kernel(const uint8_t* __restr
     }
     rowvals[3 * (size_t)stride + r] = gc;
   }
+  }
+}
+__global__ void __launch_bounds__(256) sm_rowterms_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
+                                                          const SmInfo* info, const SmPlan* plan,
+                                                          const int* __restrict__ zL, const int* __restrict__ zStar,
+                                                          const int* __restrict__ zState, const int* __restrict__ cnt,
+                                                          const uint8_t* cen, const double* isg, const double* sden,
+                                                          double* __restrict__ rowvals, int stride) {
+  sm_rowterms_body(X, pp, S, info, plan, zL, zStar, zState, cnt, cen, isg, sden, rowvals, stride,
+                   (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), (gridDim.x * blockDim.x) >> 5);
 }
 
 // fixed-order two-stage sums of the four row-value arrays
-__global__ void __launch_bounds__(256) sm_rowreduce1_kernel(const SmInfo* info, const double* __restrict__ rowvals,
-                                                            int stride, double* __restrict__ partial) {
-  __shared__ double sh[256];
-  const int nr = info->nS + 2, q = blockIdx.y;
+// The 256-leaf pairwise tree of the block reductions above, by one warp: lane l holds leaves l, l+32, ..., l+224 in
+// v[0..7].  Same pairs in the same order as the shared-memory tree (o = 128, 64, ..., 1), so the same roundings.
+// Result on lane 0.
+__device__ __forceinline__ double sm_tree256_warp(double* v) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] += v[k + 4];
+  v[0] += v[2];
+  v[1] += v[3];
+  v[0] += v[1];
+  double x = v[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(SMG_FULL, x, o);
+  return x;
+}
+// partial sum bx of array q by one warp (identical to sm_rowreduce1_body)
+__device__ __forceinline__ void sm_rowreduce1_warp(int nS, const double* rowvals, int stride, double* partial, int bx, int q,
+                                                   int lane) {
+  const int nr = nS + 2;
   const int per = (nr + SM_RB - 1) / SM_RB;
-  const int lo = blockIdx.x * per, hi = min(nr, lo + per);
-  double acc = 0.0;
-  for (int r = lo + threadIdx.x; r < hi; r += 256) acc += rowvals[(size_t)q * stride + r];
-  sh[threadIdx.x] = acc;
+  const int lo = bx * per, hi = min(nr, lo + per);
+  double v[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    double acc = 0.0;
+    for (int r = lo + lane + 32 * k; r < hi; r += 256) acc += rowvals[(size_t)q * stride + r];
+    v[k] = acc;
+  }
+  const double t = sm_tree256_warp(v);
+  if (lane == 0) partial[q * SM_RB + bx] = t;
+}
+// (partial sum bx of array q by the first 256 threads of the calling CTA; all of its threads must call)
+__device__ __forceinline__ void sm_rowreduce1_body(int nS, const double* rowvals, int stride, double* partial, int bx, int q,
+                                                   double* sh) {
+  const int nr = nS + 2;
+  const int per = (nr + SM_RB - 1) / SM_RB;
+  const int lo = bx * per, hi = min(nr, lo + per);
+  if (threadIdx.x < 256) {
+    double acc = 0.0;
+    for (int r = lo + threadIdx.x; r < hi; r += 256) acc += rowvals[(size_t)q * stride + r];
+    sh[threadIdx.x] = acc;
+  }
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
     if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) partial[q * SM_RB + blockIdx.x] = sh[0];
+  if (threadIdx.x == 0) partial[q * SM_RB + bx] = sh[0];
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) sm_rowreduce1_kernel(const SmInfo* info, const double* __restrict__ rowvals,
+                                                            int stride, double* __restrict__ partial) {
+  __shared__ double sh[256];
+  sm_rowreduce1_body(info->nS, rowvals, stride, partial, blockIdx.x, blockIdx.y, sh);
 }
 
 // final sums + MH log-ratio in the reference's order of additions + accept decision
-__global__ void __launch_bounds__(256) sm_accept_kernel(const SmInfo* info, const SmPlan* plan, const int* __restrict__ cnt,
-                                                        const double* __restrict__ partial, double gamma,
-                                                        const double* u_inj, RngKey key, double* terms, int* accepted,
-                                                        unsigned long long* stats) {
-  __shared__ double sh[256];
+__device__ __forceinline__ void sm_accept_body(const SmInfo* info, const SmPlan* plan, const int* cnt, const double* partial,
+                                               double gamma, const double* u_inj, const RngKey& key, double* terms,
+                                               int* accepted, unsigned long long* stats, double* sh) {
   __shared__ double tot[4];
-  for (int q = 0; q < 4; q++) {
-    sh[threadIdx.x] = threadIdx.x < SM_RB ? partial[q * SM_RB + threadIdx.x] : 0.0;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-      if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) tot[q] = sh[0];
-    __syncthreads();
+  static_assert(SM_RB == 256, "the final sums are 256-leaf trees");
+  if (threadIdx.x < 128) {  // warp q sums array q
+    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = partial[q * SM_RB + lane + 32 * k];
+    const double t = sm_tree256_warp(v);
+    if (lane == 0) tot[q] = t;
   }
+  __syncthreads();
   if (threadIdx.x != 0) return;
   // terms: 0 log_alpha, 1..3 lg, 4..6 pri, 7..9 ll, 10..12 gs_phi, 13 gs_c, 14 log_prior, 15 log_lik,
   //        16 log_prop, 17 log_ratio, 18 u_accept
@@ -843,16 +786,21 @@ __global__ void __launch_bounds__(256) sm_accept_kernel(const SmInfo* info, cons
   *accepted = acc;
   if (stats && acc) stats[7]++;
 }
+__global__ void __launch_bounds__(256) sm_accept_kernel(const SmInfo* info, const SmPlan* plan, const int* __restrict__ cnt,
+                                                        const double* __restrict__ partial, double gamma,
+                                                        const double* u_inj, RngKey key, double* terms, int* accepted,
+                                                        unsigned long long* stats) {
+  __shared__ double sh[256];
+  sm_accept_body(info, plan, cnt, partial, gamma, u_inj, key, terms, accepted, stats, sh);
+}
 
 // ------------------------------------------------------------------------------------------
 // accept: state <- proposal, labels compacted as clean_var does (common_functions.cpp:296-353)
 // ------------------------------------------------------------------------------------------
 // step 1 (one CTA): parameters, counts, K
-__global__ void __launch_bounds__(256) sm_apply_params_kernel(const SmInfo* info, const int* accepted, int NS, int Kcap,
-                                                              int pp, uint8_t* cen, double* sig, double* isg, double* sden,
-                                                              const int* __restrict__ cnt, int* counts, int* Kptr,
-                                                              int* status) {
-  if (*accepted == 0) return;
+__device__ __forceinline__ void sm_apply_params_body(const SmInfo* info, int NS, int Kcap, int pp, uint8_t* cen, double* sig,
+                                                     double* isg, double* sden, const int* cnt, int* counts, int* Kptr,
+                                                     int* status) {
   const int K = info->K, cA = info->cA, cB = info->cB;
   auto copy = [&](int src, int dst) {
     for (int j = threadIdx.x; j < pp; j += blockDim.x) {
@@ -890,28 +838,328 @@ __global__ void __launch_bounds__(256) sm_apply_params_kernel(const SmInfo* info
     }
   }
 }
-// step 2: labels of the members
+__global__ void __launch_bounds__(256) sm_apply_params_kernel(const SmInfo* info, const int* accepted, int NS, int Kcap,
+                                                              int pp, uint8_t* cen, double* sig, double* isg, double* sden,
+                                                              const int* __restrict__ cnt, int* counts, int* Kptr,
+                                                              int* status) {
+  if (*accepted == 0) return;
+  sm_apply_params_body(info, NS, Kcap, pp, cen, sig, isg, sden, cnt, counts, Kptr, status);
+}
+// step 2: labels of the members (thread gt of nt)
+__device__ __forceinline__ void sm_apply_members_body(const SmInfo* info, const int* S, const int* zStar, int* c, int gt,
+                                                      int nt) {
+  const int nS = info->nS, same = info->same, K = info->K, cB = info->cB;
+  for (int r = gt; r < nS + 2; r += nt) {
+    const int row = r < nS ? S[r] : (r == nS ? info->i1 : info->i2);
+    if (same) {
+      const int side = r < nS ? zStar[r] : (r - nS);
+      c[row] = side == 0 ? K : cB;
+    } else {
+      c[row] = cB;
+    }
+  }
+}
 __global__ void sm_apply_members_kernel(const SmInfo* info, const int* accepted, const int* __restrict__ S,
                                         const int* __restrict__ zStar, int* __restrict__ c) {
   if (*accepted == 0) return;
-  const int nS = info->nS;
-  int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= nS + 2) return;
-  const int row = r < nS ? S[r] : (r == nS ? info->i1 : info->i2);
-  if (info->same) {
-    const int side = r < nS ? zStar[r] : (r - nS);
-    c[row] = side == 0 ? info->K : info->cB;
-  } else {
-    c[row] = info->cB;
-  }
+  sm_apply_members_body(info, S, zStar, c, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 // step 3 (merge only): the last label moves into the hole
-__global__ void sm_apply_relabel_kernel(const SmInfo* info, const int* accepted, int n, int* __restrict__ c) {
-  if (*accepted == 0 || info->same) return;
+__device__ __forceinline__ void sm_apply_relabel_body(const SmInfo* info, int n, int* c, int gt, int nt) {
+  if (info->same) return;
   const int hole = info->cA, last = info->K - 1;
   if (hole == last) return;
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n && c[i] == last) c[i] = hole;
+  for (int i = gt; i < n; i += nt)
+    if (c[i] == last) c[i] = hole;
+}
+__global__ void sm_apply_relabel_kernel(const SmInfo* info, const int* accepted, int n, int* __restrict__ c) {
+  if (*accepted == 0) return;
+  sm_apply_relabel_body(info, n, c, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+
+// ------------------------------------------------------------------------------------------
+// the persistent kernel (see the comment above sm_job_at)
+// ------------------------------------------------------------------------------------------
+struct SmChainArgs {
+  int n, p, pp, mmax, t, r, NS, wide_from, Kcap;
+  double gamma;
+  const uint8_t* X;
+  int* c;        // labels (read by the selection, rewritten when the proposal is accepted)
+  int* counts;   // cluster sizes by label
+  int* Kptr;     // number of clusters
+  int* S;
+  SmInfo* info;
+  SmPlan* plan;
+  uint8_t* cen;
+  double *sig, *isg, *sden;
+  int *H, *cnt, *zL, *zStar, *zState;
+  int* selcnt;   // [grid] members found by each CTA
+  double *dl, *lgt;
+  double *rowvals, *partial, *terms;
+  int* accepted;
+  unsigned long long* stats;
+  PhiArgs phi;  // common fields of the parameter updates (jobs are filled on the device)
+  const double *u_rg, *u_rg_c, *u_rg_s, *u_mg_c, *u_mg_s;  // injected uniforms (bases) or null
+  const double *u_pair, *u_prior_c, *u_prior_s, *u_launch, *u_accept;
+  RngKey key;
+  unsigned* bar;       // grid-barrier counter of this launch (zero on entry)
+  unsigned* bar_next;  // the counter of the next launch: zeroed here
+  int* err;
+};
+
+#define SM_CHAIN_CTAS 120
+#define SM_CHAIN_T 512  // 128 registers per thread: the parameter-update body does not spill
+
+__global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) {
+  // dynamic shared memory: the side histograms of the histogram phase and the scratch of the decision phase
+  // (never live at the same time)
+  extern __shared__ __align__(16) int s_hist[];
+  RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>& M = *reinterpret_cast<RdecideSmem<SM_CHAIN_T * SM_DECIDE_R>*>(s_hist);
+  RdecideSmem<SM_DECIDE_WIDE_CHUNK>& MW = *reinterpret_cast<RdecideSmem<SM_DECIDE_WIDE_CHUNK>*>(s_hist);
+  __shared__ double sh[256];
+  GridBar B{A.bar, 0u, gridDim.x, A.err, A.phi.status};
+  int nS = 0, same = 0;  // known after the selection phase
+  const int n = A.n, p = A.p, pp = A.pp, NSB = A.NS;
+  constexpr int WPB = SM_CHAIN_T / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gwarp = blockIdx.x * WPB + warp, nwarps = gridDim.x * WPB;
+  const int gtid = blockIdx.x * SM_CHAIN_T + tid, gthreads = gridDim.x * SM_CHAIN_T;
+  const size_t len = (size_t)pp * A.mmax;
+  auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
+
+#ifdef SMG_PHI_PROFILE
+  long long tk = clock64();
+#define CHAIN_TICK(k)                                                                   \
+  do {                                                                                  \
+    const long long _t = clock64();                                                     \
+    if (blockIdx.x == 0 && threadIdx.x == 0 && A.phi.prof) A.phi.prof[k] += (unsigned long long)(_t - tk); \
+    tk = _t;                                                                            \
+  } while (0)
+#else
+#define CHAIN_TICK(k)
+#endif
+#ifdef SMG_SM_HT_PROFILE
+#define HT_TICK(k) CHAIN_TICK(k)
+#else
+#define HT_TICK(k)
+#endif
+  // ---- pair and S (split_merge.cpp:263-301): ordered compaction over the whole grid.  Warp w owns the rows
+  // [lo, hi); counts per warp and per CTA, one grid barrier, then every CTA knows the offset of its rows.
+  __shared__ int s_sel[8];
+  __shared__ int s_wcnt[WPB], s_woff[WPB];
+  if (tid == 0) {
+    RngKey k = A.key;
+    k.sub = SUB_SM_SELECT;
+    int i1, i2;
+    sm_pick_pair(n, A.u_pair, k, &i1, &i2);
+    s_sel[0] = i1;
+    s_sel[1] = i2;
+    s_sel[2] = A.c[i1];
+    s_sel[3] = A.c[i2];
+    if (blockIdx.x == 0) *A.bar_next = 0u;
+  }
+  if (blockIdx.x == 0)
+    for (int q = tid; q < 24; q += SM_CHAIN_T) A.terms[q] = 0.0;
+  for (size_t q = gtid; q < 2 * len; q += gthreads) A.H[(size_t)SH_S0 * len + q] = 0;  // current-state side histograms
+  if (gtid == 0) A.cnt[SH_S0] = A.cnt[SH_S1] = 0;
+  __syncthreads();
+  const int i1 = s_sel[0], i2 = s_sel[1], cA = s_sel[2], cB = s_sel[3];
+  // (the CTAs that draw the prior parameters below take no rows when the grid is large enough)
+  const int pri_ctas = 3 * A.phi.nparts;
+  const int sel_warps = ((int)gridDim.x - pri_ctas >= 4 ? (int)gridDim.x - pri_ctas : (int)gridDim.x) * WPB;
+  const int seg = ((n + sel_warps - 1) / sel_warps + 31) & ~31;
+  const int lo = gwarp < sel_warps ? (int)min((long long)n, (long long)gwarp * seg) : n, hi = min(n, lo + seg);
+  {
+    int mine = 0;
+    for (int i = lo + lane; i < hi; i += 32) {
+      const int ci = A.c[i];
+      mine += (i != i1 && i != i2 && (ci == cA || ci == cB));
+    }
+    mine = warp_sum_i(mine);
+    if (lane == 0) s_wcnt[warp] = mine;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    const int v = lane < WPB ? s_wcnt[lane] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(SMG_FULL, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane < WPB) s_woff[lane] = x - v;
+    if (lane == 31) A.selcnt[blockIdx.x] = x;
+  }
+  {  // prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380), on the last CTAs
+    const int b0 = (int)gridDim.x - pri_ctas;
+    if ((int)blockIdx.x >= b0) {
+      const int w = (int)blockIdx.x - b0, k = w % 3;
+      const PhiJob J = sm_job_at(NSB, J_PRI_A + k, SUB_SM_PRIOR, off(A.u_prior_c, (size_t)k * p), off(A.u_prior_s, (size_t)k * p), 0);
+      phi_job_body(A.phi, J, k, w / 3, A.phi.nparts, sh);
+    }
+  }
+  grid_sync(B);
+  HT_TICK(0);
+  if (warp == 0) {
+    int before = 0, total = 0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+      const int v = __ldcg(&A.selcnt[b]);
+      total += v;
+      if (b < (int)blockIdx.x) before += v;
+    }
+    total = warp_sum_i(total);
+    before = warp_sum_i(before);
+    if (lane == 0) {
+      s_sel[4] = total;
+      s_sel[5] = before;
+    }
+  }
+  __syncthreads();
+  nS = s_sel[4];
+  same = (cA == cB);
+  {
+    int offp = s_sel[5] + s_woff[warp];
+    for (int base = lo; base < hi; base += 32) {
+      const int i = base + lane;
+      const int ci = (i < hi) ? A.c[i] : -1;
+      const bool in = (i < hi) && i != i1 && i != i2 && (ci == cA || ci == cB);
+      const unsigned bal = __ballot_sync(SMG_FULL, in);
+      if (in) {
+        const int pos = offp + __popc(bal & ((1u << lane) - 1));
+        A.S[pos] = i;
+        A.zState[pos] = (ci == cA) ? 0 : 1;
+      }
+      offp += __popc(bal);
+    }
+  }
+  if (gtid == 0) sm_fill_info_plan(A.info, A.plan, NSB, i1, i2, nS, cA, cB, *A.Kptr);
+  {  // random launch allocation (split_merge.cpp:346)
+    RngKey k = A.key;
+    k.sub = SUB_SM_LAUNCH;
+    for (int pos = gtid; pos < nS; pos += gthreads) {
+      const double u = get_u(A.u_launch, pos, k, U_SM_LAUNCH, (uint32_t)pos, 0u);
+      const int z = (int)(2.0 * u);
+      A.zL[pos] = z > 1 ? 1 : z;
+    }
+  }
+  grid_sync(B);
+  HT_TICK(1);
+
+  // allocation part of restricted scan q on sides z / slots (slotA, slotB) -> histograms h0, h0+1
+  auto alloc_scan = [&](int* z, int slotA, int slotB, int h0, int q, bool first) {
+    RngKey k = A.key;
+    k.sub = SUB_SM_RG + q;
+    CHAIN_TICK(7);
+    sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, A.lgt, gwarp,
+                    nwarps);
+    // the histograms of the current-state sides (fixed for the whole proposal) ride in the first scan
+    if (first)
+      subset_hist_body(A.X, pp, A.S, nS, A.zState, &A.info->i1, A.mmax, A.H + (size_t)SH_S0 * len, A.cnt + SH_S0, s_hist,
+                       blockIdx.x, gridDim.x);
+    grid_sync(B);
+    CHAIN_TICK(4);
+    if (first && blockIdx.x != 0) {  // ... and their sum, the merged cluster's histogram, while CTA 0 decides
+      const int nt = ((int)gridDim.x - 1) * SM_CHAIN_T;
+      for (int q2 = gtid - SM_CHAIN_T; q2 < (int)len; q2 += nt)
+        A.H[(size_t)SH_M * len + q2] = A.H[(size_t)SH_S0 * len + q2] + A.H[(size_t)SH_S1 * len + q2];
+      if (gtid == SM_CHAIN_T) A.cnt[SH_M] = A.cnt[SH_S0] + A.cnt[SH_S1];
+    }
+    if (blockIdx.x == 0) {
+      if (q >= A.wide_from)
+        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_WIDE_CHUNK / SM_CHAIN_T>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len),
+                                                                       A.cnt + h0, MW);
+      else
+        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_R>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
+    }
+    grid_sync(B);
+    CHAIN_TICK(5);
+    subset_hist_body(A.X, pp, A.S, nS, z, &A.info->i1, A.mmax, A.H + (size_t)h0 * len, nullptr, s_hist, blockIdx.x,
+                     gridDim.x);
+    grid_sync(B);
+    CHAIN_TICK(6);
+  };
+  auto run_jobs = [&](const PhiJob* jobs, int nj) {
+    if ((int)blockIdx.x < nj * A.phi.nparts) phi_job_body(A.phi, jobs[blockIdx.x % nj], blockIdx.x % nj, blockIdx.x / nj, A.phi.nparts, sh);
+    grid_sync(B);
+  };
+
+  const int nsteps = A.t > A.r ? A.t : A.r;
+  for (int q = 0; q < nsteps; q++) {
+    PhiJob j[3];
+    int nj = 0;
+    if (q < A.t) {
+      alloc_scan(A.zL, NSB + SM_SL_A, NSB + SM_SL_B, SH_L0, q, q == 0);
+      for (int side = 0; side < 2; side++)
+        j[nj++] = sm_job_at(NSB, J_L0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+    }
+    if (q < A.r)
+      j[nj++] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + q, off(A.u_mg_c, (size_t)q * p), off(A.u_mg_s, (size_t)q * p), 0);
+    run_jobs(j, nj);
+    if (*(volatile int*)A.err) return;
+  }
+  // proposal = split launch state (sides + the two parameter slots) ...
+  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nS; pos += gridDim.x * blockDim.x) A.zStar[pos] = A.zL[pos];
+  if (blockIdx.x < 2) {
+    const int src = NSB + (blockIdx.x ? SM_SL_B : SM_SL_A), dst = NSB + (blockIdx.x ? SM_ST_B : SM_ST_A);
+    for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
+      A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
+      A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
+      A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
+    }
+    if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
+  }
+  grid_sync(B);
+  // ... + one more restricted scan for a split; the merged cluster's final update in both cases
+  {
+    const int q = A.t;
+    PhiJob j[3];
+    int nj = 0;
+    if (same) {
+      alloc_scan(A.zStar, NSB + SM_ST_A, NSB + SM_ST_B, SH_P0, q, false);
+      for (int side = 0; side < 2; side++)
+        j[nj++] = sm_job_at(NSB, J_P0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+    }
+    j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
+    // the job index enters the Philox counter: keep the merged cluster at index 2 as in the multi-launch path
+    if (!same) {
+      if ((int)blockIdx.x < A.phi.nparts) phi_job_body(A.phi, j[0], 2, blockIdx.x, A.phi.nparts, sh);
+      grid_sync(B);
+    } else {
+      run_jobs(j, nj);
+    }
+  }
+  if (*(volatile int*)A.err) return;
+  HT_TICK(7);
+  // ---- MH terms: the six parameter-density terms on CTAs 0..5, the per-member likelihood terms on the others
+  {
+    const int cb = gridDim.x >= 16 ? 6 : 0;
+    if (blockIdx.x < 6)
+      sm_gsphi_prior_body(blockIdx.x, pp, p, A.mmax, A.phi.attr, A.phi.v, A.phi.w, A.H, A.cnt, A.plan, A.cen, A.sig, A.terms, sh);
+    if ((int)blockIdx.x >= cb)
+      sm_rowterms_body(A.X, pp, A.S, A.info, A.plan, A.zL, A.zStar, A.zState, A.cnt, A.cen, A.isg, A.sden, A.rowvals, n + 2,
+                       ((int)blockIdx.x - cb) * WPB + warp, ((int)gridDim.x - cb) * WPB);
+  }
+  grid_sync(B);
+  HT_TICK(2);
+  for (int vb = gwarp; vb < 4 * SM_RB; vb += nwarps) sm_rowreduce1_warp(nS, A.rowvals, n + 2, A.partial, vb % SM_RB, vb / SM_RB, lane);
+  grid_sync(B);
+  if (blockIdx.x == 0) {
+    RngKey k = A.key;
+    k.sub = SUB_SM_ACCEPT;
+    sm_accept_body(A.info, A.plan, A.cnt, A.partial, A.gamma, A.u_accept, k, A.terms, A.accepted, A.stats, sh);
+  }
+  grid_sync(B);
+  HT_TICK(3);
+  // ---- accept: state <- proposal
+  if (__ldcg(A.accepted) == 0) return;
+  if (blockIdx.x == 0)
+    sm_apply_params_body(A.info, NSB, A.Kcap, pp, A.cen, A.sig, A.isg, A.sden, A.cnt, A.counts, A.Kptr, A.phi.status);
+  sm_apply_members_body(A.info, A.S, A.zStar, A.c, gtid, gthreads);
+  if (same) return;
+  grid_sync(B);
+  sm_apply_relabel_body(A.info, n, A.c, gtid, gthreads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -948,8 +1196,9 @@ static int sm_alloc(smg_chain* ch) {
   }
   SMG_CUDA(cudaFuncSetAttribute(sm_rdecide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(RdecideSmem<SM_DECIDE_WIDE_CHUNK>)));
-  SMG_CUDA(dev_malloc(&W->chain_bar, 2 * sizeof(unsigned), ch->st));
-  SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 2 * sizeof(unsigned), ch->st));
+  SMG_CUDA(dev_malloc(&W->chain_bar, 4 * sizeof(unsigned), ch->st));
+  SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 4 * sizeof(unsigned), ch->st));
+  SMG_CUDA(dev_malloc(&W->selcnt, 256 * sizeof(int), ch->st));
   {
     // the persistent chain kernel needs co-resident CTAs (cooperative launch) and the side histograms in shared memory
     int coop = 0;
@@ -1095,29 +1344,9 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
   auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
   const size_t len = (size_t)pp * ch->mmax;
   const int* same = &W->info->same;
-  // ---- pair, S, plan
-  sm_select_kernel<<<1, 1024, 0, ch->st>>>(n, ch->c, ch->K, T.u_pair, mk_key(ch, SUB_SM_SELECT), B, W->S, W->zState,
-                                           W->info, W->plan, W->cnt, W->terms);
-  ch->h_launches++;
-  SMG_CUDA(cudaGetLastError());
-  // ---- histograms of the current-state sides and of the merged cluster (fixed for the whole proposal)
-  if (sm_hist(ch, W->zState, SH_S0, false, nullptr)) return SMG_ERR_CUDA;
-  sm_hist_add_kernel<<<sm_cdiv(len, 256), 256, 0, ch->st>>>((int)len, W->H, W->cnt, SH_S0, SH_S1, SH_M);
-  ch->h_launches++;
-  // ---- prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380)
-  {
-    PhiJob j[3];
-    for (int k = 0; k < 3; k++)
-      j[k] = sm_job(ch, J_PRI_A + k, SUB_SM_PRIOR, off(T.u_prior_c, (size_t)k * p), off(T.u_prior_s, (size_t)k * p), 0);
-    if (sm_phi(ch, j, 3)) return SMG_ERR_CUDA;
-  }
-  // ---- split launch: random sides then t restricted scans (split_merge.cpp:346-349); the r parameter
-  //      updates of the merge launch (split_merge.cpp:386-387) are an independent chain on the fixed merged
-  //      histogram, so update q of it rides in the same launch as the update of scan q
-  sm_launch_alloc_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, T.u_launch, mk_key(ch, SUB_SM_LAUNCH), W->zL);
-  ch->h_launches++;
   if (W->persistent && ch->t > 0 && !(ch->many && n > 30000)) {
-    // ---- the t launch scans, the r merge-launch updates and the proposal as one cooperative kernel
+    // ---- the whole proposal as one cooperative kernel: selection, launch states, t restricted scans, r merge-launch
+    //      updates, proposal, MH ratio, acceptance
     SmChainArgs CA;
     memset(&CA, 0, sizeof(CA));
     CA.n = n;
@@ -1127,6 +1356,24 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.t = ch->t;
     CA.r = ch->r;
     CA.NS = B;
+    CA.Kcap = ch->Kcap;
+    CA.gamma = ch->gamma;
+    CA.c = ch->c;
+    CA.counts = ch->counts;
+    CA.Kptr = ch->K;
+    CA.plan = W->plan;
+    CA.zState = W->zState;
+    CA.selcnt = W->selcnt;
+    CA.rowvals = W->rowvals;
+    CA.partial = W->partial;
+    CA.terms = W->terms;
+    CA.accepted = ch->accepted_d;
+    CA.stats = ch->stats_d;
+    CA.u_pair = T.u_pair;
+    CA.u_prior_c = T.u_prior_c;
+    CA.u_prior_s = T.u_prior_s;
+    CA.u_launch = T.u_launch;
+    CA.u_accept = T.u_accept;
     CA.wide_from = sm_wide_from();
     CA.X = ch->X;
     CA.S = W->S;
@@ -1153,9 +1400,11 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.u_mg_c = T.u_mg_c;
     CA.u_mg_s = T.u_mg_s;
     CA.key = mk_key(ch, 0);
-    CA.bar = W->chain_bar;
-    CA.err = reinterpret_cast<int*>(W->chain_bar + 1);
-    SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 2 * sizeof(unsigned), ch->st));
+    // two barrier counters used in turn: each launch zeroes the one of the next (no memset between launches)
+    CA.bar = W->chain_bar + W->bar_flip;
+    CA.bar_next = W->chain_bar + (W->bar_flip ^ 1);
+    W->bar_flip ^= 1;
+    CA.err = reinterpret_cast<int*>(W->chain_bar + 2);
     void* kargs[] = {&CA};
     // grid: enough CTAs for the member-likelihood phase of a single chain; a small gang when several chains share the
     // GPU (smg_step_many), where the number of launches per sweep matters more than the latency of one proposal
@@ -1168,8 +1417,24 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
       }
       CA.phi.nparts = phi_parts_for(ch->pp, std::max(1, std::min(want, ctas / 3)));
     }
+    static const bool trace = getenv("SMG_SM_TRACE") != nullptr;  // diagnostic: device time of the persistent kernel
+    static cudaEvent_t tr0, tr1;
+    if (trace) {
+      if (!tr0) {
+        cudaEventCreate(&tr0);
+        cudaEventCreate(&tr1);
+      }
+      cudaEventRecord(tr0, ch->st);
+    }
     const cudaError_t ce =
         cudaLaunchCooperativeKernel((const void*)sm_chain_kernel, dim3(ctas), dim3(SM_CHAIN_T), kargs, W->chain_smem, ch->st);
+    if (trace && ce == cudaSuccess) {
+      cudaEventRecord(tr1, ch->st);
+      cudaEventSynchronize(tr1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, tr0, tr1);
+      fprintf(stderr, "[smgibbs] sm_chain_kernel %.1f us (%d CTAs)\n", 1000.0 * ms, ctas);
+    }
     if (ce == cudaErrorCooperativeLaunchTooLarge || ce == cudaErrorLaunchOutOfResources) {
       // the gang does not fit next to whatever else runs on this device: use the sequence of launches from now on
       (void)cudaGetLastError();
@@ -1178,7 +1443,29 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     }
     SMG_CUDA(ce);
     ch->h_launches++;
-  } else {
+    return 0;
+  }
+  // ---- pair, S, plan
+  sm_select_kernel<<<1, 1024, 0, ch->st>>>(n, ch->c, ch->K, T.u_pair, mk_key(ch, SUB_SM_SELECT), B, W->S, W->zState,
+                                           W->info, W->plan, W->cnt, W->terms);
+  ch->h_launches++;
+  SMG_CUDA(cudaGetLastError());
+  // ---- histograms of the current-state sides and of the merged cluster (fixed for the whole proposal)
+  if (sm_hist(ch, W->zState, SH_S0, false, nullptr)) return SMG_ERR_CUDA;
+  sm_hist_add_kernel<<<sm_cdiv(len, 256), 256, 0, ch->st>>>((int)len, W->H, W->cnt, SH_S0, SH_S1, SH_M);
+  ch->h_launches++;
+  // ---- prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380)
+  {
+    PhiJob j[3];
+    for (int k = 0; k < 3; k++)
+      j[k] = sm_job(ch, J_PRI_A + k, SUB_SM_PRIOR, off(T.u_prior_c, (size_t)k * p), off(T.u_prior_s, (size_t)k * p), 0);
+    if (sm_phi(ch, j, 3)) return SMG_ERR_CUDA;
+  }
+  // ---- split launch: random sides then t restricted scans (split_merge.cpp:346-349); the r parameter
+  //      updates of the merge launch (split_merge.cpp:386-387) are an independent chain on the fixed merged
+  //      histogram, so update q of it rides in the same launch as the update of scan q
+  sm_launch_alloc_kernel<<<sm_cdiv(n, 256), 256, 0, ch->st>>>(W->info, T.u_launch, mk_key(ch, SUB_SM_LAUNCH), W->zL);
+  ch->h_launches++;
   const int nsteps = ch->t > ch->r ? ch->t : ch->r;
   for (int q = 0; q < nsteps; q++) {
     PhiJob j[3];
@@ -1212,7 +1499,6 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
                        off(T.u_rg_s, ((size_t)q * 2 + side) * p), 1);
     j[2] = sm_job(ch, J_MSTAR, SUB_SM_MERGE + ch->r, off(T.u_mg_c, (size_t)ch->r * p), off(T.u_mg_s, (size_t)ch->r * p), 0);
     if (sm_phi(ch, j, 3)) return SMG_ERR_CUDA;
-  }
   }
   // ---- MH terms
   sm_gsphi_prior_kernel<<<6, 256, 0, ch->st>>>(pp, p, ch->mmax, ch->attr, ch->v, ch->w, W->H, W->cnt, W->plan, ch->cen[cur],
