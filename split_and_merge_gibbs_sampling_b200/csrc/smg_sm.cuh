@@ -1344,7 +1344,11 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
   auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
   const size_t len = (size_t)pp * ch->mmax;
   const int* same = &W->info->same;
-  if (W->persistent && ch->t > 0 && !(ch->many && n > 30000)) {
+  static const int many_max_n = [] {
+    const char* e = getenv("SMG_SM_MANY_MAXN");
+    return e ? atoi(e) : 30000;
+  }();
+  if (W->persistent && ch->t > 0 && !(ch->many && n > many_max_n)) {
     // ---- the whole proposal as one cooperative kernel: selection, launch states, t restricted scans, r merge-launch
     //      updates, proposal, MH ratio, acceptance
     SmChainArgs CA;
@@ -1408,7 +1412,11 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     void* kargs[] = {&CA};
     // grid: enough CTAs for the member-likelihood phase of a single chain; a small gang when several chains share the
     // GPU (smg_step_many), where the number of launches per sweep matters more than the latency of one proposal
-    const int ctas = ch->many ? 8 : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
+    static const int many_ctas = [] {
+      const char* e = getenv("SMG_SM_MANY_CTAS");
+      return e ? atoi(e) : 8;
+    }();
+    const int ctas = ch->many ? many_ctas : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
     {  // up to 3 parameter-update jobs run side by side, each split over `nparts` CTAs
       static int want = -1;
       if (want < 0) {
