@@ -79,10 +79,10 @@ static int chain_alloc(smg_chain* ch) {
     const char* e = getenv("SMG_PHI_PARTS");
     ch->phi_parts = phi_parts_for(pp, e ? atoi(e) : pp / 32);  // 32 attributes x PHI_G lanes = one pass of a 256-thread CTA
   }
-  if (dalloc(&ch->c, n) || dalloc(&ch->c_hist, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
+  if (dalloc(&ch->c, n + 4) || dalloc(&ch->c_hist, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
       dalloc(&ch->slot2label, NST))
     return SMG_ERR_CUDA;
-  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n) ||
+  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n + 2) || dalloc(&ch->und0, ((size_t)n + 8191) / 4096 * 4096) || dalloc(&ch->und_blk, (size_t)n / 4096 + 4) ||
       dalloc(&ch->aux_e, (size_t)n * ch->m_aux))
     return SMG_ERR_CUDA;
   const size_t P = (size_t)ch->pool_size;
@@ -95,6 +95,8 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->status, 1) || dalloc(&ch->accepted_d, 1) || dalloc(&ch->stats_d, 8) || dalloc(&ch->scan_job, 4) || dalloc(&ch->scan_prof, 16))
     return SMG_ERR_CUDA;
   SMG_CUDA(cudaMemsetAsync(ch->scan_prof, 0, 128, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->und0, 0, ((size_t)n + 8191) / 4096 * 4096, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->und_blk, 0, ((size_t)n / 4096 + 4) * sizeof(int), ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->status, 0, 4, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, 4, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->stats_d, 0, 64, ch->st));
@@ -116,7 +118,8 @@ static void chain_free(smg_chain* ch) {
                   ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
                   ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->mrg, ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
-                  ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d};
+                  ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d,
+                  ch->c_hist, ch->phi_cnt, ch->und0, ch->und_blk};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ch->st);
   if (ch->st) cudaStreamSynchronize(ch->st);
@@ -216,9 +219,11 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.status = ch->status;
   A.stats = ch->stats_d;
   A.job = ch->scan_job;
+  A.und0 = ch->und0;
+  A.und_blk = ch->und_blk;
   A.prof = ch->scan_prof;
   scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, ch->LLaux,
-                                                                          ch->c, ch->counts, A.log_gamma_m, ch->mrg);
+                                                                          ch->c, ch->counts, A.log_gamma_m, A.u_alloc, A.u_stride, A.key, ch->mrg, ch->und0, ch->und_blk);
   neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, SCAN_PF_BYTES, ch->st>>>(A);  // one cluster
   SMG_CUDA(cudaGetLastError());
   // back to canonical form: labels in c, parameters in label order in the other buffer

@@ -105,6 +105,8 @@ struct smg_chain {
   int cur = 0;
   int *c = nullptr, *K = nullptr, *counts = nullptr, *counts_slot = nullptr, *slot2label = nullptr;
   double *LL = nullptr, *LLaux = nullptr, *mrg = nullptr;
+  int* und_blk = nullptr;   // flagged rows per scan block
+  uint8_t* und0 = nullptr;  // [n padded] precomputed screen flags of the allocation scan (scan_margin_kernel)
   int* aux_e = nullptr;
   uint8_t* pcen = nullptr;
   double *psig = nullptr, *pisg = nullptr, *pden = nullptr, *psden = nullptr;

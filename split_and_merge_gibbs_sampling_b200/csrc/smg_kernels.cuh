@@ -362,6 +362,8 @@ struct ScanArgs {
   double* LL;     // [n][ldl]; columns >= K0 are filled chunk by chunk for clusters born during the pass
   const double* LLaux;
   const double* mrg;  // [n] dominance margins under the start-of-pass counts (scan_margin_kernel)
+  const uint8_t* und0;  // [n padded to 4096] 1 = margin within SCAN_FAST_DRIFT of the threshold (or below)
+  int* und_blk;         // [blocks] number of flagged rows per block of SCAN_BLOCK observations; zeroed again at the end
   const int* aux_e;
   const double* u_alloc;  // injected allocation uniforms (tape + m_aux, stride), or null
   int u_stride;
@@ -450,12 +452,16 @@ __device__ __forceinline__ unsigned cluster_cta_rank() {
 // ---------------------------------------------------------------------------------------------
 #define SCAN_DOMINANCE 44.0
 #define SCAN_SLACK 1e-6  // covers the rounding of the drift arithmetic
+#define SCAN_FAST_DRIFT 0.25  // drift allowance of the precomputed screen flags (und0)
+#define SCAN_BLOCK_ROWS 4096   // = SCAN_BLOCK of the scan kernel
 
 __global__ void __launch_bounds__(256) scan_margin_kernel(int n, const int* __restrict__ Kptr, int ldl, int m_aux,
                                                           const double* __restrict__ LL,
                                                           const double* __restrict__ LLaux, const int* __restrict__ c,
                                                           const int* __restrict__ counts, double log_gamma_m,
-                                                          double* __restrict__ mrg) {
+                                                          const double* u_alloc, int u_stride, RngKey key,
+                                                          double* __restrict__ mrg, uint8_t* __restrict__ und0,
+                                                          int* __restrict__ und_blk) {
   __shared__ double s_lc[SMG_MAX_ENTRIES], s_lcm1[SMG_MAX_ENTRIES];
   const int K = min(*Kptr, SMG_MAX_ENTRIES);
   for (int s = threadIdx.x; s < K; s += blockDim.x) {
@@ -466,24 +472,74 @@ __global__ void __launch_bounds__(256) scan_margin_kernel(int n, const int* __re
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  for (int i = blockIdx.x * wpb + (threadIdx.x >> 5); i < n; i += gridDim.x * wpb) {
+  const int w0 = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+  // Two observations per warp and step (their loads are issued together); the warp maxima go through integer REDUX
+  // on order-preserving keys instead of a butterfly of double-precision shuffles.
+  for (int ib = w0; ib < n; ib += 2 * nw)
+  for (int half = 0; half < 2; half++) {
+    const int i = ib + half * nw;
+    if (i >= n) break;
     const int own = c[i];
     const double* row = LL + (size_t)i * ldl;
-    double a_own = -CUDART_INF, best = -CUDART_INF;
-    for (int e = lane; e < K; e += 32) {
-      const double ll = row[e];
-      if (e == own)
-        a_own = s_lcm1[e] + ll;
-      else
-        best = fmax(best, s_lc[e] + ll);
-    }
-    for (int a = lane; a < m_aux; a += 32) best = fmax(best, log_gamma_m + LLaux[(size_t)i * m_aux + a]);
+    double a_own, best;
+    if (K <= 64 && m_aux <= 32) {
+      const int e0 = lane, e1 = lane + 32;
+      const double v0 = e0 < K ? row[e0] : 0.0, v1 = e1 < K ? row[e1] : 0.0;
+      const double xa = lane < m_aux ? LLaux[(size_t)i * m_aux + lane] : 0.0;
+      double bl = -CUDART_INF, al = -CUDART_INF;
+      if (e0 < K) {
+        if (e0 == own) al = s_lcm1[e0] + v0; else bl = s_lc[e0] + v0;
+      }
+      if (e1 < K) {
+        if (e1 == own) al = s_lcm1[e1] + v1; else bl = fmax(bl, s_lc[e1] + v1);
+      }
+      if (lane < m_aux) bl = fmax(bl, log_gamma_m + xa);
+      best = key_to_double(warp_max_key(sort_key(bl)));
+      a_own = shfl_d(al, own & 31);
+    } else {
+      a_own = -CUDART_INF, best = -CUDART_INF;
+      for (int e = lane; e < K; e += 32) {
+        const double ll = row[e];
+        if (e == own)
+          a_own = s_lcm1[e] + ll;
+        else
+          best = fmax(best, s_lc[e] + ll);
+      }
+      for (int a = lane; a < m_aux; a += 32) best = fmax(best, log_gamma_m + LLaux[(size_t)i * m_aux + a]);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a_own = fmax(a_own, shfl_xor_d(a_own, o));
-      best = fmax(best, shfl_xor_d(best, o));
+      for (int o = 16; o > 0; o >>= 1) {
+        a_own = fmax(a_own, shfl_xor_d(a_own, o));
+        best = fmax(best, shfl_xor_d(best, o));
+      }
     }
-    if (lane == 0) mrg[i] = (a_own > -CUDART_INF) ? a_own - best : -CUDART_INF;
+    double mg = (a_own > -CUDART_INF) ? a_own - best : -CUDART_INF;
+    if (a_own > -CUDART_INF && mg <= SCAN_DOMINANCE + 2.0 * SCAN_SLACK) {
+      // Not dominated -- but the observation's uniform is known (counter-based stream, or the injected tape), and
+      // with R = (mass of all other entries) / (own mass) the draw returns `own` iff own is the largest entry and
+      // u <= 1/(1+R).  If every other entry gains at most D nats on the own one, R grows at most by e^D: the
+      // outcome stays `own` while D < log(min(1, (1-u)/u) / R).  Stored as an equivalent margin, so the scan's drift
+      // test covers it unchanged; only observations whose draw really is close to a boundary (or moves) are left
+      // for the exact evaluation.
+      double r = 0.0;
+      for (int e = lane; e < K; e += 32)
+        if (e != own) r += exp(s_lc[e] + row[e] - a_own);
+      for (int a = lane; a < m_aux; a += 32) r += exp(log_gamma_m + LLaux[(size_t)i * m_aux + a] - a_own);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) r += shfl_xor_d(r, o);
+      const double u = get_u(u_alloc, (size_t)i * u_stride, key, U_ALLOC, (uint32_t)i, 0u);
+      const double room = fmin(1.0, (1.0 - u) / u);
+      if (r > 0.0 && room > 0.0) {
+        const double dtol = log(room / r) - 1e-5;  // the slack covers the rounding of r and of the exact evaluation
+        if (dtol > 0.0) mg = fmax(mg, dtol + SCAN_DOMINANCE + SCAN_SLACK);
+      }
+    }
+    if (lane == 0) {
+      mrg[i] = mg;
+      // the scan's screen, precomputed for as long as the counts have drifted by less than SCAN_FAST_DRIFT nats
+      const bool flag = !(mg > SCAN_DOMINANCE + SCAN_SLACK + SCAN_FAST_DRIFT);
+      und0[i] = flag;
+      if (flag) atomicAdd(&und_blk[i / SCAN_BLOCK_ROWS], 1);  // flagged rows per scan block (zeroed by the scan kernel)
+    }
   }
 }
 
@@ -500,6 +556,7 @@ struct ScanState {
   double lcm1_0[SMG_MAX_ENTRIES];  // log (n0_k - 1)
   double dminus[SMG_MAX_ENTRIES];
   double Dplus;
+  double maxdm;  // monotone upper bound of dminus over the clusters that had more than one member at the start
   int evt[SMG_SCAN_WARPS];
   int row[SMG_SCAN_WARPS];
   unsigned und[4 * SMG_SCAN_WARPS];  // undecided rows of the current block of 4096 observations (bit per row)
@@ -708,18 +765,22 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 }
 
 
-// Ring of SCAN_PF_DEPTH chunks of (slot, margin) pairs in shared memory, filled with cp.async (LDGSTS): every
-// thread copies the pair of "its" observation of a chunk SCAN_PF_DEPTH chunks ahead and later reads back only what
-// it copied itself, so cp.async.wait_group is the only synchronisation needed and a chunk with nothing to evaluate
-// costs a barrier, not a memory round trip.
-#define SCAN_PF_DEPTH 8
+// Shared-memory staging of the (slot, margin) pairs of one block of SCAN_BLOCK observations.  It is filled on demand
+// with 16-byte loads, only for blocks whose rows need the per-row screen or the serial walk: with the precomputed
+// screen flags a quiet block never reads it.  (A cp.async ring two blocks ahead was measured at ~5500 cycles per block
+// of copy issue/queueing on the one scanner SM, more than everything else in a quiet block.)
+#define SCAN_PF_DEPTH 4  // = SCAN_SUPER chunks of 1024 observations
 #define SCAN_DENSE_ENTER 6    // events in a row at the head of their batch before warp 0 goes serial
 #define SCAN_DENSE_LEAVE 48   // rows in a row without a move before it hands back to the block
-#define SCAN_SUPER 4  // ring slots (chunks of 1024 observations) screened and evaluated together
+#define SCAN_SUPER 4  // chunks of 1024 observations screened and evaluated together
 #define SCAN_BLOCK (SCAN_SUPER * SCAN_CHUNK)
-#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12)
+#define SCAN_BLKCNT_MAX 1024  // per-block flag counts kept in shared memory (larger n: read from global)
+#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4)
 __device__ __forceinline__ void scan_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void scan_cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void scan_cp_async8(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -742,6 +803,7 @@ __device__ __forceinline__ void scan_apply_move(const ScanArgs& A, ScanState& S,
   auto drift = [&](int s) {
     if (s >= K0) return;
     S.dminus[s] = (S.cnt[s] > 1) ? (S.lcm1_0[s] - S.logcm1[s]) : CUDART_INF;
+    if (S.lcm1_0[s] > -CUDART_INF && S.dminus[s] > S.maxdm) S.maxdm = S.dminus[s];
     const double dp = S.logc[s] - S.lc0[s];
     if (dp > S.Dplus) S.Dplus = dp;  // monotone upper bound
   };
@@ -824,6 +886,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     S.next = K0;
     S.err = 0;
     S.Dplus = 0.0;
+    S.maxdm = 0.0;
     S.stats[0] = S.stats[1] = S.stats[2] = S.stats[3] = 0;
     if (K0 + m > SMG_MAX_ENTRIES) S.err |= ST_TOO_MANY_ENTRIES;
     if (K0 > A.K0cap) S.err |= ST_LL_COLS;
@@ -852,21 +915,13 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     abort_pass = true;
   }
 
-  // prefetch ring (see SCAN_PF_DEPTH): one cp.async group per chunk, committed even when empty
+  // staging buffers of the current block (see SCAN_PF_DEPTH)
   extern __shared__ __align__(16) unsigned char s_ring[];
-  double* ring_mg = reinterpret_cast<double*>(s_ring);                                    // [DEPTH][1024]
-  int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [DEPTH][1024]
-  auto issue_chunk = [&](int chunk) {
-    const long long i = (long long)chunk * SCAN_CHUNK + tid;
-    if (i < n) {
-      const int slot = chunk % SCAN_PF_DEPTH;
-      scan_cp_async8(&ring_mg[slot * SCAN_CHUNK + tid], A.mrg + i);
-      scan_cp_async4(&ring_own[slot * SCAN_CHUNK + tid], A.c + i);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-#pragma unroll
-  for (int q = 0; q < SCAN_PF_DEPTH; q++) issue_chunk(q);
+  double* ring_mg = reinterpret_cast<double*>(s_ring);                                    // [SCAN_BLOCK]
+  int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [SCAN_BLOCK]
+  int* s_blkcnt = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12);       // [SCAN_BLKCNT_MAX]
+  for (int b = tid; b < SCAN_BLKCNT_MAX && (long long)b * SCAN_BLOCK < n; b += blockDim.x) s_blkcnt[b] = A.und_blk[b];
+  __syncthreads();
 
   // can observation i (slot `own`, margin `mg`) be anything but a certain non-event under the current state?
   auto undecided = [&](int i, int own, double mg) -> bool {
@@ -887,10 +942,36 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   // Blocks of SCAN_SUPER ring slots (SCAN_BLOCK = 4096 observations): thread t screens rows t, t+1024, ...; the
   // undecided rows of the whole block are evaluated together, so a quiet block costs one barrier and a block with a
   // handful of undecided rows one evaluation round instead of one per 1024 rows.
+  static_assert(SCAN_BLOCK == SCAN_BLOCK_ROWS, "block size of the precomputed screen");
   for (int i0 = 0, blk = 0; i0 < n && !abort_pass; i0 += SCAN_BLOCK, blk++) {
     const int nrows = min(SCAN_BLOCK, n - i0);
-    asm volatile("cp.async.wait_group %0;" ::"n"(SCAN_PF_DEPTH - SCAN_SUPER) : "memory");  // this block's slots have landed
-    const int slot0 = (blk * SCAN_SUPER) % SCAN_PF_DEPTH;
+    const int cnt_cur = blk < SCAN_BLKCNT_MAX ? s_blkcnt[blk] : A.und_blk[blk];
+    // a block without a flagged row, under a state the flags are valid for: nothing to do (every thread reads the
+    // same shared values; they only change in the event handling, between barriers)
+    if (cnt_cur == 0 && S.next == K0 && S.maxdm + S.Dplus <= SCAN_FAST_DRIFT) {
+      if (tid == 0) S.stats[0]++;
+      continue;
+    }
+    const unsigned und_cur = *reinterpret_cast<const unsigned*>(A.und0 + i0 + 4 * tid);  // flags of rows 4*tid.. (und0 is padded)
+    // The staging buffers are filled only when somebody reads them (block-uniform call sites).  mrg and c are padded,
+    // and rows the scan has not reached still hold their start-of-pass slot in c.
+    bool ring_ready = false;
+    auto ring_wait = [&]() {
+      if (ring_ready) return;
+#pragma unroll
+      for (int k = 0; k < SCAN_BLOCK / 2 / (SMG_SCAN_WARPS * 32); k++) {
+        const int idx = 2 * (k * SMG_SCAN_WARPS * 32 + tid);
+        if (i0 + idx < n) *reinterpret_cast<double2*>(&ring_mg[idx]) = __ldcg(reinterpret_cast<const double2*>(A.mrg + i0 + idx));
+      }
+#pragma unroll
+      for (int k = 0; k < SCAN_BLOCK / 4 / (SMG_SCAN_WARPS * 32); k++) {
+        const int idx = 4 * (k * SMG_SCAN_WARPS * 32 + tid);
+        if (i0 + idx < n) *reinterpret_cast<int4*>(&ring_own[idx]) = __ldcg(reinterpret_cast<const int4*>(A.c + i0 + idx));
+      }
+      __syncthreads();
+      ring_ready = true;
+    };
+    const int slot0 = 0;
     SCAN_TICK(0);
     int start = 0;          // rows [0, start) of the block are final
     bool screened = false;  // the undecided set below is valid for the current state
@@ -904,6 +985,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       // SCAN_DENSE_LEAVE rows without a move, the end of the block, or a draw the block must handle together
       // (a new cluster: its column is filled by the whole cluster of CTAs; an error).
       if (dense_run >= SCAN_DENSE_ENTER && S.K + m <= 64) {
+        ring_wait();
         __syncthreads();
         if (warp == 0) {
           int r = start, calm = 0;
@@ -945,8 +1027,27 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       // In quiet stretches the whole block is screened at once; while events are dense (W small: every event
       // invalidates the screen) only the 1024-row slice that holds `start` is, the later ones when they are reached.
       if (!screened) {
+        // While no cluster was born in this pass and the counts have drifted by less than SCAN_FAST_DRIFT nats, the
+        // flags written by scan_margin_kernel ARE the screen: 4 rows per thread, no per-row arithmetic.
+        const bool fast = (S.next == K0) && (S.maxdm + S.Dplus <= SCAN_FAST_DRIFT);  // (start-of-pass singletons are flagged anyway)
         const int q0 = start / SCAN_CHUNK;
-        const int q1 = (W == SMG_SCAN_WARPS) ? SCAN_SUPER : min(SCAN_SUPER, q0 + 1);
+        const int q1 = (fast || W == SMG_SCAN_WARPS) ? SCAN_SUPER : min(SCAN_SUPER, q0 + 1);
+        if (fast) {
+          const int r4 = tid * 4;
+          unsigned nib = 0;
+          if (r4 < nrows) {
+            const unsigned f = und_cur;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+              if (((f >> (8 * b)) & 0xffu) && r4 + b >= start && r4 + b < nrows) nib |= 1u << b;
+          }
+          unsigned wv = nib << (4 * (lane & 7));
+          wv |= __shfl_xor_sync(SMG_FULL, wv, 1);
+          wv |= __shfl_xor_sync(SMG_FULL, wv, 2);
+          wv |= __shfl_xor_sync(SMG_FULL, wv, 4);
+          if ((lane & 7) == 0) S.und[tid >> 3] = wv;  // word w covers rows [32w, 32w + 32) of the block
+        } else {
+        ring_wait();
 #pragma unroll
         for (int q = 0; q < SCAN_SUPER; q++) {
           const int r = q * SCAN_CHUNK + tid;
@@ -955,6 +1056,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             und = undecided(i0 + r, ring_own[(slot0 + q) * SCAN_CHUNK + tid], ring_mg[(slot0 + q) * SCAN_CHUNK + tid]);
           const unsigned b = __ballot_sync(SMG_FULL, und);
           if (lane == 0) S.und[q * SMG_SCAN_WARPS + warp] = b;  // word w covers rows [32w, 32w + 32) of the block
+        }
         }
         scr_rows = min(nrows, q1 * SCAN_CHUNK);
         screened = true;
@@ -1022,7 +1124,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       if (myrow >= 0 && ne > SMG_MAX_ENTRIES) code = -3;
       if (myrow >= 0 && ne <= SMG_MAX_ENTRIES) {
         const int i = i0 + myrow;
-        const int old_slot = ring_own[(slot0 + myrow / SCAN_CHUNK) * SCAN_CHUNK + (myrow % SCAN_CHUNK)];
+        const int old_slot = __ldcg(&A.c[i]);  // rows the scan has not reached still hold their start-of-pass slot
         code = (ne <= 64) ? scan_eval_row<2>(A, S, i, old_slot, K, lane) : scan_eval_row_wide(A, S, i, old_slot, K, lane);
       }
       if (lane == 0) {
@@ -1101,6 +1203,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
           auto drift = [&](int s) {
             if (s >= K0) return;
             S.dminus[s] = (S.cnt[s] > 1) ? (S.lcm1_0[s] - S.logcm1[s]) : CUDART_INF;
+            if (S.lcm1_0[s] > -CUDART_INF && S.dminus[s] > S.maxdm) S.maxdm = S.dminus[s];
             const double dp = S.logc[s] - S.lc0[s];
             if (dp > S.Dplus) S.Dplus = dp;  // monotone upper bound
           };
@@ -1132,9 +1235,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       __syncthreads();
       SCAN_TICK(5);
     }
-    __syncthreads();  // everybody is done with this block's ring slots
-#pragma unroll
-    for (int q = 0; q < SCAN_SUPER; q++) issue_chunk(blk * SCAN_SUPER + SCAN_PF_DEPTH + q);  // refill them, two blocks ahead
+    __syncthreads();  // everybody is done with this block's staging buffers and bit map
   }
 #ifdef SMG_SCAN_PROFILE
   if (tid == 0 && A.prof) {
@@ -1142,6 +1243,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     for (int q = 0; q < 8; q++) A.prof[q] += (unsigned long long)pc[q];
   }
 #endif
+  for (int b = tid; b * SCAN_BLOCK < n; b += blockDim.x) A.und_blk[b] = 0;  // for the next pass
   // release the helpers
   if (tid == 0) A.job[0] = -1;
   cluster_sync_all();

@@ -1219,7 +1219,7 @@ static void sm_free(smg_chain* ch) {
   if (!W) return;
   void* ptrs[] = {W->S,       W->zL,      W->zStar, W->zState, W->info,    W->plan,    W->H,      W->cnt,
                   W->rg_dl,   W->rg_lgt,  W->rowvals, W->partial, W->terms, W->chain_bar, W->u_pair,  W->u_prior_c, W->u_prior_s,
-                  W->u_launch, W->u_rg,   W->u_rg_c, W->u_rg_s, W->u_mg_c,  W->u_mg_s,  W->u_accept};
+                  W->u_launch, W->u_rg,   W->u_rg_c, W->u_rg_s, W->u_mg_c,  W->u_mg_s,  W->u_accept, W->selcnt};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ch->st);
   delete W;
