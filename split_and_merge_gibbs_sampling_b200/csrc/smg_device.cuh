@@ -96,6 +96,20 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ int warp_sum_i(int v) { return __reduce_add_sync(SMG_FULL, v); }
 
+// The 256-leaf pairwise tree of the block reductions (sh[t] += sh[t + o], o = 128 .. 1), by one warp: lane l holds leaves l, l+32, ..., l+224 in
+// v[0..7].  Same pairs in the same order as the shared-memory tree (o = 128, 64, ..., 1), so the same roundings.
+// Result on lane 0.
+__device__ __forceinline__ double tree256_warp(double* v) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] += v[k + 4];
+  v[0] += v[2];
+  v[1] += v[3];
+  v[0] += v[1];
+  double x = v[0];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(SMG_FULL, x, o);
+  return x;
+}
 // order-preserving map double -> uint64 (no NaNs expected)
 __device__ __forceinline__ uint64_t sort_key(double v) {
   uint64_t b = (uint64_t)__double_as_longlong(v);

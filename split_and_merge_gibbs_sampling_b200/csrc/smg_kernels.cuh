@@ -234,6 +234,10 @@ __global__ void __launch_bounds__(256, 2) hamming_ll_block_t16_kernel(const uint
       line[15 ^ sz] = s01 + s23;
     }
     __syncthreads();
+    // (the last slot tile is rarely full: a warp whose four slots all lie beyond K is skipped -- at K = 50 that is 12
+    // of the 64 columns of the two tiles)
+    const int ncol = K - (slot0 + wg * 4);
+    if (ncol > 0)
 #pragma unroll
     for (int jw = 0; jw < LLB_JT / 4; jw++) {
       // byte b of the swizzle constant is 8 when bit b of the word index is set
@@ -1759,17 +1763,18 @@ __device__ __forceinline__ void phi_job_body(const PhiArgs& A, const PhiJob& J, 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  double acc = 0.0;
-  if (threadIdx.x < 256) {
-    for (int j = threadIdx.x; j < A.p; j += 256) acc += __ldcg(&A.den[(size_t)J.dst * A.pp + j]);
-    sh[threadIdx.x] = acc;
+  if (threadIdx.x < 32) {  // thread t of the 256-thread block reduction summed j = t, t + 256, ...: same leaves, same tree
+    const int lane = threadIdx.x;
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      double acc = 0.0;
+      for (int j = lane + 32 * k; j < A.p; j += 256) acc += __ldcg(&A.den[(size_t)J.dst * A.pp + j]);
+      v[k] = acc;
+    }
+    const double t = tree256_warp(v);
+    if (lane == 0) A.sden[J.dst] = t;
   }
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) A.sden[J.dst] = sh[0];
 }
 
 

@@ -180,6 +180,66 @@ __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, i
   const uint8_t *cA = cen + (size_t)slotA * pp, *cB = cen + (size_t)slotB * pp;
   const double *wA = isg + (size_t)slotA * pp, *wB = isg + (size_t)slotB * pp;
   const double sdA = sden[slotA], sdB = sden[slotB];
+  if (pp <= 256) {
+    // One 8-attribute slice per lane: the two parameter vectors go to registers once, and two members are in flight
+    // per warp (their index and data loads are issued together) -- the phase is a chain of memory latencies.
+    // Same per-lane order of additions and the same butterfly as warp_mismatch_dot.
+    const int j0 = lane * 8;
+    const bool act = j0 < pp;
+    uint2 ca = make_uint2(0u, 0u), cb = make_uint2(0u, 0u);
+    double wa[8], wb[8];
+#pragma unroll
+    for (int b = 0; b < 8; b++) wa[b] = wb[b] = 0.0;
+    if (act) {
+      ca = *reinterpret_cast<const uint2*>(cA + j0);
+      cb = *reinterpret_cast<const uint2*>(cB + j0);
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const double2 ta = reinterpret_cast<const double2*>(wA + j0)[b], tb = reinterpret_cast<const double2*>(wB + j0)[b];
+        wa[2 * b] = ta.x, wa[2 * b + 1] = ta.y;
+        wb[2 * b] = tb.x, wb[2 * b + 1] = tb.y;
+      }
+    }
+    auto dot = [&](const uint2 xv, const uint2 cv, const double* w) {
+      const uint32_t m0 = __vcmpne4(xv.x, cv.x), m1 = __vcmpne4(xv.y, cv.y);
+      double acc = 0.0;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        if (m0 & (0xffu << (8 * b))) acc += w[b];
+      }
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        if (m1 & (0xffu << (8 * b))) acc += w[4 + b];
+      return acc;
+    };
+    for (int pos0 = gwarp; pos0 < nS; pos0 += 2 * nwarps) {
+      const int pos1 = pos0 + nwarps;
+      const bool has1 = pos1 < nS;
+      const int r0 = S[pos0], r1 = has1 ? S[pos1] : r0;
+      uint2 x0 = ca, x1 = ca;
+      if (act) {
+        x0 = *reinterpret_cast<const uint2*>(X + (size_t)r0 * pp + j0);
+        x1 = *reinterpret_cast<const uint2*>(X + (size_t)r1 * pp + j0);
+      }
+      double a0 = act ? dot(x0, ca, wa) : 0.0, b0 = act ? dot(x0, cb, wb) : 0.0;
+      double a1 = act ? dot(x1, ca, wa) : 0.0, b1 = act ? dot(x1, cb, wb) : 0.0;
+      a0 = warp_sum(a0);
+      b0 = warp_sum(b0);
+      a1 = warp_sum(a1);
+      b1 = warp_sum(b1);
+      if (lane == 0) {
+        const double u = get_u(u_inj, pos0, key, U_SM_RGIBBS, (uint32_t)pos0, 0u);
+        dl[pos0] = (-a0 - sdA) - (-b0 - sdB);
+        lgt[pos0] = log(u / (1.0 - u));
+      }
+      if (lane == 1 && has1) {
+        const double u = get_u(u_inj, pos1, key, U_SM_RGIBBS, (uint32_t)pos1, 0u);
+        dl[pos1] = (-a1 - sdA) - (-b1 - sdB);
+        lgt[pos1] = log(u / (1.0 - u));
+      }
+    }
+    return;
+  }
   for (int pos = gwarp; pos < nS; pos += nwarps) {
     const uint8_t* x = X + (size_t)S[pos] * pp;
     const double llA = -warp_mismatch_dot(x, cA, wA, pp, lane) - sdA;
@@ -656,20 +716,6 @@ __global__ void __launch_bounds__(256) sm_rowterms_kernel(const uint8_t* __restr
 }
 
 // fixed-order two-stage sums of the four row-value arrays
-// The 256-leaf pairwise tree of the block reductions above, by one warp: lane l holds leaves l, l+32, ..., l+224 in
-// v[0..7].  Same pairs in the same order as the shared-memory tree (o = 128, 64, ..., 1), so the same roundings.
-// Result on lane 0.
-__device__ __forceinline__ double sm_tree256_warp(double* v) {
-#pragma unroll
-  for (int k = 0; k < 4; k++) v[k] += v[k + 4];
-  v[0] += v[2];
-  v[1] += v[3];
-  v[0] += v[1];
-  double x = v[0];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(SMG_FULL, x, o);
-  return x;
-}
 // partial sum bx of array q by one warp (identical to sm_rowreduce1_body)
 __device__ __forceinline__ void sm_rowreduce1_warp(int nS, const double* rowvals, int stride, double* partial, int bx, int q,
                                                    int lane) {
@@ -683,7 +729,7 @@ __device__ __forceinline__ void sm_rowreduce1_warp(int nS, const double* rowvals
     for (int r = lo + lane + 32 * k; r < hi; r += 256) acc += rowvals[(size_t)q * stride + r];
     v[k] = acc;
   }
-  const double t = sm_tree256_warp(v);
+  const double t = tree256_warp(v);
   if (lane == 0) partial[q * SM_RB + bx] = t;
 }
 // (partial sum bx of array q by the first 256 threads of the calling CTA; all of its threads must call)
@@ -722,7 +768,7 @@ __device__ __forceinline__ void sm_accept_body(const SmInfo* info, const SmPlan*
     double v[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) v[k] = partial[q * SM_RB + lane + 32 * k];
-    const double t = sm_tree256_warp(v);
+    const double t = tree256_warp(v);
     if (lane == 0) tot[q] = t;
   }
   __syncthreads();
@@ -881,7 +927,7 @@ __global__ void sm_apply_relabel_kernel(const SmInfo* info, const int* accepted,
 // the persistent kernel (see the comment above sm_job_at)
 // ------------------------------------------------------------------------------------------
 struct SmChainArgs {
-  int n, p, pp, mmax, t, r, NS, wide_from, Kcap;
+  int n, p, pp, mmax, t, r, NS, wide_from, Kcap, hist_ctas;
   double gamma;
   const uint8_t* X;
   int* c;        // labels (read by the selection, rewritten when the proposal is accepted)
@@ -1073,8 +1119,10 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     }
     grid_sync(B);
     CHAIN_TICK(5);
-    subset_hist_body(A.X, pp, A.S, nS, z, &A.info->i1, A.mmax, A.H + (size_t)h0 * len, nullptr, s_hist, blockIdx.x,
-                     gridDim.x);
+    // (every participating CTA flushes 2*len counters with global atomics: fewer CTAs than the grid do it)
+    if ((int)blockIdx.x < A.hist_ctas)
+      subset_hist_body(A.X, pp, A.S, nS, z, &A.info->i1, A.mmax, A.H + (size_t)h0 * len, nullptr, s_hist, blockIdx.x,
+                       A.hist_ctas);
     grid_sync(B);
     CHAIN_TICK(6);
   };
@@ -1417,6 +1465,13 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
       return e ? atoi(e) : 8;
     }();
     const int ctas = ch->many ? many_ctas : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
+    {
+      static const int want_hist = [] {
+        const char* e = getenv("SMG_SM_HIST_CTAS");
+        return e ? atoi(e) : 1 << 20;
+      }();
+      CA.hist_ctas = std::max(1, std::min(ctas, want_hist));
+    }
     {  // up to 3 parameter-update jobs run side by side, each split over `nparts` CTAs
       static int want = -1;
       if (want < 0) {
