@@ -27,8 +27,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "gibbs_split_merge_sweeps_per_sec"
 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch at the metric config (ncu --set full)
-K1_DRAM_TRAFFIC_BYTES = 31398656  # 27.15 MB read + 4.25 MB written
-K1_DRAM_TRAFFIC_SOURCE = "profiles/r01_ncu_full_fused_raw.csv (ncu --set full, one launch at the metric config)"
+K1_DRAM_TRAFFIC_BYTES = 31017216  # 27.13 MB read + 3.89 MB written
+K1_DRAM_TRAFFIC_SOURCE = "profiles/r01_ncu_full_final2_raw.csv (ncu --set full, one launch at the metric config)"
 UNIT = "sweeps/s"
 
 
