@@ -44,28 +44,49 @@ def run_markov_chain(data, attrisize, gamma, v, w, verbose=0, m=5, iterations=10
                                   int(r), int(bool(neal8)), int(bool(split_merge)), int(n8_step_size), int(sam_step_size),
                                   int(thinning), C.c_ulonglong(int(seed) & (2**64 - 1)), int(device), C.byref(res))
     lb.check(rc)
-    try:
-        it = res.iterations
-        total = np.ctypeslib.as_array(res.total_cls, shape=(max(it, 1),))[:it].copy()
-        c_all = np.ctypeslib.as_array(res.c_i, shape=(max(it, 1), n))[:it].copy()
-        off = np.ctypeslib.as_array(res.phi_offset, shape=(it + 1,)).copy()
-        nphi = int(off[-1])
-        cen = np.ctypeslib.as_array(res.centers, shape=(max(nphi, 1), p))[:nphi].copy()
-        sig = np.ctypeslib.as_array(res.sigmas, shape=(max(nphi, 1), p))[:nphi].copy()
-        out = {
-            "total_cls": [int(k) for k in total],
-            "c_i": [c_all[i] for i in range(it)],
-            "centers": [[cen[q] for q in range(off[i], off[i + 1])] for i in range(it)],
-            "sigmas": [[sig[q] for q in range(off[i], off[i + 1])] for i in range(it)],
-            "loglikelihood": np.ctypeslib.as_array(res.loglikelihood, shape=(max(it, 1),))[:it].copy(),
-            "final_ass": np.ctypeslib.as_array(res.final_ass, shape=(n,)).copy(),
-            "time": int(res.time),
-            "accepted": np.ctypeslib.as_array(res.accepted, shape=(max(it, 1),))[:it].copy(),
-            "seconds": float(res.seconds),
-        }
-    finally:
-        lib.smg_free_results(C.byref(res))
-    return out
+    # The big result arrays (allocation trace, centres, sigmas) are NOT copied: the numpy arrays below are views of the
+    # library's buffers, which are released when the last of them is garbage collected.
+    owner = _ResultsOwner(lib, res)
+    it = res.iterations
+    total = _view(res.total_cls, max(it, 1), C.c_int, owner)[:it]
+    c_all = _view(res.c_i, max(it, 1) * n, C.c_int, owner).reshape(max(it, 1), n)[:it]
+    off = _view(res.phi_offset, it + 1, C.c_longlong, owner)
+    nphi = int(off[-1])
+    cen = _view(res.centers, max(nphi, 1) * p, C.c_double, owner).reshape(max(nphi, 1), p)[:nphi]
+    sig = _view(res.sigmas, max(nphi, 1) * p, C.c_double, owner).reshape(max(nphi, 1), p)[:nphi]
+    offl = off.tolist()
+    return {
+        "total_cls": total.tolist(),
+        "c_i": list(c_all),
+        "centers": [list(cen[offl[i]:offl[i + 1]]) for i in range(it)],
+        "sigmas": [list(sig[offl[i]:offl[i + 1]]) for i in range(it)],
+        "loglikelihood": _view(res.loglikelihood, max(it, 1), C.c_double, owner)[:it].copy(),
+        "final_ass": _view(res.final_ass, n, C.c_int, owner).copy(),
+        "time": int(res.time),
+        "accepted": _view(res.accepted, max(it, 1), C.c_int, owner)[:it].copy(),
+        "seconds": float(res.seconds),
+    }
+
+
+class _ResultsOwner:
+    """Keeps an smg_results alive for as long as a numpy view of one of its buffers exists."""
+
+    def __init__(self, lib, res):
+        self.lib, self.res = lib, res
+
+    def __del__(self):
+        try:
+            self.lib.smg_free_results(C.byref(self.res))
+        except Exception:
+            pass
+
+
+def _view(ptr, count, ctype, owner):
+    if not ptr:  # nothing was allocated (failed or empty run)
+        return np.zeros(count, dtype=np.ctypeslib.as_array((ctype * 1)()).dtype)
+    buf = (ctype * count).from_address(C.addressof(ptr.contents))
+    buf._owner = owner  # numpy keeps `buf` as the base of the array, `buf` keeps the owner
+    return np.ctypeslib.as_array(buf)
 
 
 class Chain:

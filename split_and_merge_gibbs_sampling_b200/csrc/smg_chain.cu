@@ -1103,7 +1103,23 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   out->loglikelihood = (double*)calloc(std::max(iterations, 1), sizeof(double));
   out->final_ass = (int*)calloc(n, sizeof(int));
   out->accepted = (int*)calloc(std::max(iterations, 1), sizeof(int));
-  std::vector<double> cen, sg;
+  // centres / sigmas of the kept iterations grow in malloc'ed buffers that are handed to the caller as they are
+  // (realloc of a large block is a remap, and there is no final copy)
+  struct Grow {
+    double* p = nullptr;
+    size_t size = 0, cap = 0;
+    bool extend(size_t add) {
+      if (size + add > cap) {
+        const size_t nc = std::max<size_t>(std::max<size_t>(2 * cap, size + add), 1 << 16);
+        double* q = (double*)realloc(p, nc * sizeof(double));
+        if (!q) return false;
+        p = q;
+        cap = nc;
+      }
+      size += add;
+      return true;
+    }
+  } cen, sg;
   // Snapshots (launcher.cpp:140-153) leave the device asynchronously: every kept iteration enqueues its copies
   // into one of RING pinned slots behind the sweep on the chain's stream and the host only waits for a slot
   // when it comes round again, so sweeps are launched back to back.
@@ -1164,13 +1180,12 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
     out->loglikelihood[slot] = *S.ll;
     memcpy(out->c_i + (size_t)slot * n, S.c, (size_t)n * 4);
     out->phi_offset[slot + 1] = out->phi_offset[slot] + K;
-    const size_t o0 = cen.size();
-    cen.resize(o0 + (size_t)K * p);
-    sg.resize(o0 + (size_t)K * p);
+    const size_t o0 = cen.size;
+    if (!cen.extend((size_t)K * p) || !sg.extend((size_t)K * p)) return fail(SMG_ERR_ARG, "out of host memory");
     for (int k = 0; k < K; k++)
       for (int j = 0; j < p; j++) {
-        cen[o0 + (size_t)k * p + j] = (double)S.cen[(size_t)k * pp + j];
-        sg[o0 + (size_t)k * p + j] = S.sig[(size_t)k * pp + j];
+        cen.p[o0 + (size_t)k * p + j] = (double)S.cen[(size_t)k * pp + j];
+        sg.p[o0 + (size_t)k * p + j] = S.sig[(size_t)k * pp + j];
       }
     return 0;
   };
@@ -1208,10 +1223,11 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   out->seconds = std::chrono::duration<double>(t1 - t0).count();
   out->time = (long long)std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count();
   if (!rc) {
-    out->centers = (double*)malloc(std::max<size_t>(cen.size(), 1) * 8);
-    out->sigmas = (double*)malloc(std::max<size_t>(sg.size(), 1) * 8);
-    std::copy(cen.begin(), cen.end(), out->centers);
-    std::copy(sg.begin(), sg.end(), out->sigmas);
+    if (!cen.p) cen.extend(1), cen.size = 0;
+    if (!sg.p) sg.extend(1), sg.size = 0;
+    out->centers = cen.p;
+    out->sigmas = sg.p;
+    cen.p = sg.p = nullptr;
   }
   cudaStreamSynchronize(st_copy);
   cudaStreamSynchronize(ch->st);
@@ -1230,6 +1246,8 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   if (verbose == 3)
     fprintf(stderr, "[smgibbs] create %.4f s, pinned alloc %.4f s, loop %.4f s, pinned free %.4f s, destroy %.4f s\n", create_s,
             pin_s, out->seconds, unpin_s, std::chrono::duration<double>(std::chrono::steady_clock::now() - td0).count());
+  free(cen.p);  // (null once handed over)
+  free(sg.p);
   if (rc) {
     smg_free_results(out);
     g_last_error = keep;

@@ -32,7 +32,7 @@ struct SmWork {
   SmPlan* plan = nullptr;
   int* anchors = nullptr;  // alias of info->i1,i2 (two ints)
   int *H = nullptr, *cnt = nullptr;
-  double *rg_dl = nullptr, *rg_lgt = nullptr;  // [n] LL_A - LL_B and logit(u) of the restricted scan in flight
+  double *rg_dl = nullptr, *rg_lgt = nullptr, *rg_lgt2 = nullptr;  // [n] LL_A - LL_B and logit(u) of the restricted scans
   double* rowvals = nullptr;  // [4][n+2]
   double* partial = nullptr;  // [4][RB]
   double* terms = nullptr;    // [24]
@@ -172,6 +172,12 @@ __global__ void sm_launch_alloc_kernel(const SmInfo* info, const double* u_inj, 
 // to the larger side iff |D| >= logit(u), to the other side otherwise.  logit(u) and d0 = LL_1 - LL_2 do
 // not depend on the running counts: sm_ll2prep_kernel evaluates them for every member in parallel
 // (one warp per member, all SMs).
+// logit of the allocation uniform of member `pos` in the scan keyed by `key` (it does not depend on the state: the
+// persistent kernel evaluates it one scan ahead on CTAs that would otherwise wait; lgt == nullptr below)
+__device__ __forceinline__ double sm_logit_u(const double* u_inj, int pos, const RngKey& key) {
+  const double u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
+  return log(u / (1.0 - u));
+}
 __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S, int nS,
                                                 const uint8_t* cen, const double* isg, const double* sden, int slotA,
                                                 int slotB, const double* u_inj, const RngKey& key, double* dl,
@@ -228,14 +234,12 @@ __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, i
       a1 = warp_sum(a1);
       b1 = warp_sum(b1);
       if (lane == 0) {
-        const double u = get_u(u_inj, pos0, key, U_SM_RGIBBS, (uint32_t)pos0, 0u);
         dl[pos0] = (-a0 - sdA) - (-b0 - sdB);
-        lgt[pos0] = log(u / (1.0 - u));
+        if (lgt) lgt[pos0] = sm_logit_u(u_inj, pos0, key);
       }
       if (lane == 1 && has1) {
-        const double u = get_u(u_inj, pos1, key, U_SM_RGIBBS, (uint32_t)pos1, 0u);
         dl[pos1] = (-a1 - sdA) - (-b1 - sdB);
-        lgt[pos1] = log(u / (1.0 - u));
+        if (lgt) lgt[pos1] = sm_logit_u(u_inj, pos1, key);
       }
     }
     return;
@@ -245,9 +249,8 @@ __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, i
     const double llA = -warp_mismatch_dot(x, cA, wA, pp, lane) - sdA;
     const double llB = -warp_mismatch_dot(x, cB, wB, pp, lane) - sdB;
     if (lane == 0) {
-      const double u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
       dl[pos] = llA - llB;
-      lgt[pos] = log(u / (1.0 - u));
+      if (lgt) lgt[pos] = sm_logit_u(u_inj, pos, key);
     }
   }
 }
@@ -940,7 +943,7 @@ struct SmChainArgs {
   double *sig, *isg, *sden;
   int *H, *cnt, *zL, *zStar, *zState;
   int* selcnt;   // [grid] members found by each CTA
-  double *dl, *lgt;
+  double *dl, *lgt, *lgt2;  // lgt / lgt2: logit(u) of the members for even / odd scans
   double *rowvals, *partial, *terms;
   int* accepted;
   unsigned long long* stats;
@@ -972,6 +975,13 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
   const int gtid = blockIdx.x * SM_CHAIN_T + tid, gthreads = gridDim.x * SM_CHAIN_T;
   const size_t len = (size_t)pp * A.mmax;
   auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
+  auto fill_lgt = [&](int q, int t0, int nt) {  // thread t0 of nt: logit(u) of scan q into its buffer
+    RngKey k = A.key;
+    k.sub = SUB_SM_RG + q;
+    double* buf = (q & 1) ? A.lgt2 : A.lgt;
+    const double* ui = off(A.u_rg, (size_t)q * n);
+    for (int pos = t0; pos < nS; pos += nt) buf[pos] = sm_logit_u(ui, pos, k);
+  };
 
 #ifdef SMG_PHI_PROFILE
   long long tk = clock64();
@@ -1088,6 +1098,7 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
       A.zL[pos] = z > 1 ? 1 : z;
     }
   }
+  fill_lgt(0, gtid, gthreads);
   grid_sync(B);
   HT_TICK(1);
 
@@ -1096,7 +1107,7 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     RngKey k = A.key;
     k.sub = SUB_SM_RG + q;
     CHAIN_TICK(7);
-    sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, A.lgt, gwarp,
+    sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, nullptr, gwarp,
                     nwarps);
     // the histograms of the current-state sides (fixed for the whole proposal) ride in the first scan
     if (first)
@@ -1110,12 +1121,15 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
         A.H[(size_t)SH_M * len + q2] = A.H[(size_t)SH_S0 * len + q2] + A.H[(size_t)SH_S1 * len + q2];
       if (gtid == SM_CHAIN_T) A.cnt[SH_M] = A.cnt[SH_S0] + A.cnt[SH_S1];
     }
+    double* lgq = (q & 1) ? A.lgt2 : A.lgt;
     if (blockIdx.x == 0) {
       if (q >= A.wide_from)
-        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_WIDE_CHUNK / SM_CHAIN_T>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len),
+        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_WIDE_CHUNK / SM_CHAIN_T>(nS, A.dl, lgq, z, A.H + (size_t)h0 * len, (int)(2 * len),
                                                                        A.cnt + h0, MW);
       else
-        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_R>(nS, A.dl, A.lgt, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
+        sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_R>(nS, A.dl, lgq, z, A.H + (size_t)h0 * len, (int)(2 * len), A.cnt + h0, M);
+    } else if (q < A.t) {
+      fill_lgt(q + 1, gtid - SM_CHAIN_T, ((int)gridDim.x - 1) * SM_CHAIN_T);  // the next scan's, while CTA 0 decides
     }
     grid_sync(B);
     CHAIN_TICK(5);
@@ -1230,6 +1244,7 @@ static int sm_alloc(smg_chain* ch) {
   SMG_CUDA(dev_malloc(&W->cnt, SH_N * 4 + 4, ch->st));
   SMG_CUDA(dev_malloc(&W->rg_dl, (size_t)n * 8, ch->st));
   SMG_CUDA(dev_malloc(&W->rg_lgt, (size_t)n * 8, ch->st));
+  SMG_CUDA(dev_malloc(&W->rg_lgt2, (size_t)n * 8, ch->st));
   SMG_CUDA(dev_malloc(&W->rowvals, (size_t)4 * (n + 2) * 8, ch->st));
   SMG_CUDA(dev_malloc(&W->partial, (size_t)4 * SM_RB * 8, ch->st));
   SMG_CUDA(dev_malloc(&W->terms, 24 * 8, ch->st));
@@ -1266,7 +1281,7 @@ static void sm_free(smg_chain* ch) {
   SmWork* W = ch->sm;
   if (!W) return;
   void* ptrs[] = {W->S,       W->zL,      W->zStar, W->zState, W->info,    W->plan,    W->H,      W->cnt,
-                  W->rg_dl,   W->rg_lgt,  W->rowvals, W->partial, W->terms, W->chain_bar, W->u_pair,  W->u_prior_c, W->u_prior_s,
+                  W->rg_dl,   W->rg_lgt,  W->rg_lgt2, W->rowvals, W->partial, W->terms, W->chain_bar, W->u_pair,  W->u_prior_c, W->u_prior_s,
                   W->u_launch, W->u_rg,   W->u_rg_c, W->u_rg_s, W->u_mg_c,  W->u_mg_s,  W->u_accept, W->selcnt};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ch->st);
@@ -1440,6 +1455,7 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.zStar = W->zStar;
     CA.dl = W->rg_dl;
     CA.lgt = W->rg_lgt;
+    CA.lgt2 = W->rg_lgt2;
     CA.phi = phi_args_base(ch, 0);
     CA.phi.H = W->H;
     CA.phi.counts = W->cnt;
