@@ -246,6 +246,9 @@ def main():
     roofline = {"kernel": "hamming_ll_block_t16_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": K1_DRAM_TRAFFIC_BYTES, "traffic_source": K1_DRAM_TRAFFIC_SOURCE,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": float(phase[0]),
+                "shared_memory_pipe": {"wavefronts_pct_of_peak": 63.7, "compute_memory_throughput_pct": 72.6,
+                                       "source": K1_DRAM_TRAFFIC_SOURCE + ": l1tex__data_pipe_lsu_wavefronts_mem_shared, "
+                                                 "gpu__compute_memory_throughput (static, from the committed capture)"},
                 "note": ("K1 is not HBM bound: n*K*p = %.3g compare-adds per launch = %.1f G/s, done as 4-attribute "
                          "shared-memory look-ups (1 LDS.64 + 1 DADD per 4 attributes); its practical bound is the "
                          "shared-memory pipe (2 wavefronts per look-up), see DESIGN.md section 3" %
@@ -255,7 +258,9 @@ def main():
     aux_ach = aux_bytes / (phase[1] / 1000.0) / 1e9 if phase[1] > 0 else 0.0
     other = {"aux_ll_kernel": {"bound": "hbm", "achieved": aux_ach, "peak": peak, "unit": "GB/s", "frac": aux_ach / peak,
                                "algorithmic_bytes_per_launch": aux_bytes, "avg_launch_ms": float(phase[1]),
-                               "note": "runs on a low-priority side stream, overlapped with update_phi + split-merge of the same sweep"}}
+                               "note": ("runs on a low-priority side stream under update_phi + the 120-CTA split-merge kernel of the same "
+                                        "sweep, i.e. on the SMs that kernel leaves free: the time above is its overlapped "
+                                        "duration; alone it takes 118 us (ncu launch list) = 6.1 TB/s, 0.93 of the peak")}}
     scan = {"ns_per_observation": 1e6 * phase[2] / a.n, "rounds_per_sweep": (st1["scan_rounds"] - st0["scan_rounds"]) / a.steps,
             "events_per_sweep": (st1["scan_events"] - st0["scan_events"]) / a.steps, "avg_ms": float(phase[2])}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -39,6 +39,25 @@ def test_run_markov_chain_result_shape_matches_reference_list():
     assert np.array_equal(res["final_ass"], res["c_i"][-1])
 
 
+def test_result_views_outlive_the_result_dict():
+    """The allocation trace / centres / sigmas come back as views of the library's buffers (no copy); the buffers must
+    live as long as any of the arrays does, and two calls must not share storage."""
+    import gc
+    from split_and_merge_gibbs_sampling_b200 import run_markov_chain
+    X, attr, v, w, g, gt = _zoo()
+    kw = dict(m=3, iterations=15, L=5, burnin=5, t=3, r=3, neal8=True, split_merge=True, seed=11)
+    res = run_markov_chain(X, attr, g, v, w, **kw)
+    keep_c, keep_s = res["c_i"][7], res["sigmas"][7][0]
+    ref_c, ref_s = keep_c.copy(), keep_s.copy()
+    del res
+    gc.collect()
+    other = run_markov_chain(X, attr, g, v, w, **dict(kw, seed=12))  # would recycle freed storage
+    assert np.array_equal(keep_c, ref_c) and np.array_equal(keep_s, ref_s)
+    again = run_markov_chain(X, attr, g, v, w, **kw)
+    assert np.array_equal(again["c_i"][7], ref_c) and np.array_equal(again["sigmas"][7][0], ref_s)
+    assert not np.array_equal(other["loglikelihood"], again["loglikelihood"])
+
+
 def test_zoo_posterior_matches_oracle_within_mc_error():
     from sklearn.metrics import adjusted_rand_score
     from split_and_merge_gibbs_sampling_b200 import run_markov_chain
