@@ -77,7 +77,7 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaMemsetAsync(ch->phi_cnt, 0, (size_t)NST * 4, ch->st));
   {
     const char* e = getenv("SMG_PHI_PARTS");
-    ch->phi_parts = phi_parts_for(pp, e ? atoi(e) : pp / 32);  // 32 attributes x PHI_G lanes = one pass of a 256-thread CTA
+    ch->phi_parts = phi_parts_for(pp, e ? atoi(e) : (pp + 31) / 32);  // 32 attributes x PHI_G lanes = one pass of a 256-thread CTA
   }
   if (dalloc(&ch->c, n + 4) || dalloc(&ch->c_hist, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
       dalloc(&ch->slot2label, NST))

@@ -1492,9 +1492,11 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
       static int want = -1;
       if (want < 0) {
         const char* e = getenv("SMG_SM_PHI_PARTS");
-        want = e ? atoi(e) : 8;
+        want = e ? atoi(e) : 0;
       }
-      CA.phi.nparts = phi_parts_for(ch->pp, std::max(1, std::min(want, ctas / 3)));
+      // default: 32 attributes (x 8 lanes) per CTA, i.e. one pass of half a CTA
+      const int w = want > 0 ? want : (ch->pp + 31) / 32;
+      CA.phi.nparts = phi_parts_for(ch->pp, std::max(1, std::min(w, ctas / 3)));
     }
     static const bool trace = getenv("SMG_SM_TRACE") != nullptr;  // diagnostic: device time of the persistent kernel
     static cudaEvent_t tr0, tr1;
