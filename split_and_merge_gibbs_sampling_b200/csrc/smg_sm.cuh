@@ -1140,57 +1140,50 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     grid_sync(B);
     CHAIN_TICK(6);
   };
-  auto run_jobs = [&](const PhiJob* jobs, int nj) {
-    if ((int)blockIdx.x < nj * A.phi.nparts) phi_job_body(A.phi, jobs[blockIdx.x % nj], blockIdx.x % nj, blockIdx.x / nj, A.phi.nparts, sh);
-    grid_sync(B);
-  };
-
+  // One loop, ONE call site for the scan phases and one for the parameter jobs: the kernel runs once per sweep on cold
+  // instruction caches, and every extra inlined copy of these bodies costs ~10 us of instruction fetch the first time
+  // it is reached.  Iterations 0 .. nsteps-1 are the launch scans (+ merge-launch updates), iteration nsteps is the
+  // proposal: copy of the split launch state, one more restricted scan for a split, the merged cluster's final update.
   const int nsteps = A.t > A.r ? A.t : A.r;
-  for (int q = 0; q < nsteps; q++) {
-    PhiJob j[3];
-    int nj = 0;
-    if (q < A.t) {
-      alloc_scan(A.zL, NSB + SM_SL_A, NSB + SM_SL_B, SH_L0, q, q == 0);
-      for (int side = 0; side < 2; side++)
-        j[nj++] = sm_job_at(NSB, J_L0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
-                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
-    }
-    if (q < A.r)
-      j[nj++] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + q, off(A.u_mg_c, (size_t)q * p), off(A.u_mg_s, (size_t)q * p), 0);
-    run_jobs(j, nj);
-    if (*(volatile int*)A.err) return;
-  }
-  // proposal = split launch state (sides + the two parameter slots) ...
-  for (int pos = blockIdx.x * blockDim.x + threadIdx.x; pos < nS; pos += gridDim.x * blockDim.x) A.zStar[pos] = A.zL[pos];
-  if (blockIdx.x < 2) {
-    const int src = NSB + (blockIdx.x ? SM_SL_B : SM_SL_A), dst = NSB + (blockIdx.x ? SM_ST_B : SM_ST_A);
-    for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
-      A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
-      A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
-      A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
-    }
-    if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
-  }
-  grid_sync(B);
-  // ... + one more restricted scan for a split; the merged cluster's final update in both cases
-  {
-    const int q = A.t;
-    PhiJob j[3];
-    int nj = 0;
-    if (same) {
-      alloc_scan(A.zStar, NSB + SM_ST_A, NSB + SM_ST_B, SH_P0, q, false);
-      for (int side = 0; side < 2; side++)
-        j[nj++] = sm_job_at(NSB, J_P0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
-                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
-    }
-    j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
-    // the job index enters the Philox counter: keep the merged cluster at index 2 as in the multi-launch path
-    if (!same) {
-      if ((int)blockIdx.x < A.phi.nparts) phi_job_body(A.phi, j[0], 2, blockIdx.x, A.phi.nparts, sh);
+  for (int it = 0; it <= nsteps; it++) {
+    const bool prop = (it == nsteps);
+    if (prop) {
+      // proposal = split launch state (sides + the two parameter slots) ...
+      for (int pos = gtid; pos < nS; pos += gthreads) A.zStar[pos] = A.zL[pos];
+      if (blockIdx.x < 2) {
+        const int src = NSB + (blockIdx.x ? SM_SL_B : SM_SL_A), dst = NSB + (blockIdx.x ? SM_ST_B : SM_ST_A);
+        for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
+          A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
+          A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
+          A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
+        }
+        if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
+      }
       grid_sync(B);
-    } else {
-      run_jobs(j, nj);
     }
+    const int q = prop ? A.t : it;
+    const bool do_scan = prop ? (same != 0) : (it < A.t);
+    PhiJob j[3];
+    int nj = 0;
+    if (do_scan) {
+      alloc_scan(prop ? A.zStar : A.zL, NSB + (prop ? SM_ST_A : SM_SL_A), NSB + (prop ? SM_ST_B : SM_SL_B), prop ? SH_P0 : SH_L0, q,
+                 it == 0);
+      for (int side = 0; side < 2; side++)
+        j[nj++] = sm_job_at(NSB, (prop ? J_P0 : J_L0) + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+    }
+    // the job index enters the Philox counter: the merged cluster's final update keeps index 2 as in the multi-launch path
+    int idx0 = 0;
+    if (prop) {
+      if (!do_scan) idx0 = 2;
+      j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
+    } else if (it < A.r) {
+      j[nj++] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + it, off(A.u_mg_c, (size_t)it * p), off(A.u_mg_s, (size_t)it * p), 0);
+    }
+    if ((int)blockIdx.x < nj * A.phi.nparts)
+      phi_job_body(A.phi, j[blockIdx.x % nj], idx0 + blockIdx.x % nj, blockIdx.x / nj, A.phi.nparts, sh);
+    grid_sync(B);
+    if (*(volatile int*)A.err) return;
   }
   if (*(volatile int*)A.err) return;
   HT_TICK(7);
