@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmgibbs.so")
+LIB_PATH = os.environ.get("SMG_LIB_PATH") or os.path.join(_HERE, "libsmgibbs.so")  # (override: instrumented builds)
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
@@ -45,7 +45,7 @@ EXPORTS = [
     "smg_step", "smg_step_many", "smg_get_iteration", "smg_resume_at", "smg_validate_state", "smg_synth_generate", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
     "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
-    "smg_debug_split_merge", "smg_debug_scan_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
+    "smg_debug_split_merge", "smg_debug_scan_profile", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
     "smg_psm_flush", "smg_psm_read", "smg_psm_info", "smg_psm_destroy", "smg_debug_psm_reference",
 ]
 
@@ -93,6 +93,7 @@ def load():
     lib.smg_get_timings.argtypes = [C.c_void_p, c_dbl_p]
     lib.smg_last_step_ms.argtypes = [C.c_void_p, c_dbl_p]
     lib.smg_debug_scan_profile.argtypes = [C.c_void_p, c_ull_p]
+    lib.smg_debug_sm_profile.argtypes = [C.c_void_p, c_ull_p]
     lib.smg_psm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.smg_psm_push_chain.argtypes = [C.c_void_p, C.c_void_p]
     lib.smg_psm_push_host.argtypes = [C.c_void_p, c_int_p]

@@ -179,6 +179,12 @@ class Chain:
         keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "_"]
         return dict(zip(keys, (int(x) for x in out)))
 
+    def sm_profile(self):
+        out = np.zeros(16, dtype=np.uint64)
+        lb.check(self.lib.smg_debug_sm_profile(self.h, out.ctypes.data_as(lb.c_ull_p)))
+        keys = ["select", "setup", "decide", "bar1", "moves", "bar2", "draws", "bar3", "mh_terms", "mh_sums", "launches"]
+        return dict(zip(keys, (int(x) for x in out)))
+
     def timings(self):
         out = np.zeros(8)
         lb.check(self.lib.smg_get_timings(self.h, lb.dptr(out)))

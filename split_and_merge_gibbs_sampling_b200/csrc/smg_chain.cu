@@ -11,7 +11,7 @@
 #include <thread>
 
 #include "smg_psm.cuh"
-#include "smg_sm.cuh"
+#include "smg_sm_host.cuh"
 
 namespace smg {
 thread_local std::string g_last_error;
@@ -49,7 +49,10 @@ static int chain_alloc(smg_chain* ch) {
     SMG_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     SMG_CUDA(cudaStreamCreateWithPriority(&ch->st, cudaStreamNonBlocking, prio_hi));
     SMG_CUDA(cudaStreamCreateWithPriority(&ch->st_aux, cudaStreamNonBlocking, prio_lo));
+    SMG_CUDA(cudaStreamCreateWithPriority(&ch->st_k1, cudaStreamNonBlocking, prio_lo));
   }
+  SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_phi_done, cudaEventDisableTiming));
+  SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_k1_done, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_scan_done, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_aux_done, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreate(&ch->ev_k1[0]));
@@ -82,8 +85,8 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->c, n + 4) || dalloc(&ch->c_hist, n) || dalloc(&ch->K, 1) || dalloc(&ch->counts, NST) || dalloc(&ch->counts_slot, NST) ||
       dalloc(&ch->slot2label, NST))
     return SMG_ERR_CUDA;
-  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux, (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n + 2) || dalloc(&ch->und0, ((size_t)n + 8191) / 4096 * 4096) || dalloc(&ch->und_blk, (size_t)n / 4096 + 4) ||
-      dalloc(&ch->aux_e, (size_t)n * ch->m_aux))
+  if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux[0], (size_t)n * ch->m_aux) || dalloc(&ch->LLaux[1], (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n + 2) || dalloc(&ch->und0, ((size_t)n + 8191) / 4096 * 4096) || dalloc(&ch->und_blk, (size_t)n / 4096 + 4) ||
+      dalloc(&ch->aux_e[0], (size_t)n * ch->m_aux) || dalloc(&ch->aux_e[1], (size_t)n * ch->m_aux))
     return SMG_ERR_CUDA;
   const size_t P = (size_t)ch->pool_size;
   if (dalloc(&ch->pcen, P * pp) || dalloc(&ch->psig, P * pp) || dalloc(&ch->pisg, P * pp) || dalloc(&ch->pden, P * pp) ||
@@ -112,11 +115,12 @@ static void chain_free(smg_chain* ch) {
   if (!ch) return;
   cudaSetDevice(ch->device);
   if (ch->st_aux) cudaStreamSynchronize(ch->st_aux);
+  if (ch->st_k1) cudaStreamSynchronize(ch->st_k1);
   if (ch->st) cudaStreamSynchronize(ch->st);
   sm_free(ch);
   void* ptrs[] = {ch->X,      ch->attr,   ch->v,         ch->w,          ch->cen[0], ch->cen[1], ch->sig[0], ch->sig[1],
                   ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
-                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux,    ch->mrg, ch->aux_e,  ch->pcen,   ch->psig,   ch->pisg,
+                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux[0], ch->LLaux[1], ch->mrg, ch->aux_e[0], ch->aux_e[1], ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
                   ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d,
                   ch->c_hist, ch->phi_cnt, ch->und0, ch->und_blk};
@@ -133,7 +137,10 @@ static void chain_free(smg_chain* ch) {
     if (ch->ev_k1[q]) cudaEventDestroy(ch->ev_k1[q]);
   if (ch->ev_aux_t0) cudaEventDestroy(ch->ev_aux_t0);
   if (ch->ev_aux_t1) cudaEventDestroy(ch->ev_aux_t1);
+  if (ch->ev_phi_done) cudaEventDestroy(ch->ev_phi_done);
+  if (ch->ev_k1_done) cudaEventDestroy(ch->ev_k1_done);
   if (ch->st_aux) cudaStreamDestroy(ch->st_aux);
+  if (ch->st_k1) cudaStreamDestroy(ch->st_k1);
   if (ch->st) cudaStreamDestroy(ch->st);
   delete ch;
 }
@@ -141,52 +148,81 @@ static void chain_free(smg_chain* ch) {
 // ------------------------------------------------------------------------------------------
 // phases
 // ------------------------------------------------------------------------------------------
-static int launch_ll_block(smg_chain* ch) {
-  cudaEventRecord(ch->ev_k1[0], ch->st);
+static int launch_ll_block(smg_chain* ch, cudaStream_t stream = nullptr) {
+  if (!stream) stream = ch->st;
+  cudaEventRecord(ch->ev_k1[0], stream);
   dim3 grid(cdiv(ch->n, LLB_ROWS), cdiv(ch->Kcap, LLB_SLOTS));
   if (ch->mmax <= 7)  // every code fits 3 bits: subset-sum table form
-    hamming_ll_block_t16_kernel<<<grid, 256, LLT_SMEM_BYTES, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur],
+    hamming_ll_block_t16_kernel<<<grid, 256, LLT_SMEM_BYTES, stream>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur],
                                                                       ch->isg[ch->cur], ch->sden[ch->cur], ch->K, ch->LL,
                                                                       ch->ldl);
   else
-    hamming_ll_block_kernel<<<grid, 256, 0, ch->st>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], ch->isg[ch->cur],
+    hamming_ll_block_kernel<<<grid, 256, 0, stream>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur], ch->isg[ch->cur],
                                                       ch->sden[ch->cur], ch->K, ch->LL, ch->ldl);
-  cudaEventRecord(ch->ev_k1[1], ch->st);
+  cudaEventRecord(ch->ev_k1[1], stream);
   ch->k1_timed = true;
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
 
-static int launch_aux_ll(smg_chain* ch, const double* tape, cudaStream_t stream, long long iter) {
+static int launch_aux_ll(smg_chain* ch, const double* tape, cudaStream_t stream, long long iter, int buf) {
   long long warps = (long long)ch->n * ch->m_aux;
   RngKey key = mk_key(ch, SUB_SCAN);
   key.sweep = (uint32_t)iter;
   aux_ll_kernel<<<cdiv(warps * 32, 256), 256, 0, stream>>>(ch->X, ch->n, ch->pp, ch->m_aux, ch->pcen, ch->pisg, ch->psden,
-                                                          ch->pool_size, tape, ch->m_aux + 1, key, ch->LLaux, ch->aux_e);
+                                                          ch->pool_size, tape, ch->m_aux + 1, key, ch->LLaux[buf], ch->aux_e[buf]);
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
 
+// The auxiliary-component columns depend on X, the pool and the Philox key only -- not on the state -- so the ones
+// of the NEXT pass are evaluated on a side stream, into the other half of the double buffer, while the (single-cluster)
+// scan and update_phi of THIS pass leave the GPU almost idle: the HBM-bound gather is completely hidden.  Not done
+// when the pool is re-drawn in between (launcher.cpp:123-129).
+static int prefetch_next_aux(smg_chain* ch) {
+  const long long next_iter = ch->iter + ch->n8_step;
+  static const bool disabled = [] { const char* e = getenv("SMG_NO_AUX_PREFETCH"); return e && e[0] == '1'; }();
+  if (disabled || !ch->neal8) return 0;
+  // an iteration that re-draws the pool before the next pass would invalidate the columns
+  for (long long it = ch->iter; it < next_iter; it++)
+    if (it % 1000 == 0) return 0;
+  // the other buffer was last read by the scan of the previous pass
+  SMG_CUDA(cudaStreamWaitEvent(ch->st_aux, ch->ev_scan_done, 0));
+  cudaEventRecord(ch->ev_aux_t0, ch->st_aux);
+  if (launch_aux_ll(ch, nullptr, ch->st_aux, next_iter, ch->aux_buf ^ 1)) return SMG_ERR_CUDA;
+  cudaEventRecord(ch->ev_aux_t1, ch->st_aux);
+  ch->aux_timed = true;
+  SMG_CUDA(cudaEventRecord(ch->ev_aux_done, ch->st_aux));
+  ch->aux_ready = true;
+  ch->aux_iter = next_iter;
+  return 0;
+}
+
 // one Neal-8 pass: launcher.cpp:95-99
-static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
+static int neal8_pass(smg_chain* ch, const double* tape, bool timed, bool prefetch = false) {
   if (!ch->pool_valid) return fail(SMG_ERR_STATE, "auxiliary pool not initialised");
   if (timed) cudaEventRecord(ch->ev[0], ch->st);
-  // the block of this pass was normally evaluated at the end of the previous iteration (see sweep())
+  // the block of this pass was normally evaluated during the previous iteration (see sweep())
   if (tape || ch->ll_for_iter != ch->iter) {
     if (launch_ll_block(ch)) return SMG_ERR_CUDA;
   }
   ch->ll_for_iter = -1;  // the pass moves observations: the block no longer matches the state
   if (timed) cudaEventRecord(ch->ev[1], ch->st);
   if (!tape && ch->aux_ready && ch->aux_iter == ch->iter) {
-    // the columns were evaluated on the side stream while the previous split-merge step was running
+    // the columns were evaluated on the side stream during the previous iteration, into the other buffer
     SMG_CUDA(cudaStreamWaitEvent(ch->st, ch->ev_aux_done, 0));
+    ch->aux_buf ^= 1;
   } else {
     if (ch->aux_ready) SMG_CUDA(cudaStreamWaitEvent(ch->st, ch->ev_aux_done, 0));  // do not race a stale prefetch
-    if (launch_aux_ll(ch, tape, ch->st, ch->iter)) return SMG_ERR_CUDA;
+    if (launch_aux_ll(ch, tape, ch->st, ch->iter, ch->aux_buf)) return SMG_ERR_CUDA;
   }
   ch->aux_ready = false;
+  if (prefetch && !tape) {
+    int rc = prefetch_next_aux(ch);
+    if (rc) return rc;
+  }
   if (timed) cudaEventRecord(ch->ev[2], ch->st);
   ScanArgs A;
   A.n = ch->n;
@@ -196,9 +232,9 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.K0cap = ch->Kcap;
   A.X = ch->X;
   A.LL = ch->LL;
-  A.LLaux = ch->LLaux;
+  A.LLaux = ch->LLaux[ch->aux_buf];
   A.mrg = ch->mrg;
-  A.aux_e = ch->aux_e;
+  A.aux_e = ch->aux_e[ch->aux_buf];
   A.u_alloc = tape ? tape + ch->m_aux : nullptr;
   A.u_stride = ch->m_aux + 1;
   A.key = mk_key(ch, SUB_SCAN);
@@ -222,7 +258,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   A.und0 = ch->und0;
   A.und_blk = ch->und_blk;
   A.prof = ch->scan_prof;
-  scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, ch->LLaux,
+  scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, A.LLaux,
                                                                           ch->c, ch->counts, A.log_gamma_m, A.u_alloc, A.u_stride, A.key, ch->mrg, ch->und0, ch->und_blk);
   neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, SCAN_PF_BYTES, ch->st>>>(A);  // one cluster
   SMG_CUDA(cudaGetLastError());
@@ -240,28 +276,6 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed) {
   ch->h_launches += 4;
   SMG_CUDA(cudaEventRecord(ch->ev_scan_done, ch->st));
   if (timed) cudaEventRecord(ch->ev[3], ch->st);
-  return 0;
-}
-
-// The auxiliary-component columns depend on X, the pool and the Philox key only -- not on the state -- so the ones
-// of the next pass are evaluated on a side stream as soon as this pass has consumed the current ones: the HBM-bound
-// gather then overlaps the latency-bound update_phi + split-merge chain.  Not done when the pool is about to be
-// re-drawn (launcher.cpp:123-129).
-static int prefetch_next_aux(smg_chain* ch) {
-  const long long next_iter = ch->iter + ch->n8_step;
-  static const bool disabled = [] { const char* e = getenv("SMG_NO_AUX_PREFETCH"); return e && e[0] == '1'; }();
-  if (disabled || !ch->neal8 || ch->iter % 1000 == 0) return 0;
-  // an iteration in between that re-draws the pool would invalidate the columns
-  for (long long it = ch->iter + 1; it < next_iter; it++)
-    if (it % 1000 == 0) return 0;
-  SMG_CUDA(cudaStreamWaitEvent(ch->st_aux, ch->ev_scan_done, 0));
-  cudaEventRecord(ch->ev_aux_t0, ch->st_aux);
-  if (launch_aux_ll(ch, nullptr, ch->st_aux, next_iter)) return SMG_ERR_CUDA;
-  cudaEventRecord(ch->ev_aux_t1, ch->st_aux);
-  ch->aux_timed = true;
-  SMG_CUDA(cudaEventRecord(ch->ev_aux_done, ch->st_aux));
-  ch->aux_ready = true;
-  ch->aux_iter = next_iter;
   return 0;
 }
 
@@ -377,13 +391,22 @@ static int draw_pool(smg_chain* ch, long long epoch_iter = -1) {
 }
 
 // one iteration of launcher.cpp:85-154 (without the snapshot)
+//
+// Stream plan of a steady iteration (Neal-8 pass and split-merge every iteration):
+//   st     : [margin + scan + compaction] -> [update_phi] -> [split-merge proposal: ONE cluster] -> [patch] -> [log-lik]
+//   st_aux :  aux columns of the next pass (HBM-bound gather), under the scan + update_phi
+//   st_k1  :                                   likelihood block of the next pass (all other SMs), under the proposal
+// The block of the next pass depends on the parameters fixed by update_phi except for the <= 2 columns an ACCEPTED
+// proposal rewrites; those are re-evaluated by sm_ll_patch_kernel (a no-op otherwise; acceptance is rare at
+// stationarity).
 static int sweep(smg_chain* ch, bool timed) {
   SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, sizeof(int), ch->st));
   if (timed) cudaEventRecord(ch->ev[0], ch->st);
-  if (ch->neal8 && ch->iter % ch->n8_step == 0) {
-    int rc = neal8_pass(ch, nullptr, timed);
-    if (rc) return rc;
-    rc = prefetch_next_aux(ch);
+  const bool pass_now = ch->neal8 && ch->iter % ch->n8_step == 0;
+  const bool pass_next = ch->neal8 && (ch->iter + 1) % ch->n8_step == 0;
+  const bool sm_now = ch->split_merge && ch->iter % ch->sam_step == 0;
+  if (pass_now) {
+    int rc = neal8_pass(ch, nullptr, timed, true);
     if (rc) return rc;
     rc = update_phi_all(ch, SUB_PHI_AFTER_SCAN, nullptr, nullptr);
     if (rc) return rc;
@@ -391,10 +414,19 @@ static int sweep(smg_chain* ch, bool timed) {
     for (int q = 1; q <= 3; q++) cudaEventRecord(ch->ev[q], ch->st);
   }
   if (timed) cudaEventRecord(ch->ev[4], ch->st);
-  if (ch->split_merge && ch->iter % ch->sam_step == 0) {
+  const bool k1_early = ch->k1_overlap && pass_next && sm_now;
+  if (k1_early) {
+    SMG_CUDA(cudaEventRecord(ch->ev_phi_done, ch->st));
+    SMG_CUDA(cudaStreamWaitEvent(ch->st_k1, ch->ev_phi_done, 0));
+  }
+  if (sm_now) {  // launched before the block so that its cluster gets its SMs first (and st outranks st_k1)
     int rc = sm_step(ch, nullptr);
     if (rc) return rc;
     ch->h_sm_props++;
+  }
+  if (k1_early) {
+    if (launch_ll_block(ch, ch->st_k1)) return SMG_ERR_CUDA;
+    SMG_CUDA(cudaEventRecord(ch->ev_k1_done, ch->st_k1));
   }
   if (timed) cudaEventRecord(ch->ev[5], ch->st);
   if (ch->iter % 1000 == 0) {
@@ -402,11 +434,19 @@ static int sweep(smg_chain* ch, bool timed) {
     if (rc) return rc;
   }
   if (timed) cudaEventRecord(ch->ev[6], ch->st);
-  if (ch->neal8 && (ch->iter + 1) % ch->n8_step == 0) {
-    // The next iteration starts with a Neal-8 pass on exactly this state: evaluate its likelihood block now and read
-    // the full-data log-likelihood (common_functions.cpp:379-401) off it, sum_i LL[i][c_i], instead of a separate pass
-    // over X.
-    if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+  ch->k1_in_tail = false;
+  if (pass_next) {
+    // The next iteration starts with a Neal-8 pass on exactly this state: its likelihood block also yields the
+    // full-data log-likelihood (common_functions.cpp:379-401), sum_i LL[i][c_i], without a second pass over X.
+    if (k1_early) {
+      SMG_CUDA(cudaStreamWaitEvent(ch->st, ch->ev_k1_done, 0));
+      sm_ll_patch_kernel<<<148 * 2, 256, 0, ch->st>>>(ch->accepted_d, ch->sm->info, ch->X, ch->n, ch->pp, ch->cen[ch->cur],
+                                                      ch->isg[ch->cur], ch->sden[ch->cur], ch->LL, ch->ldl);
+      ch->h_launches++;
+    } else {
+      if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+      ch->k1_in_tail = true;
+    }
     loglik_gather_kernel<<<ch->loglik_blocks, 256, 0, ch->st>>>(ch->LL, ch->ldl, ch->c, ch->n, ch->partial);
     reduce_final_kernel<<<1, 256, 0, ch->st>>>(ch->partial, ch->loglik_blocks, ch->loglik_d);
     ch->h_launches += 2;
@@ -486,6 +526,10 @@ static int create_common(const smg_config* cfg, smg_chain** out) {
   ch->seed = cfg->seed;
   ch->device = cfg->device;
   ch->sigma_exact = cfg->exact_sigma_inverse;
+  {
+    const char* e = getenv("SMG_NO_K1_OVERLAP");  // diagnostic: likelihood block after the proposal instead of beside it
+    ch->k1_overlap = !(e && e[0] == '1');
+  }
   ch->Kcap = cfg->max_clusters > 0 ? cfg->max_clusters : 192;
   ch->Kcap = std::min(ch->Kcap, SMG_MAX_ENTRIES - ch->m_aux);
   ch->Kcap = std::max(ch->Kcap, 8);
@@ -511,9 +555,9 @@ static int create_common(const smg_config* cfg, smg_chain** out) {
   std::copy(ch->h_attr.begin(), ch->h_attr.end(), a.begin());
   std::copy(ch->h_v.begin(), ch->h_v.end(), v.begin());
   std::copy(ch->h_w.begin(), ch->h_w.end(), w.begin());
-  if (cudaMemcpy(ch->attr, a.data(), ch->pp * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(ch->v, v.data(), ch->pp * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
-      cudaMemcpy(ch->w, w.data(), ch->pp * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+  if (h2d_sync(ch->attr, a.data(), ch->pp * 4, ch->st) != cudaSuccess ||
+      h2d_sync(ch->v, v.data(), ch->pp * 8, ch->st) != cudaSuccess ||
+      h2d_sync(ch->w, w.data(), ch->pp * 8, ch->st) != cudaSuccess) {
     chain_free(ch);
     return fail(SMG_ERR_CUDA, "upload of hyper-parameters failed");
   }
@@ -653,7 +697,7 @@ static int upload_u8(smg_chain* ch, const unsigned char* data) {
       if (x < 1 || x > ch->h_attr[j]) return fail(SMG_ERR_ARG, "data entries must be codes in 1..attrisize[j]");
       buf[(size_t)i * ch->pp + j] = x;
     }
-  SMG_CUDA(cudaMemcpy(ch->X, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+  SMG_CUDA(h2d_sync(ch->X, buf.data(), buf.size(), ch->st));
   return 0;
 }
 
@@ -804,9 +848,8 @@ static int step_finish(smg_chain* ch, int n_iters) {
       // iteration, inside the [6]-[7] interval: report it as phase [0] and take it out of the log-likelihood phase
       ms = 0;
       cudaEventElapsedTime(&ms, ch->ev_k1[0], ch->ev_k1[1]);
-      const bool in_tail = ch->ll_for_iter == ch->iter;
       ch->h_timings[0] = ms;
-      if (in_tail) ch->h_timings[6] = std::max(0.0, ch->h_timings[6] - (double)ms);
+      if (ch->k1_in_tail) ch->h_timings[6] = std::max(0.0, ch->h_timings[6] - (double)ms);
     }
     if (ch->aux_timed && cudaEventSynchronize(ch->ev_aux_t1) == cudaSuccess) {
       // the aux columns of the next pass ran on the side stream, overlapped with the split-merge step
@@ -815,7 +858,6 @@ static int step_finish(smg_chain* ch, int n_iters) {
       ch->h_timings[1] = ms;
     }
   }
-  if (ch->h_accepted) ch->h_sm_acc++;
   return rc;
 }
 
@@ -899,13 +941,13 @@ int smg_snapshot(smg_chain* ch, int* K, int* c_i, double* centers, double* sigma
   if (K) *K = Kh;
   if (loglik) *loglik = ch->h_loglik;
   if (accepted) *accepted = ch->h_accepted;
-  if (c_i) SMG_CUDA(cudaMemcpy(c_i, ch->c, (size_t)ch->n * 4, cudaMemcpyDeviceToHost));
+  if (c_i) SMG_CUDA(d2h_sync(c_i, ch->c, (size_t)ch->n * 4, ch->st));
   if (centers || sigmas) {
     if (Kh > cap_clusters) return fail(SMG_ERR_CAPACITY, "snapshot buffers hold fewer clusters than K");
     std::vector<uint8_t> hc((size_t)Kh * ch->pp);
     std::vector<double> hs((size_t)Kh * ch->pp);
-    SMG_CUDA(cudaMemcpy(hc.data(), ch->cen[ch->cur], hc.size(), cudaMemcpyDeviceToHost));
-    SMG_CUDA(cudaMemcpy(hs.data(), ch->sig[ch->cur], hs.size() * 8, cudaMemcpyDeviceToHost));
+    SMG_CUDA(d2h_sync(hc.data(), ch->cen[ch->cur], hc.size(), ch->st));
+    SMG_CUDA(d2h_sync(hs.data(), ch->sig[ch->cur], hs.size() * 8, ch->st));
     for (int k = 0; k < Kh; k++)
       for (int j = 0; j < ch->p; j++) {
         if (centers) centers[(size_t)k * ch->p + j] = (double)hc[(size_t)k * ch->pp + j];
@@ -920,7 +962,7 @@ int smg_get_stats(smg_chain* ch, unsigned long long* out8) {
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   unsigned long long d[8];
-  SMG_CUDA(cudaMemcpy(d, ch->stats_d, 64, cudaMemcpyDeviceToHost));
+  SMG_CUDA(d2h_sync(d, ch->stats_d, 64, ch->st));
   out8[0] = d[0];
   out8[1] = d[1];
   out8[2] = d[2];
@@ -945,6 +987,7 @@ int smg_resume_at(smg_chain* ch, long long iteration) {
   if (!ch || iteration < 0) return fail(SMG_ERR_ARG, "bad argument");
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st_aux));
+  SMG_CUDA(cudaStreamSynchronize(ch->st_k1));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   ch->iter = iteration;
   ch->ll_for_iter = -1;
@@ -1027,11 +1070,24 @@ int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
   if (!ch || !out8) return fail(SMG_ERR_ARG, "NULL argument");
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
-  SMG_CUDA(cudaMemcpy(out8, ch->scan_prof, 64, cudaMemcpyDeviceToHost));
+  SMG_CUDA(d2h_sync(out8, ch->scan_prof, 64, ch->st));
 #ifdef SMG_PHI_PROFILE
-  SMG_CUDA(cudaMemcpy(out8, ch->scan_prof + 8, 64, cudaMemcpyDeviceToHost));  // phi_update / chain counters instead
+  SMG_CUDA(d2h_sync(out8, ch->scan_prof + 8, 64, ch->st));  // phi_update / chain counters instead
 #endif
-  SMG_CUDA(cudaMemset(ch->scan_prof, 0, 128));
+  SMG_CUDA(cudaMemsetAsync(ch->scan_prof, 0, 128, ch->st));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  return 0;
+}
+
+int smg_debug_sm_profile(smg_chain* ch, unsigned long long* out16) {
+  if (!ch || !out16) return fail(SMG_ERR_ARG, "NULL argument");
+  memset(out16, 0, 16 * sizeof(unsigned long long));
+  SMG_CUDA(cudaSetDevice(ch->device));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
+  if (!ch->sm || !ch->sm->smc || !ch->sm->smc->prof) return 0;
+  SMG_CUDA(d2h_sync(out16, ch->sm->smc->prof, 16 * 8, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->sm->smc->prof, 0, 16 * 8, ch->st));
+  SMG_CUDA(cudaStreamSynchronize(ch->st));
   return 0;
 }
 
@@ -1276,12 +1332,12 @@ int smg_debug_set_state(smg_chain* ch, int K, const int* c_i, const double* cent
     if (c_i[i] < 0 || c_i[i] >= K) return fail(SMG_ERR_ARG, "label out of range");
     counts[c_i[i]]++;
   }
-  SMG_CUDA(cudaMemcpy(ch->cen[ch->cur], hc.data(), hc.size(), cudaMemcpyHostToDevice));
-  SMG_CUDA(cudaMemcpy(ch->sig[ch->cur], hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
-  SMG_CUDA(cudaMemcpy(ch->c, c_i, (size_t)ch->n * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(h2d_sync(ch->cen[ch->cur], hc.data(), hc.size(), ch->st));
+  SMG_CUDA(h2d_sync(ch->sig[ch->cur], hs.data(), hs.size() * 8, ch->st));
+  SMG_CUDA(h2d_sync(ch->c, c_i, (size_t)ch->n * 4, ch->st));
   ch->hist_valid = false;
-  SMG_CUDA(cudaMemcpy(ch->counts, counts.data(), counts.size() * 4, cudaMemcpyHostToDevice));
-  SMG_CUDA(cudaMemcpy(ch->K, &K, 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(h2d_sync(ch->counts, counts.data(), counts.size() * 4, ch->st));
+  SMG_CUDA(h2d_sync(ch->K, &K, 4, ch->st));
   derive_terms_kernel<<<K, 256, 0, ch->st>>>(K, ch->pp, ch->p, ch->attr, ch->sig[ch->cur], ch->isg[ch->cur], ch->den,
                                              ch->sden[ch->cur]);
   ch->h_launches++;
@@ -1305,8 +1361,8 @@ int smg_debug_set_pool(smg_chain* ch, long long pool_size, const double* pool_ce
       hc[(size_t)e * ch->pp + j] = (uint8_t)pool_center[(size_t)e * ch->p + j];
       hs[(size_t)e * ch->pp + j] = pool_sigma[(size_t)e * ch->p + j];
     }
-  SMG_CUDA(cudaMemcpy(ch->pcen, hc.data(), hc.size(), cudaMemcpyHostToDevice));
-  SMG_CUDA(cudaMemcpy(ch->psig, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
+  SMG_CUDA(h2d_sync(ch->pcen, hc.data(), hc.size(), ch->st));
+  SMG_CUDA(h2d_sync(ch->psig, hs.data(), hs.size() * 8, ch->st));
   // derive 1/sigma, den and their per-entry sums, in chunks of 65535 entries (grid.x limit is larger, keep simple)
   for (long long e0 = 0; e0 < pool_size; e0 += 1 << 20) {
     int cnt = (int)std::min<long long>(1 << 20, pool_size - e0);
@@ -1329,8 +1385,8 @@ int smg_debug_get_pool(smg_chain* ch, long long first, long long count, double* 
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   std::vector<uint8_t> hc((size_t)count * ch->pp);
   std::vector<double> hs((size_t)count * ch->pp);
-  SMG_CUDA(cudaMemcpy(hc.data(), ch->pcen + (size_t)first * ch->pp, hc.size(), cudaMemcpyDeviceToHost));
-  SMG_CUDA(cudaMemcpy(hs.data(), ch->psig + (size_t)first * ch->pp, hs.size() * 8, cudaMemcpyDeviceToHost));
+  SMG_CUDA(d2h_sync(hc.data(), ch->pcen + (size_t)first * ch->pp, hc.size(), ch->st));
+  SMG_CUDA(d2h_sync(hs.data(), ch->psig + (size_t)first * ch->pp, hs.size() * 8, ch->st));
   for (long long e = 0; e < count; e++)
     for (int j = 0; j < ch->p; j++) {
       if (pool_center) pool_center[(size_t)e * ch->p + j] = hc[(size_t)e * ch->pp + j];
@@ -1349,7 +1405,7 @@ int smg_debug_ll_block(smg_chain* ch, double* LL, int* mism) {
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   if (LL) {
     std::vector<double> h((size_t)ch->n * ch->ldl);
-    SMG_CUDA(cudaMemcpy(h.data(), ch->LL, h.size() * 8, cudaMemcpyDeviceToHost));
+    SMG_CUDA(d2h_sync(h.data(), ch->LL, h.size() * 8, ch->st));
     for (int i = 0; i < ch->n; i++)
       for (int k = 0; k < K; k++) LL[(size_t)i * K + k] = h[(size_t)i * ch->ldl + k];
   }
@@ -1361,7 +1417,7 @@ int smg_debug_ll_block(smg_chain* ch, double* LL, int* mism) {
     ch->h_launches++;
     SMG_CUDA(cudaGetLastError());
     SMG_CUDA(cudaStreamSynchronize(ch->st));
-    SMG_CUDA(cudaMemcpy(mism, d, (size_t)ch->n * K * 4, cudaMemcpyDeviceToHost));
+    SMG_CUDA(d2h_sync(mism, d, (size_t)ch->n * K * 4, ch->st));
     cudaFree(d);
   }
   return 0;
@@ -1372,7 +1428,7 @@ int smg_debug_neal8_scan(smg_chain* ch, const double* tape) {
   SMG_CUDA(cudaSetDevice(ch->device));
   const double* td = nullptr;
   if (tape) {
-    SMG_CUDA(cudaMemcpy(ch->tape_d, tape, (size_t)ch->n * (ch->m_aux + 1) * 8, cudaMemcpyHostToDevice));
+    SMG_CUDA(h2d_sync(ch->tape_d, tape, (size_t)ch->n * (ch->m_aux + 1) * 8, ch->st));
     td = ch->tape_d;
   }
   int rc = neal8_pass(ch, td, true);
@@ -1399,13 +1455,13 @@ int smg_debug_histogram(smg_chain* ch, int* H, int* counts, int* mmax_out) {
   if (mmax_out) *mmax_out = ch->mmax;
   if (H) {
     std::vector<int> h((size_t)K * ch->pp * ch->mmax);
-    SMG_CUDA(cudaMemcpy(h.data(), ch->H, h.size() * 4, cudaMemcpyDeviceToHost));
+    SMG_CUDA(d2h_sync(h.data(), ch->H, h.size() * 4, ch->st));
     for (int k = 0; k < K; k++)
       for (int j = 0; j < ch->p; j++)
         for (int a = 0; a < ch->mmax; a++)
           H[((size_t)k * ch->p + j) * ch->mmax + a] = h[((size_t)k * ch->pp + j) * ch->mmax + a];
   }
-  if (counts) SMG_CUDA(cudaMemcpy(counts, ch->counts, (size_t)K * 4, cudaMemcpyDeviceToHost));
+  if (counts) SMG_CUDA(d2h_sync(counts, ch->counts, (size_t)K * 4, ch->st));
   return 0;
 }
 
@@ -1418,11 +1474,11 @@ int smg_debug_update_phi(smg_chain* ch, const double* u_center, const double* u_
   const int K = ch->h_K;
   const double *uc = nullptr, *us = nullptr;
   if (u_center) {
-    SMG_CUDA(cudaMemcpy(ch->uc_d, u_center, (size_t)K * ch->p * 8, cudaMemcpyHostToDevice));
+    SMG_CUDA(h2d_sync(ch->uc_d, u_center, (size_t)K * ch->p * 8, ch->st));
     uc = ch->uc_d;
   }
   if (u_sigma) {
-    SMG_CUDA(cudaMemcpy(ch->us_d, u_sigma, (size_t)K * ch->p * 8, cudaMemcpyHostToDevice));
+    SMG_CUDA(h2d_sync(ch->us_d, u_sigma, (size_t)K * ch->p * 8, ch->st));
     us = ch->us_d;
   }
   rc = update_phi_all(ch, SUB_PHI_AFTER_SCAN, uc, us);
@@ -1545,19 +1601,25 @@ int smg_psm_create(int n, int device, int capacity_sweeps, void* external_psm_in
   P->n = n;
   P->device = device;
   P->cap = capacity_sweeps;
+  if (cudaStreamCreateWithFlags(&P->st, cudaStreamNonBlocking) != cudaSuccess) {
+    delete P;
+    return fail(SMG_ERR_CUDA, "cudaStreamCreate failed");
+  }
   if (external_psm_int32) {
     P->psm = (int*)external_psm_int32;
   } else {
     if (cudaMalloc(&P->psm, (size_t)n * n * sizeof(int)) != cudaSuccess) {
+      cudaStreamDestroy(P->st);
       delete P;
       return fail(SMG_ERR_CUDA, "cudaMalloc of the n x n int32 matrix failed");
     }
     P->owns = true;
-    cudaMemset(P->psm, 0, (size_t)n * n * sizeof(int));
+    // cleared on the stream the accumulate kernels run on: ordered before the first flush
+    cudaMemsetAsync(P->psm, 0, (size_t)n * n * sizeof(int), P->st);
   }
   if (cudaMalloc(&P->labels, (size_t)capacity_sweeps * n) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&P->st, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreate(&P->ev[0]) != cudaSuccess || cudaEventCreate(&P->ev[1]) != cudaSuccess) {
+      cudaEventCreate(&P->ev[0]) != cudaSuccess || cudaEventCreate(&P->ev[1]) != cudaSuccess ||
+      cudaStreamSynchronize(P->st) != cudaSuccess) {
     smg_psm_destroy(P);
     return fail(SMG_ERR_CUDA, "allocation of the label buffer failed");
   }

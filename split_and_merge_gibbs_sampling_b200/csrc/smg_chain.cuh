@@ -42,6 +42,19 @@ inline cudaError_t dev_pool_init(int device) {
   done[device] = (e == cudaSuccess);
   return e;
 }
+// Host <-> device copies ordered on the CONSUMING stream (the chains' streams are non-blocking: a legacy-stream
+// cudaMemcpy from pageable memory may return before its DMA has landed and is not ordered against them), followed by
+// a wait so that the host buffer may be reused and the data is visible to every other stream.
+inline cudaError_t h2d_sync(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+}
+inline cudaError_t d2h_sync(void* dst, const void* src, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return cudaSuccess;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+}
 template <typename T>
 inline cudaError_t dev_malloc(T** ptr, size_t bytes, cudaStream_t st) {
   return cudaMallocAsync((void**)ptr, bytes ? bytes : 1, st);
@@ -82,13 +95,17 @@ struct smg_chain {
   std::vector<double> h_v, h_w;
   // ---- device buffers
   cudaStream_t st = nullptr;
-  cudaStream_t st_aux = nullptr;  // side stream: auxiliary-component columns of the NEXT pass, behind the split-merge step
+  cudaStream_t st_aux = nullptr;  // side stream: auxiliary-component columns of the NEXT pass, under this pass's scan
+  cudaStream_t st_k1 = nullptr;   // side stream: likelihood block of the NEXT pass, under the split-merge proposal
+  cudaEvent_t ev_phi_done = nullptr, ev_k1_done = nullptr;
   cudaEvent_t ev_scan_done = nullptr, ev_aux_done = nullptr;
   cudaEvent_t ev_aux_t0 = nullptr, ev_aux_t1 = nullptr;  // device time of the prefetched aux pass (side stream)
   bool aux_timed = false;
   long long ll_for_iter = -1;      // the LL block holds the columns of the state at the start of this iteration (-1: stale)
   cudaEvent_t ev_k1[2] = {};      // device time of the likelihood-block kernel wherever in the sweep it was launched
   bool k1_timed = false;
+  bool k1_overlap = true;        // evaluate the next pass's likelihood block beside the split-merge proposal
+  bool k1_in_tail = false;       // the block of the last timed iteration ran inside its [6]-[7] interval (not overlapped)
   bool many = false;              // stepped together with other chains: keep every kernel small (no gang-scheduled grids)
   bool aux_ready = false;         // LLaux / aux_e already hold the columns of iteration aux_iter
   long long aux_iter = -1;
@@ -104,10 +121,12 @@ struct smg_chain {
   int phi_parts = 1;       // CTAs per job in phi_update_kernel
   int cur = 0;
   int *c = nullptr, *K = nullptr, *counts = nullptr, *counts_slot = nullptr, *slot2label = nullptr;
-  double *LL = nullptr, *LLaux = nullptr, *mrg = nullptr;
+  double *LL = nullptr, *mrg = nullptr;
+  double* LLaux[2] = {nullptr, nullptr};  // aux columns, double-buffered: [aux_buf] feeds the current pass
+  int* aux_e[2] = {nullptr, nullptr};
+  int aux_buf = 0;
   int* und_blk = nullptr;   // flagged rows per scan block
   uint8_t* und0 = nullptr;  // [n padded] precomputed screen flags of the allocation scan (scan_margin_kernel)
-  int* aux_e = nullptr;
   uint8_t* pcen = nullptr;
   double *psig = nullptr, *pisg = nullptr, *pden = nullptr, *psden = nullptr;
   bool pool_valid = false;

@@ -125,3 +125,58 @@ def test_validate_state_and_device_generator():
     from sklearn.metrics import adjusted_rand_score
     assert adjusted_rand_score(lab, ch.snapshot(with_phi=False)["c_i"]) > 0.95
     ch.close()
+
+
+def _run_trace(pb, mode, iters, overlap=True, **kw):
+    """Steps a chain one iteration at a time under the given split-merge device path; returns the snapshots."""
+    import os
+    os.environ["SMG_SM_MODE"] = mode
+    os.environ["SMG_NO_K1_OVERLAP"] = "0" if overlap else "1"
+    try:
+        ch = pb.chain(**kw)
+        out = []
+        for _ in range(iters):
+            ch.step(1)
+            s = ch.snapshot()
+            _check_snapshot(pb, s)
+            out.append(s)
+        st = ch.stats()
+        ch.close()
+    finally:
+        os.environ.pop("SMG_SM_MODE", None)
+        os.environ.pop("SMG_NO_K1_OVERLAP", None)
+    return out, st
+
+
+def test_split_merge_device_paths_give_the_same_chain():
+    """Cluster kernel, cooperative kernel and the sequence of launches consume the same Philox draws and take the same
+    decisions: the chains coincide (allocations, K, acceptance flags, centres).  The start is over-merged (everything in
+    one cluster) so that splits ARE accepted, and log-likelihoods are checked against the oracle after every iteration:
+    the likelihood block evaluated beside the proposal must have been patched after each acceptance."""
+    pb = Problem(2400, 32, 4, 6, seed=91, s=0.6)
+    kw = dict(c_i=np.zeros(2400, dtype=np.int32), seed=92, t=4, r=3)
+    ref, st_ref = _run_trace(pb, "multi", 40, overlap=False, **kw)
+    assert st_ref["sm_accepted"] >= 2  # the patch path is exercised
+    for mode, overlap in (("cluster", True), ("coop", True), ("multi", True), ("cluster", False)):
+        got, st = _run_trace(pb, mode, 40, overlap=overlap, **kw)
+        assert st["sm_accepted"] == st_ref["sm_accepted"], mode
+        for a, b in zip(ref, got):
+            assert a["K"] == b["K"] and a["accepted"] == b["accepted"], mode
+            assert np.array_equal(a["c_i"], b["c_i"]), mode
+            assert np.array_equal(a["centers"], b["centers"]), mode
+            assert np.max(np.abs(a["sigmas"] - b["sigmas"]) / b["sigmas"]) < 1e-12, mode
+            assert abs(a["loglikelihood"] - b["loglikelihood"]) <= 1e-12 * abs(b["loglikelihood"]), mode
+
+
+def test_merge_acceptance_is_patched_too():
+    """Over-split start (every true cluster cut in two): merges are accepted; same checks."""
+    pb = Problem(1600, 24, 4, 4, seed=93, s=0.5)
+    c0 = (pb.labels * 2 + (np.arange(1600) // 4) % 2).astype(np.int32)
+    kw = dict(c_i=c0, seed=94, t=3, r=3)
+    ref, st_ref = _run_trace(pb, "multi", 60, overlap=False, **kw)
+    assert st_ref["sm_accepted"] >= 1
+    got, st = _run_trace(pb, "cluster", 60, overlap=True, **kw)
+    assert st["sm_accepted"] == st_ref["sm_accepted"]
+    for a, b in zip(ref, got):
+        assert a["K"] == b["K"] and a["accepted"] == b["accepted"]
+        assert np.array_equal(a["c_i"], b["c_i"])

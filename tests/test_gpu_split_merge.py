@@ -103,10 +103,15 @@ def build_gpu_tape(log, n, p, t, r, ref, c_before):
     return T, labA, labB
 
 
-def run_case(pb, state, seed, t=3, r=3, persistent=True):
+MODES = ["cluster", "coop", "multi"]
+
+
+def run_case(pb, state, seed, t=3, r=3, mode="cluster"):
     import os
-    # the restricted-scan chain runs either as one cooperative kernel or as a sequence of launches (same results)
-    os.environ["SMG_SM_PERSISTENT"] = "1" if persistent else "0"
+    # the proposal runs as one thread-block cluster, as one cooperative kernel or as a sequence of launches
+    # (same draws, same decisions)
+    os.environ["SMG_SM_MODE"] = mode
+    os.environ.pop("SMG_SM_PERSISTENT", None)
     K, c, cen, sig = state
     rng = np.random.default_rng(seed)
     tape = (rng.integers(0, 2**53, size=50 + (t + 3) * pb.n + (2 * t + r + 12) * 2 * pb.p).astype(np.float64) + 0.5) / 2.0**53
@@ -159,9 +164,9 @@ def check_case(pb, ref, got, after, labA, labB):
     assert np.max(rel_err(after["sigmas"], ref["sigma"])) < 1e-9
 
 
-@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("seed", list(range(1, 13)))
-def test_split_merge_matches_oracle(seed, persistent):
+def test_split_merge_matches_oracle(seed, mode):
     # over-merged state (K_true=6 collapsed to 3 labels) => splits get accepted; seeds hit both branches
     pb = Problem(600, 24, 4, 6, seed=100 + seed, s=0.6)
     K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
@@ -171,11 +176,12 @@ def test_split_merge_matches_oracle(seed, persistent):
         state = (K2, c2, cen2, sig2)
     else:
         state = (K, c, cen, sig)
-    ref, got, after, labA, labB = run_case(pb, state, seed, persistent=persistent)
+    ref, got, after, labA, labB = run_case(pb, state, seed, mode=mode)
     check_case(pb, ref, got, after, labA, labB)
 
 
-def test_split_merge_accepts_happen_and_match():
+@pytest.mark.parametrize("mode", MODES)
+def test_split_merge_accepts_happen_and_match(mode):
     # make sure both an accepted split and an accepted merge are exercised somewhere in the seed range
     acc_split = acc_merge = 0
     for seed in range(20, 60):
@@ -192,7 +198,7 @@ def test_split_merge_accepts_happen_and_match():
             c = np.minimum(c, K - 2).astype(np.int32)
             K -= 1
             cen, sig = cen[:K].copy(), sig[:K].copy()
-        ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=2, r=2)
+        ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=2, r=2, mode=mode)
         check_case(pb, ref, got, after, labA, labB)
         if ref["accepted"]:
             if ref["is_split"]:
@@ -204,9 +210,9 @@ def test_split_merge_accepts_happen_and_match():
     assert acc_split > 0 and acc_merge > 0
 
 
-@pytest.mark.parametrize("persistent", [True, False])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("seed", [3, 4])
-def test_split_merge_large_member_set(seed, persistent):
+def test_split_merge_large_member_set(seed, mode):
     # |S| spans several 1024-member chunks of the restricted-scan decision kernel; low-dimensional, noisy data
     # keeps many members non-robust (count-dependent), so both the parallel and the ordered part are exercised
     pb = Problem(3500 if seed % 2 == 0 else 7000, 12, 3, 2, seed=200 + seed, s=0.9)
@@ -214,6 +220,6 @@ def test_split_merge_large_member_set(seed, persistent):
     if seed % 2 == 0:  # everything in one cluster => a split proposal over n-2 members
         c = np.zeros_like(c)
         K, cen, sig = 1, cen[:1].copy(), sig[:1].copy()
-    ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=3, r=2, persistent=persistent)
+    ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=3, r=2, mode=mode)
     assert ref["S"].size > 2048
     check_case(pb, ref, got, after, labA, labB)
