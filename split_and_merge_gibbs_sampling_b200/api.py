@@ -180,10 +180,17 @@ class Chain:
         return dict(zip(keys, (int(x) for x in out)))
 
     def sm_profile(self):
-        out = np.zeros(16, dtype=np.uint64)
+        out = np.zeros(64, dtype=np.uint64)
         lb.check(self.lib.smg_debug_sm_profile(self.h, out.ctypes.data_as(lb.c_ull_p)))
-        keys = ["select", "setup", "decide", "bar1", "moves", "bar2", "draws", "bar3", "mh_terms", "mh_sums", "launches"]
-        return dict(zip(keys, (int(x) for x in out)))
+        names = {0: "select+prior", 1: "bar_a", 2: "S_write", 3: "bar_b", 4: "members+rows+hist", 5: "bar_c", 6: "table",
+                 7: "dots|mg_draws", 8: "compact", 9: "bar1", 10: "walk", 11: "moves", 12: "bar2", 13: "logits|slices",
+                 14: "draws", 16: "bar3", 17: "tail", 18: "bar_f", 19: "mh_load", 20: "mh_terms", 21: "bar_h", 22: "mh_sums",
+                 23: "bar_i", 24: "accept"}
+        keys = {k: "M." + v for k, v in names.items()}
+        keys.update({32 + k: "P." + v for k, v in names.items()})
+        keys.update({50: "D.entry", 51: "D.philox", 52: "D.centre", 53: "D.sigma", 54: "D.tail", 55: "D.publish"})
+        keys.update({56: "nnr_screen_fail_cta0", 57: "nnr_pairE_micro", 58: "launches", 59: "nnr_total", 60: "nnr_scan0", 61: "nnr_scan1", 62: "nnr_scan2", 63: "nnr_scan3"})
+        return {name: int(out[k]) for k, name in keys.items()}
 
     def timings(self):
         out = np.zeros(8)

@@ -25,6 +25,31 @@ static int dalloc(T** ptr, size_t count) {
   return 0;
 }
 
+// ziggurat tables of the normal generator (smg_device.cuh), once per device
+static int zig_init(int device) {
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64) return fail(SMG_ERR_ARG, "bad device ordinal");
+  if (done[device]) return 0;
+  double x[SMG_ZIG_C + 1], r[SMG_ZIG_C];
+  double f = std::exp(-0.5 * SMG_ZIG_R * SMG_ZIG_R);
+  x[0] = SMG_ZIG_V / f;
+  x[1] = SMG_ZIG_R;
+  x[SMG_ZIG_C] = 0.0;
+  for (int i = 2; i < SMG_ZIG_C; i++) {
+    x[i] = std::sqrt(-2.0 * std::log(SMG_ZIG_V / x[i - 1] + f));
+    f = std::exp(-0.5 * x[i] * x[i]);
+  }
+  for (int i = 0; i < SMG_ZIG_C; i++) r[i] = x[i + 1] / x[i];
+  SMG_CUDA(cudaSetDevice(device));
+  SMG_CUDA(cudaMemcpyToSymbol(g_zig_x, x, sizeof(x)));
+  SMG_CUDA(cudaMemcpyToSymbol(g_zig_r, r, sizeof(r)));
+  SMG_CUDA(cudaDeviceSynchronize());
+  done[device] = true;
+  return 0;
+}
+
 static int status_to_error(int st) {
   if (st == 0) return SMG_OK;
   if (st & ST_BAD_PROB) return fail(SMG_ERR_PROB, "Probabilities must be finite and non-negative! (allocation draw)");
@@ -42,6 +67,7 @@ static int chain_alloc(smg_chain* ch) {
   const int n = ch->n, pp = ch->pp, NST = ch->NST;
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(dev_pool_init(ch->device));
+  if (zig_init(ch->device)) return SMG_ERR_CUDA;
   {
     // the chain's (latency-bound) stream outranks the side stream: the side stream's bandwidth-bound gather fills
     // every SM and would otherwise hold back the small kernels it is meant to overlap
@@ -52,6 +78,7 @@ static int chain_alloc(smg_chain* ch) {
     SMG_CUDA(cudaStreamCreateWithPriority(&ch->st_k1, cudaStreamNonBlocking, prio_lo));
   }
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_phi_done, cudaEventDisableTiming));
+  SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_aux_go, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_k1_done, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_scan_done, cudaEventDisableTiming));
   SMG_CUDA(cudaEventCreateWithFlags(&ch->ev_aux_done, cudaEventDisableTiming));
@@ -138,6 +165,7 @@ static void chain_free(smg_chain* ch) {
   if (ch->ev_aux_t0) cudaEventDestroy(ch->ev_aux_t0);
   if (ch->ev_aux_t1) cudaEventDestroy(ch->ev_aux_t1);
   if (ch->ev_phi_done) cudaEventDestroy(ch->ev_phi_done);
+  if (ch->ev_aux_go) cudaEventDestroy(ch->ev_aux_go);
   if (ch->ev_k1_done) cudaEventDestroy(ch->ev_k1_done);
   if (ch->st_aux) cudaStreamDestroy(ch->st_aux);
   if (ch->st_k1) cudaStreamDestroy(ch->st_k1);
@@ -188,8 +216,10 @@ static int prefetch_next_aux(smg_chain* ch) {
   // an iteration that re-draws the pool before the next pass would invalidate the columns
   for (long long it = ch->iter; it < next_iter; it++)
     if (it % 1000 == 0) return 0;
-  // the other buffer was last read by the scan of the previous pass
-  SMG_CUDA(cudaStreamWaitEvent(ch->st_aux, ch->ev_scan_done, 0));
+  // everything enqueued on the chain's stream so far must be complete: the other buffer was last read by the scan of
+  // the previous pass, and the pool may have been re-drawn since (launcher.cpp:123-129)
+  SMG_CUDA(cudaEventRecord(ch->ev_aux_go, ch->st));
+  SMG_CUDA(cudaStreamWaitEvent(ch->st_aux, ch->ev_aux_go, 0));
   cudaEventRecord(ch->ev_aux_t0, ch->st_aux);
   if (launch_aux_ll(ch, nullptr, ch->st_aux, next_iter, ch->aux_buf ^ 1)) return SMG_ERR_CUDA;
   cudaEventRecord(ch->ev_aux_t1, ch->st_aux);
@@ -1081,12 +1111,12 @@ int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
 
 int smg_debug_sm_profile(smg_chain* ch, unsigned long long* out16) {
   if (!ch || !out16) return fail(SMG_ERR_ARG, "NULL argument");
-  memset(out16, 0, 16 * sizeof(unsigned long long));
+  memset(out16, 0, 64 * sizeof(unsigned long long));
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   if (!ch->sm || !ch->sm->smc || !ch->sm->smc->prof) return 0;
-  SMG_CUDA(d2h_sync(out16, ch->sm->smc->prof, 16 * 8, ch->st));
-  SMG_CUDA(cudaMemsetAsync(ch->sm->smc->prof, 0, 16 * 8, ch->st));
+  SMG_CUDA(d2h_sync(out16, ch->sm->smc->prof, 64 * 8, ch->st));
+  SMG_CUDA(cudaMemsetAsync(ch->sm->smc->prof, 0, 64 * 8, ch->st));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
   return 0;
 }
@@ -1555,6 +1585,11 @@ int smg_debug_rhig_u(int count, double v, double w, double m, unsigned long long
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
   double* buf = nullptr;
+  {
+    int dev = 0;
+    SMG_CUDA(cudaGetDevice(&dev));
+    if (zig_init(dev)) return SMG_ERR_CUDA;
+  }
   SMG_CUDA(cudaMalloc(&buf, (size_t)count * 8));
   RngKey key;
   key.k0 = (uint32_t)seed;

@@ -97,7 +97,7 @@ struct smg_chain {
   cudaStream_t st = nullptr;
   cudaStream_t st_aux = nullptr;  // side stream: auxiliary-component columns of the NEXT pass, under this pass's scan
   cudaStream_t st_k1 = nullptr;   // side stream: likelihood block of the NEXT pass, under the split-merge proposal
-  cudaEvent_t ev_phi_done = nullptr, ev_k1_done = nullptr;
+  cudaEvent_t ev_phi_done = nullptr, ev_k1_done = nullptr, ev_aux_go = nullptr;
   cudaEvent_t ev_scan_done = nullptr, ev_aux_done = nullptr;
   cudaEvent_t ev_aux_t0 = nullptr, ev_aux_t1 = nullptr;  // device time of the prefetched aux pass (side stream)
   bool aux_timed = false;

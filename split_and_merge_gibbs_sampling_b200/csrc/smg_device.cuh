@@ -138,7 +138,10 @@ __device__ __forceinline__ double hamming_den(double s, int m) { return log(1.0 
 // Returns both log I_x(a,b) (lower) and log(1 - I_x(a,b)) (upper).
 // `lb` = lbeta(a,b) supplied by the caller (computed once per draw).
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ double lbeta_d(double a, double b) { return lgamma(a) + lgamma(b) - lgamma(a + b); }
+// (one out-of-line copy: lgamma expands to a few hundred instructions, and the code that calls it runs once per
+// proposal on cold instruction caches)
+__device__ __noinline__ double lgamma_ni(double x) { return lgamma(x); }
+__device__ __forceinline__ double lbeta_d(double a, double b) { return lgamma_ni(a) + lgamma_ni(b) - lgamma_ni(a + b); }
 
 __device__ __noinline__ double betacf_d(double a, double b, double x) {
   const double EPS = 3e-16, FPMIN = 1e-300;
@@ -210,7 +213,7 @@ __device__ __noinline__ double norm_const2_d(double w, double v, double m) {
 }
 
 // logdensity_hig (split_merge.cpp:6-18)
-__device__ inline double logdensity_hig_d(double s, double v, double w, double m) {
+__device__ __noinline__ double logdensity_hig_d(double s, double v, double w, double m) {
   double K = norm_const2_d(w, v, m);
   return K - (v + w) * log(1.0 + exp(-1.0 / s) * (m - 1.0)) - (w + 1.0) / s - 2.0 * log(s);
 }
@@ -292,6 +295,63 @@ struct SubStream {
   }
 };
 
+// Standard normal by the ziggurat method (Marsaglia & Tsang 2000, in Doornik's 2005 form: 128 layers, layer index and
+// position from separate random bits).  Double-precision dependent chains are what these draws cost on this GPU
+// (a log or normcdfinv is a thousand cycles); the ziggurat's common case is one table look-up, one multiplication and one
+// comparison.  Tables: g_zig_x[129] (layer edges, x[128] = 0), g_zig_r[128] = x[i+1]/x[i]; filled by the host once per
+// device (smg_zig_init).  One Philox call feeds a whole attempt: o[0..1] -> position, o[2] & 127 -> layer,
+// (o[2] >> 7, o[3]) -> the uniform of the caller's acceptance test.
+#define SMG_ZIG_C 128
+#define SMG_ZIG_R 3.442619855899
+#define SMG_ZIG_V 9.91256303526217e-3
+__device__ double g_zig_x[SMG_ZIG_C + 1];
+__device__ double g_zig_r[SMG_ZIG_C];
+
+struct NormU {
+  double x;  // N(0,1)
+  double u;  // independent U(0,1)
+};
+__device__ __forceinline__ void substream_raw(SubStream& rs, uint32_t o[4]) {
+  philox4x32_10(rs.a, rs.b | (rs.ctr << 20), rs.site | (rs.key.sub << 8), rs.key.sweep, rs.key.k0, rs.key.k1, o);
+  rs.ctr++;
+}
+__device__ __noinline__ NormU zig_normal_u(SubStream& rs) {
+  NormU out;
+  for (;;) {
+    uint32_t o[4];
+    substream_raw(rs, o);
+    const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;  // position in (-1, 1)
+    const int i = (int)(o[2] & (SMG_ZIG_C - 1));
+    out.u = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);  // 53 bits
+    const double xi = __ldg(&g_zig_x[i]);
+    if (fabs(up) < __ldg(&g_zig_r[i])) {  // inside the layer's rectangle: 98.8% of the attempts
+      out.x = up * xi;
+      return out;
+    }
+    if (i == 0) {  // tail beyond R
+      double x, y;
+      do {
+        uint32_t q[4];
+        substream_raw(rs, q);
+        x = log(u01_from_bits(q[0], q[1])) / SMG_ZIG_R;
+        y = log(u01_from_bits(q[2], q[3]));
+      } while (-2.0 * y < x * x);
+      out.x = up < 0.0 ? x - SMG_ZIG_R : SMG_ZIG_R - x;
+      return out;
+    }
+    {  // wedge
+      const double x = up * xi, xn = __ldg(&g_zig_x[i + 1]);
+      const double f0 = exp(-0.5 * (xi * xi - x * x)), f1 = exp(-0.5 * (xn * xn - x * x));
+      uint32_t q[4];
+      substream_raw(rs, q);
+      if (f1 + u01_from_bits(q[0], q[1]) * (f0 - f1) < 1.0) {
+        out.x = x;
+        return out;
+      }
+    }
+  }
+}
+
 // Gamma(shape, 1) by Marsaglia & Tsang (2000); shape < 1 through Gamma(shape+1) * U^(1/shape)
 __device__ __noinline__ double gamma_draw_d(SubStream& rs, double shape) {
   double boost = 1.0;
@@ -299,16 +359,16 @@ __device__ __noinline__ double gamma_draw_d(SubStream& rs, double shape) {
     boost = pow(rs.next(), 1.0 / shape);
     shape += 1.0;
   }
-  const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+  const double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
   for (int it = 0; it < 64; it++) {
-    const double x = normcdfinv(rs.next());
+    const NormU nu = zig_normal_u(rs);
+    const double x = nu.x;
     double vv = 1.0 + c * x;
     if (vv <= 0.0) continue;
     vv = vv * vv * vv;
-    const double u = rs.next();
     const double x2 = x * x;
-    if (u < 1.0 - 0.0331 * x2 * x2) return boost * d * vv;
-    if (log(u) < 0.5 * x2 + d * (1.0 - vv + log(vv))) return boost * d * vv;
+    if (nu.u < 1.0 - 0.0331 * x2 * x2) return boost * d * vv;
+    if (log(nu.u) < 0.5 * x2 + d * (1.0 - vv + log(vv))) return boost * d * vv;
   }
   return boost * d;  // not reached in practice (acceptance > 95% per round)
 }
@@ -318,14 +378,12 @@ __device__ __noinline__ double gamma_draw_d(SubStream& rs, double shape) {
 // hyperg.cpp:359-368); after 8 rejected proposals (the truncation keeps little mass) one exact
 // inverse-CDF draw (the reference's bisection branch) finishes -- the mixture is still the exact law.
 __device__ inline double hig_draw_u_d(SubStream& rs, double v, double w, double m) {
-  const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
+  const double a = w + 1.0, b = v - 1.0;
   for (int attempt = 0; attempt < 8; attempt++) {
     const double ga = gamma_draw_d(rs, a), gb = gamma_draw_d(rs, b);
-    const double x = ga / (ga + gb);
-    if (x > 0.0 && x <= xmax) {
-      const double u = x / ((m - 1.0) * (1.0 - x));
-      if (u > 0.0 && u < 1.0) return u;
-    }
+    // x = ga/(ga+gb) <= (m-1)/m  <=>  u = x/((m-1)(1-x)) = ga/((m-1) gb) <= 1: one division
+    const double u = ga / ((m - 1.0) * gb);
+    if (u > 0.0 && u < 1.0) return u;
   }
   return hig_inv_u_d(rs.next(), v, w, m);
 }
@@ -338,7 +396,7 @@ __device__ inline double hig_draw_u_d(SubStream& rs, double v, double w, double 
 __device__ inline double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
                                         unsigned gmask, int gbase) {
   SubStream rs(key, g == 1 ? U_SIGMA_B : U_SIGMA, sa, sb);
-  const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
+  const double a = w + 1.0, b = v - 1.0;
   double res = 0.0;
   for (int attempt = 0; attempt < 8; attempt++) {
     double gm = 0.0;
@@ -346,13 +404,10 @@ __device__ inline double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t
     const double gb = __shfl_sync(gmask, gm, gbase + 1);
     int ok = 0;
     if (g == 0) {
-      const double x = gm / (gm + gb);
-      if (x > 0.0 && x <= xmax) {
-        const double u = x / ((m - 1.0) * (1.0 - x));
-        if (u > 0.0 && u < 1.0) {
-          ok = 1;
-          res = u;
-        }
+      const double u = gm / ((m - 1.0) * gb);  // = x/((m-1)(1-x)) with x = gm/(gm+gb); u < 1 <=> x < (m-1)/m
+      if (u > 0.0 && u < 1.0) {
+        ok = 1;
+        res = u;
       }
     }
     if (__shfl_sync(gmask, ok, gbase)) return res;

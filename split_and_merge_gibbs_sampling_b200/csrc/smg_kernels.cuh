@@ -1557,7 +1557,25 @@ struct PhiArgs {
 // registers, and when the largest probability is unique and already covers u -- the first step of Rcpp's
 // descending-order walk -- the sort is skipped; ties and the other draws take the general path, which
 // reproduces R's revsort permutation.  Returns the 1-based level.
+#define SMG_CENTER_DOM 44.0
 __device__ __forceinline__ int draw_center(const int* __restrict__ h, int nk, double sg, int m, double u) {
+  {  // dominance screen (see draw_center_grp)
+    int h1 = -1, h2 = -1, arg = 0, ntop = 0;
+    for (int a = 0; a < m; a++) {
+      const int v = h[a];
+      if (v > h1) {
+        h2 = h1;
+        h1 = v;
+        arg = a;
+        ntop = 1;
+      } else if (v == h1) {
+        ntop++;
+      } else if (v > h2) {
+        h2 = v;
+      }
+    }
+    if (ntop == 1 && (double)(h1 - max(h2, 0)) >= SMG_CENTER_DOM * sg && sg > 0.0) return arg + 1;
+  }
   if (m <= 8) {
     double p[8];
     double mx = -CUDART_INF;
@@ -1621,6 +1639,19 @@ __device__ __forceinline__ int draw_center(const int* __restrict__ h, int nk, do
 __device__ __forceinline__ int draw_center_grp(int hg, int nk, double sg, int m, double u, int g, unsigned gmask,
                                                int gbase, double* s_match) {
   const bool valid = g < m;
+  {
+    // Dominance screen: when the most frequent level leads every other one by >= SMG_CENTER_DOM nats of
+    // (count difference)/sigma, the sums below are exactly 1.0 in double precision ((m-1) e^-44 < 2^-54), the leader's
+    // normalised probability is exactly 1.0 and Rcpp::sample returns it for every u: same result, no exp / division.
+    const int hv = valid ? hg : -1;
+    const int h1 = __reduce_max_sync(gmask, hv);
+    const unsigned top = __ballot_sync(gmask, hv == h1) & gmask;
+    const int h2 = __reduce_max_sync(gmask, hv == h1 ? -1 : hv);
+    if (__popc(top) == 1 && (double)(h1 - max(h2, 0)) >= SMG_CENTER_DOM * sg && sg > 0.0) {
+      *s_match = (double)h1;
+      return (__ffs(top) - 1 - gbase) + 1;
+    }
+  }
   const double lp = valid ? -((double)nk - (double)hg) / sg : -CUDART_INF;
   double mx = lp;
 #pragma unroll

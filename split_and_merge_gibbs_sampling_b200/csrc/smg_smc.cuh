@@ -1,22 +1,28 @@
 // smg_smc.cuh -- the Jain-Neal split-merge proposal (code/split_merge.cpp:542-598) as ONE thread-block cluster.
 //
 // sm_chain_kernel (smg_sm.cuh) runs the proposal on 120 CTAs that meet ~55 times at a global-counter grid barrier
-// (1.2 us each) and re-read the member rows from L2 in every phase; 57% of a sweep was spent there, 65% of its stall
-// samples on the barrier.  Here the same proposal lives on one cluster of CS (16) CTAs:
-//   * the members of S (+ the two anchors) are dealt to the CTAs in contiguous position blocks; every CTA keeps its
-//     members' rows (as many as fit), sides, row indices and allocation logits in shared memory for the whole proposal;
-//   * the parameter updates are dealt by ATTRIBUTE slices (pp/CS attributes per CTA, all jobs of a step side by side,
-//     PHI_G lanes per attribute): a CTA sums its slice of the per-CTA side histograms straight out of the other CTAs'
-//     shared memory (DSMEM), draws, and publishes (centre, 1/sigma) into every CTA's shared memory;
-//   * phases are separated by hardware cluster barriers (~0.2 us) -- three per restricted scan;
+// (1.2 us each), re-read the member rows from L2 in every phase and re-fetch the long parameter-draw code from L2 in
+// every scan; 57% of a sweep was spent there.  Here the same proposal lives on one cluster of CS (16) CTAs with two
+// roles, so that each SM's instruction footprint per scan stays inside its instruction cache:
+//   * MEMBER CTAs (the first half): the members of S (+ the two anchors) are dealt to them in contiguous position
+//     blocks; a CTA keeps its members' rows (transposed: word-major, one thread per member), sides and allocation
+//     logits in shared memory for the whole proposal.  Per scan it builds the table
+//     T[j][a] = [a != c_Bj]/sigma_Bj - [a != c_Aj]/sigma_Aj  and gets LL_A - LL_B of a member as 256 look-ups + adds;
+//     it maintains the side histograms of its members incrementally (only members that change side are moved).
+//   * PARAMETER CTAs (the second half): each owns pp/(CS/2) attributes; it sums its slice of the member CTAs' side
+//     histograms straight out of their shared memory (DSMEM), draws (centre, sigma) for the two sides -- PHI_G lanes
+//     per attribute, same arithmetic as phi_job_body -- and publishes (centre, 1/sigma) into the member CTAs' shared
+//     memory.  The r updates of the merge launch state do not depend on the scans: they run while the member CTAs
+//     work.
+//   * phases are separated by hardware cluster barriers (~0.2 us): three per restricted scan;
 //   * a member's restricted-Gibbs decision is piecewise constant in D = (log n_1 + LL_1) - (log n_2 + LL_2)
 //     (smg_sm.cuh, sm_d_region); with the count term bounded over the WHOLE scan (|log-count term| <= log nS) almost
 //     every member is decided by its owner without knowing the running counts; the few that are not go through the
 //     ordered walk of smg_sm.cuh on CTA 0 (one extra barrier, only when there are any).
-// Same draws (Philox keys, injected uniforms), same decisions and the same per-attribute arithmetic as the other two
-// paths; only the association of the sums of log-normalisers inside the scans differs (rank partials instead of the
-// 256-leaf tree), i.e. the last bits of the likelihood differences.  The slots an accepted proposal hands to the
-// state get their log-normaliser sums from the canonical tree.
+// Same draws (Philox keys, injected uniforms) and the same decisions as the other two paths.  Sums are associated
+// differently (per-thread sums over the attributes instead of warp butterflies; rank partials of the log-normalisers),
+// so likelihood values agree to the last few bits, not bit for bit.  The slots an accepted proposal hands to the state
+// get their log-normaliser sums from the canonical 256-leaf tree.
 // The kernel leaves 132 SMs free: the likelihood block of the next pass runs beside it (sweep()).
 #pragma once
 #include "smg_sm.cuh"
@@ -29,44 +35,49 @@ namespace smg {
 
 struct SmcArgs {
   SmChainArgs A;   // same fields as the cooperative kernel
-  int CS;          // CTAs in the cluster
-  int sl;          // attributes per CTA (pp / CS)
-  int mcap;        // member capacity per CTA (>= ceil((n+2)/CS))
-  int rcap;        // member rows cached in shared memory per CTA
+  int CS;          // CTAs in the cluster: CS/2 member CTAs (ranks 0 .. CS/2-1), CS/2 parameter CTAs
+  int sl;          // attributes per parameter CTA (pp / (CS/2))
+  int TL;          // table entries per attribute (power of two > largest code)
+  int mcap;        // member capacity per member CTA (>= ceil((n+2)/(CS/2)))
+  int rcap;        // members whose row and logit are kept in shared memory, per member CTA
   double* den;     // [slots][pp] per-attribute log-normalisers
   double* gsvals;  // [6][pp] per-attribute addends of the six parameter-density terms
   double *nr_d0, *nr_lg;         // [n + 64] members whose decision depends on the running counts, by region
   int *nr_pre, *nr_z, *nr_idx;   // [n + 64]
   int* walk_out;                 // [2] side-1 change of those members (per scan parity)
-  unsigned long long* prof;      // optional phase cycle counters of CTA 0 / thread 0 (SMG_SMC_PROFILE)
+  unsigned long long* prof;      // [64] optional phase cycle counters (SMG_SMC_PROFILE)
 };
 
 struct SmcLayout {
-  size_t isgv, sigS, denS, vS, wS, sdpart, lg, phs, phl, slh, attrS, xchg, sel, srow, cenv, cenS, z, rows, total;
+  size_t T, Tp, pmax, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, total;
+  int rstr;  // member stride of the transposed rows (odd: conflict-free both by member and by word)
 };
 __host__ __device__ inline size_t smc_al(size_t x) { return (x + 15) & ~(size_t)15; }
-__host__ __device__ inline SmcLayout smc_layout(int pp, int mmax, int CS, int mcap, int rcap) {
+__host__ __device__ inline SmcLayout smc_layout(int pp, int mmax, int TL, int CS, int mcap, int rcap) {
   SmcLayout L;
-  const int sl = pp / CS;
+  const int sl = pp / (CS / 2);
   size_t o = 0;
+  L.rstr = rcap | 1;
+  L.T = o, o = smc_al(o + (size_t)pp * TL * 8);
+  L.Tp = o, o = smc_al(o + (TL == 8 ? (size_t)(pp / 2) * 64 * 4 : 0));  // fp32 pair table of the screen (codes < 8 only)
+  L.pmax = o, o = smc_al(o + (size_t)(pp / 2) * 4);
   L.isgv = o, o = smc_al(o + (size_t)3 * pp * 8);
+  L.sdpart = o, o = smc_al(o + (size_t)3 * SMC_MAXCS * 8);
   L.sigS = o, o = smc_al(o + (size_t)3 * sl * 8);
   L.denS = o, o = smc_al(o + (size_t)3 * sl * 8);
   L.vS = o, o = smc_al(o + (size_t)sl * 8);
   L.wS = o, o = smc_al(o + (size_t)sl * 8);
-  L.sdpart = o, o = smc_al(o + (size_t)3 * SMC_MAXCS * 8);
-  L.lg = o, o = smc_al(o + (size_t)mcap * 8);
+  L.lg = o, o = smc_al(o + (size_t)rcap * 8);
   L.phs = o, o = smc_al(o + (size_t)2 * pp * mmax * 4);
   L.phl = o, o = smc_al(o + (size_t)2 * pp * mmax * 4);
   L.slh = o, o = smc_al(o + (size_t)SH_N * sl * mmax * 4);
   L.attrS = o, o = smc_al(o + (size_t)sl * 4);
   L.xchg = o, o = smc_al(o + (size_t)2 * SMC_MAXCS * 4 * 4);
   L.sel = o, o = smc_al(o + (size_t)SMC_MAXCS * 4);
-  L.srow = o, o = smc_al(o + (size_t)mcap * 4);
+  L.rowsT = o, o = smc_al(o + (size_t)(pp / 4) * L.rstr * 4);
   L.cenv = o, o = smc_al(o + (size_t)3 * pp);
   L.cenS = o, o = smc_al(o + (size_t)3 * sl);
-  L.z = o, o = smc_al(o + (size_t)4 * mcap);
-  L.rows = o, o = smc_al(o + (size_t)rcap * pp);
+  L.z = o, o = smc_al(o + (size_t)2 * mcap);
   L.total = o;
   return L;
 }
@@ -109,18 +120,30 @@ struct SmcJob {
   const double *uc, *us;
 };
 
-// One step's parameter updates for this CTA's attribute slice: task = (job, attribute), PHI_G lanes each.
+// Parameter updates for this (parameter) CTA's attribute slice: task = (job, attribute), PHI_G lanes each.
 // The arithmetic of a task is phi_job_body's (smg_kernels.cuh).  Results go to the slice arrays (sigma is the
 // "current sigma" of the job's next update), to the global slot `dst`, and -- for the two sides being scanned --
-// into every CTA's parameter vectors.
-__device__ __forceinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs, int nj, int rank, int j0s, const int* slh,
-                                               const int* attrS, const double* vS, const double* wS, double* sigS,
-                                               double* denS, uint8_t* cenS, uint8_t* cenv, double* isgv, bool publish) {
+// into the member CTAs' parameter vectors.
+__device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs, int nj, int j0s, const int* slh,
+                                            const int* attrS, const double* vS, const double* wS, double* sigS,
+                                            double* denS, uint8_t* cenS, uint8_t* cenv, double* isgv, bool publish) {
   const SmChainArgs& A = G.A;
-  const int sl = G.sl, pp = A.pp, mmax = A.mmax, CS = G.CS;
+  const int sl = G.sl, pp = A.pp, mmax = A.mmax, nM = G.CS / 2;
   const int g = threadIdx.x & (PHI_G - 1), lane = threadIdx.x & 31, gbase = lane & ~(PHI_G - 1);
   const unsigned gmask = ((1u << PHI_G) - 1u) << gbase;
   const int ntask = nj * sl;
+#ifdef SMG_SMC_PROFILE
+  const bool prof_me = threadIdx.x == 0 && (int)cluster_cta_rank() == nM && G.prof;
+  long long td = clock64();
+#define DRAW_TICK(k)                                                   \
+  do {                                                                 \
+    const long long _t = clock64();                                    \
+    if (prof_me) G.prof[k] += (unsigned long long)(_t - td);           \
+    td = _t;                                                           \
+  } while (0)
+#else
+#define DRAW_TICK(k)
+#endif
   for (int task0 = 0; task0 < ntask; task0 += SMC_T / PHI_G) {
     const int task = task0 + (int)(threadIdx.x / PHI_G);
     if (task >= ntask) continue;  // whole groups drop out together
@@ -138,7 +161,7 @@ __device__ __forceinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* j
         cenS[J.role * sl + jl] = 0;
       }
       if (publish && J.role < 2)
-        for (int r = g; r < CS; r += PHI_G) {
+        for (int r = g; r < nM; r += PHI_G) {
           smc_st_u8(smc_map(cenv + J.role * pp + j, r), 0);
           smc_st_f64(smc_map(isgv + J.role * pp + j, r), 0.0);
         }
@@ -147,8 +170,80 @@ __device__ __forceinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* j
     RngKey key = A.key;
     key.sub = J.sub;
     const int m = attrS[jl];
-    int center;
+    int center = 0;
     double s_match = 0.0;
+    double sigma = 0.0, isg = 0.0;
+    DRAW_TICK(50);
+    bool done = false;
+    if (!J.prior && !J.uc && !J.us && !A.phi.sigma_exact && m <= PHI_G) {
+      // ---- lean path of the common case, everything inline (a dependent double-precision chain costs ~8 cycles per
+      //      instruction here, calls spill).  Each step is the FIRST step of the generic algorithm below and is taken
+      //      only when that step alone decides; otherwise the generic code runs from scratch on the same Philox
+      //      streams and reproduces it -- results are identical either way.
+      const double sg = sigS[J.role * sl + jl];
+      const int* h = slh + ((size_t)J.hist * sl + jl) * mmax;
+      const int hv = g < m ? h[g] : -1;
+      const int h1 = __reduce_max_sync(gmask, hv);
+      const unsigned top = __ballot_sync(gmask, hv == h1) & gmask;
+      const int h2 = __reduce_max_sync(gmask, hv == h1 ? -1 : hv);
+      const bool c_ok = __popc(top) == 1 && (double)(h1 - max(h2, 0)) >= SMG_CENTER_DOM * sg && sg > 0.0;  // draw_center_grp's screen
+      if (c_ok) {
+        center = (__ffs(top) - 1 - gbase) + 1;
+        s_match = (double)h1;
+        const double a = wS[jl] + (double)J.nk - s_match + 1.0, b = vS[jl] + s_match - 1.0;  // Beta(w'+1, v'-1)
+        // first attempt of hig_draw_u_grp: lanes 0 / 1 draw Gamma(a) / Gamma(b) by Marsaglia-Tsang with a ziggurat normal
+        double gm = 0.0;
+        int ok = 1;
+        if (g < 2) {
+          const double shape = g == 0 ? a : b;
+          ok = shape >= 1.0;
+          const double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
+          uint32_t o[4];
+          philox4x32_10((uint32_t)J.idx, (uint32_t)j, (g == 1 ? U_SIGMA_B : U_SIGMA) | (key.sub << 8), key.sweep, key.k0, key.k1, o);
+          const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;
+          const int zi = (int)(o[2] & (SMG_ZIG_C - 1));
+          const double un = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);
+          const double x = up * __ldg(&g_zig_x[zi]);
+          ok = ok && fabs(up) < __ldg(&g_zig_r[zi]);
+          double vv = 1.0 + c * x;
+          ok = ok && vv > 0.0;
+          vv = vv * vv * vv;
+          const double x2 = x * x;
+          ok = ok && un < 1.0 - 0.0331 * x2 * x2;
+          gm = d * vv;
+        }
+        const double gb = __shfl_sync(gmask, gm, gbase + 1);
+        const int okb = __shfl_sync(gmask, ok, gbase + 1);
+        double uu = 0.0;
+        if (g == 0) {
+          uu = gm / ((double)(m - 1) * gb);
+          ok = ok && okb && uu > 0.0 && uu < 1.0;
+        }
+        ok = __shfl_sync(gmask, ok, gbase);
+        if (ok) {
+          done = true;
+          if (g == 0) {
+            // sigma = -1/log u as everywhere; 1/sigma and the log-normaliser through u = exp(-1/sigma) itself:
+            // 1/sigma = -log u, log(1 + (m-1)/exp(1/sigma)) = log1p((m-1) u) -- three divisions and an exp shorter.
+            // (Equal to the canonical expressions within an ulp or two; an accepted proposal's slots are re-derived
+            // canonically from sigma before they join the state.)
+            const double Lg = log(uu);
+            sigma = -1.0 / Lg;
+            isg = -Lg;
+            const double dn = log1p((double)(m - 1) * uu);
+            A.cen[o] = (uint8_t)center;
+            A.sig[o] = sigma;
+            A.isg[o] = isg;
+            G.den[o] = dn;
+            sigS[J.role * sl + jl] = sigma;
+            denS[J.role * sl + jl] = dn;
+            cenS[J.role * sl + jl] = (uint8_t)center;
+          }
+        }
+      }
+    }
+    DRAW_TICK(51);
+    if (!done) {
     const double uc = get_u(J.uc, (size_t)j, key, U_CENTER, (uint32_t)J.idx, (uint32_t)j);
     if (J.prior) {
       center = (int)((double)m * uc + 1.0);  // sample(m_j, 1): (int)(m*u + 1)
@@ -171,6 +266,7 @@ __device__ __forceinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* j
     const double vv = vS[jl] + s_match;
     const double ww = wS[jl] + (double)J.nk - s_match;
     double uu = 0.5;
+    DRAW_TICK(52);
     if (J.us || A.phi.sigma_exact) {
       if (g == 0) {
         const double us = get_u(J.us, (size_t)j, key, U_SIGMA, (uint32_t)J.idx, (uint32_t)j);
@@ -179,7 +275,7 @@ __device__ __forceinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* j
     } else {
       uu = hig_draw_u_grp(key, (uint32_t)J.idx, (uint32_t)j, vv, ww, (double)m, g, gmask, gbase);
     }
-    double sigma = 0.0, isg = 0.0;
+    DRAW_TICK(53);
     if (g == 0) {
       sigma = -1.0 / log(uu);
       isg = 1.0 / sigma;
@@ -192,34 +288,39 @@ __device__ __forceinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* j
       denS[J.role * sl + jl] = dn;
       cenS[J.role * sl + jl] = (uint8_t)center;
     }
+    }
+    DRAW_TICK(54);
     if (publish && J.role < 2) {
       isg = __shfl_sync(gmask, isg, gbase);
-      for (int r = g; r < CS; r += PHI_G) {
+      for (int r = g; r < nM; r += PHI_G) {
         smc_st_u8(smc_map(cenv + J.role * pp + j, r), center);
         smc_st_f64(smc_map(isgv + J.role * pp + j, r), isg);
       }
     }
+    DRAW_TICK(55);
   }
 }
 
-// after the draws of a step: this CTA's partial sums of the log-normalisers of the two scanned sides, to every CTA
-__device__ __forceinline__ void smc_publish_sdpart(const SmcArgs& G, int rank, const double* denS, double* sdpart) {
-  const int sl = G.sl, CS = G.CS;
+// after the draws of a step: this parameter CTA's partial sums of the log-normalisers of the two scanned sides, to
+// every member CTA (k = index of this CTA among the parameter CTAs)
+__device__ __forceinline__ void smc_publish_sdpart(const SmcArgs& G, int k, const double* denS, double* sdpart) {
+  const int sl = G.sl, nM = G.CS / 2;
   const int t = threadIdx.x;
-  if (t < 2 * CS) {
-    const int role = t / CS, r = t % CS;
+  if (t < 2 * nM) {
+    const int role = t / nM, r = t % nM;
     double acc = 0.0;
     for (int jl = 0; jl < sl; jl++) acc += denS[role * sl + jl];
-    smc_st_f64(smc_map(sdpart + role * SMC_MAXCS + rank, r), acc);
+    smc_st_f64(smc_map(sdpart + role * SMC_MAXCS + k, r), acc);
   }
 }
 
 #ifdef SMG_SMC_PROFILE
-#define SMC_TICK(k)                                                              \
-  do {                                                                           \
-    const long long _t = clock64();                                              \
-    if (rank == 0 && threadIdx.x == 0 && G.prof) G.prof[k] += (unsigned long long)(_t - tk); \
-    tk = _t;                                                                     \
+// member-side phases are timed by thread 0 of CTA 0, parameter-side phases by thread 0 of the first parameter CTA
+#define SMC_TICK(k)                                                                          \
+  do {                                                                                       \
+    const long long _t = clock64();                                                          \
+    if (threadIdx.x == 0 && (rank == 0 || rank == nM) && G.prof) G.prof[(k) + (rank ? 32 : 0)] += (unsigned long long)(_t - tk); \
+    tk = _t;                                                                                 \
   } while (0)
 #else
 #define SMC_TICK(k)
@@ -229,43 +330,46 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   const SmChainArgs& A = G.A;
   extern __shared__ __align__(16) unsigned char smc_raw[];
   const int n = A.n, p = A.p, pp = A.pp, mmax = A.mmax, NSB = A.NS;
-  const int CS = G.CS, sl = G.sl, mcap = G.mcap, rcap = G.rcap;
-  const SmcLayout L = smc_layout(pp, mmax, CS, mcap, rcap);
+  const int CS = G.CS, nM = CS / 2, nP = CS / 2, sl = G.sl, TL = G.TL, mcap = G.mcap, rcap = G.rcap;
+  const SmcLayout L = smc_layout(pp, mmax, TL, CS, mcap, rcap);
+  const int RSTR = L.rstr;
+  double* T = reinterpret_cast<double*>(smc_raw + L.T);         // [pp][TL] look-up table of the scan in progress
+  float* Tp = reinterpret_cast<float*>(smc_raw + L.Tp);         // [pp/2][64] single-precision table of attribute pairs (screen)
   double* isgv = reinterpret_cast<double*>(smc_raw + L.isgv);   // [3][pp] 1/sigma of the vectors being evaluated
+  double* sdpart = reinterpret_cast<double*>(smc_raw + L.sdpart);  // [3][16] partial log-normaliser sums by parameter CTA
   double* sigS = reinterpret_cast<double*>(smc_raw + L.sigS);   // [3][sl] current sigma of the three update chains
   double* denS = reinterpret_cast<double*>(smc_raw + L.denS);   // [3][sl]
   double* vS = reinterpret_cast<double*>(smc_raw + L.vS);
   double* wS = reinterpret_cast<double*>(smc_raw + L.wS);
-  double* sdpart = reinterpret_cast<double*>(smc_raw + L.sdpart);  // [3][16] per-CTA partial log-normaliser sums
-  double* lg = reinterpret_cast<double*>(smc_raw + L.lg);       // [mcap] logit(u) of the members, current scan
+  double* lg = reinterpret_cast<double*>(smc_raw + L.lg);       // [rcap] logit(u) of the cached members, current scan
   int* phs = reinterpret_cast<int*>(smc_raw + L.phs);           // [2][pp][mmax] own members by current-state side
   int* phl = reinterpret_cast<int*>(smc_raw + L.phl);           // [2][pp][mmax] own members by launch / proposal side
   int* slh = reinterpret_cast<int*>(smc_raw + L.slh);           // [SH_N][sl][mmax] histograms of this CTA's attributes
   int* attrS = reinterpret_cast<int*>(smc_raw + L.attrS);
-  int* xchg = reinterpret_cast<int*>(smc_raw + L.xchg);         // [2][16][4] per-CTA counters of a step, from every CTA
+  int* xchg = reinterpret_cast<int*>(smc_raw + L.xchg);         // [2][16][4] per-CTA counters of a step, from the member CTAs
   int* sel = reinterpret_cast<int*>(smc_raw + L.sel);           // [16] members found by each CTA
-  int* srow = reinterpret_cast<int*>(smc_raw + L.srow);         // [mcap] row of each own member
+  uint32_t* rowsT = reinterpret_cast<uint32_t*>(smc_raw + L.rowsT);  // [pp/4][RSTR] rows of the cached members, word-major
   uint8_t* cenv = smc_raw + L.cenv;                             // [3][pp]
   uint8_t* cenS = smc_raw + L.cenS;                             // [3][sl]
   uint8_t* zc = smc_raw + L.z;                                  // [mcap] side (launch, then proposal)
   uint8_t* zn = zc + mcap;                                      // [mcap] side decided by the scan in progress
-  uint8_t* zs = zn + mcap;                                      // [mcap] side under the current state
-  uint8_t* zl = zs + mcap;                                      // [mcap] launch side (kept for the proposal density)
-  uint8_t* rows = smc_raw + L.rows;                             // [rcap][pp]
   __shared__ double sh[256];
   __shared__ int s_sel[8];
   __shared__ int s_wa[SMC_WARPS], s_wb[SMC_WARPS], s_tot[4];
   __shared__ double s_sd[4];
 
   const int rank = (int)cluster_cta_rank();
+  const bool isM = rank < nM;
+  const int kP = rank - nM;  // index among the parameter CTAs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j0s = rank * sl;
+  const int j0s = isM ? 0 : kP * sl;
   const size_t len = (size_t)pp * mmax;
-  const int chunks = pp / 16;
+  const int words = pp / 4;
   auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
 #ifdef SMG_SMC_PROFILE
   long long tk = clock64();
 #endif
+  smc_arrive();  // (0) every CTA of the cluster is running: its shared memory may be written remotely after the wait
 
   // ---- pair (split_merge.cpp:275) and this CTA's share of the row scan that builds S (:280-301)
   if (tid == 0) {
@@ -278,11 +382,12 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     s_sel[2] = A.c[i1];
     s_sel[3] = A.c[i2];
   }
-  for (int jl = tid; jl < sl; jl += SMC_T) {
-    attrS[jl] = A.phi.attr[j0s + jl];
-    vS[jl] = A.phi.v[j0s + jl];
-    wS[jl] = A.phi.w[j0s + jl];
-  }
+  if (!isM)
+    for (int jl = tid; jl < sl; jl += SMC_T) {
+      attrS[jl] = A.phi.attr[j0s + jl];
+      vS[jl] = A.phi.v[j0s + jl];
+      wS[jl] = A.phi.w[j0s + jl];
+    }
   if (rank == 0)
     for (int q = tid; q < 24; q += SMC_T) A.terms[q] = 0.0;
   __syncthreads();
@@ -301,6 +406,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     if (lane == 0) s_wa[warp] = cntm;
   }
   __syncthreads();
+  smc_wait();  // (0)
   if (warp == 0) {
     const int v = lane < SMC_WARPS ? s_wa[lane] : 0;
     int x = v;
@@ -313,8 +419,8 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     const int tot = __shfl_sync(SMG_FULL, x, 31);
     if (lane < CS) smc_st_s32(smc_map(sel + rank, lane), tot);
   }
-  // prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380)
-  {
+  // prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380), on the parameter CTAs
+  if (!isM) {
     SmcJob jb[3];
     for (int k = 0; k < 3; k++) {
       jb[k].role = k;
@@ -327,12 +433,13 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       jb[k].uc = off(A.u_prior_c, (size_t)k * p);
       jb[k].us = off(A.u_prior_s, (size_t)k * p);
     }
-    smc_draw_slice(G, jb, 3, rank, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
+    smc_draw_slice(G, jb, 3, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
     __syncthreads();
-    smc_publish_sdpart(G, rank, denS, sdpart);
+    smc_publish_sdpart(G, kP, denS, sdpart);
   }
-  smc_sync();  // (a) member counts, launch parameters
   SMC_TICK(0);
+  smc_sync();  // (a) member counts, launch parameters
+  SMC_TICK(1);
   int nS = 0, before = 0;
   for (int r = 0; r < CS; r++) {
     const int v = sel[r];
@@ -355,68 +462,77 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     }
   }
   if (rank == 0 && tid == 0) sm_fill_info_plan(A.info, A.plan, NSB, i1, i2, nS, cA, cB, *A.Kptr);
+  SMC_TICK(2);
   smc_sync();  // (b) S complete
-  // ---- own members: positions [pos0, pos0 + mine); the anchors are the positions nS (side 0) and nS + 1 (side 1)
-  const int per = (nS + 2 + CS - 1) / CS;
-  const int pos0 = rank * per;
-  const int mine = max(0, min(per, nS + 2 - pos0));
+  SMC_TICK(3);
+  // ---- member CTAs: positions [pos0, pos0 + mine); the anchors are the positions nS (side 0) and nS + 1 (side 1)
+  const int per = (nS + 2 + nM - 1) / nM;
+  const int pos0 = isM ? rank * per : 0;
+  const int mine = isM ? max(0, min(per, nS + 2 - pos0)) : 0;
   const int ndec = max(0, min(mine, nS - pos0));  // own members that are re-allocated (not anchors)
-  {
+  // row of position `pos`
+  auto row_of = [&](int pos) -> int { return pos < nS ? A.S[pos] : (pos == nS ? i1 : i2); };
+  // word w of own member m
+  auto xword = [&](int m, int w) -> uint32_t {
+    return m < rcap ? rowsT[(size_t)w * RSTR + m]
+                    : *reinterpret_cast<const uint32_t*>(A.X + (size_t)row_of(pos0 + m) * pp + 4 * w);
+  };
+  // moves member m (whole warp): -1 in histogram (ho, go), +1 in (hn, gn); ho == nullptr: only the addition
+  auto hist_move = [&](int m, int* ho, int go, int* hn, int gn) {
+    for (int w = lane; w < words; w += 32) {
+      const uint32_t xw = xword(m, w);
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int x = (xw >> (8 * b)) & 0xff;
+        if (x) {
+          const size_t e = (size_t)(4 * w + b) * mmax + (x - 1);
+          if (ho) atomicSub(&ho[(size_t)go * len + e], 1);
+          atomicAdd(&hn[(size_t)gn * len + e], 1);
+        }
+      }
+    }
+  };
+  int nBcur = 0;   // side-1 members of the launch / proposal allocation, anchor i_2 included
+  int cntS1 = 0;
+  if (isM) {
     RngKey k = A.key;
     k.sub = SUB_SM_LAUNCH;
     for (int m = tid; m < mine; m += SMC_T) {
       const int pos = pos0 + m;
-      int row, zstate, zlaunch;
+      int zlaunch;
       if (pos < nS) {
-        row = A.S[pos];
-        zstate = A.zState[pos];
         const double u = get_u(A.u_launch, pos, k, U_SM_LAUNCH, (uint32_t)pos, 0u);  // split_merge.cpp:346
         const int z = (int)(2.0 * u);
         zlaunch = z > 1 ? 1 : z;
       } else {
-        row = pos == nS ? i1 : i2;
-        zstate = zlaunch = pos - nS;
+        zlaunch = pos - nS;
       }
-      srow[m] = row;
-      zs[m] = (uint8_t)zstate;
       zc[m] = (uint8_t)zlaunch;
       zn[m] = (uint8_t)zlaunch;
     }
-  }
-  for (int q = tid; q < 2 * (int)len; q += SMC_T) phs[q] = phl[q] = 0;
-  __syncthreads();
-  {  // rows into shared memory (as many as fit), and both side histograms of the own members
-    const int ncache = min(mine, rcap);
-    for (int t = tid; t < ncache * chunks; t += SMC_T) {
-      const int m = t / chunks, q = t % chunks;
-      *reinterpret_cast<uint4*>(rows + (size_t)m * pp + q * 16) =
-          *reinterpret_cast<const uint4*>(A.X + (size_t)srow[m] * pp + q * 16);
+    for (int q = tid; q < 2 * (int)len; q += SMC_T) phs[q] = phl[q] = 0;
+    {  // rows of the cached members into shared memory, word-major
+      const int ncache = min(mine, rcap), chunks = pp / 16;
+      for (int t = tid; t < ncache * chunks; t += SMC_T) {
+        const int m = t / chunks, q = t % chunks;
+        const uint4 v = *reinterpret_cast<const uint4*>(A.X + (size_t)row_of(pos0 + m) * pp + q * 16);
+        rowsT[(size_t)(4 * q + 0) * RSTR + m] = v.x;
+        rowsT[(size_t)(4 * q + 1) * RSTR + m] = v.y;
+        rowsT[(size_t)(4 * q + 2) * RSTR + m] = v.z;
+        rowsT[(size_t)(4 * q + 3) * RSTR + m] = v.w;
+      }
     }
     __syncthreads();
+    // both side histograms of the own members (current-state sides: fixed; launch sides: maintained by the scans)
     int c1s = 0, c1l = 0;
-    for (int t = tid; t < mine * chunks; t += SMC_T) {
-      const int m = t / chunks, q = t % chunks;
-      const uint8_t* xr = m < rcap ? rows + (size_t)m * pp : A.X + (size_t)srow[m] * pp;
-      const uint4 v = *reinterpret_cast<const uint4*>(xr + q * 16);
-      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-      const int gs = zs[m], gl = zc[m];
-      if (q == 0) {
-        c1s += gs;
-        c1l += gl;
-      }
-      int* Hs = phs + (size_t)gs * len + (size_t)q * 16 * mmax;
-      int* Hl = phl + (size_t)gl * len + (size_t)q * 16 * mmax;
-#pragma unroll
-      for (int b = 0; b < 16; b++) {
-        const int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
-        if (x) {
-          atomicAdd(&Hs[b * mmax + (x - 1)], 1);
-          atomicAdd(&Hl[b * mmax + (x - 1)], 1);
-        }
-      }
+    for (int m = warp; m < mine; m += SMC_WARPS) {
+      const int pos = pos0 + m;
+      const int gs = pos < nS ? A.zState[pos] : pos - nS, gl = zc[m];
+      c1s += gs;
+      c1l += gl;
+      hist_move(m, nullptr, 0, phs, gs);
+      hist_move(m, nullptr, 0, phl, gl);
     }
-    c1s = warp_sum_i(c1s);
-    c1l = warp_sum_i(c1l);
     if (lane == 0) {
       s_wa[warp] = c1s;
       s_wb[warp] = c1l;
@@ -430,39 +546,105 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       }
     }
   }
-  smc_sync();  // (c) side histograms and side counts of every CTA
-  SMC_TICK(1);
-  int nBcur = 0;  // side-1 members of the launch / proposal allocation, anchor i_2 included
-  int cntS1 = 0;
-  for (int r = 0; r < CS; r++) {
+  SMC_TICK(4);
+  smc_sync();  // (c) side histograms and side counts of the member CTAs
+  SMC_TICK(5);
+  for (int r = 0; r < nM; r++) {
     cntS1 += xchg[(0 * SMC_MAXCS + r) * 4 + 0];
     nBcur += xchg[(0 * SMC_MAXCS + r) * 4 + 1];
   }
-  // slice histograms: sum of the other CTAs' partial histograms over this CTA's attributes (DSMEM reads)
+  // slice histograms: sum of the member CTAs' partial histograms over this parameter CTA's attributes (DSMEM reads)
   auto reduce_slices = [&](const int* ph, int h0, bool to_global) {
     const int per_side = sl * mmax;
     for (int t = tid; t < 2 * per_side; t += SMC_T) {
       const int s = t / per_side, e = t % per_side;
       const int* src = ph + (size_t)s * len + (size_t)j0s * mmax + e;
+      int v[SMC_MAXCS / 2];  // all remote loads in flight together
+#pragma unroll
+      for (int r = 0; r < SMC_MAXCS / 2; r++) v[r] = r < nM ? smc_ld_s32(smc_map(src, r)) : 0;
       int acc = 0;
-      for (int r = 0; r < CS; r++) acc += smc_ld_s32(smc_map(src, r));
+#pragma unroll
+      for (int r = 0; r < SMC_MAXCS / 2; r++) acc += v[r];
       slh[(size_t)(h0 + s) * per_side + e] = acc;
       if (to_global) A.H[(size_t)(h0 + s) * len + (size_t)j0s * mmax + e] = acc;
     }
   };
-  reduce_slices(phs, SH_S0, true);
-  __syncthreads();
-  for (int e = tid; e < sl * mmax; e += SMC_T) {
-    const int v = slh[(size_t)SH_S0 * sl * mmax + e] + slh[(size_t)SH_S1 * sl * mmax + e];
-    slh[(size_t)SH_M * sl * mmax + e] = v;
-    A.H[(size_t)SH_M * len + (size_t)j0s * mmax + e] = v;
+  if (!isM) {
+    reduce_slices(phs, SH_S0, true);
+    __syncthreads();
+    for (int e = tid; e < sl * mmax; e += SMC_T) {
+      const int v = slh[(size_t)SH_S0 * sl * mmax + e] + slh[(size_t)SH_S1 * sl * mmax + e];
+      slh[(size_t)SH_M * sl * mmax + e] = v;
+      A.H[(size_t)SH_M * len + (size_t)j0s * mmax + e] = v;
+    }
+    __syncthreads();
   }
   if (rank == 0 && tid == 0) {
     A.cnt[SH_S0] = nS + 2 - cntS1;
     A.cnt[SH_S1] = cntS1;
     A.cnt[SH_M] = nS + 2;
   }
-  __syncthreads();
+  // member CTAs: logit(u) of the own members for scan q (it does not depend on the state)
+  auto fill_logits = [&](int q) {
+    RngKey k = A.key;
+    k.sub = SUB_SM_RG + q;
+    const double* ui = off(A.u_rg, (size_t)q * n);
+    for (int m = tid; m < ndec; m += SMC_T) {
+      const double v = sm_logit_u(ui, pos0 + m, k);
+      if (m < rcap)
+        lg[m] = v;
+      else
+        A.lgt[pos0 + m] = v;
+    }
+  };
+  // member CTAs: look-up table of the two sides' parameters (cenv / isgv rows 0, 1) and their constant term
+  double sdBA = 0.0;  // sden_B - sden_A
+  float pairE = 0.f;  // bound of |single-precision pair sum - exact sum| for any member (see the screen in P1)
+  __shared__ float s_pmax[SMC_WARPS];
+  int* s_pairmax = reinterpret_cast<int*>(smc_raw + L.pmax);  // [pp/2] largest |entry| of each pair (float bits)
+  auto build_table = [&]() {
+    const double a = lane < nP ? sdpart[0 * SMC_MAXCS + lane] : 0.0, b = lane < nP ? sdpart[1 * SMC_MAXCS + lane] : 0.0;
+    sdBA = warp_sum(b) - warp_sum(a);
+    for (int e = tid; e < pp * TL; e += SMC_T) {
+      const int j = e / TL, av = e % TL;
+      double v = 0.0;
+      if (av != 0) {
+        if (av != cenv[pp + j]) v += isgv[pp + j];
+        if (av != cenv[j]) v -= isgv[j];
+      }
+      T[e] = v;
+    }
+    if (TL == 8) {
+      // single-precision pair table: Tp[q][a1 + 8 a2] = float(T[2q][a1] + T[2q+1][a2]); S = sum over the pairs of the
+      // largest |entry| bounds sum_i |t_i| of any member, so |fp32 sum - exact| <= (pairs + 2) 2^-24 S (rounding of the
+      // entries + of the 4-way accumulation)
+      __syncthreads();
+      for (int q2 = tid; q2 < pp / 2; q2 += SMC_T) s_pairmax[q2] = 0;
+      __syncthreads();
+      for (int e2 = tid; e2 < (pp / 2) * 64; e2 += SMC_T) {
+        const int q2 = e2 >> 6, e = e2 & 63;
+        const float v = (float)(T[(2 * q2) * 8 + (e & 7)] + T[(2 * q2 + 1) * 8 + (e >> 3)]);
+        Tp[e2] = v;
+        atomicMax(&s_pairmax[q2], __float_as_int(fabsf(v)));  // non-negative floats order like their bit patterns
+      }
+      __syncthreads();
+      float mymax = 0.f;
+      for (int q2 = tid; q2 < pp / 2; q2 += SMC_T) mymax += __int_as_float(s_pairmax[q2]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mymax += __shfl_xor_sync(SMG_FULL, mymax, o);
+      if (lane == 0) s_pmax[warp] = mymax;
+      __syncthreads();
+      float S = 0.f;
+      for (int w2 = 0; w2 < SMC_WARPS; w2++) S += s_pmax[w2];
+      pairE = ((float)(pp / 2) + 4.f) * 5.97e-8f * (S + fabsf((float)sdBA)) * 1.01f + 1e-6f;
+    }
+  };
+  if (isM) {
+    if (A.t > 0) fill_logits(0);
+    build_table();
+    __syncthreads();
+  }
+  SMC_TICK(6);
 
   // ------------------------------------------------------------------------------------------
   // launch scans (+ merge-launch updates), then the proposal
@@ -476,18 +658,18 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       // launch state complete: keep its sides and counts, start the proposal from a copy of it (split_merge.cpp:575-577)
       cntL1 = nBcur;
       cntL0 = nS + 2 - nBcur;
-      for (int m = tid; m < mine; m += SMC_T) {
-        zl[m] = zc[m];
-        if (pos0 + m < nS) A.zL[pos0 + m] = zc[m];
-      }
-      for (int t = tid; t < 2 * sl; t += SMC_T) {
-        const int role = t / sl, jl = t % sl, j = j0s + jl;
-        const size_t d = (size_t)(NSB + (role ? SM_ST_B : SM_ST_A)) * pp + j;
-        const double sg = sigS[role * sl + jl];
-        A.cen[d] = cenS[role * sl + jl];
-        A.sig[d] = sg;
-        A.isg[d] = (j < p) ? 1.0 / sg : 0.0;
-        G.den[d] = denS[role * sl + jl];
+      if (isM) {
+        for (int m = tid; m < ndec; m += SMC_T) A.zL[pos0 + m] = zc[m];
+      } else {
+        for (int t = tid; t < 2 * sl; t += SMC_T) {
+          const int role = t / sl, jl = t % sl, j = j0s + jl;
+          const size_t d = (size_t)(NSB + (role ? SM_ST_B : SM_ST_A)) * pp + j;
+          const double sg = sigS[role * sl + jl];
+          A.cen[d] = cenS[role * sl + jl];
+          A.sig[d] = sg;
+          A.isg[d] = (j < p) ? 1.0 / sg : 0.0;
+          G.den[d] = denS[role * sl + jl];
+        }
       }
       if (rank == 0 && tid == 0) {
         A.cnt[SH_L0] = cntL0;
@@ -496,76 +678,104 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     }
     const int q = prop ? A.t : it;
     const bool do_scan = prop ? (same != 0) : (it < A.t);
-    if (do_scan) {
-      // ---- P1: allocation logits, likelihood differences, count-free decisions
-      {
-        RngKey k = A.key;
-        k.sub = SUB_SM_RG + q;
-        const double* ui = off(A.u_rg, (size_t)q * n);
-        for (int m = tid; m < ndec; m += SMC_T) lg[m] = sm_logit_u(ui, pos0 + m, k);
-      }
-      double sdA, sdB;
-      {
-        const double a = lane < CS ? sdpart[0 * SMC_MAXCS + lane] : 0.0, b = lane < CS ? sdpart[1 * SMC_MAXCS + lane] : 0.0;
-        sdA = warp_sum(a);
-        sdB = warp_sum(b);
-      }
-      __syncthreads();
+    const bool do_mg = prop || it < A.r;
+    // the update of the merged cluster that belongs to this step (parameter CTAs): the r updates of the merge launch
+    // state (split_merge.cpp:386-387) are an independent chain on the fixed merged histogram and run while the member
+    // CTAs evaluate the scan; the final one of the proposal (:584) keeps job index 2 as in the other paths
+    auto mg_job = [&]() {
+      SmcJob J;
+      J.role = 2;
+      J.hist = SH_M;
+      J.nk = nS + 2;
+      J.dst = NSB + (prop ? SM_ST_M : SM_ML_M);
+      J.idx = prop ? 2 : (do_scan ? 2 : 0);
+      J.prior = 0;
+      J.sub = SUB_SM_MERGE + (prop ? A.r : it);
+      J.uc = off(A.u_mg_c, (size_t)(prop ? A.r : it) * p);
+      J.us = off(A.u_mg_s, (size_t)(prop ? A.r : it) * p);
+      smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false);
+    };
+    if (!do_scan) {
+      if (!isM && do_mg) mg_job();
+      continue;
+    }
+    int dsum = 0, nnr_tot = 0, nnr_mine = 0, extra = 0;
+    if (isM) {
+      // ---- P1: likelihood differences by table look-up (one thread per member), count-free decisions
       const double dc_max = nS > 0 ? sm_dc_bound(nS, 1) + SM_DC_MARGIN : 0.0;
       const double dc_min = nS > 0 ? sm_dc_bound(nS, nS) - SM_DC_MARGIN : 0.0;
-      for (int m0 = warp; m0 < ndec; m0 += 2 * SMC_WARPS) {
-        const int m1 = m0 + SMC_WARPS;
-        const bool has1 = m1 < ndec;
-        const uint8_t* x0 = m0 < rcap ? rows + (size_t)m0 * pp : A.X + (size_t)srow[m0] * pp;
-        const uint8_t* x1 = has1 ? (m1 < rcap ? rows + (size_t)m1 * pp : A.X + (size_t)srow[m1] * pp) : x0;
-        double a0 = 0.0, b0 = 0.0, a1 = 0.0, b1 = 0.0;
-        for (int j0 = lane * 8; j0 < pp; j0 += 256) {
-          const uint2 ca = *reinterpret_cast<const uint2*>(cenv + j0), cb = *reinterpret_cast<const uint2*>(cenv + pp + j0);
-          const uint2 xv0 = *reinterpret_cast<const uint2*>(x0 + j0), xv1 = *reinterpret_cast<const uint2*>(x1 + j0);
-          double wa[8], wb[8];
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            const double2 ta = reinterpret_cast<const double2*>(isgv + j0)[b], tb = reinterpret_cast<const double2*>(isgv + pp + j0)[b];
-            wa[2 * b] = ta.x, wa[2 * b + 1] = ta.y;
-            wb[2 * b] = tb.x, wb[2 * b + 1] = tb.y;
+      const unsigned Tb = (unsigned)__cvta_generic_to_shared(T);
+      const int tsh = 31 - __clz(TL) + 3;  // log2(TL * 8): byte stride of an attribute's table row
+      const unsigned Tpb = (unsigned)__cvta_generic_to_shared(Tp);
+      const float sdf = (float)sdBA;
+      for (int m = tid; m < ndec; m += SMC_T) {
+        const double lgm = m < rcap ? lg[m] : A.lgt[pos0 + m];
+        if (TL == 8 && m < rcap) {
+          // ---- single-precision screen: LL_A - LL_B within +-pairE; decided here when the whole interval, under every
+          //      possible count, falls inside one decision region (the exact value lies in it too)
+          const uint32_t* xr = rowsT + m;
+          float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+#pragma unroll 4
+          for (int w = 0; w < words; w += 2) {
+            const uint32_t xa = xr[(size_t)w * RSTR], xb = xr[(size_t)(w + 1) * RSTR];
+            const unsigned i0 = (xa & 7u) | ((xa >> 5) & 0x38u), i1 = ((xa >> 16) & 7u) | ((xa >> 21) & 0x38u);
+            const unsigned i2 = (xb & 7u) | ((xb >> 5) & 0x38u), i3 = ((xb >> 16) & 7u) | ((xb >> 21) & 0x38u);
+            float v0, v1, v2, v3;
+            asm("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(Tpb + ((unsigned)(2 * w) << 8) + (i0 << 2)));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(Tpb + ((unsigned)(2 * w + 1) << 8) + (i1 << 2)));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(Tpb + ((unsigned)(2 * w + 2) << 8) + (i2 << 2)));
+            asm("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(Tpb + ((unsigned)(2 * w + 3) << 8) + (i3 << 2)));
+            f0 += v0;
+            f1 += v1;
+            f2 += v2;
+            f3 += v3;
           }
-          const uint32_t ma0 = __vcmpne4(xv0.x, ca.x), ma1 = __vcmpne4(xv0.y, ca.y);
-          const uint32_t mb0 = __vcmpne4(xv0.x, cb.x), mb1 = __vcmpne4(xv0.y, cb.y);
-          const uint32_t na0 = __vcmpne4(xv1.x, ca.x), na1 = __vcmpne4(xv1.y, ca.y);
-          const uint32_t nb0 = __vcmpne4(xv1.x, cb.x), nb1 = __vcmpne4(xv1.y, cb.y);
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (ma0 & (0xffu << (8 * b))) a0 += wa[b];
-            if (mb0 & (0xffu << (8 * b))) b0 += wb[b];
-            if (na0 & (0xffu << (8 * b))) a1 += wa[b];
-            if (nb0 & (0xffu << (8 * b))) b1 += wb[b];
-          }
-#pragma unroll
-          for (int b = 0; b < 4; b++) {
-            if (ma1 & (0xffu << (8 * b))) a0 += wa[4 + b];
-            if (mb1 & (0xffu << (8 * b))) b0 += wb[4 + b];
-            if (na1 & (0xffu << (8 * b))) a1 += wa[4 + b];
-            if (nb1 & (0xffu << (8 * b))) b1 += wb[4 + b];
-          }
-        }
-        a0 = warp_sum(a0);
-        b0 = warp_sum(b0);
-        a1 = warp_sum(a1);
-        b1 = warp_sum(b1);
-        if (lane < 2 && (lane == 0 || has1)) {
-          const int m = lane ? m1 : m0;
-          const double d0 = lane ? ((-a1 - sdA) - (-b1 - sdB)) : ((-a0 - sdA) - (-b0 - sdB));
-          const double lgm = lg[m];
-          const int rlo = sm_d_region(dc_min + d0, lgm), rhi = sm_d_region(dc_max + d0, lgm);
+          const float d32 = ((f0 + f1) + (f2 + f3)) + sdf;
+          const int rlo = sm_d_region(dc_min + (double)(d32 - pairE), lgm), rhi = sm_d_region(dc_max + (double)(d32 + pairE), lgm);
           if (rlo == rhi) {
             zn[m] = (uint8_t)(~rlo & 1);
-          } else {
-            zn[m] = 2;
-            A.dl[pos0 + m] = d0;
+            continue;
           }
+#ifdef SMG_SMC_PROFILE
+          if (rank == 0 && G.prof) atomicAdd(&G.prof[56], 1ull);
+#endif
+        }
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (m < rcap) {
+          const uint32_t* xr = rowsT + m;
+#pragma unroll 4
+          for (int w = 0; w < words; w++) {
+            const uint32_t xw = xr[(size_t)w * RSTR];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              const unsigned addr = Tb + ((unsigned)(4 * w + b) << tsh) + (((xw >> (8 * b)) & 0xffu) << 3);
+              double v;
+              asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+              acc[b] += v;
+            }
+          }
+        } else {
+          const uint32_t* xr = reinterpret_cast<const uint32_t*>(A.X + (size_t)A.S[pos0 + m] * pp);
+          for (int w = 0; w < words; w++) {
+            const uint32_t xw = xr[w];
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[b] += T[(size_t)(4 * w + b) * TL + ((xw >> (8 * b)) & 0xffu)];
+          }
+        }
+        const double d0 = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + sdBA;  // LL_A - LL_B
+        const int rlo = sm_d_region(dc_min + d0, lgm), rhi = sm_d_region(dc_max + d0, lgm);
+        if (rlo == rhi) {
+          zn[m] = (uint8_t)(~rlo & 1);
+        } else {
+          zn[m] = 2;
+          A.dl[pos0 + m] = d0;
         }
       }
       __syncthreads();
+#ifdef SMG_SMC_PROFILE
+      if (rank == 0 && tid == 0 && G.prof) G.prof[57] += (unsigned long long)(pairE * 1e6f);
+#endif
+      SMC_TICK(7);
       // ordered pass over the own members: side-1 change of the decided ones, list of the undecided ones (by position)
       int carry_d = 0, carry_n = 0;
       for (int base = 0; base < ndec; base += SMC_T) {
@@ -616,7 +826,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
           G.nr_pre[Lx] = carry_d + s_wa[warp] + xd - delta;
           G.nr_z[Lx] = zcm;
           G.nr_d0[Lx] = A.dl[pos0 + m];
-          G.nr_lg[Lx] = lg[m];
+          G.nr_lg[Lx] = m < rcap ? lg[m] : A.lgt[pos0 + m];
         }
         carry_d += s_tot[0];
         carry_n += s_tot[1];
@@ -626,167 +836,161 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
         smc_st_s32(smc_map(xchg + (par * SMC_MAXCS + rank) * 4 + 0, tid), carry_d);
         smc_st_s32(smc_map(xchg + (par * SMC_MAXCS + rank) * 4 + 1, tid), carry_n);
       }
-      SMC_TICK(2);
+      SMC_TICK(8);
       smc_sync();  // (1) decisions that do not depend on the counts
-      SMC_TICK(3);
-      int dsum = 0, nnr_tot = 0, nnr_mine = 0;
-      for (int r = 0; r < CS; r++) {
-        dsum += xchg[(par * SMC_MAXCS + r) * 4 + 0];
-        const int v = xchg[(par * SMC_MAXCS + r) * 4 + 1];
-        nnr_tot += v;
-        if (r == rank) nnr_mine = v;
-      }
-      int extra = 0;
-      if (nnr_tot > 0) {
-        // ---- the members whose decision depends on the running counts: ordered walk on CTA 0 (split_merge.cpp:186-216
-        //      one at a time; here 32 at a time with the count term bounded inside the batch, see sm_rdecide_body)
-        if (rank == 0 && warp == 0) {
-          int regionbase = nBcur;
-          for (int r = 0; r < CS; r++) {
-            const int nnr = xchg[(par * SMC_MAXCS + r) * 4 + 1];
-            const int lbase = r * per;
-            for (int b0 = 0; b0 < nnr; b0 += 32) {
-              const int qq = b0 + lane;
-              const bool v = qq < nnr;
-              const double md0 = v ? G.nr_d0[lbase + qq] : 0.0, mlg = v ? G.nr_lg[lbase + qq] : 0.0;
-              const int mpre = v ? G.nr_pre[lbase + qq] : 0;
-              int mz = v ? G.nr_z[lbase + qq] : 0;
-              int start = 0;
-              while (start < 32 && b0 + start < nnr) {
-                const bool act = v && lane >= start;
-                const int nBq = regionbase + mpre + extra, b = nBq - mz, dev = lane - start;
-                const int blo = max(1, b - dev), bhi = min(nS, b + dev);
-                const int rlo = sm_d_region(sm_dc_bound(nS, bhi) - SM_DC_MARGIN + md0, mlg),
-                          rhi = sm_d_region(sm_dc_bound(nS, blo) + SM_DC_MARGIN + md0, mlg);
-                const unsigned fr = __ballot_sync(SMG_FULL, act && rlo != rhi);
-                const int f = fr ? __ffs(fr) - 1 : 32;
-                int d = 0;
-                if (act && lane < f) {
-                  const int nz = ~rlo & 1;
-                  d = nz - mz;
+      SMC_TICK(9);
+    } else {
+      smc_arrive();  // (1)
+      if (do_mg) mg_job();
+      SMC_TICK(7);
+      smc_wait();  // (1)
+      SMC_TICK(9);
+    }
+    for (int r = 0; r < nM; r++) {
+      dsum += xchg[(par * SMC_MAXCS + r) * 4 + 0];
+      const int v = xchg[(par * SMC_MAXCS + r) * 4 + 1];
+      nnr_tot += v;
+      if (r == rank) nnr_mine = v;
+    }
+    if (nnr_tot > 0) {
+      // ---- the members whose decision depends on the running counts: ordered walk on CTA 0 (split_merge.cpp:186-216
+      //      one at a time; here 32 at a time with the count term bounded inside the batch, see sm_rdecide_body)
+      if (rank == 0 && warp == 0) {
+        int regionbase = nBcur;
+        for (int r = 0; r < nM; r++) {
+          const int nnr = xchg[(par * SMC_MAXCS + r) * 4 + 1];
+          const int lbase = r * per;
+          for (int b0 = 0; b0 < nnr; b0 += 32) {
+            const int qq = b0 + lane;
+            const bool v = qq < nnr;
+            const double md0 = v ? __ldcg(&G.nr_d0[lbase + qq]) : 0.0, mlg = v ? __ldcg(&G.nr_lg[lbase + qq]) : 0.0;
+            const int mpre = v ? __ldcg(&G.nr_pre[lbase + qq]) : 0;
+            int mz = v ? __ldcg(&G.nr_z[lbase + qq]) : 0;
+            int start = 0;
+            while (start < 32 && b0 + start < nnr) {
+              const bool act = v && lane >= start;
+              const int nBq = regionbase + mpre + extra, b = nBq - mz, dev = lane - start;
+              const int blo = max(1, b - dev), bhi = min(nS, b + dev);
+              const int rlo = sm_d_region(sm_dc_bound(nS, bhi) - SM_DC_MARGIN + md0, mlg),
+                        rhi = sm_d_region(sm_dc_bound(nS, blo) + SM_DC_MARGIN + md0, mlg);
+              const unsigned fr = __ballot_sync(SMG_FULL, act && rlo != rhi);
+              const int f = fr ? __ffs(fr) - 1 : 32;
+              int d = 0;
+              if (act && lane < f) {
+                const int nz = ~rlo & 1;
+                d = nz - mz;
+                mz = nz;
+              }
+              extra += warp_sum_i(d);
+              if (f < 32) {
+                int df = 0;
+                if (lane == f) {
+                  const int nBf = regionbase + mpre + extra, nAf = nS + 2 - nBf;
+                  const double dc = (mz == 0) ? log((double)(nAf - 1)) - log((double)nBf)
+                                              : log((double)nAf) - log((double)(nBf - 1));
+                  const double D = dc + md0;
+                  int nz;
+                  if (D > 0.0)
+                    nz = (D >= mlg) ? 0 : 1;
+                  else
+                    nz = (-D >= mlg) ? 1 : 0;
+                  df = nz - mz;
                   mz = nz;
                 }
-                extra += warp_sum_i(d);
-                if (f < 32) {
-                  int df = 0;
-                  if (lane == f) {
-                    const int nBf = regionbase + mpre + extra, nAf = nS + 2 - nBf;
-                    const double dc = (mz == 0) ? log((double)(nAf - 1)) - log((double)nBf)
-                                                : log((double)nAf) - log((double)(nBf - 1));
-                    const double D = dc + md0;
-                    int nz;
-                    if (D > 0.0)
-                      nz = (D >= mlg) ? 0 : 1;
-                    else
-                      nz = (-D >= mlg) ? 1 : 0;
-                    df = nz - mz;
-                    mz = nz;
-                  }
-                  extra += __shfl_sync(SMG_FULL, df, f);
-                }
-                start = f + 1;
+                extra += __shfl_sync(SMG_FULL, df, f);
               }
-              if (v) G.nr_z[lbase + qq] = mz;
+              start = f + 1;
             }
-            regionbase += xchg[(par * SMC_MAXCS + r) * 4 + 0];
+            if (v) G.nr_z[lbase + qq] = mz;
           }
-          if (lane == 0) G.walk_out[par] = extra;
+          regionbase += xchg[(par * SMC_MAXCS + r) * 4 + 0];
         }
-        smc_sync();  // (1b) their sides
-        extra = __ldcg(&G.walk_out[par]);
+        if (lane == 0) G.walk_out[par] = extra;
+      }
+      smc_sync();  // (1b) their sides
+      extra = __ldcg(&G.walk_out[par]);
+      if (isM) {
         for (int k = tid; k < nnr_mine; k += SMC_T) zn[G.nr_idx[pos0 + k]] = (uint8_t)__ldcg(&G.nr_z[pos0 + k]);
         __syncthreads();
       }
-      nBcur += dsum + extra;
-      // ---- P2: move the rows of the members that changed side between the two side histograms
-      for (int t = tid; t < ndec * chunks; t += SMC_T) {
-        const int m = t / chunks, qc = t % chunks;
-        const int go = zc[m], gn = zn[m];
-        if (go == gn) continue;
-        const uint8_t* xr = m < rcap ? rows + (size_t)m * pp : A.X + (size_t)srow[m] * pp;
-        const uint4 v = *reinterpret_cast<const uint4*>(xr + qc * 16);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        int* Ho = phl + (size_t)go * len + (size_t)qc * 16 * mmax;
-        int* Hn = phl + (size_t)gn * len + (size_t)qc * 16 * mmax;
-#pragma unroll
-        for (int b = 0; b < 16; b++) {
-          const int x = (w[b >> 2] >> ((b & 3) * 8)) & 0xff;
-          if (x) {
-            atomicSub(&Ho[b * mmax + (x - 1)], 1);
-            atomicAdd(&Hn[b * mmax + (x - 1)], 1);
-          }
+    }
+    nBcur += dsum + extra;
+    SMC_TICK(10);
+#ifdef SMG_SMC_PROFILE
+    if (rank == 0 && tid == 0 && G.prof) {
+      G.prof[59] += (unsigned long long)nnr_tot;
+      if (q < 4) G.prof[60 + q] += (unsigned long long)nnr_tot;
+    }
+#endif
+    if (isM) {
+      // ---- P2: move the rows of the members that changed side between the two side histograms (a warp per mover)
+      for (int base = warp * 32; base < ndec; base += SMC_T) {
+        const int m = base + lane;
+        const bool mv = m < ndec && zn[m] != zc[m];
+        unsigned bal = __ballot_sync(SMG_FULL, mv);
+        while (bal) {
+          const int l = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const int mm = base + l;
+          hist_move(mm, phl, zc[mm], phl, zn[mm]);
         }
+        __syncwarp();
+        if (mv) zc[m] = zn[m];
       }
+      SMC_TICK(11);
+      smc_sync();  // (2) side histograms of the member CTAs
+      SMC_TICK(12);
+      smc_arrive();  // (3)
+      if (q < A.t) fill_logits(q + 1);  // the next scan's, while the parameter CTAs draw (the proposal scan is scan t)
+      SMC_TICK(13);
+      smc_wait();  // (3) parameters of the two sides
+      SMC_TICK(16);
+      build_table();
       __syncthreads();
-      for (int m = tid; m < ndec; m += SMC_T) zc[m] = zn[m];
-      SMC_TICK(4);
-      smc_sync();  // (2) side histograms of every CTA
-      SMC_TICK(5);
+      SMC_TICK(6);
+    } else {
+      smc_sync();  // (2)
+      SMC_TICK(12);
+      // ---- P3: parameter updates of the two sides on this CTA's attributes
       reduce_slices(phl, prop ? SH_P0 : SH_L0, prop);
-      if (prop && rank == 0 && tid == 0) {
+      if (prop && kP == 0 && tid == 0) {
         A.cnt[SH_P0] = nS + 2 - nBcur;
         A.cnt[SH_P1] = nBcur;
       }
       __syncthreads();
-    }
-    // ---- P3: parameter updates of this step on this CTA's attributes
-    SmcJob jb[3];
-    int nj = 0;
-    if (do_scan) {
+      SMC_TICK(13);
+      SmcJob jb[2];
       for (int side = 0; side < 2; side++) {
-        SmcJob& J = jb[nj];
+        SmcJob& J = jb[side];
         J.role = side;
         J.hist = (prop ? SH_P0 : SH_L0) + side;
         J.nk = side ? nBcur : nS + 2 - nBcur;
         J.dst = NSB + (prop ? (side ? SM_ST_B : SM_ST_A) : (side ? SM_SL_B : SM_SL_A));
-        J.idx = nj;
+        J.idx = side;
         J.prior = 0;
         J.sub = SUB_SM_RG + q;
         J.uc = off(A.u_rg_c, ((size_t)q * 2 + side) * p);
         J.us = off(A.u_rg_s, ((size_t)q * 2 + side) * p);
-        nj++;
       }
-    }
-    if (prop || it < A.r) {
-      // the r updates of the merge launch state (split_merge.cpp:386-387) are an independent chain on the fixed merged
-      // histogram; the final one of the proposal (:584) keeps job index 2 as in the other paths
-      SmcJob& J = jb[nj];
-      J.role = 2;
-      J.hist = SH_M;
-      J.nk = nS + 2;
-      J.dst = NSB + (prop ? SM_ST_M : SM_ML_M);
-      J.idx = prop ? 2 : nj;
-      J.prior = 0;
-      J.sub = SUB_SM_MERGE + (prop ? A.r : it);
-      J.uc = off(A.u_mg_c, (size_t)(prop ? A.r : it) * p);
-      J.us = off(A.u_mg_s, (size_t)(prop ? A.r : it) * p);
-      nj++;
-    }
-    if (nj > 0) {
-      // a job on an empty side is skipped (common_functions.cpp:547): its parameters stay as they are
-      int nk_ok = 0;
-      SmcJob act[3];
-      for (int k = 0; k < nj; k++)
-        if (jb[k].nk > 0) act[nk_ok++] = jb[k];
-      smc_draw_slice(G, act, nk_ok, rank, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, do_scan);
-    }
-    if (do_scan) {
+      smc_draw_slice(G, jb, 2, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
       __syncthreads();
-      smc_publish_sdpart(G, rank, denS, sdpart);
-      SMC_TICK(6);
-      smc_sync();  // (3) parameters of the two sides in every CTA
-      SMC_TICK(7);
-      par ^= 1;
+      smc_publish_sdpart(G, kP, denS, sdpart);
+      SMC_TICK(14);
+      smc_sync();  // (3)
+      SMC_TICK(16);
     }
+    par ^= 1;
   }
   // ------------------------------------------------------------------------------------------
   // MH ratio (split_merge.cpp:438-540), acceptance (:591) and relabelling (clean_var, common_functions.cpp:296-353)
   // ------------------------------------------------------------------------------------------
-  for (int m = tid; m < mine; m += SMC_T)
-    if (pos0 + m < nS) A.zStar[pos0 + m] = zc[m];
+  if (isM)
+    for (int m = tid; m < ndec; m += SMC_T) A.zStar[pos0 + m] = zc[m];
+  SMC_TICK(17);
   smc_sync();  // (f) every slot written by the draws is visible
+  SMC_TICK(18);
   const int sA = same ? NSB + SM_ST_A : cA, sB = same ? NSB + SM_ST_B : cB, sM = same ? cA : NSB + SM_ST_M;
-  {
+  if (isM) {
     // canonical log-normaliser sums of the proposal slots (the 256-leaf tree of phi_job_body), by three warps;
     // CTA 0 also stores them: an accepted proposal hands them to the state
     if (warp < 3) {
@@ -812,44 +1016,82 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       isgv[k * pp + j] = __ldcg(&A.isg[(size_t)slots3[k] * pp + j]);
     }
     __syncthreads();
-  }
-  const double sdA = same ? s_sd[0] : A.sden[cA], sdB = same ? s_sd[1] : A.sden[cB], sdM = same ? A.sden[cA] : s_sd[2];
-  // per-member terms (sm_rowterms_body), own members; the six parameter-density terms by attribute
-  for (int m = warp; m < mine; m += SMC_WARPS) {
-    const int pos = pos0 + m;
-    const uint8_t* x = m < rcap ? rows + (size_t)m * pp : A.X + (size_t)srow[m] * pp;
-    const int side = same ? zc[m] : zs[m];
-    const double llA = -warp_mismatch_dot(x, cenv, isgv, pp, lane) - sdA;
-    const double llB = -warp_mismatch_dot(x, cenv + pp, isgv + pp, pp, lane) - sdB;
-    const double llM = -warp_mismatch_dot(x, cenv + 2 * pp, isgv + 2 * pp, pp, lane) - sdM;
-    if (lane == 0) {
-      const size_t stride = (size_t)n + 2;
-      A.rowvals[0 * stride + pos] = side == 0 ? llA : 0.0;
-      A.rowvals[1 * stride + pos] = side == 1 ? llB : 0.0;
-      A.rowvals[2 * stride + pos] = llM;
-      double gc = 0.0;
-      if (pos < nS) {
-        const int zlm = zl[m];
-        const int nA = cntL0 - (zlm == 0), nB = cntL1 - (zlm == 1);
-        const double a0 = log((double)nA) + llA, a1 = log((double)nB) + llB;
-        const double mx = a0 > a1 ? a0 : a1;
-        const double p0 = exp(a0 - mx), p1 = exp(a1 - mx);
-        double sm = 0.0;
-        sm += p0;
-        sm += p1;
-        gc = log((side == 0 ? p0 : p1) / sm);
+    const double sdv[3] = {same ? s_sd[0] : A.sden[cA], same ? s_sd[1] : A.sden[cB], same ? A.sden[cA] : s_sd[2]};
+    SMC_TICK(19);
+    // per-member terms (sm_rowterms_body) of the own members: three passes, one per parameter vector, each with its own
+    // look-up table T[j][a] = [a != c_j]/sigma_j; one thread per member
+    const size_t stride = (size_t)n + 2;
+    const unsigned Tb = (unsigned)__cvta_generic_to_shared(T);
+    const int tsh = 31 - __clz(TL) + 3;
+    for (int vec = 0; vec < 3; vec++) {
+      for (int e = tid; e < pp * TL; e += SMC_T) {
+        const int j = e / TL, av = e % TL;
+        T[e] = (av != 0 && av != cenv[vec * pp + j]) ? isgv[vec * pp + j] : 0.0;
       }
-      A.rowvals[3 * stride + pos] = gc;
+      __syncthreads();
+      for (int m = tid; m < mine; m += SMC_T) {
+        const int pos = pos0 + m;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        if (m < rcap) {
+          const uint32_t* xr = rowsT + m;
+#pragma unroll 4
+          for (int w = 0; w < words; w++) {
+            const uint32_t xw = xr[(size_t)w * RSTR];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+              const unsigned addr = Tb + ((unsigned)(4 * w + b) << tsh) + (((xw >> (8 * b)) & 0xffu) << 3);
+              double v;
+              asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+              acc[b] += v;
+            }
+          }
+        } else {
+          const uint32_t* xr = reinterpret_cast<const uint32_t*>(A.X + (size_t)row_of(pos) * pp);
+          for (int w = 0; w < words; w++) {
+            const uint32_t xw = xr[w];
+#pragma unroll
+            for (int b = 0; b < 4; b++) acc[b] += T[(size_t)(4 * w + b) * TL + ((xw >> (8 * b)) & 0xffu)];
+          }
+        }
+        const double ll = -((acc[0] + acc[1]) + (acc[2] + acc[3])) - sdv[vec];
+        if (vec == 0) {
+          A.rowvals[0 * stride + pos] = ll;  // (side selection in the next pass)
+        } else if (vec == 1) {
+          const double llA = A.rowvals[0 * stride + pos], llB = ll;
+          const int side = same ? zc[m] : (pos < nS ? A.zState[pos] : pos - nS);
+          A.rowvals[0 * stride + pos] = side == 0 ? llA : 0.0;
+          A.rowvals[1 * stride + pos] = side == 1 ? llB : 0.0;
+          double gc = 0.0;
+          if (pos < nS) {
+            const int zlm = A.zL[pos];
+            const int nA = cntL0 - (zlm == 0), nB = cntL1 - (zlm == 1);
+            const double a0 = log((double)nA) + llA, a1 = log((double)nB) + llB;
+            const double mx = a0 > a1 ? a0 : a1;
+            const double p0 = exp(a0 - mx), p1 = exp(a1 - mx);
+            double sm = 0.0;
+            sm += p0;
+            sm += p1;
+            gc = log((side == 0 ? p0 : p1) / sm);
+          }
+          A.rowvals[3 * stride + pos] = gc;
+        } else {
+          A.rowvals[2 * stride + pos] = ll;
+        }
+      }
+      __syncthreads();
+    }
+  } else {
+    // the six parameter-density terms by attribute (sm_gsphi_prior_attr), this CTA's attributes: one thread per task
+    for (int t = tid; t < 6 * sl; t += SMC_T) {
+      const int b = t / sl, j = j0s + t % sl;
+      if (j < p)
+        G.gsvals[(size_t)b * pp + j] =
+            sm_gsphi_prior_attr(b, j, pp, mmax, A.phi.attr, A.phi.v, A.phi.w, A.H, A.cnt, A.plan, A.cen, A.sig);
     }
   }
-  for (int t = tid; t < 6 * sl; t += SMC_T) {
-    const int b = t / sl, j = j0s + t % sl;
-    if (j < p)
-      G.gsvals[(size_t)b * pp + j] =
-          sm_gsphi_prior_attr(b, j, pp, mmax, A.phi.attr, A.phi.v, A.phi.w, A.H, A.cnt, A.plan, A.cen, A.sig);
-  }
-  SMC_TICK(8);
+  SMC_TICK(20);
   smc_sync();  // (h) per-member and per-attribute terms
+  SMC_TICK(21);
   {
     const int gw = rank * SMC_WARPS + warp;
     if (rank == 0 && warp < 6) {  // the 256-leaf trees of sm_gsphi_prior_body: leaf t = sum of attributes t, t + 256, ...
@@ -866,24 +1108,59 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     }
     for (int vb = gw; vb < 4 * SM_RB; vb += nwarps) sm_rowreduce1_warp(nS, A.rowvals, n + 2, A.partial, vb % SM_RB, vb / SM_RB, lane);
   }
+  SMC_TICK(22);
   smc_sync();  // (i) partial sums
+  SMC_TICK(23);
   if (rank == 0) {
     RngKey k = A.key;
     k.sub = SUB_SM_ACCEPT;
     sm_accept_body(A.info, A.plan, A.cnt, A.partial, A.gamma, A.u_accept, k, A.terms, A.accepted, A.stats, sh);
   }
-  SMC_TICK(9);
+#ifdef SMG_SMC_NODRAW
+  if (rank == 0 && tid == 0) *A.accepted = 0;
+#endif
+  SMC_TICK(24);
 #ifdef SMG_SMC_PROFILE
-  if (rank == 0 && tid == 0 && G.prof) G.prof[10] += 1ull;
+  if (rank == 0 && tid == 0 && G.prof) G.prof[58] += 1ull;
 #endif
   smc_sync();  // (j) the decision
   if (__ldcg(A.accepted) == 0) return;
   // ---- accept: state <- proposal
-  if (rank == 0)
+  if (rank == 0) {
+    // the proposal slots join the state: 1/sigma, the per-attribute log-normalisers and their sum re-derived from sigma
+    // by the canonical expressions (derive_terms_kernel / phi_job_body), so that a state restored from a snapshot of
+    // (centres, sigmas) continues bit for bit
+    for (int t = tid; t < 3 * pp; t += SMC_T) {
+      const int k = t / pp, j = t % pp;
+      const size_t o = (size_t)(NSB + (k == 0 ? SM_ST_A : (k == 1 ? SM_ST_B : SM_ST_M))) * pp + j;
+      double w = 0.0, d = 0.0;
+      if (j < p) {
+        const double sg = __ldcg(&A.sig[o]);
+        w = 1.0 / sg;
+        d = hamming_den(sg, A.phi.attr[j]);
+      }
+      A.isg[o] = w;
+      G.den[o] = d;
+    }
+    __syncthreads();
+    if (warp < 3) {
+      const int slot = NSB + (warp == 0 ? SM_ST_A : (warp == 1 ? SM_ST_B : SM_ST_M));
+      double v[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        double acc = 0.0;
+        for (int j = lane + 32 * k; j < p; j += 256) acc += G.den[(size_t)slot * pp + j];
+        v[k] = acc;
+      }
+      const double t = tree256_warp(v);
+      if (lane == 0) A.sden[slot] = t;
+    }
+    __syncthreads();
     sm_apply_params_body(A.info, NSB, A.Kcap, pp, A.cen, A.sig, A.isg, A.sden, A.cnt, A.counts, A.Kptr, A.phi.status);
-  {
+  }
+  if (isM) {
     const int Kold = A.info->K;
-    for (int m = tid; m < mine; m += SMC_T) A.c[srow[m]] = same ? (zc[m] == 0 ? Kold : cB) : cB;
+    for (int m = tid; m < mine; m += SMC_T) A.c[row_of(pos0 + m)] = same ? (zc[m] == 0 ? Kold : cB) : cB;
   }
   if (same) return;
   smc_sync();  // (k) members relabelled before the last label moves into the hole
@@ -895,13 +1172,12 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   }
 }
 
-
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 struct SmcHost {
   bool ok = false;
-  int CS = 0, mcap = 0, rcap = 0;
+  int CS = 0, TL = 8, mcap = 0, rcap = 0;
   size_t smem = 0;
   double* gsvals = nullptr;
   double *nr_d0 = nullptr, *nr_lg = nullptr;
@@ -917,20 +1193,31 @@ static int smc_setup(smg_chain* ch, SmcHost* H) {
   cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, ch->device);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ch->device);
   if (cc_major < 9 || ch->t <= 0) return 0;
-  const size_t budget = (size_t)smem_optin - 4096;  // static shared memory of the kernel
+  cudaFuncAttributes fa;
+  if (cudaFuncGetAttributes(&fa, sm_cluster_kernel) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  // the attribute is per function, not per chain: always the device maximum, so that chains of different shapes coexist
+  const size_t budget = (size_t)smem_optin - fa.sharedSizeBytes - 1024;
+  if (cudaFuncSetAttribute(sm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)smem_optin - fa.sharedSizeBytes)) != cudaSuccess ||
+      cudaFuncSetAttribute(sm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
   const char* ecs = getenv("SMG_SMC_CS");
+  int TL = 8;
+  while (TL <= ch->mmax) TL <<= 1;  // table entries per attribute: a power of two above the largest code
   for (int CS = ecs ? atoi(ecs) : SMC_MAXCS; CS >= 8; CS >>= 1) {
-    if (ch->pp % CS) continue;
-    const int mcap = ((int)(((long long)ch->n + 2 + CS - 1) / CS) + 31) & ~31;
-    const SmcLayout L0 = smc_layout(ch->pp, ch->mmax, CS, mcap, 0);
-    if (L0.total + (size_t)std::min(mcap, 64) * ch->pp > budget) continue;
-    const int rcap = (int)std::min<size_t>((size_t)mcap, (budget - L0.total) / ch->pp);
-    const SmcLayout L = smc_layout(ch->pp, ch->mmax, CS, mcap, rcap);
-    if (cudaFuncSetAttribute(sm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total) != cudaSuccess ||
-        cudaFuncSetAttribute(sm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-      (void)cudaGetLastError();
-      continue;
-    }
+    const int nM = CS / 2;
+    if (ch->pp % nM) continue;
+    const int mcap = ((int)(((long long)ch->n + 2 + nM - 1) / nM) + 31) & ~31;
+    const SmcLayout L0 = smc_layout(ch->pp, ch->mmax, TL, CS, mcap, 0);
+    if (L0.total + (size_t)std::min(mcap, 64) * (ch->pp + 8) + 64 > budget) continue;
+    int rcap = (int)std::min<size_t>((size_t)mcap, (budget - L0.total) / (ch->pp + 8));
+    while (rcap > 0 && smc_layout(ch->pp, ch->mmax, TL, CS, mcap, rcap).total > budget) rcap--;
+    if (rcap < std::min(mcap, 64)) continue;
+    const SmcLayout L = smc_layout(ch->pp, ch->mmax, TL, CS, mcap, rcap);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(CS);
     cfg.blockDim = dim3(SMC_T);
@@ -948,6 +1235,7 @@ static int smc_setup(smg_chain* ch, SmcHost* H) {
       continue;
     }
     H->CS = CS;
+    H->TL = TL;
     H->mcap = mcap;
     H->rcap = rcap;
     H->smem = L.total;
@@ -962,8 +1250,8 @@ static int smc_setup(smg_chain* ch, SmcHost* H) {
   SMG_CUDA(dev_malloc(&H->nr_z, nl * 4, ch->st));
   SMG_CUDA(dev_malloc(&H->nr_idx, nl * 4, ch->st));
   SMG_CUDA(dev_malloc(&H->walk_out, 2 * 4, ch->st));
-  SMG_CUDA(dev_malloc(&H->prof, 16 * 8, ch->st));
-  SMG_CUDA(cudaMemsetAsync(H->prof, 0, 16 * 8, ch->st));
+  SMG_CUDA(dev_malloc(&H->prof, 64 * 8, ch->st));
+  SMG_CUDA(cudaMemsetAsync(H->prof, 0, 64 * 8, ch->st));
   SMG_CUDA(cudaMemsetAsync(H->walk_out, 0, 8, ch->st));
   H->ok = true;
   return 0;
@@ -979,7 +1267,8 @@ static cudaError_t smc_launch(smg_chain* ch, const SmcHost* H, const SmChainArgs
   SmcArgs G;
   G.A = CA;
   G.CS = H->CS;
-  G.sl = ch->pp / H->CS;
+  G.sl = ch->pp / (H->CS / 2);
+  G.TL = H->TL;
   G.mcap = H->mcap;
   G.rcap = H->rcap;
   G.den = ch->den;
