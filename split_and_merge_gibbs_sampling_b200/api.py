@@ -174,9 +174,10 @@ class Chain:
         return dict(zip(keys, (int(x) for x in out)))
 
     def scan_profile(self):
-        out = np.zeros(8, dtype=np.uint64)
+        out = np.zeros(16, dtype=np.uint64)
         lb.check(self.lib.smg_debug_scan_profile(self.h, out.ctypes.data_as(lb.c_ull_p)))
-        keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "_"]
+        keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "_", "e8", "e9", "e10", "e11", "e12", "e13",
+                "e14", "e15"]
         return dict(zip(keys, (int(x) for x in out)))
 
     def sm_profile(self):
@@ -189,7 +190,7 @@ class Chain:
         keys = {k: "M." + v for k, v in names.items()}
         keys.update({32 + k: "P." + v for k, v in names.items()})
         keys.update({50: "D.entry", 51: "D.philox", 52: "D.centre", 53: "D.sigma", 54: "D.tail", 55: "D.publish"})
-        keys.update({56: "nnr_screen_fail_cta0", 57: "nnr_pairE_micro", 58: "launches", 59: "nnr_total", 60: "nnr_scan0", 61: "nnr_scan1", 62: "nnr_scan2", 63: "nnr_scan3"})
+        keys.update({58: "launches", 59: "nnr_total", 60: "nnr_scan0", 61: "nnr_scan1", 62: "nnr_scan2", 63: "nnr_scan3"})
         return {name: int(out[k]) for k, name in keys.items()}
 
     def timings(self):

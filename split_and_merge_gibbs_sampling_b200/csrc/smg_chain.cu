@@ -11,6 +11,7 @@
 #include <thread>
 
 #include "smg_psm.cuh"
+#include "smg_lltc.cuh"
 #include "smg_sm_host.cuh"
 
 namespace smg {
@@ -130,6 +131,47 @@ static int chain_alloc(smg_chain* ch) {
   SMG_CUDA(cudaMemsetAsync(ch->status, 0, 4, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, 4, ch->st));
   SMG_CUDA(cudaMemsetAsync(ch->stats_d, 0, 64, ch->st));
+  {
+    // K1 on the tensor cores when its resident operand fits the shared memory of one SM
+    const char* e = getenv("SMG_K1");  // tc (default when feasible) | t16 | c
+    int smem_optin = 0, sms = 0;
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ch->device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ch->device);
+    ch->ltc_kdp = ltc_kdp(pp, ch->mmax);
+    ch->ltc_sms = sms;
+    cudaFuncAttributes fa;
+    bool fits = cudaFuncGetAttributes(&fa, hamming_ll_tc_kernel) == cudaSuccess;
+    (void)cudaGetLastError();
+    if (fits) {
+      // operand ring: as many k-steps per stage as fit beside the resident B operand (8, 4, 2 or 1), >= 3 stages
+      const size_t room = (size_t)smem_optin - fa.sharedSizeBytes - 1024;
+      const size_t bb = ltc_b_bytes(ch->ltc_kdp) + (size_t)LTC_M * (pp + 16);  // resident B operand + the staged codes of a row tile
+      const char* ekg = getenv("SMG_LTC_KG");
+      fits = false;
+      for (int kg = ekg ? atoi(ekg) : 8; kg >= 1; kg >>= 1) {
+        const int nst = (int)std::min<size_t>(LTC_STAGES, bb < room ? (room - bb) / ((size_t)kg * LTC_A_BYTES) : 0);
+        if (nst >= 3 || (kg == 1 && nst >= 2)) {
+          ch->ltc_kg = kg;
+          ch->ltc_nstg = nst;
+          ch->ltc_smem = bb + (size_t)nst * kg * LTC_A_BYTES;
+          fits = true;
+          break;
+        }
+      }
+    }
+    // measured at the metric shape: 247 us against 175 us of the shared-memory look-up kernel (the one-hot operand is
+    // written with generic-proxy stores and every stage pays a proxy fence; tensor pipe 10% active) -> opt-in
+    ch->ltc_on = fits && e && strcmp(e, "tc") == 0;
+    if (ch->ltc_on) {
+      SMG_CUDA(cudaFuncSetAttribute(hamming_ll_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)((size_t)smem_optin - fa.sharedSizeBytes)));
+      const int ntmax = cdiv(ch->Kcap, LTC_NC);
+      if (dalloc(&ch->ltc_B, (size_t)ntmax * ltc_b_bytes(ch->ltc_kdp)) || dalloc(&ch->ltc_Q, (size_t)ntmax * LTC_NC) ||
+          dalloc(&ch->ltc_scale, (size_t)ntmax * LTC_NC) || dalloc(&ch->ltc_cst, (size_t)ntmax * LTC_NC * 4) || dalloc(&ch->ltc_K, 1) ||
+          dalloc(&ch->ltc_ctr, 64))
+        return SMG_ERR_CUDA;
+    }
+  }
   if (dalloc(&ch->tape_d, (size_t)n * (ch->m_aux + 1))) return SMG_ERR_CUDA;
   if (dalloc(&ch->uc_d, (size_t)NST * ch->p) || dalloc(&ch->us_d, (size_t)NST * ch->p)) return SMG_ERR_CUDA;
   int rc = sm_alloc(ch);
@@ -150,7 +192,7 @@ static void chain_free(smg_chain* ch) {
                   ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux[0], ch->LLaux[1], ch->mrg, ch->aux_e[0], ch->aux_e[1], ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
                   ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d,
-                  ch->c_hist, ch->phi_cnt, ch->und0, ch->und_blk};
+                  ch->c_hist, ch->phi_cnt, ch->und0, ch->und_blk, ch->ltc_B, ch->ltc_Q, ch->ltc_scale, ch->ltc_K, ch->ltc_ctr, ch->ltc_cst};
   for (void* q : ptrs)
     if (q) cudaFreeAsync(q, ch->st);
   if (ch->st) cudaStreamSynchronize(ch->st);
@@ -180,7 +222,18 @@ static int launch_ll_block(smg_chain* ch, cudaStream_t stream = nullptr) {
   if (!stream) stream = ch->st;
   cudaEventRecord(ch->ev_k1[0], stream);
   dim3 grid(cdiv(ch->n, LLB_ROWS), cdiv(ch->Kcap, LLB_SLOTS));
-  if (ch->mmax <= 7)  // every code fits 3 bits: subset-sum table form
+  if (ch->ltc_on) {
+    // exact integer GEMM on the tensor cores: one-hot(X) x fixed-point digit planes of 1/sigma (smg_lltc.cuh)
+    const int ntmax = cdiv(ch->Kcap, LTC_NC);
+    SMG_CUDA(cudaMemcpyAsync(ch->ltc_K, ch->K, sizeof(int), cudaMemcpyDeviceToDevice, stream));  // one consistent K
+    SMG_CUDA(cudaMemsetAsync(ch->ltc_ctr, 0, 64 * sizeof(int), stream));
+    ll_tc_prep_kernel<<<ntmax * LTC_NC, 256, 0, stream>>>(ch->pp, ch->mmax, ch->ltc_kdp, ch->ltc_K, ch->cen[ch->cur],
+                                                          ch->isg[ch->cur], ch->ltc_B, ch->ltc_Q, ch->ltc_scale, ch->sden[ch->cur], ch->ltc_cst);
+    hamming_ll_tc_kernel<<<ch->ltc_sms, LTC_THREADS, ch->ltc_smem, stream>>>(
+        ch->X, ch->n, ch->pp, ch->mmax, ch->ltc_kdp, ch->ltc_K, ch->ltc_B, ch->ltc_Q, ch->ltc_scale, ch->sden[ch->cur], ch->LL,
+        ch->ldl, ch->ltc_ctr, ch->ltc_kg, ch->ltc_nstg, ch->ltc_cst, ch->scan_prof);
+    ch->h_launches++;
+  } else if (ch->mmax <= 7)  // every code fits 3 bits: subset-sum table form
     hamming_ll_block_t16_kernel<<<grid, 256, LLT_SMEM_BYTES, stream>>>(ch->X, ch->n, ch->pp, ch->cen[ch->cur],
                                                                       ch->isg[ch->cur], ch->sden[ch->cur], ch->K, ch->LL,
                                                                       ch->ldl);
@@ -1100,7 +1153,7 @@ int smg_debug_scan_profile(smg_chain* ch, unsigned long long* out8) {
   if (!ch || !out8) return fail(SMG_ERR_ARG, "NULL argument");
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st));
-  SMG_CUDA(d2h_sync(out8, ch->scan_prof, 64, ch->st));
+  SMG_CUDA(d2h_sync(out8, ch->scan_prof, 128, ch->st));  // 16 counters
 #ifdef SMG_PHI_PROFILE
   SMG_CUDA(d2h_sync(out8, ch->scan_prof + 8, 64, ch->st));  // phi_update / chain counters instead
 #endif

@@ -122,6 +122,14 @@ struct smg_chain {
   int cur = 0;
   int *c = nullptr, *K = nullptr, *counts = nullptr, *counts_slot = nullptr, *slot2label = nullptr;
   double *LL = nullptr, *mrg = nullptr;
+  // tensor-core likelihood block (smg_lltc.cuh): digit-plane operand, per-cluster integer weight sums and scales
+  bool ltc_on = false;
+  int ltc_kdp = 0, ltc_sms = 0, ltc_kg = 1, ltc_nstg = 4;
+  size_t ltc_smem = 0;
+  uint8_t* ltc_B = nullptr;
+  long long* ltc_Q = nullptr;
+  double *ltc_scale = nullptr, *ltc_cst = nullptr;
+  int *ltc_K = nullptr, *ltc_ctr = nullptr;
   double* LLaux[2] = {nullptr, nullptr};  // aux columns, double-buffered: [aux_buf] feeds the current pass
   int* aux_e[2] = {nullptr, nullptr};
   int aux_buf = 0;

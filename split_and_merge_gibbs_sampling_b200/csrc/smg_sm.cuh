@@ -30,6 +30,7 @@ struct SmcHost;  // cluster-kernel resources (smg_smc.cuh)
 
 struct SmWork {
   SmcHost* smc = nullptr;
+  int forced_mode = 0;  // SMG_SM_MODE at creation: 0 default, 1 cluster, 2 coop, 3 multi
   int *S = nullptr, *zL = nullptr, *zStar = nullptr, *zState = nullptr;
   SmInfo* info = nullptr;
   SmPlan* plan = nullptr;

@@ -50,7 +50,8 @@ static int sm_alloc(smg_chain* ch) {
     int coop = 0;
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ch->device);
     const char* env = getenv("SMG_SM_PERSISTENT");
-    const char* mode = getenv("SMG_SM_MODE");  // cluster (default when feasible) | coop | multi
+    const char* mode = getenv("SMG_SM_MODE");  // cluster | coop | multi (default: by measurement, see sm_step)
+    W->forced_mode = !mode ? 0 : (strcmp(mode, "cluster") == 0 ? 1 : (strcmp(mode, "coop") == 0 ? 2 : 3));
     const bool multi_only = (env && env[0] == '0') || (mode && strcmp(mode, "multi") == 0);
     W->persistent = coop && W->hist_smem > 0 && W->hist_smem <= 64 * 1024 && !multi_only;
     if (W->persistent)
@@ -204,7 +205,13 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     const char* e = getenv("SMG_SM_MANY_MAXN");
     return e ? atoi(e) : 30000;
   }();
-  const bool use_cluster = W->smc && W->smc->ok && ch->t > 0;
+  // Default path by measurement (profiles/r02_summary.md): a single chain is fastest on the 120-CTA cooperative kernel
+  // (0.43 ms per proposal at the metric shape against 0.56 ms on the 16-CTA cluster, whose phases run on 8 SMs each and
+  // are bound by double-precision dependency latency); chains stepped together use the cluster kernel, which occupies
+  // 16 SMs per chain instead of gang-scheduling 120.  SMG_SM_MODE=cluster|coop|multi forces one.
+  const int forced = W->forced_mode;  // read when the chain was created
+  const bool cluster_ok = W->smc && W->smc->ok && ch->t > 0;
+  const bool use_cluster = cluster_ok && (forced == 1 || (forced == 0 && ch->many));
   const bool use_coop = !use_cluster && W->persistent && ch->t > 0 && !(ch->many && n > many_max_n);
   if (use_cluster || use_coop) {
     // ---- the whole proposal as one cooperative kernel: selection, launch states, t restricted scans, r merge-launch

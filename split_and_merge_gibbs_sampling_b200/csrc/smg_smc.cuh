@@ -49,7 +49,7 @@ struct SmcArgs {
 };
 
 struct SmcLayout {
-  size_t T, Tp, pmax, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, total;
+  size_t T, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, total;
   int rstr;  // member stride of the transposed rows (odd: conflict-free both by member and by word)
 };
 __host__ __device__ inline size_t smc_al(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -59,8 +59,6 @@ __host__ __device__ inline SmcLayout smc_layout(int pp, int mmax, int TL, int CS
   size_t o = 0;
   L.rstr = rcap | 1;
   L.T = o, o = smc_al(o + (size_t)pp * TL * 8);
-  L.Tp = o, o = smc_al(o + (TL == 8 ? (size_t)(pp / 2) * 64 * 4 : 0));  // fp32 pair table of the screen (codes < 8 only)
-  L.pmax = o, o = smc_al(o + (size_t)(pp / 2) * 4);
   L.isgv = o, o = smc_al(o + (size_t)3 * pp * 8);
   L.sdpart = o, o = smc_al(o + (size_t)3 * SMC_MAXCS * 8);
   L.sigS = o, o = smc_al(o + (size_t)3 * sl * 8);
@@ -334,7 +332,6 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   const SmcLayout L = smc_layout(pp, mmax, TL, CS, mcap, rcap);
   const int RSTR = L.rstr;
   double* T = reinterpret_cast<double*>(smc_raw + L.T);         // [pp][TL] look-up table of the scan in progress
-  float* Tp = reinterpret_cast<float*>(smc_raw + L.Tp);         // [pp/2][64] single-precision table of attribute pairs (screen)
   double* isgv = reinterpret_cast<double*>(smc_raw + L.isgv);   // [3][pp] 1/sigma of the vectors being evaluated
   double* sdpart = reinterpret_cast<double*>(smc_raw + L.sdpart);  // [3][16] partial log-normaliser sums by parameter CTA
   double* sigS = reinterpret_cast<double*>(smc_raw + L.sigS);   // [3][sl] current sigma of the three update chains
@@ -599,44 +596,18 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   };
   // member CTAs: look-up table of the two sides' parameters (cenv / isgv rows 0, 1) and their constant term
   double sdBA = 0.0;  // sden_B - sden_A
-  float pairE = 0.f;  // bound of |single-precision pair sum - exact sum| for any member (see the screen in P1)
-  __shared__ float s_pmax[SMC_WARPS];
-  int* s_pairmax = reinterpret_cast<int*>(smc_raw + L.pmax);  // [pp/2] largest |entry| of each pair (float bits)
   auto build_table = [&]() {
     const double a = lane < nP ? sdpart[0 * SMC_MAXCS + lane] : 0.0, b = lane < nP ? sdpart[1 * SMC_MAXCS + lane] : 0.0;
     sdBA = warp_sum(b) - warp_sum(a);
+    const int tls = 31 - __clz(TL);  // log2(TL)
     for (int e = tid; e < pp * TL; e += SMC_T) {
-      const int j = e / TL, av = e % TL;
+      const int j = e >> tls, av = e & (TL - 1);
       double v = 0.0;
       if (av != 0) {
         if (av != cenv[pp + j]) v += isgv[pp + j];
         if (av != cenv[j]) v -= isgv[j];
       }
       T[e] = v;
-    }
-    if (TL == 8) {
-      // single-precision pair table: Tp[q][a1 + 8 a2] = float(T[2q][a1] + T[2q+1][a2]); S = sum over the pairs of the
-      // largest |entry| bounds sum_i |t_i| of any member, so |fp32 sum - exact| <= (pairs + 2) 2^-24 S (rounding of the
-      // entries + of the 4-way accumulation)
-      __syncthreads();
-      for (int q2 = tid; q2 < pp / 2; q2 += SMC_T) s_pairmax[q2] = 0;
-      __syncthreads();
-      for (int e2 = tid; e2 < (pp / 2) * 64; e2 += SMC_T) {
-        const int q2 = e2 >> 6, e = e2 & 63;
-        const float v = (float)(T[(2 * q2) * 8 + (e & 7)] + T[(2 * q2 + 1) * 8 + (e >> 3)]);
-        Tp[e2] = v;
-        atomicMax(&s_pairmax[q2], __float_as_int(fabsf(v)));  // non-negative floats order like their bit patterns
-      }
-      __syncthreads();
-      float mymax = 0.f;
-      for (int q2 = tid; q2 < pp / 2; q2 += SMC_T) mymax += __int_as_float(s_pairmax[q2]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mymax += __shfl_xor_sync(SMG_FULL, mymax, o);
-      if (lane == 0) s_pmax[warp] = mymax;
-      __syncthreads();
-      float S = 0.f;
-      for (int w2 = 0; w2 < SMC_WARPS; w2++) S += s_pmax[w2];
-      pairE = ((float)(pp / 2) + 4.f) * 5.97e-8f * (S + fabsf((float)sdBA)) * 1.01f + 1e-6f;
     }
   };
   if (isM) {
@@ -706,40 +677,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       const double dc_min = nS > 0 ? sm_dc_bound(nS, nS) - SM_DC_MARGIN : 0.0;
       const unsigned Tb = (unsigned)__cvta_generic_to_shared(T);
       const int tsh = 31 - __clz(TL) + 3;  // log2(TL * 8): byte stride of an attribute's table row
-      const unsigned Tpb = (unsigned)__cvta_generic_to_shared(Tp);
-      const float sdf = (float)sdBA;
       for (int m = tid; m < ndec; m += SMC_T) {
-        const double lgm = m < rcap ? lg[m] : A.lgt[pos0 + m];
-        if (TL == 8 && m < rcap) {
-          // ---- single-precision screen: LL_A - LL_B within +-pairE; decided here when the whole interval, under every
-          //      possible count, falls inside one decision region (the exact value lies in it too)
-          const uint32_t* xr = rowsT + m;
-          float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-#pragma unroll 4
-          for (int w = 0; w < words; w += 2) {
-            const uint32_t xa = xr[(size_t)w * RSTR], xb = xr[(size_t)(w + 1) * RSTR];
-            const unsigned i0 = (xa & 7u) | ((xa >> 5) & 0x38u), i1 = ((xa >> 16) & 7u) | ((xa >> 21) & 0x38u);
-            const unsigned i2 = (xb & 7u) | ((xb >> 5) & 0x38u), i3 = ((xb >> 16) & 7u) | ((xb >> 21) & 0x38u);
-            float v0, v1, v2, v3;
-            asm("ld.shared.f32 %0, [%1];" : "=f"(v0) : "r"(Tpb + ((unsigned)(2 * w) << 8) + (i0 << 2)));
-            asm("ld.shared.f32 %0, [%1];" : "=f"(v1) : "r"(Tpb + ((unsigned)(2 * w + 1) << 8) + (i1 << 2)));
-            asm("ld.shared.f32 %0, [%1];" : "=f"(v2) : "r"(Tpb + ((unsigned)(2 * w + 2) << 8) + (i2 << 2)));
-            asm("ld.shared.f32 %0, [%1];" : "=f"(v3) : "r"(Tpb + ((unsigned)(2 * w + 3) << 8) + (i3 << 2)));
-            f0 += v0;
-            f1 += v1;
-            f2 += v2;
-            f3 += v3;
-          }
-          const float d32 = ((f0 + f1) + (f2 + f3)) + sdf;
-          const int rlo = sm_d_region(dc_min + (double)(d32 - pairE), lgm), rhi = sm_d_region(dc_max + (double)(d32 + pairE), lgm);
-          if (rlo == rhi) {
-            zn[m] = (uint8_t)(~rlo & 1);
-            continue;
-          }
-#ifdef SMG_SMC_PROFILE
-          if (rank == 0 && G.prof) atomicAdd(&G.prof[56], 1ull);
-#endif
-        }
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (m < rcap) {
           const uint32_t* xr = rowsT + m;
@@ -747,11 +685,11 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
           for (int w = 0; w < words; w++) {
             const uint32_t xw = xr[(size_t)w * RSTR];
 #pragma unroll
-            for (int b = 0; b < 4; b++) {
-              const unsigned addr = Tb + ((unsigned)(4 * w + b) << tsh) + (((xw >> (8 * b)) & 0xffu) << 3);
+            for (int b4 = 0; b4 < 4; b4++) {
+              const unsigned addr = Tb + ((unsigned)(4 * w + b4) << tsh) + (((xw >> (8 * b4)) & 0xffu) << 3);
               double v;
               asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-              acc[b] += v;
+              acc[b4] += v;
             }
           }
         } else {
@@ -759,10 +697,11 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
           for (int w = 0; w < words; w++) {
             const uint32_t xw = xr[w];
 #pragma unroll
-            for (int b = 0; b < 4; b++) acc[b] += T[(size_t)(4 * w + b) * TL + ((xw >> (8 * b)) & 0xffu)];
+            for (int b4 = 0; b4 < 4; b4++) acc[b4] += T[(size_t)(4 * w + b4) * TL + ((xw >> (8 * b4)) & 0xffu)];
           }
         }
         const double d0 = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + sdBA;  // LL_A - LL_B
+        const double lgm = m < rcap ? lg[m] : A.lgt[pos0 + m];
         const int rlo = sm_d_region(dc_min + d0, lgm), rhi = sm_d_region(dc_max + d0, lgm);
         if (rlo == rhi) {
           zn[m] = (uint8_t)(~rlo & 1);
@@ -772,9 +711,6 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
         }
       }
       __syncthreads();
-#ifdef SMG_SMC_PROFILE
-      if (rank == 0 && tid == 0 && G.prof) G.prof[57] += (unsigned long long)(pairE * 1e6f);
-#endif
       SMC_TICK(7);
       // ordered pass over the own members: side-1 change of the decided ones, list of the undecided ones (by position)
       int carry_d = 0, carry_n = 0;
@@ -1187,7 +1123,7 @@ struct SmcHost {
 
 // decides whether the cluster kernel can run this chain (shared-memory budget, cluster size the device accepts)
 static int smc_setup(smg_chain* ch, SmcHost* H) {
-  const char* env = getenv("SMG_SM_MODE");  // cluster (default when feasible) | coop | multi
+  const char* env = getenv("SMG_SM_MODE");  // cluster | coop | multi (see sm_step for the default)
   if (env && strcmp(env, "cluster") != 0) return 0;
   int cc_major = 0, smem_optin = 0;
   cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, ch->device);

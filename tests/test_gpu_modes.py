@@ -169,14 +169,22 @@ def test_split_merge_device_paths_give_the_same_chain():
 
 
 def test_merge_acceptance_is_patched_too():
-    """Over-split start (every true cluster cut in two): merges are accepted; same checks."""
-    pb = Problem(1600, 24, 4, 4, seed=93, s=0.5)
-    c0 = (pb.labels * 2 + (np.arange(1600) // 4) % 2).astype(np.int32)
-    kw = dict(c_i=c0, seed=94, t=3, r=3)
-    ref, st_ref = _run_trace(pb, "multi", 60, overlap=False, **kw)
-    assert st_ref["sm_accepted"] >= 1
-    got, st = _run_trace(pb, "cluster", 60, overlap=True, **kw)
-    assert st["sm_accepted"] == st_ref["sm_accepted"]
-    for a, b in zip(ref, got):
-        assert a["K"] == b["K"] and a["accepted"] == b["accepted"]
-        assert np.array_equal(a["c_i"], b["c_i"])
+    """Over-split start (every true cluster cut in two at random): some merge gets accepted (seeds are tried until the
+    reference path accepts one while K decreases); the overlapped likelihood block must have been patched -- same chain,
+    log-likelihoods checked against the oracle after every iteration."""
+    for seed in range(94, 104):
+        pb = Problem(320, 16, 3, 3, seed=seed, s=0.4)
+        rng = np.random.default_rng(seed)
+        c0 = (pb.labels * 2 + rng.integers(0, 2, size=320)).astype(np.int32)
+        kw = dict(c_i=c0, seed=seed, t=2, r=2)
+        ref, st_ref = _run_trace(pb, "multi", 80, overlap=False, **kw)
+        merged = any(b["accepted"] and b["K"] < a["K"] for a, b in zip(ref[:-1], ref[1:]))
+        if not merged:
+            continue
+        got, st = _run_trace(pb, "cluster", 80, overlap=True, **kw)
+        assert st["sm_accepted"] == st_ref["sm_accepted"]
+        for a, b in zip(ref, got):
+            assert a["K"] == b["K"] and a["accepted"] == b["accepted"]
+            assert np.array_equal(a["c_i"], b["c_i"])
+        return
+    pytest.fail("no seed produced an accepted merge")
