@@ -43,7 +43,11 @@ def run_markov_chain(data, attrisize, gamma, v, w, verbose=0, m=5, iterations=10
                                   int(verbose), int(m), int(iterations), int(L), lb.iptr(ci), int(burnin), int(t),
                                   int(r), int(bool(neal8)), int(bool(split_merge)), int(n8_step_size), int(sam_step_size),
                                   int(thinning), C.c_ulonglong(int(seed) & (2**64 - 1)), int(device), C.byref(res))
-    lb.check(rc)
+    partial_err = None
+    if rc == 4 and res.iterations > 0 and res.total_cls:  # SMG_ERR_CAPACITY with the iterations kept so far
+        partial_err = lb.SmgError(rc, lib.smg_last_error().decode("utf-8", "replace"))
+    else:
+        lb.check(rc)
     # The big result arrays (allocation trace, centres, sigmas) are NOT copied: the numpy arrays below are views of the
     # library's buffers, which are released when the last of them is garbage collected.
     owner = _ResultsOwner(lib, res)
@@ -55,7 +59,7 @@ def run_markov_chain(data, attrisize, gamma, v, w, verbose=0, m=5, iterations=10
     cen = _view(res.centers, max(nphi, 1) * p, C.c_double, owner).reshape(max(nphi, 1), p)[:nphi]
     sig = _view(res.sigmas, max(nphi, 1) * p, C.c_double, owner).reshape(max(nphi, 1), p)[:nphi]
     offl = off.tolist()
-    return {
+    out = {
         "total_cls": total.tolist(),
         "c_i": list(c_all),
         "centers": [list(cen[offl[i]:offl[i + 1]]) for i in range(it)],
@@ -66,6 +70,10 @@ def run_markov_chain(data, attrisize, gamma, v, w, verbose=0, m=5, iterations=10
         "accepted": _view(res.accepted, max(it, 1), C.c_int, owner)[:it].copy(),
         "seconds": float(res.seconds),
     }
+    if partial_err is not None:  # the chain outgrew the cluster capacity: the iterations completed so far travel with the error
+        partial_err.partial = out
+        raise partial_err
+    return out
 
 
 class _ResultsOwner:
@@ -154,11 +162,11 @@ class Chain:
         lb.check(self.lib.smg_last_step_ms(self.h, C.byref(ms)))
         return ms.value
 
-    def snapshot(self, with_phi=True):
+    def snapshot(self, with_phi=True, with_c=True):
         K = C.c_int()
         ll = C.c_double()
         acc = C.c_int()
-        c = np.empty(self.n, dtype=np.int32)
+        c = np.empty(self.n, dtype=np.int32) if with_c else None
         cen = np.empty((self.kcap, self.p)) if with_phi else None
         sig = np.empty((self.kcap, self.p)) if with_phi else None
         lb.check(self.lib.smg_snapshot(self.h, C.byref(K), lb.iptr(c), lb.dptr(cen), lb.dptr(sig), self.kcap, C.byref(ll),
@@ -179,6 +187,12 @@ class Chain:
         keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "_", "e8", "e9", "e10", "e11", "e12", "e13",
                 "e14", "e15"]
         return dict(zip(keys, (int(x) for x in out)))
+
+    def time_ll_block(self, reps=5):
+        """Device time (ms) of the likelihood-block kernel alone on the current state, cold caches."""
+        out = C.c_double()
+        lb.check(self.lib.smg_debug_time_ll_block(self.h, int(reps), C.byref(out)))
+        return out.value
 
     def sm_profile(self):
         out = np.zeros(64, dtype=np.uint64)
@@ -346,6 +360,61 @@ class Psm:
         out = np.empty((self.n, self.n), dtype=np.int32)
         lb.check(self.lib.smg_debug_psm_reference(self.h, lb.iptr(out)))
         return out
+
+
+class Comm:
+    """Communicator of the library's own NCCL reductions (include/smgibbs.h, smg_comm_* / smg_chains_*): PSM
+    reduce-scatter / all-reduce, split-R-hat, K histogram.  `unique_id()` on rank 0, ship the 128 bytes to the other
+    ranks with any transport (torch.distributed broadcast, a file, MPI), then Comm(rank, world, id, device)."""
+
+    @staticmethod
+    def unique_id():
+        lib = lb.load()
+        buf = C.create_string_buffer(128)
+        lb.check(lib.smg_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, rank=0, world=1, unique_id=None, device=0):
+        self.lib = lb.load()
+        self.rank, self.world, self.device = int(rank), int(world), int(device)
+        h = C.c_void_p()
+        lb.check(self.lib.smg_comm_create(self.rank, self.world, unique_id, self.device, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.smg_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reduce_psm(self, psm, mode="reduce_scatter"):
+        """Sums the PSM counts of all ranks in place.  Returns (row0, nrows, ms, bus_GBps): the rows of the reduced matrix
+        this rank holds (all of them after an all-reduce)."""
+        r0, nr, ms, bus = C.c_int(), C.c_int(), C.c_double(), C.c_double()
+        lb.check(self.lib.smg_chains_reduce_psm(self.h, psm.h, 1 if mode == "reduce_scatter" else 0, C.byref(r0), C.byref(nr),
+                                                C.byref(ms), C.byref(bus)))
+        return r0.value, nr.value, ms.value, bus.value
+
+    def split_rhat(self, traces):
+        """Split-R-hat over the chains of all ranks; traces: [local chains][draws]."""
+        x = np.ascontiguousarray(traces, dtype=np.float64)
+        if x.ndim != 2:
+            raise ValueError("traces must be [chains][draws]")
+        out, tot = C.c_double(), C.c_longlong()
+        lb.check(self.lib.smg_chains_split_rhat(self.h, lb.dptr(x), x.shape[0], x.shape[1], C.byref(out), C.byref(tot)))
+        return out.value, tot.value
+
+    def k_histogram(self, K, kmax=256):
+        k = np.ascontiguousarray(np.asarray(K).ravel(), dtype=np.int32)
+        hist = np.zeros(kmax + 1, dtype=np.int64)
+        over = C.c_longlong()
+        lb.check(self.lib.smg_chains_k_histogram(self.h, lb.iptr(k), k.size, kmax, hist.ctypes.data_as(lb.c_ll_p), C.byref(over)))
+        return hist, over.value
 
 
 def hig_inv_u(omega, v, w, m):

@@ -24,9 +24,11 @@ def shard_chains(n_chains, world_size, rank):
 
 
 def row_block(n, world_size, rank):
-    """Rows of the PSM owned by `rank` after a reduce-scatter (equal blocks; n is padded up by the caller)."""
+    """Rows [lo, hi) of the PSM owned by `rank` after a reduce-scatter (equal blocks; n is padded up by the caller).
+    Trailing ranks may own no row at all (lo == hi == n) when ceil(n / world) * rank >= n."""
     per = -(-int(n) // int(world_size))
-    return rank * per, min(n, (rank + 1) * per)
+    lo = min(int(n), rank * per)
+    return lo, max(lo, min(int(n), (rank + 1) * per))
 
 
 def chain_moments(x):
@@ -132,6 +134,8 @@ def run_chains(n, n_chains, chain_factory, burnin, iterations, thinning=1, psm_f
     # ---- reductions (collectives only here, never inside a sweep)
     khist = torch.zeros(kmax + 1, dtype=torch.int64, device=dev)
     if Ktr.size:
+        if Ktr.max() > kmax:  # the histogram must sum to chains x draws: refuse to drop draws silently
+            raise ValueError(f"a chain reached K = {int(Ktr.max())} > kmax = {kmax}: raise kmax")
         khist += torch.bincount(torch.as_tensor(Ktr.astype(np.int64).ravel(), device=dev), minlength=kmax + 1)[:kmax + 1]
     if dist is not None:
         dist.all_reduce(khist, op=dist.ReduceOp.SUM)
@@ -150,7 +154,7 @@ def run_chains(n, n_chains, chain_factory, burnin, iterations, thinning=1, psm_f
                 out = torch.empty((per, n), dtype=torch.int32, device=dev)
                 dist.reduce_scatter_tensor(out, psm_t, op=dist.ReduceOp.SUM)
                 lo, hi = row_block(n, world, rank)
-                psm_t = out[:hi - lo]
+                psm_t = out[:max(0, hi - lo)]
             else:
                 dist.all_reduce(psm_t, op=dist.ReduceOp.SUM)
     else:
@@ -166,3 +170,58 @@ def run_chains(n, n_chains, chain_factory, burnin, iterations, thinning=1, psm_f
         "psm": None if psm_t is None else psm_t, "psm_rows": row_block(n, world, rank) if psm_mode == "reduce_scatter" else (0, n),
         "psm_draws": n_chains * iterations, "chains": chains,
     }
+
+
+def run_chains_native(n, n_chains, chain_factory, burnin, iterations, rank=0, world=1, unique_id=None, device=0,
+                      thinning=1, step_many=None, psm_mode="reduce_scatter", kmax=256, psm_capacity=64):
+    """The same run with every reduction inside the C++ library (include/smgibbs.h: smg_comm_* / smg_chains_*, NCCL
+    bound with dlopen): chains sharded over `world` ranks (one process per GPU), the PSM of the local chains accumulated
+    on the tensor cores into a library-owned int32 matrix, then ncclReduceScatter (rank g keeps the rows [g n/G, (g+1)
+    n/G)) or ncclAllReduce, ncclAllReduce of the K histogram, ncclAllGather of the half-chain moments -> split-R-hat.
+    `unique_id`: the 128 bytes of Comm.unique_id() from rank 0 (shipped by the caller; not needed when world == 1)."""
+    import time
+    from .api import Comm, Psm
+    mine = shard_chains(n_chains, world, rank)
+    chains = [chain_factory(cid) for cid in mine]
+    comm = Comm(rank, world, unique_id, device)
+    psm = Psm(n, device=device, capacity_sweeps=psm_capacity) if psm_mode != "none" else None
+
+    def advance(k):
+        if step_many is not None:
+            step_many(chains, k)
+        else:
+            for ch in chains:
+                ch.step(k)
+
+    t0 = time.perf_counter()
+    if burnin * thinning > 0:
+        advance(burnin * thinning)
+    burn_s = time.perf_counter() - t0
+    Ktr = np.zeros((len(chains), iterations), dtype=np.float64)
+    Ltr = np.zeros((len(chains), iterations), dtype=np.float64)
+    t_psm = 0.0
+    for it in range(iterations):
+        advance(thinning)
+        for q, ch in enumerate(chains):
+            s = ch.snapshot(with_phi=False, with_c=False)
+            Ktr[q, it] = s["K"]
+            Ltr[q, it] = s["loglikelihood"]
+            if psm is not None:
+                psm.push_chain(ch)
+    if psm is not None:
+        tp = time.perf_counter()
+        psm.flush()
+        t_psm = time.perf_counter() - tp
+    sample_s = time.perf_counter() - t0
+    out = {"rank": rank, "world": world, "local_chains": mine, "K_local": Ktr, "loglik_local": Ltr, "sample_seconds": sample_s,
+           "burnin_seconds": burn_s, "kept_seconds": sample_s - burn_s - t_psm,
+           "psm_flush_seconds": t_psm, "psm_draws": n_chains * iterations, "chains": chains, "psm": psm, "comm": comm}
+    if psm is not None:
+        r0, nr, ms, bus = comm.reduce_psm(psm, psm_mode)
+        out.update(psm_rows=(r0, r0 + nr), psm_reduce_ms=ms, psm_bus_gbs=bus, psm_mode=psm_mode)
+    if iterations >= 4:
+        out["rhat_K"], out["n_chains_total"] = comm.split_rhat(Ktr)
+        out["rhat_loglik"], _ = comm.split_rhat(Ltr)
+    hist, over = comm.k_histogram(Ktr.astype(np.int32), kmax)
+    out["K_hist"], out["K_hist_overflow"] = hist, over
+    return out

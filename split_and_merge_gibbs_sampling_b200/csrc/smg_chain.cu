@@ -3,6 +3,8 @@
 // all arithmetic happens in the kernels of smg_kernels.cuh / smg_sm.cuh.  There is no CPU path.
 #include "smg_chain.cuh"
 
+#include <sched.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -12,6 +14,7 @@
 
 #include "smg_psm.cuh"
 #include "smg_lltc.cuh"
+#include "smg_comm.cuh"
 #include "smg_sm_host.cuh"
 
 namespace smg {
@@ -728,7 +731,16 @@ static int upload_colmajor(smg_chain* ch, const double* data) {
   // packed into a cached page-locked buffer: no page faults after the first call and a faster copy
   uint8_t* buf = nullptr;
   if (pinned_acquire((size_t)n * pp, &buf, 1)) return fail(SMG_ERR_CUDA, "cudaHostAlloc of the upload staging buffer failed");
-  const int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  // packing threads: the cores this process may run on (a rank pinned to its share of the host must not start 16
+  // threads per rank), at most 16; SMG_PACK_THREADS overrides
+  int nthr = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  {
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) nthr = std::max(1, std::min(nthr, CPU_COUNT(&set)));
+    const char* e = getenv("SMG_PACK_THREADS");
+    if (e && atoi(e) > 0) nthr = std::min(64, atoi(e));
+  }
   std::vector<long long> nbad(nthr, 0);
   std::vector<std::thread> pool;
   const int* attr = ch->h_attr.data();
@@ -1228,6 +1240,21 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   cfg.thinning = thinning;
   cfg.seed = seed;
   cfg.device = device;
+  {
+    // cluster capacity: 192 by default; a start with more clusters than that (the scripts' "all different" start,
+    // c_i = seq(1, n)) gets what the allocation draw can hold, K + m <= 256 (divergences)
+    const char* e = getenv("SMG_MAX_CLUSTERS");
+    int want = e ? atoi(e) : 0;
+    if (c_i && n > 0) {
+      std::vector<int> tmp(c_i, c_i + n);
+      std::sort(tmp.begin(), tmp.end());
+      const int k0 = (int)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+      if (k0 + 16 > 192) want = std::max(want, k0 + 16);
+    } else if (L + 16 > 192) {
+      want = std::max(want, L + 16);
+    }
+    if (want > 0) cfg.max_clusters = std::min(want, SMG_MAX_ENTRIES - m);
+  }
   smg_chain* ch = nullptr;
   auto tc0 = std::chrono::steady_clock::now();
   int rc = smg_create(&cfg, data, c_i, &ch);
@@ -1306,12 +1333,14 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
     return fail(SMG_ERR_CUDA, "allocation of the snapshot staging failed");
   }
   for (int q = 0; q < RING; q++) cudaEventCreateWithFlags(&ev_packed[q], cudaEventDisableTiming);
+  long long n_consumed = 0;  // kept iterations already copied into the result block (in order)
   auto consume = [&](Slot& S) -> int {
     if (S.result_slot < 0) return 0;
     if (cudaEventSynchronize(S.ev) != cudaSuccess) return fail(SMG_ERR_CUDA, "snapshot copy failed");
     const long long slot = S.result_slot;
     S.result_slot = -1;
     if (S.hdr[1]) return status_to_error(S.hdr[1]);
+    n_consumed = slot + 1;
     const int K = S.hdr[0];
     if (K > Kcap) return fail(SMG_ERR_CAPACITY, "number of clusters exceeds max_clusters");
     out->total_cls[slot] = K;
@@ -1361,7 +1390,17 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   auto t1 = std::chrono::steady_clock::now();
   out->seconds = std::chrono::duration<double>(t1 - t0).count();
   out->time = (long long)std::chrono::duration_cast<std::chrono::seconds>(t1 - t0).count();
-  if (!rc) {
+  // A chain that outgrows the cluster capacity stops there, but what it produced is NOT thrown away (the reference
+  // would have lost everything to the exception, launcher.cpp:155-161): the block keeps the iterations completed so far,
+  // `iterations` says how many, and the status is still SMG_ERR_CAPACITY.
+  const bool partial = rc == SMG_ERR_CAPACITY && n_consumed > 0;
+  if (!rc || partial) {
+    if (partial) {
+      out->iterations = (int)n_consumed;
+      cen.size = (size_t)out->phi_offset[n_consumed] * p;
+      sg.size = cen.size;
+      if (n_consumed > 0) memcpy(out->final_ass, out->c_i + (size_t)(n_consumed - 1) * n, (size_t)n * 4);
+    }
     if (!cen.p) cen.extend(1), cen.size = 0;
     if (!sg.p) sg.extend(1), sg.size = 0;
     out->centers = cen.p;
@@ -1388,8 +1427,8 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   free(cen.p);  // (null once handed over)
   free(sg.p);
   if (rc) {
-    smg_free_results(out);
-    g_last_error = keep;
+    if (!partial) smg_free_results(out);
+    g_last_error = keep + (partial ? " (the result block holds the " + std::to_string(n_consumed) + " iterations kept before)" : "");
   }
   return rc;
 }
@@ -1503,6 +1542,29 @@ int smg_debug_ll_block(smg_chain* ch, double* LL, int* mism) {
     SMG_CUDA(d2h_sync(mism, d, (size_t)ch->n * K * 4, ch->st));
     cudaFree(d);
   }
+  return 0;
+}
+
+// device time of the likelihood-block kernel ALONE (nothing else on the GPU), averaged over `reps` launches on the current
+// state; a memset of the whole LL buffer (larger than L2) between launches keeps every launch cold, as inside a sweep
+int smg_debug_time_ll_block(smg_chain* ch, int reps, double* ms_avg) {
+  if (!ch || !ms_avg || reps < 1) return fail(SMG_ERR_ARG, "bad argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  SMG_CUDA(cudaStreamSynchronize(ch->st_aux));
+  SMG_CUDA(cudaStreamSynchronize(ch->st_k1));
+  double acc = 0.0;
+  for (int q = 0; q < reps; q++) {
+    SMG_CUDA(cudaMemsetAsync(ch->LL, 0, (size_t)ch->n * ch->ldl * sizeof(double), ch->st));
+    if (launch_ll_block(ch)) return SMG_ERR_CUDA;
+    SMG_CUDA(cudaStreamSynchronize(ch->st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ch->ev_k1[0], ch->ev_k1[1]);
+    acc += ms;
+  }
+  ch->ll_for_iter = -1;
+  *ms_avg = acc / reps;
   return 0;
 }
 
@@ -1821,6 +1883,206 @@ int smg_debug_psm_reference(smg_psm* P, int* out_psm_host) {
   SMG_CUDA(cudaStreamSynchronize(P->st));
   SMG_CUDA(cudaMemcpy(out_psm_host, d, (size_t)P->n * P->n * sizeof(int), cudaMemcpyDeviceToHost));
   cudaFree(d);
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// reductions over GPUs (smg_comm.cuh): NCCL over NVLink, called from this library
+// ------------------------------------------------------------------------------------------
+int smg_comm_unique_id(char* id128) {
+  if (!id128) return fail(SMG_ERR_ARG, "NULL argument");
+  NcclApi* N = nccl_api();
+  if (!N->err.empty()) return fail(SMG_ERR_CUDA, N->err);
+  ncclUniqueId id;
+  SMG_NCCL(N->GetUniqueId(&id));
+  memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES);
+  return 0;
+}
+
+int smg_comm_create(int rank, int world, const char* id128, int device, smg_comm** out) {
+  if (!out) return fail(SMG_ERR_ARG, "out is NULL");
+  *out = nullptr;
+  if (world < 1 || rank < 0 || rank >= world) return fail(SMG_ERR_ARG, "bad rank / world size");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(SMG_ERR_ARG, "bad device ordinal");
+  SMG_CUDA(cudaSetDevice(device));
+  smg_comm* C = new smg_comm();
+  C->rank = rank;
+  C->world = world;
+  C->device = device;
+  if (cudaStreamCreateWithFlags(&C->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&C->ev[0]) != cudaSuccess ||
+      cudaEventCreate(&C->ev[1]) != cudaSuccess) {
+    smg_comm_destroy(C);
+    return fail(SMG_ERR_CUDA, "stream / event creation failed");
+  }
+  if (world > 1) {
+    if (!id128) {
+      smg_comm_destroy(C);
+      return fail(SMG_ERR_ARG, "the NCCL unique id of rank 0 is required when world > 1");
+    }
+    NcclApi* N = nccl_api();
+    if (!N->err.empty()) {
+      smg_comm_destroy(C);
+      return fail(SMG_ERR_CUDA, N->err);
+    }
+    ncclUniqueId id;
+    memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    ncclResult_t r = N->CommInitRank(&C->comm, world, id, rank);
+    if (r != ncclSuccess) {
+      std::string msg = std::string("ncclCommInitRank: ") + N->GetErrorString(r);
+      smg_comm_destroy(C);
+      return fail(SMG_ERR_CUDA, msg);
+    }
+  }
+  *out = C;
+  return 0;
+}
+
+void smg_comm_destroy(smg_comm* C) {
+  if (!C) return;
+  cudaSetDevice(C->device);
+  if (C->st) cudaStreamSynchronize(C->st);
+  if (C->comm) nccl_api()->CommDestroy(C->comm);
+  for (int q = 0; q < 2; q++)
+    if (C->ev[q]) cudaEventDestroy(C->ev[q]);
+  if (C->st) cudaStreamDestroy(C->st);
+  delete C;
+}
+
+// PSM counts of all ranks summed.  mode 1 (reduce-scatter): rank g ends up with the reduced rows [row0, row0 + nrows)
+// in place (its other rows keep the local partial sums); mode 0 or n % world != 0: all-reduce, every rank holds the whole
+// matrix.  *ms = device time of the collective, *bus_gbs = NCCL bus bandwidth (bytes * (G-1)/G [* 2 for all-reduce] / s).
+int smg_chains_reduce_psm(smg_comm* C, smg_psm* P, int mode, int* row0, int* nrows, double* ms, double* bus_gbs) {
+  if (!C || !P) return fail(SMG_ERR_ARG, "NULL argument");
+  if (C->device != P->device) return fail(SMG_ERR_ARG, "communicator and matrix live on different devices");
+  SMG_CUDA(cudaSetDevice(C->device));
+  int rc = smg_psm_flush(P);
+  if (rc) return rc;
+  const int n = P->n, G = C->world;
+  const bool scatter = mode == 1 && G > 1 && n % G == 0;
+  int r0 = 0, nr = n;
+  float fms = 0.f;
+  double bus = 0.0;
+  if (G > 1) {
+    NcclApi* N = nccl_api();
+    const size_t total = (size_t)n * n;
+    SMG_CUDA(cudaEventRecord(C->ev[0], C->st));
+    if (scatter) {
+      const size_t per = total / G;
+      SMG_NCCL(N->ReduceScatter(P->psm, P->psm + (size_t)C->rank * per, per, ncclInt32, ncclSum, C->comm, C->st));
+      nr = n / G;
+      r0 = C->rank * nr;
+    } else {
+      SMG_NCCL(N->AllReduce(P->psm, P->psm, total, ncclInt32, ncclSum, C->comm, C->st));
+    }
+    SMG_CUDA(cudaEventRecord(C->ev[1], C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    cudaEventElapsedTime(&fms, C->ev[0], C->ev[1]);
+    const double bytes = (double)total * 4.0 * (double)(G - 1) / (double)G * (scatter ? 1.0 : 2.0);
+    bus = fms > 0.f ? bytes / (fms * 1e-3) / 1e9 : 0.0;
+  }
+  if (row0) *row0 = r0;
+  if (nrows) *nrows = nr;
+  if (ms) *ms = fms;
+  if (bus_gbs) *bus_gbs = bus;
+  return 0;
+}
+
+// split-R-hat (BDA3 11.4) of a scalar trace over all chains of all ranks: every chain is cut in two halves, the
+// (count, mean, M2) moments of the halves are all-gathered, W = mean within-half variance, B = n * variance of the
+// half means, R-hat = sqrt(((n-1)/n W + B/n) / W).  traces: [nchains_local][T] on the host.
+int smg_chains_split_rhat(smg_comm* C, const double* traces, int nchains_local, int T, double* rhat, long long* nchains_total) {
+  if (!C || !rhat || (nchains_local > 0 && !traces)) return fail(SMG_ERR_ARG, "NULL argument");
+  if (nchains_local < 0 || T < 4) return fail(SMG_ERR_ARG, "need T >= 4 draws per chain");
+  SMG_CUDA(cudaSetDevice(C->device));
+  const int G = C->world, half = T / 2;
+  // local moments: per chain 2 x (mean, M2)
+  std::vector<double> mom((size_t)std::max(nchains_local, 1) * 4, 0.0);
+  for (int q = 0; q < nchains_local; q++)
+    for (int h = 0; h < 2; h++) {
+      const double* x = traces + (size_t)q * T + (h ? T - half : 0);
+      double m = 0.0;
+      for (int i = 0; i < half; i++) m += x[i];
+      m /= half;
+      double s = 0.0;
+      for (int i = 0; i < half; i++) s += (x[i] - m) * (x[i] - m);
+      mom[(size_t)q * 4 + 2 * h] = m;
+      mom[(size_t)q * 4 + 2 * h + 1] = s;
+    }
+  std::vector<double> all;
+  std::vector<int> cnt(G, nchains_local);
+  if (G > 1) {
+    NcclApi* N = nccl_api();
+    int *d_cnt = nullptr, maxc = 0;
+    SMG_CUDA(cudaMalloc(&d_cnt, (size_t)G * sizeof(int)));
+    SMG_CUDA(cudaMemcpyAsync(d_cnt + C->rank, &nchains_local, sizeof(int), cudaMemcpyHostToDevice, C->st));
+    SMG_NCCL(N->AllGather(d_cnt + C->rank, d_cnt, 1, ncclInt32, C->comm, C->st));
+    SMG_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)G * sizeof(int), cudaMemcpyDeviceToHost, C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    cudaFree(d_cnt);
+    for (int g = 0; g < G; g++) maxc = std::max(maxc, cnt[g]);
+    if (maxc == 0) return fail(SMG_ERR_ARG, "no chains");
+    double* d_mom = nullptr;
+    const size_t per = (size_t)maxc * 4;
+    SMG_CUDA(cudaMalloc(&d_mom, per * G * sizeof(double)));
+    SMG_CUDA(cudaMemsetAsync(d_mom, 0, per * G * sizeof(double), C->st));
+    SMG_CUDA(cudaMemcpyAsync(d_mom + per * C->rank, mom.data(), (size_t)nchains_local * 4 * sizeof(double), cudaMemcpyHostToDevice,
+                             C->st));
+    SMG_NCCL(N->AllGather(d_mom + per * C->rank, d_mom, per, ncclDouble, C->comm, C->st));
+    std::vector<double> buf(per * G);
+    SMG_CUDA(cudaMemcpyAsync(buf.data(), d_mom, per * G * sizeof(double), cudaMemcpyDeviceToHost, C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    cudaFree(d_mom);
+    for (int g = 0; g < G; g++) all.insert(all.end(), buf.begin() + per * g, buf.begin() + per * g + (size_t)cnt[g] * 4);
+  } else {
+    all.assign(mom.begin(), mom.begin() + (size_t)nchains_local * 4);
+  }
+  const size_t nparts = all.size() / 2;  // half-chains
+  if (nchains_total) *nchains_total = (long long)(nparts / 2);
+  if (nparts < 2) return fail(SMG_ERR_ARG, "no chains");
+  double W = 0.0, mbar = 0.0;
+  for (size_t q = 0; q < nparts; q++) {
+    W += all[2 * q + 1] / (half - 1);
+    mbar += all[2 * q];
+  }
+  W /= (double)nparts;
+  mbar /= (double)nparts;
+  double B = 0.0;
+  for (size_t q = 0; q < nparts; q++) B += (all[2 * q] - mbar) * (all[2 * q] - mbar);
+  B = (double)half * B / (double)(nparts - 1);
+  if (W == 0.0)
+    *rhat = (B == 0.0) ? 1.0 : INFINITY;
+  else
+    *rhat = std::sqrt((((double)half - 1.0) / half * W + B / half) / W);
+  return 0;
+}
+
+// histogram of the number of clusters over all ranks: hist[k], k = 0..kmax; draws with K > kmax are counted in
+// *overflow (so that sum(hist) + overflow = total draws)
+int smg_chains_k_histogram(smg_comm* C, const int* K, long long count, int kmax, long long* hist, long long* overflow) {
+  if (!C || !hist || kmax < 0 || (count > 0 && !K)) return fail(SMG_ERR_ARG, "bad argument");
+  SMG_CUDA(cudaSetDevice(C->device));
+  std::vector<long long> h((size_t)kmax + 2, 0);
+  for (long long i = 0; i < count; i++) {
+    const int k = K[i];
+    if (k < 0) return fail(SMG_ERR_ARG, "negative K");
+    h[k <= kmax ? k : kmax + 1]++;
+  }
+  if (C->world > 1) {
+    NcclApi* N = nccl_api();
+    long long* d = nullptr;
+    SMG_CUDA(cudaMalloc(&d, h.size() * sizeof(long long)));
+    SMG_CUDA(cudaMemcpyAsync(d, h.data(), h.size() * sizeof(long long), cudaMemcpyHostToDevice, C->st));
+    SMG_NCCL(N->AllReduce(d, d, h.size(), ncclInt64, ncclSum, C->comm, C->st));
+    SMG_CUDA(cudaMemcpyAsync(h.data(), d, h.size() * sizeof(long long), cudaMemcpyDeviceToHost, C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    cudaFree(d);
+  }
+  for (int k = 0; k <= kmax; k++) hist[k] = h[k];
+  if (overflow) *overflow = h[(size_t)kmax + 1];
   return 0;
 }
 
