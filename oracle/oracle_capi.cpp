@@ -19,6 +19,7 @@ struct orc_opts {
   int counted, stable_hig, sigma_inverse_cdf;
   double bisect_tol;
   int bisect_max, validate;
+  int det_i1;  // -1: select_observations_random; >= 0: select_observations_deterministic with this i_1
 };
 
 struct orc_data {
@@ -41,6 +42,7 @@ Opts mk_opts(const orc_opts* o) {
     r.bisect_tol = o->bisect_tol;
     r.bisect_max = o->bisect_max;
     r.validate = o->validate;
+    r.det_i1 = o->det_i1;
   }
   return r;
 }
@@ -153,6 +155,18 @@ double orc_pbeta(double x, double a, double b) { return pbeta_(x, a, b); }
 double orc_log_ibeta(double x, double a, double b) { return log_ibeta(x, a, b); }
 int orc_rhig_beta_branch(double v, double w, double m) { return rhig_beta_branch(v, w, m) ? 1 : 0; }
 void orc_revsort(double* a, int* ib, int n) { revsort(a, ib, n); }
+
+// sample_initial_assignment (common_functions.cpp:174-183) from a uniform tape of n draws
+int orc_initial_assignment(int L, int n, const double* tape, int* out) {
+  try {
+    TapeRng r(tape, (size_t)n);
+    std::vector<int> c = sample_initial_assignment(r, L, n);
+    for (int i = 0; i < n; i++) out[i] = c[i];
+    return 0;
+  } catch (const std::exception&) {
+    return -1;
+  }
+}
 
 // one Rcpp-style sample(x,1,true,probs) draw; flags[0]=exact positive tie, flags[1]=near tie
 int orc_sample_probs_one(const double* probs, int n, double u, int* flags) {

@@ -24,6 +24,7 @@ class SmgConfig(C.Structure):
         ("m_aux", C.c_int), ("L", C.c_int), ("t", C.c_int), ("r", C.c_int), ("neal8", C.c_int), ("split_merge", C.c_int),
         ("n8_step_size", C.c_int), ("sam_step_size", C.c_int), ("thinning", C.c_int), ("seed", C.c_ulonglong),
         ("max_clusters", C.c_int), ("pool_size", C.c_longlong), ("device", C.c_int), ("compact_init", C.c_int), ("exact_sigma_inverse", C.c_int),
+        ("pair_selection", C.c_int), ("aux_mode", C.c_int),
     ]
 
 
@@ -45,7 +46,7 @@ EXPORTS = [
     "smg_step", "smg_step_many", "smg_get_iteration", "smg_resume_at", "smg_validate_state", "smg_synth_generate", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
     "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
-    "smg_debug_split_merge", "smg_debug_time_ll_block", "smg_debug_scan_profile", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
+    "smg_debug_split_merge", "smg_debug_sm_terms", "smg_debug_aux_free", "smg_debug_initial_assignment", "smg_debug_time_ll_block", "smg_debug_scan_profile", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
     "smg_psm_flush", "smg_psm_read", "smg_psm_info", "smg_psm_destroy", "smg_debug_psm_reference",
     "smg_comm_unique_id", "smg_comm_create", "smg_comm_destroy", "smg_chains_reduce_psm", "smg_chains_split_rhat",
     "smg_chains_k_histogram",
@@ -124,6 +125,9 @@ def load():
     lib.smg_debug_hig_inv_u.argtypes = [C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]
     lib.smg_debug_logdensity_hig.argtypes = [C.c_int, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p]
     lib.smg_debug_rhig_u.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_ulonglong, c_dbl_p]
+    lib.smg_debug_initial_assignment.argtypes = [C.c_int, C.c_int, c_dbl_p, C.c_int, c_int_p]
+    lib.smg_debug_aux_free.argtypes = [C.c_void_p, C.c_int, c_dbl_p, c_dbl_p, c_dbl_p]
+    lib.smg_debug_sm_terms.argtypes = [C.c_void_p, c_dbl_p, c_int_p, c_int_p, c_dbl_p, C.c_double, c_int_p, c_dbl_p]
     lib.smg_debug_split_merge.argtypes = [C.c_void_p, C.POINTER(SmgSmTape), c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p,
                                           c_dbl_p]
     _lib = lib

@@ -102,7 +102,7 @@ class Chain:
 
     def __init__(self, data, attrisize, gamma, v, w, m=5, L=1, c_i=None, t=10, r=10, neal8=True, split_merge=True,
                  n8_step_size=1, sam_step_size=1, thinning=1, seed=1, max_clusters=0, pool_size=0, device=0,
-                 compact_init=False, data_u8=False, exact_sigma_inverse=False):
+                 compact_init=False, data_u8=False, exact_sigma_inverse=False, pair_selection="random", aux_mode="pool"):
         self.lib = lb.load()
         self._attr = lb.as_i32(attrisize)
         self._v, self._w = lb.as_f64(v), lb.as_f64(w)
@@ -116,7 +116,8 @@ class Chain:
         cfg = lb.SmgConfig(self.n, self.p, lb.iptr(self._attr), float(gamma), lb.dptr(self._v), lb.dptr(self._w), int(m),
                           int(L), int(t), int(r), int(bool(neal8)), int(bool(split_merge)), int(n8_step_size),
                           int(sam_step_size), int(thinning), int(seed) & (2**64 - 1), int(max_clusters), int(pool_size),
-                          int(device), int(bool(compact_init)), int(bool(exact_sigma_inverse)))
+                          int(device), int(bool(compact_init)), int(bool(exact_sigma_inverse)),
+                          {"random": 0, "deterministic": 1}[pair_selection], {"pool": 0, "philox": 1}[aux_mode])
         ci = None if c_i is None else lb.as_i32(c_i)
         h = C.c_void_p()
         if data_u8:
@@ -280,6 +281,29 @@ class Chain:
                 "nA": int(info[5]), "nB": int(info[6]), "K": int(info[7]), "S": S[:nS].copy(), "z_launch": zl[:nS].copy(),
                 "z_star": zs[:nS].copy(), "phi": phi, "terms": terms}
 
+    def aux_free(self, count):
+        """aux_mode='philox': column values and parameters of the first `count` auxiliary components of the next pass."""
+        ll = np.zeros(count)
+        cen = np.zeros((count, self.p))
+        sig = np.zeros((count, self.p))
+        lb.check(self.lib.smg_debug_aux_free(self.h, int(count), lb.dptr(ll), lb.dptr(cen), lb.dptr(sig)))
+        return ll, cen, sig
+
+    def sm_terms(self, u_pair, z_launch, z_star, phi6, u_accept=0.5):
+        """MH ratio alone (smg_debug_sm_terms) on an injected launch / proposal: phi6 [6][2][p] = (centre, sigma) of
+        split-launch A, B, merge-launch M, proposal A*, B*, M*; sides by position in S.  Returns info + terms[24]."""
+        up = lb.as_f64(u_pair)
+        zl = lb.as_i32(z_launch if len(z_launch) else np.zeros(1, dtype=np.int32))
+        zs = lb.as_i32(z_star if len(z_star) else np.zeros(1, dtype=np.int32))
+        ph = lb.as_f64(phi6)
+        assert ph.shape == (6, 2, self.p)
+        info = np.zeros(8, dtype=np.int32)
+        terms = np.zeros(24)
+        lb.check(self.lib.smg_debug_sm_terms(self.h, lb.dptr(up), lb.iptr(zl), lb.iptr(zs), lb.dptr(ph), float(u_accept),
+                                            lb.iptr(info), lb.dptr(terms)))
+        return {"i1": int(info[0]), "i2": int(info[1]), "nS": int(info[2]), "is_split": int(info[3]),
+                "accepted": int(info[4]), "terms": terms}
+
 
 def synth_generate(n, p, attrisize, k_true, s=0.5, seed=1, device=0):
     """Synthetic Hamming-mixture data generated on the GPU (smg_synth_generate): X uint8 [n][p], labels, centres."""
@@ -291,6 +315,14 @@ def synth_generate(n, p, attrisize, k_true, s=0.5, seed=1, device=0):
     lb.check(lib.smg_synth_generate(int(n), int(p), lb.iptr(attr), int(k_true), float(s), int(seed) & (2**64 - 1), int(device),
                                     X.ctypes.data_as(C.POINTER(C.c_ubyte)), lb.iptr(lab), cen.ctypes.data_as(C.POINTER(C.c_ubyte))))
     return X, lab, cen, attr
+
+
+def initial_assignment(u, L, device=0):
+    """sample_initial_assignment (common_functions.cpp:174-183) on the device under injected uniforms (parity hook)."""
+    uu = lb.as_f64(u)
+    out = np.zeros(uu.size, dtype=np.int32)
+    lb.check(lb.load().smg_debug_initial_assignment(int(uu.size), int(L), lb.dptr(uu), int(device), lb.iptr(out)))
+    return out
 
 
 def step_many(chains, n_iters=1):

@@ -119,6 +119,9 @@ static int chain_alloc(smg_chain* ch) {
   if (dalloc(&ch->LL, (size_t)n * ch->ldl) || dalloc(&ch->LLaux[0], (size_t)n * ch->m_aux) || dalloc(&ch->LLaux[1], (size_t)n * ch->m_aux) || dalloc(&ch->mrg, n + 2) || dalloc(&ch->und0, ((size_t)n + 8191) / 4096 * 4096) || dalloc(&ch->und_blk, (size_t)n / 4096 + 4) ||
       dalloc(&ch->aux_e[0], (size_t)n * ch->m_aux) || dalloc(&ch->aux_e[1], (size_t)n * ch->m_aux))
     return SMG_ERR_CUDA;
+  if (ch->aux_mode == 1 &&
+      (dalloc(&ch->aux_sd[0], (size_t)n * ch->m_aux) || dalloc(&ch->aux_sd[1], (size_t)n * ch->m_aux)))
+    return SMG_ERR_CUDA;
   const size_t P = (size_t)ch->pool_size;
   if (dalloc(&ch->pcen, P * pp) || dalloc(&ch->psig, P * pp) || dalloc(&ch->pisg, P * pp) || dalloc(&ch->pden, P * pp) ||
       dalloc(&ch->psden, P))
@@ -192,7 +195,7 @@ static void chain_free(smg_chain* ch) {
   sm_free(ch);
   void* ptrs[] = {ch->X,      ch->attr,   ch->v,         ch->w,          ch->cen[0], ch->cen[1], ch->sig[0], ch->sig[1],
                   ch->isg[0], ch->isg[1], ch->sden[0],   ch->sden[1],    ch->den,    ch->c,      ch->K,      ch->counts,
-                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux[0], ch->LLaux[1], ch->mrg, ch->aux_e[0], ch->aux_e[1], ch->pcen,   ch->psig,   ch->pisg,
+                  ch->counts_slot, ch->slot2label, ch->LL, ch->LLaux[0], ch->LLaux[1], ch->mrg, ch->aux_e[0], ch->aux_e[1], ch->aux_sd[0], ch->aux_sd[1], ch->pcen,   ch->psig,   ch->pisg,
                   ch->pden,   ch->psden,  ch->H,         ch->partial,    ch->loglik_d, ch->status, ch->accepted_d,
                   ch->stats_d, ch->scan_job, ch->scan_prof, ch->tape_d, ch->uc_d,     ch->us_d,
                   ch->c_hist, ch->phi_cnt, ch->und0, ch->und_blk, ch->ltc_B, ch->ltc_Q, ch->ltc_scale, ch->ltc_K, ch->ltc_ctr, ch->ltc_cst};
@@ -254,6 +257,16 @@ static int launch_aux_ll(smg_chain* ch, const double* tape, cudaStream_t stream,
   long long warps = (long long)ch->n * ch->m_aux;
   RngKey key = mk_key(ch, SUB_SCAN);
   key.sweep = (uint32_t)iter;
+  if (ch->aux_mode == 1) {  // pool-free: fresh prior draws from the pass's own key, nothing stored (the tape's pool-index
+                            // uniforms have no meaning here)
+    key.sub = SUB_AUX_FREE;
+    aux_ll_philox_kernel<<<cdiv(warps * 32, 256), 256, 0, stream>>>(ch->X, ch->n, ch->pp, ch->p, ch->m_aux, ch->attr, ch->v, ch->w,
+                                                                   key, ch->sigma_exact, ch->LLaux[buf], ch->aux_e[buf],
+                                                                   ch->aux_sd[buf]);
+    ch->h_launches++;
+    SMG_CUDA(cudaGetLastError());
+    return 0;
+  }
   aux_ll_kernel<<<cdiv(warps * 32, 256), 256, 0, stream>>>(ch->X, ch->n, ch->pp, ch->m_aux, ch->pcen, ch->pisg, ch->psden,
                                                           ch->pool_size, tape, ch->m_aux + 1, key, ch->LLaux[buf], ch->aux_e[buf]);
   ch->h_launches++;
@@ -271,7 +284,7 @@ static int prefetch_next_aux(smg_chain* ch) {
   if (disabled || !ch->neal8) return 0;
   // an iteration that re-draws the pool before the next pass would invalidate the columns
   for (long long it = ch->iter; it < next_iter; it++)
-    if (it % 1000 == 0) return 0;
+    if (it % 1000 == 0 && ch->aux_mode == 0) return 0;
   // everything enqueued on the chain's stream so far must be complete: the other buffer was last read by the scan of
   // the previous pass, and the pool may have been re-drawn since (launcher.cpp:123-129)
   SMG_CUDA(cudaEventRecord(ch->ev_aux_go, ch->st));
@@ -333,6 +346,14 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed, bool prefet
   A.pool_sig = ch->psig;
   A.pool_isg = ch->pisg;
   A.pool_sden = ch->psden;
+  A.aux_free = ch->aux_mode == 1;
+  A.p = ch->p;
+  A.sigma_exact = ch->sigma_exact;
+  A.aux_key = mk_key(ch, SUB_AUX_FREE);
+  A.attr = ch->attr;
+  A.hv = ch->v;
+  A.hw = ch->w;
+  A.aux_sd = ch->aux_sd[ch->aux_buf];
   A.Kptr = ch->K;
   A.counts = ch->counts;
   A.slot2label = ch->slot2label;
@@ -515,7 +536,7 @@ static int sweep(smg_chain* ch, bool timed) {
     SMG_CUDA(cudaEventRecord(ch->ev_k1_done, ch->st_k1));
   }
   if (timed) cudaEventRecord(ch->ev[5], ch->st);
-  if (ch->iter % 1000 == 0) {
+  if (ch->iter % 1000 == 0 && ch->aux_mode == 0) {
     int rc = draw_pool(ch);
     if (rc) return rc;
   }
@@ -585,6 +606,8 @@ static int validate_cfg(const smg_config* cfg) {
   if (cfg->thinning < 1 || cfg->n8_step_size < 1 || cfg->sam_step_size < 1)
     return fail(SMG_ERR_ARG, "thinning, n8_step_size and sam_step_size must be >= 1");
   if (cfg->t < 0 || cfg->r < 0) return fail(SMG_ERR_ARG, "t and r must be >= 0");
+  if (cfg->pair_selection < 0 || cfg->pair_selection > 1) return fail(SMG_ERR_ARG, "pair_selection must be 0 or 1");
+  if (cfg->aux_mode < 0 || cfg->aux_mode > 1) return fail(SMG_ERR_ARG, "aux_mode must be 0 (stored pool) or 1 (pool-free)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
@@ -612,6 +635,8 @@ static int create_common(const smg_config* cfg, smg_chain** out) {
   ch->seed = cfg->seed;
   ch->device = cfg->device;
   ch->sigma_exact = cfg->exact_sigma_inverse;
+  ch->pair_det = cfg->pair_selection == 1;
+  ch->aux_mode = cfg->aux_mode;
   {
     const char* e = getenv("SMG_NO_K1_OVERLAP");  // diagnostic: likelihood block after the proposal instead of beside it
     ch->k1_overlap = !(e && e[0] == '1');
@@ -623,6 +648,7 @@ static int create_common(const smg_config* cfg, smg_chain** out) {
   ch->NS = SMG_MAX_SLOTS;
   ch->NST = SMG_MAX_SLOTS + SM_NSLOTS;
   ch->pool_size = cfg->pool_size > 0 ? cfg->pool_size : (long long)cfg->n * cfg->m_aux * cfg->thinning;
+  if (ch->aux_mode == 1) ch->pool_size = 1;  // pool-free: a one-entry placeholder keeps the pool plumbing valid
   ch->h_attr.assign(cfg->attrisize, cfg->attrisize + cfg->p);
   ch->h_v.assign(cfg->v, cfg->v + cfg->p);
   ch->h_w.assign(cfg->w, cfg->w + cfg->p);
@@ -1471,6 +1497,7 @@ int smg_debug_set_state(smg_chain* ch, int K, const int* c_i, const double* cent
 
 int smg_debug_set_pool(smg_chain* ch, long long pool_size, const double* pool_center, const double* pool_sigma) {
   if (!ch || !pool_center || !pool_sigma) return fail(SMG_ERR_ARG, "NULL argument");
+  if (ch->aux_mode == 1) return fail(SMG_ERR_ARG, "a pool-free chain (aux_mode 1) has no pool to inject");
   if (pool_size < 1 || pool_size > ch->pool_size) return fail(SMG_ERR_ARG, "pool_size exceeds the allocated pool");
   SMG_CUDA(cudaSetDevice(ch->device));
   SMG_CUDA(cudaStreamSynchronize(ch->st_aux));  // a prefetched aux pass may still be reading the old pool
@@ -1732,6 +1759,133 @@ int smg_debug_split_merge(smg_chain* ch, const smg_sm_tape* tape, int* info, int
   rc = sync_status(ch);
   if (rc) return rc;
   return sm_readback(ch, info, S, z_launch, z_star, phi_out, terms);
+}
+
+// Pool-free auxiliary components (aux_mode 1) of the pass the chain would run next: column values of the first `count`
+// (observation, component) pairs in row-major order and the parameters they were evaluated with.
+int smg_debug_aux_free(smg_chain* ch, int count, double* llaux_out, double* centers_out, double* sigmas_out) {
+  if (!ch || count < 1 || (long long)count > (long long)ch->n * ch->m_aux) return fail(SMG_ERR_ARG, "bad argument");
+  if (ch->aux_mode != 1) return fail(SMG_ERR_ARG, "the chain was not created with aux_mode 1");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  SMG_CUDA(cudaStreamSynchronize(ch->st_aux));
+  ch->aux_ready = false;
+  const int buf = ch->aux_buf;
+  if (launch_aux_ll(ch, nullptr, ch->st, ch->iter, buf)) return SMG_ERR_CUDA;
+  if (llaux_out) SMG_CUDA(d2h_sync(llaux_out, ch->LLaux[buf], (size_t)count * 8, ch->st));
+  if (centers_out || sigmas_out) {
+    const int pp = ch->pp;
+    uint8_t* dc = nullptr;
+    double *ds = nullptr, *di = nullptr, *dd = nullptr;
+    if (dalloc(&dc, (size_t)count * pp) || dalloc(&ds, (size_t)count * pp) || dalloc(&di, (size_t)count * pp) ||
+        dalloc(&dd, (size_t)count * pp))
+      return SMG_ERR_CUDA;
+    RngKey key = mk_key(ch, SUB_AUX_FREE);
+    pool_draw_kernel<<<cdiv((long long)count * pp, 128), 128, 0, ch->st>>>(count, pp, ch->p, ch->attr, ch->v, ch->w, key,
+                                                                         ch->sigma_exact, dc, ds, di, dd);
+    ch->h_launches++;
+    SMG_CUDA(cudaGetLastError());
+    std::vector<uint8_t> hc((size_t)count * pp);
+    std::vector<double> hs((size_t)count * pp);
+    SMG_CUDA(d2h_sync(hc.data(), dc, hc.size(), ch->st));
+    SMG_CUDA(d2h_sync(hs.data(), ds, hs.size() * 8, ch->st));
+    for (int e = 0; e < count; e++)
+      for (int j = 0; j < ch->p; j++) {
+        if (centers_out) centers_out[(size_t)e * ch->p + j] = hc[(size_t)e * pp + j];
+        if (sigmas_out) sigmas_out[(size_t)e * ch->p + j] = hs[(size_t)e * pp + j];
+      }
+    void* ptrs[] = {dc, ds, di, dd};
+    for (void* q : ptrs) cudaFree(q);
+  }
+  return 0;
+}
+
+// sample_initial_assignment (common_functions.cpp:174-183) with the uniforms injected: c_i = (int)(L u_i + 1) - 1
+int smg_debug_initial_assignment(int n, int L, const double* u, int device, int* c_out) {
+  if (!u || !c_out || n < 1 || L < 1) return fail(SMG_ERR_ARG, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  SMG_CUDA(cudaSetDevice(device));
+  double* du = nullptr;
+  int* dc = nullptr;
+  SMG_CUDA(cudaMalloc(&du, (size_t)n * 8));
+  SMG_CUDA(cudaMalloc(&dc, (size_t)n * 4));
+  SMG_CUDA(cudaMemcpy(du, u, (size_t)n * 8, cudaMemcpyHostToDevice));
+  RngKey key{};
+  init_assign_kernel<<<cdiv(n, 256), 256>>>(n, L, du, key, dc);
+  SMG_CUDA(cudaGetLastError());
+  SMG_CUDA(cudaMemcpy(c_out, dc, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  cudaFree(du);
+  cudaFree(dc);
+  return 0;
+}
+
+// The MH ratio alone (split_merge.cpp:393-540) on an injected launch / proposal: no scan and no parameter draw runs, so
+// every addend depends only on the device's arithmetic of logprobgs_phi, logprobgs_c_i, loglikelihood_hamming, priors
+// and logdensity_hig -- the tests hold them to 1e-12 against the oracle's on the same (centres, sigmas, sides).
+int smg_debug_sm_terms(smg_chain* ch, const double* u_pair, const int* z_launch, const int* z_star, const double* phi6,
+                       double u_accept, int* info, double* terms) {
+  if (!ch || !u_pair || !z_launch || !z_star || !phi6) return fail(SMG_ERR_ARG, "NULL argument");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  int rc = sync_status(ch);
+  if (rc) return rc;
+  SmWork* W = ch->sm;
+  if (!W) return fail(SMG_ERR_ARG, "chain has no split-merge workspace");
+  const int n = ch->n, p = ch->p, pp = ch->pp, B = ch->NS, cur = ch->cur;
+  smg_sm_tape tp;
+  memset(&tp, 0, sizeof(tp));
+  tp.u_pair = u_pair;
+  tp.u_accept = &u_accept;
+  rc = sm_inject(ch, &tp);
+  if (rc) return rc;
+  SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, sizeof(int), ch->st));
+  sm_select_kernel<<<1, 1024, 0, ch->st>>>(n, ch->c, ch->K, W->u_pair, mk_key(ch, SUB_SM_SELECT), B, W->S, W->zState, W->info,
+                                           W->plan, W->cnt, W->terms, ch->pair_det);
+  ch->h_launches++;
+  SMG_CUDA(cudaGetLastError());
+  SmInfo I;
+  SMG_CUDA(d2h_sync(&I, W->info, sizeof(I), ch->st));
+  const size_t len = (size_t)pp * ch->mmax;
+  if (sm_hist(ch, W->zState, SH_S0, false, nullptr)) return SMG_ERR_CUDA;
+  sm_hist_add_kernel<<<sm_cdiv(len, 256), 256, 0, ch->st>>>((int)len, W->H, W->cnt, SH_S0, SH_S1, SH_M);
+  ch->h_launches++;
+  if (I.nS > 0) {
+    SMG_CUDA(h2d_sync(W->zL, z_launch, (size_t)I.nS * 4, ch->st));
+    SMG_CUDA(h2d_sync(W->zStar, z_star, (size_t)I.nS * 4, ch->st));
+  }
+  {  // the six parameter slots: split-launch A, B, merge-launch M, proposal A*, B*, M* (contiguous after the state slots)
+    std::vector<uint8_t> hc((size_t)6 * pp, 0);
+    std::vector<double> hs((size_t)6 * pp, 1.0);
+    for (int q = 0; q < 6; q++)
+      for (int j = 0; j < p; j++) {
+        hc[(size_t)q * pp + j] = (uint8_t)phi6[((size_t)q * 2 + 0) * p + j];
+        hs[(size_t)q * pp + j] = phi6[((size_t)q * 2 + 1) * p + j];
+      }
+    const size_t o = (size_t)(B + SM_SL_A) * pp;
+    SMG_CUDA(h2d_sync(ch->cen[cur] + o, hc.data(), hc.size(), ch->st));
+    SMG_CUDA(h2d_sync(ch->sig[cur] + o, hs.data(), hs.size() * 8, ch->st));
+    derive_terms_kernel<<<6, 256, 0, ch->st>>>(6, pp, p, ch->attr, ch->sig[cur] + o, ch->isg[cur] + o, ch->den + o,
+                                               ch->sden[cur] + B + SM_SL_A);
+    ch->h_launches++;
+    SMG_CUDA(cudaGetLastError());
+  }
+  if (sm_hist(ch, W->zL, SH_L0, false, nullptr)) return SMG_ERR_CUDA;
+  if (sm_hist(ch, W->zStar, SH_P0, false, nullptr)) return SMG_ERR_CUDA;
+  sm_gsphi_prior_kernel<<<6, 256, 0, ch->st>>>(pp, p, ch->mmax, ch->attr, ch->v, ch->w, W->H, W->cnt, W->plan, ch->cen[cur],
+                                               ch->sig[cur], W->terms);
+  sm_rowterms_kernel<<<sm_cdiv((long long)(n + 2) * 32, 256), 256, 0, ch->st>>>(
+      ch->X, pp, W->S, W->info, W->plan, W->zL, W->zStar, W->zState, W->cnt, ch->cen[cur], ch->isg[cur], ch->sden[cur],
+      W->rowvals, n + 2);
+  sm_rowreduce1_kernel<<<dim3(SM_RB, 4), 256, 0, ch->st>>>(W->info, W->rowvals, n + 2, W->partial);
+  sm_accept_kernel<<<1, 256, 0, ch->st>>>(W->info, W->plan, W->cnt, W->partial, ch->gamma, W->u_accept,
+                                          mk_key(ch, SUB_SM_ACCEPT), W->terms, ch->accepted_d, ch->stats_d);
+  ch->h_launches += 4;
+  SMG_CUDA(cudaGetLastError());
+  rc = sm_readback(ch, info, nullptr, nullptr, nullptr, nullptr, terms);
+  SMG_CUDA(cudaMemsetAsync(ch->accepted_d, 0, sizeof(int), ch->st));  // nothing was applied
+  return rc;
 }
 
 

@@ -72,7 +72,8 @@ enum SubPhase : uint32_t {
   SUB_SM_ACCEPT = 120,
   SUB_POOL = 121,
   SUB_INIT = 122,
-  SUB_INIT_PHI = 123
+  SUB_INIT_PHI = 123,
+  SUB_AUX_FREE = 124      // pool-free auxiliary components of a pass
 };
 
 // extra parameter slots (beyond the SMG_MAX_SLOTS scan slots) used by the split-merge step
@@ -85,7 +86,7 @@ struct SmWork;  // split-merge workspace (smg_sm.cuh)
 struct smg_chain {
   // ---- configuration (host copies)
   int n = 0, p = 0, pp = 0, mmax = 0, m_aux = 0, L = 1, t = 10, r = 10;
-  int neal8 = 0, split_merge = 1, n8_step = 1, sam_step = 1, thinning = 1, sigma_exact = 0;
+  int neal8 = 0, split_merge = 1, n8_step = 1, sam_step = 1, thinning = 1, sigma_exact = 0, pair_det = 0, aux_mode = 0;
   double gamma = 1.0;
   unsigned long long seed = 0;
   int Kcap = 192, NS = SMG_MAX_SLOTS, NST = SMG_MAX_SLOTS + smg::SM_NSLOTS, ldl = 192;
@@ -132,6 +133,7 @@ struct smg_chain {
   int *ltc_K = nullptr, *ltc_ctr = nullptr;
   double* LLaux[2] = {nullptr, nullptr};  // aux columns, double-buffered: [aux_buf] feeds the current pass
   int* aux_e[2] = {nullptr, nullptr};
+  double* aux_sd[2] = {nullptr, nullptr};  // pool-free mode: log-normaliser sums of the auxiliary components
   int aux_buf = 0;
   int* und_blk = nullptr;   // flagged rows per scan block
   uint8_t* und0 = nullptr;  // [n padded] precomputed screen flags of the allocation scan (scan_margin_kernel)

@@ -327,6 +327,65 @@ __global__ void mismatch_count_kernel(const uint8_t* __restrict__ X, int n, int 
   if (lane == 0) out[w] = acc;
 }
 
+// One prior draw (launcher.cpp:67-77: centre ~ U{1..m_j}, sigma ~ HIG(v_j, w_j, m_j)) of attribute j of entry e, a pure
+// function of (key, e, j): the stored pool (pool_draw_kernel) and the pool-free auxiliary components
+// (aux_ll_philox_kernel, and the scan when one of them becomes a cluster) evaluate the same code.
+__device__ __forceinline__ void prior_entry_attr(const RngKey& key, long long e, int j, int m, double v, double w,
+                                                 int sigma_exact, int* center_out, double* sigma_out) {
+  // 64-bit entry index split over the two counter words
+  uint32_t o[4];
+  philox4x32_10((uint32_t)e, (uint32_t)(e >> 32) | ((uint32_t)j << 8), U_POOL_CENTER | (key.sub << 8), key.sweep, key.k0,
+                key.k1, o);
+  const double uc = u01_from_bits(o[0], o[1]), us = u01_from_bits(o[2], o[3]);
+  int center = (int)((double)m * uc + 1.0);
+  if (center > m) center = m;
+  double uu;
+  if (sigma_exact) {
+    uu = hig_inv_u_d(us, v, w, (double)m);
+  } else {
+    RngKey k2 = key;
+    k2.sweep = key.sweep ^ ((uint32_t)(e >> 32) << 20);  // entries beyond 2^32 (never at the shapes in scope)
+    SubStream rs(k2, U_POOL_SIGMA, (uint32_t)e, (uint32_t)j);
+    uu = hig_draw_u_d(rs, v, w, (double)m);
+  }
+  *center_out = center;
+  *sigma_out = -1.0 / log(uu);
+}
+
+// Pool-free auxiliary components (smg_config.aux_mode == 1): the a-th auxiliary component of observation i in this
+// pass is the prior draw of the virtual entry e = i * m_aux + a under the pass's own Philox key -- fresh for every
+// observation and every pass, as Neal's Algorithm 8 states it, where the reference re-uses a stored pool of
+// n * m_aux draws for 1000 iterations (launcher.cpp:67-77,123-129; neal8.cpp:65-69).  Nothing is stored but the
+// column value and the entry's log-normaliser sum; the scan re-derives the parameters of the rare component that
+// becomes a cluster.  One warp per (i, a): a lane draws attributes lane, lane + 32, ...
+__global__ void __launch_bounds__(256) aux_ll_philox_kernel(const uint8_t* __restrict__ X, int n, int pp, int p, int m_aux,
+                                                            const int* __restrict__ attr, const double* __restrict__ v,
+                                                            const double* __restrict__ w, RngKey key, int sigma_exact,
+                                                            double* __restrict__ LLaux, int* __restrict__ aux_e,
+                                                            double* __restrict__ aux_sd) {
+  long long wi = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wi >= (long long)n * m_aux) return;
+  const int i = (int)(wi / m_aux);
+  const uint8_t* x = X + (size_t)i * pp;
+  double dot = 0.0, den = 0.0;
+  for (int j = lane; j < p; j += 32) {
+    const int m = attr[j];
+    int center;
+    double sigma;
+    prior_entry_attr(key, wi, j, m, v[j], w[j], sigma_exact, &center, &sigma);
+    if ((int)x[j] != center) dot += 1.0 / sigma;
+    den += hamming_den(sigma, m);
+  }
+  dot = warp_sum(dot);
+  den = warp_sum(den);
+  if (lane == 0) {
+    LLaux[wi] = -dot - den;
+    aux_e[wi] = (int)wi;
+    aux_sd[wi] = den;
+  }
+}
+
 // Auxiliary-component columns: for every observation i and aux slot a, draw the pool entry
 // (neal8.cpp:66: sample(pool_size,1)-1 = (int)(P*u+1)-1) and evaluate its log-likelihood.
 __global__ void __launch_bounds__(256) aux_ll_kernel(const uint8_t* __restrict__ X, int n, int pp, int m_aux,
@@ -381,6 +440,12 @@ struct ScanArgs {
   const double* pool_sig;
   const double* pool_isg;
   const double* pool_sden;
+  // pool-free auxiliary components (aux_mode 1): parameters re-derived from (aux_key, entry) when one becomes a cluster
+  int aux_free, p, sigma_exact;
+  RngKey aux_key;
+  const int* attr;
+  const double *hv, *hw;
+  const double* aux_sd;  // [n][m_aux] log-normaliser sums of the auxiliary components of this pass
   int* Kptr;      // in/out
   int* counts;    // in: by label; out: by slot
   int* slot2label;  // out [NS]
@@ -1178,12 +1243,24 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         // copy the auxiliary component's parameters into the new slot
         const int a = new_e - Kc;
         const long long e = A.aux_e[(size_t)ie * m + a];
-        for (int j = tid; j < pp; j += blockDim.x) {
-          A.cen[(size_t)new_slot * pp + j] = A.pool_cen[(size_t)e * pp + j];
-          A.sig[(size_t)new_slot * pp + j] = A.pool_sig[(size_t)e * pp + j];
-          A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
+        if (A.aux_free) {
+          for (int j = tid; j < pp; j += blockDim.x) {
+            int center = 0;
+            double sigma = 1.0;
+            if (j < A.p) prior_entry_attr(A.aux_key, e, j, A.attr[j], A.hv[j], A.hw[j], A.sigma_exact, &center, &sigma);
+            A.cen[(size_t)new_slot * pp + j] = (uint8_t)center;
+            A.sig[(size_t)new_slot * pp + j] = sigma;
+            A.isg[(size_t)new_slot * pp + j] = j < A.p ? 1.0 / sigma : 0.0;
+          }
+          if (tid == 0) A.sden[new_slot] = A.aux_sd[(size_t)ie * m + a];
+        } else {
+          for (int j = tid; j < pp; j += blockDim.x) {
+            A.cen[(size_t)new_slot * pp + j] = A.pool_cen[(size_t)e * pp + j];
+            A.sig[(size_t)new_slot * pp + j] = A.pool_sig[(size_t)e * pp + j];
+            A.isg[(size_t)new_slot * pp + j] = A.pool_isg[(size_t)e * pp + j];
+          }
+          if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
         }
-        if (tid == 0) A.sden[new_slot] = A.pool_sden[e];
         if (new_slot < A.ldl && ie + 1 < n) {
           // materialise the new column for every later observation, on the whole cluster
           if (tid == 0) {
@@ -1954,23 +2031,9 @@ __global__ void __launch_bounds__(128) pool_draw_kernel(long long pool_size, int
     return;
   }
   const int m = attr[j];
-  // 64-bit entry index split over the two counter words
-  uint32_t o[4];
-  philox4x32_10((uint32_t)e, (uint32_t)(e >> 32) | ((uint32_t)j << 8), U_POOL_CENTER | (key.sub << 8), key.sweep, key.k0,
-                key.k1, o);
-  double uc = u01_from_bits(o[0], o[1]), us = u01_from_bits(o[2], o[3]);
-  int center = (int)((double)m * uc + 1.0);
-  if (center > m) center = m;
-  double uu;
-  if (sigma_exact) {
-    uu = hig_inv_u_d(us, v[j], w[j], (double)m);
-  } else {
-    RngKey k2 = key;
-    k2.sweep = key.sweep ^ ((uint32_t)(e >> 32) << 20);  // entries beyond 2^32 (never at the shapes in scope)
-    SubStream rs(k2, U_POOL_SIGMA, (uint32_t)e, (uint32_t)j);
-    uu = hig_draw_u_d(rs, v[j], w[j], (double)m);
-  }
-  double sigma = -1.0 / log(uu);
+  int center;
+  double sigma;
+  prior_entry_attr(key, e, j, m, v[j], w[j], sigma_exact, &center, &sigma);
   pcen[t] = (uint8_t)center;
   psig[t] = sigma;
   pisg[t] = 1.0 / sigma;

@@ -56,7 +56,21 @@ struct SmWork {
 #define SM_RB 256  // partial-sum blocks of the row reductions
 
 // sample(indices, 2, replace=false) (split_merge.cpp:275): j1=(int)(n*u0); j2=(int)((n-1)*u1) over the swapped array
-__device__ __forceinline__ void sm_pick_pair(int n, const double* u_pair, const RngKey& key, int* i1, int* i2) {
+// det != 0: select_observations_deterministic (split_merge.cpp:227-261) -- i_1 walks over the observations (iteration
+// mod n), i_2 = sample(indexes, 1, false)[0] = (int)(n u), redrawn while it equals i_1 (injected uniforms: the first two)
+__device__ __forceinline__ void sm_pick_pair(int n, const double* u_pair, const RngKey& key, int* i1, int* i2, int det = 0) {
+  if (det) {
+    const int a = (int)(key.sweep % (uint32_t)n);
+    int b = a;
+    for (uint32_t k = 0; k < 4096u && b == a; k++) {
+      const double u = get_u(k < 2u ? u_pair : nullptr, k, key, U_SM_PAIR, k, 0u);
+      b = (int)((double)n * u);
+      if (b >= n) b = n - 1;
+    }
+    *i1 = a;
+    *i2 = b;
+    return;
+  }
   const double u0 = get_u(u_pair, 0, key, U_SM_PAIR, 0u, 0u), u1 = get_u(u_pair, 1, key, U_SM_PAIR, 1u, 0u);
   int j1 = (int)((double)n * u0);
   if (j1 >= n) j1 = n - 1;
@@ -107,13 +121,13 @@ __device__ __forceinline__ void sm_fill_info_plan(SmInfo* info, SmPlan* plan, in
 __global__ void __launch_bounds__(1024) sm_select_kernel(int n, const int* __restrict__ c, const int* __restrict__ Kptr,
                                                          const double* u_pair, RngKey key, int NS, int* __restrict__ S,
                                                          int* __restrict__ zState, SmInfo* info, SmPlan* plan,
-                                                         int* __restrict__ cnt, double* terms) {
+                                                         int* __restrict__ cnt, double* terms, int pair_det) {
   __shared__ int s_i1, s_i2, s_cA, s_cB, s_tot;
   __shared__ int s_wcnt[32], s_woff[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     int i1, i2;
-    sm_pick_pair(n, u_pair, key, &i1, &i2);
+    sm_pick_pair(n, u_pair, key, &i1, &i2, pair_det);
     s_i1 = i1;
     s_i2 = i2;
     s_cA = c[i1];
@@ -1010,6 +1024,7 @@ struct SmChainArgs {
   PhiArgs phi;  // common fields of the parameter updates (jobs are filled on the device)
   const double *u_rg, *u_rg_c, *u_rg_s, *u_mg_c, *u_mg_s;  // injected uniforms (bases) or null
   const double *u_pair, *u_prior_c, *u_prior_s, *u_launch, *u_accept;
+  int pair_det;  // 1: select_observations_deterministic
   RngKey key;
   unsigned* bar;       // grid-barrier counter of this launch (zero on entry)
   unsigned* bar_next;  // the counter of the next launch: zeroed here
@@ -1067,7 +1082,7 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     RngKey k = A.key;
     k.sub = SUB_SM_SELECT;
     int i1, i2;
-    sm_pick_pair(n, A.u_pair, k, &i1, &i2);
+    sm_pick_pair(n, A.u_pair, k, &i1, &i2, A.pair_det);
     s_sel[0] = i1;
     s_sel[1] = i2;
     s_sel[2] = A.c[i1];

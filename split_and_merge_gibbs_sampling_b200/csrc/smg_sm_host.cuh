@@ -243,6 +243,7 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.u_prior_s = T.u_prior_s;
     CA.u_launch = T.u_launch;
     CA.u_accept = T.u_accept;
+    CA.pair_det = ch->pair_det;
     CA.wide_from = sm_wide_from();
     CA.X = ch->X;
     CA.S = W->S;
@@ -357,7 +358,7 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
   }
   // ---- pair, S, plan
   sm_select_kernel<<<1, 1024, 0, ch->st>>>(n, ch->c, ch->K, T.u_pair, mk_key(ch, SUB_SM_SELECT), B, W->S, W->zState,
-                                           W->info, W->plan, W->cnt, W->terms);
+                                           W->info, W->plan, W->cnt, W->terms, ch->pair_det);
   ch->h_launches++;
   SMG_CUDA(cudaGetLastError());
   // ---- histograms of the current-state sides and of the merged cluster (fixed for the whole proposal)

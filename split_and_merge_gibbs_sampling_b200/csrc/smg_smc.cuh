@@ -49,7 +49,7 @@ struct SmcArgs {
 };
 
 struct SmcLayout {
-  size_t T, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, total;
+  size_t T, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, lst, total;
   int rstr;  // member stride of the transposed rows (odd: conflict-free both by member and by word)
 };
 __host__ __device__ inline size_t smc_al(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -76,6 +76,7 @@ __host__ __device__ inline SmcLayout smc_layout(int pp, int mmax, int TL, int CS
   L.cenv = o, o = smc_al(o + (size_t)3 * pp);
   L.cenS = o, o = smc_al(o + (size_t)3 * sl);
   L.z = o, o = smc_al(o + (size_t)2 * mcap);
+  L.lst = o, o = smc_al(o + (size_t)2 * rcap);
   L.total = o;
   return L;
 }
@@ -350,6 +351,8 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   uint8_t* cenS = smc_raw + L.cenS;                             // [3][sl]
   uint8_t* zc = smc_raw + L.z;                                  // [mcap] side (launch, then proposal)
   uint8_t* zn = zc + mcap;                                      // [mcap] side decided by the scan in progress
+  unsigned short* lst = reinterpret_cast<unsigned short*>(smc_raw + L.lst);  // [rcap] cached members that need the table
+  __shared__ int s_nlist;
   __shared__ double sh[256];
   __shared__ int s_sel[8];
   __shared__ int s_wa[SMC_WARPS], s_wb[SMC_WARPS], s_tot[4];
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     RngKey k = A.key;
     k.sub = SUB_SM_SELECT;
     int i1, i2;
-    sm_pick_pair(n, A.u_pair, k, &i1, &i2);
+    sm_pick_pair(n, A.u_pair, k, &i1, &i2, A.pair_det);
     s_sel[0] = i1;
     s_sel[1] = i2;
     s_sel[2] = A.c[i1];
@@ -594,11 +597,27 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
         A.lgt[pos0 + m] = v;
     }
   };
-  // member CTAs: look-up table of the two sides' parameters (cenv / isgv rows 0, 1) and their constant term
+  // member CTAs: constants of the two sides' parameters (cenv / isgv rows 0, 1) -- the difference of their log-normaliser
+  // sums and the range of 1/sigma on each side -- and, on demand, the look-up table T[j][a]
   double sdBA = 0.0;  // sden_B - sden_A
-  auto build_table = [&]() {
+  double wAmin = 0.0, wAmax = 0.0, wBmin = 0.0, wBmax = 0.0;
+  auto side_consts = [&]() {
     const double a = lane < nP ? sdpart[0 * SMC_MAXCS + lane] : 0.0, b = lane < nP ? sdpart[1 * SMC_MAXCS + lane] : 0.0;
     sdBA = warp_sum(b) - warp_sum(a);
+    double amin = 1e300, amax = 0.0, bmin = 1e300, bmax = 0.0;
+    for (int j = lane; j < p; j += 32) {
+      const double wa = isgv[j], wb = isgv[pp + j];
+      amin = fmin(amin, wa), amax = fmax(amax, wa);
+      bmin = fmin(bmin, wb), bmax = fmax(bmax, wb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      amin = fmin(amin, shfl_xor_d(amin, o)), amax = fmax(amax, shfl_xor_d(amax, o));
+      bmin = fmin(bmin, shfl_xor_d(bmin, o)), bmax = fmax(bmax, shfl_xor_d(bmax, o));
+    }
+    wAmin = amin, wAmax = amax, wBmin = bmin, wBmax = bmax;
+  };
+  auto build_table = [&]() {
     const int tls = 31 - __clz(TL);  // log2(TL)
     for (int e = tid; e < pp * TL; e += SMC_T) {
       const int j = e >> tls, av = e & (TL - 1);
@@ -612,7 +631,8 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   };
   if (isM) {
     if (A.t > 0) fill_logits(0);
-    build_table();
+    side_consts();
+    if (tid == 0) s_nlist = 0;
     __syncthreads();
   }
   SMC_TICK(6);
@@ -670,14 +690,59 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       if (!isM && do_mg) mg_job();
       continue;
     }
-    int dsum = 0, nnr_tot = 0, nnr_mine = 0, extra = 0;
+    int dsum = 0, nnr_tot = 0, nnr_mine = 0, extra = 0, cta_changed = 0, any_changed = 0;
     if (isM) {
       // ---- P1: likelihood differences by table look-up (one thread per member), count-free decisions
       const double dc_max = nS > 0 ? sm_dc_bound(nS, 1) + SM_DC_MARGIN : 0.0;
       const double dc_min = nS > 0 ? sm_dc_bound(nS, nS) - SM_DC_MARGIN : 0.0;
       const unsigned Tb = (unsigned)__cvta_generic_to_shared(T);
       const int tsh = 31 - __clz(TL) + 3;  // log2(TL * 8): byte stride of an attribute's table row
-      for (int m = tid; m < ndec; m += SMC_T) {
+      // (a) screen: with mA / mB mismatches against the two centres,
+      //       mB min(1/sigma_B) - mA max(1/sigma_A)  <=  LL_A - LL_B - (sden_B - sden_A)  <=  mB max(1/sigma_B) - mA min(1/sigma_A);
+      //     a member whose decision is the same at both ends of that range (and of the count term's) is decided from two
+      //     integer counts -- once the launch state has settled that is every member.  The others are listed.
+      const uint32_t* cwA = reinterpret_cast<const uint32_t*>(cenv);
+      const uint32_t* cwB = reinterpret_cast<const uint32_t*>(cenv + pp);
+      const int nscr = min(ndec, rcap);
+      for (int m0 = 0; m0 < nscr; m0 += SMC_T) {
+        const int m = m0 + tid;
+        bool listed = false;
+        if (m < nscr) {
+          const uint32_t* xr = rowsT + m;
+          int cA4 = 0, cB4 = 0;
+#pragma unroll 8
+          for (int w = 0; w < words; w++) {
+            const uint32_t xw = xr[(size_t)w * RSTR];
+            cA4 += __popc(__vcmpne4(xw, cwA[w]));
+            cB4 += __popc(__vcmpne4(xw, cwB[w]));
+          }
+          const double mA = (double)(cA4 >> 3), mB = (double)(cB4 >> 3);
+          const double slack = 1e-9 * (mA * wAmax + mB * wBmax) + 1e-9;
+          const double d_lo = mB * wBmin - mA * wAmax + sdBA - slack, d_hi = mB * wBmax - mA * wAmin + sdBA + slack;
+          const double lgm = lg[m];
+          const int rlo = sm_d_region(dc_min + d_lo, lgm), rhi = sm_d_region(dc_max + d_hi, lgm);
+          if (rlo == rhi)
+            zn[m] = (uint8_t)(~rlo & 1);
+          else
+            listed = true;
+        }
+        const unsigned bal = __ballot_sync(SMG_FULL, listed);
+        if (bal) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_nlist, __popc(bal));
+          base = __shfl_sync(SMG_FULL, base, 0);
+          if (listed) lst[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)m;
+        }
+      }
+      __syncthreads();
+      const int nlist = s_nlist;
+      const bool need_table = nlist > 0 || ndec > rcap;
+      if (need_table) build_table();
+      __syncthreads();
+      if (tid == 0) s_nlist = 0;
+      // (b) the listed members and the ones whose rows are not cached: LL_A - LL_B by table look-up
+      for (int k = tid; k < nlist + max(0, ndec - rcap); k += SMC_T) {
+        const int m = k < nlist ? (int)lst[k] : rcap + (k - nlist);
         double acc[4] = {0.0, 0.0, 0.0, 0.0};
         if (m < rcap) {
           const uint32_t* xr = rowsT + m;
@@ -714,7 +779,10 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       SMC_TICK(7);
       // ordered pass over the own members: side-1 change of the decided ones, list of the undecided ones (by position)
       int carry_d = 0, carry_n = 0;
-      for (int base = 0; base < ndec; base += SMC_T) {
+      int chg = 0;
+      for (int m = tid; m < ndec; m += SMC_T) chg |= (zn[m] != zc[m]);
+      cta_changed = __syncthreads_or(chg);
+      for (int base = 0; cta_changed && base < ndec; base += SMC_T) {
         const int m = base + tid;
         const bool valid = m < ndec;
         const int znm = valid ? zn[m] : 0, zcm = valid ? zc[m] : 0;
@@ -771,6 +839,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       if (tid < CS) {
         smc_st_s32(smc_map(xchg + (par * SMC_MAXCS + rank) * 4 + 0, tid), carry_d);
         smc_st_s32(smc_map(xchg + (par * SMC_MAXCS + rank) * 4 + 1, tid), carry_n);
+        smc_st_s32(smc_map(xchg + (par * SMC_MAXCS + rank) * 4 + 2, tid), cta_changed);
       }
       SMC_TICK(8);
       smc_sync();  // (1) decisions that do not depend on the counts
@@ -787,6 +856,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       const int v = xchg[(par * SMC_MAXCS + r) * 4 + 1];
       nnr_tot += v;
       if (r == rank) nnr_mine = v;
+      any_changed |= xchg[(par * SMC_MAXCS + r) * 4 + 2];
     }
     if (nnr_tot > 0) {
       // ---- the members whose decision depends on the running counts: ordered walk on CTA 0 (split_merge.cpp:186-216
@@ -860,7 +930,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
 #endif
     if (isM) {
       // ---- P2: move the rows of the members that changed side between the two side histograms (a warp per mover)
-      for (int base = warp * 32; base < ndec; base += SMC_T) {
+      for (int base = warp * 32; cta_changed && base < ndec; base += SMC_T) {
         const int m = base + lane;
         const bool mv = m < ndec && zn[m] != zc[m];
         unsigned bal = __ballot_sync(SMG_FULL, mv);
@@ -881,14 +951,13 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       SMC_TICK(13);
       smc_wait();  // (3) parameters of the two sides
       SMC_TICK(16);
-      build_table();
-      __syncthreads();
+      side_consts();
       SMC_TICK(6);
     } else {
       smc_sync();  // (2)
       SMC_TICK(12);
       // ---- P3: parameter updates of the two sides on this CTA's attributes
-      reduce_slices(phl, prop ? SH_P0 : SH_L0, prop);
+      if (prop || it == 0 || any_changed) reduce_slices(phl, prop ? SH_P0 : SH_L0, prop);  // else: nobody moved
       if (prop && kP == 0 && tid == 0) {
         A.cnt[SH_P0] = nS + 2 - nBcur;
         A.cnt[SH_P1] = nBcur;

@@ -17,11 +17,11 @@ llp = C.POINTER(C.c_longlong)
 
 class Opts(C.Structure):
     _fields_ = [("counted", C.c_int), ("stable_hig", C.c_int), ("sigma_inverse_cdf", C.c_int), ("bisect_tol", C.c_double),
-                ("bisect_max", C.c_int), ("validate", C.c_int)]
+                ("bisect_max", C.c_int), ("validate", C.c_int), ("det_i1", C.c_int)]
 
 
-def opts(counted=0, stable_hig=0, sigma_inverse_cdf=0, bisect_tol=1e-9, bisect_max=150, validate=1):
-    return Opts(counted, stable_hig, sigma_inverse_cdf, bisect_tol, bisect_max, validate)
+def opts(counted=0, stable_hig=0, sigma_inverse_cdf=0, bisect_tol=1e-9, bisect_max=150, validate=1, det_i1=-1):
+    return Opts(counted, stable_hig, sigma_inverse_cdf, bisect_tol, bisect_max, validate, det_i1)
 
 
 class Data(C.Structure):
@@ -63,6 +63,7 @@ def lib():
         L.orc_revsort.argtypes = [dp, ip, C.c_int]
         L.orc_sample_probs_one.restype = C.c_int
         L.orc_sample_probs_one.argtypes = [dp, C.c_int, C.c_double, ip]
+        L.orc_initial_assignment.argtypes = [C.c_int, C.c_int, dp, ip]
         L.orc_rhig_many.argtypes = [C.c_double] * 3 + [C.c_long, C.c_ulonglong, C.POINTER(Opts), dp]
         L.orc_rhig_u_from_omega.argtypes = [C.c_double] * 3 + [C.c_long, dp, C.POINTER(Opts), dp]
         L.orc_rbeta_many.argtypes = [C.c_double, C.c_double, C.c_long, C.c_ulonglong, dp]
@@ -226,6 +227,15 @@ def split_merge(d, t, r, c, center, sigma, tape, o=None, kcap=None, log_cap=1 <<
             "star": {"K": int(info[7]), "c": c_st, "center": ce_st, "sigma": sg_st},
             "terms": terms, "consumed": consumed.value,
             "log": {"phase": lph[:nl], "site": ls[:nl], "a": la[:nl], "b": lb_[:nl], "u": lu[:nl]}}
+
+
+def initial_assignment(L, tape):
+    """sample_initial_assignment (common_functions.cpp:174-183) from a uniform tape."""
+    tp = np.ascontiguousarray(tape, dtype=np.float64)
+    out = np.zeros(tp.size, dtype=np.int32)
+    if lib().orc_initial_assignment(int(L), tp.size, P(tp), P(out, ip)):
+        raise OracleError("initial_assignment failed")
+    return out
 
 
 def draw_pool(d, pool_size, seed, o=None):

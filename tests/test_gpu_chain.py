@@ -140,3 +140,45 @@ def test_run_markov_chain_equals_stepwise_chain_on_a_large_matrix():
     from split_and_merge_gibbs_sampling_b200 import SmgError
     with pytest.raises(SmgError):
         run_markov_chain(bad, pb.attr, pb.gamma, pb.v, pb.w, iterations=1, burnin=0, c_i=pb.labels, seed=1, **kw)
+
+
+def test_posterior_summaries_match_oracle_at_the_metric_shape():
+    """north_star: 'matching posterior summaries' -- K-posterior, ARI, log-likelihood and the PSM of whole chains
+    (launcher.cpp:85-154: Neal-8 + update_phi + split-merge every iteration) against the counted oracle at the metric's
+    attribute shape (p=256, 5 levels, 3 auxiliaries) over 5 seeds, from L=20 random labels."""
+    from sklearn.metrics import adjusted_rand_score
+    from split_and_merge_gibbs_sampling_b200 import run_markov_chain
+    n, p, kt = 3000, 256, 12
+    pb = Problem(n, p, 5, kt, seed=77, s=1.3)
+    Xd = pb.X.astype(np.float64)
+    o = orc.opts(counted=1, stable_hig=1)
+    its, burn = 30, 30
+    sub = np.arange(0, n, 7)  # PSM on a row subsample: 429 x 429
+    G = {"K": [], "ll": [], "ari": []}
+    Cc = {"K": [], "ll": [], "ari": []}
+    psm_g = np.zeros((sub.size, sub.size))
+    psm_c = np.zeros((sub.size, sub.size))
+    for seed in range(1, 6):
+        res = run_markov_chain(Xd, pb.attr, pb.gamma, pb.v, pb.w, m=3, iterations=its, L=20, burnin=burn, t=5, r=5,
+                               neal8=True, split_merge=True, seed=seed)
+        G["K"].append(np.mean(res["total_cls"]))
+        G["ll"].append(np.mean(res["loglikelihood"]))
+        G["ari"].append(adjusted_rand_score(pb.labels, res["final_ass"]))
+        cg = np.asarray(res["c_i"])[:, sub]
+        psm_g += (cg[:, :, None] == cg[:, None, :]).mean(0)
+        r = orc.run_chain(pb.od, 3, its, 20, None, burn, 5, 5, True, True, seed=seed, o=o)
+        Cc["K"].append(np.mean(r["total_cls"]))
+        Cc["ll"].append(np.mean(r["loglikelihood"]))
+        Cc["ari"].append(adjusted_rand_score(pb.labels, r["final_ass"]))
+        cc = np.asarray(r["c_i"])[:, sub]
+        psm_c += (cc[:, :, None] == cc[:, None, :]).mean(0)
+
+    def close(a, b, floor):
+        se = np.sqrt(np.var(a, ddof=1) / len(a) + np.var(b, ddof=1) / len(b))
+        return abs(np.mean(a) - np.mean(b)) <= 3 * se + floor
+    assert close(G["K"], Cc["K"], 0.5), (G["K"], Cc["K"])
+    assert close(G["ll"], Cc["ll"], 1e-3 * abs(np.mean(Cc["ll"]))), (G["ll"], Cc["ll"])
+    assert close(G["ari"], Cc["ari"], 0.02), (G["ari"], Cc["ari"])
+    assert np.mean(G["ari"]) > 0.9 and np.mean(Cc["ari"]) > 0.9
+    # PSM averaged over the seeds: mean absolute difference of the co-clustering probabilities
+    assert np.mean(np.abs(psm_g - psm_c)) / 5 < 0.02

@@ -188,3 +188,80 @@ def test_merge_acceptance_is_patched_too():
             assert np.array_equal(a["c_i"], b["c_i"])
         return
     pytest.fail("no seed produced an accepted merge")
+
+
+def test_pool_free_auxiliary_components():
+    """aux_mode='philox' (north_star item 1: auxiliary columns from per-observation Philox streams): every auxiliary
+    component is a fresh prior draw (launcher.cpp:67-77 law: centre ~ U{1..m_j}, sigma ~ HIG(v_j,w_j,m_j)) -- the column
+    values are the Hamming log-likelihood of those parameters (1e-12), centres are uniform, sigmas follow the HIG prior
+    (KS), entries differ between observations and between passes, and no n*m*p pool is allocated."""
+    from scipy import special, stats
+    pb = Problem(1500, 48, 4, 5, seed=91, s=0.9)
+    ch = pb.chain(L=6, c_i=None, compact_init=True, seed=5, aux_mode="philox")
+    cnt = 1500 * 3
+    ll, cen, sig = ch.aux_free(cnt)
+    # column value = -sum_j [x != c]/sigma - sum_j log(1 + (m-1) exp(-1/sigma))  of observation w // 3
+    X = pb.X[np.arange(cnt) // 3].astype(np.float64)
+    ref = -np.sum((X != cen) / sig, axis=1) - np.sum(np.log1p((pb.attr[None, :] - 1.0) * np.exp(-1.0 / sig)), axis=1)
+    assert np.max(np.abs(ll - ref) / np.abs(ref)) < 1e-12
+    assert cen.min() == 1 and cen.max() == 4
+    freq = np.bincount(cen.astype(int).ravel(), minlength=5)[1:] / cen.size
+    assert np.max(np.abs(freq - 0.25)) < 0.01
+    v, w, m = 6.0, 0.25, 4.0
+    u = np.exp(-1.0 / sig.ravel()[:20000])
+    a, b, xmax = w + 1.0, v - 1.0, (m - 1.0) / m
+
+    def cdf(uu):
+        x = uu * (m - 1) / (1 + uu * (m - 1))
+        return special.betainc(a, b, x) / special.betainc(a, b, xmax)
+    assert stats.kstest(u, cdf).pvalue > 1e-3
+    assert len(np.unique(sig[:, 0])) == cnt  # a fresh draw per (observation, component)
+    ch.step(1)
+    ll2, cen2, sig2 = ch.aux_free(cnt)
+    assert not np.array_equal(sig2, sig)  # and per pass
+    for _ in range(6):
+        ch.step(1)
+        _check_snapshot(pb, ch.snapshot())
+    with pytest.raises(Exception):
+        ch.set_pool(np.ones((4, pb.p)), np.ones((4, pb.p)))
+    ch.close()
+    # same seed, same chain
+    a1 = pb.chain(L=6, c_i=None, compact_init=True, seed=5, aux_mode="philox")
+    a2 = pb.chain(L=6, c_i=None, compact_init=True, seed=5, aux_mode="philox")
+    a1.step(5)
+    a2.step(5)
+    s1, s2 = a1.snapshot(), a2.snapshot()
+    assert np.array_equal(s1["c_i"], s2["c_i"]) and s1["loglikelihood"] == s2["loglikelihood"]
+    a1.close()
+    a2.close()
+
+
+def test_pool_free_and_pool_modes_agree_in_distribution():
+    """Same target distribution: K, log-likelihood and ARI of chains with pool-free auxiliary components against the
+    stored-pool mode over 6 seeds (noisy data, so that births from auxiliary components do happen)."""
+    from sklearn.metrics import adjusted_rand_score
+    pb = Problem(1000, 32, 4, 4, seed=93, s=1.0)
+    out = {"pool": {"K": [], "ll": [], "ari": [], "births": 0}, "philox": {"K": [], "ll": [], "ari": [], "births": 0}}
+    for mode in out:
+        for seed in range(1, 7):
+            ch = pb.chain(L=8, c_i=None, compact_init=True, seed=seed, aux_mode=mode, t=3, r=3)
+            ch.step(40)
+            Ks, lls = [], []
+            for _ in range(80):
+                ch.step(1)
+                s = ch.snapshot(with_phi=False)
+                Ks.append(s["K"])
+                lls.append(s["loglikelihood"])
+            out[mode]["K"].append(np.mean(Ks))
+            out[mode]["ll"].append(np.mean(lls))
+            out[mode]["ari"].append(adjusted_rand_score(pb.labels, s["c_i"]))
+            out[mode]["births"] += ch.stats()["births"]
+            ch.close()
+    assert out["pool"]["births"] > 20 and out["philox"]["births"] > 20
+
+    def close(a, b, floor):
+        se = np.sqrt(np.var(a, ddof=1) / len(a) + np.var(b, ddof=1) / len(b))
+        return abs(np.mean(a) - np.mean(b)) <= 3 * se + floor
+    assert close(out["pool"]["K"], out["philox"]["K"], 0.75), out
+    assert close(out["pool"]["ll"], out["philox"]["ll"], 15.0), out
+    assert close(out["pool"]["ari"], out["philox"]["ari"], 0.03), out

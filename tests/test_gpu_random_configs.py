@@ -36,11 +36,10 @@ def _one(case_seed):
     ch.validate_state()
     ch.close()
     desc = dict(n=n, p=p, m=m, k=k, m_aux=m_aux, s=s, mode=mode, L=L, pool=pool)
-    if ref["exact_pos_ties"] == 0:
-        assert got["K"] == ref["K"], desc
-        assert np.array_equal(got["c_i"], ref["c"]), desc
-        assert np.array_equal(got["centers"], ref["center"]), desc
-        assert np.array_equal(got["sigmas"], ref["sigma"]), desc
+    assert got["K"] == ref["K"], desc
+    assert np.array_equal(got["c_i"], ref["c"]), desc
+    assert np.array_equal(got["centers"], ref["center"]), desc
+    assert np.array_equal(got["sigmas"], ref["sigma"]), desc
     return desc
 
 

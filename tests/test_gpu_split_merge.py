@@ -223,3 +223,93 @@ def test_split_merge_large_member_set(seed, mode):
     ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=3, r=2, mode=mode)
     assert ref["S"].size > 2048
     check_case(pb, ref, got, after, labA, labB)
+
+
+def _phi6_from_oracle(ref, p):
+    """(centre, sigma) of split-launch A, B, merge-launch M, proposal A*, B*, M* out of the oracle's three states."""
+    phi = np.zeros((6, 2, p))
+    phi[:, 0, :] = 1.0
+    phi[:, 1, :] = 1.0
+    i1, i2 = ref["i1"], ref["i2"]
+    SL, ML, st = ref["SL"], ref["ML"], ref["star"]
+    for q, (stt, lab) in enumerate([(SL, SL["c"][i1]), (SL, SL["c"][i2]), (ML, ML["c"][i2])]):
+        phi[q, 0], phi[q, 1] = stt["center"][lab], stt["sigma"][lab]
+    if ref["is_split"]:
+        phi[3, 0], phi[3, 1] = st["center"][st["c"][i1]], st["sigma"][st["c"][i1]]
+        phi[4, 0], phi[4, 1] = st["center"][st["c"][i2]], st["sigma"][st["c"][i2]]
+    else:
+        phi[5, 0], phi[5, 1] = st["center"][st["c"][i2]], st["sigma"][st["c"][i2]]
+    return phi
+
+
+@pytest.mark.parametrize("seed", list(range(1, 13)))
+def test_mh_terms_alone_at_1e12(seed):
+    """a19-a24 in isolation (split_merge.cpp:393-540): the oracle's launch / proposal states (sides, centres, sigmas) are
+    injected, so no device draw feeds the addends; every addend within 1e-12 relative, the decision identical."""
+    pb = Problem(600, 24, 4, 6, seed=100 + seed, s=0.6)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    if seed % 2 == 0:
+        c = (c % 3).astype(np.int32)
+        K, cen, sig = 3, cen[:3].copy(), sig[:3].copy()
+    t = r = 3
+    rng = np.random.default_rng(seed)
+    tape = (rng.integers(0, 2**53, size=50 + (t + 3) * pb.n + (2 * t + r + 12) * 2 * pb.p).astype(np.float64) + 0.5) / 2.0**53
+    o = orc.opts(counted=1, stable_hig=1, sigma_inverse_cdf=1, bisect_tol=0.0)
+    ref = orc.split_merge(pb.od, t, r, c, cen, sig, tape, o=o)
+    T, _, _ = build_gpu_tape(ref["log"], pb.n, pb.p, t, r, ref, c)
+    S = ref["S"]
+    zl = (ref["SL"]["c"][S] != ref["SL"]["c"][ref["i1"]]).astype(np.int32)
+    zs = (ref["star"]["c"][S] != ref["star"]["c"][ref["i1"]]).astype(np.int32) if ref["is_split"] else np.zeros(S.size, np.int32)
+    ch = pb.chain(t=t, r=r)
+    ch.set_state(K, c, cen, sig)
+    got = ch.sm_terms(T["u_pair"], zl, zs, _phi6_from_oracle(ref, pb.p), float(T["u_accept"][0]))
+    after = ch.snapshot()
+    ch.close()
+    assert (got["i1"], got["i2"], got["nS"], got["is_split"]) == (ref["i1"], ref["i2"], S.size, ref["is_split"])
+    tr, tg = ref["terms"], got["terms"]
+    names = ["log_alpha", "lg0", "lg1", "lg2", "pri0", "pri1", "pri2", "ll0", "ll1", "ll2", "gs_phi0", "gs_phi1", "gs_phi2",
+             "gs_c", "log_prior", "log_lik", "log_prop"]
+    for k, nm in enumerate(names):
+        # the prior / parameter-density terms are sums of p per-attribute log-densities of order one that partly cancel:
+        # 1e-12 of the term or of p (the size of the sum of their magnitudes), whichever is larger
+        scale = max(abs(tr[k]), float(pb.p) if nm.startswith(("pri", "gs_phi")) or nm in ("log_prior", "log_prop") else 1.0)
+        assert abs(tg[k] - tr[k]) <= 1e-12 * scale, (nm, tg[k], tr[k])
+    # the ratio is a difference of the addends above: 1e-12 of the largest of them
+    assert abs(tg[17] - tr[17]) <= 1e-12 * np.max(np.abs(tr[:17]))
+    assert tg[18] == tr[18]
+    assert got["accepted"] == ref["accepted"]
+    assert after["K"] == K and np.array_equal(after["c_i"], c)  # nothing applied
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("seed,iteration", [(1, 0), (2, 7), (3, 601), (4, 1234)])
+def test_deterministic_pair_selection_matches_oracle(seed, iteration, mode):
+    """select_observations_deterministic (split_merge.cpp:227-261): i_1 walks over the observations (iteration mod n),
+    i_2 = (int)(n u) redrawn while equal to i_1; the rest of the proposal as usual."""
+    import os
+    os.environ["SMG_SM_MODE"] = mode
+    pb = Problem(600, 24, 4, 6, seed=300 + seed, s=0.6)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    if seed % 2 == 0:
+        c = (c % 3).astype(np.int32)
+        K, cen, sig = 3, cen[:3].copy(), sig[:3].copy()
+    t = r = 2
+    i1 = iteration % pb.n
+    rng = np.random.default_rng(seed)
+    tape = (rng.integers(0, 2**53, size=50 + (t + 3) * pb.n + (2 * t + r + 12) * 2 * pb.p).astype(np.float64) + 0.5) / 2.0**53
+    if seed == 3:
+        tape[0] = (i1 + 0.5) / pb.n  # the first draw of i_2 hits i_1: the reference redraws
+    o = orc.opts(counted=1, stable_hig=1, sigma_inverse_cdf=1, bisect_tol=0.0, det_i1=i1)
+    ref = orc.split_merge(pb.od, t, r, c, cen, sig, tape, o=o)
+    assert ref["i1"] == i1 and ref["i2"] != i1
+    T, labA, labB = build_gpu_tape(ref["log"], pb.n, pb.p, t, r, ref, c)
+    assert T["u_pair"].size == (2 if seed == 3 else 1)
+    T["u_pair"] = np.concatenate([T["u_pair"], [0.5]])[:2]
+    ch = pb.chain(t=t, r=r, pair_selection="deterministic")
+    ch.set_state(K, c, cen, sig)
+    lb_check = ch.lib.smg_resume_at(ch.h, int(iteration))
+    assert lb_check == 0
+    got = ch.split_merge(T)
+    after = ch.snapshot()
+    ch.close()
+    check_case(pb, ref, got, after, labA, labB)
