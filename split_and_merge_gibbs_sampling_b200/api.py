@@ -200,8 +200,8 @@ class Chain:
         lb.check(self.lib.smg_debug_sm_profile(self.h, out.ctypes.data_as(lb.c_ull_p)))
         names = {0: "select+prior", 1: "bar_a", 2: "S_write", 3: "bar_b", 4: "members+rows+hist", 5: "bar_c", 6: "table",
                  7: "dots|mg_draws", 8: "compact", 9: "bar1", 10: "walk", 11: "moves", 12: "bar2", 13: "logits|slices",
-                 14: "draws", 16: "bar3", 17: "tail", 18: "bar_f", 19: "mh_load", 20: "mh_terms", 21: "bar_h", 22: "mh_sums",
-                 23: "bar_i", 24: "accept"}
+                 14: "draws", 15: "mg_draws", 16: "bar3", 17: "tail", 18: "bar_f", 19: "mh_load", 20: "mh_terms", 21: "bar_h", 22: "mh_sums",
+                 23: "bar_i", 24: "accept", 25: "#scans_with_walk", 26: "#scans_with_change", 27: "#scans", 28: "#listed_cta0"}
         keys = {k: "M." + v for k, v in names.items()}
         keys.update({32 + k: "P." + v for k, v in names.items()})
         keys.update({50: "D.entry", 51: "D.philox", 52: "D.centre", 53: "D.sigma", 54: "D.tail", 55: "D.publish"})
@@ -387,6 +387,18 @@ class Psm:
         lb.check(self.lib.smg_psm_info(self.h, C.byref(sw), C.byref(ms), C.byref(nl)))
         return {"sweeps": sw.value, "last_flush_ms": ms.value, "launches": nl.value}
 
+    def point_estimate(self, candidates, draws, row0=0, nrows=None):
+        """Binder loss (x draws, exact integer) and n x the VI lower bound of each candidate allocation over the rows
+        [row0, row0 + nrows) of the matrix (smg_psm_point_estimate; mcclust minbinder / minVI with method='draws')."""
+        cand = np.ascontiguousarray(np.atleast_2d(candidates), dtype=np.int32)
+        assert cand.shape[1] == self.n
+        nrows = self.n - row0 if nrows is None else int(nrows)
+        b = np.zeros(cand.shape[0], dtype=np.int64)
+        v = np.zeros(cand.shape[0])
+        lb.check(self.lib.smg_psm_point_estimate(self.h, int(row0), nrows, lb.iptr(cand), cand.shape[0], int(draws),
+                                                b.ctypes.data_as(lb.c_ll_p), lb.dptr(v)))
+        return b, v
+
     def reference(self):
         """CUDA-core evaluation of the currently buffered sweeps (n x n), for cross-checks."""
         out = np.empty((self.n, self.n), dtype=np.int32)
@@ -441,12 +453,38 @@ class Comm:
         lb.check(self.lib.smg_chains_split_rhat(self.h, lb.dptr(x), x.shape[0], x.shape[1], C.byref(out), C.byref(tot)))
         return out.value, tot.value
 
+    def point_estimate(self, psm, candidates, draws, row0=0, nrows=None):
+        """Expected Binder loss and VI lower bound of each candidate over ALL ranks' row blocks, and the minimisers."""
+        cand = np.ascontiguousarray(np.atleast_2d(candidates), dtype=np.int32)
+        nrows = psm.n - row0 if nrows is None else int(nrows)
+        b, v = np.zeros(cand.shape[0]), np.zeros(cand.shape[0])
+        bb, bv = C.c_int(), C.c_int()
+        lb.check(self.lib.smg_chains_point_estimate(self.h, psm.h, int(row0), nrows, lb.iptr(cand), cand.shape[0], int(draws),
+                                                   lb.dptr(b), lb.dptr(v), C.byref(bb), C.byref(bv)))
+        return {"binder": b, "vi_lower_bound": v, "best_binder": bb.value, "best_vi": bv.value}
+
     def k_histogram(self, K, kmax=256):
         k = np.ascontiguousarray(np.asarray(K).ravel(), dtype=np.int32)
         hist = np.zeros(kmax + 1, dtype=np.int64)
         over = C.c_longlong()
         lb.check(self.lib.smg_chains_k_histogram(self.h, lb.iptr(k), k.size, kmax, hist.ctypes.data_as(lb.c_ll_p), C.byref(over)))
         return hist, over.value
+
+
+def adjusted_rand_index(a, b, device=0):
+    """Hubert-Arabie adjusted Rand index on the device (smg_adjusted_rand_index; mcclust::arandi)."""
+    aa, bb = lb.as_i32(a), lb.as_i32(b)
+    out = C.c_double()
+    lb.check(lb.load().smg_adjusted_rand_index(lb.iptr(aa), lb.iptr(bb), int(aa.size), int(device), C.byref(out)))
+    return out.value
+
+
+def trace_ess(traces, device=0):
+    """(IAT, ESS) of scalar traces [ntraces][T] on the device (smg_trace_ess; LaplacesDemon::IAT / ESS)."""
+    x = np.ascontiguousarray(np.atleast_2d(traces), dtype=np.float64)
+    iat, ess = np.zeros(x.shape[0]), np.zeros(x.shape[0])
+    lb.check(lb.load().smg_trace_ess(lb.dptr(x), x.shape[0], x.shape[1], int(device), lb.dptr(iat), lb.dptr(ess)))
+    return iat, ess
 
 
 def hig_inv_u(omega, v, w, m):

@@ -15,6 +15,7 @@
 #include "smg_psm.cuh"
 #include "smg_lltc.cuh"
 #include "smg_comm.cuh"
+#include "smg_post.cuh"
 #include "smg_sm_host.cuh"
 
 namespace smg {
@@ -598,9 +599,10 @@ static int validate_cfg(const smg_config* cfg) {
   for (int j = 0; j < cfg->p; j++) {
     if (cfg->attrisize[j] < 2 || cfg->attrisize[j] > SMG_MAX_LEVELS)
       return fail(SMG_ERR_ARG, "attrisize[j] must be in 2..64 (attribute " + std::to_string(j) + ")");
-    if (!(cfg->v[j] > 1.0))
-      return fail(SMG_ERR_ARG, "v[j] must be > 1 (the HIG sampler uses the Beta(w+1, v-1) form; attribute " +
-                                   std::to_string(j) + ")");
+    // v_j <= 1 is accepted like the reference does (hyperg.cpp:359-376: no Beta(w+1, v-1) proposal exists, every such
+    // draw goes through the inverse CDF); the density needs v_j + w_j > 0 only, v_j > 0 is what the model states
+    if (!(cfg->v[j] > 0.0))
+      return fail(SMG_ERR_ARG, "v[j] must be > 0 (attribute " + std::to_string(j) + ")");
     if (!(cfg->w[j] >= 0.0)) return fail(SMG_ERR_ARG, "w[j] must be >= 0");
   }
   if (cfg->thinning < 1 || cfg->n8_step_size < 1 || cfg->sam_step_size < 1)
@@ -2237,6 +2239,151 @@ int smg_chains_k_histogram(smg_comm* C, const int* K, long long count, int kmax,
   }
   for (int k = 0; k <= kmax; k++) hist[k] = h[k];
   if (overflow) *overflow = h[(size_t)kmax + 1];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// posterior summaries on the device (smg_post.cuh): point estimate from the PSM, adjusted Rand index, IAT / ESS
+// ------------------------------------------------------------------------------------------
+int smg_psm_point_estimate(smg_psm* P, int row0, int nrows, const int* candidates, int ncand, long long draws,
+                           long long* binder_scaled, double* vi_rowsum) {
+  if (!P || !candidates || ncand < 1 || draws < 1 || !binder_scaled || !vi_rowsum) return fail(SMG_ERR_ARG, "bad argument");
+  if (row0 < 0 || nrows < 0 || row0 + nrows > P->n) return fail(SMG_ERR_ARG, "row range out of bounds");
+  int rc = smg_psm_flush(P);
+  if (rc) return rc;
+  SMG_CUDA(cudaSetDevice(P->device));
+  const int n = P->n;
+  std::vector<uint8_t> hc((size_t)ncand * n);
+  for (size_t e = 0; e < hc.size(); e++) {
+    if (candidates[e] < 0 || candidates[e] > 255) return fail(SMG_ERR_ARG, "candidate labels must lie in 0..255");
+    hc[e] = (uint8_t)candidates[e];
+  }
+  uint8_t* dc = nullptr;
+  unsigned long long* db = nullptr;
+  long long* drs = nullptr;
+  double* dv = nullptr;
+  SMG_CUDA(cudaMalloc(&dc, hc.size()));
+  SMG_CUDA(cudaMalloc(&db, (size_t)ncand * 8));
+  SMG_CUDA(cudaMalloc(&drs, (size_t)ncand * std::max(nrows, 1) * 3 * 8));
+  SMG_CUDA(cudaMalloc(&dv, (size_t)ncand * 8));
+  SMG_CUDA(cudaMemcpyAsync(dc, hc.data(), hc.size(), cudaMemcpyHostToDevice, P->st));
+  SMG_CUDA(cudaMemsetAsync(db, 0, (size_t)ncand * 8, P->st));
+  SMG_CUDA(cudaMemsetAsync(dv, 0, (size_t)ncand * 8, P->st));
+  if (nrows > 0) {
+    for (int q0 = 0; q0 < ncand; q0 += POST_MAXC) {
+      psm_point_estimate_kernel<<<cdiv((long long)nrows * 32, 256), 256, 0, P->st>>>(P->psm + (size_t)row0 * n, n, row0, nrows, dc, ncand, q0,
+                                                                                draws, db, drs);
+      P->launches++;
+    }
+    psm_vi_reduce_kernel<<<ncand, 256, 0, P->st>>>(drs, nrows, draws, dv);
+    P->launches++;
+    SMG_CUDA(cudaGetLastError());
+  }
+  SMG_CUDA(cudaMemcpyAsync(binder_scaled, db, (size_t)ncand * 8, cudaMemcpyDeviceToHost, P->st));
+  SMG_CUDA(cudaMemcpyAsync(vi_rowsum, dv, (size_t)ncand * 8, cudaMemcpyDeviceToHost, P->st));
+  SMG_CUDA(cudaStreamSynchronize(P->st));
+  void* ptrs[] = {dc, db, drs, dv};
+  for (void* q : ptrs) cudaFree(q);
+  return 0;
+}
+
+int smg_chains_point_estimate(smg_comm* C, smg_psm* P, int row0, int nrows, const int* candidates, int ncand, long long draws,
+                              double* binder, double* vi_lower_bound, int* best_binder, int* best_vi) {
+  if (!C || !P || !binder || !vi_lower_bound) return fail(SMG_ERR_ARG, "NULL argument");
+  std::vector<long long> bs(ncand > 0 ? ncand : 1);
+  std::vector<double> vs(ncand > 0 ? ncand : 1);
+  int rc = smg_psm_point_estimate(P, row0, nrows, candidates, ncand, draws, bs.data(), vs.data());
+  if (rc) return rc;
+  if (C->world > 1) {  // Binder and VI are sums over rows: add the ranks' row blocks
+    SMG_CUDA(cudaSetDevice(C->device));
+    NcclApi* N = nccl_api();
+    long long* d = nullptr;
+    double* dd = nullptr;
+    SMG_CUDA(cudaMalloc(&d, (size_t)ncand * 8));
+    SMG_CUDA(cudaMalloc(&dd, (size_t)ncand * 8));
+    SMG_CUDA(cudaMemcpyAsync(d, bs.data(), (size_t)ncand * 8, cudaMemcpyHostToDevice, C->st));
+    SMG_CUDA(cudaMemcpyAsync(dd, vs.data(), (size_t)ncand * 8, cudaMemcpyHostToDevice, C->st));
+    SMG_NCCL(N->AllReduce(d, d, (size_t)ncand, ncclInt64, ncclSum, C->comm, C->st));
+    SMG_NCCL(N->AllReduce(dd, dd, (size_t)ncand, ncclDouble, ncclSum, C->comm, C->st));
+    SMG_CUDA(cudaMemcpyAsync(bs.data(), d, (size_t)ncand * 8, cudaMemcpyDeviceToHost, C->st));
+    SMG_CUDA(cudaMemcpyAsync(vs.data(), dd, (size_t)ncand * 8, cudaMemcpyDeviceToHost, C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    cudaFree(d);
+    cudaFree(dd);
+  }
+  int bb = 0, bv = 0;
+  for (int q = 0; q < ncand; q++) {
+    binder[q] = (double)bs[q] / (double)draws;
+    vi_lower_bound[q] = vs[q] / (double)P->n;
+    if (bs[q] < bs[bb]) bb = q;
+    if (vi_lower_bound[q] < vi_lower_bound[bv]) bv = q;
+  }
+  if (best_binder) *best_binder = bb;
+  if (best_vi) *best_vi = bv;
+  return 0;
+}
+
+int smg_adjusted_rand_index(const int* a, const int* b, int n, int device, double* ari) {
+  if (!a || !b || !ari || n < 2) return fail(SMG_ERR_ARG, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  SMG_CUDA(cudaSetDevice(device));
+  int ka = 0, kb = 0;
+  for (int i = 0; i < n; i++) {
+    if (a[i] < 0 || b[i] < 0) return fail(SMG_ERR_ARG, "labels must be non-negative");
+    ka = std::max(ka, a[i] + 1);
+    kb = std::max(kb, b[i] + 1);
+  }
+  if ((long long)ka * kb > (1ll << 26)) return fail(SMG_ERR_ARG, "contingency table too large");
+  int *da = nullptr, *db = nullptr, *tab = nullptr;
+  unsigned long long* out = nullptr;
+  SMG_CUDA(cudaMalloc(&da, (size_t)n * 4));
+  SMG_CUDA(cudaMalloc(&db, (size_t)n * 4));
+  SMG_CUDA(cudaMalloc(&tab, (size_t)ka * kb * 4));
+  SMG_CUDA(cudaMalloc(&out, 3 * 8));
+  SMG_CUDA(cudaMemcpy(da, a, (size_t)n * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemcpy(db, b, (size_t)n * 4, cudaMemcpyHostToDevice));
+  SMG_CUDA(cudaMemset(tab, 0, (size_t)ka * kb * 4));
+  SMG_CUDA(cudaMemset(out, 0, 3 * 8));
+  ari_table_kernel<<<cdiv(n, 256), 256>>>(da, db, n, kb, tab);
+  ari_sums_kernel<<<1, 256>>>(tab, ka, kb, out);
+  SMG_CUDA(cudaGetLastError());
+  unsigned long long h[3];
+  SMG_CUDA(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
+  void* ptrs[] = {da, db, tab, out};
+  for (void* q : ptrs) cudaFree(q);
+  // Hubert-Arabie (mcclust::arandi)
+  const double sij = (double)h[0], sa = (double)h[1], sb = (double)h[2], tot = 0.5 * (double)n * (double)(n - 1);
+  const double ex = sa * sb / tot, mx = 0.5 * (sa + sb);
+  *ari = (mx != ex) ? (sij - ex) / (mx - ex) : 1.0;
+  return 0;
+}
+
+int smg_trace_ess(const double* traces, int ntraces, int T, int device, double* iat_out, double* ess_out) {
+  if (!traces || ntraces < 1 || T < 2) return fail(SMG_ERR_ARG, "bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return fail(SMG_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+  SMG_CUDA(cudaSetDevice(device));
+  double *dx = nullptr, *dm = nullptr, *dg = nullptr, *di = nullptr;
+  SMG_CUDA(cudaMalloc(&dx, (size_t)ntraces * T * 8));
+  SMG_CUDA(cudaMalloc(&dm, (size_t)ntraces * 8));
+  SMG_CUDA(cudaMalloc(&dg, (size_t)ntraces * T * 8));
+  SMG_CUDA(cudaMalloc(&di, (size_t)ntraces * 8));
+  SMG_CUDA(cudaMemcpy(dx, traces, (size_t)ntraces * T * 8, cudaMemcpyHostToDevice));
+  trace_mean_kernel<<<ntraces, 256>>>(dx, T, dm);
+  trace_autocov_kernel<<<dim3(T, ntraces), 256>>>(dx, T, dm, dg);
+  trace_iat_kernel<<<cdiv(ntraces, 64), 64>>>(dg, T, ntraces, di);
+  SMG_CUDA(cudaGetLastError());
+  std::vector<double> h(ntraces);
+  SMG_CUDA(cudaMemcpy(h.data(), di, (size_t)ntraces * 8, cudaMemcpyDeviceToHost));
+  void* ptrs[] = {dx, dm, dg, di};
+  for (void* q : ptrs) cudaFree(q);
+  for (int r = 0; r < ntraces; r++) {
+    if (iat_out) iat_out[r] = h[r];
+    if (ess_out) ess_out[r] = (double)T / h[r];
+  }
   return 0;
 }
 

@@ -200,7 +200,16 @@ __device__ __noinline__ void log_ibeta_pair(double x, double a, double b, double
 // The reference evaluates log(d+1)+(d+c)log m - log 2F1(d+c,1;d+2;(m-1)/m) with GSL, which
 // overflows for clusters of ~10^3 members; both forms agree to <1e-14 rel
 // where the reference is finite (tests/test_oracle_known_answers.py).
+// log of the UNNORMALISED incomplete beta function, log int_0^x t^(a-1) (1-t)^(b-1) dt, for 0 < x < 1, a > 0 and ANY real
+// b: Gauss's continued fraction for x^a (1-x)^b / a * 2F1(a+b, 1; a+1; x) does not need b > 0 (the complete beta
+// function does).  This is what carries v_j <= 1, where the reference's Beta(w+1, v-1) proposal does not exist and
+// rhig takes its inverse-CDF branch (hyperg.cpp:359-376: qbeta returns NaN, the switching test is false).
+__device__ __noinline__ double log_incbeta_u(double x, double a, double b) {
+  return a * log(x) + b * log1p(-x) + log(betacf_d(a, b, x)) - log(a);
+}
+
 __device__ __noinline__ double norm_const2_d(double w, double v, double m) {
+  if (v <= 1.0) return (w + 1.0) * log(m - 1.0) - log_incbeta_u((m - 1.0) / m, w + 1.0, v - 1.0);
   double a = w + 1.0, b = v - 1.0, lb = lbeta_d(a, b), lo, up;
   // With data the truncation point x = (m-1)/m lies far in the upper tail of Beta(a,b).  Chernoff on the gamma
   // representation X = G_a/(G_a+G_b) gives P(X >= x) <= exp(-(a+b) KL(mu||x)), mu = a/(a+b) < x; once that is below
@@ -223,7 +232,35 @@ __device__ __noinline__ double logdensity_hig_d(double s, double v, double w, do
 // which is exactly what the reference's bisection branch solves (hyperg.cpp:221-287 with
 // lF_conK2 :183-217) and the law its Beta-rejection branch samples (hyperg.cpp:359-368).
 // Safeguarded Newton on the log of the smaller tail; returns u (sigma = -1/log u).
+// v <= 1: CDF(u) = B(x; w+1, v-1) / B(xmax; w+1, v-1) with the unnormalised incomplete beta function (any b)
+__device__ __noinline__ double hig_inv_u_smallv(double Omega, double v, double w, double m) {
+  const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
+  const double target = log(Omega) + log_incbeta_u(xmax, a, b);
+  double lo = 0.0, hi = xmax;
+  // B(x) ~ x^a / a near 0: a first guess that is exact for small Omega
+  double x = xmax * pow(Omega, 1.0 / a);
+  if (!(x > 0.0 && x < xmax)) x = 0.5 * xmax;
+  for (int it = 0; it < 200; it++) {
+    const double lB = log_incbeta_u(x, a, b);
+    const double g = lB - target;
+    if (g < 0.0)
+      lo = x;
+    else
+      hi = x;
+    const double dg = exp((a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lB);  // d/dx log B(x)
+    double xn = x - g / dg;
+    const bool newton_ok = (xn > lo && xn < hi);
+    if (!newton_ok) xn = 0.5 * (lo + hi);
+    const double dx = fabs(xn - x);
+    x = xn;
+    if (newton_ok && dx <= 1e-8 * x) break;
+    if (hi - lo <= 4e-16 * hi) break;
+  }
+  return x / ((m - 1.0) * (1.0 - x));
+}
+
 __device__ __noinline__ double hig_inv_u_d(double Omega, double v, double w, double m) {
+  if (v <= 1.0) return hig_inv_u_smallv(Omega, v, w, m);
   const double a = w + 1.0, b = v - 1.0, xmax = (m - 1.0) / m;
   const double lb = lbeta_d(a, b);
   double ltot_lo, ltot_up;
@@ -379,7 +416,7 @@ __device__ __noinline__ double gamma_draw_d(SubStream& rs, double shape) {
 // inverse-CDF draw (the reference's bisection branch) finishes -- the mixture is still the exact law.
 __device__ inline double hig_draw_u_d(SubStream& rs, double v, double w, double m) {
   const double a = w + 1.0, b = v - 1.0;
-  for (int attempt = 0; attempt < 8; attempt++) {
+  for (int attempt = 0; attempt < 8 && b > 0.0; attempt++) {  // b <= 0 (v <= 1): no Beta proposal, inversion only
     const double ga = gamma_draw_d(rs, a), gb = gamma_draw_d(rs, b);
     // x = ga/(ga+gb) <= (m-1)/m  <=>  u = x/((m-1)(1-x)) = ga/((m-1) gb) <= 1: one division
     const double u = ga / ((m - 1.0) * gb);
@@ -393,12 +430,13 @@ __device__ inline double hig_draw_u_d(SubStream& rs, double v, double w, double 
 // and 1 draw them side by side from two sub-streams -- the dependency chain of a proposal is one gamma draw
 // instead of two.  Result valid on lane 0 of the group.
 #define PHI_G 8
-__device__ inline double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
-                                        unsigned gmask, int gbase) {
+// reference form: the algorithm below written with the out-of-line building blocks; also the path of shapes < 1
+__device__ __noinline__ double hig_draw_u_grp_ref(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
+                                                  unsigned gmask, int gbase) {
   SubStream rs(key, g == 1 ? U_SIGMA_B : U_SIGMA, sa, sb);
   const double a = w + 1.0, b = v - 1.0;
   double res = 0.0;
-  for (int attempt = 0; attempt < 8; attempt++) {
+  for (int attempt = 0; attempt < 8 && b > 0.0; attempt++) {
     double gm = 0.0;
     if (g < 2) gm = gamma_draw_d(rs, g == 0 ? a : b);
     const double gb = __shfl_sync(gmask, gm, gbase + 1);
@@ -413,6 +451,69 @@ __device__ inline double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t
     if (__shfl_sync(gmask, ok, gbase)) return res;
   }
   if (g == 0) res = hig_inv_u_d(rs.next(), v, w, m);
+  return res;
+}
+
+// The production form: the same draws from the same Philox blocks (every path of the library calls this one function),
+// with the common case inline -- these draws sit on the critical path of every restricted scan and of update_phi, where a
+// double-precision call chain (gamma_draw_d -> zig_normal_u, sub-stream object in local memory) cost 3-4x the arithmetic.
+// Inline: Philox block -> ziggurat rectangle (98.8%) -> Marsaglia-Tsang squeeze, else its exact log test.  Out of line:
+// ziggurat wedge / tail (re-run from the same block by zig_normal_u), shapes < 1, the inverse-CDF fallback.
+__device__ __forceinline__ double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
+                                                 unsigned gmask, int gbase) {
+  const double a = w + 1.0, b = v - 1.0;
+  if (b < 1.0) return hig_draw_u_grp_ref(key, sa, sb, v, w, m, g, gmask, gbase);  // uniform over the group
+  const uint32_t site = g == 1 ? U_SIGMA_B : U_SIGMA;
+  const double shape = g == 0 ? a : b;
+  const double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
+  uint32_t ctr = 0;
+  double res = 0.0;
+  for (int attempt = 0; attempt < 8; attempt++) {
+    double gm = 0.0;
+    if (g < 2) {
+      gm = d;  // gamma_draw_d's exit after 64 rejected normals (not reached in practice)
+      for (int it = 0; it < 64; it++) {
+        uint32_t o[4];
+        philox4x32_10(sa, sb | (ctr << 20), site | (key.sub << 8), key.sweep, key.k0, key.k1, o);
+        ctr++;
+        const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;
+        const int zi = (int)(o[2] & (SMG_ZIG_C - 1));
+        double un = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);
+        double x = up * __ldg(&g_zig_x[zi]);
+        if (!(fabs(up) < __ldg(&g_zig_r[zi]))) {  // wedge or tail: zig_normal_u from this very block
+          SubStream rs(key, site, sa, sb);
+          rs.ctr = ctr - 1;
+          const NormU nu = zig_normal_u(rs);
+          ctr = rs.ctr;
+          x = nu.x;
+          un = nu.u;
+        }
+        double vv = 1.0 + c * x;
+        if (vv <= 0.0) continue;
+        vv = vv * vv * vv;
+        const double x2 = x * x;
+        if (un < 1.0 - 0.0331 * x2 * x2 || log(un) < 0.5 * x2 + d * (1.0 - vv + log(vv))) {
+          gm = d * vv;
+          break;
+        }
+      }
+    }
+    const double gb = __shfl_sync(gmask, gm, gbase + 1);
+    int ok = 0;
+    if (g == 0) {
+      const double u = gm / ((m - 1.0) * gb);
+      if (u > 0.0 && u < 1.0) {
+        ok = 1;
+        res = u;
+      }
+    }
+    if (__shfl_sync(gmask, ok, gbase)) return res;
+  }
+  if (g == 0) {
+    uint32_t o[4];
+    philox4x32_10(sa, sb | (ctr << 20), site | (key.sub << 8), key.sweep, key.k0, key.k1, o);
+    res = hig_inv_u_d(u01_from_bits(o[0], o[1]), v, w, m);
+  }
   return res;
 }
 

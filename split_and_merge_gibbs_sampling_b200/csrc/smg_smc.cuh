@@ -133,11 +133,15 @@ __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs
   const int ntask = nj * sl;
 #ifdef SMG_SMC_PROFILE
   const bool prof_me = threadIdx.x == 0 && (int)cluster_cta_rank() == nM && G.prof;
+  __shared__ unsigned long long d_prof[8];  // accumulated in shared memory, flushed once per call (a global RMW per tick
+                                            // would put an L2 round trip into every phase)
+  if (prof_me)
+    for (int k = 0; k < 8; k++) d_prof[k] = 0ull;
   long long td = clock64();
 #define DRAW_TICK(k)                                                   \
   do {                                                                 \
     const long long _t = clock64();                                    \
-    if (prof_me) G.prof[k] += (unsigned long long)(_t - td);           \
+    if (prof_me) d_prof[(k) - 50] += (unsigned long long)(_t - td);    \
     td = _t;                                                           \
   } while (0)
 #else
@@ -175,13 +179,12 @@ __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs
     DRAW_TICK(50);
     bool done = false;
     if (!J.prior && !J.uc && !J.us && !A.phi.sigma_exact && m <= PHI_G) {
-      // ---- lean path of the common case, everything inline (a dependent double-precision chain costs ~8 cycles per
-      //      instruction here, calls spill).  Each step is the FIRST step of the generic algorithm below and is taken
-      //      only when that step alone decides; otherwise the generic code runs from scratch on the same Philox
-      //      streams and reproduces it -- results are identical either way.
+      // ---- the common case (conditional update, Philox draws): centre by the dominance screen of draw_center_grp when it
+      //      decides alone, sigma by the inline Beta-rejection draw, and the short form of the derived quantities
       const double sg = sigS[J.role * sl + jl];
       const int* h = slh + ((size_t)J.hist * sl + jl) * mmax;
-      const int hv = g < m ? h[g] : -1;
+      const int hraw = g < m ? h[g] : 0;
+      const int hv = g < m ? hraw : -1;
       const int h1 = __reduce_max_sync(gmask, hv);
       const unsigned top = __ballot_sync(gmask, hv == h1) & gmask;
       const int h2 = __reduce_max_sync(gmask, hv == h1 ? -1 : hv);
@@ -189,56 +192,29 @@ __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs
       if (c_ok) {
         center = (__ffs(top) - 1 - gbase) + 1;
         s_match = (double)h1;
-        const double a = wS[jl] + (double)J.nk - s_match + 1.0, b = vS[jl] + s_match - 1.0;  // Beta(w'+1, v'-1)
-        // first attempt of hig_draw_u_grp: lanes 0 / 1 draw Gamma(a) / Gamma(b) by Marsaglia-Tsang with a ziggurat normal
-        double gm = 0.0;
-        int ok = 1;
-        if (g < 2) {
-          const double shape = g == 0 ? a : b;
-          ok = shape >= 1.0;
-          const double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
-          uint32_t o[4];
-          philox4x32_10((uint32_t)J.idx, (uint32_t)j, (g == 1 ? U_SIGMA_B : U_SIGMA) | (key.sub << 8), key.sweep, key.k0, key.k1, o);
-          const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;
-          const int zi = (int)(o[2] & (SMG_ZIG_C - 1));
-          const double un = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);
-          const double x = up * __ldg(&g_zig_x[zi]);
-          ok = ok && fabs(up) < __ldg(&g_zig_r[zi]);
-          double vv = 1.0 + c * x;
-          ok = ok && vv > 0.0;
-          vv = vv * vv * vv;
-          const double x2 = x * x;
-          ok = ok && un < 1.0 - 0.0331 * x2 * x2;
-          gm = d * vv;
-        }
-        const double gb = __shfl_sync(gmask, gm, gbase + 1);
-        const int okb = __shfl_sync(gmask, ok, gbase + 1);
-        double uu = 0.0;
-        if (g == 0) {
-          uu = gm / ((double)(m - 1) * gb);
-          ok = ok && okb && uu > 0.0 && uu < 1.0;
-        }
-        ok = __shfl_sync(gmask, ok, gbase);
-        if (ok) {
-          done = true;
-          if (g == 0) {
-            // sigma = -1/log u as everywhere; 1/sigma and the log-normaliser through u = exp(-1/sigma) itself:
-            // 1/sigma = -log u, log(1 + (m-1)/exp(1/sigma)) = log1p((m-1) u) -- three divisions and an exp shorter.
-            // (Equal to the canonical expressions within an ulp or two; an accepted proposal's slots are re-derived
-            // canonically from sigma before they join the state.)
-            const double Lg = log(uu);
-            sigma = -1.0 / Lg;
-            isg = -Lg;
-            const double dn = log1p((double)(m - 1) * uu);
-            A.cen[o] = (uint8_t)center;
-            A.sig[o] = sigma;
-            A.isg[o] = isg;
-            G.den[o] = dn;
-            sigS[J.role * sl + jl] = sigma;
-            denS[J.role * sl + jl] = dn;
-            cenS[J.role * sl + jl] = (uint8_t)center;
-          }
-        }
+      } else {
+        const double uc = get_u(nullptr, (size_t)j, key, U_CENTER, (uint32_t)J.idx, (uint32_t)j);
+        center = draw_center_grp(hraw, J.nk, sg, m, uc, g, gmask, gbase, &s_match);
+      }
+      const double uu = hig_draw_u_grp(key, (uint32_t)J.idx, (uint32_t)j, vS[jl] + s_match, wS[jl] + (double)J.nk - s_match,
+                                       (double)m, g, gmask, gbase);
+      done = true;
+      if (g == 0) {
+        // sigma = -1/log u as everywhere; 1/sigma and the log-normaliser through u = exp(-1/sigma) itself:
+        // 1/sigma = -log u, log(1 + (m-1)/exp(1/sigma)) = log1p((m-1) u) -- three divisions and an exp shorter.
+        // (Equal to the canonical expressions within an ulp or two; an accepted proposal's slots are re-derived
+        // canonically from sigma before they join the state.)
+        const double Lg = log(uu);
+        sigma = -1.0 / Lg;
+        isg = -Lg;
+        const double dn = log1p((double)(m - 1) * uu);
+        A.cen[o] = (uint8_t)center;
+        A.sig[o] = sigma;
+        A.isg[o] = isg;
+        G.den[o] = dn;
+        sigS[J.role * sl + jl] = sigma;
+        denS[J.role * sl + jl] = dn;
+        cenS[J.role * sl + jl] = (uint8_t)center;
       }
     }
     DRAW_TICK(51);
@@ -298,6 +274,10 @@ __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs
     }
     DRAW_TICK(55);
   }
+#ifdef SMG_SMC_PROFILE
+  if (prof_me)
+    for (int k = 0; k < 6; k++) G.prof[50 + k] += d_prof[k];
+#endif
 }
 
 // after the draws of a step: this parameter CTA's partial sums of the log-normalisers of the two scanned sides, to
@@ -318,7 +298,7 @@ __device__ __forceinline__ void smc_publish_sdpart(const SmcArgs& G, int k, cons
 #define SMC_TICK(k)                                                                          \
   do {                                                                                       \
     const long long _t = clock64();                                                          \
-    if (threadIdx.x == 0 && (rank == 0 || rank == nM) && G.prof) G.prof[(k) + (rank ? 32 : 0)] += (unsigned long long)(_t - tk); \
+    if (threadIdx.x == 0) s_prof[k] += (unsigned long long)(_t - tk);                        \
     tk = _t;                                                                                 \
   } while (0)
 #else
@@ -362,11 +342,14 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   const bool isM = rank < nM;
   const int kP = rank - nM;  // index among the parameter CTAs
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int j0s = isM ? 0 : kP * sl;
+  const int j0s = (isM ? rank : kP) * sl;  // attribute slice of this CTA's parameter updates (member CTAs: the merged cluster's)
   const size_t len = (size_t)pp * mmax;
   const int words = pp / 4;
   auto off = [](const double* base, size_t o) -> const double* { return base ? base + o : nullptr; };
 #ifdef SMG_SMC_PROFILE
+  __shared__ unsigned long long s_prof[32];  // phase cycle counters of this CTA's thread 0, flushed once at the end
+  if (tid == 0)
+    for (int k = 0; k < 32; k++) s_prof[k] = 0ull;
   long long tk = clock64();
 #endif
   smc_arrive();  // (0) every CTA of the cluster is running: its shared memory may be written remotely after the wait
@@ -382,8 +365,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     s_sel[2] = A.c[i1];
     s_sel[3] = A.c[i2];
   }
-  if (!isM)
-    for (int jl = tid; jl < sl; jl += SMC_T) {
+  for (int jl = tid; jl < sl; jl += SMC_T) {
       attrS[jl] = A.phi.attr[j0s + jl];
       vS[jl] = A.phi.v[j0s + jl];
       wS[jl] = A.phi.w[j0s + jl];
@@ -419,21 +401,25 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     const int tot = __shfl_sync(SMG_FULL, x, 31);
     if (lane < CS) smc_st_s32(smc_map(sel + rank, lane), tot);
   }
-  // prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380), on the parameter CTAs
+  // prior parameters of the three launch clusters (split_merge.cpp:331-343, :379-380): the two split-launch clusters on
+  // the parameter CTAs here, the merge-launch cluster on the member CTAs (which own its update chain) before the scans
+  auto prior_job = [&](int k) {
+    SmcJob J;
+    J.role = k;
+    J.hist = 0;
+    J.nk = 0;
+    J.dst = NSB + (k == 0 ? SM_SL_A : (k == 1 ? SM_SL_B : SM_ML_M));
+    J.idx = k;
+    J.prior = 1;
+    J.sub = SUB_SM_PRIOR;
+    J.uc = off(A.u_prior_c, (size_t)k * p);
+    J.us = off(A.u_prior_s, (size_t)k * p);
+    return J;
+  };
   if (!isM) {
-    SmcJob jb[3];
-    for (int k = 0; k < 3; k++) {
-      jb[k].role = k;
-      jb[k].hist = 0;
-      jb[k].nk = 0;
-      jb[k].dst = NSB + (k == 0 ? SM_SL_A : (k == 1 ? SM_SL_B : SM_ML_M));
-      jb[k].idx = k;
-      jb[k].prior = 1;
-      jb[k].sub = SUB_SM_PRIOR;
-      jb[k].uc = off(A.u_prior_c, (size_t)k * p);
-      jb[k].us = off(A.u_prior_s, (size_t)k * p);
-    }
-    smc_draw_slice(G, jb, 3, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
+    SmcJob jb[2];
+    for (int k = 0; k < 2; k++) jb[k] = prior_job(k);
+    smc_draw_slice(G, jb, 2, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
     __syncthreads();
     smc_publish_sdpart(G, kP, denS, sdpart);
   }
@@ -523,16 +509,75 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       }
     }
     __syncthreads();
-    // both side histograms of the own members (current-state sides: fixed; launch sides: maintained by the scans)
+    // both side histograms of the own members (current-state sides: fixed; launch sides: maintained by the scans).
+    // Cached rows with at most 8 levels: a thread owns one 4-attribute word of the rows of every (SMC_T / words)-th
+    // member and counts in registers -- for level a the four byte lanes of (x == a) are four packed 8-bit counters per
+    // (histogram, side) -- then adds its counters to the shared-memory tables once.  (One shared-memory atomic per
+    // attribute and member took 60 us here.)  Other rows: the atomic path.
     int c1s = 0, c1l = 0;
-    for (int m = warp; m < mine; m += SMC_WARPS) {
+    const int ncache = min(mine, rcap);
+    for (int m = tid; m < mine; m += SMC_T) {
       const int pos = pos0 + m;
-      const int gs = pos < nS ? A.zState[pos] : pos - nS, gl = zc[m];
+      const int gs = pos < nS ? A.zState[pos] : pos - nS;
+      zn[m] = (uint8_t)gs;  // staged for the counting loop below, restored after it
       c1s += gs;
-      c1l += gl;
-      hist_move(m, nullptr, 0, phs, gs);
-      hist_move(m, nullptr, 0, phl, gl);
+      c1l += zc[m];
     }
+    c1s = warp_sum_i(c1s);
+    c1l = warp_sum_i(c1l);
+    __syncthreads();
+    const bool packed = mmax <= 8;
+    if (packed) {
+      const int ng = words <= SMC_T ? SMC_T / words : 1, g = words <= SMC_T ? tid / words : 0;
+      for (int w = (words <= SMC_T ? tid % words : tid); w < words && g < ng; w += SMC_T) {
+        for (int mbase = g; mbase < ncache; mbase += ng * 255) {
+          uint32_t cnt[2][2][8];  // [histogram: state, launch][side][level]
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+              for (int a = 0; a < 8; a++) cnt[h][sd][a] = 0u;
+          const int mend = min(ncache, mbase + ng * 255);
+          for (int m = mbase; m < mend; m += ng) {
+            const uint32_t xw = rowsT[(size_t)w * RSTR + m];
+            const uint32_t ms = zn[m] ? 0xffffffffu : 0u, ml = zc[m] ? 0xffffffffu : 0u;
+#pragma unroll
+            for (int a = 0; a < 8; a++) {
+              if (a < mmax) {
+                const uint32_t eq = __vcmpeq4(xw, 0x01010101u * (uint32_t)(a + 1)) & 0x01010101u;
+                cnt[0][0][a] += eq & ~ms;
+                cnt[0][1][a] += eq & ms;
+                cnt[1][0][a] += eq & ~ml;
+                cnt[1][1][a] += eq & ml;
+              }
+            }
+          }
+#pragma unroll
+          for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int sd = 0; sd < 2; sd++)
+#pragma unroll
+              for (int a = 0; a < 8; a++) {
+                if (a < mmax) {
+                  const uint32_t v = cnt[h][sd][a];
+                  int* dst = (h ? phl : phs) + (size_t)sd * len + (size_t)(4 * w) * mmax + a;
+#pragma unroll
+                  for (int b = 0; b < 4; b++) {
+                    const int c = (int)((v >> (8 * b)) & 0xffu);
+                    if (c) atomicAdd(dst + (size_t)b * mmax, c);
+                  }
+                }
+              }
+        }
+      }
+    }
+    for (int m = (packed ? ncache : 0) + warp; m < mine; m += SMC_WARPS) {
+      hist_move(m, nullptr, 0, phs, zn[m]);
+      hist_move(m, nullptr, 0, phl, zc[m]);
+    }
+    __syncthreads();
+    for (int m = tid; m < mine; m += SMC_T) zn[m] = zc[m];
     if (lane == 0) {
       s_wa[warp] = c1s;
       s_wb[warp] = c1l;
@@ -578,6 +623,28 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       A.H[(size_t)SH_M * len + (size_t)j0s * mmax + e] = v;
     }
     __syncthreads();
+  }
+  if (isM) {
+    // the merged cluster's histogram on this CTA's attribute slice (both current-state sides of every member CTA, DSMEM
+    // reads; fixed for the whole proposal), then the prior draw of the merge-launch cluster: its r updates are an
+    // independent chain (split_merge.cpp:386-387) that lives on the member CTAs, next to the side updates on the
+    // parameter CTAs
+    const int per_side = sl * mmax;
+    for (int e = tid; e < per_side; e += SMC_T) {
+      int v[SMC_MAXCS];
+#pragma unroll
+      for (int r = 0; r < SMC_MAXCS / 2; r++) {
+        v[2 * r] = r < nM ? smc_ld_s32(smc_map(phs + (size_t)j0s * mmax + e, r)) : 0;
+        v[2 * r + 1] = r < nM ? smc_ld_s32(smc_map(phs + len + (size_t)j0s * mmax + e, r)) : 0;
+      }
+      int acc = 0;
+#pragma unroll
+      for (int r = 0; r < SMC_MAXCS; r++) acc += v[r];
+      slh[(size_t)SH_M * per_side + e] = acc;
+    }
+    __syncthreads();
+    const SmcJob J = prior_job(2);
+    smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false);
   }
   if (rank == 0 && tid == 0) {
     A.cnt[SH_S0] = nS + 2 - cntS1;
@@ -687,7 +754,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false);
     };
     if (!do_scan) {
-      if (!isM && do_mg) mg_job();
+      if (isM && do_mg) mg_job();
       continue;
     }
     int dsum = 0, nnr_tot = 0, nnr_mine = 0, extra = 0, cta_changed = 0, any_changed = 0;
@@ -737,6 +804,9 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       __syncthreads();
       const int nlist = s_nlist;
       const bool need_table = nlist > 0 || ndec > rcap;
+#ifdef SMG_SMC_PROFILE
+      if (tid == 0) s_prof[28] += (unsigned long long)nlist;  // members of CTA 0 the count screen did not decide
+#endif
       if (need_table) build_table();
       __syncthreads();
       if (tid == 0) s_nlist = 0;
@@ -845,10 +915,8 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       smc_sync();  // (1) decisions that do not depend on the counts
       SMC_TICK(9);
     } else {
-      smc_arrive();  // (1)
-      if (do_mg) mg_job();
       SMC_TICK(7);
-      smc_wait();  // (1)
+      smc_sync();  // (1)
       SMC_TICK(9);
     }
     for (int r = 0; r < nM; r++) {
@@ -926,6 +994,9 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     if (rank == 0 && tid == 0 && G.prof) {
       G.prof[59] += (unsigned long long)nnr_tot;
       if (q < 4) G.prof[60 + q] += (unsigned long long)nnr_tot;
+      s_prof[25] += nnr_tot > 0;     // scans that needed the ordered walk
+      s_prof[26] += any_changed;     // scans in which some member changed side (or was undecided)
+      s_prof[27] += 1ull;            // scans
     }
 #endif
     if (isM) {
@@ -949,6 +1020,8 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       smc_arrive();  // (3)
       if (q < A.t) fill_logits(q + 1);  // the next scan's, while the parameter CTAs draw (the proposal scan is scan t)
       SMC_TICK(13);
+      if (do_mg) mg_job();  // the merged cluster's update of this step, beside the two side updates on the parameter CTAs
+      SMC_TICK(15);
       smc_wait();  // (3) parameters of the two sides
       SMC_TICK(16);
       side_consts();
@@ -1126,7 +1199,10 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
 #endif
   SMC_TICK(24);
 #ifdef SMG_SMC_PROFILE
-  if (rank == 0 && tid == 0 && G.prof) G.prof[58] += 1ull;
+  if (tid == 0 && G.prof && (rank == 0 || rank == nM)) {
+    if (rank == 0) G.prof[58] += 1ull;
+    for (int k = 0; k < (rank == 0 ? 32 : 18); k++) G.prof[k + (rank ? 32 : 0)] += s_prof[k];
+  }
 #endif
   smc_sync();  // (j) the decision
   if (__ldcg(A.accepted) == 0) return;

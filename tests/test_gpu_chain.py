@@ -103,8 +103,9 @@ def test_argument_errors():
     X = np.array([[1, 2], [2, 1], [1, 1], [2, 2]], dtype=np.float64)
     with pytest.raises(SmgError, match="codes"):
         Chain(np.array([[1, 3], [2, 1], [1, 1], [2, 2]], dtype=np.float64), [2, 2], 1.0, [6, 6], [0.25, 0.25])
-    with pytest.raises(SmgError, match="v\\[j\\] must be > 1"):
-        Chain(X, [2, 2], 1.0, [0.5, 6], [0.25, 0.25])
+    with pytest.raises(SmgError, match="v\\[j\\] must be > 0"):
+        Chain(X, [2, 2], 1.0, [0.0, 6], [0.25, 0.25])
+    Chain(X, [2, 2], 1.0, [0.5, 6], [0.25, 0.25]).close()  # v_j <= 1 is accepted, as in the reference (hyperg.cpp:359-376)
     with pytest.raises(SmgError, match="State validation failed"):
         Chain(X, [2, 2], 1.0, [6, 6], [0.25, 0.25], c_i=[0, 0, 2, 2])
     ch = Chain(X, [2, 2], 1.0, [6, 6], [0.25, 0.25], c_i=[5, 5, 6, 6])  # any base, shifted by min (launcher.cpp:34-37)

@@ -90,3 +90,65 @@ def test_production_sigma_sampler_has_the_hig_law():
         assert stats.kstest(u, cdf).pvalue > 1e-3, (v, w, m)
     # draws of different seeds / sites are different streams
     assert not np.array_equal(rhig_u(100, 6, 0.25, 2, seed=1), rhig_u(100, 6, 0.25, 2, seed=2))
+
+
+def test_hig_with_v_at_most_one():
+    """v_j <= 1: the reference's Beta(w+1, v-1) proposal does not exist (qbeta -> NaN, hyperg.cpp:359), every draw takes
+    the inverse-CDF branch (:370-376).  Device inverse CDF against 40-digit quadrature of the CDF, against the oracle's
+    bisection in the reference's own 2F1 form (stable_hig=0) and in the continued-fraction form; log-density against both;
+    the production sampler in distribution."""
+    import mpmath as mp
+    from scipy import stats
+    from split_and_merge_gibbs_sampling_b200 import hig_inv_u, logdensity_hig, rhig_u
+    mp.mp.dps = 40
+    L = orc.lib()
+    rng = np.random.default_rng(17)
+    for (v, w, m) in [(1.0, 0.25, 5), (0.8, 0.25, 5), (0.3, 0.0, 2), (0.5, 2.25, 4), (1.0, 3.0, 7)]:
+        om = rng.random(24)
+        om[:3] = [1e-6, 0.5, 0.999]
+        got = hig_inv_u(om, v, w, float(m))
+        assert np.all((got > 0) & (got < 1))
+        f = lambda t: t ** w * (1 + (m - 1) * t) ** (-(v + w))  # density in u = exp(-1/sigma), hyperg.cpp:111
+        tot = mp.quad(f, [0, 1])
+        cdf = np.array([float(mp.quad(f, [0, float(g)]) / tot) for g in got])
+        assert np.max(np.abs(cdf - om)) < 1e-12, (v, w, m)
+        for stable in (0, 1):
+            ref = np.empty_like(om)
+            o = orc.opts(stable_hig=stable, sigma_inverse_cdf=1)
+            assert L.orc_rhig_u_from_omega(v, w, m, om.size, orc.P(om), C.byref(o), orc.P(ref)) == 0
+            assert np.max(np.abs(got - ref)) <= 1e-9, (v, w, m, stable)
+        s = rng.uniform(0.1, 3.0, 16)
+        gd = logdensity_hig(s, np.full(16, v), np.full(16, w), np.full(16, float(m)))
+        for stable in (0, 1):
+            ref = np.array([L.orc_logdensity_hig(a, v, w, float(m), stable, None) for a in s])
+            assert np.max(np.abs(gd - ref) / np.maximum(1.0, np.abs(ref))) < 1e-12, (v, w, m, stable)
+        u = rhig_u(8000, v, w, m, seed=5)
+        grid = np.linspace(0.0, 1.0, 2001)
+        cg = np.array([float(mp.quad(f, [0, float(g)]) / tot) if g > 0 else 0.0 for g in grid[::20]])
+        assert stats.kstest(u, lambda x: np.interp(x, grid[::20], cg)).pvalue > 1e-3, (v, w, m)
+
+
+def test_chain_with_v_at_most_one_runs_and_matches_the_oracle_update():
+    """Whole iterations with v_j = 0.8 (prior draws by inversion only), and update_phi under an injected tape against the
+    oracle (centres bit-exact, sigma within the reference's bisection bracket)."""
+    from helpers import Problem
+    pb = Problem(500, 12, 4, 3, seed=55, s=0.8, v=0.8, w=0.25)
+    ch = pb.chain(L=4, c_i=None, compact_init=True, seed=3)
+    for _ in range(8):
+        ch.step(1)
+        s = ch.snapshot()
+        ch.validate_state()
+        ll = orc.loglik(pb.od, s["c_i"], s["centers"], s["sigmas"])
+        assert abs(ll - s["loglikelihood"]) <= 1e-12 * abs(ll)
+    K, c = s["K"], s["c_i"]
+    cen, sig = s["centers"], s["sigmas"]
+    rng = np.random.default_rng(5)
+    uc, us = rng.random((K, pb.p)), rng.random((K, pb.p))
+    tape = np.concatenate([np.concatenate([uc[k], us[k]]) for k in range(K)])
+    ref = orc.update_phi(pb.od, c, cen, sig, tape, o=orc.opts(stable_hig=1, sigma_inverse_cdf=1))
+    ch.set_state(K, c, cen, sig)
+    ch.update_phi(uc, us)
+    got = ch.snapshot()
+    assert np.array_equal(got["centers"], ref["center"])
+    assert np.max(np.abs(np.exp(-1.0 / got["sigmas"]) - np.exp(-1.0 / ref["sigma"]))) <= 1e-9
+    ch.close()
