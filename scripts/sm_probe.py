@@ -22,7 +22,7 @@ def main():
     X, labels, cent, attr = ham_mix_gen(n, p, 5, k_true, s=0.5, seed=1)
     v, w = np.full(p, 6.0), np.full(p, 0.25)
     for mode in modes:
-        for overlap in ("0", "1"):
+        for overlap in (("0",) if os.environ.get("SM_PROBE_OVERLAP_ONLY") else ("0", "1")):
             os.environ["SMG_SM_MODE"] = mode
             os.environ["SMG_NO_K1_OVERLAP"] = overlap
             ch = Chain(X, attr, 1.0, v, w, m=3, L=k_true, t=10, r=10, neal8=True, split_merge=True, seed=1, compact_init=True,

@@ -514,10 +514,18 @@ static int sweep(smg_chain* ch, bool timed) {
   const bool pass_next = ch->neal8 && (ch->iter + 1) % ch->n8_step == 0;
   const bool sm_now = ch->split_merge && ch->iter % ch->sam_step == 0;
   if (pass_now) {
-    int rc = neal8_pass(ch, nullptr, timed, true);
+    // where the aux columns of the next pass are evaluated: under the scan (default) or, SMG_AUX_AT=sm, next to the
+    // likelihood block under the split-merge proposal (the HBM-bound gather slows the scan's dependent loads)
+    static const bool aux_at_sm = [] { const char* e = getenv("SMG_AUX_AT"); return e && strcmp(e, "sm") == 0; }();
+    const bool defer_aux = aux_at_sm && ch->split_merge && ch->iter % ch->sam_step == 0;
+    int rc = neal8_pass(ch, nullptr, timed, !defer_aux);
     if (rc) return rc;
     rc = update_phi_all(ch, SUB_PHI_AFTER_SCAN, nullptr, nullptr);
     if (rc) return rc;
+    if (defer_aux) {
+      rc = prefetch_next_aux(ch);
+      if (rc) return rc;
+    }
   } else if (timed) {
     for (int q = 1; q <= 3; q++) cudaEventRecord(ch->ev[q], ch->st);
   }

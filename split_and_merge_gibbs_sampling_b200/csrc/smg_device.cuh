@@ -454,50 +454,92 @@ __device__ __noinline__ double hig_draw_u_grp_ref(const RngKey& key, uint32_t sa
   return res;
 }
 
-// The production form: the same draws from the same Philox blocks (every path of the library calls this one function),
-// with the common case inline -- these draws sit on the critical path of every restricted scan and of update_phi, where a
-// double-precision call chain (gamma_draw_d -> zig_normal_u, sub-stream object in local memory) cost 3-4x the arithmetic.
-// Inline: Philox block -> ziggurat rectangle (98.8%) -> Marsaglia-Tsang squeeze, else its exact log test.  Out of line:
-// ziggurat wedge / tail (re-run from the same block by zig_normal_u), shapes < 1, the inverse-CDF fallback.
+// One Marsaglia-Tsang iteration on Philox block `blk` of the lane's sub-stream: 1 accepted (*val = the variate),
+// 0 rejected, 2 the normal is not in its ziggurat rectangle (zig_normal_u consumes further blocks)
+__device__ __forceinline__ int mt_iteration(const RngKey& key, uint32_t site, uint32_t sa, uint32_t sb, uint32_t blk, double d,
+                                            double c, double* val) {
+  uint32_t o[4];
+  philox4x32_10(sa, sb | (blk << 20), site | (key.sub << 8), key.sweep, key.k0, key.k1, o);
+  const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;
+  const int zi = (int)(o[2] & (SMG_ZIG_C - 1));
+  const double un = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);
+  const double x = up * __ldg(&g_zig_x[zi]);
+  if (!(fabs(up) < __ldg(&g_zig_r[zi]))) return 2;
+  double vv = 1.0 + c * x;
+  if (vv <= 0.0) return 0;
+  vv = vv * vv * vv;
+  const double x2 = x * x;
+  if (un < 1.0 - 0.0331 * x2 * x2 || log(un) < 0.5 * x2 + d * (1.0 - vv + log(vv))) {
+    *val = d * vv;
+    return 1;
+  }
+  return 0;
+}
+
+// The production form: the same draws from the same Philox blocks as the reference form above (every path of the library
+// calls this one function), arranged for latency -- these draws sit on the critical path of every restricted scan and of
+// update_phi, and a phase ends when the SLOWEST of its few hundred rejection samplers does.
+//   * the common case is inline (Philox block -> ziggurat rectangle -> Marsaglia-Tsang squeeze or its exact log test);
+//     ziggurat wedge / tail, shapes < 1 and the inverse-CDF fallback stay out of line;
+//   * iteration k of a gamma draw reads Philox block k as long as no earlier iteration left its rectangle, so the 8 lanes
+//     of the group evaluate iterations 0..3 of BOTH gamma variates at once (lane 2k + s: iteration k of variate s) and the
+//     first one in order that does not reject is taken: a rejection costs no extra round trip.
 __device__ __forceinline__ double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
                                                  unsigned gmask, int gbase) {
   const double a = w + 1.0, b = v - 1.0;
   if (b < 1.0) return hig_draw_u_grp_ref(key, sa, sb, v, w, m, g, gmask, gbase);  // uniform over the group
-  const uint32_t site = g == 1 ? U_SIGMA_B : U_SIGMA;
-  const double shape = g == 0 ? a : b;
+  const int sv = g & 1;  // which variate this lane works on
+  const uint32_t site = sv ? U_SIGMA_B : U_SIGMA;
+  const double shape = sv ? b : a;
   const double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
-  uint32_t ctr = 0;
+  // speculative round: lane g evaluates iteration g >> 1
+  double val = 0.0;
+  const int oc = mt_iteration(key, site, sa, sb, (uint32_t)(g >> 1), d, c, &val);
+  const unsigned nz = (__ballot_sync(gmask, oc != 0) >> gbase) & 0xffu;
+  const unsigned mine = (nz >> sv) & 0x55u;                 // iterations of my variate that did not reject: bits 0,2,4,6
+  const int kf = mine ? (__ffs(mine) - 1) >> 1 : 4;         // the first of them (4: none)
+  const int src = gbase + 2 * (kf < 4 ? kf : 0) + sv;
+  const int oc_f = __shfl_sync(gmask, oc, src);
+  const double val_f = __shfl_sync(gmask, val, src);
+  uint32_t ctr = (uint32_t)kf;  // blocks consumed so far by my variate
+  bool have = false;
+  double gm = 0.0;
+  if (kf < 4 && oc_f == 1) {
+    gm = val_f;
+    ctr = (uint32_t)kf + 1u;
+    have = true;
+  }
   double res = 0.0;
   for (int attempt = 0; attempt < 8; attempt++) {
-    double gm = 0.0;
-    if (g < 2) {
+    if (g < 2 && !have) {  // sequential continuation (a wedge / tail normal, four rejections in a row, a second attempt)
       gm = d;  // gamma_draw_d's exit after 64 rejected normals (not reached in practice)
       for (int it = 0; it < 64; it++) {
-        uint32_t o[4];
-        philox4x32_10(sa, sb | (ctr << 20), site | (key.sub << 8), key.sweep, key.k0, key.k1, o);
+        double vq = 0.0;
+        int r = mt_iteration(key, site, sa, sb, ctr, d, c, &vq);
         ctr++;
-        const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;
-        const int zi = (int)(o[2] & (SMG_ZIG_C - 1));
-        double un = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);
-        double x = up * __ldg(&g_zig_x[zi]);
-        if (!(fabs(up) < __ldg(&g_zig_r[zi]))) {  // wedge or tail: zig_normal_u from this very block
+        if (r == 2) {  // zig_normal_u from this very block
           SubStream rs(key, site, sa, sb);
           rs.ctr = ctr - 1;
           const NormU nu = zig_normal_u(rs);
           ctr = rs.ctr;
-          x = nu.x;
-          un = nu.u;
+          double vv = 1.0 + c * nu.x;
+          r = 0;
+          if (vv > 0.0) {
+            vv = vv * vv * vv;
+            const double x2 = nu.x * nu.x;
+            if (nu.u < 1.0 - 0.0331 * x2 * x2 || log(nu.u) < 0.5 * x2 + d * (1.0 - vv + log(vv))) {
+              vq = d * vv;
+              r = 1;
+            }
+          }
         }
-        double vv = 1.0 + c * x;
-        if (vv <= 0.0) continue;
-        vv = vv * vv * vv;
-        const double x2 = x * x;
-        if (un < 1.0 - 0.0331 * x2 * x2 || log(un) < 0.5 * x2 + d * (1.0 - vv + log(vv))) {
-          gm = d * vv;
+        if (r == 1) {
+          gm = vq;
           break;
         }
       }
     }
+    have = false;
     const double gb = __shfl_sync(gmask, gm, gbase + 1);
     int ok = 0;
     if (g == 0) {

@@ -311,7 +311,15 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
       const char* e = getenv("SMG_SM_MANY_CTAS");
       return e ? atoi(e) : 8;
     }();
-    const int ctas = ch->many ? many_ctas : std::max(8, std::min(SM_CHAIN_CTAS, n / 800));
+    static const int one_ctas = [] {
+      // Gang size for a single chain.  Measured at the metric shape (gpurun_out/sched1.log, profiles/r02_summary.md):
+      // the proposal itself barely slows down with fewer CTAs (0.439 ms on 120, 0.445 on 88, 0.456 on 64), but the
+      // likelihood block of the next pass, which runs beside it on the SMs the gang leaves free, goes from 0.52 ms
+      // (28 SMs) to 0.39 ms (60 SMs) and ends before the proposal does: 0.753 -> 0.674 ms per sweep.
+      const char* e = getenv("SMG_SM_CTAS");
+      return e ? atoi(e) : 88;
+    }();
+    const int ctas = ch->many ? many_ctas : std::max(8, std::min(std::min(SM_CHAIN_CTAS, one_ctas), n / 800));
     {
       static const int want_hist = [] {
         const char* e = getenv("SMG_SM_HIST_CTAS");
