@@ -47,7 +47,7 @@ EXPORTS = [
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
     "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
     "smg_debug_split_merge", "smg_debug_sm_terms", "smg_debug_aux_free", "smg_debug_initial_assignment", "smg_debug_time_ll_block", "smg_debug_scan_profile", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
-    "smg_psm_flush", "smg_psm_read", "smg_psm_info", "smg_psm_destroy", "smg_debug_psm_reference",
+    "smg_psm_flush", "smg_psm_finalize", "smg_psm_read", "smg_psm_info", "smg_psm_destroy", "smg_debug_psm_reference",
     "smg_comm_unique_id", "smg_comm_create", "smg_comm_destroy", "smg_chains_reduce_psm", "smg_chains_split_rhat",
     "smg_chains_k_histogram", "smg_psm_point_estimate", "smg_chains_point_estimate", "smg_adjusted_rand_index", "smg_trace_ess",
 ]
@@ -102,6 +102,7 @@ def load():
     lib.smg_psm_push_chain.argtypes = [C.c_void_p, C.c_void_p]
     lib.smg_psm_push_host.argtypes = [C.c_void_p, c_int_p]
     lib.smg_psm_flush.argtypes = [C.c_void_p]
+    lib.smg_psm_finalize.argtypes = [C.c_void_p]
     lib.smg_psm_read.argtypes = [C.c_void_p, C.c_int, C.c_int, c_int_p]
     lib.smg_psm_info.argtypes = [C.c_void_p, c_ll_p, c_dbl_p, c_ull_p]
     lib.smg_psm_destroy.argtypes = [C.c_void_p]

@@ -371,8 +371,10 @@ class Psm:
             raise ValueError("c_i must have length n")
         lb.check(self.lib.smg_psm_push_host(self.h, lb.iptr(c)))
 
-    def flush(self):
-        lb.check(self.lib.smg_psm_flush(self.h))
+    def flush(self, finalize=True):
+        """Fold the buffered sweeps into the matrix; finalize=True also completes the lower triangle (the tensor-core
+        kernel accumulates the tiles on or above the diagonal only), which readers of an external matrix need."""
+        lb.check(self.lib.smg_psm_finalize(self.h) if finalize else self.lib.smg_psm_flush(self.h))
 
     def read(self, row0=0, nrows=None):
         nrows = self.n - row0 if nrows is None else int(nrows)

@@ -878,6 +878,7 @@ struct smg_psm {
   long long total = 0;
   int* psm = nullptr;
   bool owns = false;
+  bool lower_stale = false;  // flushes accumulate the upper triangle of tiles only; smg_psm_finalize mirrors it down
   uint8_t* labels = nullptr;
   cudaStream_t st = nullptr;
   unsigned long long launches = 0;
@@ -891,7 +892,10 @@ static int psm_launch(smg_psm* P) {
   SMG_CUDA(cudaFuncSetAttribute(psm_accumulate_kernel<KP, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(cdiv(P->n, PSM_N), cdiv(P->n, PSM_M));
   const char* mo = getenv("SMG_PSM_MMA_ONLY");
-  psm_accumulate_kernel<KP, NST><<<grid, PSM_THREADS, smem, P->st>>>(P->labels, P->n, P->count, P->psm, (mo && mo[0] == '1') ? 1 : 0);
+  static const bool full = [] { const char* e = getenv("SMG_PSM_FULL"); return e && e[0] == '1'; }();  // every tile (A/B measurements)
+  psm_accumulate_kernel<KP, NST><<<grid, PSM_THREADS, smem, P->st>>>(P->labels, P->n, P->count, P->psm, (mo && mo[0] == '1') ? 1 : 0,
+                                                                     full ? 0 : 1);
+  P->lower_stale = true;
   SMG_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1978,6 +1982,21 @@ int smg_psm_flush(smg_psm* P) {
   return 0;
 }
 
+// flush + lower triangle <- upper triangle: the matrix as every reader expects it
+int smg_psm_finalize(smg_psm* P) {
+  int rc = smg_psm_flush(P);
+  if (rc) return rc;
+  if (P->lower_stale) {
+    const int nb = cdiv(P->n, 32);
+    psm_mirror_kernel<<<dim3(nb, nb), 256, 0, P->st>>>(P->psm, P->n);
+    SMG_CUDA(cudaGetLastError());
+    SMG_CUDA(cudaStreamSynchronize(P->st));
+    P->launches++;
+    P->lower_stale = false;
+  }
+  return 0;
+}
+
 int smg_psm_push_host(smg_psm* P, const int* c_i) {
   if (!P || !c_i) return fail(SMG_ERR_ARG, "NULL argument");
   SMG_CUDA(cudaSetDevice(P->device));
@@ -2020,7 +2039,7 @@ int smg_psm_push_chain(smg_psm* P, smg_chain* ch) {
 int smg_psm_read(smg_psm* P, int row0, int nrows, int* out) {
   if (!P || !out) return fail(SMG_ERR_ARG, "NULL argument");
   if (row0 < 0 || nrows < 0 || row0 + nrows > P->n) return fail(SMG_ERR_ARG, "row range out of bounds");
-  int rc = smg_psm_flush(P);
+  int rc = smg_psm_finalize(P);
   if (rc) return rc;
   SMG_CUDA(cudaMemcpy(out, P->psm + (size_t)row0 * P->n, (size_t)nrows * P->n * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
@@ -2123,7 +2142,7 @@ int smg_chains_reduce_psm(smg_comm* C, smg_psm* P, int mode, int* row0, int* nro
   if (!C || !P) return fail(SMG_ERR_ARG, "NULL argument");
   if (C->device != P->device) return fail(SMG_ERR_ARG, "communicator and matrix live on different devices");
   SMG_CUDA(cudaSetDevice(C->device));
-  int rc = smg_psm_flush(P);
+  int rc = smg_psm_finalize(P);
   if (rc) return rc;
   const int n = P->n, G = C->world;
   const bool scatter = mode == 1 && G > 1 && n % G == 0;
@@ -2257,7 +2276,7 @@ int smg_psm_point_estimate(smg_psm* P, int row0, int nrows, const int* candidate
                            long long* binder_scaled, double* vi_rowsum) {
   if (!P || !candidates || ncand < 1 || draws < 1 || !binder_scaled || !vi_rowsum) return fail(SMG_ERR_ARG, "bad argument");
   if (row0 < 0 || nrows < 0 || row0 + nrows > P->n) return fail(SMG_ERR_ARG, "row range out of bounds");
-  int rc = smg_psm_flush(P);
+  int rc = smg_psm_finalize(P);
   if (rc) return rc;
   SMG_CUDA(cudaSetDevice(P->device));
   const int n = P->n;

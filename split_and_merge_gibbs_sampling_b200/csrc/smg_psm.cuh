@@ -81,7 +81,8 @@ __device__ __forceinline__ uint32_t psm_tile_off(int row, int k) {
 
 template <int KP, int NST>
 __global__ void __launch_bounds__(PSM_THREADS, 2)
-    psm_accumulate_kernel(const uint8_t* __restrict__ labels, int n, int T, int* __restrict__ psm, int mma_only) {
+    psm_accumulate_kernel(const uint8_t* __restrict__ labels, int n, int T, int* __restrict__ psm, int mma_only,
+                          int upper_only) {
   constexpr int A_BYTES = PSM_M * KP, B_BYTES = PSM_N * KP, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_free[NST];
@@ -90,6 +91,9 @@ __global__ void __launch_bounds__(PSM_THREADS, 2)
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * PSM_M, n0 = blockIdx.x * PSM_N;
+  // The matrix is symmetric: tiles that lie entirely below the diagonal are not accumulated (half the MMAs and half the
+  // read-modify-write traffic of a flush); psm_mirror_kernel copies the upper triangle down once, when the matrix is read.
+  if (upper_only && n0 + PSM_N - 1 < m0) return;
 
   // zero every stage once; afterwards a stage is recycled by clearing the bytes that were set
   for (int q = tid; q < NST * STAGE_BYTES / 16; q += PSM_THREADS) reinterpret_cast<uint4*>(smem)[q] = make_uint4(0, 0, 0, 0);
@@ -246,6 +250,23 @@ __global__ void psm_reference_kernel(const uint8_t* __restrict__ labels, int n, 
   int acc = 0;
   for (int t = 0; t < T; t++) acc += (labels[(size_t)t * n + i] == labels[(size_t)t * n + j]);
   psm[(size_t)i * n + j] += acc;
+}
+
+// lower triangle <- upper triangle (32 x 32 tiles through shared memory, coalesced both ways); one CTA per tile pair
+__global__ void __launch_bounds__(256) psm_mirror_kernel(int* __restrict__ psm, int n) {
+  __shared__ int tile[32][33];
+  const int bj = blockIdx.x, bi = blockIdx.y;  // source tile: rows bi*32.., cols bj*32.. with bj >= bi
+  if (bj < bi) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bi * 32 + r, j = bj * 32 + tx;
+    tile[r][tx] = (i < n && j < n) ? psm[(size_t)i * n + j] : 0;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;  // destination (i, j) = source (j, i)
+    if (i < n && j < n && i > j) psm[(size_t)i * n + j] = tile[tx][r];
+  }
 }
 
 }  // namespace smg
