@@ -2119,6 +2119,16 @@ int smg_comm_create(int rank, int world, const char* id128, int device, smg_comm
       smg_comm_destroy(C);
       return fail(SMG_ERR_CUDA, msg);
     }
+    // NCCL connects its channels lazily, at the first collective of each kind (~1 s measured on 2 B200): pay for that
+    // here, not inside the first timed reduction
+    int* w = nullptr;
+    SMG_CUDA(cudaMalloc(&w, (size_t)world * 256 * sizeof(int)));
+    SMG_CUDA(cudaMemsetAsync(w, 0, (size_t)world * 256 * sizeof(int), C->st));
+    SMG_NCCL(N->AllReduce(w, w, 256, ncclInt32, ncclSum, C->comm, C->st));
+    SMG_NCCL(N->ReduceScatter(w, w + (size_t)rank * 256, 256, ncclInt32, ncclSum, C->comm, C->st));
+    SMG_NCCL(N->AllGather(w + (size_t)rank * 256, w, 256, ncclInt32, C->comm, C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    C->scratch = w;
   }
   *out = C;
   return 0;
@@ -2131,6 +2141,7 @@ void smg_comm_destroy(smg_comm* C) {
   if (C->comm) nccl_api()->CommDestroy(C->comm);
   for (int q = 0; q < 2; q++)
     if (C->ev[q]) cudaEventDestroy(C->ev[q]);
+  if (C->scratch) cudaFree(C->scratch);
   if (C->st) cudaStreamDestroy(C->st);
   delete C;
 }
@@ -2152,6 +2163,9 @@ int smg_chains_reduce_psm(smg_comm* C, smg_psm* P, int mode, int* row0, int* nro
   if (G > 1) {
     NcclApi* N = nccl_api();
     const size_t total = (size_t)n * n;
+    // the ranks' chains end at different times: meet first, so that *ms is the collective and not the wait for the
+    // slowest rank
+    SMG_NCCL(N->AllReduce(C->scratch, C->scratch, 1, ncclInt32, ncclSum, C->comm, C->st));
     SMG_CUDA(cudaEventRecord(C->ev[0], C->st));
     if (scatter) {
       const size_t per = total / G;

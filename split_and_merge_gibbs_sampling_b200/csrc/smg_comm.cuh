@@ -77,4 +77,5 @@ struct smg_comm {
   ncclComm_t comm = nullptr;
   cudaStream_t st = nullptr;
   cudaEvent_t ev[2] = {};
+  int* scratch = nullptr;  // [world * 256] device words for the warm-up / rendezvous collectives
 };

@@ -457,14 +457,14 @@ __device__ __noinline__ double hig_draw_u_grp_ref(const RngKey& key, uint32_t sa
 // One Marsaglia-Tsang iteration on Philox block `blk` of the lane's sub-stream: 1 accepted (*val = the variate),
 // 0 rejected, 2 the normal is not in its ziggurat rectangle (zig_normal_u consumes further blocks)
 __device__ __forceinline__ int mt_iteration(const RngKey& key, uint32_t site, uint32_t sa, uint32_t sb, uint32_t blk, double d,
-                                            double c, double* val) {
+                                            double c, double* val, const double* zx, const double* zr) {
   uint32_t o[4];
   philox4x32_10(sa, sb | (blk << 20), site | (key.sub << 8), key.sweep, key.k0, key.k1, o);
   const double up = 2.0 * u01_from_bits(o[0], o[1]) - 1.0;
   const int zi = (int)(o[2] & (SMG_ZIG_C - 1));
   const double un = ((double)((((uint64_t)(o[2] >> 7)) << 28) | (uint64_t)(o[3] >> 4)) + 0.5) * (1.0 / 9007199254740992.0);
-  const double x = up * __ldg(&g_zig_x[zi]);
-  if (!(fabs(up) < __ldg(&g_zig_r[zi]))) return 2;
+  const double x = up * zx[zi];
+  if (!(fabs(up) < zr[zi])) return 2;
   double vv = 1.0 + c * x;
   if (vv <= 0.0) return 0;
   vv = vv * vv * vv;
@@ -484,8 +484,11 @@ __device__ __forceinline__ int mt_iteration(const RngKey& key, uint32_t site, ui
 //   * iteration k of a gamma draw reads Philox block k as long as no earlier iteration left its rectangle, so the 8 lanes
 //     of the group evaluate iterations 0..3 of BOTH gamma variates at once (lane 2k + s: iteration k of variate s) and the
 //     first one in order that does not reject is taken: a rejection costs no extra round trip.
+// zx / zr: the ziggurat tables (g_zig_x, g_zig_r), or a copy of them in shared memory -- the look-up follows the Philox
+// block in the dependency chain, and a global load there is a trip to L2 in kernels that keep little L1
 __device__ __forceinline__ double hig_draw_u_grp(const RngKey& key, uint32_t sa, uint32_t sb, double v, double w, double m, int g,
-                                                 unsigned gmask, int gbase) {
+                                                 unsigned gmask, int gbase, const double* zx = g_zig_x,
+                                                 const double* zr = g_zig_r) {
   const double a = w + 1.0, b = v - 1.0;
   if (b < 1.0) return hig_draw_u_grp_ref(key, sa, sb, v, w, m, g, gmask, gbase);  // uniform over the group
   const int sv = g & 1;  // which variate this lane works on
@@ -494,7 +497,7 @@ __device__ __forceinline__ double hig_draw_u_grp(const RngKey& key, uint32_t sa,
   const double d = shape - 1.0 / 3.0, c = rsqrt(9.0 * d);
   // speculative round: lane g evaluates iteration g >> 1
   double val = 0.0;
-  const int oc = mt_iteration(key, site, sa, sb, (uint32_t)(g >> 1), d, c, &val);
+  const int oc = mt_iteration(key, site, sa, sb, (uint32_t)(g >> 1), d, c, &val, zx, zr);
   const unsigned nz = (__ballot_sync(gmask, oc != 0) >> gbase) & 0xffu;
   const unsigned mine = (nz >> sv) & 0x55u;                 // iterations of my variate that did not reject: bits 0,2,4,6
   const int kf = mine ? (__ffs(mine) - 1) >> 1 : 4;         // the first of them (4: none)
@@ -515,7 +518,7 @@ __device__ __forceinline__ double hig_draw_u_grp(const RngKey& key, uint32_t sa,
       gm = d;  // gamma_draw_d's exit after 64 rejected normals (not reached in practice)
       for (int it = 0; it < 64; it++) {
         double vq = 0.0;
-        int r = mt_iteration(key, site, sa, sb, ctr, d, c, &vq);
+        int r = mt_iteration(key, site, sa, sb, ctr, d, c, &vq, zx, zr);
         ctr++;
         if (r == 2) {  // zig_normal_u from this very block
           SubStream rs(key, site, sa, sb);

@@ -49,7 +49,7 @@ struct SmcArgs {
 };
 
 struct SmcLayout {
-  size_t T, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, lst, total;
+  size_t T, isgv, sdpart, sigS, denS, vS, wS, lg, phs, phl, slh, attrS, xchg, sel, rowsT, cenv, cenS, z, lst, zig, total;
   int rstr;  // member stride of the transposed rows (odd: conflict-free both by member and by word)
 };
 __host__ __device__ inline size_t smc_al(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -77,6 +77,7 @@ __host__ __device__ inline SmcLayout smc_layout(int pp, int mmax, int TL, int CS
   L.cenS = o, o = smc_al(o + (size_t)3 * sl);
   L.z = o, o = smc_al(o + (size_t)2 * mcap);
   L.lst = o, o = smc_al(o + (size_t)2 * rcap);
+  L.zig = o, o = smc_al(o + (size_t)(2 * SMG_ZIG_C + 1) * 8);
   L.total = o;
   return L;
 }
@@ -125,7 +126,8 @@ struct SmcJob {
 // into the member CTAs' parameter vectors.
 __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs, int nj, int j0s, const int* slh,
                                             const int* attrS, const double* vS, const double* wS, double* sigS,
-                                            double* denS, uint8_t* cenS, uint8_t* cenv, double* isgv, bool publish) {
+                                            double* denS, uint8_t* cenS, uint8_t* cenv, double* isgv, bool publish,
+                                            const double* zig) {
   const SmChainArgs& A = G.A;
   const int sl = G.sl, pp = A.pp, mmax = A.mmax, nM = G.CS / 2;
   const int g = threadIdx.x & (PHI_G - 1), lane = threadIdx.x & 31, gbase = lane & ~(PHI_G - 1);
@@ -197,7 +199,7 @@ __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs
         center = draw_center_grp(hraw, J.nk, sg, m, uc, g, gmask, gbase, &s_match);
       }
       const double uu = hig_draw_u_grp(key, (uint32_t)J.idx, (uint32_t)j, vS[jl] + s_match, wS[jl] + (double)J.nk - s_match,
-                                       (double)m, g, gmask, gbase);
+                                       (double)m, g, gmask, gbase, zig, zig + SMG_ZIG_C + 1);
       done = true;
       if (g == 0) {
         // sigma = -1/log u as everywhere; 1/sigma and the log-normaliser through u = exp(-1/sigma) itself:
@@ -248,7 +250,7 @@ __device__ __noinline__ void smc_draw_slice(const SmcArgs& G, const SmcJob* jobs
         uu = hig_inv_u_d(us, vv, ww, (double)m);
       }
     } else {
-      uu = hig_draw_u_grp(key, (uint32_t)J.idx, (uint32_t)j, vv, ww, (double)m, g, gmask, gbase);
+      uu = hig_draw_u_grp(key, (uint32_t)J.idx, (uint32_t)j, vv, ww, (double)m, g, gmask, gbase, zig, zig + SMG_ZIG_C + 1);
     }
     DRAW_TICK(53);
     if (g == 0) {
@@ -331,6 +333,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   uint8_t* cenS = smc_raw + L.cenS;                             // [3][sl]
   uint8_t* zc = smc_raw + L.z;                                  // [mcap] side (launch, then proposal)
   uint8_t* zn = zc + mcap;                                      // [mcap] side decided by the scan in progress
+  double* zigS = reinterpret_cast<double*>(smc_raw + L.zig);    // ziggurat tables: x[129] then r[128]
   unsigned short* lst = reinterpret_cast<unsigned short*>(smc_raw + L.lst);  // [rcap] cached members that need the table
   __shared__ int s_nlist;
   __shared__ double sh[256];
@@ -370,6 +373,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       vS[jl] = A.phi.v[j0s + jl];
       wS[jl] = A.phi.w[j0s + jl];
     }
+  for (int q = tid; q < 2 * SMG_ZIG_C + 1; q += SMC_T) zigS[q] = q <= SMG_ZIG_C ? g_zig_x[q] : g_zig_r[q - SMG_ZIG_C - 1];
   if (rank == 0)
     for (int q = tid; q < 24; q += SMC_T) A.terms[q] = 0.0;
   __syncthreads();
@@ -419,7 +423,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
   if (!isM) {
     SmcJob jb[2];
     for (int k = 0; k < 2; k++) jb[k] = prior_job(k);
-    smc_draw_slice(G, jb, 2, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
+    smc_draw_slice(G, jb, 2, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true, zigS);
     __syncthreads();
     smc_publish_sdpart(G, kP, denS, sdpart);
   }
@@ -644,7 +648,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
     }
     __syncthreads();
     const SmcJob J = prior_job(2);
-    smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false);
+    smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false, zigS);
   }
   if (rank == 0 && tid == 0) {
     A.cnt[SH_S0] = nS + 2 - cntS1;
@@ -751,7 +755,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
       J.sub = SUB_SM_MERGE + (prop ? A.r : it);
       J.uc = off(A.u_mg_c, (size_t)(prop ? A.r : it) * p);
       J.us = off(A.u_mg_s, (size_t)(prop ? A.r : it) * p);
-      smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false);
+      smc_draw_slice(G, &J, 1, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, false, zigS);
     };
     if (!do_scan) {
       if (isM && do_mg) mg_job();
@@ -1050,7 +1054,7 @@ __global__ void __launch_bounds__(SMC_T, 1) sm_cluster_kernel(SmcArgs G) {
         J.uc = off(A.u_rg_c, ((size_t)q * 2 + side) * p);
         J.us = off(A.u_rg_s, ((size_t)q * 2 + side) * p);
       }
-      smc_draw_slice(G, jb, 2, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true);
+      smc_draw_slice(G, jb, 2, j0s, slh, attrS, vS, wS, sigS, denS, cenS, cenv, isgv, true, zigS);
       __syncthreads();
       smc_publish_sdpart(G, kP, denS, sdpart);
       SMC_TICK(14);

@@ -313,3 +313,18 @@ def test_deterministic_pair_selection_matches_oracle(seed, iteration, mode):
     after = ch.snapshot()
     ch.close()
     check_case(pb, ref, got, after, labA, labB)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_split_merge_long_launch_on_separated_clusters(seed, mode):
+    """t = r = 8 on well separated clusters: after two or three restricted scans nobody moves any more, which is the regime
+    of the metric configuration -- the cluster kernel then decides every member from its two mismatch counts and skips
+    the table, the ordered pass, the histogram moves and their reduction.  Same launch / proposal states as the oracle."""
+    pb = Problem(2400, 64, 4, 6, seed=400 + seed, s=0.5)
+    K, c, cen, sig = oracle_state_full(pb, mode="truth", iters=1)
+    if seed % 2 == 0:  # over-merged: a split proposal over two true clusters
+        c = (c % 3).astype(np.int32)
+        K, cen, sig = 3, cen[:3].copy(), sig[:3].copy()
+    ref, got, after, labA, labB = run_case(pb, (K, c, cen, sig), seed, t=8, r=8, mode=mode)
+    check_case(pb, ref, got, after, labA, labB)
