@@ -197,11 +197,33 @@ __device__ __forceinline__ double sm_logit_u(const double* u_inj, int pos, const
   const double u = get_u(u_inj, pos, key, U_SM_RGIBBS, (uint32_t)pos, 0u);
   return log(u / (1.0 - u));
 }
+// Interval of D = (log n_1 + LL_1) - (log n_2 + LL_2) a value falls in, for logit(u) = lg; even intervals decide side 1,
+// odd ones side 0 (the rule of the ordered walk below: the larger side iff |D| >= logit u, ties in D to side 1).
+__device__ __forceinline__ int sm_d_region(double D, double lg) {
+  if (lg <= 0.0) return D > 0.0 ? 3 : 0;
+  return D >= lg ? 3 : (D > 0.0 ? 2 : (D > -lg ? 1 : 0));
+}
+// log((nS+1-b)/b) in single precision (absolute error below 1e-5 for nS < 2^31); callers widen it by SM_DC_MARGIN
+#define SM_DC_MARGIN 1e-4
+__device__ __forceinline__ double sm_dc_bound(int nS, int b) {
+  return (double)(logf((float)(nS + 1 - b)) - logf((float)b));
+}
 __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S, int nS,
                                                 const uint8_t* cen, const double* isg, const double* sden, int slotA,
                                                 int slotB, const double* u_inj, const RngKey& key, double* dl,
-                                                double* lgt, int gwarp, int nwarps) {
+                                                double* lgt, int gwarp, int nwarps, const double* lgq = nullptr,
+                                                const int* zcur = nullptr, int* exc = nullptr) {
   const int lane = threadIdx.x & 31;
+  // exc != nullptr: also count the members that are NOT certain to keep their side whatever the running counts are
+  // (decision region constant over the whole range of the count term, and equal to the current side).  When that count
+  // is zero the serial scan changes nothing: the caller skips the decision and the histogram phases.
+  const double dcx = nS > 0 ? sm_dc_bound(nS, 1) + SM_DC_MARGIN : 0.0, dcn = nS > 0 ? sm_dc_bound(nS, nS) - SM_DC_MARGIN : 0.0;
+  int nexc = 0;
+  auto settled = [&](int pos, double d0) {
+    const double lg = lgq[pos];
+    const int rlo = sm_d_region(dcn + d0, lg), rhi = sm_d_region(dcx + d0, lg);
+    return rlo == rhi && (~rlo & 1) == zcur[pos];
+  };
   const uint8_t *cA = cen + (size_t)slotA * pp, *cB = cen + (size_t)slotB * pp;
   const double *wA = isg + (size_t)slotA * pp, *wB = isg + (size_t)slotB * pp;
   const double sdA = sden[slotA], sdB = sden[slotB];
@@ -253,14 +275,19 @@ __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, i
       a1 = warp_sum(a1);
       b1 = warp_sum(b1);
       if (lane == 0) {
-        dl[pos0] = (-a0 - sdA) - (-b0 - sdB);
+        const double d0 = (-a0 - sdA) - (-b0 - sdB);
+        dl[pos0] = d0;
         if (lgt) lgt[pos0] = sm_logit_u(u_inj, pos0, key);
+        if (exc && !settled(pos0, d0)) nexc++;
       }
       if (lane == 1 && has1) {
-        dl[pos1] = (-a1 - sdA) - (-b1 - sdB);
+        const double d1 = (-a1 - sdA) - (-b1 - sdB);
+        dl[pos1] = d1;
         if (lgt) lgt[pos1] = sm_logit_u(u_inj, pos1, key);
+        if (exc && !settled(pos1, d1)) nexc++;
       }
     }
+    if (exc && nexc) atomicAdd(exc, nexc);
     return;
   }
   for (int pos = gwarp; pos < nS; pos += nwarps) {
@@ -270,8 +297,10 @@ __device__ __forceinline__ void sm_ll2prep_body(const uint8_t* __restrict__ X, i
     if (lane == 0) {
       dl[pos] = llA - llB;
       if (lgt) lgt[pos] = sm_logit_u(u_inj, pos, key);
+      if (exc && !settled(pos, llA - llB)) nexc++;
     }
   }
+  if (exc && nexc) atomicAdd(exc, nexc);
 }
 
 __global__ void __launch_bounds__(256) sm_ll2prep_kernel(const uint8_t* __restrict__ X, int pp, const int* __restrict__ S,
@@ -308,17 +337,6 @@ static inline int sm_wide_from() {
     return e ? atoi(e) : SM_DECIDE_WIDE_FROM;
   }();
   return v;
-}
-// Interval of D = (log n_1 + LL_1) - (log n_2 + LL_2) a value falls in, for logit(u) = lg; even intervals decide side 1,
-// odd ones side 0 (the rule of the ordered walk below: the larger side iff |D| >= logit u, ties in D to side 1).
-__device__ __forceinline__ int sm_d_region(double D, double lg) {
-  if (lg <= 0.0) return D > 0.0 ? 3 : 0;
-  return D >= lg ? 3 : (D > 0.0 ? 2 : (D > -lg ? 1 : 0));
-}
-// log((nS+1-b)/b) in single precision (absolute error below 1e-5 for nS < 2^31); callers widen it by SM_DC_MARGIN
-#define SM_DC_MARGIN 1e-4
-__device__ __forceinline__ double sm_dc_bound(int nS, int b) {
-  return (double)(logf((float)(nS + 1 - b)) - logf((float)b));
 }
 template <int N>
 struct RdecideSmem {  // per-member scratch of one chunk (only the non-robust members are read back)
@@ -1025,6 +1043,7 @@ struct SmChainArgs {
   const double *u_rg, *u_rg_c, *u_rg_s, *u_mg_c, *u_mg_s;  // injected uniforms (bases) or null
   const double *u_pair, *u_prior_c, *u_prior_s, *u_launch, *u_accept;
   int pair_det;  // 1: select_observations_deterministic
+  int* exc;      // [2] members not certain to keep their side in the scan in progress (by scan parity)
   RngKey key;
   unsigned* bar;       // grid-barrier counter of this launch (zero on entry)
   unsigned* bar_next;  // the counter of the next launch: zeroed here
@@ -1087,7 +1106,10 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     s_sel[1] = i2;
     s_sel[2] = A.c[i1];
     s_sel[3] = A.c[i2];
-    if (blockIdx.x == 0) *A.bar_next = 0u;
+    if (blockIdx.x == 0) {
+      *A.bar_next = 0u;
+      if (A.exc) A.exc[0] = A.exc[1] = 0;
+    }
   }
   if (blockIdx.x == 0)
     for (int q = tid; q < 24; q += SM_CHAIN_T) A.terms[q] = 0.0;
@@ -1182,21 +1204,32 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     RngKey k = A.key;
     k.sub = SUB_SM_RG + q;
     CHAIN_TICK(7);
+    // Settled scans: once the launch state has found the two groups (after two or three scans of a merge proposal, which
+    // is 98% of the proposals at K = 50), every member keeps its side with certainty.  The likelihood phase counts the
+    // members for which that is NOT certain; when there is none, the serial decision, the side histograms and their two
+    // grid barriers are skipped -- sides, counts and histograms are what they were.  (Not in the first scan, which also
+    // builds the current-state histograms, nor in the proposal scan, whose histograms do not exist yet.)
+    double* lgq = (q & 1) ? A.lgt2 : A.lgt;
+    int* excq = (first || z != A.zL || !A.exc) ? nullptr : A.exc + (q & 1);
     sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, nullptr, gwarp,
-                    nwarps);
+                    nwarps, lgq, z, excq);
     // the histograms of the current-state sides (fixed for the whole proposal) ride in the first scan
     if (first)
       subset_hist_body(A.X, pp, A.S, nS, A.zState, &A.info->i1, A.mmax, A.H + (size_t)SH_S0 * len, A.cnt + SH_S0, s_hist,
                        blockIdx.x, gridDim.x);
     grid_sync(B);
     CHAIN_TICK(4);
+    if (A.exc && gtid == 0) A.exc[(q + 1) & 1] = 0;  // the next scan's counter (last read one scan ago)
+    if (excq && __ldcg(excq) == 0) {
+      if (q < A.t) fill_lgt(q + 1, gtid, gthreads);  // the next scan's logits (normally evaluated beside the decision)
+      return;
+    }
     if (first && blockIdx.x != 0) {  // ... and their sum, the merged cluster's histogram, while CTA 0 decides
       const int nt = ((int)gridDim.x - 1) * SM_CHAIN_T;
       for (int q2 = gtid - SM_CHAIN_T; q2 < (int)len; q2 += nt)
         A.H[(size_t)SH_M * len + q2] = A.H[(size_t)SH_S0 * len + q2] + A.H[(size_t)SH_S1 * len + q2];
       if (gtid == SM_CHAIN_T) A.cnt[SH_M] = A.cnt[SH_S0] + A.cnt[SH_S1];
     }
-    double* lgq = (q & 1) ? A.lgt2 : A.lgt;
     if (blockIdx.x == 0) {
       if (q >= A.wide_from)
         sm_rdecide_body<SM_CHAIN_T, SM_DECIDE_WIDE_CHUNK / SM_CHAIN_T>(nS, A.dl, lgq, z, A.H + (size_t)h0 * len, (int)(2 * len),

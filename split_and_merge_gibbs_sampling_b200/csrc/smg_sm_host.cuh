@@ -42,8 +42,8 @@ static int sm_alloc(smg_chain* ch) {
   }
   SMG_CUDA(cudaFuncSetAttribute(sm_rdecide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(RdecideSmem<SM_DECIDE_WIDE_CHUNK>)));
-  SMG_CUDA(dev_malloc(&W->chain_bar, 4 * sizeof(unsigned), ch->st));
-  SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 4 * sizeof(unsigned), ch->st));
+  SMG_CUDA(dev_malloc(&W->chain_bar, 8 * sizeof(unsigned), ch->st));  // [0..1] barrier counters, [2] error flag, [4..5] settled-scan counters
+  SMG_CUDA(cudaMemsetAsync(W->chain_bar, 0, 8 * sizeof(unsigned), ch->st));
   SMG_CUDA(dev_malloc(&W->selcnt, 256 * sizeof(int), ch->st));
   {
     // the persistent chain kernel needs co-resident CTAs (cooperative launch) and the side histograms in shared memory
@@ -304,6 +304,10 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
     CA.bar_next = W->chain_bar + (W->bar_flip ^ 1);
     W->bar_flip ^= 1;
     CA.err = reinterpret_cast<int*>(W->chain_bar + 2);
+    {
+      static const bool no_skip = [] { const char* e = getenv("SMG_SM_NO_SETTLED_SKIP"); return e && e[0] == '1'; }();
+      CA.exc = no_skip ? nullptr : reinterpret_cast<int*>(W->chain_bar + 4);
+    }
     void* kargs[] = {&CA};
     // grid: enough CTAs for the member-likelihood phase of a single chain; a small gang when several chains share the
     // GPU (smg_step_many), where the number of launches per sweep matters more than the latency of one proposal
@@ -312,12 +316,13 @@ static int sm_step(smg_chain* ch, const smg_sm_tape* tape) {
       return e ? atoi(e) : 8;
     }();
     static const int one_ctas = [] {
-      // Gang size for a single chain.  Measured at the metric shape (gpurun_out/sched1.log, profiles/r02_summary.md):
-      // the proposal itself barely slows down with fewer CTAs (0.439 ms on 120, 0.445 on 88, 0.456 on 64), but the
-      // likelihood block of the next pass, which runs beside it on the SMs the gang leaves free, goes from 0.52 ms
-      // (28 SMs) to 0.39 ms (60 SMs) and ends before the proposal does: 0.753 -> 0.674 ms per sweep.
+      // Gang size for a single chain.  Measured at the metric shape (gpurun_out/sched1.log, sched2.log;
+      // profiles/r02_summary.md): the proposal is latency-bound and barely slows down with fewer CTAs (0.390 ms on 88,
+      // 0.399 on 72, 0.424 on 56), but the likelihood block of the next pass, which runs beside it on the SMs the gang
+      // leaves free, goes from 0.52 ms (120 CTAs: 28 SMs left) to 0.31 ms (72: 76 SMs) and ends before the proposal
+      // does; 72 minimises the sweep (0.753 ms with 120, 0.629 with 72).
       const char* e = getenv("SMG_SM_CTAS");
-      return e ? atoi(e) : 88;
+      return e ? atoi(e) : 72;
     }();
     const int ctas = ch->many ? many_ctas : std::max(8, std::min(std::min(SM_CHAIN_CTAS, one_ctas), n / 800));
     {
