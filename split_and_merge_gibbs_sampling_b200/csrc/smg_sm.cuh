@@ -1200,16 +1200,17 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
   HT_TICK(1);
 
   // allocation part of restricted scan q on sides z / slots (slotA, slotB) -> histograms h0, h0+1
-  auto alloc_scan = [&](int* z, int slotA, int slotB, int h0, int q, bool first) {
+  auto alloc_scan = [&](int* z, int slotA, int slotB, int h0, int q, bool first, bool have_dl) -> bool {
     RngKey k = A.key;
     k.sub = SUB_SM_RG + q;
     CHAIN_TICK(7);
+    double* lgq = (q & 1) ? A.lgt2 : A.lgt;
+    if (!have_dl) {
     // Settled scans: once the launch state has found the two groups (after two or three scans of a merge proposal, which
     // is 98% of the proposals at K = 50), every member keeps its side with certainty.  The likelihood phase counts the
     // members for which that is NOT certain; when there is none, the serial decision, the side histograms and their two
     // grid barriers are skipped -- sides, counts and histograms are what they were.  (Not in the first scan, which also
     // builds the current-state histograms, nor in the proposal scan, whose histograms do not exist yet.)
-    double* lgq = (q & 1) ? A.lgt2 : A.lgt;
     int* excq = (first || z != A.zL || !A.exc) ? nullptr : A.exc + (q & 1);
     sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, slotA, slotB, off(A.u_rg, (size_t)q * n), k, A.dl, nullptr, gwarp,
                     nwarps, lgq, z, excq);
@@ -1222,8 +1223,9 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     if (A.exc && gtid == 0) A.exc[(q + 1) & 1] = 0;  // the next scan's counter (last read one scan ago)
     if (excq && __ldcg(excq) == 0) {
       if (q < A.t) fill_lgt(q + 1, gtid, gthreads);  // the next scan's logits (normally evaluated beside the decision)
-      return;
+      return true;
     }
+    }  // !have_dl
     if (first && blockIdx.x != 0) {  // ... and their sum, the merged cluster's histogram, while CTA 0 decides
       const int nt = ((int)gridDim.x - 1) * SM_CHAIN_T;
       for (int q2 = gtid - SM_CHAIN_T; q2 < (int)len; q2 += nt)
@@ -1247,25 +1249,35 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
                        A.hist_ctas);
     grid_sync(B);
     CHAIN_TICK(6);
+    return false;
   };
   // One loop, ONE call site for the scan phases and one for the parameter jobs: the kernel runs once per sweep on cold
   // instruction caches, and every extra inlined copy of these bodies costs ~10 us of instruction fetch the first time
   // it is reached.  Iterations 0 .. nsteps-1 are the launch scans (+ merge-launch updates), iteration nsteps is the
   // proposal: copy of the split launch state, one more restricted scan for a split, the merged cluster's final update.
   const int nsteps = A.t > A.r ? A.t : A.r;
+  // Slots that hold the split-launch parameters of the two sides.  After a settled scan the next one is run
+  // speculatively: its check ("nobody can move") on most CTAs and its parameter update on the others AT THE SAME TIME,
+  // the update writing into the spare pair of slots; one grid barrier later the check says whether the update stands
+  // (the pairs swap roles) or the scan is redone step by step from the untouched current pair.
+  int curA = SM_SL_A, curB = SM_SL_B;
+  bool prev_settled = false;
   for (int it = 0; it <= nsteps; it++) {
     const bool prop = (it == nsteps);
     if (prop) {
       // proposal = split launch state (sides + the two parameter slots) ...
       for (int pos = gtid; pos < nS; pos += gthreads) A.zStar[pos] = A.zL[pos];
-      if (blockIdx.x < 2) {
-        const int src = NSB + (blockIdx.x ? SM_SL_B : SM_SL_A), dst = NSB + (blockIdx.x ? SM_ST_B : SM_ST_A);
-        for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
-          A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
-          A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
-          A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
+      if (blockIdx.x < 4) {  // ... copied into the proposal slots, and back into the launch slots when the spare pair holds it
+        const int side = blockIdx.x & 1;
+        const int src = NSB + (side ? curB : curA), dst = NSB + (blockIdx.x < 2 ? (side ? SM_ST_B : SM_ST_A) : (side ? SM_SL_B : SM_SL_A));
+        if (src != dst) {
+          for (int jx = threadIdx.x; jx < pp; jx += blockDim.x) {
+            A.cen[(size_t)dst * pp + jx] = A.cen[(size_t)src * pp + jx];
+            A.sig[(size_t)dst * pp + jx] = A.sig[(size_t)src * pp + jx];
+            A.isg[(size_t)dst * pp + jx] = A.isg[(size_t)src * pp + jx];
+          }
+          if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
         }
-        if (threadIdx.x == 0) A.sden[dst] = A.sden[src];
       }
       grid_sync(B);
     }
@@ -1273,19 +1285,59 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     const bool do_scan = prop ? (same != 0) : (it < A.t);
     PhiJob j[3];
     int nj = 0;
+    bool mg_done = false;
     if (do_scan) {
-      alloc_scan(prop ? A.zStar : A.zL, NSB + (prop ? SM_ST_A : SM_SL_A), NSB + (prop ? SM_ST_B : SM_SL_B), prop ? SH_P0 : SH_L0, q,
-                 it == 0);
-      for (int side = 0; side < 2; side++)
-        j[nj++] = sm_job_at(NSB, (prop ? J_P0 : J_L0) + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
-                            off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+      bool have_dl = false;
+      const int nparts = A.phi.nparts, njs = (it < A.r) ? 3 : 2;
+      if (!prop && prev_settled && A.exc && (int)gridDim.x >= 2 * njs * nparts) {
+        // ---- speculative scan: update (current pair -> spare pair) and the merged cluster's update on the first CTAs,
+        //      the check and the next scan's logits on the others
+        const int nxtA = curA == SM_SL_A ? SM_TMP0 : SM_SL_A, nxtB = curB == SM_SL_B ? SM_TMP1 : SM_SL_B;
+        PhiJob js[3];
+        for (int side = 0; side < 2; side++) {
+          js[side] = sm_job_at(NSB, J_L0 + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                               off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+          js[side].src = NSB + (side ? curB : curA);
+          js[side].dst = NSB + (side ? nxtB : nxtA);
+        }
+        if (njs == 3) js[2] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + it, off(A.u_mg_c, (size_t)it * p), off(A.u_mg_s, (size_t)it * p), 0);
+        const int njp = njs * nparts;
+        if ((int)blockIdx.x < njp) {
+          phi_job_body(A.phi, js[blockIdx.x % njs], blockIdx.x % njs, blockIdx.x / njs, nparts, sh);
+        } else {
+          RngKey k = A.key;
+          k.sub = SUB_SM_RG + q;
+          const int cw = ((int)blockIdx.x - njp) * WPB + warp, cnw = ((int)gridDim.x - njp) * WPB;
+          sm_ll2prep_body(A.X, pp, A.S, nS, A.cen, A.isg, A.sden, NSB + curA, NSB + curB, off(A.u_rg, (size_t)q * n), k, A.dl,
+                          nullptr, cw, cnw, (q & 1) ? A.lgt2 : A.lgt, A.zL, A.exc + (q & 1));
+          if (q < A.t) fill_lgt(q + 1, gtid - njp * SM_CHAIN_T, ((int)gridDim.x - njp) * SM_CHAIN_T);
+        }
+        if (gtid == 0) A.exc[(q + 1) & 1] = 0;
+        grid_sync(B);
+        mg_done = njs == 3;
+        if (__ldcg(A.exc + (q & 1)) == 0) {  // nobody moves: the update stands
+          curA = nxtA;
+          curB = nxtB;
+          if (*(volatile int*)A.err) return;
+          continue;
+        }
+        have_dl = true;  // redo from the decision phase: the likelihood differences are in place
+      }
+      prev_settled = alloc_scan(prop ? A.zStar : A.zL, NSB + (prop ? SM_ST_A : curA), NSB + (prop ? SM_ST_B : curB),
+                                prop ? SH_P0 : SH_L0, q, it == 0, have_dl);
+      for (int side = 0; side < 2; side++) {
+        j[nj] = sm_job_at(NSB, (prop ? J_P0 : J_L0) + side, SUB_SM_RG + q, off(A.u_rg_c, ((size_t)q * 2 + side) * p),
+                          off(A.u_rg_s, ((size_t)q * 2 + side) * p), 0);
+        if (!prop) j[nj].src = j[nj].dst = NSB + (side ? curB : curA);
+        nj++;
+      }
     }
     // the job index enters the Philox counter: the merged cluster's final update keeps index 2 as in the multi-launch path
     int idx0 = 0;
     if (prop) {
       if (!do_scan) idx0 = 2;
       j[nj++] = sm_job_at(NSB, J_MSTAR, SUB_SM_MERGE + A.r, off(A.u_mg_c, (size_t)A.r * p), off(A.u_mg_s, (size_t)A.r * p), 0);
-    } else if (it < A.r) {
+    } else if (it < A.r && !mg_done) {
       j[nj++] = sm_job_at(NSB, J_MG, SUB_SM_MERGE + it, off(A.u_mg_c, (size_t)it * p), off(A.u_mg_s, (size_t)it * p), 0);
     }
     if ((int)blockIdx.x < nj * A.phi.nparts)
