@@ -317,16 +317,21 @@ def main():
                          "look-ups (1 LDS.64 + 1 DADD per 4 attributes, 64%% of the wavefront peak in the ncu capture). avg_launch_ms: the "
                          "kernel alone on the chain's stream (CUDA events, cold caches, burst peak); inside a sweep it runs on "
                          "a side stream beside the split-merge proposal (avg_launch_ms_inside_sweep, hidden time). The tcgen05 digit-plane GEMM of the same block (SMG_K1=tc, smg_lltc.cuh) is exact and passes "
-                         "the parity tests but measured 0.247 ms: profiles/r02_summary.md" % cmp_adds)}
+                         "the parity tests but measured 0.234 ms (tensor pipe 9.7% active, bound by building the one-hot operand): profiles/r02_summary.md section 4" % cmp_adds)}
     # ---- the dominant kernel of the sweep: the split-merge proposal (latency-bound chain of (t+1) restricted scans)
     nS_typ = 2.0 * a.n / max(K_now, 1)
-    roofline_dominant = {"kernel": "sm_chain_kernel (cooperative, 120 CTAs) -- default for one chain; sm_cluster_kernel with SMG_SM_MODE=cluster",
+    gang = int(os.environ.get("SMG_SM_CTAS", "72"))
+    roofline_dominant = {"kernel": "sm_chain_kernel (cooperative, %d CTAs) -- default for one chain; sm_cluster_kernel (one 16-CTA cluster) for chains stepped together" % gang,
                          "bound": "latency", "avg_launch_ms": float(phase[4]), "share_of_sweep": float(phase[4] / max(phase[7], 1e-9)),
-                         "restricted_scans": a.t + 1, "grid_barriers": 4 * (a.t + 1) + 11,
+                         "restricted_scans": a.t + 1, "grid_barriers_max": 4 * (a.t + 1) + 11,
+                         "grid_barriers_typical": "2 per settled scan (check || update, update) ... 1 when speculated; ~30 per merge proposal",
                          "ns_per_member_scan": 1e6 * float(phase[4]) / ((a.t + 1) * max(nS_typ, 1.0)),
                          "algorithmic_bytes": (a.t + 2) * nS_typ * (pp + 16),
                          "achieved_GBps": (a.t + 2) * nS_typ * (pp + 16) / max(phase[4], 1e-9) / 1e6,
-                         "note": "dependent phases of 3-12 us; double-precision dependency latency (~8 cycles per dependent instruction at 4 warps per scheduler) and barrier waits, see profiles/r02_summary.md"}
+                         "note": "a chain of dependent phases of 5-15 us (61% of the warp samples wait at a grid barrier for the one CTA or the "
+                                 "24 CTAs that work in a phase); the floor of a phase is the double-precision latency of one Beta-rejection "
+                                 "draw (~5 us).  Round 2 removed phases instead: settled scans skip the serial decision and the histograms, "
+                                 "the scan after a settled one runs check and update at once.  profiles/r02_summary.md sections 2-3"}
     scan = {"ns_per_observation": 1e6 * phase[2] / a.n, "events_per_sweep": (st1["scan_events"] - st0["scan_events"]) / a.steps,
             "avg_ms": float(phase[2])}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
