@@ -317,7 +317,7 @@ def main():
                          "look-ups (1 LDS.64 + 1 DADD per 4 attributes, 64%% of the wavefront peak in the ncu capture). avg_launch_ms: the "
                          "kernel alone on the chain's stream (CUDA events, cold caches, burst peak); inside a sweep it runs on "
                          "a side stream beside the split-merge proposal (avg_launch_ms_inside_sweep, hidden time). The tcgen05 digit-plane GEMM of the same block (SMG_K1=tc, smg_lltc.cuh) is exact and passes "
-                         "the parity tests but measured 0.234 ms (tensor pipe 9.7% active, bound by building the one-hot operand): profiles/r02_summary.md section 4" % cmp_adds)}
+                         "the parity tests but measured 0.234 ms (tensor pipe 9.7%% active, bound by building the one-hot operand): profiles/r02_summary.md section 4" % cmp_adds)}
     # ---- the dominant kernel of the sweep: the split-merge proposal (latency-bound chain of (t+1) restricted scans)
     nS_typ = 2.0 * a.n / max(K_now, 1)
     gang = int(os.environ.get("SMG_SM_CTAS", "72"))

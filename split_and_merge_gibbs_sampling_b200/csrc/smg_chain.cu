@@ -1,6 +1,9 @@
 // smg_chain.cu -- host driver of one chain + the extern "C" layer declared in include/smgibbs.h.
 // Mirrors code/launcher.cpp:7-174 (state initialisation, aux pool, iteration loop, snapshots);
 // all arithmetic happens in the kernels of smg_kernels.cuh / smg_sm.cuh.  There is no CPU path.
+#include <atomic>
+#include <thread>
+
 #include "smg_chain.cuh"
 
 #include <sched.h>
@@ -1329,7 +1332,7 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   // Snapshots (launcher.cpp:140-153) leave the device asynchronously: every kept iteration enqueues its copies
   // into one of RING pinned slots behind the sweep on the chain's stream and the host only waits for a slot
   // when it comes round again, so sweeps are launched back to back.
-  const int RING = 4;
+  const int RING = 8;
   const int pp = ch->pp, Kcap = ch->Kcap;
   struct Slot {
     int* hdr;  // K, status, accepted
@@ -1400,14 +1403,39 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
   auto t0 = std::chrono::steady_clock::now();
   const long long total = (long long)(iterations + burnin) * thinning;
   long long nkept = 0;
+  // The snapshots are unpacked into the result block by a second host thread, in order, while this one keeps
+  // launching sweeps: at the metric shape unpacking (0.4 MB of labels, K x p parameters, first-touch page faults of the
+  // result block) plus the ~13 launches of a sweep did not fit into the 0.53 ms the GPU needs for it.
+  std::atomic<long long> produced{0}, consumed{0};
+  std::atomic<int> cons_rc{0};
+  std::atomic<bool> cons_stop{false};
+  std::string cons_msg;
+  std::thread consumer([&] {
+    cudaSetDevice(device);
+    for (long long k = 0;; k++) {
+      while (k >= produced.load(std::memory_order_acquire)) {
+        if (cons_stop.load(std::memory_order_acquire)) return;
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+      }
+      const int r = consume(ring[k % RING]);
+      if (r) {
+        cons_msg = g_last_error;
+        cons_rc.store(r, std::memory_order_release);
+        return;
+      }
+      consumed.store(k + 1, std::memory_order_release);
+    }
+  });
   for (long long iter = 0; iter < total && !rc; ++iter) {
     rc = sweep(ch, false);
     if (rc) break;
     if (verbose == 1 || verbose == 2) fprintf(stderr, "[DEBUG] - Iteration %lld of %d\n", iter, iterations + burnin);
     if (iter >= (long long)thinning * burnin && iter % thinning == 0) {
       Slot& S = ring[nkept % RING];
-      rc = consume(S);  // results are appended in order: the slot's previous occupant is RING snapshots old
-      if (rc) break;
+      // the slot's previous occupant (RING snapshots old) must have been unpacked
+      while (consumed.load(std::memory_order_acquire) < nkept - RING + 1 && !cons_rc.load(std::memory_order_acquire))
+        std::this_thread::sleep_for(std::chrono::microseconds(10));
+      if (cons_rc.load(std::memory_order_acquire)) break;
       const int cur = ch->cur;
       unsigned char* dslot = dstage + slot_bytes * (nkept % RING);
       snapshot_pack_kernel<<<148, 256, 0, ch->st>>>(ch->K, ch->status, ch->accepted_d, ch->loglik_d, ch->c, n, ch->cen[cur],
@@ -1422,10 +1450,15 @@ int smg_run_markov_chain(const double* data, int n, int p, const int* attrisize,
       }
       S.result_slot = iter / thinning - burnin;
       nkept++;
+      produced.store(nkept, std::memory_order_release);
     }
   }
-  // drain the ring in result order
-  for (long long q = std::max<long long>(0, nkept - RING); q < nkept && !rc; q++) rc = consume(ring[q % RING]);
+  // let the consumer drain the ring in result order
+  while (!rc && consumed.load(std::memory_order_acquire) < nkept && !cons_rc.load(std::memory_order_acquire))
+    std::this_thread::sleep_for(std::chrono::microseconds(20));
+  cons_stop.store(true, std::memory_order_release);
+  consumer.join();
+  if (!rc && cons_rc.load()) rc = fail(cons_rc.load(), cons_msg);
   if (!rc) rc = smg_snapshot(ch, nullptr, out->final_ass, nullptr, nullptr, 0, nullptr, nullptr);  // also checks the status
   auto t1 = std::chrono::steady_clock::now();
   out->seconds = std::chrono::duration<double>(t1 - t0).count();
