@@ -50,6 +50,9 @@ def parse():
     ap.add_argument("--no-psm", action="store_true", help="skip the tensor-core PSM measurement (n=2e4, C5 shape)")
     ap.add_argument("--c5-chains", type=int, default=64, help="extra: BASELINE config 5 -- this many chains of n=2e4 sharded over the GPUs, PSM + NCCL reductions (0: skip)")
     ap.add_argument("--c5-kept", type=int, default=24, help="kept sweeps per chain in the C5 job")
+    ap.add_argument("--c5-psm", default="fused", choices=["fused", "reduce_scatter", "all_reduce"],
+                    help="C5: PSM rows distributed over the ranks and every flush added into the owners' memories over NVLink "
+                         "(fused), or per-rank matrices reduced with NCCL at the end")
     ap.add_argument("--mixing-s", type=float, default=1.6, help="extra: Hamming scale of a harder data set on which the chain keeps moving (0: skip)")
     ap.add_argument("--no-random-start", action="store_true", help="skip the end-to-end call from the random start")
     ap.add_argument("--cpu-obs", type=int, default=600, help="observations of one pass timed by the faithful CPU baseline")
@@ -444,7 +447,7 @@ def main():
         tw0 = time.time()
         t0 = time.perf_counter()
         out5 = mc.run_chains_native(n5, a.c5_chains, mk, 40, a.c5_kept, rank=rank, world=world, unique_id=uid, device=local,
-                                    step_many=step_many, psm_mode="reduce_scatter", kmax=255, psm_capacity=256)
+                                    step_many=step_many, psm_mode=a.c5_psm, kmax=255, psm_capacity=256)
         c5_local = time.perf_counter() - t0
         barrier()
         windows.append((tw0, time.time()))
@@ -459,7 +462,10 @@ def main():
                       "psm_diag_ok": (None if diag is None else bool(diag[out5["psm_rows"][0]] == a.c5_chains * a.c5_kept)),
                       "rhat_K": out5.get("rhat_K"), "rhat_loglik": out5.get("rhat_loglik"), "n_chains_total": out5.get("n_chains_total"),
                       "K_hist_total": int(out5["K_hist"].sum() + out5["K_hist_overflow"]),
-                      "note": "reductions inside libsmgibbs.so (NCCL bound with dlopen); sampling time excludes them"}
+                      "psm_last_flush_ms": out5["psm"].info()["last_flush_ms"],
+                      "note": "reductions inside libsmgibbs.so (NCCL bound with dlopen); sampling time excludes them.  psm_reduce "
+                              "'fused': the accumulation kernel adds every tile into the memory of the rank that owns its rows "
+                              "(CUDA IPC over NVLink), so there is no reduction step (psm_reduce_ms 0); 'reduce_scatter': ncclReduceScatter at the end"}
         for c_ in out5["chains"]:
             c_.close()
         out5["psm"].close()

@@ -49,7 +49,7 @@ EXPORTS = [
     "smg_debug_split_merge", "smg_debug_sm_terms", "smg_debug_aux_free", "smg_debug_initial_assignment", "smg_debug_time_ll_block", "smg_debug_scan_profile", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
     "smg_psm_flush", "smg_psm_finalize", "smg_psm_read", "smg_psm_info", "smg_psm_destroy", "smg_debug_psm_reference",
     "smg_comm_unique_id", "smg_comm_create", "smg_comm_destroy", "smg_chains_reduce_psm", "smg_chains_split_rhat",
-    "smg_chains_k_histogram", "smg_psm_point_estimate", "smg_chains_point_estimate", "smg_adjusted_rand_index", "smg_trace_ess",
+    "smg_chains_k_histogram", "smg_chains_psm_distribute", "smg_psm_point_estimate", "smg_chains_point_estimate", "smg_adjusted_rand_index", "smg_trace_ess",
 ]
 
 _lib = None
@@ -113,6 +113,7 @@ def load():
     lib.smg_comm_destroy.argtypes = [C.c_void_p]
     lib.smg_comm_destroy.restype = None
     lib.smg_chains_reduce_psm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, c_int_p, c_int_p, c_dbl_p, c_dbl_p]
+    lib.smg_chains_psm_distribute.argtypes = [C.c_void_p, C.c_void_p]
     lib.smg_chains_split_rhat.argtypes = [C.c_void_p, c_dbl_p, C.c_int, C.c_int, c_dbl_p, c_ll_p]
     lib.smg_chains_k_histogram.argtypes = [C.c_void_p, c_int_p, C.c_longlong, C.c_int, c_ll_p, c_ll_p]
     lib.smg_psm_point_estimate.argtypes = [C.c_void_p, C.c_int, C.c_int, c_int_p, C.c_int, C.c_longlong, c_ll_p, c_dbl_p]

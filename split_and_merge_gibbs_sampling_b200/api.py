@@ -438,6 +438,11 @@ class Comm:
         except Exception:
             pass
 
+    def distribute_psm(self, psm):
+        """Fused accumulation + reduce-scatter: from now on every flush of `psm` adds its tiles straight into the memory
+        of the rank that owns the rows (peer-mapped over NVLink).  Call on a fresh matrix, on every rank."""
+        lb.check(self.lib.smg_chains_psm_distribute(self.h, psm.h))
+
     def reduce_psm(self, psm, mode="reduce_scatter"):
         """Sums the PSM counts of all ranks in place.  Returns (row0, nrows, ms, bus_GBps): the rows of the reduced matrix
         this rank holds (all of them after an all-reduce)."""

@@ -178,6 +178,8 @@ def run_chains_native(n, n_chains, chain_factory, burnin, iterations, rank=0, wo
     bound with dlopen): chains sharded over `world` ranks (one process per GPU), the PSM of the local chains accumulated
     on the tensor cores into a library-owned int32 matrix, then ncclReduceScatter (rank g keeps the rows [g n/G, (g+1)
     n/G)) or ncclAllReduce, ncclAllReduce of the K histogram, ncclAllGather of the half-chain moments -> split-R-hat.
+    psm_mode "fused": no reduction at the end at all -- the matrix is distributed by rows over the ranks from the start and
+    every flush adds straight into the owners' memories (smg_chains_psm_distribute; n % world == 0).
     `unique_id`: the 128 bytes of Comm.unique_id() from rank 0 (shipped by the caller; not needed when world == 1)."""
     import time
     from .api import Comm, Psm
@@ -185,6 +187,9 @@ def run_chains_native(n, n_chains, chain_factory, burnin, iterations, rank=0, wo
     chains = [chain_factory(cid) for cid in mine]
     comm = Comm(rank, world, unique_id, device)
     psm = Psm(n, device=device, capacity_sweeps=psm_capacity) if psm_mode != "none" else None
+    if psm is not None and psm_mode == "fused":
+        # accumulation and reduce-scatter in one kernel: every flush adds its tiles into the owners' memories (NVLink)
+        comm.distribute_psm(psm)
 
     def advance(k):
         if step_many is not None:

@@ -882,12 +882,27 @@ struct smg_psm {
   int* psm = nullptr;
   bool owns = false;
   bool lower_stale = false;  // flushes accumulate the upper triangle of tiles only; smg_psm_finalize mirrors it down
+  // distributed form (smg_chains_psm_distribute): rank / world of the communicator, rows per rank, the peers' matrices
+  smg_comm* dist = nullptr;
+  int rows_per = 0;
+  int** peers_d = nullptr;          // device array [world] of peer-mapped matrix pointers (own pointer at [rank])
+  std::vector<void*> peers_opened;  // IPC mappings to close
   uint8_t* labels = nullptr;
   cudaStream_t st = nullptr;
   unsigned long long launches = 0;
   double last_ms = 0.0;
   cudaEvent_t ev[2] = {};
 };
+
+// every rank of the communicator has reached this point and its stream `st` is idle
+static int comm_rendezvous(smg_comm* C) {
+  if (!C || C->world <= 1) return 0;
+  NcclApi* N = nccl_api();
+  SMG_NCCL(N->AllReduce(C->scratch, C->scratch, 1, ncclInt32, ncclSum, C->comm, C->st));
+  SMG_CUDA(cudaStreamSynchronize(C->st));
+  return 0;
+}
+
 
 template <int KP, int NST>
 static int psm_launch(smg_psm* P) {
@@ -897,7 +912,7 @@ static int psm_launch(smg_psm* P) {
   const char* mo = getenv("SMG_PSM_MMA_ONLY");
   static const bool full = [] { const char* e = getenv("SMG_PSM_FULL"); return e && e[0] == '1'; }();  // every tile (A/B measurements)
   psm_accumulate_kernel<KP, NST><<<grid, PSM_THREADS, smem, P->st>>>(P->labels, P->n, P->count, P->psm, (mo && mo[0] == '1') ? 1 : 0,
-                                                                     full ? 0 : 1);
+                                                                     full ? 0 : 1, P->peers_d, P->rows_per);
   P->lower_stale = true;
   SMG_CUDA(cudaGetLastError());
   return 0;
@@ -1982,6 +1997,11 @@ void smg_psm_destroy(smg_psm* P) {
   if (!P) return;
   cudaSetDevice(P->device);
   if (P->st) cudaStreamSynchronize(P->st);
+  if (P->peers_d) {  // distributed: unmap the peers' matrices, and free the own one only when nobody maps it any more
+    for (void* q : P->peers_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(P->peers_d);
+    comm_rendezvous(P->dist);
+  }
   if (P->owns && P->psm) cudaFree(P->psm);
   if (P->labels) cudaFree(P->labels);
   for (int q = 0; q < 2; q++)
@@ -2019,6 +2039,21 @@ int smg_psm_flush(smg_psm* P) {
 int smg_psm_finalize(smg_psm* P) {
   int rc = smg_psm_flush(P);
   if (rc) return rc;
+  if (P->peers_d) {
+    // Distributed matrix: every rank's flushes have added into the owners' memories (a flush returns when its kernel has
+    // completed); once all ranks are here the upper triangle is final, each rank copies it into the lower triangle of
+    // its own rows (reading the source rows from their owners), and nobody adds again before everybody has read.
+    // COLLECTIVE: every rank of the communicator calls this.
+    rc = comm_rendezvous(P->dist);
+    if (rc) return rc;
+    const int nb = cdiv(P->n, 32);
+    psm_mirror_dist_kernel<<<dim3(nb, nb), 256, 0, P->st>>>(P->peers_d, P->n, P->rows_per, P->dist->rank);
+    SMG_CUDA(cudaGetLastError());
+    SMG_CUDA(cudaStreamSynchronize(P->st));
+    P->launches++;
+    P->lower_stale = false;
+    return comm_rendezvous(P->dist);
+  }
   if (P->lower_stale) {
     const int nb = cdiv(P->n, 32);
     psm_mirror_kernel<<<dim3(nb, nb), 256, 0, P->st>>>(P->psm, P->n);
@@ -2188,6 +2223,13 @@ int smg_chains_reduce_psm(smg_comm* C, smg_psm* P, int mode, int* row0, int* nro
   SMG_CUDA(cudaSetDevice(C->device));
   int rc = smg_psm_finalize(P);
   if (rc) return rc;
+  if (P->peers_d) {  // already reduced and scattered by the accumulation kernel itself
+    if (row0) *row0 = C->rank * P->rows_per;
+    if (nrows) *nrows = P->rows_per;
+    if (ms) *ms = 0.0;
+    if (bus_gbs) *bus_gbs = 0.0;
+    return 0;
+  }
   const int n = P->n, G = C->world;
   const bool scatter = mode == 1 && G > 1 && n % G == 0;
   int r0 = 0, nr = n;
@@ -2224,6 +2266,51 @@ int smg_chains_reduce_psm(smg_comm* C, smg_psm* P, int mode, int* row0, int* nro
 // split-R-hat (BDA3 11.4) of a scalar trace over all chains of all ranks: every chain is cut in two halves, the
 // (count, mean, M2) moments of the halves are all-gathered, W = mean within-half variance, B = n * variance of the
 // half means, R-hat = sqrt(((n-1)/n W + B/n) / W).  traces: [nchains_local][T] on the host.
+// Deal the rows of a fresh matrix to the ranks and map every rank's matrix into every other rank's address space (CUDA IPC;
+// over NVLink between the GPUs of one box): from now on a flush adds its tiles into the owners' memories.
+int smg_chains_psm_distribute(smg_comm* C, smg_psm* P) {
+  if (!C || !P) return fail(SMG_ERR_ARG, "NULL argument");
+  if (C->device != P->device) return fail(SMG_ERR_ARG, "communicator and matrix live on different devices");
+  if (!P->owns) return fail(SMG_ERR_ARG, "an external matrix cannot be distributed (it must be the library's own allocation)");
+  if (P->peers_d) return fail(SMG_ERR_ARG, "the matrix is already distributed");
+  if (P->total != 0 || P->count != 0) return fail(SMG_ERR_ARG, "distribute the matrix before the first allocation is pushed");
+  const int G = C->world, n = P->n;
+  if (n % G) return fail(SMG_ERR_ARG, "n must be a multiple of the number of ranks");
+  SMG_CUDA(cudaSetDevice(C->device));
+  SMG_CUDA(cudaStreamSynchronize(P->st));  // the matrix has been cleared
+  std::vector<int*> ptrs(G, nullptr);
+  ptrs[C->rank] = P->psm;
+  if (G > 1) {
+    NcclApi* N = nccl_api();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t mine;
+    SMG_CUDA(cudaIpcGetMemHandle(&mine, P->psm));
+    std::vector<cudaIpcMemHandle_t> all(G);
+    unsigned char* buf = reinterpret_cast<unsigned char*>(C->scratch);  // world * 1024 bytes
+    SMG_CUDA(cudaMemcpyAsync(buf + (size_t)C->rank * 64, &mine, 64, cudaMemcpyHostToDevice, C->st));
+    SMG_NCCL(N->AllGather(buf + (size_t)C->rank * 64, buf, 64, ncclUint8, C->comm, C->st));
+    SMG_CUDA(cudaMemcpyAsync(all.data(), buf, (size_t)G * 64, cudaMemcpyDeviceToHost, C->st));
+    SMG_CUDA(cudaStreamSynchronize(C->st));
+    for (int g = 0; g < G; g++) {
+      if (g == C->rank) continue;
+      void* q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, all[g], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        const std::string msg = std::string("cudaIpcOpenMemHandle of rank ") + std::to_string(g) + ": " + cudaGetErrorString(cudaGetLastError());
+        for (void* o : P->peers_opened) cudaIpcCloseMemHandle(o);
+        P->peers_opened.clear();
+        return fail(SMG_ERR_CUDA, msg);
+      }
+      P->peers_opened.push_back(q);
+      ptrs[g] = reinterpret_cast<int*>(q);
+    }
+  }
+  SMG_CUDA(cudaMalloc(&P->peers_d, (size_t)G * sizeof(int*)));
+  SMG_CUDA(cudaMemcpy(P->peers_d, ptrs.data(), (size_t)G * sizeof(int*), cudaMemcpyHostToDevice));
+  P->rows_per = n / G;
+  P->dist = C;
+  return comm_rendezvous(C);  // nobody adds into a matrix that is not mapped everywhere yet
+}
+
 int smg_chains_split_rhat(smg_comm* C, const double* traces, int nchains_local, int T, double* rhat, long long* nchains_total) {
   if (!C || !rhat || (nchains_local > 0 && !traces)) return fail(SMG_ERR_ARG, "NULL argument");
   if (nchains_local < 0 || T < 4) return fail(SMG_ERR_ARG, "need T >= 4 draws per chain");

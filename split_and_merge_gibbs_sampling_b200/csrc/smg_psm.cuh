@@ -16,6 +16,12 @@
 // Measured, n=2e4, KP=64: 2.6 POP/s (dense u8) at 256 buffered sweeps per flush, 3.1 at 1024; the same MMAs issued
 // back to back without tile generation (SMG_PSM_MMA_ONLY=1) reach 4.2.
 // Algorithmic work per flush: 2 * n^2 * KP * T integer ops; traffic: T * n label bytes in, n^2 * 4 bytes read+written once.
+//
+// Distributed form (smg_chains_psm_distribute): the rows of the matrix are dealt to the G ranks of a communicator in
+// blocks of n / G and every rank's matrix is mapped into every other rank's address space (CUDA IPC over NVLink).  The
+// epilogue then ADDS each tile straight into the memory of the rank that owns its rows -- red.global.add.s32, one
+// coalesced 128-byte row segment per warp instruction -- so the accumulation and the reduce-scatter over the GPUs are
+// one kernel: nothing is left to reduce at the end of the run.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -82,7 +88,7 @@ __device__ __forceinline__ uint32_t psm_tile_off(int row, int k) {
 template <int KP, int NST>
 __global__ void __launch_bounds__(PSM_THREADS, 2)
     psm_accumulate_kernel(const uint8_t* __restrict__ labels, int n, int T, int* __restrict__ psm, int mma_only,
-                          int upper_only) {
+                          int upper_only, int* const* __restrict__ peers, int rows_per) {
   constexpr int A_BYTES = PSM_M * KP, B_BYTES = PSM_N * KP, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t s_free[NST];
@@ -212,7 +218,21 @@ __global__ void __launch_bounds__(PSM_THREADS, 2)
             "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (row < n) {
+      if (peers) {
+        // distributed matrix: through a per-warp 32 x 33 staging tile (the operand stages are free by now) so that a warp
+        // instruction adds 32 consecutive columns of ONE row -- a single 128-byte segment of the owner's memory
+        int* tile = reinterpret_cast<int*>(smem) + warp * (32 * 33);
+#pragma unroll
+        for (int e = 0; e < 32; e++) tile[lane * 33 + e] = (int)v[e];
+        __syncwarp();
+        const int col = n0 + col0 + lane;
+        for (int r = 0; r < 32; r++) {
+          const int rr = m0 + 32 * q + r;
+          const int val = tile[r * 33 + lane];
+          if (rr < n && col < n && val) atomicAdd(peers[rr / rows_per] + (size_t)rr * n + col, val);
+        }
+        __syncwarp();
+      } else if (row < n) {
         int* out = psm + (size_t)row * n + n0 + col0;
         if (n0 + col0 + 32 <= n && (n & 3) == 0) {
 #pragma unroll
@@ -266,6 +286,26 @@ __global__ void __launch_bounds__(256) psm_mirror_kernel(int* __restrict__ psm, 
   for (int r = ty; r < 32; r += 8) {
     const int i = bj * 32 + r, j = bi * 32 + tx;  // destination (i, j) = source (j, i)
     if (i < n && j < n && i > j) psm[(size_t)i * n + j] = tile[tx][r];
+  }
+}
+
+// distributed matrix: lower triangle of THIS rank's rows <- upper triangle, read from the rank that owns the source row
+__global__ void __launch_bounds__(256) psm_mirror_dist_kernel(int* const* __restrict__ peers, int n, int rows_per, int rank) {
+  __shared__ int tile[32][33];
+  const int bj = blockIdx.x, bi = blockIdx.y;  // source tile: rows bi*32.. (j), cols bj*32.. (i), bj >= bi
+  if (bj < bi) return;
+  const int i_lo = bj * 32, i_hi = min(n, i_lo + 32) - 1;  // destination rows
+  if (i_hi / rows_per < rank || i_lo / rows_per > rank) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int j = bi * 32 + r, i = bj * 32 + tx;
+    tile[r][tx] = (j < n && i < n) ? __ldcg(peers[j / rows_per] + (size_t)j * n + i) : 0;
+  }
+  __syncthreads();
+  int* mine = peers[rank];
+  for (int r = ty; r < 32; r += 8) {
+    const int i = bj * 32 + r, j = bi * 32 + tx;
+    if (i < n && j < n && i > j && i / rows_per == rank) mine[(size_t)i * n + j] = tile[tx][r];
   }
 }
 

@@ -108,3 +108,21 @@ def test_point_estimate_ari_and_ess_on_device_match_host():
     for r in range(3):
         assert abs(iat[r] - dg.iat(x[r])) <= 1e-9 * dg.iat(x[r])
         assert abs(ess[r] - dg.ess(x[r])) <= 1e-9 * dg.ess(x[r])
+
+
+@pytest.mark.parametrize("n,T,K,cap", [(512, 9, 12, 4), (1000, 70, 50, 32), (320, 5, 150, 8)])
+def test_psm_distributed_form_on_one_rank(n, T, K, cap):
+    """smg_chains_psm_distribute with a one-rank communicator: the epilogue that adds tiles into the owner's memory
+    (atomics through the peer table) and the distributed mirror give the same counts as numpy."""
+    from split_and_merge_gibbs_sampling_b200 import Comm, Psm
+    rng = np.random.default_rng(n + T)
+    labels = rng.integers(0, K, size=(T, n)).astype(np.int32)
+    C, P = Comm(), Psm(n, capacity_sweeps=cap)
+    C.distribute_psm(P)
+    for c in labels:
+        P.push(c)
+    r0, nr, ms, bus = C.reduce_psm(P, "reduce_scatter")
+    assert (r0, nr) == (0, n)
+    assert np.array_equal(P.read(), numpy_psm(labels))
+    P.close()
+    C.close()
