@@ -1288,8 +1288,10 @@ __global__ void __launch_bounds__(SM_CHAIN_T, 1) sm_chain_kernel(SmChainArgs A) 
     bool mg_done = false;
     if (do_scan) {
       bool have_dl = false;
-      const int nparts = A.phi.nparts, njs = (it < A.r) ? 3 : 2;
-      if (!prop && prev_settled && A.exc && (int)gridDim.x >= 2 * njs * nparts) {
+      // (parts per job of the speculative update: at most half of the gang works on it, the rest checks)
+      const int njs = (it < A.r) ? 3 : 2;
+      const int nparts = min(A.phi.nparts, phi_parts_for(pp, max(1, (int)gridDim.x / (2 * njs))));
+      if (!prop && prev_settled && A.exc && (int)gridDim.x >= njs * nparts + 8) {
         // ---- speculative scan: update (current pair -> spare pair) and the merged cluster's update on the first CTAs,
         //      the check and the next scan's logits on the others
         const int nxtA = curA == SM_SL_A ? SM_TMP0 : SM_SL_A, nxtB = curB == SM_SL_B ? SM_TMP1 : SM_SL_B;
