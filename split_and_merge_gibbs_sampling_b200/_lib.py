@@ -46,7 +46,7 @@ EXPORTS = [
     "smg_step", "smg_step_many", "smg_get_iteration", "smg_resume_at", "smg_validate_state", "smg_synth_generate", "smg_snapshot", "smg_destroy", "smg_get_stats", "smg_get_timings", "smg_last_step_ms", "smg_debug_set_state",
     "smg_debug_set_pool", "smg_debug_get_pool", "smg_debug_ll_block", "smg_debug_neal8_scan", "smg_debug_histogram",
     "smg_debug_update_phi", "smg_debug_loglik", "smg_debug_hig_inv_u", "smg_debug_logdensity_hig", "smg_debug_rhig_u",
-    "smg_debug_split_merge", "smg_debug_sm_terms", "smg_debug_aux_free", "smg_debug_initial_assignment", "smg_debug_time_ll_block", "smg_debug_scan_profile", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
+    "smg_debug_split_merge", "smg_debug_sm_terms", "smg_debug_aux_free", "smg_debug_initial_assignment", "smg_debug_time_ll_block", "smg_debug_scan_profile", "smg_debug_scan_spec", "smg_debug_sm_profile", "smg_psm_create", "smg_psm_push_chain", "smg_psm_push_host",
     "smg_psm_flush", "smg_psm_finalize", "smg_psm_read", "smg_psm_info", "smg_psm_destroy", "smg_debug_psm_reference",
     "smg_comm_unique_id", "smg_comm_create", "smg_comm_destroy", "smg_chains_reduce_psm", "smg_chains_split_rhat",
     "smg_chains_k_histogram", "smg_chains_psm_distribute", "smg_psm_point_estimate", "smg_chains_point_estimate", "smg_adjusted_rand_index", "smg_trace_ess",
@@ -96,6 +96,7 @@ def load():
     lib.smg_get_timings.argtypes = [C.c_void_p, c_dbl_p]
     lib.smg_last_step_ms.argtypes = [C.c_void_p, c_dbl_p]
     lib.smg_debug_scan_profile.argtypes = [C.c_void_p, c_ull_p]
+    lib.smg_debug_scan_spec.argtypes = [C.c_void_p, C.c_int, c_ull_p]
     lib.smg_debug_time_ll_block.argtypes = [C.c_void_p, C.c_int, c_dbl_p]
     lib.smg_debug_sm_profile.argtypes = [C.c_void_p, c_ull_p]
     lib.smg_psm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]

@@ -182,10 +182,17 @@ class Chain:
         keys = ["scan_rounds", "scan_events", "births", "deaths", "sweeps", "launches", "sm_proposals", "sm_accepted"]
         return dict(zip(keys, (int(x) for x in out)))
 
+    def scan_spec(self, mode=-1):
+        """Set the scan's speculative-evaluation mode (0 off, 1 on, 2 on + self-check, -1 library default) and return its
+        counters since creation."""
+        out = np.zeros(4, dtype=np.uint64)
+        lb.check(self.lib.smg_debug_scan_spec(self.h, int(mode), out.ctypes.data_as(lb.c_ull_p)))
+        return {"mismatches": int(out[0]), "reevaluated": int(out[1]), "dropped": int(out[2])}
+
     def scan_profile(self):
         out = np.zeros(16, dtype=np.uint64)
         lb.check(self.lib.smg_debug_scan_profile(self.h, out.ctypes.data_as(lb.c_ull_p)))
-        keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "_", "e8", "e9", "e10", "e11", "e12", "e13",
+        keys = ["prologue", "screen", "pick", "evaluate", "detect", "apply", "loop", "rows", "e8", "e9", "e10", "e11", "e12", "e13",
                 "e14", "e15"]
         return dict(zip(keys, (int(x) for x in out)))
 

@@ -369,6 +369,24 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed, bool prefet
   A.und0 = ch->und0;
   A.und_blk = ch->und_blk;
   A.prof = ch->scan_prof;
+  {
+    // speculative evaluation of the scan (SMG_SCAN_SPEC=0 switches it off, 2 adds the self-check; the tests run all three)
+    static const int spec = [] {
+      const char* e = getenv("SMG_SCAN_SPEC");
+      return e ? atoi(e) : 1;
+    }();
+    static const int rmax = [] {
+      const char* e = getenv("SMG_SCAN_SPEC_RMAX");
+      return e ? std::max(1, atoi(e)) : SCAN_SPEC_RMAX;
+    }();
+    static const double dmax = [] {
+      const char* e = getenv("SMG_SCAN_SPEC_DMAX");
+      return e ? atof(e) : 0.01;
+    }();
+    A.spec = ch->scan_spec >= 0 ? ch->scan_spec : spec;
+    A.spec_rmax = rmax;
+    A.spec_dmax = dmax;
+  }
   scan_margin_kernel<<<std::min(cdiv(ch->n, 8), 148 * 8), 256, 0, ch->st>>>(ch->n, ch->K, ch->ldl, ch->m_aux, ch->LL, A.LLaux,
                                                                           ch->c, ch->counts, A.log_gamma_m, A.u_alloc, A.u_stride, A.key, ch->mrg, ch->und0, ch->und_blk);
   neal8_scan_kernel<<<SCAN_CLUSTER, SMG_SCAN_WARPS * 32, SCAN_PF_BYTES, ch->st>>>(A);  // one cluster
@@ -1216,6 +1234,23 @@ int smg_synth_generate(int n, int p, const int* attrisize, int k_true, double s,
   std::copy(lab.begin(), lab.end(), labels_out);
   for (int k = 0; k < k_true; k++)
     for (int j = 0; j < p; j++) centres_out[(size_t)k * p + j] = cen[(size_t)k * pp + j];
+  return 0;
+}
+
+int smg_debug_scan_spec(smg_chain* ch, int mode, unsigned long long* out4) {
+  if (!ch) return fail(SMG_ERR_ARG, "NULL argument");
+  if (mode < -1 || mode > 2) return fail(SMG_ERR_ARG, "mode must be -1, 0, 1 or 2");
+  SMG_CUDA(cudaSetDevice(ch->device));
+  ch->scan_spec = mode;
+  if (out4) {
+    SMG_CUDA(cudaStreamSynchronize(ch->st));
+    unsigned long long d[8];
+    SMG_CUDA(d2h_sync(d, ch->stats_d, 64, ch->st));
+    out4[0] = d[4];
+    out4[1] = d[5];
+    out4[2] = d[6];
+    out4[3] = 0;
+  }
   return 0;
 }
 

@@ -147,6 +147,7 @@ struct smg_chain {
   unsigned long long* stats_d = nullptr;
   int* scan_job = nullptr;       // mailbox of the scan cluster
   unsigned long long* scan_prof = nullptr;  // cycle counters of the scanner's phases
+  int scan_spec = -1;                       // speculative evaluation of the scan: -1 library default, 0 / 1 / 2 (smg_debug_scan_spec)
   double* tape_d = nullptr;      // [n][m_aux+1] injected scan uniforms
   double *uc_d = nullptr, *us_d = nullptr;  // injected phi uniforms [NST][p]
   smg::SmWork* sm = nullptr;

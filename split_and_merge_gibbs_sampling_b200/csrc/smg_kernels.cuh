@@ -455,6 +455,11 @@ struct ScanArgs {
   unsigned long long* stats;  // [0] rounds, [1] events, [2] births, [3] deaths
   int* job;  // [4] mailbox of the scan cluster: {slot (-1: exit), first row, end row}
   unsigned long long* prof;  // [8] optional cycle counters of the scanner's phases (thread 0), or null
+  // speculative evaluation (see the scan kernel): 0 off, 1 on, 2 on and every speculated outcome checked by an exact
+  // evaluation under the state the row meets (stats[4] counts the differences -- must stay 0)
+  int spec;
+  int spec_rmax;      // rows evaluated per warp and speculation at most (<= SCAN_SPEC_RMAX)
+  double spec_dmax;   // drift (nats) after which the rest of a speculation is dropped and made again
 };
 
 #define EVT_NONE (-1)
@@ -636,7 +641,13 @@ struct ScanState {
   unsigned und[4 * SMG_SCAN_WARPS];  // undecided rows of the current block of 4096 observations (bit per row)
   int K, next, err;
   int serial_next;  // first row after a serial stretch of warp 0
-  unsigned long long stats[4];
+  unsigned long long stats[8];  // [4] speculation mismatches (spec = 2), [5] exact re-evaluations, [6] speculations dropped early
+  // speculative evaluation: log-counts the current speculation was evaluated with (by label), the drift since, and
+  // what the walk hands back to the block
+  double base_lc[64], base_lcm1[64];
+  double specD;
+  int spec_keep, walk_done, walk_start, walk_reason;
+  int arr[64], dep[64];  // arrivals / departures by label among the moves of a group of the walk (zero between uses)
 };
 
 // likelihood of observation i under a cluster whose column is not materialised (slot >= ldl: more births in
@@ -650,8 +661,12 @@ __device__ __noinline__ double scan_dyn_ll(const ScanArgs& A, int i, int slot, i
 // Exact allocation draw of observation i by one warp (neal8.cpp:40-102 + Rcpp::sample's descending-order
 // inverse CDF).  Entry e = q*32 + lane; NQ*32 >= K + m_aux.  Returns EVT_NONE when the draw leaves the
 // state unchanged, the selected entry (0..K+m-1) when it changes it, -2 when the weights are not finite.
-template <int NQ>
-__device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane) {
+//
+// TOL: also returns in *tol how far (nats) the log-counts may drift from the ones used here before the OUTCOME can change
+// (see "speculative evaluation" at the scan kernel); -1 when the draw must be repeated under the state it meets.
+template <int NQ, bool TOL = false>
+__device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane,
+                                             double* tol = nullptr) {
   const int m = A.m_aux, ne = K + m;
   const double* rowp = A.LL + (size_t)i * A.ldl;
   const double* auxp = A.LLaux + (size_t)i * m;
@@ -738,7 +753,9 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
   const double Ssum = warp_sum(lsum);
   const double T = u * Ssum;  // compared against the cumulative sums of the unnormalised weights
   int new_e;
+  bool fell = false;  // selected by the fall-through of the reference loop
   if (!(M > -CUDART_INF) || !(Ssum == Ssum)) {
+    if (TOL) *tol = -1.0;
     return -2;  // all -Inf or NaN: Rcpp::sample would stop()
   } else if (T <= 1.0) {
     new_e = argmax;  // first entry of the descending order already covers u
@@ -816,6 +833,7 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
     if (new_e < 0) {
       // fall-through of the reference loop: last entry of the descending order
       // (smallest probability, largest index among ties)
+      fell = true;
       uint64_t mink = ~0ull;
       int mine = -1;
 #pragma unroll
@@ -833,6 +851,57 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
       new_e = (int)__reduce_max_sync(SMG_FULL, (unsigned)((mink == wmin) ? mine : 0));
     }
   }
+  if (TOL) {
+    // With w_e the weights (count x likelihood), G the sum of the weights that precede the selected entry e* in the
+    // descending order and T = u * sum(w): e* is returned iff G < T <= G + w_e*.  If every log-count moves by at most
+    // D <= Dc, every weight moves by a factor within e^-D .. e^D, and only an entry whose log-weight lies within 2 Dc
+    // of e*'s can change place with it in the order.  With G_lo the sum over the entries that certainly precede e* and
+    // P_A the sum over the ones that may, the outcome is the same as long as
+    //   2D < log(T / (G_lo + P_A))   and   2D <= log((G_lo + w_e*) / T);
+    // or, with no entry allowed to change place with e* (2D below the smallest gap |log w_f - log w_e*|), as long as
+    //   2D < log(T / G)   and   2D <= log((G + w_e*) / T).
+    // A slack of 1e-9 nats covers the rounding of the sums (and the e^-44 cut-off of negligible entries, < 1e-17).
+    double tau = -1.0;
+    if (!singleton && !fell) {
+      const double Dc = A.spec_dmax;
+      double pstar = 0.0, lgstar = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; q++)
+        if (q == (new_e >> 5)) {
+          pstar = pe[q];
+          lgstar = lg[q];
+        }
+      pstar = shfl_d(pstar, new_e & 31);
+      lgstar = shfl_d(lgstar, new_e & 31);
+      // (two windows for "may change place": none -- then D must also stay below half the gap to the nearest
+      // log-weight -- and 2 Dc; the larger of the two tolerances holds)
+      double glo = 0.0, pa = 0.0, gex = 0.0, gap = CUDART_INF;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const int e = q * 32 + lane;
+        if (e < ne && e != new_e && lg[q] > -CUDART_INF) {
+          const double dl = lg[q] - lgstar;
+          if (dl > 2.0 * Dc)
+            glo += pe[q];
+          else if (dl >= -2.0 * Dc)
+            pa += pe[q];
+          if (pe[q] > pstar || (pe[q] == pstar && e < new_e)) gex += pe[q];
+          gap = fmin(gap, fabs(dl));
+        }
+      }
+      glo = warp_sum(glo);
+      pa = warp_sum(pa);
+      gex = warp_sum(gex);
+      gap = key_to_double(~warp_max_key(~sort_key(gap)));
+      const double up = log((glo + pstar) / T);
+      const double lo = (glo + pa) > 0.0 ? log(T / (glo + pa)) : CUDART_INF;
+      const double up1 = log((gex + pstar) / T);
+      const double lo1 = gex > 0.0 ? log(T / gex) : CUDART_INF;
+      tau = fmax(fmin(Dc, 0.5 * fmin(up, lo)), 0.5 * fmin(fmin(up1, lo1), gap)) - 1e-9;
+      if (!(tau == tau)) tau = -1.0;
+    }
+    *tol = tau;
+  }
   // ---- does the draw change the state?
   if (new_e < K) return (S.l2s[new_e] != old_slot) ? new_e : EVT_NONE;
   return (singleton && new_e == K) ? EVT_NONE : new_e;  // singleton re-drawing its own phi: no-op
@@ -849,7 +918,9 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 #define SCAN_SUPER 4  // chunks of 1024 observations screened and evaluated together
 #define SCAN_BLOCK (SCAN_SUPER * SCAN_CHUNK)
 #define SCAN_BLKCNT_MAX 1024  // per-block flag counts kept in shared memory (larger n: read from global)
-#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4)
+#define SCAN_SPEC_RMAX 64      // rows per warp in one speculation at most
+#define SCAN_SPEC_ROWS (SCAN_SPEC_RMAX * SMG_SCAN_WARPS)
+#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4 + SCAN_SPEC_ROWS * 10)
 __device__ __forceinline__ void scan_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -949,6 +1020,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     S.logcm1[s] = lcm1;
     S.l2s[s] = s;
     S.s2l[s] = (s < K0) ? s : -1;
+    if (s < 64) S.arr[s] = S.dep[s] = 0;
     if (s < SMG_MAX_ENTRIES) {
       S.lc0[s] = lc;
       S.lcm1_0[s] = lcm1;
@@ -961,7 +1033,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     S.err = 0;
     S.Dplus = 0.0;
     S.maxdm = 0.0;
-    S.stats[0] = S.stats[1] = S.stats[2] = S.stats[3] = 0;
+    for (int q = 0; q < 8; q++) S.stats[q] = 0;
     if (K0 + m > SMG_MAX_ENTRIES) S.err |= ST_TOO_MANY_ENTRIES;
     if (K0 > A.K0cap) S.err |= ST_LL_COLS;
   }
@@ -981,8 +1053,21 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     pc[k] += _t - tmark;             \
     tmark = _t;                      \
   } while (0)
+  long long wkc[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // the walk's: [0] group bounds, [1] prefix commit, [2] exact re-evaluation, [3] single move, [4..6] counts
+  long long wmark = 0;
+#define WALK_MARK() wmark = clock64()
+#define WALK_TICK(k)                 \
+  do {                               \
+    const long long _t = clock64();  \
+    wkc[k] += _t - wmark;            \
+    wmark = _t;                      \
+  } while (0)
+#define WALK_COUNT(k) wkc[k]++
 #else
 #define SCAN_TICK(k)
+#define WALK_MARK()
+#define WALK_TICK(k)
+#define WALK_COUNT(k)
 #endif
   if (S.err) {
     if (tid == 0) atomicOr(A.status, S.err);
@@ -994,6 +1079,13 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   double* ring_mg = reinterpret_cast<double*>(s_ring);                                    // [SCAN_BLOCK]
   int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [SCAN_BLOCK]
   int* s_blkcnt = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12);       // [SCAN_BLKCNT_MAX]
+  // results of a speculation, by ordinal of the row among the undecided rows it covers
+  float* spec_tau = reinterpret_cast<float*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS]
+  short* spec_row = reinterpret_cast<short*>(spec_tau + SCAN_SPEC_ROWS);                                        // [SCAN_SPEC_ROWS]
+  short* spec_code = spec_row + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS]
+  short* spec_own = spec_code + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS]
+  int R = 1;                // rows per warp of the next speculation (adapts)
+  bool one_legacy = false;  // the next round goes through the one-row-per-warp path (an event the walk does not apply)
   for (int b = tid; b < SCAN_BLKCNT_MAX && (long long)b * SCAN_BLOCK < n; b += blockDim.x) s_blkcnt[b] = A.und_blk[b];
   __syncthreads();
 
@@ -1061,7 +1153,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       // batch, warp 0 walks the rows one at a time on its own -- evaluate, apply, next -- until a stretch of
       // SCAN_DENSE_LEAVE rows without a move, the end of the block, or a draw the block must handle together
       // (a new cluster: its column is filled by the whole cluster of CTAs; an error).
-      if (dense_run >= SCAN_DENSE_ENTER && S.K + m <= 64) {
+      if (!A.spec && dense_run >= SCAN_DENSE_ENTER && S.K + m <= 64) {
         ring_wait();
         __syncthreads();
         if (warp == 0) {
@@ -1158,6 +1250,306 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         __syncthreads();   // S.und is rewritten
         continue;
       }
+
+      // ================= speculative evaluation =================
+      // Up to R undecided rows per warp are evaluated against the SAME state (the "base"), each with the drift of the
+      // log-counts its outcome tolerates (scan_eval_row<.., true>).  Warp 0 then walks the results in row order:
+      // a speculated move is applied when the drift accumulated since the base is below the row's tolerance, a
+      // speculated non-event is skipped under the same condition, and a row whose tolerance is used up is evaluated
+      // again, exactly, under the state it meets -- so the result is the one-at-a-time scan's, and a move costs one
+      // state update instead of a round of the whole block.  The walk hands back to the block for anything but a
+      // plain move (birth, last member leaving, error), when the block's screen has to be redone, and when the drift
+      // makes the remaining speculation not worth keeping (it is then made again from the new state).
+      if (A.spec && !one_legacy && S.K + m <= 64) {
+        const int K = S.K;
+        const int nb = min(R * SMG_SCAN_WARPS, total_und - consumed);
+        if (tid < K) {
+          const int sl = S.l2s[tid];
+          S.base_lc[tid] = S.logc[sl];
+          S.base_lcm1[tid] = S.logcm1[sl];
+        }
+        {
+          // lane l owns words SCAN_SUPER*l .. of the undecided bit map; ordinal -> row as in the batch path below
+          unsigned wb[SCAN_SUPER];
+          int wpc = 0;
+#pragma unroll
+          for (int k = 0; k < SCAN_SUPER; k++) {
+            wb[k] = S.und[SCAN_SUPER * lane + k];
+            wpc += __popc(wb[k]);
+          }
+          int incl = wpc;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(SMG_FULL, incl, o);
+            if (lane >= o) incl += y;
+          }
+          const int wpref = incl - wpc;
+          for (int j = warp; j < nb; j += SMG_SCAN_WARPS) {
+            const int t = consumed + j;
+            int found = -1;
+            if (t >= wpref && t < wpref + wpc) {
+              int off = t - wpref;
+#pragma unroll
+              for (int k = 0; k < SCAN_SUPER; k++) {
+                const int c = __popc(wb[k]);
+                if (found < 0 && off >= 0 && off < c) {
+                  unsigned bits = wb[k];
+                  for (int q = 0; q < off; q++) bits &= bits - 1;  // drop the `off` lowest set bits
+                  found = (SCAN_SUPER * lane + k) * 32 + __ffs(bits) - 1;
+                }
+                off -= c;
+              }
+            }
+            const unsigned hit = __ballot_sync(SMG_FULL, found >= 0);
+            const int myrow = __shfl_sync(SMG_FULL, found, __ffs(hit) - 1);
+            const int i = i0 + myrow;
+            const int old_slot = __ldcg(&A.c[i]);
+            double tol;
+            const int code = scan_eval_row<2, true>(A, S, i, old_slot, K, lane, &tol);
+#ifdef SMG_SCAN_PROFILE
+            if (tid == 0) {
+              {
+                const int bin = tol < 0.0 ? 0 : tol < 1e-4 ? 1 : tol < 1e-3 ? 2 : tol < 9e-3 ? 3 : 4;
+                if (code != EVT_NONE) wkc[1] += 1ll << (12 * bin); else wkc[2] += 1ll << (12 * bin);
+              }
+            }
+#endif
+            if (lane == 0) {
+              spec_row[j] = (short)myrow;
+              spec_code[j] = (short)code;
+              spec_own[j] = (short)old_slot;
+              spec_tau[j] = __double2float_rd(tol);
+            }
+          }
+        }
+        SCAN_TICK(3);
+        __syncthreads();
+        SCAN_TICK(4);
+#ifdef SMG_SCAN_PROFILE
+        pc[7] += nb;
+#endif
+        if (warp == 0) {
+          double D = 0.0;  // largest drift of a log-count since the base (running maximum)
+          int nfrag = 0, done = nb, next_start = -1, reason = 0;
+          auto dd = [](double x, double y) { return x == y ? 0.0 : fabs(x - y); };
+          for (int g = 0; g * 32 < nb && !reason; g++) {
+            const int jl = g * 32 + lane;
+            const bool have = jl < nb;
+            const int code_l = have ? (int)spec_code[jl] : EVT_NONE;
+            const double tau_l = have ? (double)spec_tau[jl] : CUDART_INF;
+            const int row_l = have ? (int)spec_row[jl] : -1;
+            const int own_l = have ? (int)spec_own[jl] : 0;
+            // a speculated move into an existing cluster ("plain"): the only kind the walk applies itself
+            const bool plain_l = have && code_l >= 0 && code_l < K;
+            const int ns_l = plain_l ? S.l2s[code_l] : 0;
+            const int oe_l = plain_l ? S.s2l[own_l] : 0;
+            unsigned live = __ballot_sync(SMG_FULL, have);
+            WALK_MARK();
+            while (live && !reason) {
+              const bool live_l = (live >> lane) & 1u;
+              WALK_COUNT(4);
+              // ---- (a) as many of the next rows as possible at once.  With a_k arrivals and d_k departures among the
+              // live moves of this group, the count of cluster k stays within [c_k - d_k, c_k + a_k] whatever the order,
+              // so its log-counts stay within  |now - base| + max(a/c, d/(c - d))  of the base: Dg bounds the drift
+              // every row of the group can meet.  The rows before the first one whose tolerance is below Dg (or that
+              // is not a plain move) are final as speculated: their moves are applied together.
+              const bool pl = plain_l && live_l;
+              if (pl) {
+                atomicAdd(&S.arr[code_l], 1);
+                atomicAdd(&S.dep[oe_l], 1);
+              }
+              __syncwarp();
+              double bound = 0.0, dmb = 0.0, dpb = 0.0, usedb = 0.0;
+              if (pl) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  const int sl = h ? own_l : ns_l, e = h ? oe_l : code_l;
+                  const int c = S.cnt[sl], a = S.arr[e], d = S.dep[e], lo = c - d;
+                  if (lo < 2) {
+                    bound = CUDART_INF;  // a cluster could get down to one member: one row at a time
+                  } else {
+                    // (upper bounds: single-precision reciprocals rounded up, times 1 + 2^-20 for the products)
+                    const float fa = (float)a * 1.000001f, fd = (float)d * 1.000001f;
+                    const double up0 = fa * __frcp_ru((float)c), dn0 = fd * __frcp_ru((float)lo);
+                    const double up1 = fa * __frcp_ru((float)(c - 1)), dn1 = fd * __frcp_ru((float)(lo - 1));
+                    bound = fmax(bound, dd(S.logc[sl], S.base_lc[e]) + fmax(up0, dn0));
+                    bound = fmax(bound, dd(S.logcm1[sl], S.base_lcm1[e]) + fmax(up1, dn1));
+                    // what the block's screen is told (upper bounds of the running maxima the one-at-a-time updates keep)
+                    if (sl < K0) {
+                      if (S.lcm1_0[sl] > -CUDART_INF) dmb = fmax(dmb, S.lcm1_0[sl] - S.logcm1[sl] + dn1);
+                      dpb = fmax(dpb, S.logc[sl] - S.lc0[sl] + up0);
+                    }
+                    if (h)
+                      usedb += 1.000001f * __frcp_ru((float)(lo - 1));
+                    else if (sl >= K0)
+                      usedb += 1.000001f * __frcp_ru((float)c);
+                  }
+                }
+              }
+              __syncwarp();
+              if (pl) {
+                S.arr[code_l] = 0;
+                S.dep[oe_l] = 0;
+              }
+              const double Dg = fmax(D, key_to_double(warp_max_key(sort_key(bound))));
+              unsigned frag = __ballot_sync(SMG_FULL, live_l && ((code_l != EVT_NONE && !plain_l) || !(tau_l > Dg)));
+              if (A.spec == 2) frag = live;  // self-check: every row goes through the exact evaluation below
+              const int f = frag ? __ffs(frag) - 1 : 32;
+              const unsigned pm = live & (f >= 32 ? 0xffffffffu : ((1u << f) - 1u));
+              const unsigned evp = __ballot_sync(SMG_FULL, pl) & pm;
+              int L = f;  // the row handled alone below (if any)
+              WALK_TICK(0);
+              if (pm) {
+                bool commit = true;
+                if (evp) {
+                  const bool mine = (evp >> lane) & 1u;
+                  // the screen of the block must survive the whole prefix
+                  const double maxdm1 = fmax(S.maxdm, key_to_double(warp_max_key(sort_key(mine ? dmb : 0.0))));
+                  const double dplus1 = fmax(S.Dplus, key_to_double(warp_max_key(sort_key(mine ? dpb : 0.0))));
+                  const double used = warp_sum(mine ? usedb : 0.0) + (dplus1 - S.Dplus);
+                  if (scr_kind == 2)
+                    commit = S.scr_used + used <= SCAN_RESCREEN_SLACK;
+                  else
+                    commit = scr_kind == 1 && S.next == K0 && maxdm1 + dplus1 <= SCAN_FAST_DRIFT;
+                  if (commit) {
+                    if (mine) {
+                      atomicAdd(&S.cnt[ns_l], 1);
+                      atomicSub(&S.cnt[own_l], 1);
+                      A.c[i0 + row_l] = ns_l;
+                    }
+                    __syncwarp();
+                    double dtrue = 0.0;
+                    if (mine) {
+#pragma unroll
+                      for (int h = 0; h < 2; h++) {  // (several lanes may write the same values for a cluster)
+                        const int sl = h ? own_l : ns_l, e = h ? oe_l : code_l;
+                        const int c = S.cnt[sl];
+                        const double lc = log((double)c), lcm1 = c > 1 ? log((double)(c - 1)) : -CUDART_INF;
+                        S.logc[sl] = lc;
+                        S.logcm1[sl] = lcm1;
+                        if (sl < K0) S.dminus[sl] = c > 1 ? S.lcm1_0[sl] - lcm1 : CUDART_INF;
+                        dtrue = fmax(dtrue, fmax(dd(lc, S.base_lc[e]), dd(lcm1, S.base_lcm1[e])));
+                      }
+                    }
+                    D = fmax(D, key_to_double(warp_max_key(sort_key(dtrue))));
+                    if (lane == 0) {
+                      S.maxdm = maxdm1;
+                      S.Dplus = dplus1;
+                      S.scr_used += used;
+                      S.stats[1] += __popc(evp);
+                    }
+                    __syncwarp();
+                    next_start = __shfl_sync(SMG_FULL, row_l, 31 - __clz(evp)) + 1;
+                  }
+                }
+                if (commit) {
+                  live &= ~pm;
+                  done = g * 32 + (32 - __clz(pm));
+                  if (evp && done < nb && !(D <= A.spec_dmax)) reason = 2;
+                  WALK_COUNT(5);
+                  continue;
+                }
+                L = __ffs(evp) - 1;  // the screen's allowance does not cover the prefix: its first move alone
+              }
+              // ---- (b) one row alone: exact evaluation when its tolerance is used up, anything but a plain move
+              // handed back to the block
+              int code = __shfl_sync(SMG_FULL, code_l, L);
+              const double tau = shfl_d(tau_l, L);
+              const bool robust = tau > D;
+              const int r = __shfl_sync(SMG_FULL, row_l, L);
+              const int own = __shfl_sync(SMG_FULL, own_l, L);
+              const int ie = i0 + r;
+              if (!robust && A.spec != 2 && g * 32 + L > 0) {
+                // Its tolerance is used up.  One warp evaluating one row is ~2000 dependent instructions; the whole
+                // block evaluating the next rows again from here costs about the same and covers 32 R of them.
+                reason = 2;
+                done = g * 32 + L;
+                nfrag++;
+                break;
+              }
+              if (!robust || A.spec == 2) {
+                const int exact = scan_eval_row<2>(A, S, ie, own, K, lane);
+                if (!robust)
+                  nfrag++;
+                else if (exact != code && lane == 0)
+                  S.stats[4]++;  // a speculated outcome that the state did not confirm: must never happen
+                code = exact;
+              }
+              WALK_COUNT(6);
+              live &= ~((2u << L) - 1u);
+              if (code == EVT_NONE) continue;
+              if (code < 0 || code >= K || S.cnt[own] == 1) {  // left to the block: the row is evaluated again there
+                reason = 3;
+                done = g * 32 + L;
+                next_start = r;
+                break;
+              }
+              if (lane == 0) {
+                const int ns = S.l2s[code];
+                const double dp0 = S.Dplus, dm0 = own < K0 ? S.dminus[own] : 0.0, lcn0 = S.logc[ns];
+                const int oe = S.s2l[own];
+                scan_apply_move(A, S, K0, ie, own, code);
+                double used = S.Dplus - dp0;
+                if (own < K0) used += S.dminus[own] - dm0;
+                if (ns >= K0) used += S.logc[ns] - lcn0;
+                S.scr_used += used;
+                bool keep;
+                if (scr_kind == 2)
+                  keep = S.scr_used <= SCAN_RESCREEN_SLACK;
+                else
+                  keep = scr_kind == 1 && S.next == K0 && S.maxdm + S.Dplus <= SCAN_FAST_DRIFT;
+                S.spec_keep = keep;
+                const double dn = fmax(dd(S.logc[ns], S.base_lc[code]), dd(S.logcm1[ns], S.base_lcm1[code]));
+                const double dow = fmax(dd(S.logc[own], S.base_lc[oe]), dd(S.logcm1[own], S.base_lcm1[oe]));
+                double Dn = fmax(D, fmax(dn, dow));
+                if (!(Dn == Dn)) Dn = CUDART_INF;
+                S.specD = Dn;
+              }
+              __syncwarp();
+              D = S.specD;
+              WALK_TICK(3);
+              done = g * 32 + L + 1;
+              next_start = r + 1;
+              if (!S.spec_keep) {
+                reason = 1;
+                break;
+              }
+              if (done < nb && (!(D <= A.spec_dmax) || nfrag > 8 + (done >> 4))) {
+                reason = 2;
+                break;
+              }
+            }
+          }
+          if (lane == 0) {
+            S.walk_done = done;
+            S.walk_start = next_start;
+            S.walk_reason = reason;
+            S.stats[0]++;
+            S.stats[5] += nfrag;
+            if (reason == 2) S.stats[6]++;
+          }
+        }
+        __syncthreads();
+        {
+          const int done = S.walk_done, reason = S.walk_reason;
+          if (S.walk_start >= 0) start = S.walk_start;
+          consumed += done;
+          if (reason == 0) {
+            R = max(1, min(2 * R, min(A.spec_rmax, SCAN_SPEC_RMAX)));
+            W = SMG_SCAN_WARPS;
+          } else if (reason == 1) {
+            screened = false;  // the remaining rows are screened again
+          } else if (reason == 2) {
+            R = max(1, min(R, (done + SMG_SCAN_WARPS - 1) / SMG_SCAN_WARPS));  // about as far as this one got
+          } else {
+            one_legacy = true;
+            W = 4;
+          }
+        }
+        SCAN_TICK(5);
+        continue;
+      }
+      one_legacy = false;
       // ================= batch: the next `nb` undecided rows, one warp each =================
       // (only the warps that evaluate a row run the selection; the others go straight to the barrier)
       const int nb = min(W, total_und - consumed);
@@ -1357,6 +1749,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   if (tid == 0 && A.prof) {
     pc[6] = clock64() - tstart;
     for (int q = 0; q < 8; q++) A.prof[q] += (unsigned long long)pc[q];
+    for (int q = 0; q < 8; q++) A.prof[8 + q] += (unsigned long long)wkc[q];
   }
 #endif
   for (int b = tid; b * SCAN_BLOCK < n; b += blockDim.x) A.und_blk[b] = 0;  // for the next pass
@@ -1372,7 +1765,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     *A.Kptr = S.K;
     if (S.K > A.K0cap) atomicOr(A.status, ST_LL_COLS);
     if (A.stats)
-      for (int q = 0; q < 4; q++) A.stats[q] += S.stats[q];
+      for (int q = 0; q < 7; q++) A.stats[q] += S.stats[q];  // ([7] belongs to the split-merge kernels)
   }
 }
 
