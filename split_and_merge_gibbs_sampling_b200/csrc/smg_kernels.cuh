@@ -648,6 +648,7 @@ struct ScanState {
   double specD;
   int spec_keep, walk_done, walk_start, walk_reason;
   int arr[64], dep[64];  // arrivals / departures by label among the moves of a group of the walk (zero between uses)
+  double fac[64], facm1[64];  // by label: e^(drift of log n_k) and e^(drift of log(n_k - 1)) since the base (entries >= K stay 1)
 };
 
 // likelihood of observation i under a cluster whose column is not materialised (slot >= ldl: more births in
@@ -664,9 +665,10 @@ __device__ __noinline__ double scan_dyn_ll(const ScanArgs& A, int i, int slot, i
 //
 // TOL: also returns in *tol how far (nats) the log-counts may drift from the ones used here before the OUTCOME can change
 // (see "speculative evaluation" at the scan kernel); -1 when the draw must be repeated under the state it meets.
+// wrow (TOL): the NQ*32 relative weights of the draw (0 beyond K + m) are left there, tol[1] = u, tol[2] = selected entry.
 template <int NQ, bool TOL = false>
 __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane,
-                                             double* tol = nullptr) {
+                                             double* tol = nullptr, double* wrow = nullptr) {
   const int m = A.m_aux, ne = K + m;
   const double* rowp = A.LL + (size_t)i * A.ldl;
   const double* auxp = A.LLaux + (size_t)i * m;
@@ -755,7 +757,11 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
   int new_e;
   bool fell = false;  // selected by the fall-through of the reference loop
   if (!(M > -CUDART_INF) || !(Ssum == Ssum)) {
-    if (TOL) *tol = -1.0;
+    if (TOL) {
+      tol[0] = -1.0;
+      tol[1] = u;
+      tol[2] = -1.0;
+    }
     return -2;  // all -Inf or NaN: Rcpp::sample would stop()
   } else if (T <= 1.0) {
     new_e = argmax;  // first entry of the descending order already covers u
@@ -900,7 +906,11 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
       tau = fmax(fmin(Dc, 0.5 * fmin(up, lo)), 0.5 * fmin(fmin(up1, lo1), gap)) - 1e-9;
       if (!(tau == tau)) tau = -1.0;
     }
-    *tol = tau;
+    tol[0] = tau;
+    tol[1] = u;
+    tol[2] = (double)new_e;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) wrow[q * 32 + lane] = pe[q];
   }
   // ---- does the draw change the state?
   if (new_e < K) return (S.l2s[new_e] != old_slot) ? new_e : EVT_NONE;
@@ -918,9 +928,10 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 #define SCAN_SUPER 4  // chunks of 1024 observations screened and evaluated together
 #define SCAN_BLOCK (SCAN_SUPER * SCAN_CHUNK)
 #define SCAN_BLKCNT_MAX 1024  // per-block flag counts kept in shared memory (larger n: read from global)
-#define SCAN_SPEC_RMAX 64      // rows per warp in one speculation at most
+#define SCAN_SPEC_RMAX 4       // rows per warp in one speculation at most
 #define SCAN_SPEC_ROWS (SCAN_SPEC_RMAX * SMG_SCAN_WARPS)
-#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4 + SCAN_SPEC_ROWS * 10)
+#define SCAN_SPEC_WSTRIDE 65   // doubles per row of the cached weights (64 entries + 1: lanes reading one entry of 32 rows hit 16 banks)
+#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4 + SCAN_SPEC_ROWS * (SCAN_SPEC_WSTRIDE * 8 + 8 + 4 + 8))
 __device__ __forceinline__ void scan_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -1020,7 +1031,10 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     S.logcm1[s] = lcm1;
     S.l2s[s] = s;
     S.s2l[s] = (s < K0) ? s : -1;
-    if (s < 64) S.arr[s] = S.dep[s] = 0;
+    if (s < 64) {
+      S.arr[s] = S.dep[s] = 0;
+      S.fac[s] = S.facm1[s] = 1.0;
+    }
     if (s < SMG_MAX_ENTRIES) {
       S.lc0[s] = lc;
       S.lcm1_0[s] = lcm1;
@@ -1080,10 +1094,13 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [SCAN_BLOCK]
   int* s_blkcnt = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12);       // [SCAN_BLKCNT_MAX]
   // results of a speculation, by ordinal of the row among the undecided rows it covers
-  float* spec_tau = reinterpret_cast<float*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS]
-  short* spec_row = reinterpret_cast<short*>(spec_tau + SCAN_SPEC_ROWS);                                        // [SCAN_SPEC_ROWS]
-  short* spec_code = spec_row + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS]
-  short* spec_own = spec_code + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS]
+  double* spec_w = reinterpret_cast<double*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS][SCAN_SPEC_WSTRIDE] relative weights
+  double* spec_u = spec_w + SCAN_SPEC_ROWS * SCAN_SPEC_WSTRIDE;                                                // [SCAN_SPEC_ROWS] allocation uniforms
+  float* spec_tau = reinterpret_cast<float*>(spec_u + SCAN_SPEC_ROWS);                                         // [SCAN_SPEC_ROWS]
+  short* spec_row = reinterpret_cast<short*>(spec_tau + SCAN_SPEC_ROWS);                                       // [SCAN_SPEC_ROWS]
+  short* spec_code = spec_row + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
+  short* spec_own = spec_code + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
+  short* spec_sel = spec_own + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS] selected entry (-1: none)
   int R = 1;                // rows per warp of the next speculation (adapts)
   bool one_legacy = false;  // the next round goes through the one-row-per-warp path (an event the walk does not apply)
   for (int b = tid; b < SCAN_BLKCNT_MAX && (long long)b * SCAN_BLOCK < n; b += blockDim.x) s_blkcnt[b] = A.und_blk[b];
@@ -1268,6 +1285,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
           S.base_lc[tid] = S.logc[sl];
           S.base_lcm1[tid] = S.logcm1[sl];
         }
+        if (tid < 64) S.fac[tid] = S.facm1[tid] = 1.0;
         {
           // lane l owns words SCAN_SUPER*l .. of the undecided bit map; ordinal -> row as in the batch path below
           unsigned wb[SCAN_SUPER];
@@ -1304,8 +1322,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             const int myrow = __shfl_sync(SMG_FULL, found, __ffs(hit) - 1);
             const int i = i0 + myrow;
             const int old_slot = __ldcg(&A.c[i]);
-            double tol;
-            const int code = scan_eval_row<2, true>(A, S, i, old_slot, K, lane, &tol);
+            double tol3[3];
+            const int code = scan_eval_row<2, true>(A, S, i, old_slot, K, lane, tol3, spec_w + j * SCAN_SPEC_WSTRIDE);
+            const double tol = tol3[0];
 #ifdef SMG_SCAN_PROFILE
             if (tid == 0) {
               {
@@ -1318,6 +1337,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               spec_row[j] = (short)myrow;
               spec_code[j] = (short)code;
               spec_own[j] = (short)old_slot;
+              spec_sel[j] = (short)(tol == -1.0 ? -1 : (int)tol3[2]);  // (-1: must be repeated under the state it meets)
+              spec_u[j] = tol3[1];
               spec_tau[j] = __double2float_rd(tol);
             }
           }
@@ -1332,6 +1353,14 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
           double D = 0.0;  // largest drift of a log-count since the base (running maximum)
           int nfrag = 0, done = nb, next_start = -1, reason = 0;
           auto dd = [](double x, double y) { return x == y ? 0.0 : fabs(x - y); };
+          // e^x for the drift of a log-count (5th-order series: error < 1e-13 for |x| <= 0.02; NaN beyond -- and for a
+          // count that fell to or rose from zero --, which fails every comparison below)
+          auto drift_factor = [](double now, double base) {
+            if (now == base) return 1.0;
+            const double x = now - base;
+            if (!(fabs(x) <= 0.02)) return CUDART_NAN;
+            return 1.0 + x * (1.0 + x * (1.0 / 2.0) * (1.0 + x * (1.0 / 3.0) * (1.0 + x * (1.0 / 4.0) * (1.0 + x * (1.0 / 5.0)))));
+          };
           for (int g = 0; g * 32 < nb && !reason; g++) {
             const int jl = g * 32 + lane;
             const bool have = jl < nb;
@@ -1339,6 +1368,46 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             const double tau_l = have ? (double)spec_tau[jl] : CUDART_INF;
             const int row_l = have ? (int)spec_row[jl] : -1;
             const int own_l = have ? (int)spec_own[jl] : 0;
+            const int sel_l = have ? (int)spec_sel[jl] : -1;
+            const double u_l = have ? spec_u[jl] : 0.5;
+            // Does the draw of this lane's row still return the entry it was speculated to, with every weight free to
+            // move by another factor within e^-gs .. e^gs?  The weights of the base are rescaled by the drift factors of
+            // the counts (own cluster: of n - 1); with G the sum of the weights above w_e* and T = u * sum(w):
+            //   no weight within (1 +- 2 gs) of w_e*,   G e^gs < T e^-gs,   T e^gs <= (G + w_e*) e^-gs
+            // (1e-9 relative on top: rounding of the cached weights, of the series and of the sums; the exact
+            // evaluation decides whatever is closer than that).
+            // (the whole warp works on the row of lane `src`: two entries per lane)
+            auto recheck = [&](int src, double gs) -> bool {
+              const int sel = __shfl_sync(SMG_FULL, sel_l, src), own = __shfl_sync(SMG_FULL, own_l, src);
+              const double u = shfl_d(u_l, src);
+              if (sel < 0 || !(gs <= 0.01) || S.cnt[own] < 2) return false;
+              const double* w = spec_w + (g * 32 + src) * SCAN_SPEC_WSTRIDE;
+              const int oe = S.s2l[own], ne = K + m;
+              double wf[2];
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const int e = q * 32 + lane;
+                wf[q] = e < ne ? w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
+              }
+              const double ws = shfl_d((sel >> 5) ? wf[1] : wf[0], sel & 31);
+              const double hib = ws * (1.0 + 2.02 * gs + 2e-9), lob = ws * (1.0 - 2.0 * gs - 2e-9);
+              double Gl = 0.0;
+              bool amb = false;
+#pragma unroll
+              for (int q = 0; q < 2; q++) {
+                const int e = q * 32 + lane;
+                if (e < ne && e != sel) {
+                  if (wf[q] > hib)
+                    Gl += wf[q];
+                  else if (wf[q] >= lob)
+                    amb = true;
+                }
+              }
+              const double sum = warp_sum(wf[0] + wf[1]), G = warp_sum(Gl);
+              if (__any_sync(SMG_FULL, amb)) return false;
+              const double T = u * sum, up = 1.0 + 1.01 * gs + 1e-9, dn = 1.0 - gs - 1e-9;
+              return ws > 0.0 && (G == 0.0 || T * dn > G * up) && (T * up <= (G + ws) * dn);
+            };
             // a speculated move into an existing cluster ("plain"): the only kind the walk applies itself
             const bool plain_l = have && code_l >= 0 && code_l < K;
             const int ns_l = plain_l ? S.l2s[code_l] : 0;
@@ -1359,14 +1428,14 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 atomicAdd(&S.dep[oe_l], 1);
               }
               __syncwarp();
-              double bound = 0.0, dmb = 0.0, dpb = 0.0, usedb = 0.0;
+              double bound = 0.0, dmb = 0.0, dpb = 0.0, usedb = 0.0, gsl = 0.0;
               if (pl) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   const int sl = h ? own_l : ns_l, e = h ? oe_l : code_l;
                   const int c = S.cnt[sl], a = S.arr[e], d = S.dep[e], lo = c - d;
                   if (lo < 2) {
-                    bound = CUDART_INF;  // a cluster could get down to one member: one row at a time
+                    bound = gsl = CUDART_INF;  // a cluster could get down to one member: one row at a time
                   } else {
                     // (upper bounds: single-precision reciprocals rounded up, times 1 + 2^-20 for the products)
                     const float fa = (float)a * 1.000001f, fd = (float)d * 1.000001f;
@@ -1374,6 +1443,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                     const double up1 = fa * __frcp_ru((float)(c - 1)), dn1 = fd * __frcp_ru((float)(lo - 1));
                     bound = fmax(bound, dd(S.logc[sl], S.base_lc[e]) + fmax(up0, dn0));
                     bound = fmax(bound, dd(S.logcm1[sl], S.base_lcm1[e]) + fmax(up1, dn1));
+                    gsl = fmax(gsl, fmax(up1, dn1));  // (>= up0, dn0)
                     // what the block's screen is told (upper bounds of the running maxima the one-at-a-time updates keep)
                     if (sl < K0) {
                       if (S.lcm1_0[sl] > -CUDART_INF) dmb = fmax(dmb, S.lcm1_0[sl] - S.logcm1[sl] + dn1);
@@ -1392,7 +1462,20 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 S.dep[oe_l] = 0;
               }
               const double Dg = fmax(D, key_to_double(warp_max_key(sort_key(bound))));
-              unsigned frag = __ballot_sync(SMG_FULL, live_l && ((code_l != EVT_NONE && !plain_l) || !(tau_l > Dg)));
+              bool ok_l = tau_l > Dg;
+              unsigned need = __ballot_sync(SMG_FULL, live_l && !ok_l && (code_l == EVT_NONE || plain_l));
+              if (need) {
+                const double gs = key_to_double(warp_max_key(sort_key(gsl)));
+                int budget = 6;  // (rows after the first few that fail are re-examined after the prefix before them is applied)
+                while (need && budget-- > 0) {
+                  const int src = __ffs(need) - 1;
+                  need &= need - 1;
+                  const bool ok = recheck(src, gs);
+                  if (lane == src) ok_l = ok;
+                  if (!ok) break;  // the prefix ends here anyway
+                }
+              }
+              unsigned frag = __ballot_sync(SMG_FULL, live_l && ((code_l != EVT_NONE && !plain_l) || !ok_l));
               if (A.spec == 2) frag = live;  // self-check: every row goes through the exact evaluation below
               const int f = frag ? __ffs(frag) - 1 : 32;
               const unsigned pm = live & (f >= 32 ? 0xffffffffu : ((1u << f) - 1u));
@@ -1428,6 +1511,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                         S.logc[sl] = lc;
                         S.logcm1[sl] = lcm1;
                         if (sl < K0) S.dminus[sl] = c > 1 ? S.lcm1_0[sl] - lcm1 : CUDART_INF;
+                        S.fac[e] = drift_factor(lc, S.base_lc[e]);
+                        S.facm1[e] = drift_factor(lcm1, S.base_lcm1[e]);
                         dtrue = fmax(dtrue, fmax(dd(lc, S.base_lc[e]), dd(lcm1, S.base_lcm1[e])));
                       }
                     }
@@ -1455,7 +1540,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               // handed back to the block
               int code = __shfl_sync(SMG_FULL, code_l, L);
               const double tau = shfl_d(tau_l, L);
-              const bool robust = tau > D;
+              bool robust = tau > D;
+              if (!robust) robust = recheck(L, 0.0);
               const int r = __shfl_sync(SMG_FULL, row_l, L);
               const int own = __shfl_sync(SMG_FULL, own_l, L);
               const int ie = i0 + r;
@@ -1501,6 +1587,10 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 S.spec_keep = keep;
                 const double dn = fmax(dd(S.logc[ns], S.base_lc[code]), dd(S.logcm1[ns], S.base_lcm1[code]));
                 const double dow = fmax(dd(S.logc[own], S.base_lc[oe]), dd(S.logcm1[own], S.base_lcm1[oe]));
+                S.fac[code] = drift_factor(S.logc[ns], S.base_lc[code]);
+                S.facm1[code] = drift_factor(S.logcm1[ns], S.base_lcm1[code]);
+                S.fac[oe] = drift_factor(S.logc[own], S.base_lc[oe]);
+                S.facm1[oe] = drift_factor(S.logcm1[own], S.base_lcm1[oe]);
                 double Dn = fmax(D, fmax(dn, dow));
                 if (!(Dn == Dn)) Dn = CUDART_INF;
                 S.specD = Dn;
