@@ -32,12 +32,6 @@ def main():
     tot = max(1, pr["loop"])
     print("   cycles/sweep:", {k: int(x / N) for k, x in pr.items() if x}, " shares:", {k: round(x / tot, 3) for k, x in pr.items() if x and k != "loop"})
     print(f"   us per event: {1e3 * acc / N / max(1.0, d['scan_events']):.2f}, cycles per round: {pr['loop'] / N / max(1.0, d['scan_rounds']):.0f}")
-    if pr.get("e15"):
-        print("   fragile rows: mean D %.2e, mean tau %.2e" % ((pr["e15"] & 0xffffffff) / 1e6 / max(1, ch.scan_spec()["reevaluated"] - sp0["reevaluated"]),
-                                                           (pr["e15"] >> 32) / 1e6 / max(1, ch.scan_spec()["reevaluated"] - sp0["reevaluated"])))
-    for nm, key in (("events", "e9"), ("non-events", "e10")):
-        v = pr.get(key, 0)
-        print("   tau histogram of", nm, "(warp 0; <0, <1e-4, <1e-3, <9e-3, more):", [(v >> (12 * b)) & 4095 for b in range(5)])
     sp1 = ch.scan_spec()
     print("   speculation per sweep:", {k: (sp1[k] - sp0[k]) / N for k in sp1}, "rounds/sweep", d["scan_rounds"])
     ch.close()

@@ -381,7 +381,7 @@ static int neal8_pass(smg_chain* ch, const double* tape, bool timed, bool prefet
     }();
     static const double dmax = [] {
       const char* e = getenv("SMG_SCAN_SPEC_DMAX");
-      return e ? atof(e) : 0.01;
+      return e ? std::min(0.1, atof(e)) : 0.05;
     }();
     A.spec = ch->scan_spec >= 0 ? ch->scan_spec : spec;
     A.spec_rmax = rmax;

@@ -16,6 +16,8 @@
 //   sden   fp64   [NS]        sum_j log(1+(m_j-1)/exp(1/sigma_j))
 //   LL     fp64   [n][ldl]    LL[i][slot] = -sum_j [x_ij != c_j]*isg_j - sden
 #pragma once
+#include <cooperative_groups.h>
+
 #include "smg_device.cuh"
 
 namespace smg {
@@ -648,6 +650,10 @@ struct ScanState {
   double specD;
   int spec_keep, walk_done, walk_start, walk_reason;
   int arr[64], dep[64];  // arrivals / departures by label among the moves of a group of the walk (zero between uses)
+  int sp_i0, sp_nb, sp_K;       // a speculation shared with the other CTAs of the cluster: first row of the block, rows, clusters
+  int wk_cmd, wk_j0, wk_K;      // job of the walk for the other warps: re-examine the rows `wk_need` of group wk_j0 / 32 (cmd 1: the walk is over)
+  unsigned wk_need, wk_ok;
+  double wk_gs;
   double fac[64], facm1[64];  // by label: e^(drift of log n_k) and e^(drift of log(n_k - 1)) since the base (entries >= K stay 1)
 };
 
@@ -869,7 +875,7 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
     // A slack of 1e-9 nats covers the rounding of the sums (and the e^-44 cut-off of negligible entries, < 1e-17).
     double tau = -1.0;
     if (!singleton && !fell) {
-      const double Dc = A.spec_dmax;
+      const double Dc = fmin(A.spec_dmax, 0.01);
       double pstar = 0.0, lgstar = 0.0;
 #pragma unroll
       for (int q = 0; q < NQ; q++)
@@ -986,6 +992,44 @@ __device__ __forceinline__ void scan_apply_move(const ScanArgs& A, ScanState& S,
   }
 }
 
+// Speculative evaluation, second line of defence (see the scan kernel): does the draw of a speculated row still return the
+// entry `sel` it was speculated to, under the current counts and with every weight free to move by another factor within
+// e^-gs .. e^gs?  The weights of the base (w[0 .. 63], relative to the largest) are rescaled by the drift factors of the
+// counts (own cluster: of n - 1); with G the sum of the weights above w_sel and T = u * sum(w):
+//   no weight within (1 +- 2 gs) of w_sel,   G e^gs < T e^-gs,   T e^gs <= (G + w_sel) e^-gs
+// (1e-9 relative on top: rounding of the cached weights, of the factors and of the sums; the exact evaluation decides
+// whatever is closer than that).  One warp per row, two entries per lane; the answer is uniform over the warp.
+__device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const double* w, int sel, int own, double u, double gs,
+                                                 int K, int m, int lane) {
+  if (sel < 0 || !(gs <= 0.01) || S.cnt[own] < 2) return false;
+  const int oe = S.s2l[own], ne = K + m;
+  double wf[2];
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int e = q * 32 + lane;
+    wf[q] = e < ne ? w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
+  }
+  const double ws = shfl_d((sel >> 5) ? wf[1] : wf[0], sel & 31);
+  const double hib = ws * (1.0 + 2.02 * gs + 2e-9), lob = ws * (1.0 - 2.0 * gs - 2e-9);
+  double Gl = 0.0;
+  bool amb = false;
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    const int e = q * 32 + lane;
+    if (e < ne && e != sel) {
+      if (wf[q] > hib)
+        Gl += wf[q];
+      else if (wf[q] >= lob)
+        amb = true;
+    }
+  }
+  const double sum = warp_sum(wf[0] + wf[1]), G = warp_sum(Gl);
+  if (__any_sync(SMG_FULL, amb)) return false;
+  const double T = u * sum, up = 1.0 + 1.01 * gs + 1e-9, dn = 1.0 - gs - 1e-9;
+  return ws > 0.0 && (G == 0.0 || T * dn > G * up) && (T * up <= (G + ws) * dn);
+}
+__device__ __forceinline__ void scan_walk_barrier() { asm volatile("bar.sync 1, 1024;" ::: "memory"); }  // all warps of the scan CTA
+
 // =============================================================================
 // K2: the scan proper (one resident CTA of 32 warps).
 //
@@ -1006,17 +1050,63 @@ __device__ __forceinline__ void scan_apply_move(const ScanArgs& A, ScanState& S,
 // =============================================================================
 __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_WARPS * 32, 1)
     neal8_scan_kernel(ScanArgs A) {
-  if (cluster_cta_rank() != 0) {  // ---- column-fill helpers
+  __shared__ ScanState S;
+  // staging buffers of the current block (see SCAN_PF_DEPTH) and results of a speculation, by ordinal of the row among
+  // the undecided rows it covers
+  extern __shared__ __align__(16) unsigned char s_ring[];
+  double* spec_w = reinterpret_cast<double*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS][SCAN_SPEC_WSTRIDE] relative weights
+  double* spec_u = spec_w + SCAN_SPEC_ROWS * SCAN_SPEC_WSTRIDE;                                                // [SCAN_SPEC_ROWS] allocation uniforms
+  float* spec_tau = reinterpret_cast<float*>(spec_u + SCAN_SPEC_ROWS);                                         // [SCAN_SPEC_ROWS]
+  short* spec_row = reinterpret_cast<short*>(spec_tau + SCAN_SPEC_ROWS);                                       // [SCAN_SPEC_ROWS]
+  short* spec_code = spec_row + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
+  short* spec_own = spec_code + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
+  short* spec_sel = spec_own + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS] selected entry (-1: none)
+  // one speculated row: exact draw of observation i0 + myrow against the state St, results into the arrays of the scan CTA
+  auto spec_eval = [&](const ScanState& St, int j, int myrow, int i0, int K, int lane_, double* w_, double* u_, float* tau_,
+                       short* code_, short* own_, short* sel_) {
+    const int i = i0 + myrow;
+    const int old_slot = __ldcg(&A.c[i]);
+    double tol3[3];
+    const int code = scan_eval_row<2, true>(A, St, i, old_slot, K, lane_, tol3, w_ + j * SCAN_SPEC_WSTRIDE);
+    if (lane_ == 0) {
+      code_[j] = (short)code;
+      own_[j] = (short)old_slot;
+      sel_[j] = (short)(tol3[0] == -1.0 ? -1 : (int)tol3[2]);  // (-1: must be repeated under the state it meets)
+      u_[j] = tol3[1];
+      tau_[j] = __double2float_rd(tol3[0]);
+    }
+  };
+  if (cluster_cta_rank() != 0) {  // ---- helpers: columns of clusters born in the pass, a share of the speculative evaluations
     const int lane_h = threadIdx.x & 31, warp_h = threadIdx.x >> 5;
+    const int rank_h = (int)cluster_cta_rank();
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
     for (;;) {
-      cluster_sync_all();  // the mailbox (and the new parameter vector) are published
+      cluster_sync_all();  // the mailbox (and the new parameter vector / the scan CTA's state) are published
       const int slot = __ldcg(&A.job[0]), r0 = __ldcg(&A.job[1]), r1 = __ldcg(&A.job[2]);
-      if (slot < 0) return;
-      scan_fill_column(A, slot, r0, r1, warp_h, lane_h, (int)cluster_cta_rank(), SCAN_CLUSTER);
-      cluster_sync_all();  // the column is complete
+      if (slot == -1) return;
+      if (slot == -2) {
+        // rows [32 rank, 32 rank + 32) of the speculation, one per warp, against a copy of the scan CTA's counts
+        const ScanState* S0 = cl.map_shared_rank(&S, 0);
+        const int i0 = S0->sp_i0, nb = S0->sp_nb, K = S0->sp_K;
+        for (int e = threadIdx.x; e < K; e += blockDim.x) {
+          const int sl = S0->l2s[e];
+          S.l2s[e] = sl;
+          S.cnt[sl] = S0->cnt[sl];
+          S.logc[sl] = S0->logc[sl];
+          S.logcm1[sl] = S0->logcm1[sl];
+        }
+        __syncthreads();
+        const int j = rank_h * SMG_SCAN_WARPS + warp_h;
+        if (j < nb)
+          spec_eval(S, j, (int)cl.map_shared_rank(spec_row, 0)[j], i0, K, lane_h, cl.map_shared_rank(spec_w, 0),
+                    cl.map_shared_rank(spec_u, 0), cl.map_shared_rank(spec_tau, 0), cl.map_shared_rank(spec_code, 0),
+                    cl.map_shared_rank(spec_own, 0), cl.map_shared_rank(spec_sel, 0));
+      } else {
+        scan_fill_column(A, slot, r0, r1, warp_h, lane_h, rank_h, SCAN_CLUSTER);
+      }
+      cluster_sync_all();  // the column is complete / the results are in the scan CTA's shared memory
     }
   }
-  __shared__ ScanState S;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = A.n, pp = A.pp, m = A.m_aux;
@@ -1088,19 +1178,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     abort_pass = true;
   }
 
-  // staging buffers of the current block (see SCAN_PF_DEPTH)
-  extern __shared__ __align__(16) unsigned char s_ring[];
   double* ring_mg = reinterpret_cast<double*>(s_ring);                                    // [SCAN_BLOCK]
   int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [SCAN_BLOCK]
   int* s_blkcnt = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12);       // [SCAN_BLKCNT_MAX]
-  // results of a speculation, by ordinal of the row among the undecided rows it covers
-  double* spec_w = reinterpret_cast<double*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS][SCAN_SPEC_WSTRIDE] relative weights
-  double* spec_u = spec_w + SCAN_SPEC_ROWS * SCAN_SPEC_WSTRIDE;                                                // [SCAN_SPEC_ROWS] allocation uniforms
-  float* spec_tau = reinterpret_cast<float*>(spec_u + SCAN_SPEC_ROWS);                                         // [SCAN_SPEC_ROWS]
-  short* spec_row = reinterpret_cast<short*>(spec_tau + SCAN_SPEC_ROWS);                                       // [SCAN_SPEC_ROWS]
-  short* spec_code = spec_row + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
-  short* spec_own = spec_code + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
-  short* spec_sel = spec_own + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS] selected entry (-1: none)
   int R = 1;                // rows per warp of the next speculation (adapts)
   bool one_legacy = false;  // the next round goes through the one-row-per-warp path (an event the walk does not apply)
   for (int b = tid; b < SCAN_BLKCNT_MAX && (long long)b * SCAN_BLOCK < n; b += blockDim.x) s_blkcnt[b] = A.und_blk[b];
@@ -1163,6 +1243,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
     int total_und = 0, consumed = 0;  // undecided rows from `start` on / already evaluated without an event
     int scr_kind = 0;                 // how the current bit map was made: 1 from the precomputed flags, 2 by the per-row screen
     int scr_rows = 0;                 // rows [start, scr_rows) are covered by the current screen
+    bool scr_all = false;             // every row the current screen covers is marked undecided: no drift can make it wrong
     for (;;) {
       // ================= serial stretch: one warp, no block barriers =================
       // While nearly every observation moves (burn-in from a random start) speculation over a batch buys nothing
@@ -1255,6 +1336,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
 #pragma unroll
         for (int k = 0; k < SCAN_SUPER; k++) pc += __popc(S.und[SCAN_SUPER * lane + k]);
         total_und = warp_sum_i(pc);
+        scr_all = total_und == scr_rows - start;
       }
       SCAN_TICK(1);
       if (consumed >= total_und) {  // every screened row from `start` on is final
@@ -1320,29 +1402,24 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             }
             const unsigned hit = __ballot_sync(SMG_FULL, found >= 0);
             const int myrow = __shfl_sync(SMG_FULL, found, __ffs(hit) - 1);
-            const int i = i0 + myrow;
-            const int old_slot = __ldcg(&A.c[i]);
-            double tol3[3];
-            const int code = scan_eval_row<2, true>(A, S, i, old_slot, K, lane, tol3, spec_w + j * SCAN_SPEC_WSTRIDE);
-            const double tol = tol3[0];
-#ifdef SMG_SCAN_PROFILE
-            if (tid == 0) {
-              {
-                const int bin = tol < 0.0 ? 0 : tol < 1e-4 ? 1 : tol < 1e-3 ? 2 : tol < 9e-3 ? 3 : 4;
-                if (code != EVT_NONE) wkc[1] += 1ll << (12 * bin); else wkc[2] += 1ll << (12 * bin);
-              }
-            }
-#endif
-            if (lane == 0) {
-              spec_row[j] = (short)myrow;
-              spec_code[j] = (short)code;
-              spec_own[j] = (short)old_slot;
-              spec_sel[j] = (short)(tol == -1.0 ? -1 : (int)tol3[2]);  // (-1: must be repeated under the state it meets)
-              spec_u[j] = tol3[1];
-              spec_tau[j] = __double2float_rd(tol);
-            }
+            if (lane == 0) spec_row[j] = (short)myrow;
           }
         }
+        // more than one row per warp: the other CTAs of the cluster take rows 32 .. nb - 1 (one per warp there too)
+        const bool wide = nb > SMG_SCAN_WARPS;
+        if (wide) {
+          if (tid == 0) {
+            S.sp_i0 = i0;
+            S.sp_nb = nb;
+            S.sp_K = K;
+            A.job[0] = -2;
+          }
+          cluster_sync_all();
+        } else {
+          __syncwarp();
+        }
+        if (warp < nb) spec_eval(S, warp, (int)spec_row[warp], i0, K, lane, spec_w, spec_u, spec_tau, spec_code, spec_own, spec_sel);
+        if (wide) cluster_sync_all();
         SCAN_TICK(3);
         __syncthreads();
         SCAN_TICK(4);
@@ -1353,13 +1430,20 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
           double D = 0.0;  // largest drift of a log-count since the base (running maximum)
           int nfrag = 0, done = nb, next_start = -1, reason = 0;
           auto dd = [](double x, double y) { return x == y ? 0.0 : fabs(x - y); };
-          // e^x for the drift of a log-count (5th-order series: error < 1e-13 for |x| <= 0.02; NaN beyond -- and for a
-          // count that fell to or rose from zero --, which fails every comparison below)
+          // e^x for the drift of a log-count (8th-order series: error < 1e-14 for |x| <= 0.125; NaN beyond -- and for a
+          // count that fell to or rose from zero --, which fails every comparison of scan_recheck_row)
           auto drift_factor = [](double now, double base) {
             if (now == base) return 1.0;
             const double x = now - base;
-            if (!(fabs(x) <= 0.02)) return CUDART_NAN;
-            return 1.0 + x * (1.0 + x * (1.0 / 2.0) * (1.0 + x * (1.0 / 3.0) * (1.0 + x * (1.0 / 4.0) * (1.0 + x * (1.0 / 5.0)))));
+            if (!(fabs(x) <= 0.125)) return CUDART_NAN;
+            double r = 1.0 + x * (1.0 / 8.0);
+            r = 1.0 + x * (1.0 / 7.0) * r;
+            r = 1.0 + x * (1.0 / 6.0) * r;
+            r = 1.0 + x * (1.0 / 5.0) * r;
+            r = 1.0 + x * (1.0 / 4.0) * r;
+            r = 1.0 + x * (1.0 / 3.0) * r;
+            r = 1.0 + x * (1.0 / 2.0) * r;
+            return 1.0 + x * r;
           };
           for (int g = 0; g * 32 < nb && !reason; g++) {
             const int jl = g * 32 + lane;
@@ -1368,46 +1452,6 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             const double tau_l = have ? (double)spec_tau[jl] : CUDART_INF;
             const int row_l = have ? (int)spec_row[jl] : -1;
             const int own_l = have ? (int)spec_own[jl] : 0;
-            const int sel_l = have ? (int)spec_sel[jl] : -1;
-            const double u_l = have ? spec_u[jl] : 0.5;
-            // Does the draw of this lane's row still return the entry it was speculated to, with every weight free to
-            // move by another factor within e^-gs .. e^gs?  The weights of the base are rescaled by the drift factors of
-            // the counts (own cluster: of n - 1); with G the sum of the weights above w_e* and T = u * sum(w):
-            //   no weight within (1 +- 2 gs) of w_e*,   G e^gs < T e^-gs,   T e^gs <= (G + w_e*) e^-gs
-            // (1e-9 relative on top: rounding of the cached weights, of the series and of the sums; the exact
-            // evaluation decides whatever is closer than that).
-            // (the whole warp works on the row of lane `src`: two entries per lane)
-            auto recheck = [&](int src, double gs) -> bool {
-              const int sel = __shfl_sync(SMG_FULL, sel_l, src), own = __shfl_sync(SMG_FULL, own_l, src);
-              const double u = shfl_d(u_l, src);
-              if (sel < 0 || !(gs <= 0.01) || S.cnt[own] < 2) return false;
-              const double* w = spec_w + (g * 32 + src) * SCAN_SPEC_WSTRIDE;
-              const int oe = S.s2l[own], ne = K + m;
-              double wf[2];
-#pragma unroll
-              for (int q = 0; q < 2; q++) {
-                const int e = q * 32 + lane;
-                wf[q] = e < ne ? w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
-              }
-              const double ws = shfl_d((sel >> 5) ? wf[1] : wf[0], sel & 31);
-              const double hib = ws * (1.0 + 2.02 * gs + 2e-9), lob = ws * (1.0 - 2.0 * gs - 2e-9);
-              double Gl = 0.0;
-              bool amb = false;
-#pragma unroll
-              for (int q = 0; q < 2; q++) {
-                const int e = q * 32 + lane;
-                if (e < ne && e != sel) {
-                  if (wf[q] > hib)
-                    Gl += wf[q];
-                  else if (wf[q] >= lob)
-                    amb = true;
-                }
-              }
-              const double sum = warp_sum(wf[0] + wf[1]), G = warp_sum(Gl);
-              if (__any_sync(SMG_FULL, amb)) return false;
-              const double T = u * sum, up = 1.0 + 1.01 * gs + 1e-9, dn = 1.0 - gs - 1e-9;
-              return ws > 0.0 && (G == 0.0 || T * dn > G * up) && (T * up <= (G + ws) * dn);
-            };
             // a speculated move into an existing cluster ("plain"): the only kind the walk applies itself
             const bool plain_l = have && code_l >= 0 && code_l < K;
             const int ns_l = plain_l ? S.l2s[code_l] : 0;
@@ -1462,17 +1506,38 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 S.dep[oe_l] = 0;
               }
               const double Dg = fmax(D, key_to_double(warp_max_key(sort_key(bound))));
+              WALK_TICK(0);
               bool ok_l = tau_l > Dg;
               unsigned need = __ballot_sync(SMG_FULL, live_l && !ok_l && (code_l == EVT_NONE || plain_l));
               if (need) {
                 const double gs = key_to_double(warp_max_key(sort_key(gsl)));
-                int budget = 6;  // (rows after the first few that fail are re-examined after the prefix before them is applied)
-                while (need && budget-- > 0) {
-                  const int src = __ffs(need) - 1;
-                  need &= need - 1;
-                  const bool ok = recheck(src, gs);
-                  if (lane == src) ok_l = ok;
-                  if (!ok) break;  // the prefix ends here anyway
+                if (__popc(need) >= 3) {
+                  // one row per warp, the whole CTA: the other warps wait for this in scan_walk_barrier()
+                  if (lane == 0) {
+                    S.wk_cmd = 0;
+                    S.wk_j0 = g * 32;
+                    S.wk_need = need;
+                    S.wk_ok = 0u;
+                    S.wk_gs = gs;
+                  }
+                  scan_walk_barrier();
+                  {
+                    const int src = __ffs(need) - 1;  // warp 0 takes the first one
+                    const int j = g * 32 + src;
+                    if (scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], gs, K, m, lane) && lane == 0)
+                      atomicOr(&S.wk_ok, 1u << src);
+                  }
+                  scan_walk_barrier();
+                  if ((need >> lane) & 1u) ok_l = (S.wk_ok >> lane) & 1u;
+                } else {
+                  while (need) {
+                    const int src = __ffs(need) - 1;
+                    need &= need - 1;
+                    const int j = g * 32 + src;
+                    const bool ok = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], gs, K, m, lane);
+                    if (lane == src) ok_l = ok;
+                    if (!ok) break;  // the prefix ends here anyway
+                  }
                 }
               }
               unsigned frag = __ballot_sync(SMG_FULL, live_l && ((code_l != EVT_NONE && !plain_l) || !ok_l));
@@ -1481,7 +1546,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               const unsigned pm = live & (f >= 32 ? 0xffffffffu : ((1u << f) - 1u));
               const unsigned evp = __ballot_sync(SMG_FULL, pl) & pm;
               int L = f;  // the row handled alone below (if any)
-              WALK_TICK(0);
+              WALK_TICK(1);
               if (pm) {
                 bool commit = true;
                 if (evp) {
@@ -1490,7 +1555,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                   const double maxdm1 = fmax(S.maxdm, key_to_double(warp_max_key(sort_key(mine ? dmb : 0.0))));
                   const double dplus1 = fmax(S.Dplus, key_to_double(warp_max_key(sort_key(mine ? dpb : 0.0))));
                   const double used = warp_sum(mine ? usedb : 0.0) + (dplus1 - S.Dplus);
-                  if (scr_kind == 2)
+                  if (scr_all)
+                    commit = true;
+                  else if (scr_kind == 2)
                     commit = S.scr_used + used <= SCAN_RESCREEN_SLACK;
                   else
                     commit = scr_kind == 1 && S.next == K0 && maxdm1 + dplus1 <= SCAN_FAST_DRIFT;
@@ -1532,6 +1599,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                   done = g * 32 + (32 - __clz(pm));
                   if (evp && done < nb && !(D <= A.spec_dmax)) reason = 2;
                   WALK_COUNT(5);
+                  WALK_TICK(2);
                   continue;
                 }
                 L = __ffs(evp) - 1;  // the screen's allowance does not cover the prefix: its first move alone
@@ -1541,7 +1609,10 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               int code = __shfl_sync(SMG_FULL, code_l, L);
               const double tau = shfl_d(tau_l, L);
               bool robust = tau > D;
-              if (!robust) robust = recheck(L, 0.0);
+              if (!robust) {
+                const int j = g * 32 + L;
+                robust = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], 0.0, K, m, lane);
+              }
               const int r = __shfl_sync(SMG_FULL, row_l, L);
               const int own = __shfl_sync(SMG_FULL, own_l, L);
               const int ie = i0 + r;
@@ -1580,7 +1651,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 if (ns >= K0) used += S.logc[ns] - lcn0;
                 S.scr_used += used;
                 bool keep;
-                if (scr_kind == 2)
+                if (scr_all)
+                  keep = true;
+                else if (scr_kind == 2)
                   keep = S.scr_used <= SCAN_RESCREEN_SLACK;
                 else
                   keep = scr_kind == 1 && S.next == K0 && S.maxdm + S.Dplus <= SCAN_FAST_DRIFT;
@@ -1617,6 +1690,21 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             S.stats[0]++;
             S.stats[5] += nfrag;
             if (reason == 2) S.stats[6]++;
+            S.wk_cmd = 1;
+          }
+          scan_walk_barrier();
+        } else {
+          for (;;) {
+            scan_walk_barrier();
+            if (S.wk_cmd) break;
+            const unsigned need = S.wk_need;
+            if (warp < __popc(need)) {
+              const int src = __fns(need, 0, warp + 1);  // the (warp+1)-th row of the job
+              const int j = S.wk_j0 + src;
+              if (scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], S.wk_gs, K, m, lane) && lane == 0)
+                atomicOr(&S.wk_ok, 1u << src);
+            }
+            scan_walk_barrier();
           }
         }
         __syncthreads();
