@@ -1182,6 +1182,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   int* ring_own = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 8);         // [SCAN_BLOCK]
   int* s_blkcnt = reinterpret_cast<int*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12);       // [SCAN_BLKCNT_MAX]
   int R = 1;                // rows per warp of the next speculation (adapts)
+  int hot = 0;              // > 0 while moves are being found: a quiet stretch (a handful of undecided rows per block, none of
+                            // which moves) goes through the plain rounds, which cost less when nothing is applied
   bool one_legacy = false;  // the next round goes through the one-row-per-warp path (an event the walk does not apply)
   for (int b = tid; b < SCAN_BLKCNT_MAX && (long long)b * SCAN_BLOCK < n; b += blockDim.x) s_blkcnt[b] = A.und_blk[b];
   __syncthreads();
@@ -1359,7 +1361,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       // state update instead of a round of the whole block.  The walk hands back to the block for anything but a
       // plain move (birth, last member leaving, error), when the block's screen has to be redone, and when the drift
       // makes the remaining speculation not worth keeping (it is then made again from the new state).
-      if (A.spec && !one_legacy && S.K + m <= 64) {
+      if (A.spec && (hot > 0 || A.spec == 2) && !one_legacy && S.K + m <= 64) {
         const int K = S.K;
         const int nb = min(R * SMG_SCAN_WARPS, total_und - consumed);
         if (tid < K) {
@@ -1710,6 +1712,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         __syncthreads();
         {
           const int done = S.walk_done, reason = S.walk_reason;
+          hot = (S.walk_start >= 0 || reason) ? 16 : hot - 1;
           if (S.walk_start >= 0) start = S.walk_start;
           consumed += done;
           if (reason == 0) {
@@ -1797,6 +1800,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       }
       SCAN_TICK(4);
       const int first = __ffs(evm) - 1;
+      hot = 16;
       // event-dense stretches (burn-in): evaluating 32 rows per round only burns issue slots
       W = min(SMG_SCAN_WARPS, max(4, 2 * (first + 1)));
       dense_run = (first == 0) ? dense_run + 1 : 0;
