@@ -674,7 +674,7 @@ __device__ __noinline__ double scan_dyn_ll(const ScanArgs& A, int i, int slot, i
 // wrow (TOL): the NQ*32 relative weights of the draw (0 beyond K + m) are left there, tol[1] = u, tol[2] = selected entry.
 template <int NQ, bool TOL = false>
 __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState& S, int i, int old_slot, int K, int lane,
-                                             double* tol = nullptr, double* wrow = nullptr) {
+                                             double* tol = nullptr, float* wrow = nullptr) {
   const int m = A.m_aux, ne = K + m;
   const double* rowp = A.LL + (size_t)i * A.ldl;
   const double* auxp = A.LLaux + (size_t)i * m;
@@ -916,7 +916,7 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
     tol[1] = u;
     tol[2] = (double)new_e;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) wrow[q * 32 + lane] = pe[q];
+    for (int q = 0; q < NQ; q++) wrow[q * 32 + lane] = (float)pe[q];
   }
   // ---- does the draw change the state?
   if (new_e < K) return (S.l2s[new_e] != old_slot) ? new_e : EVT_NONE;
@@ -936,8 +936,12 @@ __device__ __forceinline__ int scan_eval_row(const ScanArgs& A, const ScanState&
 #define SCAN_BLKCNT_MAX 1024  // per-block flag counts kept in shared memory (larger n: read from global)
 #define SCAN_SPEC_RMAX 4       // rows per warp in one speculation at most
 #define SCAN_SPEC_ROWS (SCAN_SPEC_RMAX * SMG_SCAN_WARPS)
-#define SCAN_SPEC_WSTRIDE 65   // doubles per row of the cached weights (64 entries + 1: lanes reading one entry of 32 rows hit 16 banks)
-#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4 + SCAN_SPEC_ROWS * (SCAN_SPEC_WSTRIDE * 8 + 8 + 4 + 8))
+#define SCAN_SPEC_WSTRIDE 65   // floats per row of the cached weights (64 entries + 1)
+// The cached weights (33 KB) lie OVER the staging buffers of the block (48 KB), which a speculation does not read and which
+// are filled again on demand: with them beside the buffers the kernel needed the 164 KB shared-memory configuration instead
+// of the 100 KB one, and the 64 KB of L1 that went with it slowed every phase of a quiet pass (spills) by a few percent.
+#define SCAN_PF_BYTES (SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4 + SCAN_SPEC_ROWS * (8 + 4 + 8))
+static_assert(SCAN_SPEC_ROWS * SCAN_SPEC_WSTRIDE * 4 <= SCAN_PF_DEPTH * SCAN_CHUNK * 12, "cached weights fit the staging buffers");
 __device__ __forceinline__ void scan_cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -997,9 +1001,9 @@ __device__ __forceinline__ void scan_apply_move(const ScanArgs& A, ScanState& S,
 // e^-gs .. e^gs?  The weights of the base (w[0 .. 63], relative to the largest) are rescaled by the drift factors of the
 // counts (own cluster: of n - 1); with G the sum of the weights above w_sel and T = u * sum(w):
 //   no weight within (1 +- 2 gs) of w_sel,   G e^gs < T e^-gs,   T e^gs <= (G + w_sel) e^-gs
-// (1e-9 relative on top: rounding of the cached weights, of the factors and of the sums; the exact evaluation decides
-// whatever is closer than that).  One warp per row, two entries per lane; the answer is uniform over the warp.
-__device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const double* w, int sel, int own, double u, double gs,
+// (5e-7 relative on top: the cached weights are single precision, 6e-8 each; the exact evaluation decides whatever is
+// closer than that).  One warp per row, two entries per lane; the answer is uniform over the warp.
+__device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const float* w, int sel, int own, double u, double gs,
                                                  int K, int m, int lane) {
   if (sel < 0 || !(gs <= 0.01) || S.cnt[own] < 2) return false;
   const int oe = S.s2l[own], ne = K + m;
@@ -1007,10 +1011,10 @@ __device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const doubl
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     const int e = q * 32 + lane;
-    wf[q] = e < ne ? w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
+    wf[q] = e < ne ? (double)w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
   }
   const double ws = shfl_d((sel >> 5) ? wf[1] : wf[0], sel & 31);
-  const double hib = ws * (1.0 + 2.02 * gs + 2e-9), lob = ws * (1.0 - 2.0 * gs - 2e-9);
+  const double hib = ws * (1.0 + 2.02 * gs + 1e-6), lob = ws * (1.0 - 2.0 * gs - 1e-6);
   double Gl = 0.0;
   bool amb = false;
 #pragma unroll
@@ -1025,7 +1029,7 @@ __device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const doubl
   }
   const double sum = warp_sum(wf[0] + wf[1]), G = warp_sum(Gl);
   if (__any_sync(SMG_FULL, amb)) return false;
-  const double T = u * sum, up = 1.0 + 1.01 * gs + 1e-9, dn = 1.0 - gs - 1e-9;
+  const double T = u * sum, up = 1.0 + 1.01 * gs + 5e-7, dn = 1.0 - gs - 5e-7;
   return ws > 0.0 && (G == 0.0 || T * dn > G * up) && (T * up <= (G + ws) * dn);
 }
 __device__ __forceinline__ void scan_walk_barrier() { asm volatile("bar.sync 1, 1024;" ::: "memory"); }  // all warps of the scan CTA
@@ -1054,15 +1058,15 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
   // staging buffers of the current block (see SCAN_PF_DEPTH) and results of a speculation, by ordinal of the row among
   // the undecided rows it covers
   extern __shared__ __align__(16) unsigned char s_ring[];
-  double* spec_w = reinterpret_cast<double*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS][SCAN_SPEC_WSTRIDE] relative weights
-  double* spec_u = spec_w + SCAN_SPEC_ROWS * SCAN_SPEC_WSTRIDE;                                                // [SCAN_SPEC_ROWS] allocation uniforms
+  float* spec_w = reinterpret_cast<float*>(s_ring);  // [SCAN_SPEC_ROWS][SCAN_SPEC_WSTRIDE] relative weights, over the staging buffers
+  double* spec_u = reinterpret_cast<double*>(s_ring + SCAN_PF_DEPTH * SCAN_CHUNK * 12 + SCAN_BLKCNT_MAX * 4);  // [SCAN_SPEC_ROWS] allocation uniforms
   float* spec_tau = reinterpret_cast<float*>(spec_u + SCAN_SPEC_ROWS);                                         // [SCAN_SPEC_ROWS]
   short* spec_row = reinterpret_cast<short*>(spec_tau + SCAN_SPEC_ROWS);                                       // [SCAN_SPEC_ROWS]
   short* spec_code = spec_row + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
   short* spec_own = spec_code + SCAN_SPEC_ROWS;                                                                // [SCAN_SPEC_ROWS]
   short* spec_sel = spec_own + SCAN_SPEC_ROWS;                                                                 // [SCAN_SPEC_ROWS] selected entry (-1: none)
   // one speculated row: exact draw of observation i0 + myrow against the state St, results into the arrays of the scan CTA
-  auto spec_eval = [&](const ScanState& St, int j, int myrow, int i0, int K, int lane_, double* w_, double* u_, float* tau_,
+  auto spec_eval = [&](const ScanState& St, int j, int myrow, int i0, int K, int lane_, float* w_, double* u_, float* tau_,
                        short* code_, short* own_, short* sel_) {
     const int i = i0 + myrow;
     const int old_slot = __ldcg(&A.c[i]);
@@ -1712,7 +1716,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
         __syncthreads();
         {
           const int done = S.walk_done, reason = S.walk_reason;
-          hot = (S.walk_start >= 0 || reason) ? 16 : hot - 1;
+          hot = (S.walk_start >= 0 || reason) ? 4 : hot - 1;
           if (S.walk_start >= 0) start = S.walk_start;
           consumed += done;
           if (reason == 0) {
@@ -1727,6 +1731,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             W = 4;
           }
         }
+        ring_ready = false;  // (the cached weights lie over the staging buffers)
         SCAN_TICK(5);
         continue;
       }
@@ -1800,7 +1805,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
       }
       SCAN_TICK(4);
       const int first = __ffs(evm) - 1;
-      hot = 16;
+      hot = 4;
       // event-dense stretches (burn-in): evaluating 32 rows per round only burns issue slots
       W = min(SMG_SCAN_WARPS, max(4, 2 * (first + 1)));
       dense_run = (first == 0) ? dense_run + 1 : 0;
