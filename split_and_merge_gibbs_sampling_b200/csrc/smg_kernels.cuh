@@ -1463,6 +1463,10 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             const int ns_l = plain_l ? S.l2s[code_l] : 0;
             const int oe_l = plain_l ? S.s2l[own_l] : 0;
             unsigned live = __ballot_sync(SMG_FULL, have);
+            // bounds of the group (below); they hold until a row is decided by an exact evaluation, whose outcome may
+            // differ from the speculated one they were made with
+            bool bounds_valid = false;
+            double dmb = 0.0, dpb = 0.0, usedb = 0.0, Bg = 0.0, gs = 0.0;
             WALK_MARK();
             while (live && !reason) {
               const bool live_l = (live >> lane) & 1u;
@@ -1472,13 +1476,17 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               // so its log-counts stay within  |now - base| + max(a/c, d/(c - d))  of the base: Dg bounds the drift
               // every row of the group can meet.  The rows before the first one whose tolerance is below Dg (or that
               // is not a plain move) are final as speculated: their moves are applied together.
+              // (a_k and d_k count every move of the group that is still to come when they are made; the ones applied
+              // since are part of them, so the bounds hold for the rest of the group.)
               const bool pl = plain_l && live_l;
+              if (!bounds_valid) {
               if (pl) {
                 atomicAdd(&S.arr[code_l], 1);
                 atomicAdd(&S.dep[oe_l], 1);
               }
               __syncwarp();
-              double bound = 0.0, dmb = 0.0, dpb = 0.0, usedb = 0.0, gsl = 0.0;
+              double bound = 0.0, gsl = 0.0;
+              dmb = dpb = usedb = 0.0;
               if (pl) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -1511,12 +1519,15 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 S.arr[code_l] = 0;
                 S.dep[oe_l] = 0;
               }
-              const double Dg = fmax(D, key_to_double(warp_max_key(sort_key(bound))));
+              Bg = key_to_double(warp_max_key(sort_key(bound)));
+              gs = key_to_double(warp_max_key(sort_key(gsl)));
+              bounds_valid = true;
+              }
+              const double Dg = fmax(D, Bg);
               WALK_TICK(0);
               bool ok_l = tau_l > Dg;
               unsigned need = __ballot_sync(SMG_FULL, live_l && !ok_l && (code_l == EVT_NONE || plain_l));
               if (need) {
-                const double gs = key_to_double(warp_max_key(sort_key(gsl)));
                 if (__popc(need) >= 3) {
                   // one row per warp, the whole CTA: the other warps wait for this in scan_walk_barrier()
                   if (lane == 0) {
@@ -1631,6 +1642,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 break;
               }
               if (!robust || A.spec == 2) {
+                bounds_valid = false;
                 const int exact = scan_eval_row<2>(A, S, ie, own, K, lane);
                 if (!robust)
                   nfrag++;
