@@ -1501,7 +1501,10 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                     const double up1 = fa * __frcp_ru((float)(c - 1)), dn1 = fd * __frcp_ru((float)(lo - 1));
                     bound = fmax(bound, dd(S.logc[sl], S.base_lc[e]) + fmax(up0, dn0));
                     bound = fmax(bound, dd(S.logcm1[sl], S.base_lcm1[e]) + fmax(up1, dn1));
-                    gsl = fmax(gsl, fmax(up1, dn1));  // (>= up0, dn0)
+                    // slack between ANY two states of the rest of the group (the rechecks rescale from the state they
+                    // meet, not from the one the bounds were made in): at any time the count is >= lo = c - d, at most a
+                    // arrivals and d departures are still to come, so |log n' - log n_t| <= max(a, d) / lo (n - 1: lo - 1)
+                    gsl = fmax(gsl, (double)(fmaxf(fa, fd) * __frcp_ru((float)(lo - 1))));
                     // what the block's screen is told (upper bounds of the running maxima the one-at-a-time updates keep)
                     if (sl < K0) {
                       if (S.lcm1_0[sl] > -CUDART_INF) dmb = fmax(dmb, S.lcm1_0[sl] - S.logcm1[sl] + dn1);
