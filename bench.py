@@ -417,6 +417,21 @@ def main():
                                   "the scan evaluates up to 128 undecided observations against one state with the count drift each outcome "
                                   "tolerates and applies the moves in order (DESIGN.md section 3, speculative evaluation; 6.6 us per move without it)"}
         cm.close()
+    # ---- extra: the first sweeps from the declared random start, one per call (device time of each)
+    if not a.no_random_start and rank == 0:
+        cb = Chain(X, attr, gamma, v, w, m=a.m_aux, L=a.k_true, t=a.t, r=a.r, neal8=True, split_merge=True, seed=a.seed + rank,
+                   device=local, compact_init=True, data_u8=True)
+        firsts, evs, prev = [], [], cb.stats()
+        for _ in range(6):
+            cb.step(1)
+            firsts.append(round(cb.timings()["total_ms"], 3))
+            stb = cb.stats()
+            evs.append(stb["scan_events"] - prev["scan_events"])
+            prev = stb
+        cb.close()
+        line["burn_in"] = {"first_sweeps_ms": firsts, "moves": evs,
+                           "note": "sweeps 1-6 from L random labels (the same chain as the timed one), CUDA-event time of each; "
+                                   "round 1 / start of round 2: 480, 288, 95, 24, 11, 4.8 ms"}
     # ---- extra: several independent chains of the metric shape stepped together on this GPU
     if a.multi_chains > 1:
         group = [Chain(X, attr, gamma, v, w, m=a.m_aux, L=a.k_true, t=a.t, r=a.r, neal8=True, split_merge=True,

@@ -68,3 +68,31 @@ def test_speculative_chain_equals_plain_chain_while_mixing():
         for a, b in zip(runs[0][0], runs[mode][0]):
             assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
     assert runs[1][1]["scan_rounds"] < runs[0][1]["scan_rounds"]  # the point of it: far fewer rounds of the whole block
+
+
+@pytest.mark.parametrize("seed,k_true,m_aux,gamma,s,L", [(11, 58, 5, 1.0, 1.4, 58), (12, 10, 3, 60.0, 1.3, 14), (13, 30, 4, 5.0, 1.6, 40)])
+def test_speculative_scan_near_capacity_and_with_births(seed, k_true, m_aux, gamma, s, L):
+    # 63 of the 64 entries of the two-per-lane evaluation in use; a large concentration parameter (clusters are born and
+    # closed inside the pass, so the walk hands rows back to the block and the born columns are filled between
+    # speculations); pool-free auxiliary components are covered by test_gpu_modes
+    pb = Problem(4000, 32, 4, k_true, seed=seed, s=s, gamma=gamma)
+    K, c, cen, sig = oracle_state_full(pb, mode="random", seed=seed, L=L, iters=1, m_aux=m_aux)
+    pc, ps = orc.draw_pool(pb.od, 257, seed + 1, o=orc.opts(stable_hig=1))
+    tape = _tape(pb.n, m_aux, seed)
+    ref = orc.neal8_scan(pb.od, m_aux, c, cen, sig, pc, ps, tape, o=orc.opts(counted=1), kcap=512)
+    for mode in (1, 2):
+        ch = pb.chain(m=m_aux, max_clusters=200)
+        ch.scan_spec(mode)
+        ch.set_state(K, c, cen, sig)
+        ch.set_pool(pc, ps)
+        ch.neal8_scan(tape)
+        got = ch.snapshot()
+        st = ch.stats()
+        sp = ch.scan_spec(mode)
+        ch.close()
+        assert got["K"] == ref["K"] and np.array_equal(got["c_i"], ref["c"]), mode
+        assert np.array_equal(got["centers"], ref["center"]) and np.array_equal(got["sigmas"], ref["sigma"]), mode
+        assert sp["mismatches"] == 0
+        assert st["scan_events"] > 200
+    if gamma > 50.0:
+        assert st["births"] > 0
