@@ -1467,6 +1467,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             // differ from the speculated one they were made with
             bool bounds_valid = false;
             double dmb = 0.0, dpb = 0.0, usedb = 0.0, Bg = 0.0, gs = 0.0;
+            // outcome of this lane's recheck under the current bounds: gs covers every later state of the group, so a row
+            // is re-examined once per set of bounds, not once per applied prefix
+            bool rechecked_l = false, recheck_ok_l = false;
             WALK_MARK();
             while (live && !reason) {
               const bool live_l = (live >> lane) & 1u;
@@ -1487,6 +1490,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               __syncwarp();
               double bound = 0.0, gsl = 0.0;
               dmb = dpb = usedb = 0.0;
+              rechecked_l = recheck_ok_l = false;
               if (pl) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -1528,8 +1532,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               }
               const double Dg = fmax(D, Bg);
               WALK_TICK(0);
-              bool ok_l = tau_l > Dg;
-              unsigned need = __ballot_sync(SMG_FULL, live_l && !ok_l && (code_l == EVT_NONE || plain_l));
+              bool ok_l = tau_l > Dg || recheck_ok_l;
+              unsigned need = __ballot_sync(SMG_FULL, live_l && !ok_l && !rechecked_l && (code_l == EVT_NONE || plain_l));
               if (need) {
                 if (__popc(need) >= 3) {
                   // one row per warp, the whole CTA: the other warps wait for this in scan_walk_barrier()
@@ -1548,14 +1552,20 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                       atomicOr(&S.wk_ok, 1u << src);
                   }
                   scan_walk_barrier();
-                  if ((need >> lane) & 1u) ok_l = (S.wk_ok >> lane) & 1u;
+                  if ((need >> lane) & 1u) {
+                    rechecked_l = true;
+                    ok_l = recheck_ok_l = (S.wk_ok >> lane) & 1u;
+                  }
                 } else {
                   while (need) {
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const int j = g * 32 + src;
                     const bool ok = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], gs, K, m, lane);
-                    if (lane == src) ok_l = ok;
+                    if (lane == src) {
+                      rechecked_l = true;
+                      ok_l = recheck_ok_l = ok;
+                    }
                     if (!ok) break;  // the prefix ends here anyway
                   }
                 }
