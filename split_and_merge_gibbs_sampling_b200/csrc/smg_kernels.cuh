@@ -654,6 +654,7 @@ struct ScanState {
   int wk_cmd, wk_j0, wk_K;      // job of the walk for the other warps: re-examine the rows `wk_need` of group wk_j0 / 32 (cmd 1: the walk is over)
   unsigned wk_need, wk_ok;
   double wk_gs;
+  double gsk[64];  // by label: slack of the cluster's log-counts over the rest of the current group of the walk
   double fac[64], facm1[64];  // by label: e^(drift of log n_k) and e^(drift of log(n_k - 1)) since the base (entries >= K stay 1)
 };
 
@@ -997,40 +998,47 @@ __device__ __forceinline__ void scan_apply_move(const ScanArgs& A, ScanState& S,
 }
 
 // Speculative evaluation, second line of defence (see the scan kernel): does the draw of a speculated row still return the
-// entry `sel` it was speculated to, under the current counts and with every weight free to move by another factor within
-// e^-gs .. e^gs?  The weights of the base (w[0 .. 63], relative to the largest) are rescaled by the drift factors of the
-// counts (own cluster: of n - 1); with G the sum of the weights above w_sel and T = u * sum(w):
-//   no weight within (1 +- 2 gs) of w_sel,   G e^gs < T e^-gs,   T e^gs <= (G + w_sel) e^-gs
+// entry `sel` it was speculated to, under the current counts and with the weight of every cluster free to move by another
+// factor within e^-s_k .. e^s_k (s_k = S.gsk[k], the slack of the clusters the rest of the group touches; `slack` false:
+// under the current counts exactly)?  The weights of the base (w[0 .. 63], relative to the largest) are rescaled by the
+// drift factors of the counts (own cluster: of n - 1); with G the sum of the weights above w_sel and T = u * sum(w):
+//   no weight whose interval meets w_sel's,   max G < min T,   max T <= min (G + w_sel)
 // (5e-7 relative on top: the cached weights are single precision, 6e-8 each; the exact evaluation decides whatever is
 // closer than that).  One warp per row, two entries per lane; the answer is uniform over the warp.
-__device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const float* w, int sel, int own, double u, double gs,
+__device__ __forceinline__ bool scan_recheck_row(const ScanState& S, const float* w, int sel, int own, double u, bool slack,
                                                  int K, int m, int lane) {
-  if (sel < 0 || !(gs <= 0.01) || S.cnt[own] < 2) return false;
+  if (sel < 0 || S.cnt[own] < 2) return false;
   const int oe = S.s2l[own], ne = K + m;
-  double wf[2];
+  // every weight within [w (1 - s - 5e-7), w (1 + s + s^2 + 5e-7)], s the slack of its cluster (e^s <= 1 + s + s^2 for s <= 1)
+  double wlo[2], whi[2];
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     const int e = q * 32 + lane;
-    wf[q] = e < ne ? (double)w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
+    const double wf = e < ne ? (double)w[e] * (e == oe ? S.facm1[e] : (e < K ? S.fac[e] : 1.0)) : 0.0;
+    const double sk = (slack && e < K) ? S.gsk[e] : 0.0;
+    wlo[q] = wf * (1.0 - sk - 5e-7);
+    whi[q] = (sk <= 0.5) ? wf * (1.0 + sk * (1.0 + sk) + 5e-7) : CUDART_NAN;
   }
-  const double ws = shfl_d((sel >> 5) ? wf[1] : wf[0], sel & 31);
-  const double hib = ws * (1.0 + 2.02 * gs + 1e-6), lob = ws * (1.0 - 2.0 * gs - 1e-6);
-  double Gl = 0.0;
+  const double slo = shfl_d((sel >> 5) ? wlo[1] : wlo[0], sel & 31), shi = shfl_d((sel >> 5) ? whi[1] : whi[0], sel & 31);
+  double Glo = 0.0, Ghi = 0.0;
   bool amb = false;
 #pragma unroll
   for (int q = 0; q < 2; q++) {
     const int e = q * 32 + lane;
     if (e < ne && e != sel) {
-      if (wf[q] > hib)
-        Gl += wf[q];
-      else if (wf[q] >= lob)
+      if (wlo[q] > shi) {  // certainly before sel in the descending order
+        Glo += wlo[q];
+        Ghi += whi[q];
+      } else if (!(whi[q] < slo)) {  // not certainly after it (or not a number): may change place
         amb = true;
+      }
     }
   }
-  const double sum = warp_sum(wf[0] + wf[1]), G = warp_sum(Gl);
+  const double Tlo = u * warp_sum(wlo[0] + wlo[1]), Thi = u * warp_sum(whi[0] + whi[1]);
+  Glo = warp_sum(Glo);
+  Ghi = warp_sum(Ghi);
   if (__any_sync(SMG_FULL, amb)) return false;
-  const double T = u * sum, up = 1.0 + 1.01 * gs + 5e-7, dn = 1.0 - gs - 5e-7;
-  return ws > 0.0 && (G == 0.0 || T * dn > G * up) && (T * up <= (G + ws) * dn);
+  return slo > 0.0 && (Ghi == 0.0 || Tlo > Ghi) && (Thi <= Glo + slo);
 }
 __device__ __forceinline__ void scan_walk_barrier() { asm volatile("bar.sync 1, 1024;" ::: "memory"); }  // all warps of the scan CTA
 
@@ -1491,6 +1499,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               double bound = 0.0, gsl = 0.0;
               dmb = dpb = usedb = 0.0;
               rechecked_l = recheck_ok_l = false;
+              S.gsk[lane] = S.gsk[lane + 32] = 0.0;
+              __syncwarp();
               if (pl) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -1498,6 +1508,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                   const int c = S.cnt[sl], a = S.arr[e], d = S.dep[e], lo = c - d;
                   if (lo < 2) {
                     bound = gsl = CUDART_INF;  // a cluster could get down to one member: one row at a time
+                    S.gsk[e] = CUDART_INF;
                   } else {
                     // (upper bounds: single-precision reciprocals rounded up, times 1 + 2^-20 for the products)
                     const float fa = (float)a * 1.000001f, fd = (float)d * 1.000001f;
@@ -1508,7 +1519,9 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                     // slack between ANY two states of the rest of the group (the rechecks rescale from the state they
                     // meet, not from the one the bounds were made in): at any time the count is >= lo = c - d, at most a
                     // arrivals and d departures are still to come, so |log n' - log n_t| <= max(a, d) / lo (n - 1: lo - 1)
-                    gsl = fmax(gsl, (double)(fmaxf(fa, fd) * __frcp_ru((float)(lo - 1))));
+                    const double sk = (double)(fmaxf(fa, fd) * __frcp_ru((float)(lo - 1)));
+                    S.gsk[e] = sk;  // (every lane that touches label e writes the same value)
+                    gsl = fmax(gsl, sk);
                     // what the block's screen is told (upper bounds of the running maxima the one-at-a-time updates keep)
                     if (sl < K0) {
                       if (S.lcm1_0[sl] > -CUDART_INF) dmb = fmax(dmb, S.lcm1_0[sl] - S.logcm1[sl] + dn1);
@@ -1548,7 +1561,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                   {
                     const int src = __ffs(need) - 1;  // warp 0 takes the first one
                     const int j = g * 32 + src;
-                    if (scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], gs, K, m, lane) && lane == 0)
+                    if (scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], true, K, m, lane) && lane == 0)
                       atomicOr(&S.wk_ok, 1u << src);
                   }
                   scan_walk_barrier();
@@ -1561,7 +1574,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                     const int src = __ffs(need) - 1;
                     need &= need - 1;
                     const int j = g * 32 + src;
-                    const bool ok = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], gs, K, m, lane);
+                    const bool ok = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], true, K, m, lane);
                     if (lane == src) {
                       rechecked_l = true;
                       ok_l = recheck_ok_l = ok;
@@ -1641,7 +1654,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
               bool robust = tau > D;
               if (!robust) {
                 const int j = g * 32 + L;
-                robust = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], 0.0, K, m, lane);
+                robust = scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], false, K, m, lane);
               }
               const int r = __shfl_sync(SMG_FULL, row_l, L);
               const int own = __shfl_sync(SMG_FULL, own_l, L);
@@ -1732,7 +1745,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             if (warp < __popc(need)) {
               const int src = __fns(need, 0, warp + 1);  // the (warp+1)-th row of the job
               const int j = S.wk_j0 + src;
-              if (scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], S.wk_gs, K, m, lane) && lane == 0)
+              if (scan_recheck_row(S, spec_w + j * SCAN_SPEC_WSTRIDE, (int)spec_sel[j], (int)spec_own[j], spec_u[j], true, K, m, lane) && lane == 0)
                 atomicOr(&S.wk_ok, 1u << src);
             }
             scan_walk_barrier();
