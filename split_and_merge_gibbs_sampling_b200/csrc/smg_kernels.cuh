@@ -651,9 +651,8 @@ struct ScanState {
   int spec_keep, walk_done, walk_start, walk_reason;
   int arr[64], dep[64];  // arrivals / departures by label among the moves of a group of the walk (zero between uses)
   int sp_i0, sp_nb, sp_K;       // a speculation shared with the other CTAs of the cluster: first row of the block, rows, clusters
-  int wk_cmd, wk_j0, wk_K;      // job of the walk for the other warps: re-examine the rows `wk_need` of group wk_j0 / 32 (cmd 1: the walk is over)
+  int wk_cmd, wk_j0;            // job of the walk for the other warps: re-examine the rows `wk_need` of group wk_j0 / 32 (cmd 1: the walk is over)
   unsigned wk_need, wk_ok;
-  double wk_gs;
   double gsk[64];  // by label: slack of the cluster's log-counts over the rest of the current group of the walk
   double fac[64], facm1[64];  // by label: e^(drift of log n_k) and e^(drift of log(n_k - 1)) since the base (entries >= K stay 1)
 };
@@ -1474,8 +1473,8 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
             // bounds of the group (below); they hold until a row is decided by an exact evaluation, whose outcome may
             // differ from the speculated one they were made with
             bool bounds_valid = false;
-            double dmb = 0.0, dpb = 0.0, usedb = 0.0, Bg = 0.0, gs = 0.0;
-            // outcome of this lane's recheck under the current bounds: gs covers every later state of the group, so a row
+            double dmb = 0.0, dpb = 0.0, usedb = 0.0, Bg = 0.0;
+            // outcome of this lane's recheck under the current bounds: the slacks cover every later state of the group, so a row
             // is re-examined once per set of bounds, not once per applied prefix
             bool rechecked_l = false, recheck_ok_l = false;
             WALK_MARK();
@@ -1496,7 +1495,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 atomicAdd(&S.dep[oe_l], 1);
               }
               __syncwarp();
-              double bound = 0.0, gsl = 0.0;
+              double bound = 0.0;
               dmb = dpb = usedb = 0.0;
               rechecked_l = recheck_ok_l = false;
               S.gsk[lane] = S.gsk[lane + 32] = 0.0;
@@ -1507,7 +1506,7 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                   const int sl = h ? own_l : ns_l, e = h ? oe_l : code_l;
                   const int c = S.cnt[sl], a = S.arr[e], d = S.dep[e], lo = c - d;
                   if (lo < 2) {
-                    bound = gsl = CUDART_INF;  // a cluster could get down to one member: one row at a time
+                    bound = CUDART_INF;  // a cluster could get down to one member: one row at a time
                     S.gsk[e] = CUDART_INF;
                   } else {
                     // (upper bounds: single-precision reciprocals rounded up, times 1 + 2^-20 for the products)
@@ -1521,7 +1520,6 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                     // arrivals and d departures are still to come, so |log n' - log n_t| <= max(a, d) / lo (n - 1: lo - 1)
                     const double sk = (double)(fmaxf(fa, fd) * __frcp_ru((float)(lo - 1)));
                     S.gsk[e] = sk;  // (every lane that touches label e writes the same value)
-                    gsl = fmax(gsl, sk);
                     // what the block's screen is told (upper bounds of the running maxima the one-at-a-time updates keep)
                     if (sl < K0) {
                       if (S.lcm1_0[sl] > -CUDART_INF) dmb = fmax(dmb, S.lcm1_0[sl] - S.logcm1[sl] + dn1);
@@ -1540,7 +1538,6 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                 S.dep[oe_l] = 0;
               }
               Bg = key_to_double(warp_max_key(sort_key(bound)));
-              gs = key_to_double(warp_max_key(sort_key(gsl)));
               bounds_valid = true;
               }
               const double Dg = fmax(D, Bg);
@@ -1555,7 +1552,6 @@ __global__ void __cluster_dims__(SCAN_CLUSTER, 1, 1) __launch_bounds__(SMG_SCAN_
                     S.wk_j0 = g * 32;
                     S.wk_need = need;
                     S.wk_ok = 0u;
-                    S.wk_gs = gs;
                   }
                   scan_walk_barrier();
                   {
